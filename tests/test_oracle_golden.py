@@ -1,0 +1,66 @@
+"""CPU: pin the C restatement (oracle/kmer_oracle.c) against the fixtures generated from the compiled
+reference (tests/golden/make_golden.py) and, when oracle/_ref is present, against the reference live."""
+import numpy as np
+import pytest
+
+from conftest import assert_results_equal, golden_cases, load_golden
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_oracle_matches_golden(oracle_mod, name):
+    g = load_golden(name)
+    with oracle_mod.Oracle(g["text"], int(g["sigma"]), g["ks"].tolist()) as o:
+        got = o.search(g["q"], g["q_off"])
+        # the UB mask is a property of the algorithm, so the restatement must reproduce it too
+        assert np.array_equal(o.last_ub, g["ub"].astype(bool))
+        assert_results_equal(got, (g["r_off"], g["r_pos"], g["r_status"]), skip=g["ub"].astype(bool), label=name)
+        flat, o_ = g["scheme_flat"], 0
+        for m, ln, multi in zip(g["scheme_m"], g["scheme_len"], g["scheme_multi"]):
+            ks, use_multi = o.scheme(int(m))
+            assert ks == flat[o_:o_ + ln].tolist() and use_multi == bool(multi), (name, int(m))
+            o_ += int(ln)
+
+
+def test_ub_queries_only_differ_by_reference_out_of_range():
+    """On the UB-flagged queries the compiled reference either agrees with the 'not equal' evaluation
+    or dies with std::out_of_range (status 2) -- never a silent different answer in the fixtures."""
+    n_diff = 0
+    for name in golden_cases():
+        g = load_golden(name)
+        n_diff += int((g["r_status"] > 1).sum())
+        assert np.all(g["ub"][g["r_status"] > 1] == 1), name
+    assert n_diff >= 1  # the fixtures do contain such a case (low_dna4_k5)
+
+
+def test_fast_pow_and_choose_best_k(oracle_mod):
+    s = load_golden("scalars")
+    for bi, b in enumerate(s["bases"]):
+        for ei, e in enumerate(s["exps"]):
+            assert oracle_mod.Oracle.fast_pow(int(b), int(e)) == int(s["fast_pow"][bi, ei]), (b, e)
+    o_ = 0
+    for ln, want in zip(s["cbk_intervals"], s["cbk_out"]):
+        iv = s["cbk_flat"][o_:o_ + ln]
+        o_ += int(ln)
+        assert oracle_mod.Oracle.choose_best_k(iv, 4) == want.tolist()
+
+
+def test_truth_scan_small(oracle_mod):
+    text = np.array([0, 1, 0, 1, 0, 2, 0, 1], dtype=np.uint8)
+    q = np.array([0, 1, 0, 1, 0, 3], dtype=np.uint8)
+    off = np.array([0, 2, 5, 6], dtype=np.uint64)
+    o, p, _ = oracle_mod.Oracle.truth(text, q, off)
+    assert o.tolist() == [0, 3, 5, 5] and p.tolist() == [0, 2, 6, 0, 2]
+
+
+@pytest.mark.parametrize("sigma,ks,mmax", [(4, [6], 40), (4, [5, 7, 9, 11, 13], 60), (15, [5, 6, 7], 12),
+                                            (27, [3], 9), (5, [4], 14)])
+def test_oracle_matches_live_reference(oracle_mod, sigma, ks, mmax):
+    if not oracle_mod.have_reference():
+        pytest.skip("oracle/_ref not built on this box (needs /root/reference)")
+    from kmer_index_b200 import synth
+    text = synth.low_entropy_text(11, sigma=sigma)
+    q, off = synth.stress_queries(text, 1500, 1, mmax, sigma, 4242 + ks[0], low_sigma=2)
+    with oracle_mod.Oracle(text, sigma, ks) as o, oracle_mod.Reference(text, sigma, ks) as r:
+        got = o.search(q, off)
+        want = r.search(q, off)
+        assert_results_equal(got, want, skip=o.last_ub, label=f"sigma={sigma} ks={ks}")
