@@ -1,0 +1,180 @@
+/*
+ * kmer_b200.h -- C ABI of libkmer_b200.so, the B200 (sm_100a) build + batched-search engine behind the
+ * header-only C++ API in include/kmer_index.hpp.
+ *
+ * The reference (Clemapfel/kmer_index) is header-only C++ with no FFI; the boundary replaced here is the
+ * body of its templates. Each entry point names the reference interface it stands in for (file:line into
+ * the reference tree). Plain C types only: opaque handles, pointers and sizes. All functions return
+ * KMER_B200_OK (0) or a negative kmer_b200_status; kmer_b200_last_error() gives the message of the last
+ * failure on the calling thread. There is NO CPU fallback: without a CUDA device every entry point that
+ * computes returns KMER_B200_ERR_CUDA.
+ */
+#ifndef KMER_B200_H
+#define KMER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KMER_B200_ABI_VERSION 1
+
+typedef enum kmer_b200_status {
+    KMER_B200_OK = 0,
+    KMER_B200_ERR_INVALID_ARGUMENT = -1, /* null pointer, k out of range, sigma^k >= 2^32, n < k, ... */
+    KMER_B200_ERR_CUDA = -2,             /* any CUDA runtime failure (including "no device") */
+    KMER_B200_ERR_OUT_OF_MEMORY = -3,
+    KMER_B200_ERR_INVALID_RANK = -4,     /* a text/query symbol rank >= sigma */
+    KMER_B200_ERR_UNSUPPORTED = -5
+} kmer_b200_status;
+
+/* Per-query status, mirroring what the reference's search() does for that query. */
+typedef enum kmer_b200_query_status {
+    KMER_B200_QUERY_OK = 0,
+    /* the reference throws std::invalid_argument: "query size too low for specified k"
+       (kmer_index.hpp:119-122) or "query size exceed the maximum size" (kmer_index.hpp:507-509) */
+    KMER_B200_QUERY_THROW_INVALID_ARGUMENT = 1,
+    /* the reference's behaviour is undefined for this query (empty query: assert kmer_index.hpp:195;
+       length == 10000: out-of-bounds table read kmer_index.hpp:512); no hits are reported */
+    KMER_B200_QUERY_UNDEFINED = 2,
+    /* sharded index only: query longer than the shard's halo allows (see kmer_b200_config.halo) */
+    KMER_B200_QUERY_TOO_LONG_FOR_SHARD = 3
+} kmer_b200_query_status;
+
+/* Search semantics. REFERENCE_EXACT reproduces kmer_index.hpp:193-346 and :505-558 bit for bit,
+   including the two defects documented in DESIGN.md (later parts compared against the last part,
+   kmer_index.hpp:314; multi-k offsets not accumulated, kmer_index.hpp:526,535,544) and the throw
+   conditions. CORRECT returns the true occurrence set of every query and never throws for short rests. */
+typedef enum kmer_b200_mode {
+    KMER_B200_MODE_REFERENCE_EXACT = 0,
+    KMER_B200_MODE_CORRECT = 1
+} kmer_b200_mode;
+
+typedef struct kmer_b200_config {
+    int32_t device;        /* CUDA device ordinal; -1 = the calling thread's current device */
+    uint32_t mode;         /* default kmer_b200_mode for searches */
+    void *stream;          /* cudaStream_t all work is enqueued on; NULL = a private non-blocking stream */
+    /* Position-range sharding (multi-GPU). `ranks` passed to create is the slice
+       [shard_begin, shard_begin + n) of a text of n_total symbols; the last `halo` symbols of the slice
+       belong to the next shard and are only read to complete matches that start in this shard.
+       Single-GPU: shard_begin = 0, n_total = 0 (meaning n), halo = 0. */
+    uint64_t shard_begin;
+    uint64_t n_total;
+    uint32_t halo;
+    uint32_t directory_bits; /* 0 = automatic; otherwise log2 of the directory size cap per element */
+    uint32_t profile;        /* 1 = bracket every kernel launch with CUDA events (kmer_b200_stats) */
+    uint32_t reserved;
+} kmer_b200_config;
+
+typedef struct kmer_b200_index kmer_b200_index;
+typedef struct kmer_b200_result kmer_b200_result;
+
+void kmer_b200_config_default(kmer_b200_config *cfg);
+int kmer_b200_abi_version(void);
+const char *kmer_b200_last_error(void);
+
+/* ---- build: replaces kmer::kmer_index<alphabet, position_t, ks...>::kmer_index(text, n_threads)
+   (kmer_index.hpp:480-496), i.e. kmer_index_element<k>::create for every k (kmer_index.hpp:154-179)
+   plus choose_search_scheme (kmer_index.hpp:407-476).
+   ranks: n symbol ranks, one byte each, in [0, sigma) -- the memory layout of std::vector<alphabet_t>
+   for seqan3 alphabets. ks: the template parameter pack ks... in template order. The caller's buffer is
+   not referenced after the call returns. */
+int kmer_b200_create(const uint8_t *ranks, uint64_t n, uint32_t sigma, const uint32_t *ks, uint32_t n_ks,
+                     const kmer_b200_config *cfg, kmer_b200_index **out);
+
+/* Same, with `d_ranks` already resident in device memory (used to time the build without the H2D copy). */
+int kmer_b200_create_from_device(const uint8_t *d_ranks, uint64_t n, uint32_t sigma, const uint32_t *ks,
+                                 uint32_t n_ks, const kmer_b200_config *cfg, kmer_b200_index **out);
+
+void kmer_b200_destroy(kmer_b200_index *index);
+
+/* ---- search: replaces kmer_index::search(std::vector<alphabet_t>&) (kmer_index.hpp:505-558) followed
+   by kmer_index_result::to_vector() (kmer_index_result.hpp:244-260), for a batch of Q queries.
+   q_ranks: all queries' ranks back to back; q_offsets[Q+1]: start of each query in q_ranks.
+   The result holds, in host memory, offsets[Q+1], the per-query ascending hit positions back to back,
+   and status[Q] (kmer_b200_query_status). mode: a kmer_b200_mode, or UINT32_MAX for the index default. */
+int kmer_b200_search_batch(kmer_b200_index *index, const uint8_t *q_ranks, const uint64_t *q_offsets, uint64_t n_queries,
+                           uint32_t mode, kmer_b200_result **out);
+
+/* Same with queries resident in device memory and the result left in device memory.
+   max_query_len must be >= the longest query in the batch. */
+int kmer_b200_search_batch_device(kmer_b200_index *index, const uint8_t *d_q_ranks, const uint64_t *d_q_offsets,
+                                  uint64_t n_queries, uint64_t max_query_len, uint32_t mode, kmer_b200_result **out);
+
+/* Count-only variant of the device search (no position list is materialised); the reference analogue is
+   timing search() without to_vector(), as its benchmarks do (benchmarks/just_k/main.cpp:58-62). */
+int kmer_b200_count_batch_device(kmer_b200_index *index, const uint8_t *d_q_ranks, const uint64_t *d_q_offsets,
+                                 uint64_t n_queries, uint64_t max_query_len, uint32_t mode, kmer_b200_result **out);
+
+uint64_t kmer_b200_result_n_queries(const kmer_b200_result *r);
+uint64_t kmer_b200_result_n_positions(const kmer_b200_result *r);
+int kmer_b200_result_on_device(const kmer_b200_result *r);
+const uint64_t *kmer_b200_result_offsets(const kmer_b200_result *r);   /* [Q+1] */
+const uint32_t *kmer_b200_result_positions(const kmer_b200_result *r); /* [offsets[Q]], NULL if count-only */
+const uint8_t *kmer_b200_result_status(const kmer_b200_result *r);     /* [Q] */
+void kmer_b200_result_free(kmer_b200_result *r);
+
+/* ---- sharded (multi-GPU) search, two phases around one cross-rank exchange.
+   Phase A fills d_present[Q] with one bit per indexed part of the query (bit j = part j occurs in this
+   shard); the caller ORs the masks of all shards (NCCL) and passes the result to phase B
+   (kmer_b200_search_batch_device_global), which then reproduces the reference's whole-text
+   early-return / throw decisions (kmer_index.hpp:216-227, :119-122) on every shard. */
+int kmer_b200_presence_batch_device(kmer_b200_index *index, const uint8_t *d_q_ranks, const uint64_t *d_q_offsets,
+                                    uint64_t n_queries, uint64_t max_query_len, uint32_t mode, uint64_t *d_present);
+int kmer_b200_search_batch_device_global(kmer_b200_index *index, const uint8_t *d_q_ranks, const uint64_t *d_q_offsets,
+                                         uint64_t n_queries, uint64_t max_query_len, uint32_t mode,
+                                         const uint64_t *d_present_global, kmer_b200_result **out);
+
+/* ---- introspection (parity tests and roofline accounting) */
+typedef struct kmer_b200_element_info {
+    uint32_t k;
+    uint32_t key_bits;        /* ceil(log2(sigma^k)) */
+    uint32_t directory_shift; /* bucket directory is indexed by hash >> shift */
+    uint32_t sort_passes;
+    uint64_t n_kmers;         /* n - k + 1 */
+    uint64_t directory_entries;
+    uint64_t device_bytes;
+} kmer_b200_element_info;
+
+uint32_t kmer_b200_n_elements(const kmer_b200_index *index);
+int kmer_b200_element_info_get(const kmer_b200_index *index, uint32_t element, kmer_b200_element_info *out);
+/* Copy element's position array (all k-mer start positions stably sorted by hash: the concatenation of
+   the reference's _data buckets in ascending hash order, kmer_index.hpp:52,165) to host memory. */
+int kmer_b200_element_positions(kmer_b200_index *index, uint32_t element, uint32_t *out, uint64_t cap);
+/* Copy the sorted hash array (one per position above) to host memory. */
+int kmer_b200_element_hashes(kmer_b200_index *index, uint32_t element, uint32_t *out, uint64_t cap);
+/* Row m of the scheme table (_optimal_nk_sum[m], _use_multi_search_scheme[m]; kmer_index.hpp:404-476).
+   Returns the number of summands and writes up to cap of them. */
+uint64_t kmer_b200_scheme(const kmer_b200_index *index, uint64_t m, uint32_t *out_ks, uint64_t cap, int *use_multi);
+
+/* Per-kernel accounting since the last reset: launches, device time (CUDA events on the launching
+   stream; only when cfg.profile = 1) and the algorithmic bytes the kernel must move. */
+typedef struct kmer_b200_kernel_stat {
+    const char *name;
+    uint64_t launches;
+    double device_ms;
+    double algorithmic_bytes;
+} kmer_b200_kernel_stat;
+
+uint32_t kmer_b200_stats(kmer_b200_index *index, kmer_b200_kernel_stat *out, uint32_t cap);
+void kmer_b200_stats_reset(kmer_b200_index *index);
+uint64_t kmer_b200_device_bytes(const kmer_b200_index *index);
+
+/* ---- scalar helpers kept from the reference API */
+/* kmer::detail::fast_pow (fast_pow.hpp:46-93): base^exp mod 2^64, 0 when exp >= 63 and base != 1 */
+uint64_t kmer_b200_fast_pow(uint64_t base, uint8_t exp);
+/* the k-mer hash sum_i rank_i * sigma^(k-1-i) (kmer_index.hpp:56-73) */
+uint64_t kmer_b200_hash(const uint8_t *ranks, uint32_t k, uint32_t sigma);
+/* choose_best_k (choose_best_k.hpp:12-60); ties keep the candidate order (stable) */
+uint64_t kmer_b200_choose_best_k(const uint64_t *query_lengths, uint64_t n_lengths, uint64_t n_k, uint64_t *out_ks);
+
+/* ---- synthetic inputs on the device (bench.py): counter-based SplitMix64, identical to
+   kmer_index_b200/synth.py */
+int kmer_b200_synth_ranks_device(uint8_t *d_out, uint64_t n, uint64_t start, uint32_t sigma, uint64_t seed, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMER_B200_H */

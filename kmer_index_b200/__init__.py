@@ -1,0 +1,191 @@
+"""kmer_index_b200: B200-native k-mer index (build + batched search) behind the reference's API.
+
+This package is the thin Python host layer over libkmer_b200.so (hand-written sm_100a kernels behind
+the C ABI in include/kmer_b200.h). It mirrors kmer::kmer_index / make_kmer_index of the reference
+(kmer_index.hpp:350-579): build from a text of symbol ranks, ``search`` returns sorted positions.
+There is no CPU fallback: without the CUDA library every operation raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from . import _capi
+from ._capi import (MODE_CORRECT, MODE_DEFAULT, MODE_REFERENCE_EXACT, QUERY_OK, QUERY_THROW_INVALID_ARGUMENT,
+                    QUERY_TOO_LONG_FOR_SHARD, QUERY_UNDEFINED, KmerB200Error)
+
+__all__ = ["KmerIndex", "make_kmer_index", "BatchResult", "fast_pow", "kmer_hash", "choose_best_k",
+           "MODE_REFERENCE_EXACT", "MODE_CORRECT", "KmerB200Error", "ALPHABETS"]
+
+# alphabet sizes of the seqan3 alphabets the reference is used with
+ALPHABETS = {"dna4": 4, "dna5": 5, "dna15": 15, "aa27": 27}
+
+
+def fast_pow(base: int, exp: int) -> int:
+    """kmer::detail::fast_pow (fast_pow.hpp:46-93)."""
+    return int(_capi.lib().kmer_b200_fast_pow(base, exp))
+
+
+def kmer_hash(ranks, sigma: int) -> int:
+    """The k-mer hash of `ranks` (kmer_index.hpp:56-73)."""
+    r = np.ascontiguousarray(np.asarray(ranks, dtype=np.uint8))
+    return int(_capi.lib().kmer_b200_hash(r.ctypes.data_as(_capi.u8p), r.size, sigma))
+
+
+def choose_best_k(query_lengths: Iterable[int], n_k: int = 4) -> list[int]:
+    """choose_best_k (choose_best_k.hpp:12-60)."""
+    a = np.ascontiguousarray(np.asarray(list(query_lengths), dtype=np.uint64))
+    out = np.zeros(16, dtype=np.uint64)
+    n = _capi.lib().kmer_b200_choose_best_k(a.ctypes.data_as(_capi.u64p), a.size, n_k, out.ctypes.data_as(_capi.u64p))
+    return [int(x) for x in out[:n]]
+
+
+class BatchResult:
+    """CSR result of a batch: offsets[Q+1], positions (ascending per query), status[Q]."""
+
+    def __init__(self, offsets: np.ndarray, positions: np.ndarray, status: np.ndarray):
+        self.offsets = offsets
+        self.positions = positions
+        self.status = status
+
+    def __len__(self) -> int:
+        return int(self.status.size)
+
+    def to_vector(self, i: int) -> np.ndarray:
+        """kmer_index_result::to_vector() of query i (kmer_index_result.hpp:244-260)."""
+        if self.status[i] == QUERY_THROW_INVALID_ARGUMENT:
+            raise ValueError("the reference throws std::invalid_argument for this query")
+        return self.positions[int(self.offsets[i]):int(self.offsets[i + 1])]
+
+    def as_tuple(self):
+        return self.offsets, self.positions, self.status
+
+
+class KmerIndex:
+    """kmer::kmer_index<alphabet, uint32_t, ks...> (kmer_index.hpp:350-566) on one B200."""
+
+    def __init__(self, text, sigma: int, ks: Sequence[int], *, mode: int = MODE_REFERENCE_EXACT, device: int = -1,
+                 stream: int | None = None, profile: bool = False, shard_begin: int = 0, n_total: int = 0,
+                 halo: int = 0, directory_bits: int = 0, text_device_ptr: int | None = None, n: int | None = None):
+        L = _capi.lib()
+        self._L = L
+        self._h = C.c_void_p()
+        self.sigma = int(sigma)
+        self.ks = [int(k) for k in ks]
+        cfg = _capi.Config()
+        L.kmer_b200_config_default(C.byref(cfg))
+        cfg.device = device
+        cfg.mode = mode
+        cfg.stream = stream
+        cfg.profile = 1 if profile else 0
+        cfg.shard_begin = shard_begin
+        cfg.n_total = n_total
+        cfg.halo = halo
+        cfg.directory_bits = directory_bits
+        ks_a = np.asarray(self.ks, dtype=np.uint32)
+        if text_device_ptr is not None:
+            self.n = int(n)
+            _capi.check(L.kmer_b200_create_from_device(C.c_void_p(text_device_ptr), self.n, self.sigma,
+                                                       ks_a.ctypes.data_as(_capi.u32p), ks_a.size, C.byref(cfg),
+                                                       C.byref(self._h)))
+        else:
+            t = np.ascontiguousarray(np.asarray(text, dtype=np.uint8))
+            self.n = int(t.size)
+            _capi.check(L.kmer_b200_create(t.ctypes.data_as(_capi.u8p), t.size, self.sigma,
+                                           ks_a.ctypes.data_as(_capi.u32p), ks_a.size, C.byref(cfg), C.byref(self._h)))
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.kmer_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def handle(self):
+        return self._h
+
+    # -- search
+    def search_batch(self, q_ranks, q_offsets, mode: int = MODE_DEFAULT) -> BatchResult:
+        """Batch of queries in host memory -> host CSR result (kmer_index::search + to_vector per query)."""
+        L = self._L
+        q = np.ascontiguousarray(np.asarray(q_ranks, dtype=np.uint8))
+        off = np.ascontiguousarray(np.asarray(q_offsets, dtype=np.uint64))
+        Q = off.size - 1
+        r = C.c_void_p()
+        _capi.check(L.kmer_b200_search_batch(self._h, q.ctypes.data, off.ctypes.data, Q, mode, C.byref(r)))
+        try:
+            total = L.kmer_b200_result_n_positions(r)
+            offsets = np.ctypeslib.as_array(C.cast(L.kmer_b200_result_offsets(r), _capi.u64p), shape=(Q + 1,)).copy()
+            status = (np.ctypeslib.as_array(C.cast(L.kmer_b200_result_status(r), _capi.u8p), shape=(Q,)).copy()
+                      if Q else np.zeros(0, dtype=np.uint8))
+            positions = (np.ctypeslib.as_array(C.cast(L.kmer_b200_result_positions(r), _capi.u32p),
+                                               shape=(total,)).copy() if total else np.zeros(0, dtype=np.uint32))
+        finally:
+            L.kmer_b200_result_free(r)
+        return BatchResult(offsets, positions, status)
+
+    def search(self, query, mode: int = MODE_DEFAULT) -> np.ndarray:
+        """kmer_index::search(query).to_vector() for one query; raises ValueError where the reference throws
+        std::invalid_argument (kmer_index.hpp:121,508). A batch of one: correct but latency-bound."""
+        q = np.ascontiguousarray(np.asarray(query, dtype=np.uint8))
+        res = self.search_batch(q, np.array([0, q.size], dtype=np.uint64), mode)
+        if res.status[0] == QUERY_THROW_INVALID_ARGUMENT:
+            if q.size > 10000:
+                raise ValueError("query size exceed the maximum size 10000 specified")
+            raise ValueError("query size too low for specified k")
+        if res.status[0] == QUERY_UNDEFINED:
+            raise ValueError("query length 0 or 10000: undefined in the reference")
+        return res.positions
+
+    # -- introspection
+    def element_info(self, e: int) -> _capi.ElementInfo:
+        info = _capi.ElementInfo()
+        _capi.check(self._L.kmer_b200_element_info_get(self._h, e, C.byref(info)))
+        return info
+
+    def element_arrays(self, e: int):
+        """(sorted hashes, positions stably sorted by hash) of element e."""
+        info = self.element_info(e)
+        h = np.zeros(info.n_kmers, dtype=np.uint32)
+        p = np.zeros(info.n_kmers, dtype=np.uint32)
+        _capi.check(self._L.kmer_b200_element_hashes(self._h, e, h.ctypes.data_as(_capi.u32p), h.size))
+        _capi.check(self._L.kmer_b200_element_positions(self._h, e, p.ctypes.data_as(_capi.u32p), p.size))
+        return h, p
+
+    def scheme(self, m: int):
+        out = np.zeros(4096, dtype=np.uint32)
+        multi = C.c_int(0)
+        n = self._L.kmer_b200_scheme(self._h, m, out.ctypes.data_as(_capi.u32p), out.size, C.byref(multi))
+        return [int(x) for x in out[:n]], bool(multi.value)
+
+    def stats(self) -> dict:
+        arr = (_capi.KernelStat * 32)()
+        n = self._L.kmer_b200_stats(self._h, arr, 32)
+        return {arr[i].name.decode(): {"launches": int(arr[i].launches), "device_ms": float(arr[i].device_ms),
+                                       "algorithmic_bytes": float(arr[i].algorithmic_bytes)} for i in range(n)}
+
+    def stats_reset(self):
+        self._L.kmer_b200_stats_reset(self._h)
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self._L.kmer_b200_device_bytes(self._h))
+
+
+def make_kmer_index(text, sigma: int, *ks: int, **kw) -> KmerIndex:
+    """kmer::make_kmer_index<ks...>(text) (kmer_index.hpp:569-579); position type is uint32."""
+    return KmerIndex(text, sigma, ks, **kw)

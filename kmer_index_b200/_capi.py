@@ -1,0 +1,113 @@
+"""ctypes binding of libkmer_b200.so (include/kmer_b200.h). No fallback: a missing library is an error."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libkmer_b200.so")
+
+u8p = C.POINTER(C.c_uint8)
+u32p = C.POINTER(C.c_uint32)
+u64p = C.POINTER(C.c_uint64)
+
+OK = 0
+MODE_REFERENCE_EXACT = 0
+MODE_CORRECT = 1
+MODE_DEFAULT = 0xFFFFFFFF
+
+QUERY_OK = 0
+QUERY_THROW_INVALID_ARGUMENT = 1
+QUERY_UNDEFINED = 2
+QUERY_TOO_LONG_FOR_SHARD = 3
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("mode", C.c_uint32), ("stream", C.c_void_p), ("shard_begin", C.c_uint64),
+                ("n_total", C.c_uint64), ("halo", C.c_uint32), ("directory_bits", C.c_uint32),
+                ("profile", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class ElementInfo(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("key_bits", C.c_uint32), ("directory_shift", C.c_uint32),
+                ("sort_passes", C.c_uint32), ("n_kmers", C.c_uint64), ("directory_entries", C.c_uint64),
+                ("device_bytes", C.c_uint64)]
+
+
+class KernelStat(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("launches", C.c_uint64), ("device_ms", C.c_double),
+                ("algorithmic_bytes", C.c_double)]
+
+
+# every symbol include/kmer_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "kmer_b200_config_default": (None, [C.POINTER(Config)]),
+    "kmer_b200_abi_version": (C.c_int, []),
+    "kmer_b200_last_error": (C.c_char_p, []),
+    "kmer_b200_create": (C.c_int, [u8p, C.c_uint64, C.c_uint32, u32p, C.c_uint32, C.POINTER(Config),
+                                   C.POINTER(C.c_void_p)]),
+    "kmer_b200_create_from_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, u32p, C.c_uint32,
+                                               C.POINTER(Config), C.POINTER(C.c_void_p)]),
+    "kmer_b200_destroy": (None, [C.c_void_p]),
+    "kmer_b200_search_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32,
+                                         C.POINTER(C.c_void_p)]),
+    "kmer_b200_search_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
+                                                C.c_uint32, C.POINTER(C.c_void_p)]),
+    "kmer_b200_count_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
+                                               C.c_uint32, C.POINTER(C.c_void_p)]),
+    "kmer_b200_result_n_queries": (C.c_uint64, [C.c_void_p]),
+    "kmer_b200_result_n_positions": (C.c_uint64, [C.c_void_p]),
+    "kmer_b200_result_on_device": (C.c_int, [C.c_void_p]),
+    "kmer_b200_result_offsets": (C.c_void_p, [C.c_void_p]),
+    "kmer_b200_result_positions": (C.c_void_p, [C.c_void_p]),
+    "kmer_b200_result_status": (C.c_void_p, [C.c_void_p]),
+    "kmer_b200_result_free": (None, [C.c_void_p]),
+    "kmer_b200_presence_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
+                                                  C.c_uint32, C.c_void_p]),
+    "kmer_b200_search_batch_device_global": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
+                                                       C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "kmer_b200_n_elements": (C.c_uint32, [C.c_void_p]),
+    "kmer_b200_element_info_get": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(ElementInfo)]),
+    "kmer_b200_element_positions": (C.c_int, [C.c_void_p, C.c_uint32, u32p, C.c_uint64]),
+    "kmer_b200_element_hashes": (C.c_int, [C.c_void_p, C.c_uint32, u32p, C.c_uint64]),
+    "kmer_b200_scheme": (C.c_uint64, [C.c_void_p, C.c_uint64, u32p, C.c_uint64, C.POINTER(C.c_int)]),
+    "kmer_b200_stats": (C.c_uint32, [C.c_void_p, C.POINTER(KernelStat), C.c_uint32]),
+    "kmer_b200_stats_reset": (None, [C.c_void_p]),
+    "kmer_b200_device_bytes": (C.c_uint64, [C.c_void_p]),
+    "kmer_b200_fast_pow": (C.c_uint64, [C.c_uint64, C.c_uint8]),
+    "kmer_b200_hash": (C.c_uint64, [u8p, C.c_uint32, C.c_uint32]),
+    "kmer_b200_choose_best_k": (C.c_uint64, [u64p, C.c_uint64, C.c_uint64, u64p]),
+    "kmer_b200_synth_ranks_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64,
+                                               C.c_void_p]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libkmer_b200.so. Raises (never falls back) when the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m kmer_index_b200.build` "
+                               "(there is no CPU or PyTorch fallback for the k-mer index)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        if L.kmer_b200_abi_version() != 1:
+            raise RuntimeError("libkmer_b200.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+class KmerB200Error(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"kmer_b200 error {code}: {message}")
+        self.code = code
+
+
+def check(code: int) -> None:
+    if code != OK:
+        raise KmerB200Error(code, (lib().kmer_b200_last_error() or b"").decode())

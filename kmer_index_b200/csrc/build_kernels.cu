@@ -1,0 +1,315 @@
+// Index construction kernels (sm_100a): the replacement for kmer_index_element::create
+// (kmer_index.hpp:154-179). Pipeline per element (one k):
+//
+//   pack_text            bytes (1 B/symbol) -> b-bit packed words                      [once per index]
+//   radix_hist<Text>     per-tile digit histogram, keys recomputed from the packed text (0.25 B/base)
+//   column_scan_*        exclusive scan of the [tile][digit] matrix in digit-major order
+//   radix_scatter<Text>  pass 0: hash + stable scatter of (hash, position); positions are generated
+//   radix_hist<Keys> / radix_scatter<Keys>   passes 1..d-1 over (hash, position) pairs
+//   directory_fill       run boundaries of the sorted hashes -> bucket directory (CSR offsets)
+//
+// Every pass is a streaming kernel bounded by HBM bandwidth; DESIGN.md lists the algorithmic bytes.
+#include "radix.cuh"
+#include "launch.h"
+
+namespace kb {
+
+// ------------------------------------------------------------------------------------------------
+// pack_text: one thread produces one 64-bit word from 64/bits input bytes.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_text_kernel(const uint8_t *__restrict__ ranks, uint64_t n, uint32_t bits,
+                                                        uint32_t sigma, uint64_t n_words, uint64_t *__restrict__ words,
+                                                        uint32_t *__restrict__ error_flag) {
+    const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    const uint32_t spw = 64 / bits;
+    const uint64_t s0 = w * spw;
+    uint64_t word = 0;
+    bool bad = false;
+    if (s0 + spw <= n && ((uintptr_t)(ranks + s0) & 7) == 0) {
+        // aligned fast path: 8 bytes at a time
+        const uint64_t *src = reinterpret_cast<const uint64_t *>(ranks + s0);
+        for (uint32_t j = 0; j < spw; j += 8) {
+            const uint64_t v = src[j >> 3];
+#pragma unroll
+            for (uint32_t b = 0; b < 8; ++b) {
+                const uint32_t r = (uint32_t)(v >> (8 * b)) & 0xFF;
+                bad |= r >= sigma;
+                word |= (uint64_t)r << (64 - bits * (j + b + 1));
+            }
+        }
+    } else {
+        for (uint32_t j = 0; j < spw && s0 + j < n; ++j) {
+            const uint32_t r = ranks[s0 + j];
+            bad |= r >= sigma;
+            word |= (uint64_t)r << (64 - bits * (j + 1));
+        }
+    }
+    words[w] = word;
+    if (bad) atomicOr(error_flag, 1u);
+}
+
+void launch_pack_text(const uint8_t *d_ranks, uint64_t n, uint32_t bits, uint32_t sigma, uint64_t n_words_total,
+                      uint64_t *d_words, uint32_t *d_error_flag, cudaStream_t stream) {
+    // n_words_total includes the two padding words; threads past the text write zeros
+    const uint64_t blocks = (n_words_total + 255) / 256;
+    pack_text_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_ranks, n, bits, sigma, n_words_total, d_words, d_error_flag);
+}
+
+// ------------------------------------------------------------------------------------------------
+// key sources
+// ------------------------------------------------------------------------------------------------
+struct TextSource {  // key(i) = hash of the k-mer starting at symbol i; value(i) = i
+    PackedText text;
+    uint32_t k;
+    __device__ __forceinline__ uint32_t key(uint64_t i) const {
+        return key_from_window(window64(text.words, i, text.bits), k, text.bits, text.sigma);
+    }
+    __device__ __forceinline__ uint32_t val(uint64_t i) const { return (uint32_t)i; }
+};
+
+struct PairSource {  // materialised (key, value) pairs; vals == nullptr: keys only
+    const uint32_t *keys;
+    const uint32_t *vals;
+    __device__ __forceinline__ uint32_t key(uint64_t i) const { return keys[i]; }
+    __device__ __forceinline__ uint32_t val(uint64_t i) const { return vals[i]; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// radix_hist: tile_hist[tile][digit] = number of elements of the tile with that digit
+// ------------------------------------------------------------------------------------------------
+template <typename Source>
+__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(Source src, uint64_t n, uint32_t shift, uint32_t mask,
+                                                                  uint32_t *__restrict__ tile_hist) {
+    __shared__ uint32_t hist[kRadix];
+    const int tid = threadIdx.x;
+    if (tid < kRadix) hist[tid] = 0;
+    __syncthreads();
+    const uint64_t tile_begin = (uint64_t)blockIdx.x * kSortTile;
+    const int lane = tid & 31;
+    const uint32_t lt_mask = (1u << lane) - 1;
+#pragma unroll 4
+    for (int r = 0; r < kSortItems; ++r) {
+        const uint64_t i = tile_begin + (uint64_t)r * kSortThreads + tid;
+        const uint32_t d = i < n ? ((src.key(i) >> shift) & mask) : kInvalidDigit;
+        // warp-aggregated shared-memory atomics: one atomic per distinct digit per warp
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+        if (d != kInvalidDigit && (peers & lt_mask) == 0) atomicAdd(&hist[d], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    if (tid < kRadix) tile_hist[(uint64_t)blockIdx.x * kRadix + tid] = hist[tid];
+}
+
+// ------------------------------------------------------------------------------------------------
+// column scan: in place, tile_hist[tile][digit] -> global exclusive offset of (digit, tile) in
+// digit-major order, i.e. base(d) + sum_{t' < tile} hist[t'][d].
+// Three small kernels over the [n_tiles][256] matrix, all with 256 threads = one per digit so that
+// every access is a coalesced 1 KB row.
+// ------------------------------------------------------------------------------------------------
+constexpr int kScanChunk = 64;  // tiles per chunk
+
+__global__ void __launch_bounds__(kRadix) column_sum_kernel(const uint32_t *__restrict__ tile_hist, uint32_t n_tiles,
+                                                            uint32_t *__restrict__ chunk_sums) {
+    const uint32_t t0 = blockIdx.x * kScanChunk;
+    const uint32_t t1 = min(t0 + kScanChunk, n_tiles);
+    uint32_t s = 0;
+#pragma unroll 8
+    for (uint32_t t = t0; t < t1; ++t) s += tile_hist[(uint64_t)t * kRadix + threadIdx.x];
+    chunk_sums[(uint64_t)blockIdx.x * kRadix + threadIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(kRadix) column_base_kernel(uint32_t *__restrict__ chunk_sums, uint32_t n_chunks) {
+    __shared__ uint32_t warp_sums[kRadix / 32];
+    const int d = threadIdx.x;
+    // digit totals
+    uint32_t total = 0;
+#pragma unroll 8
+    for (uint32_t c = 0; c < n_chunks; ++c) total += chunk_sums[(uint64_t)c * kRadix + d];
+    // exclusive scan of totals over digits
+    const int lane = d & 31, warp = d >> 5;
+    uint32_t incl = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    uint32_t base = incl - total;
+    for (int w = 0; w < warp; ++w) base += warp_sums[w];
+    // chunk_sums[c][d] <- base(d) + sum of earlier chunks
+    uint32_t run = base;
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+        const uint32_t v = chunk_sums[(uint64_t)c * kRadix + d];
+        chunk_sums[(uint64_t)c * kRadix + d] = run;
+        run += v;
+    }
+}
+
+__global__ void __launch_bounds__(kRadix) column_apply_kernel(uint32_t *__restrict__ tile_hist, uint32_t n_tiles,
+                                                              const uint32_t *__restrict__ chunk_sums) {
+    const uint32_t t0 = blockIdx.x * kScanChunk;
+    const uint32_t t1 = min(t0 + kScanChunk, n_tiles);
+    uint32_t run = chunk_sums[(uint64_t)blockIdx.x * kRadix + threadIdx.x];
+    uint32_t v[8];
+    for (uint32_t t = t0; t < t1; t += 8) {
+#pragma unroll
+        for (uint32_t j = 0; j < 8; ++j) v[j] = (t + j < t1) ? tile_hist[(uint64_t)(t + j) * kRadix + threadIdx.x] : 0;
+#pragma unroll
+        for (uint32_t j = 0; j < 8; ++j) {
+            if (t + j < t1) tile_hist[(uint64_t)(t + j) * kRadix + threadIdx.x] = run;
+            run += v[j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// radix_scatter: stable scatter of one tile. Elements are ranked in registers, staged in shared memory
+// in digit order and written out as per-digit runs (coalesced: a run of a digit is contiguous in the
+// destination).
+// ------------------------------------------------------------------------------------------------
+struct ScatterSmem {
+    RankSmem rank;
+    uint32_t delta[kRadix];
+    uint32_t keys[kSortTile];
+    uint32_t vals[kSortTile];
+};
+
+template <typename Source, bool kWriteKeys>
+__global__ void __launch_bounds__(kSortThreads, 1)
+    radix_scatter_kernel(Source src, uint64_t n, uint32_t shift, uint32_t mask, const uint32_t *__restrict__ tile_base,
+                         uint32_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ScatterSmem &sm = *reinterpret_cast<ScatterSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const uint64_t tile_begin = (uint64_t)blockIdx.x * kSortTile;
+    const uint32_t count = (uint32_t)min((uint64_t)kSortTile, n - tile_begin);
+
+    uint32_t key[kSortItems], val[kSortItems], digit[kSortItems], local_pos[kSortItems];
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const uint32_t e = (uint32_t)((warp * kSortItems + r) * 32 + lane);
+        if (e < count) {
+            key[r] = src.key(tile_begin + e);
+            val[r] = src.val(tile_begin + e);
+            digit[r] = (key[r] >> shift) & mask;
+        } else {
+            key[r] = 0;
+            val[r] = 0;
+            digit[r] = kInvalidDigit;
+        }
+    }
+    tile_rank(digit, local_pos, sm.rank);
+    if (tid < kRadix) sm.delta[tid] = tile_base[(uint64_t)blockIdx.x * kRadix + tid] - sm.rank.excl[tid];
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        if (digit[r] != kInvalidDigit) {
+            sm.keys[local_pos[r]] = key[r];
+            sm.vals[local_pos[r]] = val[r];
+        }
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (uint32_t j = tid; j < count; j += kSortThreads) {
+        const uint32_t kk = sm.keys[j];
+        const uint32_t dst = sm.delta[(kk >> shift) & mask] + j;  // mod 2^32; true destination < n < 2^32
+        if (kWriteKeys) out_keys[dst] = kk;
+        out_vals[dst] = sm.vals[j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// directory_fill: dir[j] = number of sorted keys with (key >> shift) < j, for j in [0, dir_entries).
+// Thread i owns the boundary between sorted elements i-1 and i and fills the directory entries that
+// fall into it; long runs (sparse key spaces) are filled by the whole warp, coalesced.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) directory_fill_kernel(const uint32_t *__restrict__ keys, uint64_t n_kmers,
+                                                             uint32_t shift, uint64_t dir_entries,
+                                                             uint32_t *__restrict__ dir) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // boundary index in [0, n_kmers]
+    const int lane = threadIdx.x & 31;
+    int64_t lo = 0, hi = -1;  // fill dir[lo..hi] = i
+    if (i <= n_kmers) {
+        const int64_t t_prev = (i == 0) ? -1 : (int64_t)(keys[i - 1] >> shift);
+        const int64_t t_cur = (i == n_kmers) ? (int64_t)dir_entries - 1 : (int64_t)(keys[i] >> shift);
+        lo = t_prev + 1;
+        hi = t_cur;
+    }
+    const int64_t len = hi - lo + 1;
+    const bool is_long = len >= 32;
+    if (!is_long) {
+        for (int64_t j = lo; j <= hi; ++j) dir[j] = (uint32_t)i;
+    }
+    uint32_t long_mask = __ballot_sync(0xFFFFFFFFu, is_long);
+    while (long_mask) {
+        const int src = __ffs(long_mask) - 1;
+        long_mask &= long_mask - 1;
+        const int64_t l0 = __shfl_sync(0xFFFFFFFFu, lo, src);
+        const int64_t h0 = __shfl_sync(0xFFFFFFFFu, hi, src);
+        const uint32_t v = (uint32_t)__shfl_sync(0xFFFFFFFFu, (unsigned long long)i, src);
+        for (int64_t j = l0 + lane; j <= h0; j += 32) dir[j] = v;
+    }
+}
+
+void launch_directory_fill(const uint32_t *d_keys, uint64_t n_kmers, uint32_t shift, uint64_t dir_entries, uint32_t *d_dir,
+                           cudaStream_t stream) {
+    const uint64_t blocks = (n_kmers + 1 + 255) / 256;
+    directory_fill_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_keys, n_kmers, shift, dir_entries, d_dir);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side pass drivers
+// ------------------------------------------------------------------------------------------------
+size_t scatter_smem_bytes() { return sizeof(ScatterSmem); }
+
+template <typename Source, bool kWriteKeys>
+static void configure_scatter() {
+    // per-device attribute; cheap enough to set on every launch
+    cudaFuncSetAttribute(radix_scatter_kernel<Source, kWriteKeys>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sizeof(ScatterSmem));
+}
+
+void launch_column_scan(uint32_t *d_tile_hist, uint32_t n_tiles, uint32_t *d_chunk_sums, cudaStream_t stream) {
+    const uint32_t n_chunks = (n_tiles + kScanChunk - 1) / kScanChunk;
+    column_sum_kernel<<<n_chunks, kRadix, 0, stream>>>(d_tile_hist, n_tiles, d_chunk_sums);
+    column_base_kernel<<<1, kRadix, 0, stream>>>(d_chunk_sums, n_chunks);
+    column_apply_kernel<<<n_chunks, kRadix, 0, stream>>>(d_tile_hist, n_tiles, d_chunk_sums);
+}
+
+void launch_hist_text(const PackedText &text, uint32_t k, uint64_t n_kmers, uint32_t shift, uint32_t mask,
+                      uint32_t *d_tile_hist, cudaStream_t stream) {
+    const uint32_t n_tiles = (uint32_t)((n_kmers + kSortTile - 1) / kSortTile);
+    TextSource src{text, k};
+    radix_hist_kernel<TextSource><<<n_tiles, kSortThreads, 0, stream>>>(src, n_kmers, shift, mask, d_tile_hist);
+}
+
+void launch_hist_pairs(const uint32_t *d_keys, uint64_t n, uint32_t shift, uint32_t mask, uint32_t *d_tile_hist,
+                       cudaStream_t stream) {
+    const uint32_t n_tiles = (uint32_t)((n + kSortTile - 1) / kSortTile);
+    PairSource src{d_keys, nullptr};
+    radix_hist_kernel<PairSource><<<n_tiles, kSortThreads, 0, stream>>>(src, n, shift, mask, d_tile_hist);
+}
+
+void launch_scatter_text(const PackedText &text, uint32_t k, uint64_t n_kmers, uint32_t shift, uint32_t mask,
+                         const uint32_t *d_tile_base, uint32_t *d_out_keys, uint32_t *d_out_vals, cudaStream_t stream) {
+    const uint32_t n_tiles = (uint32_t)((n_kmers + kSortTile - 1) / kSortTile);
+    TextSource src{text, k};
+    configure_scatter<TextSource, true>();
+    radix_scatter_kernel<TextSource, true>
+        <<<n_tiles, kSortThreads, sizeof(ScatterSmem), stream>>>(src, n_kmers, shift, mask, d_tile_base, d_out_keys, d_out_vals);
+}
+
+void launch_scatter_pairs(const uint32_t *d_keys, const uint32_t *d_vals, uint64_t n, uint32_t shift, uint32_t mask,
+                          const uint32_t *d_tile_base, uint32_t *d_out_keys, uint32_t *d_out_vals, cudaStream_t stream) {
+    const uint32_t n_tiles = (uint32_t)((n + kSortTile - 1) / kSortTile);
+    PairSource src{d_keys, d_vals};
+    configure_scatter<PairSource, true>();
+    radix_scatter_kernel<PairSource, true>
+        <<<n_tiles, kSortThreads, sizeof(ScatterSmem), stream>>>(src, n, shift, mask, d_tile_base, d_out_keys, d_out_vals);
+}
+
+uint32_t sort_tile_size() { return kSortTile; }
+uint32_t scan_chunk_tiles() { return kScanChunk; }
+
+}  // namespace kb

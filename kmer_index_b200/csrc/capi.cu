@@ -1,0 +1,984 @@
+// C ABI of libkmer_b200.so (include/kmer_b200.h): host-side orchestration of the build and search kernels.
+// No CPU fallback anywhere: every computing entry point needs a CUDA device.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "launch.h"
+#include "radix.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define KB_CUDA(expr)                                                                                      \
+    do {                                                                                                   \
+        cudaError_t _e = (expr);                                                                           \
+        if (_e != cudaSuccess) {                                                                           \
+            cudaGetLastError();                                                                            \
+            return fail(_e == cudaErrorMemoryAllocation ? KMER_B200_ERR_OUT_OF_MEMORY : KMER_B200_ERR_CUDA, \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));                               \
+        }                                                                                                  \
+    } while (0)
+
+#define KB_TRY(expr)           \
+    do {                       \
+        int _s = (expr);       \
+        if (_s != 0) return _s; \
+    } while (0)
+
+// kmer::detail::fast_pow, fast_pow.hpp:46-93
+uint64_t fast_pow(uint64_t base, uint8_t exp) {
+    if (exp >= 63) return base == 1 ? 1 : 0;  // the "overflow" row of highest_bit_set
+    uint64_t result = 1;
+    while (exp) {
+        if (exp & 1) result *= base;
+        exp >>= 1;
+        base *= base;
+    }
+    return result;
+}
+
+uint32_t bit_length(uint64_t v) {
+    uint32_t b = 0;
+    while (v) {
+        ++b;
+        v >>= 1;
+    }
+    return b;
+}
+
+enum KernelId : int {
+    K_PACK_TEXT = 0,
+    K_HIST_TEXT,
+    K_HIST_PAIRS,
+    K_COLUMN_SCAN,
+    K_SCATTER_TEXT,
+    K_SCATTER_PAIRS,
+    K_DIRECTORY_FILL,
+    K_SEARCH_COUNT,
+    K_SEARCH_WRITE,
+    K_SEARCH_PRESENCE,
+    K_OFFSETS_SCAN,
+    K_SEGMENT_SORT,
+    K_COUNT_
+};
+
+const char *const kKernelNames[K_COUNT_] = {
+    "pack_text",       "radix_hist_text", "radix_hist_pairs", "column_scan",     "radix_scatter_text", "radix_scatter_pairs",
+    "directory_fill",  "search_count",    "search_write",     "search_presence", "offsets_scan",       "segment_sort"};
+
+struct Profiler {
+    bool enabled = false;
+    cudaStream_t stream = nullptr;
+    uint64_t launches[K_COUNT_] = {};
+    double bytes[K_COUNT_] = {};
+    double ms[K_COUNT_] = {};
+    struct Pending {
+        int id;
+        cudaEvent_t a, b;
+    };
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> pool;
+
+    cudaEvent_t get_event() {
+        if (!pool.empty()) {
+            cudaEvent_t e = pool.back();
+            pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void begin(int id, double algorithmic_bytes, uint64_t n_launches = 1) {
+        launches[id] += n_launches;
+        bytes[id] += algorithmic_bytes;
+        if (!enabled) return;
+        Pending p{id, get_event(), get_event()};
+        cudaEventRecord(p.a, stream);
+        pending.push_back(p);
+    }
+    void end() {
+        if (!enabled) return;
+        cudaEventRecord(pending.back().b, stream);
+    }
+    void resolve() {
+        if (pending.empty()) return;
+        cudaStreamSynchronize(stream);
+        for (auto &p : pending) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, p.a, p.b) == cudaSuccess) ms[p.id] += t;
+            pool.push_back(p.a);
+            pool.push_back(p.b);
+        }
+        pending.clear();
+    }
+    void reset() {
+        resolve();
+        for (int i = 0; i < K_COUNT_; ++i) {
+            launches[i] = 0;
+            bytes[i] = 0;
+            ms[i] = 0;
+        }
+    }
+    ~Profiler() {
+        resolve();
+        for (auto e : pool) cudaEventDestroy(e);
+    }
+};
+
+struct HostElement {
+    kb::Element dev{};  // device pointers inside
+    uint32_t key_bits = 0;
+    uint32_t sort_passes = 0;
+    uint64_t bytes = 0;
+    uint32_t *d_dir = nullptr, *d_keys = nullptr, *d_pos = nullptr;
+};
+
+}  // namespace
+
+struct kmer_b200_index {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    kmer_b200_config cfg{};
+    uint64_t n = 0;
+    uint32_t sigma = 0, bits = 0;
+    std::vector<uint32_t> ks;
+    std::vector<HostElement> elems;
+    uint64_t *d_text = nullptr;
+    uint64_t text_words = 0;
+    // scheme tables (host copies for kmer_b200_scheme + device copies)
+    std::vector<uint32_t> sum_off;
+    std::vector<uint8_t> sum_elem, use_multi;
+    uint32_t *d_sum_off = nullptr;
+    uint8_t *d_sum_elem = nullptr, *d_use_multi = nullptr;
+    kb::DeviceIndex host_index{};
+    kb::DeviceIndex *d_index = nullptr;
+    uint32_t *d_flags = nullptr;     // u32[2]: error bits, unsorted-segment count
+    uint64_t *h_pinned = nullptr;    // small pinned scratch: [0] total hits, [1] flags
+    uint64_t device_bytes = 0;
+    Profiler prof;
+    std::mutex mu;  // serialises searches on one handle (they share the stream and the flag words)
+    // cache of pinned host buffers handed out to host results
+    std::vector<std::pair<void *, size_t>> pinned_cache;
+};
+
+struct kmer_b200_result {
+    kmer_b200_index *index = nullptr;
+    bool on_device = false;
+    uint64_t n_queries = 0, n_positions = 0;
+    uint64_t *offsets = nullptr;
+    uint32_t *positions = nullptr;
+    uint8_t *status = nullptr;
+    size_t cap_offsets = 0, cap_positions = 0, cap_status = 0;  // host buffers: byte capacities
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+int dev_alloc(kmer_b200_index *ix, T **p, uint64_t count, bool persistent) {
+    const size_t bytes = std::max<uint64_t>(count, 1) * sizeof(T);
+    KB_CUDA(cudaMallocAsync((void **)p, bytes, ix->stream));
+    if (persistent) ix->device_bytes += bytes;
+    return 0;
+}
+
+template <typename T>
+void dev_free(kmer_b200_index *ix, T *p) {
+    if (p) cudaFreeAsync((void *)p, ix->stream);
+}
+
+void *pinned_get(kmer_b200_index *ix, size_t bytes, size_t *cap) {
+    bytes = std::max<size_t>(bytes, 64);
+    size_t best = SIZE_MAX, best_i = SIZE_MAX;
+    for (size_t i = 0; i < ix->pinned_cache.size(); ++i) {
+        const size_t c = ix->pinned_cache[i].second;
+        if (c >= bytes && c < best) {
+            best = c;
+            best_i = i;
+        }
+    }
+    if (best_i != SIZE_MAX && best <= 4 * bytes + (1u << 20)) {
+        void *p = ix->pinned_cache[best_i].first;
+        ix->pinned_cache.erase(ix->pinned_cache.begin() + best_i);
+        *cap = best;
+        return p;
+    }
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    *cap = bytes;
+    return p;
+}
+
+void pinned_put(kmer_b200_index *ix, void *p, size_t cap) {
+    if (!p) return;
+    if (ix->pinned_cache.size() >= 16) {
+        cudaFreeHost(p);
+        return;
+    }
+    ix->pinned_cache.emplace_back(p, cap);
+}
+
+// choose_search_scheme, kmer_index.hpp:407-476, in integer arithmetic.
+// sum lists are stored as chains (last summand + previous length) and flattened at the end.
+void build_scheme(kmer_b200_index *ix) {
+    const uint32_t R = kb::kQuerySizeRange;
+    std::vector<uint32_t> all_ks(ix->ks);
+    std::sort(all_ks.begin(), all_ks.end(), [](uint32_t a, uint32_t b) { return a > b; });  // :410
+    std::vector<uint32_t> high;
+    for (uint32_t k : all_ks)
+        if (k >= 9) high.push_back(k);  // :414
+    std::vector<uint32_t> len(R, 0), last(R, 0), prev(R, 0);
+    ix->use_multi.assign(R, 0);
+    for (uint32_t k : high)  // :421-425
+        if (k < R) {
+            len[k] = 1;
+            last[k] = k;
+            ix->use_multi[k] = 1;
+        }
+    for (uint32_t q = all_ks.front() + 1; q < R; ++q)  // :427-443: first (largest) high k whose remainder is reachable
+        for (uint32_t k : high)
+            if (len[q - k] != 0) {
+                len[q] = len[q - k] + 1;
+                last[q] = k;
+                prev[q] = q - k;
+                ix->use_multi[q] = 1;
+                break;
+            }
+    for (uint32_t q = 0; q < R; ++q) {  // :445-475
+        if (len[q] != 0) continue;
+        uint32_t best = all_ks.front();
+        if (q < all_ks.front()) {
+            // smallest k >= q (:450-462)
+            for (uint32_t k : all_ks)
+                if (q <= k && k - q < best - q) best = k;
+        } else {
+            // k minimising the padding ceil(q/k)*k - q; ties keep the larger k (:463-474)
+            auto waste = [q](uint32_t k) { return ((q + k - 1) / k) * k - q; };
+            for (uint32_t k : all_ks)
+                if (waste(k) < waste(best)) best = k;
+        }
+        len[q] = 1;
+        last[q] = best;
+    }
+    auto elem_of = [ix](uint32_t k) {
+        for (size_t i = 0; i < ix->ks.size(); ++i)
+            if (ix->ks[i] == k) return (uint8_t)i;
+        return (uint8_t)0;
+    };
+    ix->sum_off.assign(R + 2, 0);
+    uint64_t total = 0;
+    for (uint32_t q = 0; q < R; ++q) {
+        ix->sum_off[q] = (uint32_t)total;
+        total += len[q];
+    }
+    ix->sum_off[R] = (uint32_t)total;
+    ix->sum_off[R + 1] = (uint32_t)total;
+    ix->sum_elem.assign(total, 0);
+    for (uint32_t q = 0; q < R; ++q) {
+        uint64_t o = (uint64_t)ix->sum_off[q] + len[q];
+        uint32_t c = q;
+        for (uint32_t j = 0; j < len[q]; ++j) {
+            ix->sum_elem[--o] = elem_of(last[c]);
+            c = prev[c];
+        }
+    }
+}
+
+int build_element(kmer_b200_index *ix, uint32_t k, HostElement &he) {
+    using namespace kb;
+    cudaStream_t st = ix->stream;
+    Profiler &pf = ix->prof;
+    const uint64_t n_kmers = ix->n - k + 1;
+    const uint64_t key_space = fast_pow(ix->sigma, (uint8_t)k);
+    he.key_bits = std::max<uint32_t>(1, bit_length(key_space - 1));
+    he.sort_passes = (he.key_bits + kRadixBitsMax - 1) / kRadixBitsMax;
+    const uint32_t bits_per_pass = (he.key_bits + he.sort_passes - 1) / he.sort_passes;
+    const uint32_t mask = (1u << bits_per_pass) - 1;
+    const uint32_t n_tiles = (uint32_t)((n_kmers + sort_tile_size() - 1) / sort_tile_size());
+    const uint32_t n_chunks = (n_tiles + scan_chunk_tiles() - 1) / scan_chunk_tiles();
+    const double text_bytes = (double)n_kmers * ix->bits / 8.0;
+    const double hist_bytes = (double)n_tiles * kRadix * 4;
+
+    uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr};
+    uint32_t *tile_hist = nullptr, *chunk_sums = nullptr;
+    KB_TRY(dev_alloc(ix, &keys[0], n_kmers, true));
+    KB_TRY(dev_alloc(ix, &vals[0], n_kmers, true));
+    KB_TRY(dev_alloc(ix, &tile_hist, (uint64_t)n_tiles * kRadix, false));
+    KB_TRY(dev_alloc(ix, &chunk_sums, (uint64_t)n_chunks * kRadix, false));
+
+    PackedText text{ix->d_text, ix->n, ix->bits, ix->sigma};
+    // pass 0: keys come straight from the packed text
+    pf.begin(K_HIST_TEXT, text_bytes + hist_bytes);
+    launch_hist_text(text, k, n_kmers, 0, mask, tile_hist, st);
+    pf.end();
+    pf.begin(K_COLUMN_SCAN, 3 * hist_bytes, 3);
+    launch_column_scan(tile_hist, n_tiles, chunk_sums, st);
+    pf.end();
+    pf.begin(K_SCATTER_TEXT, text_bytes + hist_bytes + 8.0 * n_kmers);
+    launch_scatter_text(text, k, n_kmers, 0, mask, tile_hist, keys[0], vals[0], st);
+    pf.end();
+    int cur = 0;
+    for (uint32_t p = 1; p < he.sort_passes; ++p) {
+        const int nxt = cur ^ 1;
+        if (!keys[nxt]) {
+            KB_TRY(dev_alloc(ix, &keys[nxt], n_kmers, true));
+            KB_TRY(dev_alloc(ix, &vals[nxt], n_kmers, true));
+        }
+        const uint32_t shift = p * bits_per_pass;
+        pf.begin(K_HIST_PAIRS, 4.0 * n_kmers + hist_bytes);
+        launch_hist_pairs(keys[cur], n_kmers, shift, mask, tile_hist, st);
+        pf.end();
+        pf.begin(K_COLUMN_SCAN, 3 * hist_bytes, 3);
+        launch_column_scan(tile_hist, n_tiles, chunk_sums, st);
+        pf.end();
+        pf.begin(K_SCATTER_PAIRS, 16.0 * n_kmers + hist_bytes);
+        launch_scatter_pairs(keys[cur], vals[cur], n_kmers, shift, mask, tile_hist, keys[nxt], vals[nxt], st);
+        pf.end();
+        cur = nxt;
+    }
+    KB_CUDA(cudaGetLastError());
+    if (keys[cur ^ 1]) {
+        dev_free(ix, keys[cur ^ 1]);
+        dev_free(ix, vals[cur ^ 1]);
+        ix->device_bytes -= 2 * n_kmers * sizeof(uint32_t);
+    }
+    dev_free(ix, tile_hist);
+    dev_free(ix, chunk_sums);
+    he.d_keys = keys[cur];
+    he.d_pos = vals[cur];
+
+    // directory: dense (shift 0) while the key space is at most ~4x the number of k-mers
+    uint32_t shift = 0;
+    if (ix->cfg.directory_bits) {
+        if (he.key_bits > ix->cfg.directory_bits) shift = he.key_bits - ix->cfg.directory_bits;
+    } else {
+        uint32_t want = bit_length(n_kmers) + 1;
+        if (want < 16) want = 16;
+        if (he.key_bits > want) shift = he.key_bits - want;
+    }
+    const uint64_t dir_entries = ((key_space - 1) >> shift) + 2;
+    KB_TRY(dev_alloc(ix, &he.d_dir, dir_entries, true));
+    pf.begin(K_DIRECTORY_FILL, 4.0 * n_kmers + 4.0 * dir_entries);
+    launch_directory_fill(he.d_keys, n_kmers, shift, dir_entries, he.d_dir, st);
+    pf.end();
+    KB_CUDA(cudaGetLastError());
+
+    he.dev.k = k;
+    he.dev.shift = shift;
+    he.dev.n_kmers = n_kmers;
+    he.dev.dir_entries = dir_entries;
+    he.dev.key_space = key_space;
+    he.dev.dir = he.d_dir;
+    he.dev.keys = he.d_keys;
+    he.dev.pos = he.d_pos;
+    he.bytes = 2 * n_kmers * sizeof(uint32_t) + dir_entries * sizeof(uint32_t);
+    return 0;
+}
+
+int create_impl(const uint8_t *ranks, bool ranks_on_device, uint64_t n, uint32_t sigma, const uint32_t *ks, uint32_t n_ks,
+                const kmer_b200_config *cfg_in, kmer_b200_index **out) {
+    if (!out) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "out is null");
+    *out = nullptr;
+    if (!ranks || !ks) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "ranks/ks is null");
+    if (n_ks == 0 || n_ks > (uint32_t)kb::kMaxElements)
+        return fail(KMER_B200_ERR_INVALID_ARGUMENT, "number of ks must be in [1, 32]");
+    if (sigma < 2 || sigma > 256) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "sigma must be in [2, 256]");
+    const uint32_t bits = sigma <= 4 ? 2 : (sigma <= 16 ? 4 : 8);
+    uint32_t k_max = 0;
+    for (uint32_t i = 0; i < n_ks; ++i) {
+        const uint32_t k = ks[i];
+        // static_assert(k > 0 and k < 64 / log2(sigma)), kmer_index.hpp:42-43
+        if (k == 0 || !((double)k < 64.0 / std::log2((double)sigma)))
+            return fail(KMER_B200_ERR_INVALID_ARGUMENT, "k must satisfy 0 < k < 64 / log2(sigma) (kmer_index.hpp:42)");
+        if (k * bits > 64 || std::pow((double)sigma, (double)k) > 4294967296.0)
+            return fail(KMER_B200_ERR_UNSUPPORTED, "sigma^k must be <= 2^32 (32-bit hashes) in this build");
+        for (uint32_t j = 0; j < i; ++j)
+            if (ks[j] == k) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "duplicate k");
+        k_max = std::max(k_max, k);
+    }
+    if (n < k_max) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "text shorter than the largest k");
+    // assert(i + k - 1 < numeric_limits<position_t>::max()), kmer_index.hpp:169 with position_t = uint32_t (:575)
+    kmer_b200_config cfg;
+    if (cfg_in)
+        cfg = *cfg_in;
+    else
+        kmer_b200_config_default(&cfg);
+    const uint64_t n_total = cfg.n_total ? cfg.n_total : n;
+    if (cfg.shard_begin + n > n_total) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "shard exceeds n_total");
+    if (n_total >= 0xFFFFFFFFull) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "text too large for 32-bit positions");
+    const bool sharded = cfg.n_total != 0 && (cfg.shard_begin != 0 || n != n_total);
+    const bool last_shard = cfg.shard_begin + n == n_total;
+    if (cfg.halo >= n && cfg.halo) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "halo must be smaller than the slice");
+    if (sharded && !last_shard && cfg.halo + 1 < k_max)
+        return fail(KMER_B200_ERR_INVALID_ARGUMENT, "interior shards need halo >= max k - 1");
+    if (last_shard && cfg.halo) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "the last shard has no halo");
+
+    int device = cfg.device;
+    if (device < 0) {
+        cudaError_t e = cudaGetDevice(&device);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(KMER_B200_ERR_CUDA, std::string("cudaGetDevice: ") + cudaGetErrorString(e));
+        }
+    }
+    {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || device >= count) {
+            cudaGetLastError();
+            return fail(KMER_B200_ERR_CUDA, "no usable CUDA device (libkmer_b200 has no CPU fallback)");
+        }
+    }
+    DeviceGuard guard(device);
+    kmer_b200_index *ix = new (std::nothrow) kmer_b200_index();
+    if (!ix) return fail(KMER_B200_ERR_OUT_OF_MEMORY, "host allocation failed");
+    ix->device = device;
+    ix->cfg = cfg;
+    ix->n = n;
+    ix->sigma = sigma;
+    ix->bits = bits;
+    ix->ks.assign(ks, ks + n_ks);
+    auto bail = [&](int code) {
+        kmer_b200_destroy(ix);
+        return code;
+    };
+#define KB_OR_BAIL(expr)                \
+    do {                                \
+        int _s = (expr);                \
+        if (_s != 0) return bail(_s);   \
+    } while (0)
+#define KB_CUDA_OR_BAIL(expr)                                                                      \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            cudaGetLastError();                                                                    \
+            return bail(fail(_e == cudaErrorMemoryAllocation ? KMER_B200_ERR_OUT_OF_MEMORY         \
+                                                             : KMER_B200_ERR_CUDA,                 \
+                             std::string(#expr) + ": " + cudaGetErrorString(_e)));                 \
+        }                                                                                          \
+    } while (0)
+
+    if (cfg.stream) {
+        ix->stream = (cudaStream_t)cfg.stream;
+    } else {
+        KB_CUDA_OR_BAIL(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+        ix->own_stream = true;
+    }
+    ix->prof.enabled = cfg.profile != 0;
+    ix->prof.stream = ix->stream;
+    {
+        // keep freed blocks in the stream-ordered pool so repeated builds/searches do not hit the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t threshold = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+        }
+    }
+    KB_CUDA_OR_BAIL(cudaMallocHost((void **)&ix->h_pinned, 8 * sizeof(uint64_t)));
+    KB_OR_BAIL(dev_alloc(ix, &ix->d_flags, 2, true));
+    KB_CUDA_OR_BAIL(cudaMemsetAsync(ix->d_flags, 0, 2 * sizeof(uint32_t), ix->stream));
+
+    // ---- text: H2D (if needed) + pack
+    const uint8_t *d_ranks = ranks;
+    uint8_t *d_ranks_owned = nullptr;
+    if (!ranks_on_device) {
+        KB_OR_BAIL(dev_alloc(ix, &d_ranks_owned, n, false));
+        KB_CUDA_OR_BAIL(cudaMemcpyAsync(d_ranks_owned, ranks, n, cudaMemcpyHostToDevice, ix->stream));
+        d_ranks = d_ranks_owned;
+    }
+    ix->text_words = (n * bits + 63) / 64 + 2;
+    KB_OR_BAIL(dev_alloc(ix, &ix->d_text, ix->text_words, true));
+    ix->prof.begin(K_PACK_TEXT, (double)n + (double)n * bits / 8.0);
+    kb::launch_pack_text(d_ranks, n, bits, sigma, ix->text_words, ix->d_text, ix->d_flags, ix->stream);
+    ix->prof.end();
+    if (d_ranks_owned) dev_free(ix, d_ranks_owned);
+
+    // ---- elements
+    ix->elems.resize(n_ks);
+    for (uint32_t i = 0; i < n_ks; ++i) KB_OR_BAIL(build_element(ix, ks[i], ix->elems[i]));
+
+    // ---- scheme tables
+    build_scheme(ix);
+    KB_OR_BAIL(dev_alloc(ix, &ix->d_sum_off, ix->sum_off.size(), true));
+    KB_OR_BAIL(dev_alloc(ix, &ix->d_sum_elem, ix->sum_elem.size(), true));
+    KB_OR_BAIL(dev_alloc(ix, &ix->d_use_multi, ix->use_multi.size(), true));
+    KB_CUDA_OR_BAIL(cudaMemcpyAsync(ix->d_sum_off, ix->sum_off.data(), ix->sum_off.size() * sizeof(uint32_t),
+                                    cudaMemcpyHostToDevice, ix->stream));
+    KB_CUDA_OR_BAIL(cudaMemcpyAsync(ix->d_sum_elem, ix->sum_elem.data(), ix->sum_elem.size(), cudaMemcpyHostToDevice,
+                                    ix->stream));
+    KB_CUDA_OR_BAIL(cudaMemcpyAsync(ix->d_use_multi, ix->use_multi.data(), ix->use_multi.size(), cudaMemcpyHostToDevice,
+                                    ix->stream));
+
+    // ---- device-side index descriptor
+    kb::DeviceIndex &D = ix->host_index;
+    std::memset(&D, 0, sizeof(D));
+    D.text = kb::PackedText{ix->d_text, n, bits, sigma};
+    D.owned = n - cfg.halo;
+    D.global_base = cfg.shard_begin;
+    D.n_elems = n_ks;
+    D.sharded = sharded ? 1 : 0;
+    for (uint32_t i = 0; i < n_ks; ++i) D.elem[i] = ix->elems[i].dev;
+    D.scheme = kb::SchemeTables{ix->d_sum_off, ix->d_sum_elem, ix->d_use_multi};
+    for (uint32_t e = 0; e <= 32; ++e) {
+        // saturating: only compared against 1e7 and used as slab width when < sigma^k <= 2^32
+        const double approx = std::pow((double)sigma, (double)e);
+        D.pow_sigma[e] = approx > 9.0e18 ? (1ull << 63) : fast_pow(sigma, (uint8_t)e);
+    }
+    {
+        std::vector<uint32_t> order(n_ks);
+        for (uint32_t i = 0; i < n_ks; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ks[a] > ks[b]; });
+        for (uint32_t i = 0; i < n_ks; ++i) D.elem_by_k_desc[i] = (uint8_t)order[i];
+    }
+    KB_OR_BAIL(dev_alloc(ix, &ix->d_index, 1, true));
+    KB_CUDA_OR_BAIL(cudaMemcpyAsync(ix->d_index, &D, sizeof(D), cudaMemcpyHostToDevice, ix->stream));
+
+    // ---- finish: surface asynchronous failures and invalid ranks
+    KB_CUDA_OR_BAIL(cudaMemcpyAsync(ix->h_pinned, ix->d_flags, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ix->stream));
+    KB_CUDA_OR_BAIL(cudaStreamSynchronize(ix->stream));
+    KB_CUDA_OR_BAIL(cudaGetLastError());
+    if (reinterpret_cast<uint32_t *>(ix->h_pinned)[0] & 1u)
+        return bail(fail(KMER_B200_ERR_INVALID_RANK, "text contains a rank >= sigma"));
+    *out = ix;
+    return KMER_B200_OK;
+#undef KB_OR_BAIL
+#undef KB_CUDA_OR_BAIL
+}
+
+enum SearchFlavor { kFlavorFull, kFlavorCountOnly };
+
+// queries already on the device; result stays on the device
+int search_device_impl(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off, uint64_t Q, uint64_t max_len,
+                       uint32_t mode, const uint64_t *d_present_global, SearchFlavor flavor, kmer_b200_result **out) {
+    using namespace kb;
+    if (mode == UINT32_MAX) mode = ix->cfg.mode;
+    if (mode > KMER_B200_MODE_CORRECT) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "unknown mode");
+    cudaStream_t st = ix->stream;
+    kmer_b200_result *res = new (std::nothrow) kmer_b200_result();
+    if (!res) return fail(KMER_B200_ERR_OUT_OF_MEMORY, "host allocation failed");
+    res->index = ix;
+    res->on_device = true;
+    res->n_queries = Q;
+    auto bail = [&](int code) {
+        kmer_b200_result_free(res);
+        return code;
+    };
+    uint8_t *d_unsorted = nullptr;
+    uint64_t *d_block_sums = nullptr;
+    if (dev_alloc(ix, &res->offsets, Q + 1, false) || dev_alloc(ix, &res->status, Q, false) ||
+        dev_alloc(ix, &d_unsorted, Q, false) || dev_alloc(ix, &d_block_sums, offsets_scan_blocks(Q) + 1, false))
+        return bail(KMER_B200_ERR_OUT_OF_MEMORY);
+
+    // shared-memory reservation per query: ceil(max_len / 32) rounds of bits/2 words, plus two padding words
+    uint64_t len_cap = std::max<uint64_t>(max_len, 1);
+    if (ix->host_index.sharded && ix->cfg.halo + 1 < len_cap && ix->host_index.owned != ix->n) len_cap = ix->cfg.halo + 1;
+    if (mode == KMER_B200_MODE_REFERENCE_EXACT) len_cap = std::min<uint64_t>(len_cap, kQuerySizeRange);
+    const uint32_t q_words = (uint32_t)(((len_cap + 31) / 32) * (ix->bits / 2) + 2);
+    if ((size_t)q_words * 8 * 8 > 200 * 1024)
+        return bail(fail(KMER_B200_ERR_UNSUPPORTED, "query too long for the shared-memory staging of this build"));
+
+    SearchArgs a{};
+    a.index = ix->d_index;
+    a.q_ranks = d_q;
+    a.q_offsets = d_off;
+    a.n_queries = Q;
+    a.mode = mode;
+    a.q_words = q_words;
+    a.max_len = (uint32_t)len_cap;
+    a.present_global = d_present_global;
+    a.counts = res->offsets;
+    a.status = res->status;
+    a.unsorted = d_unsorted;
+    a.positions = nullptr;
+    a.present = nullptr;
+    a.error_flag = ix->d_flags;
+
+    cudaMemsetAsync(ix->d_flags, 0, 2 * sizeof(uint32_t), st);
+    ix->prof.begin(K_SEARCH_COUNT, 0);
+    launch_search(a, kPassCount, st);
+    ix->prof.end();
+    ix->prof.begin(K_OFFSETS_SCAN, 3.0 * 8 * Q, 3);
+    launch_offsets_scan(res->offsets, Q, d_block_sums, st);
+    ix->prof.end();
+    // total hits + flags back to the host: the one synchronisation point of a search
+    cudaMemcpyAsync(&ix->h_pinned[0], res->offsets + Q, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&ix->h_pinned[1], ix->d_flags, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return bail(fail(KMER_B200_ERR_CUDA, std::string("search (count pass): ") + cudaGetErrorString(e)));
+    }
+    const uint64_t total = ix->h_pinned[0];
+    const uint32_t *flags = reinterpret_cast<const uint32_t *>(&ix->h_pinned[1]);
+    if (flags[0] & 1u) {
+        dev_free(ix, d_unsorted);
+        dev_free(ix, d_block_sums);
+        return bail(fail(KMER_B200_ERR_INVALID_RANK, "a query contains a rank >= sigma"));
+    }
+    res->n_positions = total;
+    if (flavor == kFlavorFull && total > 0) {
+        if (dev_alloc(ix, &res->positions, total, false)) {
+            dev_free(ix, d_unsorted);
+            dev_free(ix, d_block_sums);
+            return bail(KMER_B200_ERR_OUT_OF_MEMORY);
+        }
+        a.positions = res->positions;
+        ix->prof.begin(K_SEARCH_WRITE, 0);
+        launch_search(a, kPassWrite, st);
+        ix->prof.end();
+        if (flags[1] != 0) {
+            uint32_t *d_tmp = nullptr;
+            if (dev_alloc(ix, &d_tmp, total, false)) {
+                dev_free(ix, d_unsorted);
+                dev_free(ix, d_block_sums);
+                return bail(KMER_B200_ERR_OUT_OF_MEMORY);
+            }
+            const uint32_t key_bits = bit_length(ix->cfg.shard_begin + ix->n);
+            ix->prof.begin(K_SEGMENT_SORT, 0);
+            launch_segment_sort(res->positions, d_tmp, res->offsets, d_unsorted, Q, key_bits, st);
+            ix->prof.end();
+            dev_free(ix, d_tmp);
+        }
+    }
+    dev_free(ix, d_unsorted);
+    dev_free(ix, d_block_sums);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return bail(fail(KMER_B200_ERR_CUDA, std::string("search (write pass): ") + cudaGetErrorString(e)));
+    *out = res;
+    return KMER_B200_OK;
+}
+
+__global__ void max_len_kernel(const uint64_t *__restrict__ off, uint64_t Q, unsigned long long *out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long m = 0;
+    for (; i < Q; i += (uint64_t)gridDim.x * blockDim.x) m = max(m, (unsigned long long)(off[i + 1] - off[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+}  // namespace
+
+extern "C" {
+
+void kmer_b200_config_default(kmer_b200_config *cfg) {
+    if (!cfg) return;
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->device = -1;
+    cfg->mode = KMER_B200_MODE_REFERENCE_EXACT;
+}
+
+int kmer_b200_abi_version(void) { return KMER_B200_ABI_VERSION; }
+
+const char *kmer_b200_last_error(void) { return g_last_error.c_str(); }
+
+int kmer_b200_create(const uint8_t *ranks, uint64_t n, uint32_t sigma, const uint32_t *ks, uint32_t n_ks,
+                     const kmer_b200_config *cfg, kmer_b200_index **out) {
+    return create_impl(ranks, false, n, sigma, ks, n_ks, cfg, out);
+}
+
+int kmer_b200_create_from_device(const uint8_t *d_ranks, uint64_t n, uint32_t sigma, const uint32_t *ks, uint32_t n_ks,
+                                 const kmer_b200_config *cfg, kmer_b200_index **out) {
+    return create_impl(d_ranks, true, n, sigma, ks, n_ks, cfg, out);
+}
+
+void kmer_b200_destroy(kmer_b200_index *ix) {
+    if (!ix) return;
+    DeviceGuard guard(ix->device);
+    if (ix->stream) cudaStreamSynchronize(ix->stream);
+    ix->prof.resolve();
+    for (auto &he : ix->elems) {
+        dev_free(ix, he.d_dir);
+        dev_free(ix, he.d_keys);
+        dev_free(ix, he.d_pos);
+    }
+    dev_free(ix, ix->d_text);
+    dev_free(ix, ix->d_sum_off);
+    dev_free(ix, ix->d_sum_elem);
+    dev_free(ix, ix->d_use_multi);
+    dev_free(ix, ix->d_index);
+    dev_free(ix, ix->d_flags);
+    if (ix->stream) cudaStreamSynchronize(ix->stream);
+    for (auto &pc : ix->pinned_cache) cudaFreeHost(pc.first);
+    if (ix->h_pinned) cudaFreeHost(ix->h_pinned);
+    for (auto e : ix->prof.pool) cudaEventDestroy(e);
+    ix->prof.pool.clear();
+    if (ix->own_stream && ix->stream) cudaStreamDestroy(ix->stream);
+    cudaGetLastError();
+    delete ix;
+}
+
+int kmer_b200_search_batch_device(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off, uint64_t Q,
+                                  uint64_t max_len, uint32_t mode, kmer_b200_result **out) {
+    if (!ix || !out || (!d_off)) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    DeviceGuard guard(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    return search_device_impl(ix, d_q, d_off, Q, max_len, mode, nullptr, kFlavorFull, out);
+}
+
+int kmer_b200_count_batch_device(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off, uint64_t Q,
+                                 uint64_t max_len, uint32_t mode, kmer_b200_result **out) {
+    if (!ix || !out || (!d_off)) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    DeviceGuard guard(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    return search_device_impl(ix, d_q, d_off, Q, max_len, mode, nullptr, kFlavorCountOnly, out);
+}
+
+int kmer_b200_search_batch_device_global(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off, uint64_t Q,
+                                         uint64_t max_len, uint32_t mode, const uint64_t *d_present_global,
+                                         kmer_b200_result **out) {
+    if (!ix || !out || (!d_off)) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    DeviceGuard guard(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    return search_device_impl(ix, d_q, d_off, Q, max_len, mode, d_present_global, kFlavorFull, out);
+}
+
+int kmer_b200_presence_batch_device(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off, uint64_t Q,
+                                    uint64_t max_len, uint32_t mode, uint64_t *d_present) {
+    using namespace kb;
+    if (!ix || !d_off || !d_present) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
+    if (mode == UINT32_MAX) mode = ix->cfg.mode;
+    DeviceGuard guard(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    uint64_t len_cap = std::max<uint64_t>(max_len, 1);
+    if (mode == KMER_B200_MODE_REFERENCE_EXACT) len_cap = std::min<uint64_t>(len_cap, kQuerySizeRange);
+    SearchArgs a{};
+    a.index = ix->d_index;
+    a.q_ranks = d_q;
+    a.q_offsets = d_off;
+    a.n_queries = Q;
+    a.mode = mode;
+    a.q_words = (uint32_t)(((len_cap + 31) / 32) * (ix->bits / 2) + 2);
+    a.max_len = (uint32_t)len_cap;
+    a.present = d_present;
+    a.error_flag = ix->d_flags;
+    ix->prof.begin(K_SEARCH_PRESENCE, 0);
+    launch_search(a, kPassPresence, ix->stream);
+    ix->prof.end();
+    KB_CUDA(cudaGetLastError());
+    return KMER_B200_OK;
+}
+
+int kmer_b200_search_batch(kmer_b200_index *ix, const uint8_t *q_ranks, const uint64_t *q_offsets, uint64_t Q,
+                           uint32_t mode, kmer_b200_result **out) {
+    if (!ix || !out || !q_offsets) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    DeviceGuard guard(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    cudaStream_t st = ix->stream;
+    const uint64_t n_sym = q_offsets[Q] - q_offsets[0];
+    if (n_sym && !q_ranks) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "q_ranks is null");
+    uint8_t *d_q = nullptr;
+    uint64_t *d_off = nullptr;
+    unsigned long long *d_max = nullptr;
+    KB_TRY(dev_alloc(ix, &d_q, n_sym, false));
+    KB_TRY(dev_alloc(ix, &d_off, Q + 1, false));
+    KB_TRY(dev_alloc(ix, &d_max, 1, false));
+    // offsets are rebased on the device side by passing q_ranks - q_offsets[0]
+    KB_CUDA(cudaMemcpyAsync(d_off, q_offsets, (Q + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    if (n_sym) KB_CUDA(cudaMemcpyAsync(d_q, q_ranks + q_offsets[0], n_sym, cudaMemcpyHostToDevice, st));
+    KB_CUDA(cudaMemsetAsync(d_max, 0, sizeof(unsigned long long), st));
+    if (Q) max_len_kernel<<<(unsigned)std::min<uint64_t>((Q + 255) / 256, 148 * 8), 256, 0, st>>>(d_off, Q, d_max);
+    KB_CUDA(cudaMemcpyAsync(&ix->h_pinned[2], d_max, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    KB_CUDA(cudaStreamSynchronize(st));
+    const uint64_t max_len = ix->h_pinned[2];
+    kmer_b200_result *dres = nullptr;
+    int s = search_device_impl(ix, d_q - q_offsets[0], d_off, Q, max_len, mode, nullptr, kFlavorFull, &dres);
+    dev_free(ix, d_q);
+    dev_free(ix, d_off);
+    dev_free(ix, d_max);
+    if (s != 0) return s;
+    // device result -> pinned host buffers
+    kmer_b200_result *res = new (std::nothrow) kmer_b200_result();
+    if (!res) {
+        kmer_b200_result_free(dres);
+        return fail(KMER_B200_ERR_OUT_OF_MEMORY, "host allocation failed");
+    }
+    res->index = ix;
+    res->on_device = false;
+    res->n_queries = Q;
+    res->n_positions = dres->n_positions;
+    res->offsets = (uint64_t *)pinned_get(ix, (Q + 1) * sizeof(uint64_t), &res->cap_offsets);
+    res->status = (uint8_t *)pinned_get(ix, Q, &res->cap_status);
+    res->positions = (uint32_t *)pinned_get(ix, res->n_positions * sizeof(uint32_t), &res->cap_positions);
+    if (!res->offsets || !res->status || !res->positions) {
+        kmer_b200_result_free(dres);
+        kmer_b200_result_free(res);
+        return fail(KMER_B200_ERR_OUT_OF_MEMORY, "pinned host allocation failed");
+    }
+    cudaMemcpyAsync(res->offsets, dres->offsets, (Q + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
+    if (Q) cudaMemcpyAsync(res->status, dres->status, Q, cudaMemcpyDeviceToHost, st);
+    if (res->n_positions)
+        cudaMemcpyAsync(res->positions, dres->positions, res->n_positions * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    kmer_b200_result_free(dres);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        kmer_b200_result_free(res);
+        return fail(KMER_B200_ERR_CUDA, std::string("search (D2H): ") + cudaGetErrorString(e));
+    }
+    *out = res;
+    return KMER_B200_OK;
+}
+
+uint64_t kmer_b200_result_n_queries(const kmer_b200_result *r) { return r ? r->n_queries : 0; }
+uint64_t kmer_b200_result_n_positions(const kmer_b200_result *r) { return r ? r->n_positions : 0; }
+int kmer_b200_result_on_device(const kmer_b200_result *r) { return r && r->on_device; }
+const uint64_t *kmer_b200_result_offsets(const kmer_b200_result *r) { return r ? r->offsets : nullptr; }
+const uint32_t *kmer_b200_result_positions(const kmer_b200_result *r) { return r ? r->positions : nullptr; }
+const uint8_t *kmer_b200_result_status(const kmer_b200_result *r) { return r ? r->status : nullptr; }
+
+void kmer_b200_result_free(kmer_b200_result *r) {
+    if (!r) return;
+    kmer_b200_index *ix = r->index;
+    if (r->on_device) {
+        DeviceGuard guard(ix->device);
+        dev_free(ix, r->offsets);
+        dev_free(ix, r->positions);
+        dev_free(ix, r->status);
+    } else {
+        pinned_put(ix, r->offsets, r->cap_offsets);
+        pinned_put(ix, r->positions, r->cap_positions);
+        pinned_put(ix, r->status, r->cap_status);
+    }
+    delete r;
+}
+
+uint32_t kmer_b200_n_elements(const kmer_b200_index *ix) { return ix ? (uint32_t)ix->elems.size() : 0; }
+
+int kmer_b200_element_info_get(const kmer_b200_index *ix, uint32_t e, kmer_b200_element_info *out) {
+    if (!ix || !out || e >= ix->elems.size()) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad element");
+    const HostElement &he = ix->elems[e];
+    out->k = he.dev.k;
+    out->key_bits = he.key_bits;
+    out->directory_shift = he.dev.shift;
+    out->sort_passes = he.sort_passes;
+    out->n_kmers = he.dev.n_kmers;
+    out->directory_entries = he.dev.dir_entries;
+    out->device_bytes = he.bytes;
+    return KMER_B200_OK;
+}
+
+int kmer_b200_element_positions(kmer_b200_index *ix, uint32_t e, uint32_t *out, uint64_t cap) {
+    if (!ix || !out || e >= ix->elems.size()) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad element");
+    DeviceGuard guard(ix->device);
+    const uint64_t n = std::min<uint64_t>(cap, ix->elems[e].dev.n_kmers);
+    KB_CUDA(cudaMemcpyAsync(out, ix->elems[e].d_pos, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ix->stream));
+    KB_CUDA(cudaStreamSynchronize(ix->stream));
+    return KMER_B200_OK;
+}
+
+int kmer_b200_element_hashes(kmer_b200_index *ix, uint32_t e, uint32_t *out, uint64_t cap) {
+    if (!ix || !out || e >= ix->elems.size()) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad element");
+    DeviceGuard guard(ix->device);
+    const uint64_t n = std::min<uint64_t>(cap, ix->elems[e].dev.n_kmers);
+    KB_CUDA(cudaMemcpyAsync(out, ix->elems[e].d_keys, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ix->stream));
+    KB_CUDA(cudaStreamSynchronize(ix->stream));
+    return KMER_B200_OK;
+}
+
+uint64_t kmer_b200_scheme(const kmer_b200_index *ix, uint64_t m, uint32_t *out_ks, uint64_t cap, int *use_multi) {
+    if (!ix || m >= kb::kQuerySizeRange) return 0;
+    const uint32_t o = ix->sum_off[m], len = ix->sum_off[m + 1] - o;
+    for (uint32_t i = 0; i < len && i < cap && out_ks; ++i) out_ks[i] = ix->ks[ix->sum_elem[o + i]];
+    if (use_multi) *use_multi = ix->use_multi[m];
+    return len;
+}
+
+uint32_t kmer_b200_stats(kmer_b200_index *ix, kmer_b200_kernel_stat *out, uint32_t cap) {
+    if (!ix) return 0;
+    DeviceGuard guard(ix->device);
+    ix->prof.resolve();
+    uint32_t n = 0;
+    for (int i = 0; i < K_COUNT_ && n < cap; ++i) {
+        if (out) {
+            out[n].name = kKernelNames[i];
+            out[n].launches = ix->prof.launches[i];
+            out[n].device_ms = ix->prof.ms[i];
+            out[n].algorithmic_bytes = ix->prof.bytes[i];
+        }
+        ++n;
+    }
+    return n;
+}
+
+void kmer_b200_stats_reset(kmer_b200_index *ix) {
+    if (!ix) return;
+    DeviceGuard guard(ix->device);
+    ix->prof.reset();
+}
+
+uint64_t kmer_b200_device_bytes(const kmer_b200_index *ix) { return ix ? ix->device_bytes : 0; }
+
+uint64_t kmer_b200_fast_pow(uint64_t base, uint8_t exp) { return fast_pow(base, exp); }
+
+uint64_t kmer_b200_hash(const uint8_t *ranks, uint32_t k, uint32_t sigma) {
+    uint64_t h = 0;
+    for (uint32_t i = 0; i < k; ++i) h += (uint64_t)ranks[i] * fast_pow(sigma, (uint8_t)(k - i - 1));
+    return h;
+}
+
+uint64_t kmer_b200_choose_best_k(const uint64_t *lens, uint64_t n_lens, uint64_t n_k, uint64_t *out_ks) {
+    // choose_best_k.hpp:12-60. Candidates in the reference's priority order; the first candidate that divides
+    // the length (+3) or misses a multiple by at most 3 (+4 - miss) takes the length's points.
+    static const uint64_t cand[10] = {29, 27, 25, 23, 21, 19, 17, 13, 11, 10};
+    uint64_t score[10] = {};
+    for (uint64_t a = 0; a < n_lens; ++a)
+        for (int c = 0; c < 10; ++c) {
+            const uint64_t rem = lens[a] % cand[c];
+            if (rem == 0) {
+                score[c] += 3;
+                break;
+            }
+            if (cand[c] - rem <= 3) {
+                score[c] += 4 - (cand[c] - rem);
+                break;
+            }
+        }
+    int order[10] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9};
+    std::stable_sort(order, order + 10, [&](int x, int y) { return score[x] > score[y]; });
+    uint64_t w = 0;
+    for (; w < n_k && w < 10; ++w) out_ks[w] = cand[order[w]];
+    return w;
+}
+
+int kmer_b200_synth_ranks_device(uint8_t *d_out, uint64_t n, uint64_t start, uint32_t sigma, uint64_t seed, void *stream) {
+    if (!d_out && n) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null output");
+    kb::launch_synth_ranks(d_out, n, start, sigma, seed, (cudaStream_t)stream);
+    KB_CUDA(cudaGetLastError());
+    return KMER_B200_OK;
+}
+
+}  // extern "C"

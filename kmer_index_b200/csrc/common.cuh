@@ -1,0 +1,90 @@
+// Shared device-side definitions for libkmer_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/kmer_b200.h"
+
+namespace kb {
+
+constexpr int kMaxElements = 32;
+constexpr uint32_t kQuerySizeRange = 10000;  // kmer_index.hpp:401
+
+// ---------------------------------------------------------------------------------------------
+// Packed text. Symbol i occupies `bits` bits (2, 4 or 8), MSB-first inside 64-bit words, so that a
+// window of consecutive symbols read as one big-endian bit field IS the reference's positional hash
+// for power-of-two alphabets (kmer_index.hpp:56-73: the first symbol carries sigma^(k-1)).
+// The word array carries two zero words of padding so a window read never leaves the allocation.
+// ---------------------------------------------------------------------------------------------
+struct PackedText {
+    const uint64_t *words;
+    uint64_t n;     // symbols
+    uint32_t bits;  // per symbol
+    uint32_t sigma;
+};
+
+// 64 bits starting at symbol `sym` (left-aligned: the first symbol sits in the top `bits` bits).
+template <typename WordPtr>
+__device__ __forceinline__ uint64_t window64(WordPtr words, uint64_t sym, uint32_t bits) {
+    const uint64_t bit = sym * bits;
+    const uint64_t w = bit >> 6;
+    const uint32_t sh = (uint32_t)(bit & 63);
+    const uint64_t hi = words[w];
+    const uint64_t lo = words[w + 1];
+    return sh ? ((hi << sh) | (lo >> (64 - sh))) : hi;
+}
+
+// The k-mer hash of the k symbols at the top of window `w` (kmer_index.hpp:56-73).
+// sigma == 4: the 2k-bit field itself. Otherwise Horner over the k symbols (k * bits <= 64).
+__device__ __forceinline__ uint32_t key_from_window(uint64_t w, uint32_t k, uint32_t bits, uint32_t sigma) {
+    if (sigma == (1u << bits)) return (uint32_t)(w >> (64 - k * bits));
+    uint32_t h = 0;
+    const uint64_t mask = (1ull << bits) - 1;
+#pragma unroll 1
+    for (uint32_t i = 0; i < k; ++i) {
+        h = h * sigma + (uint32_t)((w >> (64 - bits * (i + 1))) & mask);
+    }
+    return h;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One index element (one k): the CSR form of the reference's
+// robin_hood::unordered_map<hash, std::vector<position>> (kmer_index.hpp:52).
+//   pos[n_kmers]   all k-mer start positions, stably sorted by hash (bucket = run of equal hashes,
+//                  ascending positions inside, as push_back in text order yields, kmer_index.hpp:165)
+//   dir[entries]   dir[j] = number of k-mers with (hash >> shift) < j      (entries = (max_hash >> shift) + 2)
+//   keys[n_kmers]  the sorted hashes (always kept: sub-k slabs and shift > 0 lookups read them)
+// ---------------------------------------------------------------------------------------------
+struct Element {
+    uint32_t k;
+    uint32_t shift;
+    uint64_t n_kmers;
+    uint64_t dir_entries;
+    uint64_t key_space;  // sigma^k
+    const uint32_t *dir;
+    const uint32_t *keys;
+    const uint32_t *pos;
+};
+
+struct SchemeTables {
+    // row m of the reference's _optimal_nk_sum / _use_multi_search_scheme (kmer_index.hpp:404-405),
+    // with ks replaced by element indices
+    const uint32_t *sum_off;   // [kQuerySizeRange + 1]
+    const uint8_t *sum_elem;   // flattened lists
+    const uint8_t *use_multi;  // [kQuerySizeRange]
+};
+
+struct DeviceIndex {
+    PackedText text;
+    uint64_t owned;        // match starts p are reported only for p < owned (sharding); == n unsharded
+    uint64_t global_base;  // added to every reported position (shard_begin)
+    uint32_t n_elems;
+    uint32_t sharded;
+    Element elem[kMaxElements];
+    SchemeTables scheme;
+    uint64_t pow_sigma[33];  // sigma^e for e <= 32 (saturating at 2^63)
+    uint8_t elem_by_k_desc[kMaxElements];  // element indices ordered by k descending (_all_ks, :410)
+};
+
+}  // namespace kb

@@ -1,0 +1,56 @@
+// Host-callable launchers of the kernels in build_kernels.cu / search_kernels.cu / synth.cu.
+#pragma once
+
+#include "common.cuh"
+
+namespace kb {
+
+// ---- build
+void launch_pack_text(const uint8_t *d_ranks, uint64_t n, uint32_t bits, uint32_t sigma, uint64_t n_words_total,
+                      uint64_t *d_words, uint32_t *d_error_flag, cudaStream_t stream);
+void launch_hist_text(const PackedText &text, uint32_t k, uint64_t n_kmers, uint32_t shift, uint32_t mask,
+                      uint32_t *d_tile_hist, cudaStream_t stream);
+void launch_hist_pairs(const uint32_t *d_keys, uint64_t n, uint32_t shift, uint32_t mask, uint32_t *d_tile_hist,
+                       cudaStream_t stream);
+void launch_column_scan(uint32_t *d_tile_hist, uint32_t n_tiles, uint32_t *d_chunk_sums, cudaStream_t stream);
+void launch_scatter_text(const PackedText &text, uint32_t k, uint64_t n_kmers, uint32_t shift, uint32_t mask,
+                         const uint32_t *d_tile_base, uint32_t *d_out_keys, uint32_t *d_out_vals, cudaStream_t stream);
+void launch_scatter_pairs(const uint32_t *d_keys, const uint32_t *d_vals, uint64_t n, uint32_t shift, uint32_t mask,
+                          const uint32_t *d_tile_base, uint32_t *d_out_keys, uint32_t *d_out_vals, cudaStream_t stream);
+void launch_directory_fill(const uint32_t *d_keys, uint64_t n_kmers, uint32_t shift, uint64_t dir_entries, uint32_t *d_dir,
+                           cudaStream_t stream);
+uint32_t sort_tile_size();
+uint32_t scan_chunk_tiles();
+
+// ---- search
+enum SearchPass : int { kPassCount = 0, kPassWrite = 1, kPassPresence = 2 };
+
+struct SearchArgs {
+    const DeviceIndex *index;        // device pointer
+    const uint8_t *q_ranks;          // device
+    const uint64_t *q_offsets;       // device, [Q + 1]
+    uint64_t n_queries;
+    uint32_t mode;                   // kmer_b200_mode
+    uint32_t q_words;                // packed words reserved per query in shared memory
+    uint32_t max_len;                // longest query the shared-memory reservation (and the shard halo) allows
+    const uint64_t *present_global;  // device or null: OR over shards of the presence masks
+    uint64_t *counts;                // device, [Q + 1]: per-query hit counts (count pass), then offsets
+    uint8_t *status;                 // device, [Q]
+    uint8_t *unsorted;               // device, [Q]: 1 = the written segment still needs sorting (sub-k)
+    uint32_t *positions;             // device (write pass)
+    uint64_t *present;               // device (presence pass), [Q]
+    uint32_t *error_flag;            // device u32[2]: [0] bit 0 = query rank >= sigma; [1] = #segments to sort
+};
+
+void launch_search(const SearchArgs &args, SearchPass pass, cudaStream_t stream);
+// in place: counts[0..Q) -> exclusive offsets, counts[Q] = total
+void launch_offsets_scan(uint64_t *d_counts, uint64_t n_queries, uint64_t *d_block_sums, cudaStream_t stream);
+uint64_t offsets_scan_blocks(uint64_t n_queries);
+// sort the flagged per-query segments of positions ascending (one CTA per flagged segment)
+void launch_segment_sort(uint32_t *d_positions, uint32_t *d_tmp, const uint64_t *d_offsets, const uint8_t *d_unsorted,
+                         uint64_t n_queries, uint32_t key_bits, cudaStream_t stream);
+
+// ---- synthetic inputs
+void launch_synth_ranks(uint8_t *d_out, uint64_t n, uint64_t start, uint32_t sigma, uint64_t seed, cudaStream_t stream);
+
+}  // namespace kb

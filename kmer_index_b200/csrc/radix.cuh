@@ -1,0 +1,95 @@
+// Stable LSD radix-sort building blocks (sm_100a). Used by
+//   * the index build: (hash, position) pairs, first pass fused with the rolling hash over the packed
+//     text (keys are never materialised unsorted), and
+//   * the per-query segment sort of sub-k results.
+// Stability is what makes every bucket's positions ascend, which the reference gets from push_back in
+// text order (kmer_index.hpp:165) and relies on for std::binary_search / lower_bound (:242,283,315).
+#pragma once
+
+#include "common.cuh"
+
+namespace kb {
+
+constexpr int kRadixBitsMax = 8;
+constexpr int kRadix = 1 << kRadixBitsMax;
+
+// Tile geometry: one CTA ranks kSortTile elements; element e of a tile belongs to
+// (warp, round, lane) = (e / (32*ITEMS), (e / 32) % ITEMS, e % 32), so rank order == element order.
+constexpr int kSortThreads = 512;
+constexpr int kSortItems = 16;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kSortTile = kSortThreads * kSortItems;  // 8192
+
+constexpr uint32_t kInvalidDigit = 0xFFFFFFFFu;
+
+struct RankSmem {
+    uint32_t warp_cnt[kSortWarps][kRadix];  // per-warp digit counters, then exclusive warp prefixes
+    uint32_t excl[kRadix];                  // exclusive prefix of the tile's digit counts
+    uint32_t count[kRadix];                 // the tile's digit counts
+    uint32_t warp_sums[kRadix / 32];
+};
+
+// Stable rank of this thread's kSortItems digits inside the tile. On return
+//   local_pos[r] = position of item r in the tile's digit-sorted order (undefined for invalid items),
+//   sm.count[d]  = number of items with digit d, sm.excl[d] = exclusive prefix of count.
+// All kSortThreads threads must call. Ends with a __syncthreads().
+__device__ __forceinline__ void tile_rank(const uint32_t (&digit)[kSortItems], uint32_t (&local_pos)[kSortItems],
+                                          RankSmem &sm) {
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const uint32_t lt_mask = (1u << lane) - 1;
+
+    for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) (&sm.warp_cnt[0][0])[i] = 0;
+    __syncthreads();
+
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const uint32_t d = digit[r];
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+        const bool valid = d != kInvalidDigit;
+        uint32_t pre = 0;
+        if (valid) pre = sm.warp_cnt[warp][d];
+        __syncwarp();
+        if (valid && (peers & lt_mask) == 0) sm.warp_cnt[warp][d] = pre + __popc(peers);
+        __syncwarp();
+        local_pos[r] = pre + __popc(peers & lt_mask);
+    }
+    __syncthreads();
+
+    // per digit: exclusive prefix over warps, total count
+    if (tid < kRadix) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) {
+            const uint32_t c = sm.warp_cnt[w][tid];
+            sm.warp_cnt[w][tid] = run;
+            run += c;
+        }
+        sm.count[tid] = run;
+        // exclusive scan of counts over the 256 digits (8 warps)
+        uint32_t incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) sm.warp_sums[warp] = incl;
+        sm.excl[tid] = incl - run;  // warp-local exclusive for now
+    }
+    __syncthreads();
+    if (tid < kRadix) {
+        uint32_t base = 0;
+        for (int w = 0; w < warp; ++w) base += sm.warp_sums[w];
+        sm.excl[tid] += base;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const uint32_t d = digit[r];
+        if (d != kInvalidDigit) local_pos[r] += sm.excl[d] + sm.warp_cnt[warp][d];
+    }
+    __syncthreads();
+}
+
+}  // namespace kb

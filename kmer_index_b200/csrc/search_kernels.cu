@@ -1,0 +1,589 @@
+// Batched search kernels (sm_100a): the replacement for kmer_index::search (kmer_index.hpp:505-558),
+// kmer_index_element::search (kmer_index.hpp:193-346) and kmer_index_result::to_vector
+// (kmer_index_result.hpp:244-260).
+//
+// One warp per query. The warp
+//   1. packs the query into shared memory (same b-bit MSB-first layout as the text),
+//   2. derives the query's plan from its length and the scheme table (which element(s), which parts),
+//   3. hashes all indexed parts in parallel (one lane per part) and gathers their bucket ranges from the
+//      directory -- the reference's early "part absent => empty result" return and its throw for short
+//      rests are decided here, in the reference's order,
+//   4. walks the seed bucket 32 candidates at a time; every lane checks its candidate's remaining
+//      constraints directly against the packed text (the text is the intersection oracle: position x is
+//      in bucket hash(T[x,x+k)) and in no other, so "p + d is in the bucket of part j" is
+//      "T[p+d, p+d+k) == part j"), and hits are compacted with ballot/popc.
+// Results are produced in two passes (count -> exclusive scan -> write) so the output is an exact CSR.
+#include "radix.cuh"
+#include "launch.h"
+
+namespace kb {
+
+constexpr int kSearchWarps = 8;
+constexpr int kSearchThreads = kSearchWarps * 32;
+
+enum PlanKind : int { kExact = 0, kSubK = 1, kContig = 2, kBuggySingle = 3, kMultiSum = 4 };
+
+struct Range {
+    uint64_t lo;
+    uint64_t cnt;
+};
+
+// index of the first sorted k-mer of element E whose hash is >= key (key may equal key_space)
+__device__ __forceinline__ uint64_t lower_bound_key(const Element &E, uint64_t key) {
+    if (key >= E.key_space) return E.n_kmers;
+    const uint64_t t = key >> E.shift;
+    uint64_t lo = E.dir[t];
+    if (E.shift == 0) return lo;
+    uint64_t hi = E.dir[t + 1];
+    while (lo < hi) {
+        const uint64_t mid = lo + ((hi - lo) >> 1);
+        if ((uint64_t)E.keys[mid] < key)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+// the bucket of `key`: the reference's at(hash) (kmer_index.hpp:76-84)
+__device__ __forceinline__ Range bucket_of(const Element &E, uint32_t key) {
+    const uint64_t t = key >> E.shift;
+    uint64_t lo = E.dir[t];
+    uint64_t hi = E.dir[t + 1];
+    if (E.shift != 0) {
+        uint64_t a = lo, b = hi;
+        while (a < b) {
+            const uint64_t mid = a + ((b - a) >> 1);
+            if (E.keys[mid] < key)
+                a = mid + 1;
+            else
+                b = mid;
+        }
+        lo = a;
+        b = hi;
+        while (a < b) {
+            const uint64_t mid = a + ((b - a) >> 1);
+            if (E.keys[mid] <= key)
+                a = mid + 1;
+            else
+                b = mid;
+        }
+        hi = a;
+    }
+    return Range{lo, hi - lo};
+}
+
+// T[tpos, tpos+len) == q[qpos, qpos+len), false if the text span leaves the text
+__device__ __forceinline__ bool match_span(const PackedText &T, const uint64_t *qw, uint64_t tpos, uint32_t qpos,
+                                           uint32_t len) {
+    if (tpos + len > T.n) return false;
+    const uint32_t spw = 64 / T.bits;
+    while (len) {
+        const uint32_t c = len < spw ? len : spw;
+        const uint64_t a = window64(T.words, tpos, T.bits);
+        const uint64_t b = window64(qw, (uint64_t)qpos, T.bits);
+        if ((a ^ b) >> (64 - c * T.bits)) return false;
+        tpos += c;
+        qpos += c;
+        len -= c;
+    }
+    return true;
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(kSearchThreads) search_kernel(const SearchArgs a) {
+    extern __shared__ uint64_t smem_q[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1;
+    const uint64_t q = (uint64_t)blockIdx.x * kSearchWarps + warp;
+    if (q >= a.n_queries) return;
+
+    uint64_t out_base = 0;
+    if (PASS == kPassWrite) {
+        out_base = a.counts[q];
+        if (a.counts[q + 1] == out_base) return;  // nothing to write (also covers every non-OK status)
+    }
+
+    const DeviceIndex &ix = *a.index;
+    const PackedText T = ix.text;
+    uint64_t *qw = smem_q + (size_t)warp * a.q_words;
+    const uint64_t off0 = a.q_offsets[q];
+    const uint64_t m64 = a.q_offsets[q + 1] - off0;
+
+    uint32_t status = KMER_B200_QUERY_OK;
+    if (m64 == 0) {
+        status = KMER_B200_QUERY_UNDEFINED;  // assert(query.size() > 0), kmer_index.hpp:195
+    } else if (a.mode == KMER_B200_MODE_REFERENCE_EXACT && m64 > kQuerySizeRange) {
+        status = KMER_B200_QUERY_THROW_INVALID_ARGUMENT;  // kmer_index.hpp:507-509
+    } else if (a.mode == KMER_B200_MODE_REFERENCE_EXACT && m64 == kQuerySizeRange) {
+        status = KMER_B200_QUERY_UNDEFINED;  // out-of-bounds table read, kmer_index.hpp:512
+    } else if (m64 > a.max_len) {
+        status = KMER_B200_QUERY_TOO_LONG_FOR_SHARD;
+    }
+    if (status != KMER_B200_QUERY_OK) {
+        if (lane == 0) {
+            if (PASS == kPassCount) {
+                a.counts[q] = 0;
+                a.status[q] = (uint8_t)status;
+                a.unsorted[q] = 0;
+            } else if (PASS == kPassPresence) {
+                a.present[q] = 0;
+            }
+        }
+        return;
+    }
+    const uint32_t m = (uint32_t)m64;
+
+    // ---- 1. pack the query (b bits per symbol, MSB-first) -------------------------------------------
+    {
+        const uint8_t *qr = a.q_ranks + off0;
+        const uint32_t wpr = T.bits >> 1;  // words per 32-symbol round
+        const uint32_t my_word = (lane * T.bits) >> 6;
+        const uint32_t my_shift = 64 - T.bits - ((lane * T.bits) & 63);
+        bool bad = false;
+        for (uint32_t base = 0; base < m; base += 32) {
+            const uint32_t s = base + lane;
+            uint32_t r = 0;
+            if (s < m) {
+                r = qr[s];
+                bad |= r >= T.sigma;
+            }
+            const uint64_t v = (uint64_t)r << my_shift;
+            for (uint32_t w = 0; w < wpr; ++w) {
+                const uint64_t mine = (my_word == w) ? v : 0;
+                const uint32_t hi = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)(mine >> 32));
+                const uint32_t lo = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)mine);
+                if (lane == 0) qw[(base >> 5) * wpr + w] = ((uint64_t)hi << 32) | lo;
+            }
+        }
+        if (lane < 2) qw[((m + 31) >> 5) * wpr + lane] = 0;
+        if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) atomicOr(a.error_flag, 1u);
+        __syncwarp();
+    }
+
+    // ---- 2. plan -----------------------------------------------------------------------------------------
+    int kind = kExact;
+    uint32_t e0 = 0, k0 = 0, nparts = 1, P = 0, rest = 0;
+    bool throw_after = false, from_list = false;
+    const uint8_t *S = nullptr;
+    if (a.mode == KMER_B200_MODE_CORRECT) {
+        // any element answers correctly; take the largest k <= m (fewest candidates), else the smallest k
+        e0 = ix.elem_by_k_desc[ix.n_elems - 1];
+        for (uint32_t i = 0; i < ix.n_elems; ++i) {
+            const uint32_t e = ix.elem_by_k_desc[i];
+            if (ix.elem[e].k <= m) {
+                e0 = e;
+                break;
+            }
+        }
+        k0 = ix.elem[e0].k;
+        kind = (m == k0) ? kExact : (m > k0 ? kContig : kSubK);
+    } else {
+        const uint32_t s_off = ix.scheme.sum_off[m];
+        const uint32_t s_len = ix.scheme.sum_off[m + 1] - s_off;
+        S = ix.scheme.sum_elem + s_off;
+        e0 = S[0];
+        k0 = ix.elem[e0].k;
+        const bool multi = ix.scheme.use_multi[m] && ix.n_elems > 1;  // kmer_index.hpp:512
+        if (!multi) {
+            // kmer_index_element<k0>::search, kmer_index.hpp:193-346
+            if (m == k0) {
+                kind = kExact;
+            } else if (m < k0) {
+                if (ix.pow_sigma[k0 - m] > 10000000ull)  // kmer_index.hpp:119-122
+                    status = KMER_B200_QUERY_THROW_INVALID_ARGUMENT;
+                kind = kSubK;
+            } else {
+                P = m / k0;
+                rest = m % k0;
+                nparts = P;
+                throw_after = rest > 0 && ix.pow_sigma[k0 - rest] > 10000000ull;  // :234 -> :119
+                // :314 compares every later part against the LAST part when P >= 3 and rest > 0
+                kind = (rest == 0 || P <= 2) ? kContig : kBuggySingle;
+            }
+        } else {
+            // kmer_index.hpp:516-557
+            from_list = true;
+            nparts = s_len;
+            kind = s_len == 1 ? kExact : (s_len == 2 ? kContig : kMultiSum);
+        }
+    }
+    if (status != KMER_B200_QUERY_OK) {
+        if (lane == 0) {
+            if (PASS == kPassCount) {
+                a.counts[q] = 0;
+                a.status[q] = (uint8_t)status;
+                a.unsorted[q] = 0;
+            } else if (PASS == kPassPresence) {
+                a.present[q] = 0;
+            }
+        }
+        return;
+    }
+
+    // ---- 3. presence of every indexed part + seed bucket -----------------------------------------------
+    Range seed{0, 0};
+    bool all_present = true;
+    uint64_t present_mask = 0;
+    if (kind != kSubK) {
+        for (uint32_t base = 0; base < nparts; base += 32) {
+            const uint32_t j = base + lane;
+            const bool valid = j < nparts;
+            Range rg{0, 0};
+            if (valid) {
+                uint32_t e = e0, o = j * k0;
+                if (from_list) {  // `last_k = current_k` is not cumulative, kmer_index.hpp:526
+                    e = S[j];
+                    o = j ? ix.elem[S[j - 1]].k : 0;
+                }
+                const Element &E = ix.elem[e];
+                const uint32_t key = key_from_window(window64(qw, (uint64_t)o, T.bits), E.k, T.bits, T.sigma);
+                rg = bucket_of(E, key);
+            }
+            if (base == 0) {
+                seed.lo = __shfl_sync(0xFFFFFFFFu, rg.lo, 0);
+                seed.cnt = __shfl_sync(0xFFFFFFFFu, rg.cnt, 0);
+            }
+            const uint32_t here = __ballot_sync(0xFFFFFFFFu, valid && rg.cnt != 0);
+            if (base < 64) present_mask |= (uint64_t)here << base;
+            const uint32_t want = __ballot_sync(0xFFFFFFFFu, valid);
+            if (here != want) {
+                all_present = false;
+                if (PASS != kPassPresence) break;
+            }
+        }
+    }
+    if (PASS == kPassPresence) {
+        if (lane == 0) a.present[q] = present_mask;
+        return;
+    }
+    if (a.present_global != nullptr && kind != kSubK) {
+        // sharded: presence is a property of the whole text (kmer_index.hpp:216-227)
+        const uint64_t full = nparts >= 64 ? ~0ull : ((1ull << nparts) - 1);
+        all_present = (a.present_global[q] & full) == full;
+    }
+    if (!all_present) {  // kmer_index.hpp:224 / :524  return result_t()
+        if (PASS == kPassCount && lane == 0) {
+            a.counts[q] = 0;
+            a.status[q] = KMER_B200_QUERY_OK;
+            a.unsorted[q] = 0;
+        }
+        return;
+    }
+    if (throw_after) {  // all full parts present, then the rest lookup throws
+        if (PASS == kPassCount && lane == 0) {
+            a.counts[q] = 0;
+            a.status[q] = KMER_B200_QUERY_THROW_INVALID_ARGUMENT;
+            a.unsorted[q] = 0;
+        }
+        return;
+    }
+
+    // ---- 4. candidates ---------------------------------------------------------------------------------------
+    const Element &E0 = ix.elem[e0];
+    uint64_t n_hits = 0;
+    bool unsorted = false;
+    if (kind == kSubK) {
+        // get_position_for_all_kmer_with_prefix (kmer_index.hpp:115-148): the buckets of all hashes in
+        // [prefix_hash, prefix_hash + sigma^(k-m)) are one contiguous slab of the sorted position array
+        const uint64_t width = ix.pow_sigma[k0 - m];
+        const uint64_t lo_key = (uint64_t)key_from_window(window64(qw, 0, T.bits), m, T.bits, T.sigma) * width;
+        const uint64_t slo = lower_bound_key(E0, lo_key);
+        const uint64_t shi = lower_bound_key(E0, lo_key + width);
+        if (shi - slo > 1) unsorted = E0.keys[slo] != E0.keys[shi - 1];
+        for (uint64_t c0 = slo; c0 < shi; c0 += 32) {
+            const uint64_t c = c0 + lane;
+            uint32_t p = 0;
+            bool ok = false;
+            if (c < shi) {
+                p = E0.pos[c];
+                ok = (uint64_t)p < ix.owned;
+            }
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, ok);
+            if (PASS == kPassWrite && ok)
+                a.positions[out_base + n_hits + __popc(b & lt_mask)] = p + (uint32_t)ix.global_base;
+            n_hits += __popc(b);
+        }
+        // check_last_kmer (kmer_index.hpp:90-112): starts in the last k-1 positions, where no k-mer starts
+        {
+            const uint64_t p = T.n - k0 + 1 + lane;
+            const bool ok = (uint32_t)lane < k0 - m && p < ix.owned && match_span(T, qw, p, 0, m);
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, ok);
+            if (PASS == kPassWrite && ok)
+                a.positions[out_base + n_hits + __popc(b & lt_mask)] = (uint32_t)p + (uint32_t)ix.global_base;
+            n_hits += __popc(b);
+        }
+    } else {
+        const Element &Es = from_list ? ix.elem[S[0]] : E0;
+        const uint32_t ks = Es.k;
+        for (uint64_t c0 = 0; c0 < seed.cnt; c0 += 32) {
+            const uint64_t c = c0 + lane;
+            uint32_t p = 0;
+            bool ok = false;
+            if (c < seed.cnt) {
+                p = Es.pos[seed.lo + c];
+                ok = (uint64_t)p < ix.owned;
+                if (ok) {
+                    if (kind == kContig) {
+                        ok = match_span(T, qw, (uint64_t)p + ks, ks, m - ks);
+                    } else if (kind == kBuggySingle) {
+                        const uint32_t last = (P - 1) * k0;  // query offset of the last full part
+                        for (uint32_t j = 1; ok && j + 1 < P; ++j) ok = match_span(T, qw, (uint64_t)p + j * k0, last, k0);
+                        if (ok) ok = match_span(T, qw, (uint64_t)p + last, last, k0 + rest);
+                    } else if (kind == kMultiSum) {
+                        // part i is read at query offset k_{i-1} and expected at text offset i*k_0
+                        // (kmer_index.hpp:526 and :535,544)
+                        for (uint32_t i = 1; ok && i < nparts; ++i)
+                            ok = match_span(T, qw, (uint64_t)p + (uint64_t)i * ks, ix.elem[S[i - 1]].k, ix.elem[S[i]].k);
+                    }
+                }
+            }
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, ok);
+            if (PASS == kPassWrite && ok)
+                a.positions[out_base + n_hits + __popc(b & lt_mask)] = p + (uint32_t)ix.global_base;
+            n_hits += __popc(b);
+        }
+    }
+    if (PASS == kPassCount && lane == 0) {
+        a.counts[q] = n_hits;
+        a.status[q] = KMER_B200_QUERY_OK;
+        const bool flag = unsorted && n_hits > 1;
+        a.unsorted[q] = flag ? 1 : 0;
+        if (flag) atomicAdd(a.error_flag + 1, 1u);  // number of segments the sort pass has to visit
+    }
+}
+
+void launch_search(const SearchArgs &args, SearchPass pass, cudaStream_t stream) {
+    if (args.n_queries == 0) return;
+    const uint64_t blocks = (args.n_queries + kSearchWarps - 1) / kSearchWarps;
+    const size_t smem = (size_t)kSearchWarps * args.q_words * sizeof(uint64_t);
+    switch (pass) {
+        case kPassCount:
+            cudaFuncSetAttribute(search_kernel<kPassCount>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            search_kernel<kPassCount><<<(unsigned)blocks, kSearchThreads, smem, stream>>>(args);
+            break;
+        case kPassWrite:
+            cudaFuncSetAttribute(search_kernel<kPassWrite>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            search_kernel<kPassWrite><<<(unsigned)blocks, kSearchThreads, smem, stream>>>(args);
+            break;
+        case kPassPresence:
+            cudaFuncSetAttribute(search_kernel<kPassPresence>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            search_kernel<kPassPresence><<<(unsigned)blocks, kSearchThreads, smem, stream>>>(args);
+            break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// exclusive scan of the per-query counts (u64), in place; counts[Q] receives the total
+// ------------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanPerThread = 16;
+constexpr int kScanBlock = kScanThreads * kScanPerThread;  // 4096
+
+__device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t *total) {
+    __shared__ uint64_t warp_sums[kScanThreads / 32];
+    __shared__ uint64_t block_total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t run = 0;
+        for (int w = 0; w < kScanThreads / 32; ++w) {
+            const uint64_t t = warp_sums[w];
+            warp_sums[w] = run;
+            run += t;
+        }
+        block_total = run;
+    }
+    __syncthreads();
+    const uint64_t r = incl - v + warp_sums[warp];
+    *total = block_total;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const uint64_t *__restrict__ v, uint64_t n,
+                                                                   uint64_t *__restrict__ block_sums) {
+    const uint64_t base = (uint64_t)blockIdx.x * kScanBlock + (uint64_t)threadIdx.x * kScanPerThread;
+    uint64_t s = 0;
+#pragma unroll
+    for (int j = 0; j < kScanPerThread; ++j)
+        if (base + j < n) s += v[base + j];
+    uint64_t total;
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_block_sums_kernel(uint64_t *__restrict__ block_sums, uint64_t n_blocks,
+                                                                       uint64_t *__restrict__ grand_total) {
+    // single CTA: every thread owns a contiguous slice
+    const uint64_t per = (n_blocks + kScanThreads - 1) / kScanThreads;
+    const uint64_t b0 = (uint64_t)threadIdx.x * per;
+    const uint64_t b1 = b0 + per < n_blocks ? b0 + per : n_blocks;
+    uint64_t s = 0;
+    for (uint64_t b = b0; b < b1; ++b) s += block_sums[b];
+    uint64_t total;
+    uint64_t run = block_exclusive_scan(s, &total);
+    for (uint64_t b = b0; b < b1; ++b) {
+        const uint64_t t = block_sums[b];
+        block_sums[b] = run;
+        run += t;
+    }
+    if (threadIdx.x == 0) *grand_total = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(uint64_t *__restrict__ v, uint64_t n,
+                                                                  const uint64_t *__restrict__ block_sums) {
+    const uint64_t base = (uint64_t)blockIdx.x * kScanBlock + (uint64_t)threadIdx.x * kScanPerThread;
+    uint64_t x[kScanPerThread];
+    uint64_t s = 0;
+#pragma unroll
+    for (int j = 0; j < kScanPerThread; ++j) {
+        x[j] = base + j < n ? v[base + j] : 0;
+        s += x[j];
+    }
+    uint64_t total;
+    uint64_t run = block_exclusive_scan(s, &total) + block_sums[blockIdx.x];
+#pragma unroll
+    for (int j = 0; j < kScanPerThread; ++j) {
+        if (base + j < n) v[base + j] = run;
+        run += x[j];
+    }
+}
+
+uint64_t offsets_scan_blocks(uint64_t n_queries) { return (n_queries + kScanBlock - 1) / kScanBlock; }
+
+void launch_offsets_scan(uint64_t *d_counts, uint64_t n_queries, uint64_t *d_block_sums, cudaStream_t stream) {
+    const uint64_t blocks = offsets_scan_blocks(n_queries);
+    if (n_queries == 0) {
+        cudaMemsetAsync(d_counts, 0, sizeof(uint64_t), stream);
+        return;
+    }
+    scan_reduce_kernel<<<(unsigned)blocks, kScanThreads, 0, stream>>>(d_counts, n_queries, d_block_sums);
+    scan_block_sums_kernel<<<1, kScanThreads, 0, stream>>>(d_block_sums, blocks, d_counts + n_queries);
+    scan_apply_kernel<<<(unsigned)blocks, kScanThreads, 0, stream>>>(d_counts, n_queries, d_block_sums);
+}
+
+// ------------------------------------------------------------------------------------------------
+// segment sort: ascending sort of each flagged query's positions (sub-k results spanning several
+// buckets; the reference's std::sort in to_vector, kmer_index_result.hpp:257). One CTA per query.
+// Segments up to kSortTile elements are sorted by a bitonic network in shared memory; longer ones by
+// an in-CTA stable LSD radix sort ping-ponging between `positions` and `tmp`.
+// ------------------------------------------------------------------------------------------------
+struct SegSortSmem {
+    RankSmem rank;
+    uint32_t base[kRadix];
+    uint32_t vals[kSortTile];
+};
+
+__global__ void __launch_bounds__(kSortThreads, 1)
+    segment_sort_kernel(uint32_t *__restrict__ positions, uint32_t *__restrict__ tmp, const uint64_t *__restrict__ offsets,
+                        const uint8_t *__restrict__ unsorted, uint64_t n_queries, uint32_t key_bits) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SegSortSmem &sm = *reinterpret_cast<SegSortSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    for (uint64_t q = blockIdx.x; q < n_queries; q += gridDim.x) {
+        if (!unsorted[q]) continue;
+        const uint64_t seg0 = offsets[q];
+        const uint64_t len = offsets[q + 1] - seg0;
+        if (len < 2) continue;
+        if (len <= (uint64_t)kSortTile) {
+            uint32_t np2 = 1;
+            while (np2 < len) np2 <<= 1;
+            for (uint32_t i = tid; i < np2; i += kSortThreads) sm.vals[i] = i < len ? positions[seg0 + i] : 0xFFFFFFFFu;
+            __syncthreads();
+            for (uint32_t size = 2; size <= np2; size <<= 1) {
+                for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                    for (uint32_t i = tid; i < (np2 >> 1); i += kSortThreads) {
+                        const uint32_t lo = 2 * i - (i & (stride - 1));
+                        const uint32_t hi = lo + stride;
+                        const bool up = (lo & size) == 0;
+                        const uint32_t x = sm.vals[lo], y = sm.vals[hi];
+                        if ((x > y) == up) {
+                            sm.vals[lo] = y;
+                            sm.vals[hi] = x;
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            for (uint32_t i = tid; i < len; i += kSortThreads) positions[seg0 + i] = sm.vals[i];
+            __syncthreads();
+            continue;
+        }
+        // long segment: LSD radix, 8 bits per pass
+        uint32_t *src = positions + seg0, *dst = tmp + seg0;
+        const uint32_t n_pass = (key_bits + 7) / 8;
+        for (uint32_t pass = 0; pass < n_pass; ++pass) {
+            const uint32_t shift = pass * 8;
+            if (tid < kRadix) sm.base[tid] = 0;
+            __syncthreads();
+            for (uint64_t i = tid; i < len; i += kSortThreads) atomicAdd(&sm.base[(src[i] >> shift) & 0xFF], 1u);
+            __syncthreads();
+            if (tid < kRadix) {  // exclusive scan over digits -> running destination of each digit
+                const uint32_t c = sm.base[tid];
+                uint32_t incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                if (lane == 31) sm.rank.warp_sums[warp] = incl;
+                sm.rank.count[tid] = incl - c;
+            }
+            __syncthreads();
+            if (tid < kRadix) {
+                uint32_t b = sm.rank.count[tid];
+                for (int w = 0; w < warp; ++w) b += sm.rank.warp_sums[w];
+                sm.base[tid] = b;
+            }
+            __syncthreads();
+            for (uint64_t t0 = 0; t0 < len; t0 += kSortTile) {
+                const uint32_t count = (uint32_t)min((uint64_t)kSortTile, len - t0);
+                uint32_t val[kSortItems], digit[kSortItems], local_pos[kSortItems];
+#pragma unroll
+                for (int r = 0; r < kSortItems; ++r) {
+                    const uint32_t e = (uint32_t)((warp * kSortItems + r) * 32 + lane);
+                    if (e < count) {
+                        val[r] = src[t0 + e];
+                        digit[r] = (val[r] >> shift) & 0xFF;
+                    } else {
+                        val[r] = 0;
+                        digit[r] = kInvalidDigit;
+                    }
+                }
+                tile_rank(digit, local_pos, sm.rank);
+#pragma unroll
+                for (int r = 0; r < kSortItems; ++r)
+                    if (digit[r] != kInvalidDigit) dst[sm.base[digit[r]] + (local_pos[r] - sm.rank.excl[digit[r]])] = val[r];
+                __syncthreads();
+                if (tid < kRadix) sm.base[tid] += sm.rank.count[tid];
+                __syncthreads();
+            }
+            uint32_t *t = src;
+            src = dst;
+            dst = t;
+        }
+        if (src != positions + seg0)
+            for (uint64_t i = tid; i < len; i += kSortThreads) positions[seg0 + i] = src[i];
+        __syncthreads();
+    }
+}
+
+void launch_segment_sort(uint32_t *d_positions, uint32_t *d_tmp, const uint64_t *d_offsets, const uint8_t *d_unsorted,
+                         uint64_t n_queries, uint32_t key_bits, cudaStream_t stream) {
+    if (n_queries == 0) return;
+    cudaFuncSetAttribute(segment_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SegSortSmem));
+    const uint64_t blocks = n_queries < 148ull * 64 ? n_queries : 148ull * 64;
+    segment_sort_kernel<<<(unsigned)blocks, kSortThreads, sizeof(SegSortSmem), stream>>>(d_positions, d_tmp, d_offsets,
+                                                                                        d_unsorted, n_queries, key_bits);
+}
+
+}  // namespace kb

@@ -1,0 +1,129 @@
+"""GPU parity: the CUDA path (through the C ABI) against the golden fixtures generated from the compiled
+reference, against the C restatement oracle on larger seeded inputs, and against ground truth (CORRECT mode)."""
+import numpy as np
+import pytest
+
+from conftest import assert_results_equal, golden_cases, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def kb():
+    import kmer_index_b200
+    return kmer_index_b200
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_cuda_matches_golden(kb, name):
+    g = load_golden(name)
+    with kb.KmerIndex(g["text"], int(g["sigma"]), g["ks"].tolist()) as ix:
+        got = ix.search_batch(g["q"], g["q_off"]).as_tuple()
+        assert_results_equal(got, (g["r_off"], g["r_pos"], g["r_status"]), skip=g["ub"].astype(bool), label=name)
+        flat, o_ = g["scheme_flat"], 0
+        for m, ln, multi in zip(g["scheme_m"], g["scheme_len"], g["scheme_multi"]):
+            ks, use_multi = ix.scheme(int(m))
+            assert ks == flat[o_:o_ + ln].tolist() and use_multi == bool(multi), (name, int(m))
+            o_ += int(ln)
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_cuda_matches_oracle_on_golden_inputs_including_ub(kb, oracle_mod, name):
+    """On UB-flagged queries the product's defined behaviour is the oracle's ('not equal')."""
+    g = load_golden(name)
+    with kb.KmerIndex(g["text"], int(g["sigma"]), g["ks"].tolist()) as ix, \
+            oracle_mod.Oracle(g["text"], int(g["sigma"]), g["ks"].tolist()) as o:
+        assert_results_equal(ix.search_batch(g["q"], g["q_off"]).as_tuple(), o.search(g["q"], g["q_off"]), label=name)
+
+
+@pytest.mark.parametrize("sigma,ks,n", [(4, [10], 1_000_000), (4, [12], 3_000_000), (4, [5, 7, 9, 11, 13], 500_000),
+                                        (15, [8], 1_000_000), (27, [5], 1_000_000), (4, [16], 2_000_000),
+                                        (4, [1], 5000), (5, [13], 300_000), (4, [3, 9, 16], 200_000)])
+def test_csr_matches_oracle(kb, oracle_mod, sigma, ks, n):
+    """The index itself: positions stably sorted by hash == the reference's buckets in hash order."""
+    from kmer_index_b200 import synth
+    text = synth.random_text(n, sigma, 77 + n % 13)
+    with kb.KmerIndex(text, sigma, ks) as ix, oracle_mod.Oracle(text, sigma, ks) as o:
+        for e in range(len(ks)):
+            h, p = ix.element_arrays(e)
+            oh, op = o.element(e)
+            assert np.array_equal(h.astype(np.uint64), oh), (ks, e)
+            assert np.array_equal(p, op), (ks, e)
+
+
+CASES = [
+    # (label, sigma, ks, n, Q, m_lo, m_hi)
+    ("c1", 4, [10], 1_000_000, 10_000, 10, 10),
+    ("c2", 4, [12], 4_000_000, 20_000, 13, 100),
+    ("c3", 4, [5, 7, 9, 11, 13], 2_000_000, 20_000, 4, 40),
+    ("c4a", 15, [8], 2_000_000, 20_000, 8, 8),
+    ("c4b", 27, [5], 2_000_000, 20_000, 5, 5),
+    ("c5", 4, [16], 4_000_000, 20_000, 16, 64),
+    ("short", 4, [12], 300_000, 4000, 1, 30),
+    ("dna15_mix", 15, [8], 300_000, 6000, 1, 30),
+    ("aa27_mix", 27, [5], 300_000, 6000, 1, 20),
+    ("dna5", 5, [13], 300_000, 4000, 5, 40),
+]
+
+
+@pytest.mark.parametrize("label,sigma,ks,n,Q,m_lo,m_hi", CASES)
+@pytest.mark.parametrize("qkind", ["random", "stress"])
+def test_cuda_matches_oracle(kb, oracle_mod, label, sigma, ks, n, Q, m_lo, m_hi, qkind):
+    from kmer_index_b200 import synth
+    text = synth.random_text(n, sigma, 200 + len(label))
+    if qkind == "random":
+        q, off = synth.random_queries(Q, m_lo, m_hi, sigma, 1234 + len(label))
+    else:
+        q, off = synth.stress_queries(text, Q, m_lo, m_hi, sigma, 4321 + len(label))
+    with kb.KmerIndex(text, sigma, ks) as ix, oracle_mod.Oracle(text, sigma, ks) as o:
+        got = ix.search_batch(q, off).as_tuple()
+        want = o.search(q, off)
+        assert_results_equal(got, want, label=f"{label}/{qkind}")
+        if qkind == "stress":
+            assert want[1].size > 0
+
+
+@pytest.mark.parametrize("sigma,ks,n,m_hi", [(4, [12], 200_000, 60), (4, [5, 7, 9, 11, 13], 200_000, 45),
+                                             (15, [8], 100_000, 30), (4, [16], 100_000, 70)])
+def test_correct_mode_matches_ground_truth(kb, oracle_mod, sigma, ks, n, m_hi):
+    from kmer_index_b200 import synth
+    text = synth.random_text(n, sigma, 31)
+    text[1000:1400] = np.resize(np.array([0, 1, 1], dtype=np.uint8), 400)  # a repetitive stretch
+    q, off = synth.stress_queries(text, 3000, 1, m_hi, sigma, 5150)
+    with kb.KmerIndex(text, sigma, ks, mode=kb.MODE_CORRECT) as ix:
+        got = ix.search_batch(q, off).as_tuple()
+    want = oracle_mod.Oracle.truth(text, q, off)
+    assert_results_equal(got, want, label=f"correct {ks}")
+
+
+def test_edge_cases(kb):
+    text = np.array([0, 1, 2, 3, 0, 1, 2, 3, 0, 1], dtype=np.uint8)
+    with kb.KmerIndex(text, 4, [3]) as ix:
+        # empty batch
+        r = ix.search_batch(np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+        assert len(r) == 0 and r.offsets.tolist() == [0]
+        # empty query inside a batch -> UNDEFINED status, no hits
+        r = ix.search_batch(np.array([0, 1, 2], np.uint8), np.array([0, 0, 3], np.uint64))
+        assert r.status.tolist() == [kb.QUERY_UNDEFINED, kb.QUERY_OK]
+        assert r.positions.tolist() == [0, 4]
+        # query longer than the text
+        r = ix.search_batch(np.resize(text, 30), np.array([0, 30], np.uint64))
+        assert r.status.tolist() == [0] and r.positions.size == 0
+        # end of text: sub-k query matching only in the last k-1 positions (check_last_kmer)
+        assert ix.search(np.array([0, 1], np.uint8)).tolist() == [0, 4, 8]
+        assert ix.search(np.array([1], np.uint8)).tolist() == [1, 5, 9]
+        # text of exactly k symbols
+    with kb.KmerIndex(text[:3], 4, [3]) as ix:
+        assert ix.search(np.array([0, 1, 2], np.uint8)).tolist() == [0]
+        assert ix.search(np.array([1, 2], np.uint8)).tolist() == [1]
+    # invalid rank is an error, not a silent wrong answer
+    with pytest.raises(kb.KmerB200Error):
+        kb.KmerIndex(np.array([0, 1, 2, 7, 1, 1], np.uint8), 4, [3])
+    with pytest.raises(kb.KmerB200Error):
+        kb.KmerIndex(text, 4, [40])   # k >= 64 / log2(sigma)
+    with kb.KmerIndex(text, 4, [3]) as ix:
+        with pytest.raises(kb.KmerB200Error):
+            ix.search(np.array([0, 9, 1], np.uint8))
+        # m > 10000 throws in the reference
+        with pytest.raises(ValueError):
+            ix.search(np.zeros(10001, np.uint8))
