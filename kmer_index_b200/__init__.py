@@ -45,10 +45,25 @@ def choose_best_k(query_lengths: Iterable[int], n_k: int = 4) -> list[int]:
 class BatchResult:
     """CSR result of a batch: offsets[Q+1], positions (ascending per query), status[Q]."""
 
-    def __init__(self, offsets: np.ndarray, positions: np.ndarray, status: np.ndarray):
+    def __init__(self, offsets: np.ndarray, positions: np.ndarray, status: np.ndarray, _owner=None):
         self.offsets = offsets
         self.positions = positions
         self.status = status
+        self._owner = _owner   # (lib, C result handle) when the arrays are views of the pinned C result
+
+    def free(self):
+        """Release the C result (only needed for copy=False results; the arrays become invalid)."""
+        if self._owner is not None:
+            L, r = self._owner
+            self._owner = None
+            self.offsets = self.positions = self.status = None
+            L.kmer_b200_result_free(r)
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
     def __len__(self) -> int:
         return int(self.status.size)
@@ -61,6 +76,45 @@ class BatchResult:
 
     def as_tuple(self):
         return self.offsets, self.positions, self.status
+
+
+class _DevArray:
+    """Zero-copy view of device memory for torch.as_tensor / cupy via __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, n: int, typestr: str, owner):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+        self._owner = owner
+
+
+class DeviceResult:
+    """Result of a device-resident batch; the buffers live in HBM until free()."""
+
+    def __init__(self, L, handle, Q: int):
+        self._L, self._r, self.n_queries = L, handle, Q
+        self.n_positions = int(L.kmer_b200_result_n_positions(handle))
+        self.offsets_ptr = L.kmer_b200_result_offsets(handle) or 0
+        self.positions_ptr = L.kmer_b200_result_positions(handle) or 0
+        self.status_ptr = L.kmer_b200_result_status(handle) or 0
+
+    def offsets(self):      # int64 view of the uint64 offsets (values < 2^63)
+        return _DevArray(self.offsets_ptr, self.n_queries + 1, "<i8", self)
+
+    def positions(self):    # int32 view of the uint32 positions (reinterpret for positions >= 2^31)
+        return _DevArray(self.positions_ptr, self.n_positions, "<i4", self)
+
+    def status(self):
+        return _DevArray(self.status_ptr, self.n_queries, "|u1", self)
+
+    def free(self):
+        if self._r:
+            self._L.kmer_b200_result_free(self._r)
+            self._r = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 class KmerIndex:
@@ -119,24 +173,26 @@ class KmerIndex:
         return self._h
 
     # -- search
-    def search_batch(self, q_ranks, q_offsets, mode: int = MODE_DEFAULT) -> BatchResult:
-        """Batch of queries in host memory -> host CSR result (kmer_index::search + to_vector per query)."""
+    def search_batch(self, q_ranks, q_offsets, mode: int = MODE_DEFAULT, copy: bool = True) -> BatchResult:
+        """Batch of queries in host memory -> host CSR result (kmer_index::search + to_vector per query).
+        copy=False returns views of the library's pinned result buffers (valid until BatchResult.free())."""
         L = self._L
         q = np.ascontiguousarray(np.asarray(q_ranks, dtype=np.uint8))
         off = np.ascontiguousarray(np.asarray(q_offsets, dtype=np.uint64))
         Q = off.size - 1
         r = C.c_void_p()
         _capi.check(L.kmer_b200_search_batch(self._h, q.ctypes.data, off.ctypes.data, Q, mode, C.byref(r)))
-        try:
-            total = L.kmer_b200_result_n_positions(r)
-            offsets = np.ctypeslib.as_array(C.cast(L.kmer_b200_result_offsets(r), _capi.u64p), shape=(Q + 1,)).copy()
-            status = (np.ctypeslib.as_array(C.cast(L.kmer_b200_result_status(r), _capi.u8p), shape=(Q,)).copy()
-                      if Q else np.zeros(0, dtype=np.uint8))
-            positions = (np.ctypeslib.as_array(C.cast(L.kmer_b200_result_positions(r), _capi.u32p),
-                                               shape=(total,)).copy() if total else np.zeros(0, dtype=np.uint32))
-        finally:
-            L.kmer_b200_result_free(r)
-        return BatchResult(offsets, positions, status)
+        total = L.kmer_b200_result_n_positions(r)
+        offsets = np.ctypeslib.as_array(C.cast(L.kmer_b200_result_offsets(r), _capi.u64p), shape=(Q + 1,))
+        status = (np.ctypeslib.as_array(C.cast(L.kmer_b200_result_status(r), _capi.u8p), shape=(Q,))
+                  if Q else np.zeros(0, dtype=np.uint8))
+        positions = (np.ctypeslib.as_array(C.cast(L.kmer_b200_result_positions(r), _capi.u32p), shape=(total,))
+                     if total else np.zeros(0, dtype=np.uint32))
+        if not copy:
+            return BatchResult(offsets, positions, status, _owner=(L, r))
+        out = BatchResult(offsets.copy(), positions.copy(), status.copy())
+        L.kmer_b200_result_free(r)
+        return out
 
     def search(self, query, mode: int = MODE_DEFAULT) -> np.ndarray:
         """kmer_index::search(query).to_vector() for one query; raises ValueError where the reference throws
@@ -150,6 +206,28 @@ class KmerIndex:
         if res.status[0] == QUERY_UNDEFINED:
             raise ValueError("query length 0 or 10000: undefined in the reference")
         return res.positions
+
+    # -- device-resident batches (inputs and result stay in HBM)
+    def _device_call(self, fn, q_ptr: int, off_ptr: int, Q: int, max_len: int, mode: int, *extra) -> "DeviceResult":
+        r = C.c_void_p()
+        _capi.check(fn(self._h, C.c_void_p(q_ptr), C.c_void_p(off_ptr), Q, max_len, mode, *extra, C.byref(r)))
+        return DeviceResult(self._L, r, Q)
+
+    def search_batch_device(self, q_ptr: int, off_ptr: int, Q: int, max_len: int, mode: int = MODE_DEFAULT):
+        return self._device_call(self._L.kmer_b200_search_batch_device, q_ptr, off_ptr, Q, max_len, mode)
+
+    def count_batch_device(self, q_ptr: int, off_ptr: int, Q: int, max_len: int, mode: int = MODE_DEFAULT):
+        return self._device_call(self._L.kmer_b200_count_batch_device, q_ptr, off_ptr, Q, max_len, mode)
+
+    def presence_batch_device(self, q_ptr: int, off_ptr: int, Q: int, max_len: int, present_ptr: int,
+                              mode: int = MODE_DEFAULT) -> None:
+        _capi.check(self._L.kmer_b200_presence_batch_device(self._h, C.c_void_p(q_ptr), C.c_void_p(off_ptr), Q,
+                                                            max_len, mode, C.c_void_p(present_ptr)))
+
+    def search_batch_device_global(self, q_ptr: int, off_ptr: int, Q: int, max_len: int, present_global_ptr: int,
+                                   mode: int = MODE_DEFAULT):
+        return self._device_call(self._L.kmer_b200_search_batch_device_global, q_ptr, off_ptr, Q, max_len, mode,
+                                 C.c_void_p(present_global_ptr))
 
     # -- introspection
     def element_info(self, e: int) -> _capi.ElementInfo:

@@ -81,23 +81,68 @@ struct PairSource {  // materialised (key, value) pairs; vals == nullptr: keys o
 template <typename Source>
 __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(Source src, uint64_t n, uint32_t shift, uint32_t mask,
                                                                   uint32_t *__restrict__ tile_hist) {
-    __shared__ uint32_t hist[kRadix];
+    // one private histogram per warp: shared-memory atomics only collide inside a warp
+    __shared__ uint32_t hist[kSortWarps][kRadix];
     const int tid = threadIdx.x;
-    if (tid < kRadix) hist[tid] = 0;
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) (&hist[0][0])[i] = 0;
     __syncthreads();
     const uint64_t tile_begin = (uint64_t)blockIdx.x * kSortTile;
-    const int lane = tid & 31;
-    const uint32_t lt_mask = (1u << lane) - 1;
-#pragma unroll 4
+    uint32_t d[kSortItems];
+#pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
         const uint64_t i = tile_begin + (uint64_t)r * kSortThreads + tid;
-        const uint32_t d = i < n ? ((src.key(i) >> shift) & mask) : kInvalidDigit;
-        // warp-aggregated shared-memory atomics: one atomic per distinct digit per warp
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
-        if (d != kInvalidDigit && (peers & lt_mask) == 0) atomicAdd(&hist[d], (uint32_t)__popc(peers));
+        d[r] = i < n ? ((src.key(i) >> shift) & mask) : kInvalidDigit;
+    }
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        // a warp whose 32 digits are all equal (low-entropy text) adds once instead of colliding 32 times
+        const uint32_t d0 = __shfl_sync(0xFFFFFFFFu, d[r], 0);
+        if (__all_sync(0xFFFFFFFFu, d[r] == d0)) {
+            if (lane == 0 && d0 != kInvalidDigit) hist[warp][d0] += 32;
+        } else if (d[r] != kInvalidDigit) {
+            atomicAdd(&hist[warp][d[r]], 1u);
+        }
     }
     __syncthreads();
-    if (tid < kRadix) tile_hist[(uint64_t)blockIdx.x * kRadix + tid] = hist[tid];
+    if (tid < kRadix) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) s += hist[w][tid];
+        tile_hist[(uint64_t)blockIdx.x * kRadix + tid] = s;
+    }
+}
+
+// Text-sourced histogram: a thread walks kSortItems CONSECUTIVE positions and slides one 64-bit window over
+// them (one window load serves 64/bits - k + 1 k-mers), instead of re-reading two words per k-mer.
+__global__ void __launch_bounds__(kSortThreads) radix_hist_text_kernel(PackedText text, uint32_t k, uint64_t n,
+                                                                       uint32_t shift, uint32_t mask,
+                                                                       uint32_t *__restrict__ tile_hist) {
+    __shared__ uint32_t hist[kSortWarps][kRadix];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) (&hist[0][0])[i] = 0;
+    __syncthreads();
+    const uint64_t i0 = (uint64_t)blockIdx.x * kSortTile + (uint64_t)tid * kSortItems;
+    const uint32_t per_window = 64 / text.bits - k + 1;  // k-mers fully inside one window
+    uint32_t j = 0;
+    while (j < (uint32_t)kSortItems && i0 + j < n) {
+        uint64_t w = window64(text.words, i0 + j, text.bits);
+        const uint32_t cnt = min(min(per_window, (uint32_t)kSortItems - j), (uint32_t)min((uint64_t)kSortItems, n - i0 - j));
+        for (uint32_t t = 0; t < cnt; ++t) {
+            const uint32_t d = (key_from_window(w, k, text.bits, text.sigma) >> shift) & mask;
+            atomicAdd(&hist[warp][d], 1u);
+            w <<= text.bits;
+        }
+        j += cnt;
+    }
+    __syncthreads();
+    if (tid < kRadix) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) s += hist[w][tid];
+        tile_hist[(uint64_t)blockIdx.x * kRadix + tid] = s;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -176,39 +221,39 @@ struct ScatterSmem {
 };
 
 template <typename Source, bool kWriteKeys>
-__global__ void __launch_bounds__(kSortThreads, 1)
-    radix_scatter_kernel(Source src, uint64_t n, uint32_t shift, uint32_t mask, const uint32_t *__restrict__ tile_base,
-                         uint32_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals) {
+__global__ void __launch_bounds__(kSortThreads, 2)
+    radix_scatter_kernel(Source src, uint64_t n, uint32_t shift, uint32_t mask, uint32_t bits,
+                         const uint32_t *__restrict__ tile_base, uint32_t *__restrict__ out_keys,
+                         uint32_t *__restrict__ out_vals) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScatterSmem &sm = *reinterpret_cast<ScatterSmem *>(smem_raw);
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const uint64_t tile_begin = (uint64_t)blockIdx.x * kSortTile;
     const uint32_t count = (uint32_t)min((uint64_t)kSortTile, n - tile_begin);
+    const uint32_t e0 = (uint32_t)(warp * kSortItems * 32 + lane);
 
-    uint32_t key[kSortItems], val[kSortItems], digit[kSortItems], local_pos[kSortItems];
+    // keys live in registers through the ranking; values reuse the same registers afterwards, which keeps the
+    // kernel at <= 64 registers so two CTAs share an SM and one CTA's loads overlap the other's ranking
+    uint32_t kv[kSortItems], local_pos[kSortItems];
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
-        const uint32_t e = (uint32_t)((warp * kSortItems + r) * 32 + lane);
-        if (e < count) {
-            key[r] = src.key(tile_begin + e);
-            val[r] = src.val(tile_begin + e);
-            digit[r] = (key[r] >> shift) & mask;
-        } else {
-            key[r] = 0;
-            val[r] = 0;
-            digit[r] = kInvalidDigit;
-        }
+        const uint32_t e = e0 + r * 32;
+        kv[r] = e < count ? src.key(tile_begin + e) : 0u;
     }
-    tile_rank(digit, local_pos, sm.rank);
+    tile_rank(kv, count, shift, mask, bits, local_pos, sm.rank);
     if (tid < kRadix) sm.delta[tid] = tile_base[(uint64_t)blockIdx.x * kRadix + tid] - sm.rank.excl[tid];
 #pragma unroll
+    for (int r = 0; r < kSortItems; ++r)
+        if (e0 + r * 32 < count) sm.keys[local_pos[r]] = kv[r];
+#pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
-        if (digit[r] != kInvalidDigit) {
-            sm.keys[local_pos[r]] = key[r];
-            sm.vals[local_pos[r]] = val[r];
-        }
+        const uint32_t e = e0 + r * 32;
+        kv[r] = e < count ? src.val(tile_begin + e) : 0u;
     }
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r)
+        if (e0 + r * 32 < count) sm.vals[local_pos[r]] = kv[r];
     __syncthreads();
 #pragma unroll 4
     for (uint32_t j = tid; j < count; j += kSortThreads) {
@@ -280,8 +325,7 @@ void launch_column_scan(uint32_t *d_tile_hist, uint32_t n_tiles, uint32_t *d_chu
 void launch_hist_text(const PackedText &text, uint32_t k, uint64_t n_kmers, uint32_t shift, uint32_t mask,
                       uint32_t *d_tile_hist, cudaStream_t stream) {
     const uint32_t n_tiles = (uint32_t)((n_kmers + kSortTile - 1) / kSortTile);
-    TextSource src{text, k};
-    radix_hist_kernel<TextSource><<<n_tiles, kSortThreads, 0, stream>>>(src, n_kmers, shift, mask, d_tile_hist);
+    radix_hist_text_kernel<<<n_tiles, kSortThreads, 0, stream>>>(text, k, n_kmers, shift, mask, d_tile_hist);
 }
 
 void launch_hist_pairs(const uint32_t *d_keys, uint64_t n, uint32_t shift, uint32_t mask, uint32_t *d_tile_hist,
@@ -297,7 +341,7 @@ void launch_scatter_text(const PackedText &text, uint32_t k, uint64_t n_kmers, u
     TextSource src{text, k};
     configure_scatter<TextSource, true>();
     radix_scatter_kernel<TextSource, true>
-        <<<n_tiles, kSortThreads, sizeof(ScatterSmem), stream>>>(src, n_kmers, shift, mask, d_tile_base, d_out_keys, d_out_vals);
+        <<<n_tiles, kSortThreads, sizeof(ScatterSmem), stream>>>(src, n_kmers, shift, mask, (uint32_t)__builtin_popcount(mask), d_tile_base, d_out_keys, d_out_vals);
 }
 
 void launch_scatter_pairs(const uint32_t *d_keys, const uint32_t *d_vals, uint64_t n, uint32_t shift, uint32_t mask,
@@ -306,7 +350,7 @@ void launch_scatter_pairs(const uint32_t *d_keys, const uint32_t *d_vals, uint64
     PairSource src{d_keys, d_vals};
     configure_scatter<PairSource, true>();
     radix_scatter_kernel<PairSource, true>
-        <<<n_tiles, kSortThreads, sizeof(ScatterSmem), stream>>>(src, n, shift, mask, d_tile_base, d_out_keys, d_out_vals);
+        <<<n_tiles, kSortThreads, sizeof(ScatterSmem), stream>>>(src, n, shift, mask, (uint32_t)__builtin_popcount(mask), d_tile_base, d_out_keys, d_out_vals);
 }
 
 uint32_t sort_tile_size() { return kSortTile; }

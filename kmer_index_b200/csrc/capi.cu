@@ -170,10 +170,10 @@ struct kmer_b200_index {
     uint32_t *d_flags = nullptr;     // u32[2]: error bits, unsorted-segment count
     uint64_t *h_pinned = nullptr;    // small pinned scratch: [0] total hits, [1] flags
     uint64_t device_bytes = 0;
+    bool reaches_end = true;  // the local slice ends at the end of the whole text
     Profiler prof;
     std::mutex mu;  // serialises searches on one handle (they share the stream and the flag words)
-    // cache of pinned host buffers handed out to host results
-    std::vector<std::pair<void *, size_t>> pinned_cache;
+    size_t h_pinned_cap = 0;
 };
 
 struct kmer_b200_result {
@@ -212,21 +212,29 @@ void dev_free(kmer_b200_index *ix, T *p) {
     if (p) cudaFreeAsync((void *)p, ix->stream);
 }
 
-void *pinned_get(kmer_b200_index *ix, size_t bytes, size_t *cap) {
+// Process-wide cache of pinned host buffers (results handed to the caller, small scratch words). Pinned
+// allocation costs milliseconds, so buffers outlive the index that first asked for them.
+std::mutex g_pinned_mu;
+std::vector<std::pair<void *, size_t>> g_pinned_cache;
+
+void *pinned_get(size_t bytes, size_t *cap) {
     bytes = std::max<size_t>(bytes, 64);
-    size_t best = SIZE_MAX, best_i = SIZE_MAX;
-    for (size_t i = 0; i < ix->pinned_cache.size(); ++i) {
-        const size_t c = ix->pinned_cache[i].second;
-        if (c >= bytes && c < best) {
-            best = c;
-            best_i = i;
+    {
+        std::lock_guard<std::mutex> lock(g_pinned_mu);
+        size_t best = SIZE_MAX, best_i = SIZE_MAX;
+        for (size_t i = 0; i < g_pinned_cache.size(); ++i) {
+            const size_t c = g_pinned_cache[i].second;
+            if (c >= bytes && c < best) {
+                best = c;
+                best_i = i;
+            }
         }
-    }
-    if (best_i != SIZE_MAX && best <= 4 * bytes + (1u << 20)) {
-        void *p = ix->pinned_cache[best_i].first;
-        ix->pinned_cache.erase(ix->pinned_cache.begin() + best_i);
-        *cap = best;
-        return p;
+        if (best_i != SIZE_MAX && best <= 4 * bytes + (1u << 20)) {
+            void *p = g_pinned_cache[best_i].first;
+            g_pinned_cache.erase(g_pinned_cache.begin() + best_i);
+            *cap = best;
+            return p;
+        }
     }
     void *p = nullptr;
     if (cudaMallocHost(&p, bytes) != cudaSuccess) {
@@ -237,13 +245,16 @@ void *pinned_get(kmer_b200_index *ix, size_t bytes, size_t *cap) {
     return p;
 }
 
-void pinned_put(kmer_b200_index *ix, void *p, size_t cap) {
+void pinned_put(void *p, size_t cap) {
     if (!p) return;
-    if (ix->pinned_cache.size() >= 16) {
-        cudaFreeHost(p);
-        return;
+    {
+        std::lock_guard<std::mutex> lock(g_pinned_mu);
+        if (g_pinned_cache.size() < 32) {
+            g_pinned_cache.emplace_back(p, cap);
+            return;
+        }
     }
-    ix->pinned_cache.emplace_back(p, cap);
+    cudaFreeHost(p);
 }
 
 // choose_search_scheme, kmer_index.hpp:407-476, in integer arithmetic.
@@ -435,11 +446,10 @@ int create_impl(const uint8_t *ranks, bool ranks_on_device, uint64_t n, uint32_t
     if (cfg.shard_begin + n > n_total) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "shard exceeds n_total");
     if (n_total >= 0xFFFFFFFFull) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "text too large for 32-bit positions");
     const bool sharded = cfg.n_total != 0 && (cfg.shard_begin != 0 || n != n_total);
-    const bool last_shard = cfg.shard_begin + n == n_total;
+    const bool reaches_end = cfg.shard_begin + n == n_total;  // the slice ends where the text ends
     if (cfg.halo >= n && cfg.halo) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "halo must be smaller than the slice");
-    if (sharded && !last_shard && cfg.halo + 1 < k_max)
+    if (sharded && !reaches_end && cfg.halo + 1 < k_max)
         return fail(KMER_B200_ERR_INVALID_ARGUMENT, "interior shards need halo >= max k - 1");
-    if (last_shard && cfg.halo) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "the last shard has no halo");
 
     int device = cfg.device;
     if (device < 0) {
@@ -466,6 +476,7 @@ int create_impl(const uint8_t *ranks, bool ranks_on_device, uint64_t n, uint32_t
     ix->sigma = sigma;
     ix->bits = bits;
     ix->ks.assign(ks, ks + n_ks);
+    ix->reaches_end = reaches_end;
     auto bail = [&](int code) {
         kmer_b200_destroy(ix);
         return code;
@@ -502,7 +513,8 @@ int create_impl(const uint8_t *ranks, bool ranks_on_device, uint64_t n, uint32_t
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
         }
     }
-    KB_CUDA_OR_BAIL(cudaMallocHost((void **)&ix->h_pinned, 8 * sizeof(uint64_t)));
+    ix->h_pinned = (uint64_t *)pinned_get(8 * sizeof(uint64_t), &ix->h_pinned_cap);
+    if (!ix->h_pinned) return bail(fail(KMER_B200_ERR_OUT_OF_MEMORY, "pinned host allocation failed"));
     KB_OR_BAIL(dev_alloc(ix, &ix->d_flags, 2, true));
     KB_CUDA_OR_BAIL(cudaMemsetAsync(ix->d_flags, 0, 2 * sizeof(uint32_t), ix->stream));
 
@@ -599,7 +611,8 @@ int search_device_impl(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *
 
     // shared-memory reservation per query: ceil(max_len / 32) rounds of bits/2 words, plus two padding words
     uint64_t len_cap = std::max<uint64_t>(max_len, 1);
-    if (ix->host_index.sharded && ix->cfg.halo + 1 < len_cap && ix->host_index.owned != ix->n) len_cap = ix->cfg.halo + 1;
+    // an interior shard can only complete matches of length <= halo + 1 that start in its owned range
+    if (!ix->reaches_end && ix->cfg.halo + 1 < len_cap) len_cap = ix->cfg.halo + 1;
     if (mode == KMER_B200_MODE_REFERENCE_EXACT) len_cap = std::min<uint64_t>(len_cap, kQuerySizeRange);
     const uint32_t q_words = (uint32_t)(((len_cap + 31) / 32) * (ix->bits / 2) + 2);
     if ((size_t)q_words * 8 * 8 > 200 * 1024)
@@ -728,8 +741,7 @@ void kmer_b200_destroy(kmer_b200_index *ix) {
     dev_free(ix, ix->d_index);
     dev_free(ix, ix->d_flags);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
-    for (auto &pc : ix->pinned_cache) cudaFreeHost(pc.first);
-    if (ix->h_pinned) cudaFreeHost(ix->h_pinned);
+    pinned_put(ix->h_pinned, ix->h_pinned_cap);
     for (auto e : ix->prof.pool) cudaEventDestroy(e);
     ix->prof.pool.clear();
     if (ix->own_stream && ix->stream) cudaStreamDestroy(ix->stream);
@@ -830,9 +842,9 @@ int kmer_b200_search_batch(kmer_b200_index *ix, const uint8_t *q_ranks, const ui
     res->on_device = false;
     res->n_queries = Q;
     res->n_positions = dres->n_positions;
-    res->offsets = (uint64_t *)pinned_get(ix, (Q + 1) * sizeof(uint64_t), &res->cap_offsets);
-    res->status = (uint8_t *)pinned_get(ix, Q, &res->cap_status);
-    res->positions = (uint32_t *)pinned_get(ix, res->n_positions * sizeof(uint32_t), &res->cap_positions);
+    res->offsets = (uint64_t *)pinned_get((Q + 1) * sizeof(uint64_t), &res->cap_offsets);
+    res->status = (uint8_t *)pinned_get(Q, &res->cap_status);
+    res->positions = (uint32_t *)pinned_get(res->n_positions * sizeof(uint32_t), &res->cap_positions);
     if (!res->offsets || !res->status || !res->positions) {
         kmer_b200_result_free(dres);
         kmer_b200_result_free(res);
@@ -869,9 +881,9 @@ void kmer_b200_result_free(kmer_b200_result *r) {
         dev_free(ix, r->positions);
         dev_free(ix, r->status);
     } else {
-        pinned_put(ix, r->offsets, r->cap_offsets);
-        pinned_put(ix, r->positions, r->cap_positions);
-        pinned_put(ix, r->status, r->cap_status);
+        pinned_put(r->offsets, r->cap_offsets);
+        pinned_put(r->positions, r->cap_positions);
+        pinned_put(r->status, r->cap_status);
     }
     delete r;
 }

@@ -29,25 +29,44 @@ struct RankSmem {
     uint32_t warp_sums[kRadix / 32];
 };
 
-// Stable rank of this thread's kSortItems digits inside the tile. On return
-//   local_pos[r] = position of item r in the tile's digit-sorted order (undefined for invalid items),
+// Lanes of the warp holding the same digit as this lane (invalid lanes excluded). Built from one ballot per
+// digit bit: the hardware match.any instruction is several times slower than 8 votes on sm_100a.
+__device__ __forceinline__ uint32_t match_digit(uint32_t d, bool valid, uint32_t bits) {
+    uint32_t peers = __ballot_sync(0xFFFFFFFFu, valid);
+#pragma unroll
+    for (uint32_t b = 0; b < (uint32_t)kRadixBitsMax; ++b) {
+        if (b < bits) {
+            const bool bit = (d >> b) & 1u;
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, bit);
+            peers &= bit ? m : ~m;
+        }
+    }
+    return peers;
+}
+
+// Stable rank of this thread's kSortItems keys inside the tile by digit (key >> shift) & mask.
+// Item r of this thread is tile element ((warp * kSortItems + r) * 32 + lane); elements >= count are ignored.
+// On return
+//   local_pos[r] = position of item r in the tile's digit-sorted order (undefined for ignored items),
 //   sm.count[d]  = number of items with digit d, sm.excl[d] = exclusive prefix of count.
 // All kSortThreads threads must call. Ends with a __syncthreads().
-__device__ __forceinline__ void tile_rank(const uint32_t (&digit)[kSortItems], uint32_t (&local_pos)[kSortItems],
+__device__ __forceinline__ void tile_rank(const uint32_t (&key)[kSortItems], uint32_t count, uint32_t shift,
+                                          uint32_t mask, uint32_t bits, uint32_t (&local_pos)[kSortItems],
                                           RankSmem &sm) {
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
     const uint32_t lt_mask = (1u << lane) - 1;
+    const uint32_t e0 = (uint32_t)(warp * kSortItems * 32 + lane);
 
     for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) (&sm.warp_cnt[0][0])[i] = 0;
     __syncthreads();
 
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
-        const uint32_t d = digit[r];
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
-        const bool valid = d != kInvalidDigit;
+        const uint32_t d = (key[r] >> shift) & mask;
+        const bool valid = e0 + r * 32 < count;
+        const uint32_t peers = match_digit(d, valid, bits);
         uint32_t pre = 0;
         if (valid) pre = sm.warp_cnt[warp][d];
         __syncwarp();
@@ -86,8 +105,8 @@ __device__ __forceinline__ void tile_rank(const uint32_t (&digit)[kSortItems], u
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
-        const uint32_t d = digit[r];
-        if (d != kInvalidDigit) local_pos[r] += sm.excl[d] + sm.warp_cnt[warp][d];
+        const uint32_t d = (key[r] >> shift) & mask;
+        if (e0 + r * 32 < count) local_pos[r] += sm.excl[d] + sm.warp_cnt[warp][d];
     }
     __syncthreads();
 }

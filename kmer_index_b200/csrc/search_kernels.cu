@@ -547,22 +547,19 @@ __global__ void __launch_bounds__(kSortThreads, 1)
             __syncthreads();
             for (uint64_t t0 = 0; t0 < len; t0 += kSortTile) {
                 const uint32_t count = (uint32_t)min((uint64_t)kSortTile, len - t0);
-                uint32_t val[kSortItems], digit[kSortItems], local_pos[kSortItems];
+                uint32_t val[kSortItems], local_pos[kSortItems];
 #pragma unroll
                 for (int r = 0; r < kSortItems; ++r) {
                     const uint32_t e = (uint32_t)((warp * kSortItems + r) * 32 + lane);
-                    if (e < count) {
-                        val[r] = src[t0 + e];
-                        digit[r] = (val[r] >> shift) & 0xFF;
-                    } else {
-                        val[r] = 0;
-                        digit[r] = kInvalidDigit;
-                    }
+                    val[r] = e < count ? src[t0 + e] : 0u;
                 }
-                tile_rank(digit, local_pos, sm.rank);
+                tile_rank(val, count, shift, 0xFFu, 8, local_pos, sm.rank);
 #pragma unroll
-                for (int r = 0; r < kSortItems; ++r)
-                    if (digit[r] != kInvalidDigit) dst[sm.base[digit[r]] + (local_pos[r] - sm.rank.excl[digit[r]])] = val[r];
+                for (int r = 0; r < kSortItems; ++r) {
+                    const uint32_t e = (uint32_t)((warp * kSortItems + r) * 32 + lane);
+                    const uint32_t d = (val[r] >> shift) & 0xFF;
+                    if (e < count) dst[sm.base[d] + (local_pos[r] - sm.rank.excl[d])] = val[r];
+                }
                 __syncthreads();
                 if (tid < kRadix) sm.base[tid] += sm.rank.count[tid];
                 __syncthreads();
