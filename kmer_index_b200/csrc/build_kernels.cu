@@ -59,20 +59,42 @@ void launch_pack_text(const uint8_t *d_ranks, uint64_t n, uint32_t bits, uint32_
 // ------------------------------------------------------------------------------------------------
 // key sources
 // ------------------------------------------------------------------------------------------------
+// A source hands a thread its kSortItems tile items: item r is element first + 32 * r; `avail` = number of
+// valid elements starting at `first` (only consulted when FULL is false).
 struct TextSource {  // key(i) = hash of the k-mer starting at symbol i; value(i) = i
     PackedText text;
     uint32_t k;
     __device__ __forceinline__ uint32_t key(uint64_t i) const {
         return key_from_window(window64(text.words, i, text.bits), k, text.bits, text.sigma);
     }
-    __device__ __forceinline__ uint32_t val(uint64_t i) const { return (uint32_t)i; }
+    template <bool FULL>
+    __device__ __forceinline__ void load_keys(uint64_t first, uint32_t avail, uint32_t (&out)[kSortItems]) const {
+#pragma unroll
+        for (int r = 0; r < kSortItems; ++r) out[r] = (FULL || (uint32_t)(r * 32) < avail) ? key(first + r * 32) : 0u;
+    }
+    template <bool FULL>
+    __device__ __forceinline__ void load_vals(uint64_t first, uint32_t, uint32_t (&out)[kSortItems]) const {
+#pragma unroll
+        for (int r = 0; r < kSortItems; ++r) out[r] = (uint32_t)first + r * 32;
+    }
 };
 
-struct PairSource {  // materialised (key, value) pairs; vals == nullptr: keys only
+struct PairSource {  // materialised (key, value) pairs
     const uint32_t *keys;
     const uint32_t *vals;
     __device__ __forceinline__ uint32_t key(uint64_t i) const { return keys[i]; }
-    __device__ __forceinline__ uint32_t val(uint64_t i) const { return vals[i]; }
+    template <bool FULL>
+    __device__ __forceinline__ void load_keys(uint64_t first, uint32_t avail, uint32_t (&out)[kSortItems]) const {
+        const uint32_t *p = keys + first;  // one base pointer; the unrolled loads use immediate offsets
+#pragma unroll
+        for (int r = 0; r < kSortItems; ++r) out[r] = (FULL || (uint32_t)(r * 32) < avail) ? p[r * 32] : 0u;
+    }
+    template <bool FULL>
+    __device__ __forceinline__ void load_vals(uint64_t first, uint32_t avail, uint32_t (&out)[kSortItems]) const {
+        const uint32_t *p = vals + first;
+#pragma unroll
+        for (int r = 0; r < kSortItems; ++r) out[r] = (FULL || (uint32_t)(r * 32) < avail) ? p[r * 32] : 0u;
+    }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -220,48 +242,62 @@ struct ScatterSmem {
     uint32_t vals[kSortTile];
 };
 
-template <typename Source, bool kWriteKeys>
-__global__ void __launch_bounds__(kSortThreads, 2)
-    radix_scatter_kernel(Source src, uint64_t n, uint32_t shift, uint32_t mask, uint32_t bits,
-                         const uint32_t *__restrict__ tile_base, uint32_t *__restrict__ out_keys,
-                         uint32_t *__restrict__ out_vals) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    ScatterSmem &sm = *reinterpret_cast<ScatterSmem *>(smem_raw);
+template <typename Source, int BITS, bool FULL>
+__device__ __forceinline__ void scatter_tile(const Source &src, uint64_t tile_begin, uint32_t count, uint32_t shift,
+                                             uint32_t mask, const uint32_t *__restrict__ tile_base_row,
+                                             uint32_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals,
+                                             ScatterSmem &sm) {
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const uint64_t tile_begin = (uint64_t)blockIdx.x * kSortTile;
-    const uint32_t count = (uint32_t)min((uint64_t)kSortTile, n - tile_begin);
     const uint32_t e0 = (uint32_t)(warp * kSortItems * 32 + lane);
 
     // keys live in registers through the ranking; values reuse the same registers afterwards, which keeps the
     // kernel at <= 64 registers so two CTAs share an SM and one CTA's loads overlap the other's ranking
     uint32_t kv[kSortItems], local_pos[kSortItems];
-#pragma unroll
-    for (int r = 0; r < kSortItems; ++r) {
-        const uint32_t e = e0 + r * 32;
-        kv[r] = e < count ? src.key(tile_begin + e) : 0u;
-    }
-    tile_rank(kv, count, shift, mask, bits, local_pos, sm.rank);
-    if (tid < kRadix) sm.delta[tid] = tile_base[(uint64_t)blockIdx.x * kRadix + tid] - sm.rank.excl[tid];
+    src.template load_keys<FULL>(tile_begin + e0, count - min(count, e0), kv);
+    tile_rank<BITS, FULL>(kv, count, shift, mask, local_pos, sm.rank);
+    if (tid < kRadix) sm.delta[tid] = tile_base_row[tid] - sm.rank.excl[tid];
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r)
-        if (e0 + r * 32 < count) sm.keys[local_pos[r]] = kv[r];
-#pragma unroll
-    for (int r = 0; r < kSortItems; ++r) {
-        const uint32_t e = e0 + r * 32;
-        kv[r] = e < count ? src.val(tile_begin + e) : 0u;
-    }
+        if (FULL || e0 + r * 32 < count) sm.keys[local_pos[r]] = kv[r];
+    src.template load_vals<FULL>(tile_begin + e0, count - min(count, e0), kv);
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r)
-        if (e0 + r * 32 < count) sm.vals[local_pos[r]] = kv[r];
+        if (FULL || e0 + r * 32 < count) sm.vals[local_pos[r]] = kv[r];
     __syncthreads();
-#pragma unroll 4
-    for (uint32_t j = tid; j < count; j += kSortThreads) {
-        const uint32_t kk = sm.keys[j];
-        const uint32_t dst = sm.delta[(kk >> shift) & mask] + j;  // mod 2^32; true destination < n < 2^32
-        if (kWriteKeys) out_keys[dst] = kk;
-        out_vals[dst] = sm.vals[j];
+    if (FULL) {
+#pragma unroll
+        for (int it = 0; it < kSortItems; ++it) {
+            const uint32_t j = it * kSortThreads + tid;
+            const uint32_t kk = sm.keys[j];
+            const uint32_t dst = sm.delta[(kk >> shift) & mask] + j;  // mod 2^32; true destination < n < 2^32
+            out_keys[dst] = kk;
+            out_vals[dst] = sm.vals[j];
+        }
+    } else {
+        for (uint32_t j = tid; j < count; j += kSortThreads) {
+            const uint32_t kk = sm.keys[j];
+            const uint32_t dst = sm.delta[(kk >> shift) & mask] + j;
+            out_keys[dst] = kk;
+            out_vals[dst] = sm.vals[j];
+        }
     }
+}
+
+template <typename Source, int BITS>
+__global__ void __launch_bounds__(kSortThreads, 2)
+    radix_scatter_kernel(const Source src, uint64_t n, uint32_t shift, uint32_t mask,
+                         const uint32_t *__restrict__ tile_base, uint32_t *__restrict__ out_keys,
+                         uint32_t *__restrict__ out_vals) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ScatterSmem &sm = *reinterpret_cast<ScatterSmem *>(smem_raw);
+    const uint64_t tile_begin = (uint64_t)blockIdx.x * kSortTile;
+    const uint32_t count = (uint32_t)min((uint64_t)kSortTile, n - tile_begin);
+    const uint32_t *row = tile_base + (uint64_t)blockIdx.x * kRadix;
+    if (count == (uint32_t)kSortTile)
+        scatter_tile<Source, BITS, true>(src, tile_begin, count, shift, mask, row, out_keys, out_vals, sm);
+    else
+        scatter_tile<Source, BITS, false>(src, tile_begin, count, shift, mask, row, out_keys, out_vals, sm);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -308,11 +344,30 @@ void launch_directory_fill(const uint32_t *d_keys, uint64_t n_kmers, uint32_t sh
 // ------------------------------------------------------------------------------------------------
 size_t scatter_smem_bytes() { return sizeof(ScatterSmem); }
 
-template <typename Source, bool kWriteKeys>
-static void configure_scatter() {
+template <typename Source, int BITS>
+static void launch_scatter_bits(const Source &src, uint64_t n, uint32_t shift, uint32_t mask, const uint32_t *d_tile_base,
+                                uint32_t *d_out_keys, uint32_t *d_out_vals, cudaStream_t stream) {
+    const uint32_t n_tiles = (uint32_t)((n + kSortTile - 1) / kSortTile);
     // per-device attribute; cheap enough to set on every launch
-    cudaFuncSetAttribute(radix_scatter_kernel<Source, kWriteKeys>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(radix_scatter_kernel<Source, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)sizeof(ScatterSmem));
+    radix_scatter_kernel<Source, BITS>
+        <<<n_tiles, kSortThreads, sizeof(ScatterSmem), stream>>>(src, n, shift, mask, d_tile_base, d_out_keys, d_out_vals);
+}
+
+// the vote loop is unrolled for the digit width (rounded up to one of the instantiated widths)
+template <typename Source>
+static void launch_scatter(const Source &src, uint64_t n, uint32_t shift, uint32_t mask, const uint32_t *d_tile_base,
+                           uint32_t *d_out_keys, uint32_t *d_out_vals, cudaStream_t stream) {
+    const int bits = __builtin_popcount(mask);
+    if (bits <= 5)
+        launch_scatter_bits<Source, 5>(src, n, shift, mask, d_tile_base, d_out_keys, d_out_vals, stream);
+    else if (bits == 6)
+        launch_scatter_bits<Source, 6>(src, n, shift, mask, d_tile_base, d_out_keys, d_out_vals, stream);
+    else if (bits == 7)
+        launch_scatter_bits<Source, 7>(src, n, shift, mask, d_tile_base, d_out_keys, d_out_vals, stream);
+    else
+        launch_scatter_bits<Source, 8>(src, n, shift, mask, d_tile_base, d_out_keys, d_out_vals, stream);
 }
 
 void launch_column_scan(uint32_t *d_tile_hist, uint32_t n_tiles, uint32_t *d_chunk_sums, cudaStream_t stream) {
@@ -337,20 +392,12 @@ void launch_hist_pairs(const uint32_t *d_keys, uint64_t n, uint32_t shift, uint3
 
 void launch_scatter_text(const PackedText &text, uint32_t k, uint64_t n_kmers, uint32_t shift, uint32_t mask,
                          const uint32_t *d_tile_base, uint32_t *d_out_keys, uint32_t *d_out_vals, cudaStream_t stream) {
-    const uint32_t n_tiles = (uint32_t)((n_kmers + kSortTile - 1) / kSortTile);
-    TextSource src{text, k};
-    configure_scatter<TextSource, true>();
-    radix_scatter_kernel<TextSource, true>
-        <<<n_tiles, kSortThreads, sizeof(ScatterSmem), stream>>>(src, n_kmers, shift, mask, (uint32_t)__builtin_popcount(mask), d_tile_base, d_out_keys, d_out_vals);
+    launch_scatter(TextSource{text, k}, n_kmers, shift, mask, d_tile_base, d_out_keys, d_out_vals, stream);
 }
 
 void launch_scatter_pairs(const uint32_t *d_keys, const uint32_t *d_vals, uint64_t n, uint32_t shift, uint32_t mask,
                           const uint32_t *d_tile_base, uint32_t *d_out_keys, uint32_t *d_out_vals, cudaStream_t stream) {
-    const uint32_t n_tiles = (uint32_t)((n + kSortTile - 1) / kSortTile);
-    PairSource src{d_keys, d_vals};
-    configure_scatter<PairSource, true>();
-    radix_scatter_kernel<PairSource, true>
-        <<<n_tiles, kSortThreads, sizeof(ScatterSmem), stream>>>(src, n, shift, mask, (uint32_t)__builtin_popcount(mask), d_tile_base, d_out_keys, d_out_vals);
+    launch_scatter(PairSource{d_keys, d_vals}, n, shift, mask, d_tile_base, d_out_keys, d_out_vals, stream);
 }
 
 uint32_t sort_tile_size() { return kSortTile; }

@@ -29,35 +29,45 @@ struct RankSmem {
     uint32_t warp_sums[kRadix / 32];
 };
 
-// Lanes of the warp holding the same digit as this lane (invalid lanes excluded). Built from one ballot per
-// digit bit: the hardware match.any instruction is several times slower than 8 votes on sm_100a.
-__device__ __forceinline__ uint32_t match_digit(uint32_t d, bool valid, uint32_t bits) {
-    uint32_t peers = __ballot_sync(0xFFFFFFFFu, valid);
+// Lanes of the warp holding the same digit as this lane, restricted to `peers` on entry. One vote per digit
+// bit: the hardware match.any instruction is several times slower than 8 votes on sm_100a, and the ALU pipe
+// (one warp instruction per two cycles per SM sub-partition) is what bounds the scatter passes, so every bit
+// costs exactly three ALU instructions here: test, conditional complement, and.
+template <int BITS>
+__device__ __forceinline__ uint32_t match_digit(uint32_t d, uint32_t peers) {
 #pragma unroll
-    for (uint32_t b = 0; b < (uint32_t)kRadixBitsMax; ++b) {
-        if (b < bits) {
-            const bool bit = (d >> b) & 1u;
-            const uint32_t m = __ballot_sync(0xFFFFFFFFu, bit);
-            peers &= bit ? m : ~m;
-        }
+    for (int b = 0; b < BITS; ++b) {
+        asm volatile(
+            "{\n"
+            " .reg .pred p;\n"
+            " .reg .b32 m;\n"
+            " and.b32 m, %1, %2;\n"
+            " setp.ne.u32 p, m, 0;\n"
+            " vote.sync.ballot.b32 m, p, 0xffffffff;\n"
+            " @!p not.b32 m, m;\n"
+            " and.b32 %0, %0, m;\n"
+            "}\n"
+            : "+r"(peers)
+            : "r"(d), "r"(1u << b));
     }
     return peers;
 }
 
-// Stable rank of this thread's kSortItems keys inside the tile by digit (key >> shift) & mask.
-// Item r of this thread is tile element ((warp * kSortItems + r) * 32 + lane); elements >= count are ignored.
-// On return
+// Stable rank of this thread's kSortItems keys inside the tile by digit (key >> shift) & mask (BITS >= the
+// digit width). Item r of this thread is tile element ((warp * kSortItems + r) * 32 + lane); with FULL = false
+// elements >= count are ignored. On return
 //   local_pos[r] = position of item r in the tile's digit-sorted order (undefined for ignored items),
 //   sm.count[d]  = number of items with digit d, sm.excl[d] = exclusive prefix of count.
 // All kSortThreads threads must call. Ends with a __syncthreads().
+template <int BITS, bool FULL>
 __device__ __forceinline__ void tile_rank(const uint32_t (&key)[kSortItems], uint32_t count, uint32_t shift,
-                                          uint32_t mask, uint32_t bits, uint32_t (&local_pos)[kSortItems],
-                                          RankSmem &sm) {
+                                          uint32_t mask, uint32_t (&local_pos)[kSortItems], RankSmem &sm) {
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
     const uint32_t lt_mask = (1u << lane) - 1;
     const uint32_t e0 = (uint32_t)(warp * kSortItems * 32 + lane);
+    uint32_t *my_cnt = sm.warp_cnt[warp];
 
     for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) (&sm.warp_cnt[0][0])[i] = 0;
     __syncthreads();
@@ -65,18 +75,19 @@ __device__ __forceinline__ void tile_rank(const uint32_t (&key)[kSortItems], uin
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
         const uint32_t d = (key[r] >> shift) & mask;
-        const bool valid = e0 + r * 32 < count;
-        const uint32_t peers = match_digit(d, valid, bits);
+        const bool valid = FULL || e0 + r * 32 < count;
+        const uint32_t peers = match_digit<BITS>(d, FULL ? 0xFFFFFFFFu : __ballot_sync(0xFFFFFFFFu, valid));
+        const uint32_t lower = peers & lt_mask;
         uint32_t pre = 0;
-        if (valid) pre = sm.warp_cnt[warp][d];
+        if (valid) pre = my_cnt[d];
         __syncwarp();
-        if (valid && (peers & lt_mask) == 0) sm.warp_cnt[warp][d] = pre + __popc(peers);
+        if (valid && lower == 0) my_cnt[d] = pre + __popc(peers);
         __syncwarp();
-        local_pos[r] = pre + __popc(peers & lt_mask);
+        local_pos[r] = pre + __popc(lower);
     }
     __syncthreads();
 
-    // per digit: exclusive prefix over warps, total count
+    // per digit: exclusive prefix over warps, total count, exclusive prefix over digits
     if (tid < kRadix) {
         uint32_t run = 0;
 #pragma unroll
@@ -86,7 +97,6 @@ __device__ __forceinline__ void tile_rank(const uint32_t (&key)[kSortItems], uin
             run += c;
         }
         sm.count[tid] = run;
-        // exclusive scan of counts over the 256 digits (8 warps)
         uint32_t incl = run;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -98,15 +108,18 @@ __device__ __forceinline__ void tile_rank(const uint32_t (&key)[kSortItems], uin
     }
     __syncthreads();
     if (tid < kRadix) {
-        uint32_t base = 0;
+        uint32_t base = sm.excl[tid];
         for (int w = 0; w < warp; ++w) base += sm.warp_sums[w];
-        sm.excl[tid] += base;
+        sm.excl[tid] = base;
+        // fold the digit base into the warp prefixes: one lookup per item below instead of two
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) sm.warp_cnt[w][tid] += base;
     }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
         const uint32_t d = (key[r] >> shift) & mask;
-        if (e0 + r * 32 < count) local_pos[r] += sm.excl[d] + sm.warp_cnt[warp][d];
+        if (FULL || e0 + r * 32 < count) local_pos[r] += my_cnt[d];
     }
     __syncthreads();
 }

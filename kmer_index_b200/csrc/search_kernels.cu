@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(kSortThreads, 1)
                     const uint32_t e = (uint32_t)((warp * kSortItems + r) * 32 + lane);
                     val[r] = e < count ? src[t0 + e] : 0u;
                 }
-                tile_rank(val, count, shift, 0xFFu, 8, local_pos, sm.rank);
+                tile_rank<8, false>(val, count, shift, 0xFFu, local_pos, sm.rank);
 #pragma unroll
                 for (int r = 0; r < kSortItems; ++r) {
                     const uint32_t e = (uint32_t)((warp * kSortItems + r) * 32 + lane);
