@@ -149,6 +149,10 @@ int kmer_b200_element_hashes(kmer_b200_index *index, uint32_t element, uint32_t 
    Returns the number of summands and writes up to cap of them. */
 uint64_t kmer_b200_scheme(const kmer_b200_index *index, uint64_t m, uint32_t *out_ks, uint64_t cap, int *use_multi);
 
+/* The same row computed on the host from the ks alone (no device, no index needed). */
+uint64_t kmer_b200_scheme_for_ks(const uint32_t *ks, uint32_t n_ks, uint64_t m, uint32_t *out_ks, uint64_t cap,
+                                 int *use_multi);
+
 /* Per-kernel accounting since the last reset: launches, device time (CUDA events on the launching
    stream; only when cfg.profile = 1) and the algorithmic bytes the kernel must move. */
 typedef struct kmer_b200_kernel_stat {

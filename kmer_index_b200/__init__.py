@@ -16,7 +16,7 @@ from . import _capi
 from ._capi import (MODE_CORRECT, MODE_DEFAULT, MODE_REFERENCE_EXACT, QUERY_OK, QUERY_THROW_INVALID_ARGUMENT,
                     QUERY_TOO_LONG_FOR_SHARD, QUERY_UNDEFINED, KmerB200Error)
 
-__all__ = ["KmerIndex", "make_kmer_index", "BatchResult", "fast_pow", "kmer_hash", "choose_best_k",
+__all__ = ["KmerIndex", "make_kmer_index", "BatchResult", "fast_pow", "kmer_hash", "choose_best_k", "scheme_for_ks",
            "MODE_REFERENCE_EXACT", "MODE_CORRECT", "KmerB200Error", "ALPHABETS"]
 
 # alphabet sizes of the seqan3 alphabets the reference is used with
@@ -40,6 +40,17 @@ def choose_best_k(query_lengths: Iterable[int], n_k: int = 4) -> list[int]:
     out = np.zeros(16, dtype=np.uint64)
     n = _capi.lib().kmer_b200_choose_best_k(a.ctypes.data_as(_capi.u64p), a.size, n_k, out.ctypes.data_as(_capi.u64p))
     return [int(x) for x in out[:n]]
+
+
+def scheme_for_ks(ks: Sequence[int], m: int):
+    """Row m of the scheme table the reference builds in choose_search_scheme (kmer_index.hpp:407-476):
+    (_optimal_nk_sum[m], _use_multi_search_scheme[m]). Host-only."""
+    ks_a = np.asarray(list(ks), dtype=np.uint32)
+    out = np.zeros(4096, dtype=np.uint32)
+    multi = C.c_int(0)
+    n = _capi.lib().kmer_b200_scheme_for_ks(ks_a.ctypes.data_as(_capi.u32p), ks_a.size, m,
+                                            out.ctypes.data_as(_capi.u32p), out.size, C.byref(multi))
+    return [int(x) for x in out[:n]], bool(multi.value)
 
 
 class BatchResult:

@@ -259,7 +259,13 @@ void pinned_put(void *p, size_t cap) {
 
 // choose_search_scheme, kmer_index.hpp:407-476, in integer arithmetic.
 // sum lists are stored as chains (last summand + previous length) and flattened at the end.
-void build_scheme(kmer_b200_index *ix) {
+struct SchemeHost {
+    std::vector<uint32_t> ks;  // template order
+    std::vector<uint32_t> sum_off;
+    std::vector<uint8_t> sum_elem, use_multi;
+};
+
+void build_scheme(SchemeHost *ix) {
     const uint32_t R = kb::kQuerySizeRange;
     std::vector<uint32_t> all_ks(ix->ks);
     std::sort(all_ks.begin(), all_ks.end(), [](uint32_t a, uint32_t b) { return a > b; });  // :410
@@ -538,7 +544,14 @@ int create_impl(const uint8_t *ranks, bool ranks_on_device, uint64_t n, uint32_t
     for (uint32_t i = 0; i < n_ks; ++i) KB_OR_BAIL(build_element(ix, ks[i], ix->elems[i]));
 
     // ---- scheme tables
-    build_scheme(ix);
+    {
+        SchemeHost sh;
+        sh.ks = ix->ks;
+        build_scheme(&sh);
+        ix->sum_off.swap(sh.sum_off);
+        ix->sum_elem.swap(sh.sum_elem);
+        ix->use_multi.swap(sh.use_multi);
+    }
     KB_OR_BAIL(dev_alloc(ix, &ix->d_sum_off, ix->sum_off.size(), true));
     KB_OR_BAIL(dev_alloc(ix, &ix->d_sum_elem, ix->sum_elem.size(), true));
     KB_OR_BAIL(dev_alloc(ix, &ix->d_use_multi, ix->use_multi.size(), true));
@@ -926,6 +939,26 @@ uint64_t kmer_b200_scheme(const kmer_b200_index *ix, uint64_t m, uint32_t *out_k
     const uint32_t o = ix->sum_off[m], len = ix->sum_off[m + 1] - o;
     for (uint32_t i = 0; i < len && i < cap && out_ks; ++i) out_ks[i] = ix->ks[ix->sum_elem[o + i]];
     if (use_multi) *use_multi = ix->use_multi[m];
+    return len;
+}
+
+uint64_t kmer_b200_scheme_for_ks(const uint32_t *ks, uint32_t n_ks, uint64_t m, uint32_t *out_ks, uint64_t cap,
+                                 int *use_multi) {
+    if (!ks || n_ks == 0 || n_ks > (uint32_t)kb::kMaxElements || m >= kb::kQuerySizeRange) return 0;
+    for (uint32_t i = 0; i < n_ks; ++i)
+        if (ks[i] == 0 || ks[i] > 63) return 0;
+    // the table only depends on the ks; cache the last one built (tests walk m for a fixed ks)
+    static std::mutex mu;
+    static SchemeHost cached;
+    std::lock_guard<std::mutex> lock(mu);
+    if (cached.ks != std::vector<uint32_t>(ks, ks + n_ks)) {
+        cached = SchemeHost();
+        cached.ks.assign(ks, ks + n_ks);
+        build_scheme(&cached);
+    }
+    const uint32_t o = cached.sum_off[m], len = cached.sum_off[m + 1] - o;
+    for (uint32_t i = 0; i < len && i < cap && out_ks; ++i) out_ks[i] = cached.ks[cached.sum_elem[o + i]];
+    if (use_multi) *use_multi = cached.use_multi[m];
     return len;
 }
 

@@ -49,6 +49,14 @@ def fold_presence(gathered):
     return acc
 
 
+def all_gather_fold(mask, world: int, dist):
+    """all_gather the per-shard presence masks [Q] and OR them (NCCL has no bitwise-OR reduction)."""
+    import torch
+    flat = torch.empty(world * mask.numel(), dtype=mask.dtype, device=mask.device)
+    dist.all_gather_into_tensor(flat, mask)
+    return fold_presence(flat.view(world, mask.numel()))
+
+
 def merge_offsets(counts):
     """counts[world, Q] (hits of query q on shard r) -> (global offsets [Q+1], write base [world, Q]):
     shard r's hits of query q go to global_offsets[q] + sum_{r' < r} counts[r', q]."""
@@ -110,9 +118,7 @@ def _global_presence(ix, q_ptr, off_ptr, Q, max_len, world, dev):
     ix.presence_batch_device(q_ptr, off_ptr, Q, max_len, present.data_ptr())
     max_parts = max_len // min(ix.ks) + 1
     narrow = present.to(torch.uint8) if max_parts <= 8 else present   # fewer bytes over NVLink
-    gathered = torch.empty((world,) + narrow.shape, dtype=narrow.dtype, device=dev)
-    dist.all_gather_into_tensor(gathered, narrow)
-    return fold_presence(gathered).to(torch.int64)
+    return all_gather_fold(narrow, world, dist).to(torch.int64)
 
 
 def search_device(ix, q_ptr: int, off_ptr: int, Q: int, max_len: int, world: int, dev, count_only: bool = False) -> int:

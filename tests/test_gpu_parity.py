@@ -138,3 +138,56 @@ def test_edge_cases(kb):
         # m > 10000 throws in the reference
         with pytest.raises(ValueError):
             ix.search(np.zeros(10001, np.uint8))
+
+
+@pytest.mark.parametrize("sigma,ks,n,m_lo,m_hi,world", [(4, [16], 400_000, 16, 64, 2), (4, [12], 300_000, 13, 64, 3),
+                                                       (4, [5, 7, 9, 11, 13], 200_000, 4, 40, 2), (15, [8], 200_000, 3, 20, 4)])
+def test_sharded_search_emulated_on_one_gpu(kb, oracle_mod, sigma, ks, n, m_lo, m_hi, world):
+    """The sharded path (position-range shards with halo, presence OR, global-presence search, rank-order merge)
+    run as `world` indices on one GPU must equal the unsharded reference-exact result."""
+    import torch
+
+    from kmer_index_b200 import sharded, synth
+    dev = torch.device("cuda", 0)
+    text = synth.random_text(n, sigma, 91)
+    q, off = synth.stress_queries(text, 5000, m_lo, m_hi, sigma, 92)
+    Q = off.size - 1
+    d_q = torch.from_numpy(q).to(dev)
+    d_off = torch.from_numpy(off.view(np.int64)).to(dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    shards = [sharded.shard_range(n, world, r, halo=m_hi - 1) for r in range(world)]
+    idx = [kb.KmerIndex(text[s.begin:s.begin + s.length], sigma, ks, shard_begin=s.begin, n_total=n, halo=s.halo,
+                        stream=stream or None) for s in shards]
+    try:
+        masks = []
+        for ix in idx:
+            m = torch.zeros(Q, dtype=torch.int64, device=dev)
+            ix.presence_batch_device(d_q.data_ptr(), d_off.data_ptr(), Q, m_hi, m.data_ptr())
+            torch.cuda.synchronize()
+            masks.append(m)
+        present = sharded.fold_presence(torch.stack(masks))
+        per_shard = []
+        for ix in idx:
+            r = ix.search_batch_device_global(d_q.data_ptr(), d_off.data_ptr(), Q, m_hi, present.data_ptr())
+            torch.cuda.synchronize()
+            o = torch.as_tensor(r.offsets(), device=dev).clone()
+            p = (torch.as_tensor(r.positions(), device=dev).clone() if r.n_positions
+                 else torch.empty(0, dtype=torch.int32, device=dev))
+            st = torch.as_tensor(r.status(), device=dev).clone()
+            r.free()
+            per_shard.append((o, p, st))
+        counts = torch.stack([o[1:] - o[:-1] for o, _, _ in per_shard])
+        g_off, base = sharded.merge_offsets(counts)
+        final = torch.empty(int(g_off[-1].item()), dtype=torch.int32, device=dev)
+        for r, (o, p, _) in enumerate(per_shard):
+            sharded.place_shard(final, o, p, base[r])
+        got = (g_off.cpu().numpy().astype(np.uint64), final.cpu().numpy().view(np.uint32), per_shard[0][2].cpu().numpy())
+        for _, _, st in per_shard[1:]:
+            assert torch.equal(st, per_shard[0][2])
+    finally:
+        for ix in idx:
+            ix.close()
+    with oracle_mod.Oracle(text, sigma, ks) as o:
+        want = o.search(q, off)
+    assert_results_equal(got, want, label=f"sharded x{world} {ks}")
+    assert want[1].size > 0

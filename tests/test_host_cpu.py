@@ -1,0 +1,96 @@
+"""CPU (no GPU): the C-ABI library loads and exports every declared symbol, the host-side logic (scheme table,
+fast_pow, hash, choose_best_k, shard geometry) matches the golden vectors and the oracle, and computing entry
+points fail loudly without a device."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden_cases, load_golden
+
+
+@pytest.fixture(scope="module")
+def kb():
+    from kmer_index_b200 import build
+    build.build()
+    import kmer_index_b200
+    return kmer_index_b200
+
+
+def test_library_exports_every_declared_symbol(kb):
+    from kmer_index_b200 import _capi
+    header = open(os.path.join(ROOT, "include", "kmer_b200.h")).read()
+    declared = set(re.findall(r"\b(kmer_b200_[a-z0-9_]+)\s*\(", header))
+    declared -= {"kmer_b200_config_default"} - {"kmer_b200_config_default"}  # keep all
+    out = subprocess.run(["nm", "-D", "--defined-only", _capi.LIB_PATH], check=True, capture_output=True, text=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    missing = sorted(declared - exported)
+    assert not missing, f"declared in include/kmer_b200.h but not exported: {missing}"
+    assert declared == set(_capi.SYMBOLS), sorted(declared ^ set(_capi.SYMBOLS))
+    assert _capi.lib().kmer_b200_abi_version() == 1
+
+
+def test_no_oracle_or_cpu_fallback_in_product(kb):
+    """The product never imports/links the oracle, and there is no torch/numpy compute fallback."""
+    for root, _, files in os.walk(os.path.join(ROOT, "kmer_index_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert "oracle" not in src.replace("intersection oracle", ""), f"{f} mentions the oracle"
+    out = subprocess.run(["ldd", kb._capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "kmer_oracle" not in out and "kmer_ref" not in out
+
+
+def test_compute_fails_loudly_without_gpu(kb):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(kb.KmerB200Error) as e:
+        kb.KmerIndex(np.zeros(100, np.uint8), 4, [5])
+    assert e.value.code == -2
+
+
+def test_fast_pow_hash_choose_best_k(kb, oracle_mod):
+    s = load_golden("scalars")
+    for bi, b in enumerate(s["bases"]):
+        for ei, e in enumerate(s["exps"]):
+            assert kb.fast_pow(int(b), int(e)) == int(s["fast_pow"][bi, ei]), (b, e)
+    o_ = 0
+    for ln, want in zip(s["cbk_intervals"], s["cbk_out"]):
+        iv = s["cbk_flat"][o_:o_ + ln]
+        o_ += int(ln)
+        assert kb.choose_best_k(iv.tolist(), 4) == want.tolist()
+    rng = np.random.default_rng(5)
+    for sigma, k in [(4, 12), (4, 16), (15, 8), (27, 5), (5, 13), (4, 31), (27, 13)]:
+        r = rng.integers(0, sigma, k, dtype=np.uint8)
+        assert kb.kmer_hash(r, sigma) == oracle_mod.Oracle.hash(r, sigma)
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_scheme_table_matches_golden(kb, name):
+    g = load_golden(name)
+    flat, o_ = g["scheme_flat"], 0
+    for m, ln, multi in zip(g["scheme_m"], g["scheme_len"], g["scheme_multi"]):
+        ks, use_multi = kb.scheme_for_ks(g["ks"].tolist(), int(m))
+        assert ks == flat[o_:o_ + ln].tolist() and use_multi == bool(multi), (name, int(m), ks)
+        o_ += int(ln)
+
+
+@pytest.mark.parametrize("ks", [[12], [5, 7, 9, 11, 13], [9, 10], [3], [16], [10, 11, 12], [29, 27, 25, 23], [13, 5, 11, 7, 9]])
+def test_scheme_table_matches_oracle_full_range(kb, oracle_mod, ks):
+    text = np.zeros(64, dtype=np.uint8)
+    with oracle_mod.Oracle(text, 4, ks) as o:
+        for m in list(range(1, 400)) + [999, 5000, 9998, 9999]:
+            assert kb.scheme_for_ks(ks, m) == o.scheme(m), (ks, m)
+
+
+def test_shard_geometry():
+    from kmer_index_b200 import sharded
+    n, world, halo = 1000, 4, 63
+    shards = [sharded.shard_range(n, world, r, halo) for r in range(world)]
+    assert shards[0].begin == 0 and shards[-1].end == n and shards[-1].halo == 0
+    for a, b in zip(shards, shards[1:]):
+        assert a.end == b.begin and a.halo == min(halo, n - a.end) and a.length == a.end - a.begin + a.halo
+    assert sum(s.end - s.begin for s in shards) == n
