@@ -1,0 +1,276 @@
+// kmer_index.hpp -- header-only C++ API of the B200 k-mer index.
+//
+// Source-compatible with the reference's public surface (Clemapfel/kmer_index, kmer_index.hpp):
+//
+//   kmer::kmer_index<alphabet_t, position_t, ks...>(text, n_threads)      kmer_index.hpp:350-352, 480-496
+//   kmer::make_kmer_index<ks...>(text, n_threads)                         kmer_index.hpp:569-579
+//   index.search(query) -> kmer::detail::kmer_index_result<position_t>    kmer_index.hpp:505-558
+//   result.to_vector()                                                    kmer_index_result.hpp:244-260
+//   kmer::detail::fast_pow(base, exp)                                     fast_pow.hpp:46-93
+//
+// plus kmer::single_kmer_index<k> / kmer::multi_kmer_index<ks...> (the thesis' names) and the batched entry
+// point search_batch(), which is what a GPU wants to be fed. Everything heavy happens in libkmer_b200.so
+// (include/kmer_b200.h); this header only converts alphabets to ranks and results to vectors.
+// Link with -lkmer_b200. There is no CPU fallback: construction throws std::runtime_error without a device.
+//
+// Differences from the reference, all deliberate:
+//   * the result OWNS its sorted positions (the reference's holds pointers into the index);
+//     size() is the number of hits (the reference's returns 0 for bypass results, a defect);
+//     begin()/end() iterate the positions (the reference's iterator does not compile).
+//   * search(std::vector<alphabet_t>&&) returns its result (the reference's has no return statement).
+//   * n_threads is accepted and ignored; extend_query_size_range() is rejected above 10000.
+//   * the alphabet requirement is `a.to_rank()` plus kmer::alphabet_size<A>; seqan3 alphabets satisfy it when
+//     seqan3 is available, kmer::dna4 / dna5 / dna15 / aa27 below are rank-only stand-ins.
+#pragma once
+
+#include <algorithm>
+#include <array>
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <ranges>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include "kmer_b200.h"
+
+#if __has_include(<seqan3/alphabet/concept.hpp>)
+#include <seqan3/alphabet/concept.hpp>
+#define KMER_B200_HAVE_SEQAN3 1
+#endif
+
+namespace kmer
+{
+    // ------------------------------------------------------------------------------------------ alphabets
+    template<std::size_t SIGMA>
+    struct rank_alphabet
+    {
+        static constexpr std::size_t alphabet_size = SIGMA;
+        std::uint8_t rank{0};
+        constexpr std::uint8_t to_rank() const noexcept { return rank; }
+        constexpr rank_alphabet& assign_rank(std::uint8_t r) noexcept { rank = r; return *this; }
+        friend constexpr bool operator==(rank_alphabet a, rank_alphabet b) noexcept { return a.rank == b.rank; }
+        friend constexpr bool operator!=(rank_alphabet a, rank_alphabet b) noexcept { return a.rank != b.rank; }
+    };
+    using dna4 = rank_alphabet<4>;
+    using dna5 = rank_alphabet<5>;
+    using dna15 = rank_alphabet<15>;
+    using aa27 = rank_alphabet<27>;
+
+    namespace detail
+    {
+        template<typename T, typename = void>
+        struct alphabet_size_of;
+        template<typename T>
+        struct alphabet_size_of<T, std::void_t<decltype(T::alphabet_size)>>
+        { static constexpr std::size_t value = T::alphabet_size; };
+#ifdef KMER_B200_HAVE_SEQAN3
+        template<typename T>
+            requires (!requires { T::alphabet_size; }) && seqan3::alphabet<T>
+        struct alphabet_size_of<T, void>
+        { static constexpr std::size_t value = seqan3::alphabet_size<T>; };
+#endif
+    }
+
+    template<typename T>
+    inline constexpr std::size_t alphabet_size = detail::alphabet_size_of<std::remove_cvref_t<T>>::value;
+
+    template<typename T>
+    concept alphabet = requires(T const a) {
+        { a.to_rank() } -> std::convertible_to<std::size_t>;
+        { alphabet_size<T> } -> std::convertible_to<std::size_t>;
+    };
+
+    namespace detail
+    {
+        // fast_pow.hpp:46-93: square-and-multiply mod 2^64; 0 once exp needs more than 6 bits... i.e. exp >= 63
+        // (the reference's table returns the "overflow" marker there), except base == 1
+        constexpr std::size_t fast_pow(std::size_t base, std::uint8_t exp)
+        {
+            if (exp >= 63)
+                return base == 1 ? 1 : 0;
+            std::size_t result = 1;
+            while (exp)
+            {
+                if (exp & 1) result *= base;
+                exp >>= 1;
+                base *= base;
+            }
+            return result;
+        }
+
+        enum class BYPASS_BITMASK : bool { YES = true, NO = false };   // kmer_index_result.hpp:11 (kept for source compat)
+
+        // kmer_index_result.hpp:14-272
+        template<typename position_t>
+        class kmer_index_result
+        {
+            std::vector<position_t> _positions;   // ascending
+
+        public:
+            kmer_index_result() = default;
+            explicit kmer_index_result(std::vector<position_t> sorted_positions) : _positions(std::move(sorted_positions)) {}
+
+            std::size_t size() const noexcept { return _positions.size(); }
+            bool empty() const noexcept { return _positions.empty(); }
+            std::vector<position_t> to_vector() const { return _positions; }
+            auto begin() const noexcept { return _positions.begin(); }
+            auto end() const noexcept { return _positions.end(); }
+        };
+
+        inline void check(int status)
+        {
+            if (status == KMER_B200_OK)
+                return;
+            std::string msg = kmer_b200_last_error();
+            if (status == KMER_B200_ERR_INVALID_ARGUMENT || status == KMER_B200_ERR_INVALID_RANK)
+                throw std::invalid_argument("kmer_b200: " + msg);
+            throw std::runtime_error("kmer_b200 (" + std::to_string(status) + "): " + msg);
+        }
+
+        template<typename range_t>
+        std::vector<std::uint8_t> to_ranks(range_t const& r)
+        {
+            std::vector<std::uint8_t> out;
+            if constexpr (std::ranges::sized_range<range_t>)
+                out.reserve(std::ranges::size(r));
+            for (auto const& c : r)
+                out.push_back(static_cast<std::uint8_t>(c.to_rank()));
+            return out;
+        }
+    }
+
+    // result of search_batch(): CSR over the batch
+    template<typename position_t>
+    struct kmer_batch_result
+    {
+        std::vector<std::uint64_t> offsets;   // [n_queries + 1]
+        std::vector<position_t> positions;    // ascending per query
+        std::vector<std::uint8_t> status;     // kmer_b200_query_status per query
+
+        std::size_t size() const noexcept { return status.size(); }
+        bool threw(std::size_t i) const { return status[i] == KMER_B200_QUERY_THROW_INVALID_ARGUMENT; }
+        detail::kmer_index_result<position_t> operator[](std::size_t i) const
+        {
+            return detail::kmer_index_result<position_t>(
+                std::vector<position_t>(positions.begin() + offsets[i], positions.begin() + offsets[i + 1]));
+        }
+    };
+
+    // kmer_index.hpp:350-566
+    template<alphabet alphabet_t, typename position_t, std::size_t... ks>
+    class kmer_index
+    {
+        static_assert(sizeof...(ks) > 0, "at least one k");
+        static_assert(std::is_same_v<position_t, std::uint32_t>,
+                      "the device index stores 32-bit positions (make_kmer_index fixes position_t = uint32_t, kmer_index.hpp:575)");
+        // kmer_index.hpp:42-43
+        static_assert(((ks > 0 && double(ks) < 64.0 / __builtin_log2(double(alphabet_size<alphabet_t>))) && ...),
+                      "the hashspace for the current k cannot be represented with only a 64-bit integer. Please specify a valid k");
+
+        using result_t = detail::kmer_index_result<position_t>;
+        kmer_b200_index* _handle = nullptr;
+        std::size_t _query_size_range = 10000;   // kmer_index.hpp:401
+
+    public:
+        template<std::ranges::range text_t>
+        explicit kmer_index(text_t& text, std::size_t /*n_threads*/ = 1, kmer_b200_mode mode = KMER_B200_MODE_REFERENCE_EXACT,
+                            int device = -1)
+        {
+            static constexpr std::uint32_t k_list[] = {std::uint32_t(ks)...};
+            auto ranks = detail::to_ranks(text);
+            kmer_b200_config cfg;
+            kmer_b200_config_default(&cfg);
+            cfg.mode = mode;
+            cfg.device = device;
+            detail::check(kmer_b200_create(ranks.data(), ranks.size(), std::uint32_t(alphabet_size<alphabet_t>), k_list,
+                                           sizeof...(ks), &cfg, &_handle));
+        }
+
+        kmer_index(kmer_index const&) = delete;
+        kmer_index& operator=(kmer_index const&) = delete;
+        kmer_index(kmer_index&& o) noexcept : _handle(std::exchange(o._handle, nullptr)), _query_size_range(o._query_size_range) {}
+        kmer_index& operator=(kmer_index&& o) noexcept
+        {
+            if (this != &o)
+            {
+                kmer_b200_destroy(_handle);
+                _handle = std::exchange(o._handle, nullptr);
+            }
+            return *this;
+        }
+        ~kmer_index() { kmer_b200_destroy(_handle); }
+
+        // kmer_index.hpp:498-502: the scheme table is built for query lengths below 10000
+        void extend_query_size_range(std::size_t new_maximum)
+        {
+            if (new_maximum > 10000)
+                throw std::invalid_argument("query size range above 10000 is not supported");
+        }
+
+        // All queries in one launch. queries: any range of ranges of alphabet_t.
+        template<std::ranges::range queries_t>
+        kmer_batch_result<position_t> search_batch(queries_t const& queries) const
+        {
+            std::vector<std::uint8_t> ranks;
+            std::vector<std::uint64_t> offsets{0};
+            for (auto const& q : queries)
+            {
+                for (auto const& c : q)
+                    ranks.push_back(static_cast<std::uint8_t>(c.to_rank()));
+                offsets.push_back(ranks.size());
+            }
+            kmer_b200_result* r = nullptr;
+            detail::check(kmer_b200_search_batch(_handle, ranks.data(), offsets.data(), offsets.size() - 1, UINT32_MAX, &r));
+            kmer_batch_result<position_t> out;
+            const std::uint64_t n_q = kmer_b200_result_n_queries(r), n_p = kmer_b200_result_n_positions(r);
+            out.offsets.assign(kmer_b200_result_offsets(r), kmer_b200_result_offsets(r) + n_q + 1);
+            out.status.assign(kmer_b200_result_status(r), kmer_b200_result_status(r) + n_q);
+            if (n_p)
+                out.positions.assign(kmer_b200_result_positions(r), kmer_b200_result_positions(r) + n_p);
+            kmer_b200_result_free(r);
+            return out;
+        }
+
+        // kmer_index.hpp:505-558. A batch of one: correct, but a GPU is fed with search_batch().
+        result_t search(std::vector<alphabet_t>& query) const
+        {
+            if (query.size() > _query_size_range)   // :507-509
+                throw std::invalid_argument("query size exceed the maximum size " + std::to_string(_query_size_range) + " specified");
+            std::array<std::vector<alphabet_t> const*, 1> one{&query};
+            auto deref = one | std::views::transform([](auto const* p) -> std::vector<alphabet_t> const& { return *p; });
+            auto batch = search_batch(deref);
+            if (batch.status[0] == KMER_B200_QUERY_THROW_INVALID_ARGUMENT)   // :119-122
+                throw std::invalid_argument("query size too low for specified k");
+            if (batch.status[0] != KMER_B200_QUERY_OK)
+                throw std::invalid_argument("query length 0 or 10000 is undefined in the reference (kmer_index.hpp:195,512)");
+            return result_t(std::move(batch.positions));
+        }
+
+        result_t search(std::vector<alphabet_t>&& query) const   // :561-565, with the missing return
+        {
+            auto hold = std::move(query);
+            return search(hold);
+        }
+
+        kmer_b200_index* native_handle() const noexcept { return _handle; }
+    };
+
+    // kmer_index.hpp:569-579
+    template<std::size_t... ks, std::ranges::range text_t>
+    auto make_kmer_index(text_t&& text, std::size_t n_threads = 1)
+    {
+        using alphabet_t = std::ranges::range_value_t<std::remove_cvref_t<text_t>>;
+        using position_t = std::uint32_t;
+        return kmer_index<alphabet_t, position_t, ks...>(text, n_threads);
+    }
+
+    // names used by the thesis (thesis/content/02_implementation.tex:253-274)
+    template<typename alphabet_t, std::size_t k>
+    using single_kmer_index = kmer_index<alphabet_t, std::uint32_t, k>;
+    template<typename alphabet_t, std::size_t... ks>
+    using multi_kmer_index = kmer_index<alphabet_t, std::uint32_t, ks...>;
+}   // namespace kmer

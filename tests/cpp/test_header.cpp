@@ -1,0 +1,115 @@
+// Exercises include/kmer_index.hpp the way a user of the reference would (test_main.cpp:21-69 protocol):
+// build single and multi indices with make_kmer_index, search(), compare to_vector() with a plain scan.
+// Exit code 0 = all good. Needs a GPU at run time; compile-only is part of the CPU test suite.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include <kmer_index.hpp>
+
+using alphabet_t = kmer::dna4;
+
+static uint64_t lcg_state = 88172645463325252ull;
+static uint32_t next_u32()
+{
+    lcg_state = lcg_state * 6364136223846793005ull + 1442695040888963407ull;
+    return uint32_t(lcg_state >> 33);
+}
+
+static std::vector<alphabet_t> random_sequence(size_t n)
+{
+    std::vector<alphabet_t> s(n);
+    for (auto& c : s) c.assign_rank(uint8_t(next_u32() % 4));
+    return s;
+}
+
+static std::vector<uint32_t> scan(std::vector<alphabet_t> const& text, std::vector<alphabet_t> const& q)
+{
+    std::vector<uint32_t> out;
+    if (q.size() > text.size()) return out;
+    for (size_t p = 0; p + q.size() <= text.size(); ++p)
+    {
+        bool eq = true;
+        for (size_t i = 0; i < q.size() && eq; ++i) eq = text[p + i] == q[i];
+        if (eq) out.push_back(uint32_t(p));
+    }
+    return out;
+}
+
+#define REQUIRE(cond)                                                        \
+    do {                                                                     \
+        if (!(cond)) {                                                       \
+            std::fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+            return 1;                                                        \
+        }                                                                    \
+    } while (0)
+
+int main()
+{
+    static_assert(kmer::detail::fast_pow(4, 12) == 16777216);
+    static_assert(kmer::detail::fast_pow(2, 63) == 0 && kmer::detail::fast_pow(1, 200) == 1);
+
+    auto text = random_sequence(200000);
+    auto single = kmer::make_kmer_index<10>(text);
+    auto multi = kmer::make_kmer_index<10, 11, 12>(text);
+    kmer::single_kmer_index<alphabet_t, 16> k16(text);
+
+    // lengths on which the reference is correct for these indices: k-5 .. 2k-1 (test_main.cpp:32)
+    for (size_t m = 5; m < 20; ++m)
+        for (int rep = 0; rep < 6; ++rep)
+        {
+            std::vector<alphabet_t> q;
+            if (rep % 2 == 0) {
+                size_t start = next_u32() % (text.size() - m + 1);
+                if (rep == 4) start = text.size() - m;   // ends at the end of the text
+                q.assign(text.begin() + start, text.begin() + start + m);
+            } else {
+                q = random_sequence(m);
+            }
+            auto truth = scan(text, q);
+            REQUIRE(single.search(q).to_vector() == truth);
+            REQUIRE(multi.search(q).to_vector() == truth);
+            REQUIRE(single.search(q).size() == truth.size());
+        }
+
+    // rvalue overload returns (the reference's does not)
+    {
+        std::vector<alphabet_t> q(text.begin() + 77, text.begin() + 87);
+        REQUIRE(single.search(std::vector<alphabet_t>(q)).to_vector() == scan(text, q));
+    }
+    // the reference throws std::invalid_argument when the rest is too short for k (kmer_index.hpp:119-122):
+    // k = 16, m = 17 -> rest 1 -> 4^15 > 1e7, once the full part is present
+    {
+        std::vector<alphabet_t> q(text.begin() + 1000, text.begin() + 1017);
+        bool threw = false;
+        try { (void)k16.search(q); } catch (std::invalid_argument const&) { threw = true; }
+        REQUIRE(threw);
+        std::vector<alphabet_t> too_long(10001);
+        threw = false;
+        try { (void)k16.search(too_long); } catch (std::invalid_argument const&) { threw = true; }
+        REQUIRE(threw);
+    }
+    // batch API
+    {
+        std::vector<std::vector<alphabet_t>> qs;
+        for (int i = 0; i < 100; ++i) {
+            size_t m = 10 + i % 10, start = next_u32() % (text.size() - m + 1);
+            qs.emplace_back(text.begin() + start, text.begin() + start + m);
+        }
+        auto batch = single.search_batch(qs);
+        REQUIRE(batch.size() == qs.size());
+        for (size_t i = 0; i < qs.size(); ++i)
+            REQUIRE(batch[i].to_vector() == scan(text, qs[i]));
+    }
+    // other alphabets
+    {
+        std::vector<kmer::dna15> t15(50000);
+        for (auto& c : t15) c.assign_rank(uint8_t(next_u32() % 15));
+        auto idx = kmer::make_kmer_index<8>(t15);
+        std::vector<kmer::dna15> q(t15.begin() + 123, t15.begin() + 131);
+        auto r = idx.search(q).to_vector();
+        REQUIRE(!r.empty() && r.front() <= 123);
+    }
+    std::printf("kmer_index.hpp: all checks passed\n");
+    return 0;
+}
