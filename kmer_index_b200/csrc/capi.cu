@@ -171,6 +171,7 @@ struct kmer_b200_index {
     uint64_t *h_pinned = nullptr;    // small pinned scratch: [0] total hits, [1] flags
     uint64_t device_bytes = 0;
     bool reaches_end = true;  // the local slice ends at the end of the whole text
+    double max_avg_bucket = 0;  // max over elements of (k-mers / distinct possible hashes)
     Profiler prof;
     std::mutex mu;  // serialises searches on one handle (they share the stream and the flag words)
     size_t h_pinned_cap = 0;
@@ -417,6 +418,7 @@ int build_element(kmer_b200_index *ix, uint32_t k, HostElement &he) {
     he.dev.keys = he.d_keys;
     he.dev.pos = he.d_pos;
     he.bytes = 2 * n_kmers * sizeof(uint32_t) + dir_entries * sizeof(uint32_t);
+    ix->max_avg_bucket = std::max(ix->max_avg_bucket, (double)n_kmers / (double)std::min<uint64_t>(key_space, n_kmers));
     return 0;
 }
 
@@ -600,6 +602,25 @@ int create_impl(const uint8_t *ranks, bool ranks_on_device, uint64_t n, uint32_t
 
 enum SearchFlavor { kFlavorFull, kFlavorCountOnly };
 
+// lanes per query, shared-memory words per query and the longest admissible query of a batch
+int search_geometry(const kmer_b200_index *ix, uint64_t max_len, uint32_t mode, kb::SearchArgs *a) {
+    uint64_t len_cap = std::max<uint64_t>(max_len, 1);
+    // an interior shard can only complete matches of length <= halo + 1 that start in its owned range
+    if (!ix->reaches_end && ix->cfg.halo + 1 < len_cap) len_cap = ix->cfg.halo + 1;
+    if (mode == KMER_B200_MODE_REFERENCE_EXACT) len_cap = std::min<uint64_t>(len_cap, kb::kQuerySizeRange);
+    // 8 lanes per query while queries are short and buckets small (the common case: k chosen so that
+    // sigma^k >~ n); a full warp per query for long candidate lists or long queries
+    uint32_t group = 8;
+    if (ix->max_avg_bucket > 64.0 || (size_t)kb::search_q_words(8, ix->bits, len_cap) * 8 * 32 > 48 * 1024) group = 32;
+    const uint32_t q_words = kb::search_q_words(group, ix->bits, len_cap);
+    if ((size_t)q_words * 8 * (256 / group) > 200 * 1024)
+        return fail(KMER_B200_ERR_UNSUPPORTED, "query too long for the shared-memory staging of this build");
+    a->group = group;
+    a->q_words = q_words;
+    a->max_len = (uint32_t)len_cap;
+    return 0;
+}
+
 // queries already on the device; result stays on the device
 int search_device_impl(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off, uint64_t Q, uint64_t max_len,
                        uint32_t mode, const uint64_t *d_present_global, SearchFlavor flavor, kmer_b200_result **out) {
@@ -623,22 +644,13 @@ int search_device_impl(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *
         return bail(KMER_B200_ERR_OUT_OF_MEMORY);
 
     // shared-memory reservation per query: ceil(max_len / 32) rounds of bits/2 words, plus two padding words
-    uint64_t len_cap = std::max<uint64_t>(max_len, 1);
-    // an interior shard can only complete matches of length <= halo + 1 that start in its owned range
-    if (!ix->reaches_end && ix->cfg.halo + 1 < len_cap) len_cap = ix->cfg.halo + 1;
-    if (mode == KMER_B200_MODE_REFERENCE_EXACT) len_cap = std::min<uint64_t>(len_cap, kQuerySizeRange);
-    const uint32_t q_words = (uint32_t)(((len_cap + 31) / 32) * (ix->bits / 2) + 2);
-    if ((size_t)q_words * 8 * 8 > 200 * 1024)
-        return bail(fail(KMER_B200_ERR_UNSUPPORTED, "query too long for the shared-memory staging of this build"));
-
     SearchArgs a{};
+    if (int s = search_geometry(ix, max_len, mode, &a)) return bail(s);
     a.index = ix->d_index;
     a.q_ranks = d_q;
     a.q_offsets = d_off;
     a.n_queries = Q;
     a.mode = mode;
-    a.q_words = q_words;
-    a.max_len = (uint32_t)len_cap;
     a.present_global = d_present_global;
     a.counts = res->offsets;
     a.status = res->status;
@@ -797,16 +809,13 @@ int kmer_b200_presence_batch_device(kmer_b200_index *ix, const uint8_t *d_q, con
     if (mode == UINT32_MAX) mode = ix->cfg.mode;
     DeviceGuard guard(ix->device);
     std::lock_guard<std::mutex> lock(ix->mu);
-    uint64_t len_cap = std::max<uint64_t>(max_len, 1);
-    if (mode == KMER_B200_MODE_REFERENCE_EXACT) len_cap = std::min<uint64_t>(len_cap, kQuerySizeRange);
     SearchArgs a{};
+    KB_TRY(search_geometry(ix, max_len, mode, &a));
     a.index = ix->d_index;
     a.q_ranks = d_q;
     a.q_offsets = d_off;
     a.n_queries = Q;
     a.mode = mode;
-    a.q_words = (uint32_t)(((len_cap + 31) / 32) * (ix->bits / 2) + 2);
-    a.max_len = (uint32_t)len_cap;
     a.present = d_present;
     a.error_flag = ix->d_flags;
     ix->prof.begin(K_SEARCH_PRESENCE, 0);

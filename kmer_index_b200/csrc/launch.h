@@ -31,7 +31,8 @@ struct SearchArgs {
     const uint64_t *q_offsets;       // device, [Q + 1]
     uint64_t n_queries;
     uint32_t mode;                   // kmer_b200_mode
-    uint32_t q_words;                // packed words reserved per query in shared memory
+    uint32_t group;                  // lanes per query: 8 or 32
+    uint32_t q_words;                // packed words reserved per query in shared memory (search_q_words)
     uint32_t max_len;                // longest query the shared-memory reservation (and the shard halo) allows
     const uint64_t *present_global;  // device or null: OR over shards of the presence masks
     uint64_t *counts;                // device, [Q + 1]: per-query hit counts (count pass), then offsets
@@ -43,6 +44,7 @@ struct SearchArgs {
 };
 
 void launch_search(const SearchArgs &args, SearchPass pass, cudaStream_t stream);
+uint32_t search_q_words(uint32_t group, uint32_t bits, uint64_t max_len);
 // in place: counts[0..Q) -> exclusive offsets, counts[Q] = total
 void launch_offsets_scan(uint64_t *d_counts, uint64_t n_queries, uint64_t *d_block_sums, cudaStream_t stream);
 uint64_t offsets_scan_blocks(uint64_t n_queries);

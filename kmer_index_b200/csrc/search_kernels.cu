@@ -13,6 +13,8 @@
 //      in bucket hash(T[x,x+k)) and in no other, so "p + d is in the bucket of part j" is
 //      "T[p+d, p+d+k) == part j"), and hits are compacted with ballot/popc.
 // Results are produced in two passes (count -> exclusive scan -> write) so the output is an exact CSR.
+#include <algorithm>
+
 #include "radix.cuh"
 #include "launch.h"
 
@@ -90,13 +92,56 @@ __device__ __forceinline__ bool match_span(const PackedText &T, const uint64_t *
     return true;
 }
 
-template <int PASS>
+// ---- query packing helpers ----------------------------------------------------------------------------
+// 8 ranks held as the bytes of v (byte j = symbol j) -> 8*bits bits, symbol 0 in the most significant field
+__device__ __forceinline__ uint64_t pack8(uint64_t v, uint32_t bits) {
+    if (bits == 8) {  // byte reversal
+        const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+        return ((uint64_t)__byte_perm(lo, 0, 0x0123) << 32) | __byte_perm(hi, 0, 0x0123);
+    }
+    // three pairwise merges; fields are < 2^bits so a left shift by `bits` never crosses into a kept field
+    const uint64_t m1 = bits == 2 ? 0x000F000F000F000Full : 0x00FF00FF00FF00FFull;
+    const uint64_t m2 = bits == 2 ? 0x000000FF000000FFull : 0x0000FFFF0000FFFFull;
+    const uint64_t m3 = bits == 2 ? 0xFFFFull : 0xFFFFFFFFull;
+    uint64_t y = ((v << bits) | (v >> 8)) & m1;
+    y = ((y << (2 * bits)) | (y >> 16)) & m2;
+    return ((y << (4 * bits)) | (y >> 32)) & m3;
+}
+
+// 8 query bytes starting at p (unaligned), bytes >= n_valid zeroed. `safe` = [p, p + 16) lies inside the buffer.
+__device__ __forceinline__ uint64_t load8(const uint8_t *p, uint32_t n_valid, bool safe) {
+    uint64_t v;
+    if (safe) {
+        const uint64_t *a = reinterpret_cast<const uint64_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)7);
+        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 7) * 8;
+        const uint64_t lo = a[0];
+        v = lo;
+        if (sh) v = (lo >> sh) | (a[1] << (64 - sh));
+    } else {
+        v = 0;
+        for (uint32_t j = 0; j < 8 && j < n_valid; ++j) v |= (uint64_t)p[j] << (8 * j);
+    }
+    if (n_valid < 8) v &= (1ull << (8 * n_valid)) - 1;
+    return v;
+}
+
+// One group of G lanes per query (G = 8 for short queries and short buckets, 32 otherwise): the scalar part
+// of a query (plan, status) costs a warp instruction per group, not per warp, and G/32 more queries are in
+// flight per SM to cover the chain of dependent gathers (offsets -> ranks -> directory -> bucket -> text).
+template <int PASS, int G>
 __global__ void __launch_bounds__(kSearchThreads) search_kernel(const SearchArgs a) {
+    constexpr int kGroups = kSearchThreads / G;
     extern __shared__ uint64_t smem_q[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t lt_mask = (1u << lane) - 1;
-    const uint64_t q = (uint64_t)blockIdx.x * kSearchWarps + warp;
+    const int lane = threadIdx.x & 31;
+    const int gl = threadIdx.x & (G - 1);          // lane inside the group
+    const int group = threadIdx.x / G;             // group inside the CTA
+    const uint32_t gshift = (uint32_t)(lane - gl);  // first warp lane of the group
+    const uint32_t gfull = G == 32 ? 0xFFFFFFFFu : ((1u << G) - 1);
+    const uint32_t gmask = gfull << gshift;
+    const uint32_t lt_mask = (1u << gl) - 1;
+    const uint64_t q = (uint64_t)blockIdx.x * kGroups + group;
     if (q >= a.n_queries) return;
+#define GBALLOT(pred) ((__ballot_sync(gmask, (pred)) >> gshift) & gfull)
 
     uint64_t out_base = 0;
     if (PASS == kPassWrite) {
@@ -106,9 +151,10 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const SearchArgs
 
     const DeviceIndex &ix = *a.index;
     const PackedText T = ix.text;
-    uint64_t *qw = smem_q + (size_t)warp * a.q_words;
+    uint64_t *qw = smem_q + (size_t)group * a.q_words;
     const uint64_t off0 = a.q_offsets[q];
     const uint64_t m64 = a.q_offsets[q + 1] - off0;
+    const uint64_t q_total = a.q_offsets[a.n_queries];  // symbols in q_ranks: bounds the 16-byte reads
 
     uint32_t status = KMER_B200_QUERY_OK;
     if (m64 == 0) {
@@ -121,7 +167,7 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const SearchArgs
         status = KMER_B200_QUERY_TOO_LONG_FOR_SHARD;
     }
     if (status != KMER_B200_QUERY_OK) {
-        if (lane == 0) {
+        if (gl == 0) {
             if (PASS == kPassCount) {
                 a.counts[q] = 0;
                 a.status[q] = (uint8_t)status;
@@ -134,31 +180,33 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const SearchArgs
     }
     const uint32_t m = (uint32_t)m64;
 
-    // ---- 1. pack the query (b bits per symbol, MSB-first) -------------------------------------------
+    // ---- 1. pack the query (b bits per symbol, MSB-first): 8 symbols per lane and round ---------------------
     {
         const uint8_t *qr = a.q_ranks + off0;
-        const uint32_t wpr = T.bits >> 1;  // words per 32-symbol round
-        const uint32_t my_word = (lane * T.bits) >> 6;
-        const uint32_t my_shift = 64 - T.bits - ((lane * T.bits) & 63);
+        const uint32_t lpw = 8 / T.bits;            // lanes that share one 64-bit word
+        const uint32_t wpr = (uint32_t)G / lpw;     // words per round of 8 * G symbols
+        const uint32_t my_shift = 64 - 8 * T.bits * ((gl % lpw) + 1);
+        const uint64_t guard = (0x80u - (T.sigma > 128 ? 128u : T.sigma)) * 0x0101010101010101ull;
         bool bad = false;
-        for (uint32_t base = 0; base < m; base += 32) {
-            const uint32_t s = base + lane;
-            uint32_t r = 0;
-            if (s < m) {
-                r = qr[s];
-                bad |= r >= T.sigma;
+        uint32_t round = 0;
+        for (uint32_t base = 0; base < m; base += 8 * G, ++round) {
+            const uint32_t s0 = base + 8 * gl;
+            uint64_t v = 0;
+            if (s0 < m) {
+                v = load8(qr + s0, m - s0, off0 + s0 + 16 <= q_total);
+                if (T.sigma <= 128) {
+                    bad |= (((v + guard) | v) & 0x8080808080808080ull) != 0;
+                } else {
+                    for (uint32_t j = 0; j < 8; ++j) bad |= ((v >> (8 * j)) & 0xFF) >= T.sigma;
+                }
             }
-            const uint64_t v = (uint64_t)r << my_shift;
-            for (uint32_t w = 0; w < wpr; ++w) {
-                const uint64_t mine = (my_word == w) ? v : 0;
-                const uint32_t hi = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)(mine >> 32));
-                const uint32_t lo = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)mine);
-                if (lane == 0) qw[(base >> 5) * wpr + w] = ((uint64_t)hi << 32) | lo;
-            }
+            uint64_t w = pack8(v, T.bits) << my_shift;
+            for (uint32_t o = 1; o < lpw; o <<= 1) w |= __shfl_xor_sync(gmask, w, o, G);
+            if (gl % lpw == 0) qw[round * wpr + gl / lpw] = w;
         }
-        if (lane < 2) qw[((m + 31) >> 5) * wpr + lane] = 0;
-        if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) atomicOr(a.error_flag, 1u);
-        __syncwarp();
+        if (gl < 2) qw[round * wpr + gl] = 0;
+        if (__any_sync(gmask, bad) && gl == 0) atomicOr(a.error_flag, 1u);
+        __syncwarp(gmask);
     }
 
     // ---- 2. plan -----------------------------------------------------------------------------------------
@@ -209,7 +257,7 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const SearchArgs
         }
     }
     if (status != KMER_B200_QUERY_OK) {
-        if (lane == 0) {
+        if (gl == 0) {
             if (PASS == kPassCount) {
                 a.counts[q] = 0;
                 a.status[q] = (uint8_t)status;
@@ -226,8 +274,8 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const SearchArgs
     bool all_present = true;
     uint64_t present_mask = 0;
     if (kind != kSubK) {
-        for (uint32_t base = 0; base < nparts; base += 32) {
-            const uint32_t j = base + lane;
+        for (uint32_t base = 0; base < nparts; base += G) {
+            const uint32_t j = base + gl;
             const bool valid = j < nparts;
             Range rg{0, 0};
             if (valid) {
@@ -241,12 +289,12 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const SearchArgs
                 rg = bucket_of(E, key);
             }
             if (base == 0) {
-                seed.lo = __shfl_sync(0xFFFFFFFFu, rg.lo, 0);
-                seed.cnt = __shfl_sync(0xFFFFFFFFu, rg.cnt, 0);
+                seed.lo = __shfl_sync(gmask, rg.lo, 0, G);
+                seed.cnt = __shfl_sync(gmask, rg.cnt, 0, G);
             }
-            const uint32_t here = __ballot_sync(0xFFFFFFFFu, valid && rg.cnt != 0);
+            const uint32_t here = GBALLOT(valid && rg.cnt != 0);
             if (base < 64) present_mask |= (uint64_t)here << base;
-            const uint32_t want = __ballot_sync(0xFFFFFFFFu, valid);
+            const uint32_t want = GBALLOT(valid);
             if (here != want) {
                 all_present = false;
                 if (PASS != kPassPresence) break;
@@ -254,7 +302,7 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const SearchArgs
         }
     }
     if (PASS == kPassPresence) {
-        if (lane == 0) a.present[q] = present_mask;
+        if (gl == 0) a.present[q] = present_mask;
         return;
     }
     if (a.present_global != nullptr && kind != kSubK) {
@@ -263,7 +311,7 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const SearchArgs
         all_present = (a.present_global[q] & full) == full;
     }
     if (!all_present) {  // kmer_index.hpp:224 / :524  return result_t()
-        if (PASS == kPassCount && lane == 0) {
+        if (PASS == kPassCount && gl == 0) {
             a.counts[q] = 0;
             a.status[q] = KMER_B200_QUERY_OK;
             a.unsorted[q] = 0;
@@ -271,7 +319,7 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const SearchArgs
         return;
     }
     if (throw_after) {  // all full parts present, then the rest lookup throws
-        if (PASS == kPassCount && lane == 0) {
+        if (PASS == kPassCount && gl == 0) {
             a.counts[q] = 0;
             a.status[q] = KMER_B200_QUERY_THROW_INVALID_ARGUMENT;
             a.unsorted[q] = 0;
@@ -291,24 +339,25 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const SearchArgs
         const uint64_t slo = lower_bound_key(E0, lo_key);
         const uint64_t shi = lower_bound_key(E0, lo_key + width);
         if (shi - slo > 1) unsorted = E0.keys[slo] != E0.keys[shi - 1];
-        for (uint64_t c0 = slo; c0 < shi; c0 += 32) {
-            const uint64_t c = c0 + lane;
+        for (uint64_t c0 = slo; c0 < shi; c0 += G) {
+            const uint64_t c = c0 + gl;
             uint32_t p = 0;
             bool ok = false;
             if (c < shi) {
                 p = E0.pos[c];
                 ok = (uint64_t)p < ix.owned;
             }
-            const uint32_t b = __ballot_sync(0xFFFFFFFFu, ok);
+            const uint32_t b = GBALLOT(ok);
             if (PASS == kPassWrite && ok)
                 a.positions[out_base + n_hits + __popc(b & lt_mask)] = p + (uint32_t)ix.global_base;
             n_hits += __popc(b);
         }
         // check_last_kmer (kmer_index.hpp:90-112): starts in the last k-1 positions, where no k-mer starts
-        {
-            const uint64_t p = T.n - k0 + 1 + lane;
-            const bool ok = (uint32_t)lane < k0 - m && p < ix.owned && match_span(T, qw, p, 0, m);
-            const uint32_t b = __ballot_sync(0xFFFFFFFFu, ok);
+        for (uint32_t t0 = 0; t0 < k0 - m; t0 += G) {
+            const uint32_t t = t0 + gl;
+            const uint64_t p = T.n - k0 + 1 + t;
+            const bool ok = t < k0 - m && p < ix.owned && match_span(T, qw, p, 0, m);
+            const uint32_t b = GBALLOT(ok);
             if (PASS == kPassWrite && ok)
                 a.positions[out_base + n_hits + __popc(b & lt_mask)] = (uint32_t)p + (uint32_t)ix.global_base;
             n_hits += __popc(b);
@@ -316,8 +365,8 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const SearchArgs
     } else {
         const Element &Es = from_list ? ix.elem[S[0]] : E0;
         const uint32_t ks = Es.k;
-        for (uint64_t c0 = 0; c0 < seed.cnt; c0 += 32) {
-            const uint64_t c = c0 + lane;
+        for (uint64_t c0 = 0; c0 < seed.cnt; c0 += G) {
+            const uint64_t c = c0 + gl;
             uint32_t p = 0;
             bool ok = false;
             if (c < seed.cnt) {
@@ -338,38 +387,47 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const SearchArgs
                     }
                 }
             }
-            const uint32_t b = __ballot_sync(0xFFFFFFFFu, ok);
+            const uint32_t b = GBALLOT(ok);
             if (PASS == kPassWrite && ok)
                 a.positions[out_base + n_hits + __popc(b & lt_mask)] = p + (uint32_t)ix.global_base;
             n_hits += __popc(b);
         }
     }
-    if (PASS == kPassCount && lane == 0) {
+    if (PASS == kPassCount && gl == 0) {
         a.counts[q] = n_hits;
         a.status[q] = KMER_B200_QUERY_OK;
         const bool flag = unsorted && n_hits > 1;
         a.unsorted[q] = flag ? 1 : 0;
         if (flag) atomicAdd(a.error_flag + 1, 1u);  // number of segments the sort pass has to visit
     }
+#undef GBALLOT
+}
+
+template <int PASS, int G>
+static void launch_search_pg(const SearchArgs &args, cudaStream_t stream) {
+    constexpr int kGroups = kSearchThreads / G;
+    const uint64_t blocks = (args.n_queries + kGroups - 1) / kGroups;
+    const size_t smem = (size_t)kGroups * args.q_words * sizeof(uint64_t);
+    cudaFuncSetAttribute(search_kernel<PASS, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    search_kernel<PASS, G><<<(unsigned)blocks, kSearchThreads, smem, stream>>>(args);
+}
+
+uint32_t search_q_words(uint32_t group, uint32_t bits, uint64_t max_len) {
+    // rounds of 8 * group symbols, group * bits / 8 words each, plus two zero words
+    const uint64_t rounds = (std::max<uint64_t>(max_len, 1) + 8ull * group - 1) / (8ull * group);
+    return (uint32_t)(rounds * (group * bits / 8) + 2);
 }
 
 void launch_search(const SearchArgs &args, SearchPass pass, cudaStream_t stream) {
     if (args.n_queries == 0) return;
-    const uint64_t blocks = (args.n_queries + kSearchWarps - 1) / kSearchWarps;
-    const size_t smem = (size_t)kSearchWarps * args.q_words * sizeof(uint64_t);
-    switch (pass) {
-        case kPassCount:
-            cudaFuncSetAttribute(search_kernel<kPassCount>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            search_kernel<kPassCount><<<(unsigned)blocks, kSearchThreads, smem, stream>>>(args);
-            break;
-        case kPassWrite:
-            cudaFuncSetAttribute(search_kernel<kPassWrite>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            search_kernel<kPassWrite><<<(unsigned)blocks, kSearchThreads, smem, stream>>>(args);
-            break;
-        case kPassPresence:
-            cudaFuncSetAttribute(search_kernel<kPassPresence>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            search_kernel<kPassPresence><<<(unsigned)blocks, kSearchThreads, smem, stream>>>(args);
-            break;
+    if (args.group == 8) {
+        if (pass == kPassCount) launch_search_pg<kPassCount, 8>(args, stream);
+        if (pass == kPassWrite) launch_search_pg<kPassWrite, 8>(args, stream);
+        if (pass == kPassPresence) launch_search_pg<kPassPresence, 8>(args, stream);
+    } else {
+        if (pass == kPassCount) launch_search_pg<kPassCount, 32>(args, stream);
+        if (pass == kPassWrite) launch_search_pg<kPassWrite, 32>(args, stream);
+        if (pass == kPassPresence) launch_search_pg<kPassPresence, 32>(args, stream);
     }
 }
 
