@@ -69,8 +69,28 @@ struct TextSource {  // key(i) = hash of the k-mer starting at symbol i; value(i
     }
     template <bool FULL>
     __device__ __forceinline__ void load_keys(uint64_t first, uint32_t avail, uint32_t (&out)[kSortItems]) const {
+        // items are 32 symbols = 32 * bits bits = `step` whole words apart, so the bit offset inside the word is
+        // the same for all of them: walk the words once (step + 1 loads serve an item, step == 1 shares one)
+        const uint64_t bit0 = first * text.bits;
+        const uint64_t *w = text.words + (bit0 >> 6);
+        const uint32_t sh = (uint32_t)(bit0 & 63);
+        const uint32_t step = text.bits >> 1;
+        const bool pow2 = text.sigma == (1u << text.bits);
+        const uint32_t down = 64 - k * text.bits;
+        uint64_t cur = w[0];
 #pragma unroll
-        for (int r = 0; r < kSortItems; ++r) out[r] = (FULL || (uint32_t)(r * 32) < avail) ? key(first + r * 32) : 0u;
+        for (int r = 0; r < kSortItems; ++r) {
+            // a valid item's two words are inside the (padded) text; invalid items read nothing
+            const bool valid = FULL || (uint32_t)(r * 32) < avail;
+            const uint64_t next = valid ? w[r * step + 1] : 0ull;
+            const uint64_t win = sh ? ((cur << sh) | (next >> (64 - sh))) : cur;
+            const uint32_t kk = pow2 ? (uint32_t)(win >> down) : key_from_window(win, k, text.bits, text.sigma);
+            out[r] = valid ? kk : 0u;
+            if (r + 1 < kSortItems) {
+                const bool valid_next = FULL || (uint32_t)((r + 1) * 32) < avail;
+                cur = step == 1 ? next : (valid_next ? w[(r + 1) * step] : 0ull);
+            }
+        }
     }
     template <bool FULL>
     __device__ __forceinline__ void load_vals(uint64_t first, uint32_t, uint32_t (&out)[kSortItems]) const {

@@ -608,10 +608,21 @@ int search_geometry(const kmer_b200_index *ix, uint64_t max_len, uint32_t mode, 
     // an interior shard can only complete matches of length <= halo + 1 that start in its owned range
     if (!ix->reaches_end && ix->cfg.halo + 1 < len_cap) len_cap = ix->cfg.halo + 1;
     if (mode == KMER_B200_MODE_REFERENCE_EXACT) len_cap = std::min<uint64_t>(len_cap, kb::kQuerySizeRange);
-    // 8 lanes per query while queries are short and buckets small (the common case: k chosen so that
-    // sigma^k >~ n); a full warp per query for long candidate lists or long queries
-    uint32_t group = 8;
-    if (ix->max_avg_bucket > 64.0 || (size_t)kb::search_q_words(8, ix->bits, len_cap) * 8 * 32 > 48 * 1024) group = 32;
+    // Lanes per query. The search is a chain of dependent gathers (offsets -> ranks -> directory -> bucket ->
+    // text), so throughput = queries in flight / chain latency: short queries over an index whose buckets are
+    // short (sigma^k >~ n, the usual choice of k) get one lane each; longer queries and longer candidate lists
+    // get more lanes to pack / verify in parallel, up to a full warp. Measured on B200 (profiles/): config 5
+    // runs at 1.1e9 queries/s with a warp per query and 7.3e9 with a lane per query.
+    uint32_t group = len_cap <= 64 ? 1 : len_cap <= 128 ? 2 : len_cap <= 256 ? 4 : len_cap <= 1024 ? 8 : 32;
+    if (ix->max_avg_bucket > 8.0) group = std::max(group, 8u);
+    if (ix->max_avg_bucket > 64.0) group = 32;
+    if (const char *env = std::getenv("KMER_B200_GROUP")) {  // tuning override: lanes per query
+        const int g = std::atoi(env);
+        if (g == 1 || g == 2 || g == 4 || g == 8 || g == 32) group = (uint32_t)g;
+    }
+    // keep the per-CTA staging of packed queries within 48 KB (several CTAs per SM)
+    while (group < 32 && (size_t)kb::search_q_words(group, ix->bits, len_cap) * 8 * (256 / group) > 48 * 1024)
+        group = group == 8 ? 32 : group * 2;
     const uint32_t q_words = kb::search_q_words(group, ix->bits, len_cap);
     if ((size_t)q_words * 8 * (256 / group) > 200 * 1024)
         return fail(KMER_B200_ERR_UNSUPPORTED, "query too long for the shared-memory staging of this build");

@@ -180,31 +180,42 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const SearchArgs
     }
     const uint32_t m = (uint32_t)m64;
 
-    // ---- 1. pack the query (b bits per symbol, MSB-first): 8 symbols per lane and round ---------------------
+    // ---- 1. pack the query (b bits per symbol, MSB-first) -----------------------------------------------
+    // A chunk is 8 symbols (one 8-byte load); `lpw` chunks make one 64-bit word. Each lane takes `cpl`
+    // consecutive chunks per round so that a round always covers whole words; lanes sharing a word combine
+    // their parts with xor-shuffles.
     {
         const uint8_t *qr = a.q_ranks + off0;
-        const uint32_t lpw = 8 / T.bits;            // lanes that share one 64-bit word
-        const uint32_t wpr = (uint32_t)G / lpw;     // words per round of 8 * G symbols
-        const uint32_t my_shift = 64 - 8 * T.bits * ((gl % lpw) + 1);
+        const uint32_t lpw = 8 / T.bits;                          // chunks per word: 4, 2, 1
+        const uint32_t cpl = lpw > (uint32_t)G ? lpw / G : 1;     // chunks per lane and round
+        const uint32_t share = lpw / cpl;                         // lanes sharing one word
+        const uint32_t wpr = (uint32_t)G * cpl / lpw;             // words per round
         const uint64_t guard = (0x80u - (T.sigma > 128 ? 128u : T.sigma)) * 0x0101010101010101ull;
         bool bad = false;
         uint32_t round = 0;
-        for (uint32_t base = 0; base < m; base += 8 * G, ++round) {
-            const uint32_t s0 = base + 8 * gl;
-            uint64_t v = 0;
-            if (s0 < m) {
-                v = load8(qr + s0, m - s0, off0 + s0 + 16 <= q_total);
-                if (T.sigma <= 128) {
-                    bad |= (((v + guard) | v) & 0x8080808080808080ull) != 0;
-                } else {
-                    for (uint32_t j = 0; j < 8; ++j) bad |= ((v >> (8 * j)) & 0xFF) >= T.sigma;
+        for (uint32_t base = 0; base < m; base += 8 * G * cpl, ++round) {
+            uint64_t w = 0;
+            for (uint32_t c = 0; c < cpl; ++c) {
+                const uint32_t chunk = gl * cpl + c;              // chunk index inside the round
+                const uint32_t s0 = base + 8 * chunk;
+                uint64_t v = 0;
+                if (s0 < m) {
+                    v = load8(qr + s0, m - s0, off0 + s0 + 16 <= q_total);
+                    if (T.sigma <= 128) {
+                        bad |= (((v + guard) | v) & 0x8080808080808080ull) != 0;
+                    } else {
+                        for (uint32_t j = 0; j < 8; ++j) bad |= ((v >> (8 * j)) & 0xFF) >= T.sigma;
+                    }
                 }
+                w |= pack8(v, T.bits) << (64 - 8 * T.bits * ((chunk % lpw) + 1));
             }
-            uint64_t w = pack8(v, T.bits) << my_shift;
-            for (uint32_t o = 1; o < lpw; o <<= 1) w |= __shfl_xor_sync(gmask, w, o, G);
-            if (gl % lpw == 0) qw[round * wpr + gl / lpw] = w;
+            for (uint32_t o = 1; o < share; o <<= 1) w |= __shfl_xor_sync(gmask, w, o, G);
+            if (gl % share == 0) qw[round * wpr + gl / share] = w;
         }
-        if (gl < 2) qw[round * wpr + gl] = 0;
+        if (gl == 0) {
+            qw[round * wpr] = 0;
+            qw[round * wpr + 1] = 0;
+        }
         if (__any_sync(gmask, bad) && gl == 0) atomicOr(a.error_flag, 1u);
         __syncwarp(gmask);
     }
@@ -414,13 +425,28 @@ static void launch_search_pg(const SearchArgs &args, cudaStream_t stream) {
 
 uint32_t search_q_words(uint32_t group, uint32_t bits, uint64_t max_len) {
     // rounds of 8 * group symbols, group * bits / 8 words each, plus two zero words
-    const uint64_t rounds = (std::max<uint64_t>(max_len, 1) + 8ull * group - 1) / (8ull * group);
-    return (uint32_t)(rounds * (group * bits / 8) + 2);
+    const uint32_t lpw = 8 / bits;
+    const uint32_t cpl = lpw > group ? lpw / group : 1;
+    const uint64_t per_round = 8ull * group * cpl;
+    const uint64_t rounds = (std::max<uint64_t>(max_len, 1) + per_round - 1) / per_round;
+    return (uint32_t)(rounds * (group * cpl / lpw) + 2);
 }
 
 void launch_search(const SearchArgs &args, SearchPass pass, cudaStream_t stream) {
     if (args.n_queries == 0) return;
-    if (args.group == 8) {
+    if (args.group == 1) {
+        if (pass == kPassCount) launch_search_pg<kPassCount, 1>(args, stream);
+        if (pass == kPassWrite) launch_search_pg<kPassWrite, 1>(args, stream);
+        if (pass == kPassPresence) launch_search_pg<kPassPresence, 1>(args, stream);
+    } else if (args.group == 2) {
+        if (pass == kPassCount) launch_search_pg<kPassCount, 2>(args, stream);
+        if (pass == kPassWrite) launch_search_pg<kPassWrite, 2>(args, stream);
+        if (pass == kPassPresence) launch_search_pg<kPassPresence, 2>(args, stream);
+    } else if (args.group == 4) {
+        if (pass == kPassCount) launch_search_pg<kPassCount, 4>(args, stream);
+        if (pass == kPassWrite) launch_search_pg<kPassWrite, 4>(args, stream);
+        if (pass == kPassPresence) launch_search_pg<kPassPresence, 4>(args, stream);
+    } else if (args.group == 8) {
         if (pass == kPassCount) launch_search_pg<kPassCount, 8>(args, stream);
         if (pass == kPassWrite) launch_search_pg<kPassWrite, 8>(args, stream);
         if (pass == kPassPresence) launch_search_pg<kPassPresence, 8>(args, stream);
