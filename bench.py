@@ -272,6 +272,20 @@ def run_ours(args, wl):
     t_region = time.perf_counter() - t_region
     clocks = sampler.stop() if sampler else None
 
+    # ---- outside the timed region: algorithmic gathers of the batch (profile = 2 counts the 32-byte sectors
+    # the search must fetch at data-dependent addresses) and the device's random-gather ceiling
+    gathers = gather_peak = None
+    if rank == 0 or world > 1:
+        ix = make_index(2, text_ptr=text.data_ptr())
+        sharded.search_device(ix, q.data_ptr(), q_off.data_ptr(), Q, m_hi, world, dev, count_only=True)
+        gathers = ix.last_search_gathers
+        ix.close()
+    if rank == 0:
+        try:
+            gather_peak = kb.gather_probe(16 << 30, 1 << 29, sptr)
+        except kb.KmerB200Error:
+            gather_peak = None
+
     # ---- end to end through the host C ABI (pinned host buffers in, pinned host result out)
     e2e = None
     if not args.no_e2e:
@@ -351,6 +365,23 @@ def run_ours(args, wl):
             "clocks": clocks,
             "wall_s_timed_region": t_region,
         }
+        # search roofline: sectors gathered per second against the measured random-gather ceiling
+        s_ms = sum(stats_acc[k]["device_ms"] for k in ("search_count", "search_presence") if k in stats_acc) / args.steps
+        if gathers and gather_peak and s_ms > 0:
+            rate = gathers / (s_ms * 1e-3)
+            line["roofline_search"] = {"kernel": "search_count", "bound": "hbm-gather", "achieved": rate * 32 / 1e9,
+                                       "peak": gather_peak * 32 / 1e9, "unit": "GB/s", "frac": rate / gather_peak,
+                                       "sectors_per_query": gathers / Q, "gather_peak_sectors_per_s": gather_peak,
+                                       "peak_source": "kmer_b200_gather_probe: independent 8-byte reads from a 16 GiB table",
+                                       "kernel_ms": s_ms, "rank": 0}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            key = f"{args.workload}:{name}"
+            if key in traffic and args.scale == 1.0:
+                line["roofline"]["traffic"] = traffic[key]["dram_bytes_per_launch"]
+                line["roofline"]["traffic_source"] = traffic[key]["source"]
+        except (OSError, ValueError, KeyError):
+            pass
         if e2e:
             line["e2e"] = {"value": Q / (e2e["search_ms"] * 1e-3), "unit": "queries/s",
                            "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),

@@ -64,7 +64,8 @@ typedef struct kmer_b200_config {
     uint64_t n_total;
     uint32_t halo;
     uint32_t directory_bits; /* 0 = automatic; otherwise log2 of the directory size cap per element */
-    uint32_t profile;        /* 1 = bracket every kernel launch with CUDA events (kmer_b200_stats) */
+    uint32_t profile;        /* 1 = bracket every kernel launch with CUDA events (kmer_b200_stats);
+                                2 = additionally count the 32-byte sectors each search gathers */
     uint32_t reserved;
 } kmer_b200_config;
 
@@ -165,6 +166,13 @@ typedef struct kmer_b200_kernel_stat {
 uint32_t kmer_b200_stats(kmer_b200_index *index, kmer_b200_kernel_stat *out, uint32_t cap);
 void kmer_b200_stats_reset(kmer_b200_index *index);
 uint64_t kmer_b200_device_bytes(const kmer_b200_index *index);
+
+/* profile = 2 only: number of 32-byte sectors at data-dependent addresses (directory slots, bucket entries,
+   text windows) the last search had to gather -- the algorithmic work of the search kernel. */
+uint64_t kmer_b200_last_search_gathers(const kmer_b200_index *index);
+/* Calibration of the random-gather ceiling: n_gathers independent 8-byte reads at random addresses of a
+   table_bytes table (>> L2); *ms_out = device time. sectors/s = n_gathers / time. */
+int kmer_b200_gather_probe(uint64_t table_bytes, uint64_t n_gathers, void *stream, double *ms_out);
 
 /* ---- scalar helpers kept from the reference API */
 /* kmer::detail::fast_pow (fast_pow.hpp:46-93): base^exp mod 2^64, 0 when exp >= 63 and base != 1 */

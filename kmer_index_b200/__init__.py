@@ -53,6 +53,13 @@ def scheme_for_ks(ks: Sequence[int], m: int):
     return [int(x) for x in out[:n]], bool(multi.value)
 
 
+def gather_probe(table_bytes: int = 16 << 30, n_gathers: int = 1 << 30, stream: int | None = None) -> float:
+    """Random-gather ceiling of the device in sectors/s (independent 8-byte reads from a table >> L2)."""
+    ms = C.c_double(0)
+    _capi.check(_capi.lib().kmer_b200_gather_probe(table_bytes, n_gathers, stream, C.byref(ms)))
+    return n_gathers / (ms.value * 1e-3)
+
+
 class BatchResult:
     """CSR result of a batch: offsets[Q+1], positions (ascending per query), status[Q]."""
 
@@ -144,7 +151,7 @@ class KmerIndex:
         cfg.device = device
         cfg.mode = mode
         cfg.stream = stream
-        cfg.profile = 1 if profile else 0
+        cfg.profile = int(profile)   # 1: per-kernel CUDA-event times; 2: also count gathered sectors per search
         cfg.shard_begin = shard_begin
         cfg.n_total = n_total
         cfg.halo = halo
@@ -269,6 +276,11 @@ class KmerIndex:
 
     def stats_reset(self):
         self._L.kmer_b200_stats_reset(self._h)
+
+    @property
+    def last_search_gathers(self) -> int:
+        """profile=2: 32-byte sectors the last search gathered at data-dependent addresses."""
+        return int(self._L.kmer_b200_last_search_gathers(self._h))
 
     @property
     def device_bytes(self) -> int:

@@ -97,6 +97,8 @@ struct TextSource {  // key(i) = hash of the k-mer starting at symbol i; value(i
 #pragma unroll
         for (int r = 0; r < kSortItems; ++r) out[r] = (uint32_t)first + r * 32;
     }
+    template <bool FULL>
+    __device__ __forceinline__ void prefetch_vals(uint64_t, uint32_t) const {}
 };
 
 struct PairSource {  // materialised (key, value) pairs
@@ -114,6 +116,14 @@ struct PairSource {  // materialised (key, value) pairs
         const uint32_t *p = vals + first;
 #pragma unroll
         for (int r = 0; r < kSortItems; ++r) out[r] = (FULL || (uint32_t)(r * 32) < avail) ? p[r * 32] : 0u;
+    }
+    // values are only needed after the ranking; pull their lines into L2 now so the later loads are short
+    template <bool FULL>
+    __device__ __forceinline__ void prefetch_vals(uint64_t first, uint32_t avail) const {
+        const uint32_t *p = vals + first;
+#pragma unroll
+        for (int r = 0; r < kSortItems; ++r)
+            if (FULL || (uint32_t)(r * 32) < avail) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + r * 32));
     }
 };
 
@@ -258,8 +268,7 @@ __global__ void __launch_bounds__(kRadix) column_apply_kernel(uint32_t *__restri
 struct ScatterSmem {
     RankSmem rank;
     uint32_t delta[kRadix];
-    uint32_t keys[kSortTile];
-    uint32_t vals[kSortTile];
+    uint2 kv[kSortTile];  // (key, value) staged in digit order: one 64-bit shared-memory access per element
 };
 
 template <typename Source, int BITS, bool FULL>
@@ -273,33 +282,34 @@ __device__ __forceinline__ void scatter_tile(const Source &src, uint64_t tile_be
 
     // keys live in registers through the ranking; values reuse the same registers afterwards, which keeps the
     // kernel at <= 64 registers so two CTAs share an SM and one CTA's loads overlap the other's ranking
-    uint32_t kv[kSortItems], local_pos[kSortItems];
-    src.template load_keys<FULL>(tile_begin + e0, count - min(count, e0), kv);
-    tile_rank<BITS, FULL>(kv, count, shift, mask, local_pos, sm.rank);
+    uint32_t key[kSortItems], local_pos[kSortItems];
+    src.template load_keys<FULL>(tile_begin + e0, count - min(count, e0), key);
+    src.template prefetch_vals<FULL>(tile_begin + e0, count - min(count, e0));
+    tile_rank<BITS, FULL>(key, count, shift, mask, local_pos, sm.rank);
     if (tid < kRadix) sm.delta[tid] = tile_base_row[tid] - sm.rank.excl[tid];
+    {
+        uint32_t val[kSortItems];
+        src.template load_vals<FULL>(tile_begin + e0, count - min(count, e0), val);
 #pragma unroll
-    for (int r = 0; r < kSortItems; ++r)
-        if (FULL || e0 + r * 32 < count) sm.keys[local_pos[r]] = kv[r];
-    src.template load_vals<FULL>(tile_begin + e0, count - min(count, e0), kv);
-#pragma unroll
-    for (int r = 0; r < kSortItems; ++r)
-        if (FULL || e0 + r * 32 < count) sm.vals[local_pos[r]] = kv[r];
+        for (int r = 0; r < kSortItems; ++r)
+            if (FULL || e0 + r * 32 < count) sm.kv[local_pos[r]] = make_uint2(key[r], val[r]);
+    }
     __syncthreads();
     if (FULL) {
 #pragma unroll
         for (int it = 0; it < kSortItems; ++it) {
             const uint32_t j = it * kSortThreads + tid;
-            const uint32_t kk = sm.keys[j];
-            const uint32_t dst = sm.delta[(kk >> shift) & mask] + j;  // mod 2^32; true destination < n < 2^32
-            out_keys[dst] = kk;
-            out_vals[dst] = sm.vals[j];
+            const uint2 e = sm.kv[j];
+            const uint32_t dst = sm.delta[(e.x >> shift) & mask] + j;  // mod 2^32; true destination < n < 2^32
+            out_keys[dst] = e.x;
+            out_vals[dst] = e.y;
         }
     } else {
         for (uint32_t j = tid; j < count; j += kSortThreads) {
-            const uint32_t kk = sm.keys[j];
-            const uint32_t dst = sm.delta[(kk >> shift) & mask] + j;
-            out_keys[dst] = kk;
-            out_vals[dst] = sm.vals[j];
+            const uint2 e = sm.kv[j];
+            const uint32_t dst = sm.delta[(e.x >> shift) & mask] + j;
+            out_keys[dst] = e.x;
+            out_vals[dst] = e.y;
         }
     }
 }
@@ -330,26 +340,31 @@ __global__ void __launch_bounds__(256) directory_fill_kernel(const uint32_t *__r
                                                              uint32_t *__restrict__ dir) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // boundary index in [0, n_kmers]
     const int lane = threadIdx.x & 31;
-    int64_t lo = 0, hi = -1;  // fill dir[lo..hi] = i
+    // boundary i fills dir[lo .. lo + len) = i, where lo = (key[i-1] >> shift) + 1 and the run ends at
+    // key[i] >> shift (dir_entries - 1 for the closing boundary i == n_kmers)
+    uint64_t lo = 0;
+    uint64_t len = 0;
     if (i <= n_kmers) {
-        const int64_t t_prev = (i == 0) ? -1 : (int64_t)(keys[i - 1] >> shift);
-        const int64_t t_cur = (i == n_kmers) ? (int64_t)dir_entries - 1 : (int64_t)(keys[i] >> shift);
-        lo = t_prev + 1;
-        hi = t_cur;
+        lo = (i == 0) ? 0 : (uint64_t)(keys[i - 1] >> shift) + 1;
+        const uint64_t hi = (i == n_kmers) ? dir_entries - 1 : (uint64_t)(keys[i] >> shift);
+        len = hi + 1 - lo;  // 0 when both neighbours share a directory slot
     }
-    const int64_t len = hi - lo + 1;
-    const bool is_long = len >= 32;
-    if (!is_long) {
-        for (int64_t j = lo; j <= hi; ++j) dir[j] = (uint32_t)i;
+    uint32_t *out = dir + lo;
+    const uint32_t v = (uint32_t)i;
+    if (len >= 1) out[0] = v;  // the common cases, branch-free
+    if (len >= 2) out[1] = v;
+    if (len >= 3 && len < 32) {
+        for (uint32_t j = 2; j < (uint32_t)len; ++j) out[j] = v;
     }
-    uint32_t long_mask = __ballot_sync(0xFFFFFFFFu, is_long);
+    // long runs (sparse key spaces, low-entropy texts): the whole warp fills them, coalesced
+    uint32_t long_mask = __ballot_sync(0xFFFFFFFFu, len >= 32);
     while (long_mask) {
         const int src = __ffs(long_mask) - 1;
         long_mask &= long_mask - 1;
-        const int64_t l0 = __shfl_sync(0xFFFFFFFFu, lo, src);
-        const int64_t h0 = __shfl_sync(0xFFFFFFFFu, hi, src);
-        const uint32_t v = (uint32_t)__shfl_sync(0xFFFFFFFFu, (unsigned long long)i, src);
-        for (int64_t j = l0 + lane; j <= h0; j += 32) dir[j] = v;
+        const uint64_t l0 = __shfl_sync(0xFFFFFFFFu, lo, src);
+        const uint64_t n0 = __shfl_sync(0xFFFFFFFFu, len, src);
+        const uint32_t vv = __shfl_sync(0xFFFFFFFFu, v, src);
+        for (uint64_t j = 2 + lane; j < n0; j += 32) dir[l0 + j] = vv;
     }
 }
 

@@ -168,7 +168,9 @@ struct kmer_b200_index {
     kb::DeviceIndex host_index{};
     kb::DeviceIndex *d_index = nullptr;
     uint32_t *d_flags = nullptr;     // u32[2]: error bits, unsorted-segment count
-    uint64_t *h_pinned = nullptr;    // small pinned scratch: [0] total hits, [1] flags
+    uint64_t *h_pinned = nullptr;    // small pinned scratch: [0] total hits, [1] flags, [2] max len, [3] gathers
+    unsigned long long *d_gathers = nullptr;  // profile mode: sectors gathered by the last search
+    uint64_t last_gathers = 0;
     uint64_t device_bytes = 0;
     bool reaches_end = true;  // the local slice ends at the end of the whole text
     double max_avg_bucket = 0;  // max over elements of (k-mers / distinct possible hashes)
@@ -524,6 +526,7 @@ int create_impl(const uint8_t *ranks, bool ranks_on_device, uint64_t n, uint32_t
     ix->h_pinned = (uint64_t *)pinned_get(8 * sizeof(uint64_t), &ix->h_pinned_cap);
     if (!ix->h_pinned) return bail(fail(KMER_B200_ERR_OUT_OF_MEMORY, "pinned host allocation failed"));
     KB_OR_BAIL(dev_alloc(ix, &ix->d_flags, 2, true));
+    KB_OR_BAIL(dev_alloc(ix, &ix->d_gathers, 1, true));
     KB_CUDA_OR_BAIL(cudaMemsetAsync(ix->d_flags, 0, 2 * sizeof(uint32_t), ix->stream));
 
     // ---- text: H2D (if needed) + pack
@@ -669,10 +672,12 @@ int search_device_impl(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *
     a.positions = nullptr;
     a.present = nullptr;
     a.error_flag = ix->d_flags;
+    a.gather_count = ix->cfg.profile >= 2 ? ix->d_gathers : nullptr;  // profile = 2: also count gathered sectors
+    if (a.gather_count) cudaMemsetAsync(ix->d_gathers, 0, sizeof(unsigned long long), st);
 
     cudaMemsetAsync(ix->d_flags, 0, 2 * sizeof(uint32_t), st);
     ix->prof.begin(K_SEARCH_COUNT, 0);
-    launch_search(a, kPassCount, st);
+    launch_search(a, a.gather_count ? kPassCountAccount : kPassCount, st);
     ix->prof.end();
     ix->prof.begin(K_OFFSETS_SCAN, 3.0 * 8 * Q, 3);
     launch_offsets_scan(res->offsets, Q, d_block_sums, st);
@@ -680,7 +685,9 @@ int search_device_impl(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *
     // total hits + flags back to the host: the one synchronisation point of a search
     cudaMemcpyAsync(&ix->h_pinned[0], res->offsets + Q, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(&ix->h_pinned[1], ix->d_flags, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    if (a.gather_count) cudaMemcpyAsync(&ix->h_pinned[3], ix->d_gathers, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
+    if (a.gather_count) ix->last_gathers = ix->h_pinned[3];
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -776,6 +783,7 @@ void kmer_b200_destroy(kmer_b200_index *ix) {
     dev_free(ix, ix->d_use_multi);
     dev_free(ix, ix->d_index);
     dev_free(ix, ix->d_flags);
+    dev_free(ix, ix->d_gathers);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     pinned_put(ix->h_pinned, ix->h_pinned_cap);
     for (auto e : ix->prof.pool) cudaEventDestroy(e);
@@ -1006,6 +1014,35 @@ void kmer_b200_stats_reset(kmer_b200_index *ix) {
 }
 
 uint64_t kmer_b200_device_bytes(const kmer_b200_index *ix) { return ix ? ix->device_bytes : 0; }
+
+uint64_t kmer_b200_last_search_gathers(const kmer_b200_index *ix) { return ix ? ix->last_gathers : 0; }
+
+int kmer_b200_gather_probe(uint64_t table_bytes, uint64_t n_gathers, void *stream, double *ms_out) {
+    if (!ms_out || table_bytes < 4096 || n_gathers == 0) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad probe arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint64_t *table = nullptr, *sink = nullptr;
+    const uint64_t n_words = table_bytes / 8;
+    KB_CUDA(cudaMalloc((void **)&table, n_words * 8));
+    KB_CUDA(cudaMalloc((void **)&sink, 8));
+    KB_CUDA(cudaMemsetAsync(table, 1, n_words * 8, st));
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    kb::launch_gather_probe(table, n_words, std::min<uint64_t>(n_gathers, 1u << 24), sink, st);  // warm-up
+    cudaEventRecord(a, st);
+    kb::launch_gather_probe(table, n_words, n_gathers, sink, st);
+    cudaEventRecord(b, st);
+    cudaError_t e = cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(table);
+    cudaFree(sink);
+    if (e != cudaSuccess) return fail(KMER_B200_ERR_CUDA, cudaGetErrorString(e));
+    *ms_out = ms;
+    return KMER_B200_OK;
+}
 
 uint64_t kmer_b200_fast_pow(uint64_t base, uint8_t exp) { return fast_pow(base, exp); }
 

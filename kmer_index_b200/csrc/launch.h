@@ -23,7 +23,7 @@ uint32_t sort_tile_size();
 uint32_t scan_chunk_tiles();
 
 // ---- search
-enum SearchPass : int { kPassCount = 0, kPassWrite = 1, kPassPresence = 2 };
+enum SearchPass : int { kPassCount = 0, kPassWrite = 1, kPassPresence = 2, kPassCountAccount = 3 };  // 3 = count + gather accounting
 
 struct SearchArgs {
     const DeviceIndex *index;        // device pointer
@@ -40,6 +40,7 @@ struct SearchArgs {
     uint8_t *unsorted;               // device, [Q]: 1 = the written segment still needs sorting (sub-k)
     uint32_t *positions;             // device (write pass)
     uint64_t *present;               // device (presence pass), [Q]
+    unsigned long long *gather_count;  // device or null: accumulates the 32-byte sectors the batch must gather
     uint32_t *error_flag;            // device u32[2]: [0] bit 0 = query rank >= sigma; [1] = #segments to sort
 };
 
@@ -51,6 +52,9 @@ uint64_t offsets_scan_blocks(uint64_t n_queries);
 // sort the flagged per-query segments of positions ascending (one CTA per flagged segment)
 void launch_segment_sort(uint32_t *d_positions, uint32_t *d_tmp, const uint64_t *d_offsets, const uint8_t *d_unsorted,
                          uint64_t n_queries, uint32_t key_bits, cudaStream_t stream);
+
+// ---- random-gather calibration (the denominator of the search roofline)
+void launch_gather_probe(const uint64_t *d_table, uint64_t n_words, uint64_t n_gathers, uint64_t *d_sink, cudaStream_t stream);
 
 // ---- synthetic inputs
 void launch_synth_ranks(uint8_t *d_out, uint64_t n, uint64_t start, uint32_t sigma, uint64_t seed, cudaStream_t stream);

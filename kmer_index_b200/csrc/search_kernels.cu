@@ -22,6 +22,9 @@ namespace kb {
 
 constexpr int kSearchWarps = 8;
 constexpr int kSearchThreads = kSearchWarps * 32;
+#ifndef KB_SEARCH_MIN_BLOCKS
+#define KB_SEARCH_MIN_BLOCKS 8  // <= 32 registers: 2048 threads per SM in flight beats the few spills (profiles/)
+#endif
 
 enum PlanKind : int { kExact = 0, kSubK = 1, kContig = 2, kBuggySingle = 3, kMultiSum = 4 };
 
@@ -128,8 +131,10 @@ __device__ __forceinline__ uint64_t load8(const uint8_t *p, uint32_t n_valid, bo
 // One group of G lanes per query (G = 8 for short queries and short buckets, 32 otherwise): the scalar part
 // of a query (plan, status) costs a warp instruction per group, not per warp, and G/32 more queries are in
 // flight per SM to cover the chain of dependent gathers (offsets -> ranks -> directory -> bucket -> text).
-template <int PASS, int G>
-__global__ void __launch_bounds__(kSearchThreads) search_kernel(const SearchArgs a) {
+template <int PASS_, int G>
+__global__ void __launch_bounds__(kSearchThreads, KB_SEARCH_MIN_BLOCKS) search_kernel(const SearchArgs a) {
+    constexpr bool kAccount = PASS_ == kPassCountAccount;  // count pass that also sums the gathered sectors
+    constexpr int PASS = kAccount ? (int)kPassCount : PASS_;
     constexpr int kGroups = kSearchThreads / G;
     extern __shared__ uint64_t smem_q[];
     const int lane = threadIdx.x & 31;
@@ -280,6 +285,9 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const SearchArgs
         return;
     }
 
+    // algorithmic gathers of this lane (32-byte sectors at data-dependent addresses), summed per batch when asked
+    uint32_t n_gather = 0;
+
     // ---- 3. presence of every indexed part + seed bucket -----------------------------------------------
     Range seed{0, 0};
     bool all_present = true;
@@ -298,6 +306,7 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const SearchArgs
                 const Element &E = ix.elem[e];
                 const uint32_t key = key_from_window(window64(qw, (uint64_t)o, T.bits), E.k, T.bits, T.sigma);
                 rg = bucket_of(E, key);
+                if (kAccount) n_gather += 1 + (E.shift ? 1 : 0);
             }
             if (base == 0) {
                 seed.lo = __shfl_sync(gmask, rg.lo, 0, G);
@@ -320,6 +329,10 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const SearchArgs
         // sharded: presence is a property of the whole text (kmer_index.hpp:216-227)
         const uint64_t full = nparts >= 64 ? ~0ull : ((1ull << nparts) - 1);
         all_present = (a.present_global[q] & full) == full;
+    }
+    if (kAccount && (!all_present || throw_after)) {
+        for (int o = G >> 1; o > 0; o >>= 1) n_gather += __shfl_xor_sync(gmask, n_gather, o, G);
+        if (gl == 0) atomicAdd(a.gather_count, (unsigned long long)n_gather);
     }
     if (!all_present) {  // kmer_index.hpp:224 / :524  return result_t()
         if (PASS == kPassCount && gl == 0) {
@@ -357,6 +370,7 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const SearchArgs
             if (c < shi) {
                 p = E0.pos[c];
                 ok = (uint64_t)p < ix.owned;
+                if (kAccount && ((c & 7) == 0 || c == slo)) ++n_gather;
             }
             const uint32_t b = GBALLOT(ok);
             if (PASS == kPassWrite && ok)
@@ -383,6 +397,8 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const SearchArgs
             if (c < seed.cnt) {
                 p = Es.pos[seed.lo + c];
                 ok = (uint64_t)p < ix.owned;
+                if (kAccount && (((seed.lo + c) & 7) == 0 || c == 0)) ++n_gather;
+                if (kAccount && ok && kind != kExact) n_gather += 1 + ((m - ks) * T.bits >> 8);
                 if (ok) {
                     if (kind == kContig) {
                         ok = match_span(T, qw, (uint64_t)p + ks, ks, m - ks);
@@ -403,6 +419,11 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const SearchArgs
                 a.positions[out_base + n_hits + __popc(b & lt_mask)] = p + (uint32_t)ix.global_base;
             n_hits += __popc(b);
         }
+    }
+    if (kAccount) {
+        if (kind == kSubK && gl == 0) n_gather += 2;  // the two directory lookups of the slab bounds
+        for (int o = G >> 1; o > 0; o >>= 1) n_gather += __shfl_xor_sync(gmask, n_gather, o, G);
+        if (gl == 0) atomicAdd(a.gather_count, (unsigned long long)n_gather);
     }
     if (PASS == kPassCount && gl == 0) {
         a.counts[q] = n_hits;
@@ -436,22 +457,27 @@ void launch_search(const SearchArgs &args, SearchPass pass, cudaStream_t stream)
     if (args.n_queries == 0) return;
     if (args.group == 1) {
         if (pass == kPassCount) launch_search_pg<kPassCount, 1>(args, stream);
+        if (pass == kPassCountAccount) launch_search_pg<kPassCountAccount, 1>(args, stream);
         if (pass == kPassWrite) launch_search_pg<kPassWrite, 1>(args, stream);
         if (pass == kPassPresence) launch_search_pg<kPassPresence, 1>(args, stream);
     } else if (args.group == 2) {
         if (pass == kPassCount) launch_search_pg<kPassCount, 2>(args, stream);
+        if (pass == kPassCountAccount) launch_search_pg<kPassCountAccount, 2>(args, stream);
         if (pass == kPassWrite) launch_search_pg<kPassWrite, 2>(args, stream);
         if (pass == kPassPresence) launch_search_pg<kPassPresence, 2>(args, stream);
     } else if (args.group == 4) {
         if (pass == kPassCount) launch_search_pg<kPassCount, 4>(args, stream);
+        if (pass == kPassCountAccount) launch_search_pg<kPassCountAccount, 4>(args, stream);
         if (pass == kPassWrite) launch_search_pg<kPassWrite, 4>(args, stream);
         if (pass == kPassPresence) launch_search_pg<kPassPresence, 4>(args, stream);
     } else if (args.group == 8) {
         if (pass == kPassCount) launch_search_pg<kPassCount, 8>(args, stream);
+        if (pass == kPassCountAccount) launch_search_pg<kPassCountAccount, 8>(args, stream);
         if (pass == kPassWrite) launch_search_pg<kPassWrite, 8>(args, stream);
         if (pass == kPassPresence) launch_search_pg<kPassPresence, 8>(args, stream);
     } else {
         if (pass == kPassCount) launch_search_pg<kPassCount, 32>(args, stream);
+        if (pass == kPassCountAccount) launch_search_pg<kPassCountAccount, 32>(args, stream);
         if (pass == kPassWrite) launch_search_pg<kPassWrite, 32>(args, stream);
         if (pass == kPassPresence) launch_search_pg<kPassPresence, 32>(args, stream);
     }
@@ -539,6 +565,36 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(uint64_t *__re
         if (base + j < n) v[base + j] = run;
         run += x[j];
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gather probe: independent random 8-byte reads (one 32-byte sector each) from a table much larger than L2,
+// 8 in flight per thread. Its sectors/s is the denominator of the search roofline ("gather roofline").
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_probe_kernel(const uint64_t *__restrict__ table, uint64_t n_words,
+                                                           uint64_t n_gathers, uint64_t *__restrict__ sink) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t acc = 0;
+    for (uint64_t g = t * 8; g < n_gathers; g += stride * 8) {
+        uint64_t v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            uint64_t x = (g + j) * 0x9E3779B97F4A7C15ull;
+            x ^= x >> 29;
+            x *= 0xBF58476D1CE4E5B9ull;
+            x ^= x >> 32;
+            v[j] = table[x % n_words];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += v[j];
+    }
+    if (acc == 0x1234567887654321ull) *sink = acc;  // keeps the loads alive
+}
+
+void launch_gather_probe(const uint64_t *d_table, uint64_t n_words, uint64_t n_gathers, uint64_t *d_sink,
+                         cudaStream_t stream) {
+    gather_probe_kernel<<<148 * 16, 256, 0, stream>>>(d_table, n_words, n_gathers, d_sink);
 }
 
 uint64_t offsets_scan_blocks(uint64_t n_queries) { return (n_queries + kScanBlock - 1) / kScanBlock; }
