@@ -300,7 +300,10 @@ def run_ours(args, wl):
             ev[0].record(stream)
             ix = make_index(False, host_text=h_text.numpy())
             ev[1].record(stream)
-            res = sharded.search_host(ix, h_q.numpy(), h_off.numpy().view(np.uint64), world, dev)
+            if world == 1:
+                res = sharded.search_host(ix, h_q.numpy(), h_off.numpy().view(np.uint64), world, dev)
+            else:
+                res = sharded.search_host(ix, h_q, h_off, world, dev)
             ev[2].record(stream)
             torch.cuda.synchronize()
             d2h = (Q + 1) * 8 + Q + 4 * int(res.positions.size)

@@ -118,15 +118,19 @@ const uint8_t *kmer_b200_result_status(const kmer_b200_result *r);     /* [Q] */
 void kmer_b200_result_free(kmer_b200_result *r);
 
 /* ---- sharded (multi-GPU) search, two phases around one cross-rank exchange.
-   Phase A fills d_present[Q] with one bit per indexed part of the query (bit j = part j occurs in this
-   shard); the caller ORs the masks of all shards (NCCL) and passes the result to phase B
-   (kmer_b200_search_batch_device_global), which then reproduces the reference's whole-text
-   early-return / throw decisions (kmer_index.hpp:216-227, :119-122) on every shard. */
+   Phase A fills d_present[Q] with one flag per indexed part of the query (part j occurs in this shard); the
+   caller combines the flags of all shards over NCCL and passes the result to phase B
+   (kmer_b200_search_batch_device_global), which then reproduces the reference's whole-text early-return /
+   throw decisions (kmer_index.hpp:216-227, :119-122) on every shard.
+   present_format 0: uint64_t per query, bit j = part j (combine with bitwise OR; up to 64 parts);
+   present_format 1: uint32_t per query, bit 4j = part j (combine with a SUM all-reduce over <= 15 shards --
+                     NCCL has no bitwise OR; up to 8 parts per query, longer queries report no hits). */
 int kmer_b200_presence_batch_device(kmer_b200_index *index, const uint8_t *d_q_ranks, const uint64_t *d_q_offsets,
-                                    uint64_t n_queries, uint64_t max_query_len, uint32_t mode, uint64_t *d_present);
+                                    uint64_t n_queries, uint64_t max_query_len, uint32_t mode, void *d_present,
+                                    uint32_t present_format);
 int kmer_b200_search_batch_device_global(kmer_b200_index *index, const uint8_t *d_q_ranks, const uint64_t *d_q_offsets,
                                          uint64_t n_queries, uint64_t max_query_len, uint32_t mode,
-                                         const uint64_t *d_present_global, kmer_b200_result **out);
+                                         const void *d_present_global, uint32_t present_format, kmer_b200_result **out);
 
 /* ---- introspection (parity tests and roofline accounting) */
 typedef struct kmer_b200_element_info {

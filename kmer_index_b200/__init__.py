@@ -238,14 +238,15 @@ class KmerIndex:
         return self._device_call(self._L.kmer_b200_count_batch_device, q_ptr, off_ptr, Q, max_len, mode)
 
     def presence_batch_device(self, q_ptr: int, off_ptr: int, Q: int, max_len: int, present_ptr: int,
-                              mode: int = MODE_DEFAULT) -> None:
+                              mode: int = MODE_DEFAULT, fmt: int = 0) -> None:
+        """fmt 0: uint64 bit mask per query (OR across shards); fmt 1: uint32 nibble flags (SUM across shards)."""
         _capi.check(self._L.kmer_b200_presence_batch_device(self._h, C.c_void_p(q_ptr), C.c_void_p(off_ptr), Q,
-                                                            max_len, mode, C.c_void_p(present_ptr)))
+                                                            max_len, mode, C.c_void_p(present_ptr), fmt))
 
     def search_batch_device_global(self, q_ptr: int, off_ptr: int, Q: int, max_len: int, present_global_ptr: int,
-                                   mode: int = MODE_DEFAULT):
+                                   mode: int = MODE_DEFAULT, fmt: int = 0):
         return self._device_call(self._L.kmer_b200_search_batch_device_global, q_ptr, off_ptr, Q, max_len, mode,
-                                 C.c_void_p(present_global_ptr))
+                                 C.c_void_p(present_global_ptr), fmt)
 
     # -- introspection
     def element_info(self, e: int) -> _capi.ElementInfo:

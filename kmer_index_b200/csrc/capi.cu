@@ -637,7 +637,8 @@ int search_geometry(const kmer_b200_index *ix, uint64_t max_len, uint32_t mode, 
 
 // queries already on the device; result stays on the device
 int search_device_impl(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off, uint64_t Q, uint64_t max_len,
-                       uint32_t mode, const uint64_t *d_present_global, SearchFlavor flavor, kmer_b200_result **out) {
+                       uint32_t mode, const void *d_present_global, uint32_t present_format, SearchFlavor flavor,
+                       kmer_b200_result **out) {
     using namespace kb;
     if (mode == UINT32_MAX) mode = ix->cfg.mode;
     if (mode > KMER_B200_MODE_CORRECT) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "unknown mode");
@@ -665,7 +666,8 @@ int search_device_impl(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *
     a.q_offsets = d_off;
     a.n_queries = Q;
     a.mode = mode;
-    a.present_global = d_present_global;
+    a.present_global = present_format == 0 ? (const uint64_t *)d_present_global : nullptr;
+    a.present_global4 = present_format == 1 ? (const uint32_t *)d_present_global : nullptr;
     a.counts = res->offsets;
     a.status = res->status;
     a.unsorted = d_unsorted;
@@ -799,7 +801,7 @@ int kmer_b200_search_batch_device(kmer_b200_index *ix, const uint8_t *d_q, const
     *out = nullptr;
     DeviceGuard guard(ix->device);
     std::lock_guard<std::mutex> lock(ix->mu);
-    return search_device_impl(ix, d_q, d_off, Q, max_len, mode, nullptr, kFlavorFull, out);
+    return search_device_impl(ix, d_q, d_off, Q, max_len, mode, nullptr, 0, kFlavorFull, out);
 }
 
 int kmer_b200_count_batch_device(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off, uint64_t Q,
@@ -808,23 +810,24 @@ int kmer_b200_count_batch_device(kmer_b200_index *ix, const uint8_t *d_q, const 
     *out = nullptr;
     DeviceGuard guard(ix->device);
     std::lock_guard<std::mutex> lock(ix->mu);
-    return search_device_impl(ix, d_q, d_off, Q, max_len, mode, nullptr, kFlavorCountOnly, out);
+    return search_device_impl(ix, d_q, d_off, Q, max_len, mode, nullptr, 0, kFlavorCountOnly, out);
 }
 
 int kmer_b200_search_batch_device_global(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off, uint64_t Q,
-                                         uint64_t max_len, uint32_t mode, const uint64_t *d_present_global,
-                                         kmer_b200_result **out) {
-    if (!ix || !out || (!d_off)) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
+                                         uint64_t max_len, uint32_t mode, const void *d_present_global,
+                                         uint32_t present_format, kmer_b200_result **out) {
+    if (!ix || !out || !d_off || !d_present_global || present_format > 1)
+        return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad argument");
     *out = nullptr;
     DeviceGuard guard(ix->device);
     std::lock_guard<std::mutex> lock(ix->mu);
-    return search_device_impl(ix, d_q, d_off, Q, max_len, mode, d_present_global, kFlavorFull, out);
+    return search_device_impl(ix, d_q, d_off, Q, max_len, mode, d_present_global, present_format, kFlavorFull, out);
 }
 
 int kmer_b200_presence_batch_device(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off, uint64_t Q,
-                                    uint64_t max_len, uint32_t mode, uint64_t *d_present) {
+                                    uint64_t max_len, uint32_t mode, void *d_present, uint32_t present_format) {
     using namespace kb;
-    if (!ix || !d_off || !d_present) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
+    if (!ix || !d_off || !d_present || present_format > 1) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad argument");
     if (mode == UINT32_MAX) mode = ix->cfg.mode;
     DeviceGuard guard(ix->device);
     std::lock_guard<std::mutex> lock(ix->mu);
@@ -835,7 +838,8 @@ int kmer_b200_presence_batch_device(kmer_b200_index *ix, const uint8_t *d_q, con
     a.q_offsets = d_off;
     a.n_queries = Q;
     a.mode = mode;
-    a.present = d_present;
+    a.present = present_format == 0 ? (uint64_t *)d_present : nullptr;
+    a.present4 = present_format == 1 ? (uint32_t *)d_present : nullptr;
     a.error_flag = ix->d_flags;
     ix->prof.begin(K_SEARCH_PRESENCE, 0);
     launch_search(a, kPassPresence, ix->stream);
@@ -868,7 +872,7 @@ int kmer_b200_search_batch(kmer_b200_index *ix, const uint8_t *q_ranks, const ui
     KB_CUDA(cudaStreamSynchronize(st));
     const uint64_t max_len = ix->h_pinned[2];
     kmer_b200_result *dres = nullptr;
-    int s = search_device_impl(ix, d_q - q_offsets[0], d_off, Q, max_len, mode, nullptr, kFlavorFull, &dres);
+    int s = search_device_impl(ix, d_q - q_offsets[0], d_off, Q, max_len, mode, nullptr, 0, kFlavorFull, &dres);
     dev_free(ix, d_q);
     dev_free(ix, d_off);
     dev_free(ix, d_max);

@@ -34,7 +34,9 @@ struct SearchArgs {
     uint32_t group;                  // lanes per query: 8 or 32
     uint32_t q_words;                // packed words reserved per query in shared memory (search_q_words)
     uint32_t max_len;                // longest query the shared-memory reservation (and the shard halo) allows
-    const uint64_t *present_global;  // device or null: OR over shards of the presence masks
+    const uint64_t *present_global;  // device or null: OR over shards of the presence masks (format 0)
+    const uint32_t *present_global4; // device or null: SUM over shards of the nibble-encoded masks (format 1)
+    uint32_t *present4;              // device (presence pass, format 1), [Q]: bit 4j = part j occurs in this shard
     uint64_t *counts;                // device, [Q + 1]: per-query hit counts (count pass), then offsets
     uint8_t *status;                 // device, [Q]
     uint8_t *unsorted;               // device, [Q]: 1 = the written segment still needs sorting (sub-k)

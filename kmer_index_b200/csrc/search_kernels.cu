@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(kSearchThreads, KB_SEARCH_MIN_BLOCKS) search_k
                 a.status[q] = (uint8_t)status;
                 a.unsorted[q] = 0;
             } else if (PASS == kPassPresence) {
-                a.present[q] = 0;
+                if (a.present4 != nullptr) a.present4[q] = 0; else a.present[q] = 0;
             }
         }
         return;
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(kSearchThreads, KB_SEARCH_MIN_BLOCKS) search_k
                 a.status[q] = (uint8_t)status;
                 a.unsorted[q] = 0;
             } else if (PASS == kPassPresence) {
-                a.present[q] = 0;
+                if (a.present4 != nullptr) a.present4[q] = 0; else a.present[q] = 0;
             }
         }
         return;
@@ -322,13 +322,29 @@ __global__ void __launch_bounds__(kSearchThreads, KB_SEARCH_MIN_BLOCKS) search_k
         }
     }
     if (PASS == kPassPresence) {
-        if (gl == 0) a.present[q] = present_mask;
+        if (gl == 0) {
+            if (a.present4 != nullptr) {
+                // one nibble per part so that a SUM all-reduce over <= 15 shards acts as an OR
+                uint32_t enc = 0;
+                for (uint32_t j = 0; j < 8; ++j) enc |= (uint32_t)((present_mask >> j) & 1) << (4 * j);
+                a.present4[q] = enc;
+            } else {
+                a.present[q] = present_mask;
+            }
+        }
         return;
     }
-    if (a.present_global != nullptr && kind != kSubK) {
+    if (kind != kSubK) {
         // sharded: presence is a property of the whole text (kmer_index.hpp:216-227)
-        const uint64_t full = nparts >= 64 ? ~0ull : ((1ull << nparts) - 1);
-        all_present = (a.present_global[q] & full) == full;
+        if (a.present_global != nullptr) {
+            const uint64_t full = nparts >= 64 ? ~0ull : ((1ull << nparts) - 1);
+            all_present = (a.present_global[q] & full) == full;
+        } else if (a.present_global4 != nullptr) {
+            uint32_t x = a.present_global4[q];
+            x = (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u;  // nibble j non-zero <=> part j occurs somewhere
+            const uint32_t full = nparts >= 8 ? 0x11111111u : (0x11111111u >> (4 * (8 - nparts)));
+            all_present = (x & full) == full && nparts <= 8;
+        }
     }
     if (kAccount && (!all_present || throw_after)) {
         for (int o = G >> 1; o > 0; o >>= 1) n_gather += __shfl_xor_sync(gmask, n_gather, o, G);

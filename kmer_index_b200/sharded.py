@@ -82,43 +82,74 @@ def place_shard(final, shard_offsets, shard_positions, write_base):
 
 def merge_to_rank0(offsets, positions, world: int, rank: int, dist):
     """Gather every shard's (offsets[Q+1], positions) on rank 0 and merge; returns (offsets, positions) on
-    rank 0 and (None, None) elsewhere. offsets: int64, positions: any 32-bit integer dtype."""
+    rank 0 and (None, None) elsewhere. offsets: int64, positions: a 32-bit integer dtype.
+
+    Only queries that have hits on a shard travel: (query id, count) pairs plus the positions. With random
+    queries over a k chosen so that sigma^k >~ n almost every per-shard list is empty, so this is a small
+    fraction of the dense count matrix."""
     import torch
     Q = offsets.numel() - 1
-    counts = (offsets[1:] - offsets[:-1]).to(torch.int32)
-    if rank == 0:
-        all_counts = [torch.empty_like(counts) for _ in range(world)]
-        dist.gather(counts, all_counts, dst=0)
-        cm = torch.stack(all_counts).to(torch.int64)
-        g_off, base = merge_offsets(cm)
-        final = torch.empty(int(g_off[-1].item()), dtype=positions.dtype, device=positions.device)
-        place_shard(final, offsets, positions, base[0])
-        for r in range(1, world):
-            tot = int(cm[r].sum().item())
-            buf = torch.empty(tot, dtype=positions.dtype, device=positions.device)
-            if tot:
-                dist.recv(buf, src=r)
-            off_r = torch.zeros(Q + 1, dtype=torch.int64, device=positions.device)
-            torch.cumsum(cm[r], 0, out=off_r[1:])
-            place_shard(final, off_r, buf, base[r])
-        return g_off, final
-    dist.gather(counts, None, dst=0)
-    if positions.numel():
-        dist.send(positions, dst=0)
-    return None, None
+    dev = offsets.device
+    counts = offsets[1:] - offsets[:-1]
+    qids = torch.nonzero(counts).squeeze(1)                      # ascending query ids with >= 1 hit here
+    cnts = counts[qids]
+    meta = torch.tensor([qids.numel(), positions.numel()], dtype=torch.int64, device=dev)
+    all_meta = torch.empty(2 * world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_meta, meta)
+    all_meta = all_meta.view(world, 2).cpu()
+    if rank != 0:
+        if qids.numel():
+            dist.send(torch.cat([qids, cnts]), dst=0)
+            dist.send(positions, dst=0)
+        return None, None
+    shards = [(qids, cnts, positions)]
+    for r in range(1, world):
+        nq, npos = int(all_meta[r, 0]), int(all_meta[r, 1])
+        if nq == 0:
+            shards.append((qids[:0], cnts[:0], positions[:0]))
+            continue
+        buf = torch.empty(2 * nq, dtype=torch.int64, device=dev)
+        dist.recv(buf, src=r)
+        pos_r = torch.empty(npos, dtype=positions.dtype, device=dev)
+        dist.recv(pos_r, src=r)
+        shards.append((buf[:nq], buf[nq:], pos_r))
+    total = torch.zeros(Q, dtype=torch.int64, device=dev)
+    for q_r, c_r, _ in shards:
+        total.index_add_(0, q_r, c_r)
+    g_off = torch.zeros(Q + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(total, 0, out=g_off[1:])
+    final = torch.empty(int(g_off[-1].item()), dtype=positions.dtype, device=dev)
+    filled = total.zero_()                                       # reuse: hits of query q already placed
+    for q_r, c_r, p_r in shards:                                 # rank order == ascending position order
+        if p_r.numel() == 0:
+            continue
+        start = g_off[q_r] + filled[q_r]
+        filled.index_add_(0, q_r, c_r)
+        seg_off = torch.cumsum(c_r, 0) - c_r
+        seg = torch.repeat_interleave(torch.arange(q_r.numel(), device=dev), c_r)
+        idx = torch.arange(p_r.numel(), dtype=torch.int64, device=dev)
+        final[start[seg] + (idx - seg_off[seg])] = p_r
+    return g_off, final
 
 
 # ----------------------------------------------------------------------------------------------------------
 # GPU paths used by bench.py
 # ----------------------------------------------------------------------------------------------------------
 def _global_presence(ix, q_ptr, off_ptr, Q, max_len, world, dev):
+    """Per-query flags "part j occurs somewhere in the text", combined over all shards. Returns (tensor, format)
+    for KmerIndex.search_batch_device_global."""
     import torch
     import torch.distributed as dist
+    max_parts = max(1, max_len // min(ix.ks))
+    if max_parts <= 8 and world <= 15:
+        # nibble per part, SUM all-reduce acts as OR (NCCL has no bitwise OR); 4 bytes per query over NVLink
+        present = torch.empty(Q, dtype=torch.int32, device=dev)
+        ix.presence_batch_device(q_ptr, off_ptr, Q, max_len, present.data_ptr(), fmt=1)
+        dist.all_reduce(present, op=dist.ReduceOp.SUM)
+        return present, 1
     present = torch.empty(Q, dtype=torch.int64, device=dev)
-    ix.presence_batch_device(q_ptr, off_ptr, Q, max_len, present.data_ptr())
-    max_parts = max_len // min(ix.ks) + 1
-    narrow = present.to(torch.uint8) if max_parts <= 8 else present   # fewer bytes over NVLink
-    return all_gather_fold(narrow, world, dist).to(torch.int64)
+    ix.presence_batch_device(q_ptr, off_ptr, Q, max_len, present.data_ptr(), fmt=0)
+    return all_gather_fold(present, world, dist), 0
 
 
 def search_device(ix, q_ptr: int, off_ptr: int, Q: int, max_len: int, world: int, dev, count_only: bool = False) -> int:
@@ -132,8 +163,8 @@ def search_device(ix, q_ptr: int, off_ptr: int, Q: int, max_len: int, world: int
         return hits
     import torch.distributed as dist
     rank = dist.get_rank()
-    present = _global_presence(ix, q_ptr, off_ptr, Q, max_len, world, dev)
-    res = ix.search_batch_device_global(q_ptr, off_ptr, Q, max_len, present.data_ptr())
+    present, fmt = _global_presence(ix, q_ptr, off_ptr, Q, max_len, world, dev)
+    res = ix.search_batch_device_global(q_ptr, off_ptr, Q, max_len, present.data_ptr(), fmt=fmt)
     offsets = torch.as_tensor(res.offsets(), device=dev)
     positions = (torch.as_tensor(res.positions(), device=dev) if res.n_positions
                  else torch.empty(0, dtype=torch.int32, device=dev))
@@ -144,31 +175,51 @@ def search_device(ix, q_ptr: int, off_ptr: int, Q: int, max_len: int, world: int
     return hits
 
 
-def search_host(ix, h_q: np.ndarray, h_off: np.ndarray, world: int, dev):
-    """Whole-job search through host buffers. world == 1: the plain C-ABI host call. Sharded: H2D on every rank,
-    device search + NCCL merge, D2H of the merged result on rank 0."""
+_pinned_cache: dict = {}
+
+
+def _pinned(name: str, n: int, dtype):
+    """Grow-only pinned host buffers for the merged result (pinned allocation is slow; reuse across calls)."""
+    import torch
+    buf = _pinned_cache.get(name)
+    if buf is None or buf.numel() < n or buf.dtype != dtype:
+        buf = torch.empty(max(n, 1), dtype=dtype, pin_memory=True)
+        _pinned_cache[name] = buf
+    return buf[:n]
+
+
+def search_host(ix, h_q, h_off, world: int, dev):
+    """Whole-job search through host buffers. world == 1: the plain C-ABI host call (numpy arrays). Sharded:
+    h_q (uint8) / h_off (int64) are pinned torch tensors; H2D on every rank, device search + NCCL merge, D2H of
+    the merged result into pinned memory on rank 0."""
     import torch
     if world == 1:
         return ix.search_batch(h_q, h_off, copy=False)
     import torch.distributed as dist
     from . import BatchResult
     rank = dist.get_rank()
-    Q = h_off.size - 1
-    d_q = torch.from_numpy(h_q).to(dev, non_blocking=True)
-    d_off = torch.from_numpy(h_off.view(np.int64)).to(dev, non_blocking=True)
+    Q = h_off.numel() - 1
+    d_q = h_q.to(dev, non_blocking=True)
+    d_off = h_off.to(dev, non_blocking=True)
     max_len = int((d_off[1:] - d_off[:-1]).max().item()) if Q else 0
-    present = _global_presence(ix, d_q.data_ptr(), d_off.data_ptr(), Q, max_len, world, dev)
-    res = ix.search_batch_device_global(d_q.data_ptr(), d_off.data_ptr(), Q, max_len, present.data_ptr())
+    present, fmt = _global_presence(ix, d_q.data_ptr(), d_off.data_ptr(), Q, max_len, world, dev)
+    res = ix.search_batch_device_global(d_q.data_ptr(), d_off.data_ptr(), Q, max_len, present.data_ptr(), fmt=fmt)
     offsets = torch.as_tensor(res.offsets(), device=dev)
     positions = (torch.as_tensor(res.positions(), device=dev) if res.n_positions
                  else torch.empty(0, dtype=torch.int32, device=dev))
-    status = torch.as_tensor(res.status(), device=dev).clone()
+    status = torch.as_tensor(res.status(), device=dev)
     g_off, final = merge_to_rank0(offsets, positions, world, rank, dist)
-    out = None
+    h_status = _pinned("status", Q, torch.uint8)
+    h_status.copy_(status, non_blocking=True)
     if rank == 0:
-        out = BatchResult(g_off.cpu().numpy().view(np.uint64), final.cpu().numpy().view(np.uint32), status.cpu().numpy())
+        h_goff = _pinned("offsets", Q + 1, torch.int64)
+        h_pos = _pinned("positions", final.numel(), torch.int32)
+        h_goff.copy_(g_off, non_blocking=True)
+        h_pos.copy_(final, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        out = BatchResult(h_goff.numpy().view(np.uint64), h_pos.numpy().view(np.uint32), h_status.numpy())
     else:
-        out = BatchResult(np.zeros(Q + 1, np.uint64), np.zeros(0, np.uint32), status.cpu().numpy())
-    torch.cuda.current_stream().synchronize()
+        torch.cuda.current_stream().synchronize()
+        out = BatchResult(np.zeros(Q + 1, np.uint64), np.zeros(0, np.uint32), h_status.numpy())
     res.free()
     return out

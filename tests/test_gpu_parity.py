@@ -140,9 +140,10 @@ def test_edge_cases(kb):
             ix.search(np.zeros(10001, np.uint8))
 
 
+@pytest.mark.parametrize("fmt", [0, 1])
 @pytest.mark.parametrize("sigma,ks,n,m_lo,m_hi,world", [(4, [16], 400_000, 16, 64, 2), (4, [12], 300_000, 13, 64, 3),
                                                        (4, [5, 7, 9, 11, 13], 200_000, 4, 40, 2), (15, [8], 200_000, 3, 20, 4)])
-def test_sharded_search_emulated_on_one_gpu(kb, oracle_mod, sigma, ks, n, m_lo, m_hi, world):
+def test_sharded_search_emulated_on_one_gpu(kb, oracle_mod, sigma, ks, n, m_lo, m_hi, world, fmt):
     """The sharded path (position-range shards with halo, presence OR, global-presence search, rank-order merge)
     run as `world` indices on one GPU must equal the unsharded reference-exact result."""
     import torch
@@ -161,14 +162,15 @@ def test_sharded_search_emulated_on_one_gpu(kb, oracle_mod, sigma, ks, n, m_lo, 
     try:
         masks = []
         for ix in idx:
-            m = torch.zeros(Q, dtype=torch.int64, device=dev)
-            ix.presence_batch_device(d_q.data_ptr(), d_off.data_ptr(), Q, m_hi, m.data_ptr())
+            m = torch.zeros(Q, dtype=torch.int64 if fmt == 0 else torch.int32, device=dev)
+            ix.presence_batch_device(d_q.data_ptr(), d_off.data_ptr(), Q, m_hi, m.data_ptr(), fmt=fmt)
             torch.cuda.synchronize()
             masks.append(m)
-        present = sharded.fold_presence(torch.stack(masks))
+        # what the NCCL exchange computes: OR of bit masks (fmt 0) / SUM of nibble flags (fmt 1)
+        present = sharded.fold_presence(torch.stack(masks)) if fmt == 0 else torch.stack(masks).sum(0).to(torch.int32)
         per_shard = []
         for ix in idx:
-            r = ix.search_batch_device_global(d_q.data_ptr(), d_off.data_ptr(), Q, m_hi, present.data_ptr())
+            r = ix.search_batch_device_global(d_q.data_ptr(), d_off.data_ptr(), Q, m_hi, present.data_ptr(), fmt=fmt)
             torch.cuda.synchronize()
             o = torch.as_tensor(r.offsets(), device=dev).clone()
             p = (torch.as_tensor(r.positions(), device=dev).clone() if r.n_positions
