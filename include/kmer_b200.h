@@ -66,7 +66,8 @@ typedef struct kmer_b200_config {
     uint32_t directory_bits; /* 0 = automatic; otherwise log2 of the directory size cap per element */
     uint32_t profile;        /* 1 = bracket every kernel launch with CUDA events (kmer_b200_stats);
                                 2 = additionally count the 32-byte sectors each search gathers */
-    uint32_t reserved;
+    uint32_t reserved;       /* bit 0: never build auxiliary k' = m elements for sub-k query lengths (saves memory;
+                                those results are then sorted by the segment-sort kernel instead) */
 } kmer_b200_config;
 
 typedef struct kmer_b200_index kmer_b200_index;

@@ -140,7 +140,8 @@ class KmerIndex:
 
     def __init__(self, text, sigma: int, ks: Sequence[int], *, mode: int = MODE_REFERENCE_EXACT, device: int = -1,
                  stream: int | None = None, profile: bool = False, shard_begin: int = 0, n_total: int = 0,
-                 halo: int = 0, directory_bits: int = 0, text_device_ptr: int | None = None, n: int | None = None):
+                 halo: int = 0, directory_bits: int = 0, text_device_ptr: int | None = None, n: int | None = None,
+                 aux_elements: bool = True):
         L = _capi.lib()
         self._L = L
         self._h = C.c_void_p()
@@ -156,6 +157,7 @@ class KmerIndex:
         cfg.n_total = n_total
         cfg.halo = halo
         cfg.directory_bits = directory_bits
+        cfg.reserved = 0 if aux_elements else 1   # bit 0: no auxiliary k' = m elements for sub-k lengths
         ks_a = np.asarray(self.ks, dtype=np.uint32)
         if text_device_ptr is not None:
             self.n = int(n)

@@ -167,7 +167,7 @@ struct kmer_b200_index {
     uint8_t *d_sum_elem = nullptr, *d_use_multi = nullptr;
     kb::DeviceIndex host_index{};
     kb::DeviceIndex *d_index = nullptr;
-    uint32_t *d_flags = nullptr;     // u32[2]: error bits, unsorted-segment count
+    uint32_t *d_flags = nullptr;     // u32[4]: error bits, unsorted-segment count, u64 mask of sub-k lengths w/o aux
     uint64_t *h_pinned = nullptr;    // small pinned scratch: [0] total hits, [1] flags, [2] max len, [3] gathers
     unsigned long long *d_gathers = nullptr;  // profile mode: sectors gathered by the last search
     uint64_t last_gathers = 0;
@@ -332,7 +332,7 @@ void build_scheme(SchemeHost *ix) {
     }
 }
 
-int build_element(kmer_b200_index *ix, uint32_t k, HostElement &he) {
+int build_element(kmer_b200_index *ix, uint32_t k, HostElement &he, bool auxiliary = false) {
     using namespace kb;
     cudaStream_t st = ix->stream;
     Profiler &pf = ix->prof;
@@ -420,7 +420,8 @@ int build_element(kmer_b200_index *ix, uint32_t k, HostElement &he) {
     he.dev.keys = he.d_keys;
     he.dev.pos = he.d_pos;
     he.bytes = 2 * n_kmers * sizeof(uint32_t) + dir_entries * sizeof(uint32_t);
-    ix->max_avg_bucket = std::max(ix->max_avg_bucket, (double)n_kmers / (double)std::min<uint64_t>(key_space, n_kmers));
+    if (!auxiliary)
+        ix->max_avg_bucket = std::max(ix->max_avg_bucket, (double)n_kmers / (double)std::min<uint64_t>(key_space, n_kmers));
     return 0;
 }
 
@@ -525,9 +526,9 @@ int create_impl(const uint8_t *ranks, bool ranks_on_device, uint64_t n, uint32_t
     }
     ix->h_pinned = (uint64_t *)pinned_get(8 * sizeof(uint64_t), &ix->h_pinned_cap);
     if (!ix->h_pinned) return bail(fail(KMER_B200_ERR_OUT_OF_MEMORY, "pinned host allocation failed"));
-    KB_OR_BAIL(dev_alloc(ix, &ix->d_flags, 2, true));
+    KB_OR_BAIL(dev_alloc(ix, &ix->d_flags, 4, true));
     KB_OR_BAIL(dev_alloc(ix, &ix->d_gathers, 1, true));
-    KB_CUDA_OR_BAIL(cudaMemsetAsync(ix->d_flags, 0, 2 * sizeof(uint32_t), ix->stream));
+    KB_CUDA_OR_BAIL(cudaMemsetAsync(ix->d_flags, 0, 4 * sizeof(uint32_t), ix->stream));
 
     // ---- text: H2D (if needed) + pack
     const uint8_t *d_ranks = ranks;
@@ -548,14 +549,24 @@ int create_impl(const uint8_t *ranks, bool ranks_on_device, uint64_t n, uint32_t
     ix->elems.resize(n_ks);
     for (uint32_t i = 0; i < n_ks; ++i) KB_OR_BAIL(build_element(ix, ks[i], ix->elems[i]));
 
-    // ---- scheme tables
+    // ---- scheme tables (depend on the ks only: cached per process, a multi-k table costs ~50 ms of host time)
     {
-        SchemeHost sh;
-        sh.ks = ix->ks;
-        build_scheme(&sh);
-        ix->sum_off.swap(sh.sum_off);
-        ix->sum_elem.swap(sh.sum_elem);
-        ix->use_multi.swap(sh.use_multi);
+        static std::mutex mu;
+        static std::vector<SchemeHost> cache;
+        std::lock_guard<std::mutex> lock(mu);
+        const SchemeHost *hit = nullptr;
+        for (const auto &c : cache)
+            if (c.ks == ix->ks) hit = &c;
+        if (!hit) {
+            if (cache.size() >= 16) cache.erase(cache.begin());
+            cache.emplace_back();
+            cache.back().ks = ix->ks;
+            build_scheme(&cache.back());
+            hit = &cache.back();
+        }
+        ix->sum_off = hit->sum_off;
+        ix->sum_elem = hit->sum_elem;
+        ix->use_multi = hit->use_multi;
     }
     KB_OR_BAIL(dev_alloc(ix, &ix->d_sum_off, ix->sum_off.size(), true));
     KB_OR_BAIL(dev_alloc(ix, &ix->d_sum_elem, ix->sum_elem.size(), true));
@@ -577,6 +588,7 @@ int create_impl(const uint8_t *ranks, bool ranks_on_device, uint64_t n, uint32_t
     D.sharded = sharded ? 1 : 0;
     for (uint32_t i = 0; i < n_ks; ++i) D.elem[i] = ix->elems[i].dev;
     D.scheme = kb::SchemeTables{ix->d_sum_off, ix->d_sum_elem, ix->d_use_multi};
+    std::memset(D.aux_for_len, 0xFF, sizeof(D.aux_for_len));
     for (uint32_t e = 0; e <= 32; ++e) {
         // saturating: only compared against 1e7 and used as slab width when < sigma^k <= 2^32
         const double approx = std::pow((double)sigma, (double)e);
@@ -601,6 +613,39 @@ int create_impl(const uint8_t *ranks, bool ranks_on_device, uint64_t n, uint32_t
     return KMER_B200_OK;
 #undef KB_OR_BAIL
 #undef KB_CUDA_OR_BAIL
+}
+
+// Build auxiliary k' = m elements for the sub-k query lengths in `want` (bit m) that have none yet, memory
+// permitting; returns the lengths that still have none. See DeviceIndex::aux_for_len.
+uint64_t ensure_aux_elements(kmer_b200_index *ix, uint64_t want) {
+    uint64_t missing = 0;
+    bool changed = false;
+    for (uint32_t m = 1; m < 64; ++m) {
+        if (!((want >> m) & 1) || ix->host_index.aux_for_len[m] != 0xFF) continue;
+        const size_t slot = ix->elems.size();
+        const double key_space = std::pow((double)ix->sigma, (double)m);
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const double need = 16.0 * (double)ix->n + 4.0 * key_space + (64 << 20);  // two (key, pos) buffers + directory
+        if (slot >= (size_t)kb::kMaxElements || m > ix->n || m * ix->bits > 64 || key_space > 4294967296.0 ||
+            need * 1.5 > (double)free_b) {
+            missing |= 1ull << m;
+            continue;
+        }
+        HostElement he;
+        if (build_element(ix, m, he, true) != 0) {
+            cudaGetLastError();
+            missing |= 1ull << m;
+            continue;
+        }
+        ix->elems.push_back(he);
+        ix->host_index.elem[slot] = he.dev;
+        ix->host_index.aux_for_len[m] = (uint8_t)slot;
+        changed = true;
+    }
+    if (changed)
+        cudaMemcpyAsync(ix->d_index, &ix->host_index, sizeof(kb::DeviceIndex), cudaMemcpyHostToDevice, ix->stream);
+    return missing;
 }
 
 enum SearchFlavor { kFlavorFull, kFlavorCountOnly };
@@ -677,7 +722,7 @@ int search_device_impl(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *
     a.gather_count = ix->cfg.profile >= 2 ? ix->d_gathers : nullptr;  // profile = 2: also count gathered sectors
     if (a.gather_count) cudaMemsetAsync(ix->d_gathers, 0, sizeof(unsigned long long), st);
 
-    cudaMemsetAsync(ix->d_flags, 0, 2 * sizeof(uint32_t), st);
+    cudaMemsetAsync(ix->d_flags, 0, 4 * sizeof(uint32_t), st);
     ix->prof.begin(K_SEARCH_COUNT, 0);
     launch_search(a, a.gather_count ? kPassCountAccount : kPassCount, st);
     ix->prof.end();
@@ -686,7 +731,7 @@ int search_device_impl(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *
     ix->prof.end();
     // total hits + flags back to the host: the one synchronisation point of a search
     cudaMemcpyAsync(&ix->h_pinned[0], res->offsets + Q, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
-    cudaMemcpyAsync(&ix->h_pinned[1], ix->d_flags, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&ix->h_pinned[4], ix->d_flags, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
     if (a.gather_count) cudaMemcpyAsync(&ix->h_pinned[3], ix->d_gathers, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
     if (a.gather_count) ix->last_gathers = ix->h_pinned[3];
@@ -696,13 +741,18 @@ int search_device_impl(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *
         return bail(fail(KMER_B200_ERR_CUDA, std::string("search (count pass): ") + cudaGetErrorString(e)));
     }
     const uint64_t total = ix->h_pinned[0];
-    const uint32_t *flags = reinterpret_cast<const uint32_t *>(&ix->h_pinned[1]);
+    const uint32_t *flags = reinterpret_cast<const uint32_t *>(&ix->h_pinned[4]);
+    const uint64_t want_aux = ix->h_pinned[5];  // flags[2..3]: sub-k query lengths answered by slab enumeration
     if (flags[0] & 1u) {
         dev_free(ix, d_unsorted);
         dev_free(ix, d_block_sums);
         return bail(fail(KMER_B200_ERR_INVALID_RANK, "a query contains a rank >= sigma"));
     }
     res->n_positions = total;
+    // sub-k lengths seen in this batch get an auxiliary k' = m element (kept for later batches); the write pass
+    // below already reads through it, so those results come out sorted and skip the segment sort
+    uint64_t aux_missing = want_aux;
+    if (flavor == kFlavorFull && want_aux && ix->cfg.reserved == 0) aux_missing = ensure_aux_elements(ix, want_aux);
     if (flavor == kFlavorFull && total > 0) {
         if (dev_alloc(ix, &res->positions, total, false)) {
             dev_free(ix, d_unsorted);
@@ -713,7 +763,7 @@ int search_device_impl(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *
         ix->prof.begin(K_SEARCH_WRITE, 0);
         launch_search(a, kPassWrite, st);
         ix->prof.end();
-        if (flags[1] != 0) {
+        if (flags[1] != 0 && aux_missing != 0) {
             uint32_t *d_tmp = nullptr;
             if (dev_alloc(ix, &d_tmp, total, false)) {
                 dev_free(ix, d_unsorted);
@@ -933,7 +983,7 @@ void kmer_b200_result_free(kmer_b200_result *r) {
     delete r;
 }
 
-uint32_t kmer_b200_n_elements(const kmer_b200_index *ix) { return ix ? (uint32_t)ix->elems.size() : 0; }
+uint32_t kmer_b200_n_elements(const kmer_b200_index *ix) { return ix ? (uint32_t)ix->ks.size() : 0; }
 
 int kmer_b200_element_info_get(const kmer_b200_index *ix, uint32_t e, kmer_b200_element_info *out) {
     if (!ix || !out || e >= ix->elems.size()) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad element");

@@ -85,6 +85,11 @@ struct DeviceIndex {
     SchemeTables scheme;
     uint64_t pow_sigma[33];  // sigma^e for e <= 32 (saturating at 2^63)
     uint8_t elem_by_k_desc[kMaxElements];  // element indices ordered by k descending (_all_ks, :410)
+    // Auxiliary elements (slots n_elems..): an index with k' = m built on demand for a query length m that the
+    // plan answers by prefix enumeration (m < k). The bucket of the whole query in the k' = m index IS the
+    // sorted union of the sigma^(k-m) buckets the reference enumerates (kmer_index.hpp:138-144) plus the
+    // end-of-text positions of check_last_kmer (:90-112), so the result is identical and needs no sort.
+    uint8_t aux_for_len[64];  // element slot for query length m < 64, 0xFF = none
 };
 
 }  // namespace kb

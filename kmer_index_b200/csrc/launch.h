@@ -43,7 +43,8 @@ struct SearchArgs {
     uint32_t *positions;             // device (write pass)
     uint64_t *present;               // device (presence pass), [Q]
     unsigned long long *gather_count;  // device or null: accumulates the 32-byte sectors the batch must gather
-    uint32_t *error_flag;            // device u32[2]: [0] bit 0 = query rank >= sigma; [1] = #segments to sort
+    uint32_t *error_flag;            // device u32[4]: [0] bit 0 = query rank >= sigma; [1] = #segments to sort;
+                                     // [2..3] = u64 mask of sub-k query lengths that found no auxiliary element
 };
 
 void launch_search(const SearchArgs &args, SearchPass pass, cudaStream_t stream);

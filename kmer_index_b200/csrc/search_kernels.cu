@@ -285,32 +285,57 @@ __global__ void __launch_bounds__(kSearchThreads, KB_SEARCH_MIN_BLOCKS) search_k
         return;
     }
 
+    bool was_subk = false;
+    if (kind == kSubK) {
+        if (m < 64 && ix.aux_for_len[m] != 0xFF) {  // an auxiliary k' = m element answers it as an exact lookup
+            e0 = ix.aux_for_len[m];
+            k0 = m;
+            kind = kExact;
+            nparts = 1;
+            from_list = false;
+            was_subk = true;  // no whole-text presence rule applies to prefix enumeration
+        } else if (PASS == kPassCount && m < 64 && gl == 0) {
+            atomicOr(reinterpret_cast<unsigned long long *>(a.error_flag + 2), 1ull << m);  // ask the host for one
+        }
+    }
+
     // algorithmic gathers of this lane (32-byte sectors at data-dependent addresses), summed per batch when asked
     uint32_t n_gather = 0;
 
-    // ---- 3. presence of every indexed part + seed bucket -----------------------------------------------
-    Range seed{0, 0};
+    // ---- 3. presence of the indexed parts ------------------------------------------------------------------
+    // The reference looks every indexed part up first and returns empty when one is absent (:216-227, :516-527).
+    // Where the plan is a contiguous comparison of the whole query that rule is redundant -- an occurrence of
+    // the query contains an occurrence of every part -- so the lookups are only done when the outcome depends on
+    // them: the throw for short rests happens only if all parts are present, and the two defective plans do not
+    // constrain every part's position.
+    const bool need_presence = throw_after || kind == kBuggySingle || kind == kMultiSum;
+    if (PASS == kPassPresence && (!need_presence || was_subk)) {  // nothing about this query depends on other shards
+        if (gl == 0) {
+            if (a.present4 != nullptr) a.present4[q] = 0; else a.present[q] = 0;
+        }
+        return;
+    }
+    Range seed{0, 0};       // candidate list: positions pos[seed.lo .. +cnt) of element seed_e, match start = pos - seed_d
+    uint32_t seed_e = e0, seed_d = 0;
     bool all_present = true;
     uint64_t present_mask = 0;
-    if (kind != kSubK) {
+    if (kind != kSubK && need_presence) {
+        uint64_t best_cnt = ~0ull;
         for (uint32_t base = 0; base < nparts; base += G) {
             const uint32_t j = base + gl;
             const bool valid = j < nparts;
             Range rg{0, 0};
+            uint32_t e = e0, o = j * k0, d = j * k0;
             if (valid) {
-                uint32_t e = e0, o = j * k0;
                 if (from_list) {  // `last_k = current_k` is not cumulative, kmer_index.hpp:526
                     e = S[j];
                     o = j ? ix.elem[S[j - 1]].k : 0;
+                    d = j * ix.elem[S[0]].k;  // expected at text offset j * k_0 (:535,544)
                 }
                 const Element &E = ix.elem[e];
                 const uint32_t key = key_from_window(window64(qw, (uint64_t)o, T.bits), E.k, T.bits, T.sigma);
                 rg = bucket_of(E, key);
                 if (kAccount) n_gather += 1 + (E.shift ? 1 : 0);
-            }
-            if (base == 0) {
-                seed.lo = __shfl_sync(gmask, rg.lo, 0, G);
-                seed.cnt = __shfl_sync(gmask, rg.cnt, 0, G);
             }
             const uint32_t here = GBALLOT(valid && rg.cnt != 0);
             if (base < 64) present_mask |= (uint64_t)here << base;
@@ -318,6 +343,26 @@ __global__ void __launch_bounds__(kSearchThreads, KB_SEARCH_MIN_BLOCKS) search_k
             if (here != want) {
                 all_present = false;
                 if (PASS != kPassPresence) break;
+            }
+            // seed from the shortest bucket among the parts whose position the plan constrains:
+            // all of them, except the middle parts of the kmer_index.hpp:314 defect
+            const bool seedable = valid && (kind != kBuggySingle || j == 0 || j + 1 == nparts);
+            uint64_t c = seedable ? rg.cnt : ~0ull;
+            uint32_t who = gl;
+            for (int off = G >> 1; off > 0; off >>= 1) {
+                const uint64_t oc = __shfl_xor_sync(gmask, c, off, G);
+                const uint32_t ow = __shfl_xor_sync(gmask, who, off, G);
+                if (oc < c || (oc == c && ow < who)) {
+                    c = oc;
+                    who = ow;
+                }
+            }
+            if (c < best_cnt) {
+                best_cnt = c;
+                seed.lo = __shfl_sync(gmask, rg.lo, who, G);
+                seed.cnt = c;
+                seed_e = __shfl_sync(gmask, e, who, G);
+                seed_d = __shfl_sync(gmask, d, who, G);
             }
         }
     }
@@ -334,7 +379,7 @@ __global__ void __launch_bounds__(kSearchThreads, KB_SEARCH_MIN_BLOCKS) search_k
         }
         return;
     }
-    if (kind != kSubK) {
+    if (kind != kSubK && need_presence && !was_subk) {
         // sharded: presence is a property of the whole text (kmer_index.hpp:216-227)
         if (a.present_global != nullptr) {
             const uint64_t full = nparts >= 64 ? ~0ull : ((1ull << nparts) - 1);
@@ -379,7 +424,9 @@ __global__ void __launch_bounds__(kSearchThreads, KB_SEARCH_MIN_BLOCKS) search_k
         const uint64_t slo = lower_bound_key(E0, lo_key);
         const uint64_t shi = lower_bound_key(E0, lo_key + width);
         if (shi - slo > 1) unsorted = E0.keys[slo] != E0.keys[shi - 1];
-        for (uint64_t c0 = slo; c0 < shi; c0 += G) {
+        const bool count_by_range = PASS != kPassWrite && ix.owned == T.n;  // unsharded: every hit is owned
+        if (count_by_range) n_hits = shi - slo;
+        for (uint64_t c0 = slo; c0 < shi && !count_by_range; c0 += G) {
             const uint64_t c = c0 + gl;
             uint32_t p = 0;
             bool ok = false;
@@ -404,29 +451,100 @@ __global__ void __launch_bounds__(kSearchThreads, KB_SEARCH_MIN_BLOCKS) search_k
             n_hits += __popc(b);
         }
     } else {
-        const Element &Es = from_list ? ix.elem[S[0]] : E0;
+        if (!need_presence) {
+            // contiguous plan (or exact lookup): any element finds the same occurrences, so seed from the one with
+            // the largest k <= m (the shortest candidate list); the rest of the query is compared against the text
+            if (kind == kContig) {
+                for (uint32_t i = 0; i < ix.n_elems; ++i) {
+                    const uint32_t e = ix.elem_by_k_desc[i];
+                    if (ix.elem[e].k <= m) {
+                        seed_e = e;
+                        break;
+                    }
+                }
+            }
+            const Element &E = ix.elem[seed_e];
+            if (gl == 0) {
+                const uint32_t key = key_from_window(window64(qw, 0, T.bits), E.k, T.bits, T.sigma);
+                seed = bucket_of(E, key);
+                if (kAccount) n_gather += 1 + (E.shift ? 1 : 0);
+            }
+            seed.lo = __shfl_sync(gmask, seed.lo, 0, G);
+            seed.cnt = __shfl_sync(gmask, seed.cnt, 0, G);
+        } else if (kind == kBuggySingle && ix.n_elems > 1) {
+            // the last full part and the rest are one contiguous stretch of k0 + rest symbols: an element with a
+            // larger k (multi-k index) gives a shorter candidate list for it
+            const uint32_t last = (P - 1) * k0;
+            uint32_t e = e0;
+            for (uint32_t i = 0; i < ix.n_elems; ++i) {
+                const uint32_t c = ix.elem_by_k_desc[i];
+                if (ix.elem[c].k <= k0 + rest) {
+                    e = c;
+                    break;
+                }
+            }
+            if (ix.elem[e].k > k0) {
+                Range alt{0, 0};
+                if (gl == 0) {
+                    const Element &E = ix.elem[e];
+                    alt = bucket_of(E, key_from_window(window64(qw, (uint64_t)last, T.bits), E.k, T.bits, T.sigma));
+                    if (kAccount) n_gather += 1 + (E.shift ? 1 : 0);
+                }
+                alt.lo = __shfl_sync(gmask, alt.lo, 0, G);
+                alt.cnt = __shfl_sync(gmask, alt.cnt, 0, G);
+                if (alt.cnt < seed.cnt) {
+                    seed = alt;
+                    seed_e = e;
+                    seed_d = last;
+                }
+            }
+        }
+        const Element &Es = ix.elem[seed_e];
         const uint32_t ks = Es.k;
-        for (uint64_t c0 = 0; c0 < seed.cnt; c0 += G) {
+        const uint32_t kf = from_list ? ix.elem[S[0]].k : k0;  // k of part 0 (text stride of the multi-k defect)
+        bool count_by_range = PASS != kPassWrite && kind == kExact && ix.owned == T.n;
+        if (count_by_range) n_hits = seed.cnt;
+        if (PASS == kPassWrite && kind == kExact && ix.owned == T.n) {
+            // the whole bucket is the result: a plain copy with 8 independent loads in flight per lane
+            const uint32_t *src = Es.pos + seed.lo;
+            uint32_t *dst = a.positions + out_base;
+            const uint32_t gb = (uint32_t)ix.global_base;
+            uint64_t c = gl;
+            for (; c + 7 * G < seed.cnt; c += 8 * G) {
+                uint32_t v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = src[c + j * G];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dst[c + j * G] = v[j] + gb;
+            }
+            for (; c < seed.cnt; c += G) dst[c] = src[c] + gb;
+            count_by_range = true;  // skips the generic loop below
+        }
+        for (uint64_t c0 = 0; c0 < seed.cnt && !count_by_range; c0 += G) {
             const uint64_t c = c0 + gl;
             uint32_t p = 0;
             bool ok = false;
             if (c < seed.cnt) {
-                p = Es.pos[seed.lo + c];
-                ok = (uint64_t)p < ix.owned;
+                const uint32_t at = Es.pos[seed.lo + c];
+                ok = at >= seed_d;
+                p = at - seed_d;
+                ok = ok && (uint64_t)p < ix.owned;
                 if (kAccount && (((seed.lo + c) & 7) == 0 || c == 0)) ++n_gather;
-                if (kAccount && ok && kind != kExact) n_gather += 1 + ((m - ks) * T.bits >> 8);
+                if (kAccount && ok && kind != kExact) n_gather += 1 + (m * T.bits >> 8);
                 if (ok) {
                     if (kind == kContig) {
                         ok = match_span(T, qw, (uint64_t)p + ks, ks, m - ks);
                     } else if (kind == kBuggySingle) {
                         const uint32_t last = (P - 1) * k0;  // query offset of the last full part
+                        ok = match_span(T, qw, (uint64_t)p, 0, k0);
                         for (uint32_t j = 1; ok && j + 1 < P; ++j) ok = match_span(T, qw, (uint64_t)p + j * k0, last, k0);
                         if (ok) ok = match_span(T, qw, (uint64_t)p + last, last, k0 + rest);
                     } else if (kind == kMultiSum) {
                         // part i is read at query offset k_{i-1} and expected at text offset i*k_0
                         // (kmer_index.hpp:526 and :535,544)
+                        ok = match_span(T, qw, (uint64_t)p, 0, kf);
                         for (uint32_t i = 1; ok && i < nparts; ++i)
-                            ok = match_span(T, qw, (uint64_t)p + (uint64_t)i * ks, ix.elem[S[i - 1]].k, ix.elem[S[i]].k);
+                            ok = match_span(T, qw, (uint64_t)p + (uint64_t)i * kf, ix.elem[S[i - 1]].k, ix.elem[S[i]].k);
                     }
                 }
             }
