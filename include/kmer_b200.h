@@ -133,6 +133,15 @@ int kmer_b200_search_batch_device_global(kmer_b200_index *index, const uint8_t *
                                          uint64_t n_queries, uint64_t max_query_len, uint32_t mode,
                                          const void *d_present_global, uint32_t present_format, kmer_b200_result **out);
 
+/* Fused form of the two phases (presence flags in format 1 only): begin runs the count pass and writes this
+   shard's flags to d_present4[Q]; the caller SUM-all-reduces them; finish applies the whole-text rule, then
+   scans and writes the positions. One pass over the queries less than presence + search_global. */
+typedef struct kmer_b200_pending kmer_b200_pending;
+int kmer_b200_search_sharded_begin(kmer_b200_index *index, const uint8_t *d_q_ranks, const uint64_t *d_q_offsets,
+                                   uint64_t n_queries, uint64_t max_query_len, uint32_t mode, uint32_t *d_present4,
+                                   kmer_b200_pending **out);
+int kmer_b200_search_sharded_finish(kmer_b200_pending *pending, const uint32_t *d_present4_global, kmer_b200_result **out);
+
 /* ---- introspection (parity tests and roofline accounting) */
 typedef struct kmer_b200_element_info {
     uint32_t k;

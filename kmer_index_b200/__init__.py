@@ -250,6 +250,20 @@ class KmerIndex:
         return self._device_call(self._L.kmer_b200_search_batch_device_global, q_ptr, off_ptr, Q, max_len, mode,
                                  C.c_void_p(present_global_ptr), fmt)
 
+    def search_sharded_begin(self, q_ptr: int, off_ptr: int, Q: int, max_len: int, present4_ptr: int,
+                             mode: int = MODE_DEFAULT):
+        """Count pass of a sharded search; this shard's presence flags (uint32 nibble format) go to present4_ptr.
+        Returns the pending handle for search_sharded_finish()."""
+        h = C.c_void_p()
+        _capi.check(self._L.kmer_b200_search_sharded_begin(self._h, C.c_void_p(q_ptr), C.c_void_p(off_ptr), Q, max_len,
+                                                           mode, C.c_void_p(present4_ptr), C.byref(h)))
+        return h
+
+    def search_sharded_finish(self, pending, present4_global_ptr: int, Q: int) -> "DeviceResult":
+        r = C.c_void_p()
+        _capi.check(self._L.kmer_b200_search_sharded_finish(pending, C.c_void_p(present4_global_ptr), C.byref(r)))
+        return DeviceResult(self._L, r, Q)
+
     # -- introspection
     def element_info(self, e: int) -> _capi.ElementInfo:
         info = _capi.ElementInfo()

@@ -66,6 +66,9 @@ SYMBOLS = {
                                                   C.c_uint32, C.c_void_p, C.c_uint32]),
     "kmer_b200_search_batch_device_global": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
                                                        C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "kmer_b200_search_sharded_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
+                                                 C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "kmer_b200_search_sharded_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "kmer_b200_n_elements": (C.c_uint32, [C.c_void_p]),
     "kmer_b200_element_info_get": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(ElementInfo)]),
     "kmer_b200_element_positions": (C.c_int, [C.c_void_p, C.c_uint32, u32p, C.c_uint64]),

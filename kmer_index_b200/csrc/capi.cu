@@ -681,9 +681,29 @@ int search_geometry(const kmer_b200_index *ix, uint64_t max_len, uint32_t mode, 
 }
 
 // queries already on the device; result stays on the device
-int search_device_impl(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off, uint64_t Q, uint64_t max_len,
-                       uint32_t mode, const void *d_present_global, uint32_t present_format, SearchFlavor flavor,
-                       kmer_b200_result **out) {
+// A search in flight between its count pass and its write pass (the sharded path exchanges presence flags
+// between the two).
+struct PendingSearch {
+    kmer_b200_index *ix = nullptr;
+    kmer_b200_result *res = nullptr;
+    kb::SearchArgs args{};
+    uint8_t *d_unsorted = nullptr;
+    uint8_t *d_defer = nullptr;
+    uint64_t *d_block_sums = nullptr;
+    void release() {
+        dev_free(ix, d_unsorted);
+        dev_free(ix, d_defer);
+        dev_free(ix, d_block_sums);
+        d_unsorted = d_defer = nullptr;
+        d_block_sums = nullptr;
+    }
+};
+
+// count pass. d_present4 != nullptr: deferred mode -- the per-part presence flags go to d_present4 and the
+// whole-text presence rule is applied later by search_finish().
+int search_begin(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off, uint64_t Q, uint64_t max_len,
+                 uint32_t mode, const void *d_present_global, uint32_t present_format, uint32_t *d_present4,
+                 PendingSearch *p) {
     using namespace kb;
     if (mode == UINT32_MAX) mode = ix->cfg.mode;
     if (mode > KMER_B200_MODE_CORRECT) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "unknown mode");
@@ -693,18 +713,21 @@ int search_device_impl(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *
     res->index = ix;
     res->on_device = true;
     res->n_queries = Q;
+    p->ix = ix;
+    p->res = res;
     auto bail = [&](int code) {
+        p->release();
         kmer_b200_result_free(res);
+        p->res = nullptr;
         return code;
     };
-    uint8_t *d_unsorted = nullptr;
-    uint64_t *d_block_sums = nullptr;
     if (dev_alloc(ix, &res->offsets, Q + 1, false) || dev_alloc(ix, &res->status, Q, false) ||
-        dev_alloc(ix, &d_unsorted, Q, false) || dev_alloc(ix, &d_block_sums, offsets_scan_blocks(Q) + 1, false))
+        dev_alloc(ix, &p->d_unsorted, Q, false) || dev_alloc(ix, &p->d_block_sums, offsets_scan_blocks(Q) + 1, false) ||
+        (d_present4 && dev_alloc(ix, &p->d_defer, Q, false)))
         return bail(KMER_B200_ERR_OUT_OF_MEMORY);
 
-    // shared-memory reservation per query: ceil(max_len / 32) rounds of bits/2 words, plus two padding words
-    SearchArgs a{};
+    SearchArgs &a = p->args;
+    a = SearchArgs{};
     if (int s = search_geometry(ix, max_len, mode, &a)) return bail(s);
     a.index = ix->d_index;
     a.q_ranks = d_q;
@@ -715,19 +738,49 @@ int search_device_impl(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *
     a.present_global4 = present_format == 1 ? (const uint32_t *)d_present_global : nullptr;
     a.counts = res->offsets;
     a.status = res->status;
-    a.unsorted = d_unsorted;
+    a.unsorted = p->d_unsorted;
     a.positions = nullptr;
     a.present = nullptr;
+    a.present4 = d_present4;
+    a.defer = p->d_defer;
     a.error_flag = ix->d_flags;
     a.gather_count = ix->cfg.profile >= 2 ? ix->d_gathers : nullptr;  // profile = 2: also count gathered sectors
     if (a.gather_count) cudaMemsetAsync(ix->d_gathers, 0, sizeof(unsigned long long), st);
 
     cudaMemsetAsync(ix->d_flags, 0, 4 * sizeof(uint32_t), st);
     ix->prof.begin(K_SEARCH_COUNT, 0);
-    launch_search(a, a.gather_count ? kPassCountAccount : kPassCount, st);
+    launch_search(a, d_present4 ? kPassCountDeferred : (a.gather_count ? kPassCountAccount : kPassCount), st);
     ix->prof.end();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return bail(fail(KMER_B200_ERR_CUDA, std::string("search (count pass): ") + cudaGetErrorString(e)));
+    return KMER_B200_OK;
+}
+
+// [deferred: apply the whole-text presence rule] -> scan -> write pass -> segment sort
+int search_finish(PendingSearch *p, const uint32_t *d_present4_global, SearchFlavor flavor, kmer_b200_result **out) {
+    using namespace kb;
+    kmer_b200_index *ix = p->ix;
+    kmer_b200_result *res = p->res;
+    cudaStream_t st = ix->stream;
+    SearchArgs &a = p->args;
+    const uint64_t Q = a.n_queries;
+    auto bail = [&](int code) {
+        p->release();
+        kmer_b200_result_free(res);
+        p->res = nullptr;
+        return code;
+    };
+    if (p->d_defer) {
+        if (!d_present4_global) return bail(fail(KMER_B200_ERR_INVALID_ARGUMENT, "missing global presence flags"));
+        ix->prof.begin(K_SEARCH_PRESENCE, 9.0 * Q);
+        launch_finalize_deferred(res->offsets, res->status, p->d_defer, d_present4_global, Q, st);
+        ix->prof.end();
+        a.present4 = nullptr;
+        a.defer = nullptr;
+        a.present_global4 = d_present4_global;  // the write pass applies the same rule
+    }
     ix->prof.begin(K_OFFSETS_SCAN, 3.0 * 8 * Q, 3);
-    launch_offsets_scan(res->offsets, Q, d_block_sums, st);
+    launch_offsets_scan(res->offsets, Q, p->d_block_sums, st);
     ix->prof.end();
     // total hits + flags back to the host: the one synchronisation point of a search
     cudaMemcpyAsync(&ix->h_pinned[0], res->offsets + Q, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
@@ -743,46 +796,47 @@ int search_device_impl(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *
     const uint64_t total = ix->h_pinned[0];
     const uint32_t *flags = reinterpret_cast<const uint32_t *>(&ix->h_pinned[4]);
     const uint64_t want_aux = ix->h_pinned[5];  // flags[2..3]: sub-k query lengths answered by slab enumeration
-    if (flags[0] & 1u) {
-        dev_free(ix, d_unsorted);
-        dev_free(ix, d_block_sums);
-        return bail(fail(KMER_B200_ERR_INVALID_RANK, "a query contains a rank >= sigma"));
-    }
+    if (flags[0] & 1u) return bail(fail(KMER_B200_ERR_INVALID_RANK, "a query contains a rank >= sigma"));
     res->n_positions = total;
     // sub-k lengths seen in this batch get an auxiliary k' = m element (kept for later batches); the write pass
     // below already reads through it, so those results come out sorted and skip the segment sort
     uint64_t aux_missing = want_aux;
     if (flavor == kFlavorFull && want_aux && ix->cfg.reserved == 0) aux_missing = ensure_aux_elements(ix, want_aux);
     if (flavor == kFlavorFull && total > 0) {
-        if (dev_alloc(ix, &res->positions, total, false)) {
-            dev_free(ix, d_unsorted);
-            dev_free(ix, d_block_sums);
-            return bail(KMER_B200_ERR_OUT_OF_MEMORY);
-        }
+        if (dev_alloc(ix, &res->positions, total, false)) return bail(KMER_B200_ERR_OUT_OF_MEMORY);
         a.positions = res->positions;
         ix->prof.begin(K_SEARCH_WRITE, 0);
         launch_search(a, kPassWrite, st);
         ix->prof.end();
         if (flags[1] != 0 && aux_missing != 0) {
             uint32_t *d_tmp = nullptr;
-            if (dev_alloc(ix, &d_tmp, total, false)) {
-                dev_free(ix, d_unsorted);
-                dev_free(ix, d_block_sums);
-                return bail(KMER_B200_ERR_OUT_OF_MEMORY);
-            }
+            if (dev_alloc(ix, &d_tmp, total, false)) return bail(KMER_B200_ERR_OUT_OF_MEMORY);
             const uint32_t key_bits = bit_length(ix->cfg.shard_begin + ix->n);
             ix->prof.begin(K_SEGMENT_SORT, 0);
-            launch_segment_sort(res->positions, d_tmp, res->offsets, d_unsorted, Q, key_bits, st);
+            launch_segment_sort(res->positions, d_tmp, res->offsets, p->d_unsorted, Q, key_bits, st);
             ix->prof.end();
             dev_free(ix, d_tmp);
         }
     }
-    dev_free(ix, d_unsorted);
-    dev_free(ix, d_block_sums);
+    p->release();
     e = cudaGetLastError();
-    if (e != cudaSuccess) return bail(fail(KMER_B200_ERR_CUDA, std::string("search (write pass): ") + cudaGetErrorString(e)));
+    if (e != cudaSuccess) {
+        kmer_b200_result_free(res);
+        p->res = nullptr;
+        return fail(KMER_B200_ERR_CUDA, std::string("search (write pass): ") + cudaGetErrorString(e));
+    }
     *out = res;
+    p->res = nullptr;
     return KMER_B200_OK;
+}
+
+// queries already on the device; result stays on the device
+int search_device_impl(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off, uint64_t Q, uint64_t max_len,
+                       uint32_t mode, const void *d_present_global, uint32_t present_format, SearchFlavor flavor,
+                       kmer_b200_result **out) {
+    PendingSearch p;
+    KB_TRY(search_begin(ix, d_q, d_off, Q, max_len, mode, d_present_global, present_format, nullptr, &p));
+    return search_finish(&p, nullptr, flavor, out);
 }
 
 __global__ void max_len_kernel(const uint64_t *__restrict__ off, uint64_t Q, unsigned long long *out) {
@@ -872,6 +926,38 @@ int kmer_b200_search_batch_device_global(kmer_b200_index *ix, const uint8_t *d_q
     DeviceGuard guard(ix->device);
     std::lock_guard<std::mutex> lock(ix->mu);
     return search_device_impl(ix, d_q, d_off, Q, max_len, mode, d_present_global, present_format, kFlavorFull, out);
+}
+
+struct kmer_b200_pending {
+    PendingSearch p;
+};
+
+int kmer_b200_search_sharded_begin(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off, uint64_t Q,
+                                   uint64_t max_len, uint32_t mode, uint32_t *d_present4, kmer_b200_pending **out) {
+    if (!ix || !out || !d_off || !d_present4) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    DeviceGuard guard(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    kmer_b200_pending *h = new (std::nothrow) kmer_b200_pending();
+    if (!h) return fail(KMER_B200_ERR_OUT_OF_MEMORY, "host allocation failed");
+    int s = search_begin(ix, d_q, d_off, Q, max_len, mode, nullptr, 0, d_present4, &h->p);
+    if (s != 0) {
+        delete h;
+        return s;
+    }
+    *out = h;
+    return KMER_B200_OK;
+}
+
+int kmer_b200_search_sharded_finish(kmer_b200_pending *h, const uint32_t *d_present4_global, kmer_b200_result **out) {
+    if (!h || !out || !d_present4_global) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    kmer_b200_index *ix = h->p.ix;
+    DeviceGuard guard(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    int s = search_finish(&h->p, d_present4_global, kFlavorFull, out);
+    delete h;
+    return s;
 }
 
 int kmer_b200_presence_batch_device(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off, uint64_t Q,

@@ -23,7 +23,13 @@ uint32_t sort_tile_size();
 uint32_t scan_chunk_tiles();
 
 // ---- search
-enum SearchPass : int { kPassCount = 0, kPassWrite = 1, kPassPresence = 2, kPassCountAccount = 3 };  // 3 = count + gather accounting
+enum SearchPass : int {
+    kPassCount = 0,
+    kPassWrite = 1,
+    kPassPresence = 2,
+    kPassCountAccount = 3,   // count + gather accounting
+    kPassCountDeferred = 4   // sharded: count + per-part presence flags, whole-text rule applied afterwards
+};
 
 struct SearchArgs {
     const DeviceIndex *index;        // device pointer
@@ -41,6 +47,7 @@ struct SearchArgs {
     uint8_t *status;                 // device, [Q]
     uint8_t *unsorted;               // device, [Q]: 1 = the written segment still needs sorting (sub-k)
     uint32_t *positions;             // device (write pass)
+    uint8_t *defer;                  // device (deferred count pass), [Q]: 0x40 | throw << 7 | parts, 0 = no rule applies
     uint64_t *present;               // device (presence pass), [Q]
     unsigned long long *gather_count;  // device or null: accumulates the 32-byte sectors the batch must gather
     uint32_t *error_flag;            // device u32[4]: [0] bit 0 = query rank >= sigma; [1] = #segments to sort;
@@ -49,6 +56,9 @@ struct SearchArgs {
 
 void launch_search(const SearchArgs &args, SearchPass pass, cudaStream_t stream);
 uint32_t search_q_words(uint32_t group, uint32_t bits, uint64_t max_len);
+// deferred count pass epilogue: zero the counts / set THROW according to the combined presence flags
+void launch_finalize_deferred(uint64_t *d_counts, uint8_t *d_status, const uint8_t *d_defer, const uint32_t *d_present4_global,
+                              uint64_t n_queries, cudaStream_t stream);
 // in place: counts[0..Q) -> exclusive offsets, counts[Q] = total
 void launch_offsets_scan(uint64_t *d_counts, uint64_t n_queries, uint64_t *d_block_sums, cudaStream_t stream);
 uint64_t offsets_scan_blocks(uint64_t n_queries);

@@ -134,7 +134,8 @@ __device__ __forceinline__ uint64_t load8(const uint8_t *p, uint32_t n_valid, bo
 template <int PASS_, int G>
 __global__ void __launch_bounds__(kSearchThreads, KB_SEARCH_MIN_BLOCKS) search_kernel(const SearchArgs a) {
     constexpr bool kAccount = PASS_ == kPassCountAccount;  // count pass that also sums the gathered sectors
-    constexpr int PASS = kAccount ? (int)kPassCount : PASS_;
+    constexpr bool kDefer = PASS_ == kPassCountDeferred;   // count pass that leaves the whole-text rule for later
+    constexpr int PASS = (kAccount || kDefer) ? (int)kPassCount : PASS_;
     constexpr int kGroups = kSearchThreads / G;
     extern __shared__ uint64_t smem_q[];
     const int lane = threadIdx.x & 31;
@@ -177,6 +178,10 @@ __global__ void __launch_bounds__(kSearchThreads, KB_SEARCH_MIN_BLOCKS) search_k
                 a.counts[q] = 0;
                 a.status[q] = (uint8_t)status;
                 a.unsorted[q] = 0;
+                if (kDefer) {
+                    a.defer[q] = 0;
+                    a.present4[q] = 0;
+                }
             } else if (PASS == kPassPresence) {
                 if (a.present4 != nullptr) a.present4[q] = 0; else a.present[q] = 0;
             }
@@ -278,6 +283,10 @@ __global__ void __launch_bounds__(kSearchThreads, KB_SEARCH_MIN_BLOCKS) search_k
                 a.counts[q] = 0;
                 a.status[q] = (uint8_t)status;
                 a.unsorted[q] = 0;
+                if (kDefer) {
+                    a.defer[q] = 0;
+                    a.present4[q] = 0;
+                }
             } else if (PASS == kPassPresence) {
                 if (a.present4 != nullptr) a.present4[q] = 0; else a.present[q] = 0;
             }
@@ -342,7 +351,8 @@ __global__ void __launch_bounds__(kSearchThreads, KB_SEARCH_MIN_BLOCKS) search_k
             const uint32_t want = GBALLOT(valid);
             if (here != want) {
                 all_present = false;
-                if (PASS != kPassPresence) break;
+                // stop early only when the local answer is final (unsharded search)
+                if (PASS != kPassPresence && !kDefer && a.present_global == nullptr && a.present_global4 == nullptr) break;
             }
             // seed from the shortest bucket among the parts whose position the plan constrains:
             // all of them, except the middle parts of the kmer_index.hpp:314 defect
@@ -379,7 +389,30 @@ __global__ void __launch_bounds__(kSearchThreads, KB_SEARCH_MIN_BLOCKS) search_k
         }
         return;
     }
-    if (kind != kSubK && need_presence && !was_subk) {
+    if (kDefer) {
+        // publish this shard's flags and what the epilogue has to decide; the local absence of a part never
+        // empties the result here (another shard may hold it), it only empties the local candidate list
+        const bool rule = kind != kSubK && need_presence && !was_subk;
+        if (gl == 0) {
+            uint32_t enc = 0;
+            if (rule)
+                for (uint32_t j = 0; j < 8; ++j) enc |= (uint32_t)((present_mask >> j) & 1) << (4 * j);
+            a.present4[q] = enc;
+            // more than 8 parts cannot be encoded: parts = 63 makes the epilogue report no hits
+            a.defer[q] = rule ? (uint8_t)(0x40u | (throw_after ? 0x80u : 0u) | (nparts <= 8 ? nparts : 63u)) : 0;
+        }
+        if (rule && throw_after) {  // either THROW or empty: no hits in both cases
+            if (gl == 0) {
+                a.counts[q] = 0;
+                a.status[q] = KMER_B200_QUERY_OK;
+                a.unsorted[q] = 0;
+            }
+            return;
+        }
+        all_present = true;
+        throw_after = false;
+    }
+    if (!kDefer && kind != kSubK && need_presence && !was_subk) {
         // sharded: presence is a property of the whole text (kmer_index.hpp:216-227)
         if (a.present_global != nullptr) {
             const uint64_t full = nparts >= 64 ? ~0ull : ((1ull << nparts) - 1);
@@ -578,6 +611,34 @@ static void launch_search_pg(const SearchArgs &args, cudaStream_t stream) {
     search_kernel<PASS, G><<<(unsigned)blocks, kSearchThreads, smem, stream>>>(args);
 }
 
+// epilogue of the deferred count pass: the whole-text presence rule (kmer_index.hpp:216-227, :234 -> :119)
+__global__ void __launch_bounds__(256) finalize_deferred_kernel(uint64_t *__restrict__ counts, uint8_t *__restrict__ status,
+                                                                const uint8_t *__restrict__ defer,
+                                                                const uint32_t *__restrict__ present4_global, uint64_t n) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const uint32_t d = defer[q];
+    if (!(d & 0x40u)) return;
+    const uint32_t parts = d & 0x3Fu;
+    uint32_t x = present4_global[q];
+    x = (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u;
+    const uint32_t full = parts >= 8 ? 0x11111111u : (0x11111111u >> (4 * (8 - parts)));
+    const bool all_present = parts <= 8 && (x & full) == full;
+    if (!all_present) {
+        counts[q] = 0;
+    } else if (d & 0x80u) {
+        counts[q] = 0;
+        status[q] = KMER_B200_QUERY_THROW_INVALID_ARGUMENT;
+    }
+}
+
+void launch_finalize_deferred(uint64_t *d_counts, uint8_t *d_status, const uint8_t *d_defer, const uint32_t *d_present4_global,
+                              uint64_t n_queries, cudaStream_t stream) {
+    if (n_queries == 0) return;
+    finalize_deferred_kernel<<<(unsigned)((n_queries + 255) / 256), 256, 0, stream>>>(d_counts, d_status, d_defer,
+                                                                                        d_present4_global, n_queries);
+}
+
 uint32_t search_q_words(uint32_t group, uint32_t bits, uint64_t max_len) {
     // rounds of 8 * group symbols, group * bits / 8 words each, plus two zero words
     const uint32_t lpw = 8 / bits;
@@ -592,26 +653,31 @@ void launch_search(const SearchArgs &args, SearchPass pass, cudaStream_t stream)
     if (args.group == 1) {
         if (pass == kPassCount) launch_search_pg<kPassCount, 1>(args, stream);
         if (pass == kPassCountAccount) launch_search_pg<kPassCountAccount, 1>(args, stream);
+        if (pass == kPassCountDeferred) launch_search_pg<kPassCountDeferred, 1>(args, stream);
         if (pass == kPassWrite) launch_search_pg<kPassWrite, 1>(args, stream);
         if (pass == kPassPresence) launch_search_pg<kPassPresence, 1>(args, stream);
     } else if (args.group == 2) {
         if (pass == kPassCount) launch_search_pg<kPassCount, 2>(args, stream);
         if (pass == kPassCountAccount) launch_search_pg<kPassCountAccount, 2>(args, stream);
+        if (pass == kPassCountDeferred) launch_search_pg<kPassCountDeferred, 2>(args, stream);
         if (pass == kPassWrite) launch_search_pg<kPassWrite, 2>(args, stream);
         if (pass == kPassPresence) launch_search_pg<kPassPresence, 2>(args, stream);
     } else if (args.group == 4) {
         if (pass == kPassCount) launch_search_pg<kPassCount, 4>(args, stream);
         if (pass == kPassCountAccount) launch_search_pg<kPassCountAccount, 4>(args, stream);
+        if (pass == kPassCountDeferred) launch_search_pg<kPassCountDeferred, 4>(args, stream);
         if (pass == kPassWrite) launch_search_pg<kPassWrite, 4>(args, stream);
         if (pass == kPassPresence) launch_search_pg<kPassPresence, 4>(args, stream);
     } else if (args.group == 8) {
         if (pass == kPassCount) launch_search_pg<kPassCount, 8>(args, stream);
         if (pass == kPassCountAccount) launch_search_pg<kPassCountAccount, 8>(args, stream);
+        if (pass == kPassCountDeferred) launch_search_pg<kPassCountDeferred, 8>(args, stream);
         if (pass == kPassWrite) launch_search_pg<kPassWrite, 8>(args, stream);
         if (pass == kPassPresence) launch_search_pg<kPassPresence, 8>(args, stream);
     } else {
         if (pass == kPassCount) launch_search_pg<kPassCount, 32>(args, stream);
         if (pass == kPassCountAccount) launch_search_pg<kPassCountAccount, 32>(args, stream);
+        if (pass == kPassCountDeferred) launch_search_pg<kPassCountDeferred, 32>(args, stream);
         if (pass == kPassWrite) launch_search_pg<kPassWrite, 32>(args, stream);
         if (pass == kPassPresence) launch_search_pg<kPassPresence, 32>(args, stream);
     }

@@ -152,6 +152,21 @@ def _global_presence(ix, q_ptr, off_ptr, Q, max_len, world, dev):
     return all_gather_fold(present, world, dist), 0
 
 
+def _search_shard(ix, q_ptr, off_ptr, Q, max_len, world, dev):
+    """This shard's result with the whole-text presence rule applied: count pass -> one all-reduce of the
+    presence flags -> epilogue + write pass. Falls back to the two-pass form for queries with > 8 indexed parts."""
+    import torch
+    import torch.distributed as dist
+    max_parts = max(1, max_len // min(ix.ks))
+    if max_parts <= 8 and world <= 15:
+        present = torch.empty(Q, dtype=torch.int32, device=dev)
+        pending = ix.search_sharded_begin(q_ptr, off_ptr, Q, max_len, present.data_ptr())
+        dist.all_reduce(present, op=dist.ReduceOp.SUM)   # nibble per part: SUM over <= 15 shards acts as OR
+        return ix.search_sharded_finish(pending, present.data_ptr(), Q)
+    present, fmt = _global_presence(ix, q_ptr, off_ptr, Q, max_len, world, dev)
+    return ix.search_batch_device_global(q_ptr, off_ptr, Q, max_len, present.data_ptr(), fmt=fmt)
+
+
 def search_device(ix, q_ptr: int, off_ptr: int, Q: int, max_len: int, world: int, dev, count_only: bool = False) -> int:
     """Whole-job search with queries resident in HBM; returns the total number of hits (on rank 0 when sharded)."""
     import torch
@@ -163,8 +178,7 @@ def search_device(ix, q_ptr: int, off_ptr: int, Q: int, max_len: int, world: int
         return hits
     import torch.distributed as dist
     rank = dist.get_rank()
-    present, fmt = _global_presence(ix, q_ptr, off_ptr, Q, max_len, world, dev)
-    res = ix.search_batch_device_global(q_ptr, off_ptr, Q, max_len, present.data_ptr(), fmt=fmt)
+    res = _search_shard(ix, q_ptr, off_ptr, Q, max_len, world, dev)
     offsets = torch.as_tensor(res.offsets(), device=dev)
     positions = (torch.as_tensor(res.positions(), device=dev) if res.n_positions
                  else torch.empty(0, dtype=torch.int32, device=dev))
@@ -202,8 +216,7 @@ def search_host(ix, h_q, h_off, world: int, dev):
     d_q = h_q.to(dev, non_blocking=True)
     d_off = h_off.to(dev, non_blocking=True)
     max_len = int((d_off[1:] - d_off[:-1]).max().item()) if Q else 0
-    present, fmt = _global_presence(ix, d_q.data_ptr(), d_off.data_ptr(), Q, max_len, world, dev)
-    res = ix.search_batch_device_global(d_q.data_ptr(), d_off.data_ptr(), Q, max_len, present.data_ptr(), fmt=fmt)
+    res = _search_shard(ix, d_q.data_ptr(), d_off.data_ptr(), Q, max_len, world, dev)
     offsets = torch.as_tensor(res.offsets(), device=dev)
     positions = (torch.as_tensor(res.positions(), device=dev) if res.n_positions
                  else torch.empty(0, dtype=torch.int32, device=dev))

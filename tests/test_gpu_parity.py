@@ -142,7 +142,7 @@ def test_edge_cases(kb):
             ix.search(np.zeros(10001, np.uint8))
 
 
-@pytest.mark.parametrize("fmt", [0, 1])
+@pytest.mark.parametrize("fmt", [0, 1, "fused"])
 @pytest.mark.parametrize("sigma,ks,n,m_lo,m_hi,world", [(4, [16], 400_000, 16, 64, 2), (4, [12], 300_000, 13, 64, 3),
                                                        (4, [5, 7, 9, 11, 13], 200_000, 4, 40, 2), (15, [8], 200_000, 3, 20, 4)])
 def test_sharded_search_emulated_on_one_gpu(kb, oracle_mod, sigma, ks, n, m_lo, m_hi, world, fmt):
@@ -162,17 +162,23 @@ def test_sharded_search_emulated_on_one_gpu(kb, oracle_mod, sigma, ks, n, m_lo, 
     idx = [kb.KmerIndex(text[s.begin:s.begin + s.length], sigma, ks, shard_begin=s.begin, n_total=n, halo=s.halo,
                         stream=stream or None) for s in shards]
     try:
-        masks = []
+        masks, pending = [], []
         for ix in idx:
             m = torch.zeros(Q, dtype=torch.int64 if fmt == 0 else torch.int32, device=dev)
-            ix.presence_batch_device(d_q.data_ptr(), d_off.data_ptr(), Q, m_hi, m.data_ptr(), fmt=fmt)
+            if fmt == "fused":   # count pass with deferred presence rule
+                pending.append(ix.search_sharded_begin(d_q.data_ptr(), d_off.data_ptr(), Q, m_hi, m.data_ptr()))
+            else:
+                ix.presence_batch_device(d_q.data_ptr(), d_off.data_ptr(), Q, m_hi, m.data_ptr(), fmt=fmt)
             torch.cuda.synchronize()
             masks.append(m)
-        # what the NCCL exchange computes: OR of bit masks (fmt 0) / SUM of nibble flags (fmt 1)
+        # what the NCCL exchange computes: OR of bit masks (fmt 0) / SUM of nibble flags (fmt 1, fused)
         present = sharded.fold_presence(torch.stack(masks)) if fmt == 0 else torch.stack(masks).sum(0).to(torch.int32)
         per_shard = []
-        for ix in idx:
-            r = ix.search_batch_device_global(d_q.data_ptr(), d_off.data_ptr(), Q, m_hi, present.data_ptr(), fmt=fmt)
+        for i, ix in enumerate(idx):
+            if fmt == "fused":
+                r = ix.search_sharded_finish(pending[i], present.data_ptr(), Q)
+            else:
+                r = ix.search_batch_device_global(d_q.data_ptr(), d_off.data_ptr(), Q, m_hi, present.data_ptr(), fmt=fmt)
             torch.cuda.synchronize()
             o = torch.as_tensor(r.offsets(), device=dev).clone()
             p = (torch.as_tensor(r.positions(), device=dev).clone() if r.n_positions
