@@ -312,8 +312,9 @@ def run_ours(args, wl):
             if it >= min(args.warmup, 1):
                 eb.append(ev[0].elapsed_time(ev[1]))
                 es.append(ev[1].elapsed_time(ev[2]))
-        e2e = {"build_ms": float(np.mean(eb)), "search_ms": float(np.mean(es)), "h2d": n_local + n_sym + (Q + 1) * 8,
-               "d2h": d2h}
+        # sharded: only rank 0 reads the query batch from the host (NCCL broadcast to the others)
+        h2d_q = n_sym + (Q + 1) * 8 if (world == 1 or rank == 0) else 0
+        e2e = {"build_ms": float(np.mean(eb)), "search_ms": float(np.mean(es)), "h2d": n_local + h2d_q, "d2h": d2h}
         del h_text, h_q, h_off
 
     # ---- max over ranks
@@ -329,6 +330,10 @@ def run_ours(args, wl):
     if e2e:
         e2e["build_ms"] = max_over_ranks(e2e["build_ms"])
         e2e["search_ms"] = max_over_ranks(e2e["search_ms"])
+        if world > 1:   # bytes per step over all ranks
+            t = torch.tensor([e2e["h2d"], e2e["d2h"] if rank == 0 else 0], dtype=torch.float64, device=dev)
+            dist.all_reduce(t)
+            e2e["h2d"], e2e["d2h"] = int(t[0].item()), int(t[1].item())
 
     if rank == 0:
         peaks = {}

@@ -213,8 +213,16 @@ def search_host(ix, h_q, h_off, world: int, dev):
     from . import BatchResult
     rank = dist.get_rank()
     Q = h_off.numel() - 1
-    d_q = h_q.to(dev, non_blocking=True)
-    d_off = h_off.to(dev, non_blocking=True)
+    # "queries are broadcast": rank 0 alone reads the host batch, the other ranks receive it over NVLink
+    # (8 ranks pulling the same 5 GB through PCIe at once is 2x slower than one H2D + one NCCL broadcast)
+    if rank == 0:
+        d_q = h_q.to(dev, non_blocking=True)
+        d_off = h_off.to(dev, non_blocking=True)
+    else:
+        d_q = torch.empty(h_q.numel(), dtype=torch.uint8, device=dev)
+        d_off = torch.empty(Q + 1, dtype=torch.int64, device=dev)
+    dist.broadcast(d_off, src=0)
+    dist.broadcast(d_q, src=0)
     max_len = int((d_off[1:] - d_off[:-1]).max().item()) if Q else 0
     res = _search_shard(ix, d_q.data_ptr(), d_off.data_ptr(), Q, max_len, world, dev)
     offsets = torch.as_tensor(res.offsets(), device=dev)
