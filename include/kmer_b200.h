@@ -23,7 +23,7 @@ extern "C" {
 
 typedef enum kmer_b200_status {
     KMER_B200_OK = 0,
-    KMER_B200_ERR_INVALID_ARGUMENT = -1, /* null pointer, k out of range, sigma^k >= 2^32, n < k, ... */
+    KMER_B200_ERR_INVALID_ARGUMENT = -1, /* null pointer, k out of range, n < k, ... */
     KMER_B200_ERR_CUDA = -2,             /* any CUDA runtime failure (including "no device") */
     KMER_B200_ERR_OUT_OF_MEMORY = -3,
     KMER_B200_ERR_INVALID_RANK = -4,     /* a text/query symbol rank >= sigma */
@@ -159,7 +159,7 @@ int kmer_b200_element_info_get(const kmer_b200_index *index, uint32_t element, k
    the reference's _data buckets in ascending hash order, kmer_index.hpp:52,165) to host memory. */
 int kmer_b200_element_positions(kmer_b200_index *index, uint32_t element, uint32_t *out, uint64_t cap);
 /* Copy the sorted hash array (one per position above) to host memory. */
-int kmer_b200_element_hashes(kmer_b200_index *index, uint32_t element, uint32_t *out, uint64_t cap);
+int kmer_b200_element_hashes(kmer_b200_index *index, uint32_t element, uint64_t *out, uint64_t cap);
 /* Row m of the scheme table (_optimal_nk_sum[m], _use_multi_search_scheme[m]; kmer_index.hpp:404-476).
    Returns the number of summands and writes up to cap of them. */
 uint64_t kmer_b200_scheme(const kmer_b200_index *index, uint64_t m, uint32_t *out_ks, uint64_t cap, int *use_multi);

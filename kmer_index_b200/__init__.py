@@ -273,9 +273,9 @@ class KmerIndex:
     def element_arrays(self, e: int):
         """(sorted hashes, positions stably sorted by hash) of element e."""
         info = self.element_info(e)
-        h = np.zeros(info.n_kmers, dtype=np.uint32)
+        h = np.zeros(info.n_kmers, dtype=np.uint64)
         p = np.zeros(info.n_kmers, dtype=np.uint32)
-        _capi.check(self._L.kmer_b200_element_hashes(self._h, e, h.ctypes.data_as(_capi.u32p), h.size))
+        _capi.check(self._L.kmer_b200_element_hashes(self._h, e, h.ctypes.data_as(_capi.u64p), h.size))
         _capi.check(self._L.kmer_b200_element_positions(self._h, e, p.ctypes.data_as(_capi.u32p), p.size))
         return h, p
 

@@ -72,7 +72,7 @@ SYMBOLS = {
     "kmer_b200_n_elements": (C.c_uint32, [C.c_void_p]),
     "kmer_b200_element_info_get": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(ElementInfo)]),
     "kmer_b200_element_positions": (C.c_int, [C.c_void_p, C.c_uint32, u32p, C.c_uint64]),
-    "kmer_b200_element_hashes": (C.c_int, [C.c_void_p, C.c_uint32, u32p, C.c_uint64]),
+    "kmer_b200_element_hashes": (C.c_int, [C.c_void_p, C.c_uint32, u64p, C.c_uint64]),
     "kmer_b200_scheme": (C.c_uint64, [C.c_void_p, C.c_uint64, u32p, C.c_uint64, C.POINTER(C.c_int)]),
     "kmer_b200_scheme_for_ks": (C.c_uint64, [u32p, C.c_uint32, C.c_uint64, u32p, C.c_uint64, C.POINTER(C.c_int)]),
     "kmer_b200_stats": (C.c_uint32, [C.c_void_p, C.POINTER(KernelStat), C.c_uint32]),

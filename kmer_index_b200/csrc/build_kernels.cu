@@ -60,15 +60,17 @@ void launch_pack_text(const uint8_t *d_ranks, uint64_t n, uint32_t bits, uint32_
 // key sources
 // ------------------------------------------------------------------------------------------------
 // A source hands a thread its kSortItems tile items: item r is element first + 32 * r; `avail` = number of
-// valid elements starting at `first` (only consulted when FULL is false).
+// valid elements starting at `first` (only consulted when FULL is false). KeyT is uint32_t while sigma^k <= 2^32.
+template <typename KeyT>
 struct TextSource {  // key(i) = hash of the k-mer starting at symbol i; value(i) = i
+    using key_type = KeyT;
     PackedText text;
     uint32_t k;
-    __device__ __forceinline__ uint32_t key(uint64_t i) const {
-        return key_from_window(window64(text.words, i, text.bits), k, text.bits, text.sigma);
+    __device__ __forceinline__ KeyT key(uint64_t i) const {
+        return (KeyT)key_from_window(window64(text.words, i, text.bits), k, text.bits, text.sigma);
     }
     template <bool FULL>
-    __device__ __forceinline__ void load_keys(uint64_t first, uint32_t avail, uint32_t (&out)[kSortItems]) const {
+    __device__ __forceinline__ void load_keys(uint64_t first, uint32_t avail, KeyT (&out)[kSortItems]) const {
         // items are 32 symbols = 32 * bits bits = `step` whole words apart, so the bit offset inside the word is
         // the same for all of them: walk the words once (step + 1 loads serve an item, step == 1 shares one)
         const uint64_t bit0 = first * text.bits;
@@ -84,8 +86,8 @@ struct TextSource {  // key(i) = hash of the k-mer starting at symbol i; value(i
             const bool valid = FULL || (uint32_t)(r * 32) < avail;
             const uint64_t next = valid ? w[r * step + 1] : 0ull;
             const uint64_t win = sh ? ((cur << sh) | (next >> (64 - sh))) : cur;
-            const uint32_t kk = pow2 ? (uint32_t)(win >> down) : key_from_window(win, k, text.bits, text.sigma);
-            out[r] = valid ? kk : 0u;
+            const KeyT kk = pow2 ? (KeyT)(win >> down) : (KeyT)key_from_window(win, k, text.bits, text.sigma);
+            out[r] = valid ? kk : (KeyT)0;
             if (r + 1 < kSortItems) {
                 const bool valid_next = FULL || (uint32_t)((r + 1) * 32) < avail;
                 cur = step == 1 ? next : (valid_next ? w[(r + 1) * step] : 0ull);
@@ -101,15 +103,17 @@ struct TextSource {  // key(i) = hash of the k-mer starting at symbol i; value(i
     __device__ __forceinline__ void prefetch_vals(uint64_t, uint32_t) const {}
 };
 
+template <typename KeyT>
 struct PairSource {  // materialised (key, value) pairs
-    const uint32_t *keys;
+    using key_type = KeyT;
+    const KeyT *keys;
     const uint32_t *vals;
-    __device__ __forceinline__ uint32_t key(uint64_t i) const { return keys[i]; }
+    __device__ __forceinline__ KeyT key(uint64_t i) const { return keys[i]; }
     template <bool FULL>
-    __device__ __forceinline__ void load_keys(uint64_t first, uint32_t avail, uint32_t (&out)[kSortItems]) const {
-        const uint32_t *p = keys + first;  // one base pointer; the unrolled loads use immediate offsets
+    __device__ __forceinline__ void load_keys(uint64_t first, uint32_t avail, KeyT (&out)[kSortItems]) const {
+        const KeyT *p = keys + first;  // one base pointer; the unrolled loads use immediate offsets
 #pragma unroll
-        for (int r = 0; r < kSortItems; ++r) out[r] = (FULL || (uint32_t)(r * 32) < avail) ? p[r * 32] : 0u;
+        for (int r = 0; r < kSortItems; ++r) out[r] = (FULL || (uint32_t)(r * 32) < avail) ? p[r * 32] : (KeyT)0;
     }
     template <bool FULL>
     __device__ __forceinline__ void load_vals(uint64_t first, uint32_t avail, uint32_t (&out)[kSortItems]) const {
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(Source src, ui
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
         const uint64_t i = tile_begin + (uint64_t)r * kSortThreads + tid;
-        d[r] = i < n ? ((src.key(i) >> shift) & mask) : kInvalidDigit;
+        d[r] = i < n ? ((uint32_t)(src.key(i) >> shift) & mask) : kInvalidDigit;
     }
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
@@ -182,7 +186,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_text_kernel(PackedTex
         uint64_t w = window64(text.words, i0 + j, text.bits);
         const uint32_t cnt = min(min(per_window, (uint32_t)kSortItems - j), (uint32_t)min((uint64_t)kSortItems, n - i0 - j));
         for (uint32_t t = 0; t < cnt; ++t) {
-            const uint32_t d = (key_from_window(w, k, text.bits, text.sigma) >> shift) & mask;
+            const uint32_t d = (uint32_t)(key_from_window(w, k, text.bits, text.sigma) >> shift) & mask;
             atomicAdd(&hist[warp][d], 1u);
             w <<= text.bits;
         }
@@ -265,24 +269,52 @@ __global__ void __launch_bounds__(kRadix) column_apply_kernel(uint32_t *__restri
 // in digit order and written out as per-digit runs (coalesced: a run of a digit is contiguous in the
 // destination).
 // ------------------------------------------------------------------------------------------------
-struct ScatterSmem {
+// (key, value) staged in digit order. 32-bit keys: one 64-bit shared-memory access per element.
+template <typename KeyT>
+struct ScatterSmem;
+template <>
+struct ScatterSmem<uint32_t> {
     RankSmem rank;
     uint32_t delta[kRadix];
-    uint2 kv[kSortTile];  // (key, value) staged in digit order: one 64-bit shared-memory access per element
+    uint2 kv[kSortTile];
+    __device__ __forceinline__ void put(uint32_t i, uint32_t k, uint32_t v) { kv[i] = make_uint2(k, v); }
+    __device__ __forceinline__ void get(uint32_t i, uint32_t &k, uint32_t &v) const {
+        const uint2 e = kv[i];
+        k = e.x;
+        v = e.y;
+    }
+};
+template <>
+struct ScatterSmem<uint64_t> {
+    RankSmem rank;
+    uint32_t delta[kRadix];
+    uint64_t keys[kSortTile];
+    uint32_t vals[kSortTile];
+    __device__ __forceinline__ void put(uint32_t i, uint64_t k, uint32_t v) {
+        keys[i] = k;
+        vals[i] = v;
+    }
+    __device__ __forceinline__ void get(uint32_t i, uint64_t &k, uint32_t &v) const {
+        k = keys[i];
+        v = vals[i];
+    }
 };
 
 template <typename Source, int BITS, bool FULL>
 __device__ __forceinline__ void scatter_tile(const Source &src, uint64_t tile_begin, uint32_t count, uint32_t shift,
                                              uint32_t mask, const uint32_t *__restrict__ tile_base_row,
-                                             uint32_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals,
-                                             ScatterSmem &sm) {
+                                             typename Source::key_type *__restrict__ out_keys,
+                                             uint32_t *__restrict__ out_vals,
+                                             ScatterSmem<typename Source::key_type> &sm) {
+    using KeyT = typename Source::key_type;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const uint32_t e0 = (uint32_t)(warp * kSortItems * 32 + lane);
 
-    // keys live in registers through the ranking; values reuse the same registers afterwards, which keeps the
-    // kernel at <= 64 registers so two CTAs share an SM and one CTA's loads overlap the other's ranking
-    uint32_t key[kSortItems], local_pos[kSortItems];
+    // keys live in registers through the ranking; values are fetched afterwards (prefetched to L2 meanwhile),
+    // which keeps the 32-bit kernel at <= 64 registers so two CTAs share an SM and overlap each other's phases
+    KeyT key[kSortItems];
+    uint32_t local_pos[kSortItems];
     src.template load_keys<FULL>(tile_begin + e0, count - min(count, e0), key);
     src.template prefetch_vals<FULL>(tile_begin + e0, count - min(count, e0));
     tile_rank<BITS, FULL>(key, count, shift, mask, local_pos, sm.rank);
@@ -292,35 +324,39 @@ __device__ __forceinline__ void scatter_tile(const Source &src, uint64_t tile_be
         src.template load_vals<FULL>(tile_begin + e0, count - min(count, e0), val);
 #pragma unroll
         for (int r = 0; r < kSortItems; ++r)
-            if (FULL || e0 + r * 32 < count) sm.kv[local_pos[r]] = make_uint2(key[r], val[r]);
+            if (FULL || e0 + r * 32 < count) sm.put(local_pos[r], key[r], val[r]);
     }
     __syncthreads();
     if (FULL) {
 #pragma unroll
         for (int it = 0; it < kSortItems; ++it) {
             const uint32_t j = it * kSortThreads + tid;
-            const uint2 e = sm.kv[j];
-            const uint32_t dst = sm.delta[(e.x >> shift) & mask] + j;  // mod 2^32; true destination < n < 2^32
-            out_keys[dst] = e.x;
-            out_vals[dst] = e.y;
+            KeyT kk;
+            uint32_t vv;
+            sm.get(j, kk, vv);
+            const uint32_t dst = sm.delta[(uint32_t)(kk >> shift) & mask] + j;  // mod 2^32; true destination < n < 2^32
+            out_keys[dst] = kk;
+            out_vals[dst] = vv;
         }
     } else {
         for (uint32_t j = tid; j < count; j += kSortThreads) {
-            const uint2 e = sm.kv[j];
-            const uint32_t dst = sm.delta[(e.x >> shift) & mask] + j;
-            out_keys[dst] = e.x;
-            out_vals[dst] = e.y;
+            KeyT kk;
+            uint32_t vv;
+            sm.get(j, kk, vv);
+            const uint32_t dst = sm.delta[(uint32_t)(kk >> shift) & mask] + j;
+            out_keys[dst] = kk;
+            out_vals[dst] = vv;
         }
     }
 }
 
 template <typename Source, int BITS>
-__global__ void __launch_bounds__(kSortThreads, 2)
+__global__ void __launch_bounds__(kSortThreads, sizeof(typename Source::key_type) == 4 ? 2 : 1)
     radix_scatter_kernel(const Source src, uint64_t n, uint32_t shift, uint32_t mask,
-                         const uint32_t *__restrict__ tile_base, uint32_t *__restrict__ out_keys,
+                         const uint32_t *__restrict__ tile_base, typename Source::key_type *__restrict__ out_keys,
                          uint32_t *__restrict__ out_vals) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    ScatterSmem &sm = *reinterpret_cast<ScatterSmem *>(smem_raw);
+    auto &sm = *reinterpret_cast<ScatterSmem<typename Source::key_type> *>(smem_raw);
     const uint64_t tile_begin = (uint64_t)blockIdx.x * kSortTile;
     const uint32_t count = (uint32_t)min((uint64_t)kSortTile, n - tile_begin);
     const uint32_t *row = tile_base + (uint64_t)blockIdx.x * kRadix;
@@ -335,7 +371,8 @@ __global__ void __launch_bounds__(kSortThreads, 2)
 // Thread i owns the boundary between sorted elements i-1 and i and fills the directory entries that
 // fall into it; long runs (sparse key spaces) are filled by the whole warp, coalesced.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) directory_fill_kernel(const uint32_t *__restrict__ keys, uint64_t n_kmers,
+template <typename KeyT>
+__global__ void __launch_bounds__(256) directory_fill_kernel(const KeyT *__restrict__ keys, uint64_t n_kmers,
                                                              uint32_t shift, uint64_t dir_entries,
                                                              uint32_t *__restrict__ dir) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // boundary index in [0, n_kmers]
@@ -368,32 +405,33 @@ __global__ void __launch_bounds__(256) directory_fill_kernel(const uint32_t *__r
     }
 }
 
-void launch_directory_fill(const uint32_t *d_keys, uint64_t n_kmers, uint32_t shift, uint64_t dir_entries, uint32_t *d_dir,
-                           cudaStream_t stream) {
+void launch_directory_fill(const void *d_keys, uint32_t key_bytes, uint64_t n_kmers, uint32_t shift, uint64_t dir_entries,
+                           uint32_t *d_dir, cudaStream_t stream) {
     const uint64_t blocks = (n_kmers + 1 + 255) / 256;
-    directory_fill_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_keys, n_kmers, shift, dir_entries, d_dir);
+    if (key_bytes == 8)
+        directory_fill_kernel<uint64_t><<<(unsigned)blocks, 256, 0, stream>>>((const uint64_t *)d_keys, n_kmers, shift, dir_entries, d_dir);
+    else
+        directory_fill_kernel<uint32_t><<<(unsigned)blocks, 256, 0, stream>>>((const uint32_t *)d_keys, n_kmers, shift, dir_entries, d_dir);
 }
 
 // ------------------------------------------------------------------------------------------------
 // host-side pass drivers
 // ------------------------------------------------------------------------------------------------
-size_t scatter_smem_bytes() { return sizeof(ScatterSmem); }
-
 template <typename Source, int BITS>
 static void launch_scatter_bits(const Source &src, uint64_t n, uint32_t shift, uint32_t mask, const uint32_t *d_tile_base,
-                                uint32_t *d_out_keys, uint32_t *d_out_vals, cudaStream_t stream) {
+                                typename Source::key_type *d_out_keys, uint32_t *d_out_vals, cudaStream_t stream) {
+    using Smem = ScatterSmem<typename Source::key_type>;
     const uint32_t n_tiles = (uint32_t)((n + kSortTile - 1) / kSortTile);
     // per-device attribute; cheap enough to set on every launch
-    cudaFuncSetAttribute(radix_scatter_kernel<Source, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)sizeof(ScatterSmem));
+    cudaFuncSetAttribute(radix_scatter_kernel<Source, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     radix_scatter_kernel<Source, BITS>
-        <<<n_tiles, kSortThreads, sizeof(ScatterSmem), stream>>>(src, n, shift, mask, d_tile_base, d_out_keys, d_out_vals);
+        <<<n_tiles, kSortThreads, sizeof(Smem), stream>>>(src, n, shift, mask, d_tile_base, d_out_keys, d_out_vals);
 }
 
 // the vote loop is unrolled for the digit width (rounded up to one of the instantiated widths)
 template <typename Source>
 static void launch_scatter(const Source &src, uint64_t n, uint32_t shift, uint32_t mask, const uint32_t *d_tile_base,
-                           uint32_t *d_out_keys, uint32_t *d_out_vals, cudaStream_t stream) {
+                           typename Source::key_type *d_out_keys, uint32_t *d_out_vals, cudaStream_t stream) {
     const int bits = __builtin_popcount(mask);
     if (bits <= 5)
         launch_scatter_bits<Source, 5>(src, n, shift, mask, d_tile_base, d_out_keys, d_out_vals, stream);
@@ -418,21 +456,36 @@ void launch_hist_text(const PackedText &text, uint32_t k, uint64_t n_kmers, uint
     radix_hist_text_kernel<<<n_tiles, kSortThreads, 0, stream>>>(text, k, n_kmers, shift, mask, d_tile_hist);
 }
 
-void launch_hist_pairs(const uint32_t *d_keys, uint64_t n, uint32_t shift, uint32_t mask, uint32_t *d_tile_hist,
-                       cudaStream_t stream) {
+void launch_hist_pairs(const void *d_keys, uint32_t key_bytes, uint64_t n, uint32_t shift, uint32_t mask,
+                       uint32_t *d_tile_hist, cudaStream_t stream) {
     const uint32_t n_tiles = (uint32_t)((n + kSortTile - 1) / kSortTile);
-    PairSource src{d_keys, nullptr};
-    radix_hist_kernel<PairSource><<<n_tiles, kSortThreads, 0, stream>>>(src, n, shift, mask, d_tile_hist);
+    if (key_bytes == 8) {
+        PairSource<uint64_t> src{(const uint64_t *)d_keys, nullptr};
+        radix_hist_kernel<<<n_tiles, kSortThreads, 0, stream>>>(src, n, shift, mask, d_tile_hist);
+    } else {
+        PairSource<uint32_t> src{(const uint32_t *)d_keys, nullptr};
+        radix_hist_kernel<<<n_tiles, kSortThreads, 0, stream>>>(src, n, shift, mask, d_tile_hist);
+    }
 }
 
-void launch_scatter_text(const PackedText &text, uint32_t k, uint64_t n_kmers, uint32_t shift, uint32_t mask,
-                         const uint32_t *d_tile_base, uint32_t *d_out_keys, uint32_t *d_out_vals, cudaStream_t stream) {
-    launch_scatter(TextSource{text, k}, n_kmers, shift, mask, d_tile_base, d_out_keys, d_out_vals, stream);
+void launch_scatter_text(const PackedText &text, uint32_t k, uint32_t key_bytes, uint64_t n_kmers, uint32_t shift,
+                         uint32_t mask, const uint32_t *d_tile_base, void *d_out_keys, uint32_t *d_out_vals,
+                         cudaStream_t stream) {
+    if (key_bytes == 8)
+        launch_scatter(TextSource<uint64_t>{text, k}, n_kmers, shift, mask, d_tile_base, (uint64_t *)d_out_keys, d_out_vals, stream);
+    else
+        launch_scatter(TextSource<uint32_t>{text, k}, n_kmers, shift, mask, d_tile_base, (uint32_t *)d_out_keys, d_out_vals, stream);
 }
 
-void launch_scatter_pairs(const uint32_t *d_keys, const uint32_t *d_vals, uint64_t n, uint32_t shift, uint32_t mask,
-                          const uint32_t *d_tile_base, uint32_t *d_out_keys, uint32_t *d_out_vals, cudaStream_t stream) {
-    launch_scatter(PairSource{d_keys, d_vals}, n, shift, mask, d_tile_base, d_out_keys, d_out_vals, stream);
+void launch_scatter_pairs(const void *d_keys, const uint32_t *d_vals, uint32_t key_bytes, uint64_t n, uint32_t shift,
+                          uint32_t mask, const uint32_t *d_tile_base, void *d_out_keys, uint32_t *d_out_vals,
+                          cudaStream_t stream) {
+    if (key_bytes == 8)
+        launch_scatter(PairSource<uint64_t>{(const uint64_t *)d_keys, d_vals}, n, shift, mask, d_tile_base,
+                       (uint64_t *)d_out_keys, d_out_vals, stream);
+    else
+        launch_scatter(PairSource<uint32_t>{(const uint32_t *)d_keys, d_vals}, n, shift, mask, d_tile_base,
+                       (uint32_t *)d_out_keys, d_out_vals, stream);
 }
 
 uint32_t sort_tile_size() { return kSortTile; }

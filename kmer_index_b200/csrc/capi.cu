@@ -144,7 +144,9 @@ struct HostElement {
     uint32_t key_bits = 0;
     uint32_t sort_passes = 0;
     uint64_t bytes = 0;
-    uint32_t *d_dir = nullptr, *d_keys = nullptr, *d_pos = nullptr;
+    uint32_t *d_dir = nullptr, *d_pos = nullptr;
+    void *d_keys = nullptr;  // uint32_t or uint64_t hashes (key_bytes)
+    uint32_t key_bytes = 4;
 };
 
 }  // namespace
@@ -347,9 +349,14 @@ int build_element(kmer_b200_index *ix, uint32_t k, HostElement &he, bool auxilia
     const double text_bytes = (double)n_kmers * ix->bits / 8.0;
     const double hist_bytes = (double)n_tiles * kRadix * 4;
 
-    uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr};
+    // 32-bit hashes while sigma^k <= 2^32 (all BASELINE configs), 64-bit above
+    const uint32_t key_bytes = he.key_bits > 32 ? 8 : 4;
+    he.key_bytes = key_bytes;
+    void *keys[2] = {nullptr, nullptr};
+    uint32_t *vals[2] = {nullptr, nullptr};
     uint32_t *tile_hist = nullptr, *chunk_sums = nullptr;
-    KB_TRY(dev_alloc(ix, &keys[0], n_kmers, true));
+    auto alloc_keys = [&](void **p) { return dev_alloc(ix, (uint8_t **)p, n_kmers * key_bytes, true); };
+    KB_TRY(alloc_keys(&keys[0]));
     KB_TRY(dev_alloc(ix, &vals[0], n_kmers, true));
     KB_TRY(dev_alloc(ix, &tile_hist, (uint64_t)n_tiles * kRadix, false));
     KB_TRY(dev_alloc(ix, &chunk_sums, (uint64_t)n_chunks * kRadix, false));
@@ -362,33 +369,33 @@ int build_element(kmer_b200_index *ix, uint32_t k, HostElement &he, bool auxilia
     pf.begin(K_COLUMN_SCAN, 3 * hist_bytes, 3);
     launch_column_scan(tile_hist, n_tiles, chunk_sums, st);
     pf.end();
-    pf.begin(K_SCATTER_TEXT, text_bytes + hist_bytes + 8.0 * n_kmers);
-    launch_scatter_text(text, k, n_kmers, 0, mask, tile_hist, keys[0], vals[0], st);
+    pf.begin(K_SCATTER_TEXT, text_bytes + hist_bytes + (4.0 + key_bytes) * n_kmers);
+    launch_scatter_text(text, k, key_bytes, n_kmers, 0, mask, tile_hist, keys[0], vals[0], st);
     pf.end();
     int cur = 0;
     for (uint32_t p = 1; p < he.sort_passes; ++p) {
         const int nxt = cur ^ 1;
         if (!keys[nxt]) {
-            KB_TRY(dev_alloc(ix, &keys[nxt], n_kmers, true));
+            KB_TRY(alloc_keys(&keys[nxt]));
             KB_TRY(dev_alloc(ix, &vals[nxt], n_kmers, true));
         }
         const uint32_t shift = p * bits_per_pass;
-        pf.begin(K_HIST_PAIRS, 4.0 * n_kmers + hist_bytes);
-        launch_hist_pairs(keys[cur], n_kmers, shift, mask, tile_hist, st);
+        pf.begin(K_HIST_PAIRS, (double)key_bytes * n_kmers + hist_bytes);
+        launch_hist_pairs(keys[cur], key_bytes, n_kmers, shift, mask, tile_hist, st);
         pf.end();
         pf.begin(K_COLUMN_SCAN, 3 * hist_bytes, 3);
         launch_column_scan(tile_hist, n_tiles, chunk_sums, st);
         pf.end();
-        pf.begin(K_SCATTER_PAIRS, 16.0 * n_kmers + hist_bytes);
-        launch_scatter_pairs(keys[cur], vals[cur], n_kmers, shift, mask, tile_hist, keys[nxt], vals[nxt], st);
+        pf.begin(K_SCATTER_PAIRS, 2.0 * (4.0 + key_bytes) * n_kmers + hist_bytes);
+        launch_scatter_pairs(keys[cur], vals[cur], key_bytes, n_kmers, shift, mask, tile_hist, keys[nxt], vals[nxt], st);
         pf.end();
         cur = nxt;
     }
     KB_CUDA(cudaGetLastError());
     if (keys[cur ^ 1]) {
-        dev_free(ix, keys[cur ^ 1]);
+        dev_free(ix, (uint8_t *)keys[cur ^ 1]);
         dev_free(ix, vals[cur ^ 1]);
-        ix->device_bytes -= 2 * n_kmers * sizeof(uint32_t);
+        ix->device_bytes -= n_kmers * (sizeof(uint32_t) + key_bytes);
     }
     dev_free(ix, tile_hist);
     dev_free(ix, chunk_sums);
@@ -404,10 +411,11 @@ int build_element(kmer_b200_index *ix, uint32_t k, HostElement &he, bool auxilia
         if (want < 16) want = 16;
         if (he.key_bits > want) shift = he.key_bits - want;
     }
+    if (he.key_bits > 32 + shift) shift = he.key_bits - 32;  // directory indices stay below 2^32
     const uint64_t dir_entries = ((key_space - 1) >> shift) + 2;
     KB_TRY(dev_alloc(ix, &he.d_dir, dir_entries, true));
-    pf.begin(K_DIRECTORY_FILL, 4.0 * n_kmers + 4.0 * dir_entries);
-    launch_directory_fill(he.d_keys, n_kmers, shift, dir_entries, he.d_dir, st);
+    pf.begin(K_DIRECTORY_FILL, (double)key_bytes * n_kmers + 4.0 * dir_entries);
+    launch_directory_fill(he.d_keys, key_bytes, n_kmers, shift, dir_entries, he.d_dir, st);
     pf.end();
     KB_CUDA(cudaGetLastError());
 
@@ -419,7 +427,8 @@ int build_element(kmer_b200_index *ix, uint32_t k, HostElement &he, bool auxilia
     he.dev.dir = he.d_dir;
     he.dev.keys = he.d_keys;
     he.dev.pos = he.d_pos;
-    he.bytes = 2 * n_kmers * sizeof(uint32_t) + dir_entries * sizeof(uint32_t);
+    he.dev.key_bytes = key_bytes;
+    he.bytes = n_kmers * (sizeof(uint32_t) + key_bytes) + dir_entries * sizeof(uint32_t);
     if (!auxiliary)
         ix->max_avg_bucket = std::max(ix->max_avg_bucket, (double)n_kmers / (double)std::min<uint64_t>(key_space, n_kmers));
     return 0;
@@ -440,8 +449,8 @@ int create_impl(const uint8_t *ranks, bool ranks_on_device, uint64_t n, uint32_t
         // static_assert(k > 0 and k < 64 / log2(sigma)), kmer_index.hpp:42-43
         if (k == 0 || !((double)k < 64.0 / std::log2((double)sigma)))
             return fail(KMER_B200_ERR_INVALID_ARGUMENT, "k must satisfy 0 < k < 64 / log2(sigma) (kmer_index.hpp:42)");
-        if (k * bits > 64 || std::pow((double)sigma, (double)k) > 4294967296.0)
-            return fail(KMER_B200_ERR_UNSUPPORTED, "sigma^k must be <= 2^32 (32-bit hashes) in this build");
+        if (k * bits > 64)
+            return fail(KMER_B200_ERR_UNSUPPORTED, "k * bits-per-symbol must be <= 64 (one 64-bit text window per k-mer) in this build");
         for (uint32_t j = 0; j < i; ++j)
             if (ks[j] == k) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "duplicate k");
         k_max = std::max(k_max, k);
@@ -627,7 +636,7 @@ uint64_t ensure_aux_elements(kmer_b200_index *ix, uint64_t want) {
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
         const double need = 16.0 * (double)ix->n + 4.0 * key_space + (64 << 20);  // two (key, pos) buffers + directory
-        if (slot >= (size_t)kb::kMaxElements || m > ix->n || m * ix->bits > 64 || key_space > 4294967296.0 ||
+        if (slot >= (size_t)kb::kMaxElements || m > ix->n || m * ix->bits > 64 || key_space > 4294967296.0 * 64 ||
             need * 1.5 > (double)free_b) {
             missing |= 1ull << m;
             continue;
@@ -880,7 +889,7 @@ void kmer_b200_destroy(kmer_b200_index *ix) {
     ix->prof.resolve();
     for (auto &he : ix->elems) {
         dev_free(ix, he.d_dir);
-        dev_free(ix, he.d_keys);
+        dev_free(ix, (uint8_t *)he.d_keys);
         dev_free(ix, he.d_pos);
     }
     dev_free(ix, ix->d_text);
@@ -1093,12 +1102,20 @@ int kmer_b200_element_positions(kmer_b200_index *ix, uint32_t e, uint32_t *out, 
     return KMER_B200_OK;
 }
 
-int kmer_b200_element_hashes(kmer_b200_index *ix, uint32_t e, uint32_t *out, uint64_t cap) {
+int kmer_b200_element_hashes(kmer_b200_index *ix, uint32_t e, uint64_t *out, uint64_t cap) {
     if (!ix || !out || e >= ix->elems.size()) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad element");
     DeviceGuard guard(ix->device);
-    const uint64_t n = std::min<uint64_t>(cap, ix->elems[e].dev.n_kmers);
-    KB_CUDA(cudaMemcpyAsync(out, ix->elems[e].d_keys, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ix->stream));
-    KB_CUDA(cudaStreamSynchronize(ix->stream));
+    const HostElement &he = ix->elems[e];
+    const uint64_t n = std::min<uint64_t>(cap, he.dev.n_kmers);
+    if (he.key_bytes == 8) {
+        KB_CUDA(cudaMemcpyAsync(out, he.d_keys, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ix->stream));
+        KB_CUDA(cudaStreamSynchronize(ix->stream));
+    } else {  // widen 32-bit hashes on the host
+        std::vector<uint32_t> tmp(n);
+        KB_CUDA(cudaMemcpyAsync(tmp.data(), he.d_keys, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ix->stream));
+        KB_CUDA(cudaStreamSynchronize(ix->stream));
+        for (uint64_t i = 0; i < n; ++i) out[i] = tmp[i];
+    }
     return KMER_B200_OK;
 }
 

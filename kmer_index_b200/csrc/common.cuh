@@ -37,13 +37,13 @@ __device__ __forceinline__ uint64_t window64(WordPtr words, uint64_t sym, uint32
 
 // The k-mer hash of the k symbols at the top of window `w` (kmer_index.hpp:56-73).
 // sigma == 4: the 2k-bit field itself. Otherwise Horner over the k symbols (k * bits <= 64).
-__device__ __forceinline__ uint32_t key_from_window(uint64_t w, uint32_t k, uint32_t bits, uint32_t sigma) {
-    if (sigma == (1u << bits)) return (uint32_t)(w >> (64 - k * bits));
-    uint32_t h = 0;
+__device__ __forceinline__ uint64_t key_from_window(uint64_t w, uint32_t k, uint32_t bits, uint32_t sigma) {
+    if (sigma == (1u << bits)) return w >> (64 - k * bits);
+    uint64_t h = 0;
     const uint64_t mask = (1ull << bits) - 1;
 #pragma unroll 1
     for (uint32_t i = 0; i < k; ++i) {
-        h = h * sigma + (uint32_t)((w >> (64 - bits * (i + 1))) & mask);
+        h = h * sigma + ((w >> (64 - bits * (i + 1))) & mask);
     }
     return h;
 }
@@ -54,7 +54,8 @@ __device__ __forceinline__ uint32_t key_from_window(uint64_t w, uint32_t k, uint
 //   pos[n_kmers]   all k-mer start positions, stably sorted by hash (bucket = run of equal hashes,
 //                  ascending positions inside, as push_back in text order yields, kmer_index.hpp:165)
 //   dir[entries]   dir[j] = number of k-mers with (hash >> shift) < j      (entries = (max_hash >> shift) + 2)
-//   keys[n_kmers]  the sorted hashes (always kept: sub-k slabs and shift > 0 lookups read them)
+//   keys[n_kmers]  the sorted hashes (always kept: sub-k slabs and shift > 0 lookups read them);
+//                  32-bit while sigma^k <= 2^32, 64-bit otherwise (then shift > 0: the directory stays <= 2^32)
 // ---------------------------------------------------------------------------------------------
 struct Element {
     uint32_t k;
@@ -63,9 +64,15 @@ struct Element {
     uint64_t dir_entries;
     uint64_t key_space;  // sigma^k
     const uint32_t *dir;
-    const uint32_t *keys;
+    const void *keys;
     const uint32_t *pos;
+    uint32_t key_bytes;  // 4 or 8
+    uint32_t pad_;
 };
+
+__device__ __forceinline__ uint64_t element_key(const Element &E, uint64_t i) {
+    return E.key_bytes == 8 ? static_cast<const uint64_t *>(E.keys)[i] : (uint64_t)static_cast<const uint32_t *>(E.keys)[i];
+}
 
 struct SchemeTables {
     // row m of the reference's _optimal_nk_sum / _use_multi_search_scheme (kmer_index.hpp:404-405),

@@ -10,15 +10,18 @@ void launch_pack_text(const uint8_t *d_ranks, uint64_t n, uint32_t bits, uint32_
                       uint64_t *d_words, uint32_t *d_error_flag, cudaStream_t stream);
 void launch_hist_text(const PackedText &text, uint32_t k, uint64_t n_kmers, uint32_t shift, uint32_t mask,
                       uint32_t *d_tile_hist, cudaStream_t stream);
-void launch_hist_pairs(const uint32_t *d_keys, uint64_t n, uint32_t shift, uint32_t mask, uint32_t *d_tile_hist,
-                       cudaStream_t stream);
+void launch_hist_pairs(const void *d_keys, uint32_t key_bytes, uint64_t n, uint32_t shift, uint32_t mask,
+                       uint32_t *d_tile_hist, cudaStream_t stream);
 void launch_column_scan(uint32_t *d_tile_hist, uint32_t n_tiles, uint32_t *d_chunk_sums, cudaStream_t stream);
-void launch_scatter_text(const PackedText &text, uint32_t k, uint64_t n_kmers, uint32_t shift, uint32_t mask,
-                         const uint32_t *d_tile_base, uint32_t *d_out_keys, uint32_t *d_out_vals, cudaStream_t stream);
-void launch_scatter_pairs(const uint32_t *d_keys, const uint32_t *d_vals, uint64_t n, uint32_t shift, uint32_t mask,
-                          const uint32_t *d_tile_base, uint32_t *d_out_keys, uint32_t *d_out_vals, cudaStream_t stream);
-void launch_directory_fill(const uint32_t *d_keys, uint64_t n_kmers, uint32_t shift, uint64_t dir_entries, uint32_t *d_dir,
-                           cudaStream_t stream);
+// key_bytes: 4 (sigma^k <= 2^32) or 8
+void launch_scatter_text(const PackedText &text, uint32_t k, uint32_t key_bytes, uint64_t n_kmers, uint32_t shift,
+                         uint32_t mask, const uint32_t *d_tile_base, void *d_out_keys, uint32_t *d_out_vals,
+                         cudaStream_t stream);
+void launch_scatter_pairs(const void *d_keys, const uint32_t *d_vals, uint32_t key_bytes, uint64_t n, uint32_t shift,
+                          uint32_t mask, const uint32_t *d_tile_base, void *d_out_keys, uint32_t *d_out_vals,
+                          cudaStream_t stream);
+void launch_directory_fill(const void *d_keys, uint32_t key_bytes, uint64_t n_kmers, uint32_t shift, uint64_t dir_entries,
+                           uint32_t *d_dir, cudaStream_t stream);
 uint32_t sort_tile_size();
 uint32_t scan_chunk_tiles();
 

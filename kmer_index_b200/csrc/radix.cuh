@@ -59,8 +59,8 @@ __device__ __forceinline__ uint32_t match_digit(uint32_t d, uint32_t peers) {
 //   local_pos[r] = position of item r in the tile's digit-sorted order (undefined for ignored items),
 //   sm.count[d]  = number of items with digit d, sm.excl[d] = exclusive prefix of count.
 // All kSortThreads threads must call. Ends with a __syncthreads().
-template <int BITS, bool FULL>
-__device__ __forceinline__ void tile_rank(const uint32_t (&key)[kSortItems], uint32_t count, uint32_t shift,
+template <int BITS, bool FULL, typename KeyT>
+__device__ __forceinline__ void tile_rank(const KeyT (&key)[kSortItems], uint32_t count, uint32_t shift,
                                           uint32_t mask, uint32_t (&local_pos)[kSortItems], RankSmem &sm) {
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -74,7 +74,7 @@ __device__ __forceinline__ void tile_rank(const uint32_t (&key)[kSortItems], uin
 
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
-        const uint32_t d = (key[r] >> shift) & mask;
+        const uint32_t d = (uint32_t)(key[r] >> shift) & mask;
         const bool valid = FULL || e0 + r * 32 < count;
         const uint32_t peers = match_digit<BITS>(d, FULL ? 0xFFFFFFFFu : __ballot_sync(0xFFFFFFFFu, valid));
         const uint32_t lower = peers & lt_mask;
@@ -118,7 +118,7 @@ __device__ __forceinline__ void tile_rank(const uint32_t (&key)[kSortItems], uin
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
-        const uint32_t d = (key[r] >> shift) & mask;
+        const uint32_t d = (uint32_t)(key[r] >> shift) & mask;
         if (FULL || e0 + r * 32 < count) local_pos[r] += my_cnt[d];
     }
     __syncthreads();

@@ -42,7 +42,7 @@ __device__ __forceinline__ uint64_t lower_bound_key(const Element &E, uint64_t k
     uint64_t hi = E.dir[t + 1];
     while (lo < hi) {
         const uint64_t mid = lo + ((hi - lo) >> 1);
-        if ((uint64_t)E.keys[mid] < key)
+        if (element_key(E, mid) < key)
             lo = mid + 1;
         else
             hi = mid;
@@ -51,7 +51,7 @@ __device__ __forceinline__ uint64_t lower_bound_key(const Element &E, uint64_t k
 }
 
 // the bucket of `key`: the reference's at(hash) (kmer_index.hpp:76-84)
-__device__ __forceinline__ Range bucket_of(const Element &E, uint32_t key) {
+__device__ __forceinline__ Range bucket_of(const Element &E, uint64_t key) {
     const uint64_t t = key >> E.shift;
     uint64_t lo = E.dir[t];
     uint64_t hi = E.dir[t + 1];
@@ -59,7 +59,7 @@ __device__ __forceinline__ Range bucket_of(const Element &E, uint32_t key) {
         uint64_t a = lo, b = hi;
         while (a < b) {
             const uint64_t mid = a + ((b - a) >> 1);
-            if (E.keys[mid] < key)
+            if (element_key(E, mid) < key)
                 a = mid + 1;
             else
                 b = mid;
@@ -68,7 +68,7 @@ __device__ __forceinline__ Range bucket_of(const Element &E, uint32_t key) {
         b = hi;
         while (a < b) {
             const uint64_t mid = a + ((b - a) >> 1);
-            if (E.keys[mid] <= key)
+            if (element_key(E, mid) <= key)
                 a = mid + 1;
             else
                 b = mid;
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(kSearchThreads, KB_SEARCH_MIN_BLOCKS) search_k
                     d = j * ix.elem[S[0]].k;  // expected at text offset j * k_0 (:535,544)
                 }
                 const Element &E = ix.elem[e];
-                const uint32_t key = key_from_window(window64(qw, (uint64_t)o, T.bits), E.k, T.bits, T.sigma);
+                const uint64_t key = key_from_window(window64(qw, (uint64_t)o, T.bits), E.k, T.bits, T.sigma);
                 rg = bucket_of(E, key);
                 if (kAccount) n_gather += 1 + (E.shift ? 1 : 0);
             }
@@ -453,10 +453,10 @@ __global__ void __launch_bounds__(kSearchThreads, KB_SEARCH_MIN_BLOCKS) search_k
         // get_position_for_all_kmer_with_prefix (kmer_index.hpp:115-148): the buckets of all hashes in
         // [prefix_hash, prefix_hash + sigma^(k-m)) are one contiguous slab of the sorted position array
         const uint64_t width = ix.pow_sigma[k0 - m];
-        const uint64_t lo_key = (uint64_t)key_from_window(window64(qw, 0, T.bits), m, T.bits, T.sigma) * width;
+        const uint64_t lo_key = key_from_window(window64(qw, 0, T.bits), m, T.bits, T.sigma) * width;
         const uint64_t slo = lower_bound_key(E0, lo_key);
         const uint64_t shi = lower_bound_key(E0, lo_key + width);
-        if (shi - slo > 1) unsorted = E0.keys[slo] != E0.keys[shi - 1];
+        if (shi - slo > 1) unsorted = element_key(E0, slo) != element_key(E0, shi - 1);
         const bool count_by_range = PASS != kPassWrite && ix.owned == T.n;  // unsharded: every hit is owned
         if (count_by_range) n_hits = shi - slo;
         for (uint64_t c0 = slo; c0 < shi && !count_by_range; c0 += G) {
@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(kSearchThreads, KB_SEARCH_MIN_BLOCKS) search_k
             }
             const Element &E = ix.elem[seed_e];
             if (gl == 0) {
-                const uint32_t key = key_from_window(window64(qw, 0, T.bits), E.k, T.bits, T.sigma);
+                const uint64_t key = key_from_window(window64(qw, 0, T.bits), E.k, T.bits, T.sigma);
                 seed = bucket_of(E, key);
                 if (kAccount) n_gather += 1 + (E.shift ? 1 : 0);
             }
@@ -893,7 +893,7 @@ __global__ void __launch_bounds__(kSortThreads, 1)
                     const uint32_t e = (uint32_t)((warp * kSortItems + r) * 32 + lane);
                     val[r] = e < count ? src[t0 + e] : 0u;
                 }
-                tile_rank<8, false>(val, count, shift, 0xFFu, local_pos, sm.rank);
+                tile_rank<8, false, uint32_t>(val, count, shift, 0xFFu, local_pos, sm.rank);
 #pragma unroll
                 for (int r = 0; r < kSortItems; ++r) {
                     const uint32_t e = (uint32_t)((warp * kSortItems + r) * 32 + lane);

@@ -15,13 +15,14 @@ def kb():
 
 
 def build_or_skip(kb, text, sigma, ks, **kw):
-    """Builds the index; configurations whose hashes need more than 32 bits are a documented gap of this
-    build ('Limits') and must fail loudly with ERR_UNSUPPORTED, never silently."""
+    """Builds the index; a k-mer wider than one 64-bit text window (k * bits-per-symbol > 64, e.g. aa27 k >= 9)
+    is a documented gap of this build ('Limits') and must fail loudly with ERR_UNSUPPORTED."""
     try:
         return kb.KmerIndex(text, sigma, ks, **kw)
     except kb.KmerB200Error as e:
-        if e.code == -5 and max(ks) * np.log2(sigma) > 32:
-            pytest.skip(f"sigma={sigma} k={max(ks)}: hashes wider than 32 bits are not built yet")
+        bits = 2 if sigma <= 4 else 4 if sigma <= 16 else 8
+        if e.code == -5 and max(ks) * bits > 64:
+            pytest.skip(f"sigma={sigma} k={max(ks)}: k-mers wider than 64 packed bits are not built yet")
         raise
 
 
@@ -49,7 +50,10 @@ def test_cuda_matches_oracle_on_golden_inputs_including_ub(kb, oracle_mod, name)
 
 @pytest.mark.parametrize("sigma,ks,n", [(4, [10], 1_000_000), (4, [12], 3_000_000), (4, [5, 7, 9, 11, 13], 500_000),
                                         (15, [8], 1_000_000), (27, [5], 1_000_000), (4, [16], 2_000_000),
-                                        (4, [1], 5000), (5, [13], 300_000), (4, [3, 9, 16], 200_000)])
+                                        (4, [1], 5000), (5, [13], 300_000), (4, [3, 9, 16], 200_000),
+                                        # hashes wider than 32 bits
+                                        (4, [20], 300_000), (4, [31], 100_000), (15, [12], 200_000), (15, [16], 50_000),
+                                        (27, [8], 100_000), (4, [12, 24], 100_000)])
 def test_csr_matches_oracle(kb, oracle_mod, sigma, ks, n):
     """The index itself: positions stably sorted by hash == the reference's buckets in hash order."""
     from kmer_index_b200 import synth
@@ -74,6 +78,12 @@ CASES = [
     ("dna15_mix", 15, [8], 300_000, 6000, 1, 30),
     ("aa27_mix", 27, [5], 300_000, 6000, 1, 20),
     ("dna5", 5, [13], 300_000, 4000, 5, 40),
+    # hashes wider than 32 bits (legal in the reference: k < 64 / log2(sigma), kmer_index.hpp:42)
+    ("dna4_k20", 4, [20], 500_000, 6000, 10, 70),
+    ("dna4_k31", 4, [31], 300_000, 4000, 20, 100),
+    ("dna15_k10", 15, [10], 300_000, 6000, 5, 30),
+    ("dna15_multi", 15, [10, 11, 12], 300_000, 6000, 5, 40),
+    ("dna4_mixed", 4, [9, 21], 300_000, 6000, 5, 70),
 ]
 
 
