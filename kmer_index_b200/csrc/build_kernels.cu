@@ -317,8 +317,13 @@ __device__ __forceinline__ void scatter_tile(const Source &src, uint64_t tile_be
     uint32_t local_pos[kSortItems];
     src.template load_keys<FULL>(tile_begin + e0, count - min(count, e0), key);
     src.template prefetch_vals<FULL>(tile_begin + e0, count - min(count, e0));
+#ifdef KB_ABL_NORANK  // timing ablation (profiles/README.md): identity placement instead of ranking
+    for (int r = 0; r < kSortItems; ++r) local_pos[r] = e0 + r * 32;
+    if (tid < kRadix) sm.delta[tid] = (uint32_t)tile_begin;
+#else
     tile_rank<BITS, FULL>(key, count, shift, mask, local_pos, sm.rank);
     if (tid < kRadix) sm.delta[tid] = tile_base_row[tid] - sm.rank.excl[tid];
+#endif
     {
         uint32_t val[kSortItems];
         src.template load_vals<FULL>(tile_begin + e0, count - min(count, e0), val);
@@ -327,6 +332,9 @@ __device__ __forceinline__ void scatter_tile(const Source &src, uint64_t tile_be
             if (FULL || e0 + r * 32 < count) sm.put(local_pos[r], key[r], val[r]);
     }
     __syncthreads();
+#ifdef KB_ABL_NOOUT  // timing ablation (profiles/README.md): skip the global stores
+    if (tile_begin == 0xFFFFFFFFFFull)
+#endif
     if (FULL) {
 #pragma unroll
         for (int it = 0; it < kSortItems; ++it) {
