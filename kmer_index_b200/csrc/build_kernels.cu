@@ -219,28 +219,43 @@ __global__ void __launch_bounds__(kRadix) column_sum_kernel(const uint32_t *__re
     chunk_sums[(uint64_t)blockIdx.x * kRadix + threadIdx.x] = s;
 }
 
-__global__ void __launch_bounds__(kRadix) column_base_kernel(uint32_t *__restrict__ chunk_sums, uint32_t n_chunks) {
+constexpr int kBaseSlices = 4;  // column_base: 4 x 256 threads, each slice walks a quarter of the chunks
+
+__global__ void __launch_bounds__(kRadix * kBaseSlices) column_base_kernel(uint32_t *__restrict__ chunk_sums, uint32_t n_chunks) {
     __shared__ uint32_t warp_sums[kRadix / 32];
-    const int d = threadIdx.x;
-    // digit totals
+    __shared__ uint32_t slice_tot[kBaseSlices][kRadix];
+    const int d = threadIdx.x & (kRadix - 1);
+    const int slice = threadIdx.x / kRadix;
+    const uint32_t per = (n_chunks + kBaseSlices - 1) / kBaseSlices;
+    const uint32_t c0 = min(slice * per, n_chunks), c1 = min(c0 + per, n_chunks);
+    // per-slice digit totals
     uint32_t total = 0;
 #pragma unroll 8
-    for (uint32_t c = 0; c < n_chunks; ++c) total += chunk_sums[(uint64_t)c * kRadix + d];
-    // exclusive scan of totals over digits
+    for (uint32_t c = c0; c < c1; ++c) total += chunk_sums[(uint64_t)c * kRadix + d];
+    slice_tot[slice][d] = total;
+    __syncthreads();
+    uint32_t before = 0, digit_total = 0;  // chunks of earlier slices; all chunks
+#pragma unroll
+    for (int sl = 0; sl < kBaseSlices; ++sl) {
+        const uint32_t t = slice_tot[sl][d];
+        if (sl < slice) before += t;
+        digit_total += t;
+    }
+    // exclusive scan of the digit totals over the 256 digits (done redundantly by every slice)
     const int lane = d & 31, warp = d >> 5;
-    uint32_t incl = total;
+    uint32_t incl = digit_total;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
         if (lane >= o) incl += v;
     }
-    if (lane == 31) warp_sums[warp] = incl;
+    if (slice == 0 && lane == 31) warp_sums[warp] = incl;
     __syncthreads();
-    uint32_t base = incl - total;
+    uint32_t base = incl - digit_total;
     for (int w = 0; w < warp; ++w) base += warp_sums[w];
     // chunk_sums[c][d] <- base(d) + sum of earlier chunks
-    uint32_t run = base;
-    for (uint32_t c = 0; c < n_chunks; ++c) {
+    uint32_t run = base + before;
+    for (uint32_t c = c0; c < c1; ++c) {
         const uint32_t v = chunk_sums[(uint64_t)c * kRadix + d];
         chunk_sums[(uint64_t)c * kRadix + d] = run;
         run += v;
@@ -379,43 +394,79 @@ __global__ void __launch_bounds__(kSortThreads, sizeof(typename Source::key_type
 // Thread i owns the boundary between sorted elements i-1 and i and fills the directory entries that
 // fall into it; long runs (sparse key spaces) are filled by the whole warp, coalesced.
 // ------------------------------------------------------------------------------------------------
+constexpr int kDirItems = 4;  // boundaries per thread: one 16-byte (32-bit keys) or two 16-byte loads in flight
+
 template <typename KeyT>
 __global__ void __launch_bounds__(256) directory_fill_kernel(const KeyT *__restrict__ keys, uint64_t n_kmers,
                                                              uint32_t shift, uint64_t dir_entries,
                                                              uint32_t *__restrict__ dir) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // boundary index in [0, n_kmers]
+    const uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * kDirItems;  // first boundary of this thread
     const int lane = threadIdx.x & 31;
     // boundary i fills dir[lo .. lo + len) = i, where lo = (key[i-1] >> shift) + 1 and the run ends at
     // key[i] >> shift (dir_entries - 1 for the closing boundary i == n_kmers)
-    uint64_t lo = 0;
-    uint64_t len = 0;
-    if (i <= n_kmers) {
-        lo = (i == 0) ? 0 : (uint64_t)(keys[i - 1] >> shift) + 1;
-        const uint64_t hi = (i == n_kmers) ? dir_entries - 1 : (uint64_t)(keys[i] >> shift);
-        len = hi + 1 - lo;  // 0 when both neighbours share a directory slot
+    KeyT k[kDirItems + 1];  // keys[i0 - 1 .. i0 + kDirItems - 1]
+    k[0] = (i0 >= 1 && i0 - 1 < n_kmers) ? keys[i0 - 1] : (KeyT)0;
+    if (i0 + kDirItems <= n_kmers) {
+        // aligned vector load: i0 is a multiple of kDirItems and the array comes from cudaMalloc
+        if (sizeof(KeyT) == 4) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(keys + i0);
+            k[1] = (KeyT)v.x;
+            k[2] = (KeyT)v.y;
+            k[3] = (KeyT)v.z;
+            k[4] = (KeyT)v.w;
+        } else {
+            const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(keys + i0);
+            const ulonglong2 b = *reinterpret_cast<const ulonglong2 *>(keys + i0 + 2);
+            k[1] = (KeyT)a.x;
+            k[2] = (KeyT)a.y;
+            k[3] = (KeyT)b.x;
+            k[4] = (KeyT)b.y;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kDirItems; ++j) k[j + 1] = (i0 + j < n_kmers) ? keys[i0 + j] : (KeyT)0;
     }
-    uint32_t *out = dir + lo;
-    const uint32_t v = (uint32_t)i;
-    if (len >= 1) out[0] = v;  // the common cases, branch-free
-    if (len >= 2) out[1] = v;
-    if (len >= 3 && len < 32) {
-        for (uint32_t j = 2; j < (uint32_t)len; ++j) out[j] = v;
+    bool any_long = false;
+    uint64_t lo[kDirItems], len[kDirItems];
+#pragma unroll
+    for (int j = 0; j < kDirItems; ++j) {
+        const uint64_t i = i0 + j;
+        lo[j] = 0;
+        len[j] = 0;
+        if (i <= n_kmers) {
+            lo[j] = (i == 0) ? 0 : (uint64_t)(k[j] >> shift) + 1;
+            const uint64_t hi = (i == n_kmers) ? dir_entries - 1 : (uint64_t)(k[j + 1] >> shift);
+            len[j] = hi + 1 - lo[j];  // 0 when both neighbours share a directory slot
+        }
+        uint32_t *out = dir + lo[j];
+        const uint32_t v = (uint32_t)i;
+        if (len[j] >= 1) out[0] = v;  // the common cases, branch-free
+        if (len[j] >= 2) out[1] = v;
+        if (len[j] >= 3 && len[j] < 32) {
+            for (uint32_t e = 2; e < (uint32_t)len[j]; ++e) out[e] = v;
+        }
+        any_long |= len[j] >= 32;
     }
     // long runs (sparse key spaces, low-entropy texts): the whole warp fills them, coalesced
-    uint32_t long_mask = __ballot_sync(0xFFFFFFFFu, len >= 32);
-    while (long_mask) {
-        const int src = __ffs(long_mask) - 1;
-        long_mask &= long_mask - 1;
-        const uint64_t l0 = __shfl_sync(0xFFFFFFFFu, lo, src);
-        const uint64_t n0 = __shfl_sync(0xFFFFFFFFu, len, src);
-        const uint32_t vv = __shfl_sync(0xFFFFFFFFu, v, src);
-        for (uint64_t j = 2 + lane; j < n0; j += 32) dir[l0 + j] = vv;
+    if (__any_sync(0xFFFFFFFFu, any_long)) {
+#pragma unroll
+        for (int j = 0; j < kDirItems; ++j) {
+            uint32_t long_mask = __ballot_sync(0xFFFFFFFFu, len[j] >= 32);
+            while (long_mask) {
+                const int src = __ffs(long_mask) - 1;
+                long_mask &= long_mask - 1;
+                const uint64_t l0 = __shfl_sync(0xFFFFFFFFu, lo[j], src);
+                const uint64_t n0 = __shfl_sync(0xFFFFFFFFu, len[j], src);
+                const uint32_t vv = (uint32_t)__shfl_sync(0xFFFFFFFFu, (unsigned long long)(i0 + j), src);
+                for (uint64_t e = 2 + lane; e < n0; e += 32) dir[l0 + e] = vv;
+            }
+        }
     }
 }
 
 void launch_directory_fill(const void *d_keys, uint32_t key_bytes, uint64_t n_kmers, uint32_t shift, uint64_t dir_entries,
                            uint32_t *d_dir, cudaStream_t stream) {
-    const uint64_t blocks = (n_kmers + 1 + 255) / 256;
+    const uint64_t blocks = (n_kmers + 1 + 256 * kDirItems - 1) / (256 * kDirItems);
     if (key_bytes == 8)
         directory_fill_kernel<uint64_t><<<(unsigned)blocks, 256, 0, stream>>>((const uint64_t *)d_keys, n_kmers, shift, dir_entries, d_dir);
     else
@@ -454,7 +505,7 @@ static void launch_scatter(const Source &src, uint64_t n, uint32_t shift, uint32
 void launch_column_scan(uint32_t *d_tile_hist, uint32_t n_tiles, uint32_t *d_chunk_sums, cudaStream_t stream) {
     const uint32_t n_chunks = (n_tiles + kScanChunk - 1) / kScanChunk;
     column_sum_kernel<<<n_chunks, kRadix, 0, stream>>>(d_tile_hist, n_tiles, d_chunk_sums);
-    column_base_kernel<<<1, kRadix, 0, stream>>>(d_chunk_sums, n_chunks);
+    column_base_kernel<<<1, kRadix * kBaseSlices, 0, stream>>>(d_chunk_sums, n_chunks);
     column_apply_kernel<<<n_chunks, kRadix, 0, stream>>>(d_tile_hist, n_tiles, d_chunk_sums);
 }
 
