@@ -699,12 +699,15 @@ struct PendingSearch {
     uint8_t *d_unsorted = nullptr;
     uint8_t *d_defer = nullptr;
     uint64_t *d_block_sums = nullptr;
+    uint32_t *d_heavy = nullptr;  // [0] = count, [1..Q] = ids of queries with long candidate lists
     void release() {
         dev_free(ix, d_unsorted);
         dev_free(ix, d_defer);
         dev_free(ix, d_block_sums);
+        dev_free(ix, d_heavy);
         d_unsorted = d_defer = nullptr;
         d_block_sums = nullptr;
+        d_heavy = nullptr;
     }
 };
 
@@ -732,8 +735,9 @@ int search_begin(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off,
     };
     if (dev_alloc(ix, &res->offsets, Q + 1, false) || dev_alloc(ix, &res->status, Q, false) ||
         dev_alloc(ix, &p->d_unsorted, Q, false) || dev_alloc(ix, &p->d_block_sums, offsets_scan_blocks(Q) + 1, false) ||
-        (d_present4 && dev_alloc(ix, &p->d_defer, Q, false)))
+        (d_present4 && dev_alloc(ix, &p->d_defer, Q, false)) || dev_alloc(ix, &p->d_heavy, Q + 1, false))
         return bail(KMER_B200_ERR_OUT_OF_MEMORY);
+    cudaMemsetAsync(p->d_heavy, 0, sizeof(uint32_t), st);
 
     SearchArgs &a = p->args;
     a = SearchArgs{};
@@ -752,6 +756,8 @@ int search_begin(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off,
     a.present = nullptr;
     a.present4 = d_present4;
     a.defer = p->d_defer;
+    a.heavy = p->d_heavy;
+    a.bits = ix->bits;
     a.error_flag = ix->d_flags;
     a.gather_count = ix->cfg.profile >= 2 ? ix->d_gathers : nullptr;  // profile = 2: also count gathered sectors
     if (a.gather_count) cudaMemsetAsync(ix->d_gathers, 0, sizeof(unsigned long long), st);
@@ -985,6 +991,7 @@ int kmer_b200_presence_batch_device(kmer_b200_index *ix, const uint8_t *d_q, con
     a.mode = mode;
     a.present = present_format == 0 ? (uint64_t *)d_present : nullptr;
     a.present4 = present_format == 1 ? (uint32_t *)d_present : nullptr;
+    a.bits = ix->bits;
     a.error_flag = ix->d_flags;
     ix->prof.begin(K_SEARCH_PRESENCE, 0);
     launch_search(a, kPassPresence, ix->stream);

@@ -131,13 +131,16 @@ __device__ __forceinline__ uint64_t load8(const uint8_t *p, uint32_t n_valid, bo
 // One group of G lanes per query (G = 8 for short queries and short buckets, 32 otherwise): the scalar part
 // of a query (plan, status) costs a warp instruction per group, not per warp, and G/32 more queries are in
 // flight per SM to cover the chain of dependent gathers (offsets -> ranks -> directory -> bucket -> text).
-template <int PASS_, int G>
-__global__ void __launch_bounds__(kSearchThreads, KB_SEARCH_MIN_BLOCKS) search_kernel(const SearchArgs a) {
+// Candidate lists longer than this are not walked by a small group: the query is appended to the batch's
+// "heavy" list and a second launch gives it a full warp (long buckets of repetitive / low-entropy text).
+constexpr uint32_t kHeavyCandidates = 2048;
+
+// HEAVY = true: the second launch (G = 32) over the heavy list; never hands a query off again.
+template <int PASS_, int G, bool HEAVY>
+__device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t q, uint64_t *smem_q) {
     constexpr bool kAccount = PASS_ == kPassCountAccount;  // count pass that also sums the gathered sectors
     constexpr bool kDefer = PASS_ == kPassCountDeferred;   // count pass that leaves the whole-text rule for later
     constexpr int PASS = (kAccount || kDefer) ? (int)kPassCount : PASS_;
-    constexpr int kGroups = kSearchThreads / G;
-    extern __shared__ uint64_t smem_q[];
     const int lane = threadIdx.x & 31;
     const int gl = threadIdx.x & (G - 1);          // lane inside the group
     const int group = threadIdx.x / G;             // group inside the CTA
@@ -145,9 +148,18 @@ __global__ void __launch_bounds__(kSearchThreads, KB_SEARCH_MIN_BLOCKS) search_k
     const uint32_t gfull = G == 32 ? 0xFFFFFFFFu : ((1u << G) - 1);
     const uint32_t gmask = gfull << gshift;
     const uint32_t lt_mask = (1u << gl) - 1;
-    const uint64_t q = (uint64_t)blockIdx.x * kGroups + group;
-    if (q >= a.n_queries) return;
 #define GBALLOT(pred) ((__ballot_sync(gmask, (pred)) >> gshift) & gfull)
+// hand the query to the heavy launch: count passes enlist it (and report no hits for now), the write pass skips it
+#define HAND_OFF_IF_HEAVY(len)                                                        \
+    if (!HEAVY && G < 32 && a.heavy != nullptr && (len) > (uint64_t)kHeavyCandidates) { \
+        if (PASS == kPassCount && gl == 0) {                                          \
+            a.heavy[1 + atomicAdd(a.heavy, 1u)] = (uint32_t)q;                        \
+            a.counts[q] = 0;                                                          \
+            a.status[q] = KMER_B200_QUERY_OK;                                         \
+            a.unsorted[q] = 0;                                                        \
+        }                                                                             \
+        return;                                                                       \
+    }
 
     uint64_t out_base = 0;
     if (PASS == kPassWrite) {
@@ -458,6 +470,7 @@ __global__ void __launch_bounds__(kSearchThreads, KB_SEARCH_MIN_BLOCKS) search_k
         const uint64_t shi = lower_bound_key(E0, lo_key + width);
         if (shi - slo > 1) unsorted = element_key(E0, slo) != element_key(E0, shi - 1);
         const bool count_by_range = PASS != kPassWrite && ix.owned == T.n;  // unsharded: every hit is owned
+        HAND_OFF_IF_HEAVY(shi - slo)  // same decision in the count and the write pass
         if (count_by_range) n_hits = shi - slo;
         for (uint64_t c0 = slo; c0 < shi && !count_by_range; c0 += G) {
             const uint64_t c = c0 + gl;
@@ -536,6 +549,7 @@ __global__ void __launch_bounds__(kSearchThreads, KB_SEARCH_MIN_BLOCKS) search_k
         const uint32_t ks = Es.k;
         const uint32_t kf = from_list ? ix.elem[S[0]].k : k0;  // k of part 0 (text stride of the multi-k defect)
         bool count_by_range = PASS != kPassWrite && kind == kExact && ix.owned == T.n;
+        HAND_OFF_IF_HEAVY(seed.cnt)  // same decision in the count and the write pass
         if (count_by_range) n_hits = seed.cnt;
         if (PASS == kPassWrite && kind == kExact && ix.owned == T.n) {
             // the whole bucket is the result: a plain copy with 8 independent loads in flight per lane
@@ -599,7 +613,28 @@ __global__ void __launch_bounds__(kSearchThreads, KB_SEARCH_MIN_BLOCKS) search_k
         a.unsorted[q] = flag ? 1 : 0;
         if (flag) atomicAdd(a.error_flag + 1, 1u);  // number of segments the sort pass has to visit
     }
+#undef HAND_OFF_IF_HEAVY
 #undef GBALLOT
+}
+
+template <int PASS, int G>
+__global__ void __launch_bounds__(kSearchThreads, KB_SEARCH_MIN_BLOCKS) search_kernel(const SearchArgs a) {
+    constexpr int kGroups = kSearchThreads / G;
+    extern __shared__ uint64_t smem_q[];
+    const uint64_t q = (uint64_t)blockIdx.x * kGroups + threadIdx.x / G;
+    if (q < a.n_queries) search_query<PASS, G, false>(a, q, smem_q);
+}
+
+// second launch of a pass: one warp per query of the heavy list (a.heavy[0] = length, a.heavy[1..] = query ids)
+template <int PASS>
+__global__ void __launch_bounds__(kSearchThreads) search_heavy_kernel(const SearchArgs a) {
+    constexpr int kGroups = kSearchThreads / 32;
+    extern __shared__ uint64_t smem_q[];
+    const uint32_t n_heavy = a.heavy[0];
+    for (uint32_t i = blockIdx.x * kGroups + threadIdx.x / 32; i < n_heavy; i += gridDim.x * kGroups) {
+        search_query<PASS, 32, true>(a, (uint64_t)a.heavy[1 + i], smem_q);
+        __syncwarp();
+    }
 }
 
 template <int PASS, int G>
@@ -609,6 +644,14 @@ static void launch_search_pg(const SearchArgs &args, cudaStream_t stream) {
     const size_t smem = (size_t)kGroups * args.q_words * sizeof(uint64_t);
     cudaFuncSetAttribute(search_kernel<PASS, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     search_kernel<PASS, G><<<(unsigned)blocks, kSearchThreads, smem, stream>>>(args);
+    if (G < 32 && args.heavy != nullptr && PASS != kPassPresence) {
+        // queries with long candidate lists, if any (the list length lives on the device: fixed grid, no host sync)
+        SearchArgs h = args;
+        h.q_words = search_q_words(32, args.bits, args.max_len);
+        const size_t hsmem = (size_t)(kSearchThreads / 32) * h.q_words * sizeof(uint64_t);
+        cudaFuncSetAttribute(search_heavy_kernel<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem);
+        search_heavy_kernel<PASS><<<148 * 2, kSearchThreads, hsmem, stream>>>(h);
+    }
 }
 
 // epilogue of the deferred count pass: the whole-text presence rule (kmer_index.hpp:216-227, :234 -> :119)

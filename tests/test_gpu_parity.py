@@ -211,3 +211,27 @@ def test_sharded_search_emulated_on_one_gpu(kb, oracle_mod, sigma, ks, n, m_lo, 
         want = o.search(q, off)
     assert_results_equal(got, want, label=f"sharded x{world} {ks}")
     assert want[1].size > 0
+
+
+@pytest.mark.parametrize("sigma,ks", [(4, [12]), (4, [5, 7, 9, 11, 13]), (15, [8]), (4, [20])])
+def test_heavy_buckets_take_the_warp_path(kb, oracle_mod, sigma, ks):
+    """A text with one enormous bucket (a long constant run): the index-wide average bucket is ~1, so queries get
+    one or two lanes each -- except those whose candidate list is long, which are handed to the warp-per-query
+    launch. Results must not depend on which launch answered."""
+    from kmer_index_b200 import synth
+    text = synth.random_text(150_000, sigma, 5)
+    text[20_000:90_000] = 0
+    text[100_000:100_300] = np.resize(np.array([1, 0, 0], dtype=np.uint8), 300)
+    q, off = synth.stress_queries(text, 3000, 1, 48, sigma, 6, low_sigma=2)
+    # make sure the batch contains constant queries of many lengths (they hit the 70 000-element buckets)
+    lens = (off[1:] - off[:-1]).astype(np.int64)
+    for i in range(0, 600, 3):
+        q[int(off[i]):int(off[i]) + int(lens[i])] = 0
+    with kb.KmerIndex(text, sigma, ks) as ix, oracle_mod.Oracle(text, sigma, ks) as o:
+        want = o.search(q, off)
+        for attempt in range(2):
+            got = ix.search_batch(q, off).as_tuple()
+            assert_results_equal(got, want, label=f"heavy {ks}/{attempt}")
+        assert int((want[0][1:] - want[0][:-1]).max()) > 2048
+    with kb.KmerIndex(text, sigma, ks, mode=kb.MODE_CORRECT) as ix:
+        assert_results_equal(ix.search_batch(q, off).as_tuple(), oracle_mod.Oracle.truth(text, q, off), label="heavy correct")
