@@ -92,6 +92,13 @@ int kmer_b200_create_from_device(const uint8_t *d_ranks, uint64_t n, uint32_t si
 
 void kmer_b200_destroy(kmer_b200_index *index);
 
+/* ---- serialization: construct once, load later (the thesis assumes it, thesis/content/02_implementation.tex:44-46,
+   the reference ships no code for it). The file holds the packed text and every element's CSR arrays; load
+   restores the index without rebuilding. cfg (device, stream, mode, profile) applies to the loaded index; its
+   shard geometry comes from the file. */
+int kmer_b200_save(kmer_b200_index *index, const char *path);
+int kmer_b200_load(const char *path, const kmer_b200_config *cfg, kmer_b200_index **out);
+
 /* ---- search: replaces kmer_index::search(std::vector<alphabet_t>&) (kmer_index.hpp:505-558) followed
    by kmer_index_result::to_vector() (kmer_index_result.hpp:244-260), for a batch of Q queries.
    q_ranks: all queries' ranks back to back; q_offsets[Q+1]: start of each query in q_ranks.

@@ -175,6 +175,8 @@ namespace kmer
         kmer_b200_index* _handle = nullptr;
         std::size_t _query_size_range = 10000;   // kmer_index.hpp:401
 
+        explicit kmer_index(std::nullptr_t) {}   // empty shell for load()
+
     public:
         template<std::ranges::range text_t>
         explicit kmer_index(text_t& text, std::size_t /*n_threads*/ = 1, kmer_b200_mode mode = KMER_B200_MODE_REFERENCE_EXACT,
@@ -188,6 +190,29 @@ namespace kmer
             cfg.device = device;
             detail::check(kmer_b200_create(ranks.data(), ranks.size(), std::uint32_t(alphabet_size<alphabet_t>), k_list,
                                            sizeof...(ks), &cfg, &_handle));
+        }
+
+        // construct once, load later: kmer_index<...>::load(path) restores an index written by save(path)
+        void save(std::string const& path) const { detail::check(kmer_b200_save(_handle, path.c_str())); }
+        static kmer_index load(std::string const& path, kmer_b200_mode mode = KMER_B200_MODE_REFERENCE_EXACT, int device = -1)
+        {
+            kmer_b200_config cfg;
+            kmer_b200_config_default(&cfg);
+            cfg.mode = mode;
+            cfg.device = device;
+            kmer_index out{nullptr};
+            detail::check(kmer_b200_load(path.c_str(), &cfg, &out._handle));
+            static constexpr std::uint32_t k_list[] = {std::uint32_t(ks)...};
+            if (kmer_b200_n_elements(out._handle) != sizeof...(ks))
+                throw std::invalid_argument("index file holds a different set of ks");
+            for (std::uint32_t i = 0; i < sizeof...(ks); ++i)
+            {
+                kmer_b200_element_info info;
+                detail::check(kmer_b200_element_info_get(out._handle, i, &info));
+                if (info.k != k_list[i])
+                    throw std::invalid_argument("index file holds a different set of ks");
+            }
+            return out;
         }
 
         kmer_index(kmer_index const&) = delete;

@@ -170,6 +170,28 @@ class KmerIndex:
             _capi.check(L.kmer_b200_create(t.ctypes.data_as(_capi.u8p), t.size, self.sigma,
                                            ks_a.ctypes.data_as(_capi.u32p), ks_a.size, C.byref(cfg), C.byref(self._h)))
 
+    # -- serialization (construct once, load later)
+    def save(self, path: str) -> None:
+        _capi.check(self._L.kmer_b200_save(self._h, str(path).encode()))
+
+    @classmethod
+    def load(cls, path: str, *, mode: int | None = None, device: int = -1, stream: int | None = None,
+             profile: int = 0) -> "KmerIndex":
+        L = _capi.lib()
+        self = cls.__new__(cls)
+        self._L = L
+        self._h = C.c_void_p()
+        cfg = _capi.Config()
+        L.kmer_b200_config_default(C.byref(cfg))
+        cfg.device, cfg.stream, cfg.profile = device, stream, int(profile)
+        cfg.mode = MODE_REFERENCE_EXACT if mode is None else mode
+        _capi.check(L.kmer_b200_load(str(path).encode(), C.byref(cfg), C.byref(self._h)))
+        n_el = L.kmer_b200_n_elements(self._h)
+        self.ks = [int(self.element_info(e).k) for e in range(n_el)]
+        self.sigma = None
+        self.n = int(self.element_info(0).n_kmers) + self.ks[0] - 1
+        return self
+
     # -- lifetime
     def close(self):
         if getattr(self, "_h", None):

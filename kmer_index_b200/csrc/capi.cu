@@ -175,6 +175,7 @@ struct kmer_b200_index {
     uint64_t last_gathers = 0;
     uint64_t device_bytes = 0;
     bool reaches_end = true;  // the local slice ends at the end of the whole text
+    bool sharded = false;
     double max_avg_bucket = 0;  // max over elements of (k-mers / distinct possible hashes)
     Profiler prof;
     std::mutex mu;  // serialises searches on one handle (they share the stream and the flag words)
@@ -434,11 +435,21 @@ int build_element(kmer_b200_index *ix, uint32_t k, HostElement &he, bool auxilia
     return 0;
 }
 
-int create_impl(const uint8_t *ranks, bool ranks_on_device, uint64_t n, uint32_t sigma, const uint32_t *ks, uint32_t n_ks,
-                const kmer_b200_config *cfg_in, kmer_b200_index **out) {
-    if (!out) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "out is null");
+#define KB_CUDA_RET(expr)                                                                           \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            cudaGetLastError();                                                                     \
+            return fail(_e == cudaErrorMemoryAllocation ? KMER_B200_ERR_OUT_OF_MEMORY : KMER_B200_ERR_CUDA, \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));                        \
+        }                                                                                           \
+    } while (0)
+
+// Validated, empty index: configuration, device, stream, scratch. The caller destroys it on later failures.
+int new_index(uint64_t n, uint32_t sigma, const uint32_t *ks, uint32_t n_ks, const kmer_b200_config *cfg_in,
+              kmer_b200_index **out) {
     *out = nullptr;
-    if (!ranks || !ks) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "ranks/ks is null");
+    if (!ks) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "ks is null");
     if (n_ks == 0 || n_ks > (uint32_t)kb::kMaxElements)
         return fail(KMER_B200_ERR_INVALID_ARGUMENT, "number of ks must be in [1, 32]");
     if (sigma < 2 || sigma > 256) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "sigma must be in [2, 256]");
@@ -497,30 +508,12 @@ int create_impl(const uint8_t *ranks, bool ranks_on_device, uint64_t n, uint32_t
     ix->bits = bits;
     ix->ks.assign(ks, ks + n_ks);
     ix->reaches_end = reaches_end;
-    auto bail = [&](int code) {
-        kmer_b200_destroy(ix);
-        return code;
-    };
-#define KB_OR_BAIL(expr)                \
-    do {                                \
-        int _s = (expr);                \
-        if (_s != 0) return bail(_s);   \
-    } while (0)
-#define KB_CUDA_OR_BAIL(expr)                                                                      \
-    do {                                                                                           \
-        cudaError_t _e = (expr);                                                                   \
-        if (_e != cudaSuccess) {                                                                   \
-            cudaGetLastError();                                                                    \
-            return bail(fail(_e == cudaErrorMemoryAllocation ? KMER_B200_ERR_OUT_OF_MEMORY         \
-                                                             : KMER_B200_ERR_CUDA,                 \
-                             std::string(#expr) + ": " + cudaGetErrorString(_e)));                 \
-        }                                                                                          \
-    } while (0)
-
+    ix->sharded = sharded;
+    *out = ix;  // from here on the caller owns (and destroys) it
     if (cfg.stream) {
         ix->stream = (cudaStream_t)cfg.stream;
     } else {
-        KB_CUDA_OR_BAIL(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+        KB_CUDA_RET(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
         ix->own_stream = true;
     }
     ix->prof.enabled = cfg.profile != 0;
@@ -534,30 +527,18 @@ int create_impl(const uint8_t *ranks, bool ranks_on_device, uint64_t n, uint32_t
         }
     }
     ix->h_pinned = (uint64_t *)pinned_get(8 * sizeof(uint64_t), &ix->h_pinned_cap);
-    if (!ix->h_pinned) return bail(fail(KMER_B200_ERR_OUT_OF_MEMORY, "pinned host allocation failed"));
-    KB_OR_BAIL(dev_alloc(ix, &ix->d_flags, 4, true));
-    KB_OR_BAIL(dev_alloc(ix, &ix->d_gathers, 1, true));
-    KB_CUDA_OR_BAIL(cudaMemsetAsync(ix->d_flags, 0, 4 * sizeof(uint32_t), ix->stream));
-
-    // ---- text: H2D (if needed) + pack
-    const uint8_t *d_ranks = ranks;
-    uint8_t *d_ranks_owned = nullptr;
-    if (!ranks_on_device) {
-        KB_OR_BAIL(dev_alloc(ix, &d_ranks_owned, n, false));
-        KB_CUDA_OR_BAIL(cudaMemcpyAsync(d_ranks_owned, ranks, n, cudaMemcpyHostToDevice, ix->stream));
-        d_ranks = d_ranks_owned;
-    }
+    if (!ix->h_pinned) return fail(KMER_B200_ERR_OUT_OF_MEMORY, "pinned host allocation failed");
+    KB_TRY(dev_alloc(ix, &ix->d_flags, 4, true));
+    KB_TRY(dev_alloc(ix, &ix->d_gathers, 1, true));
+    KB_CUDA_RET(cudaMemsetAsync(ix->d_flags, 0, 4 * sizeof(uint32_t), ix->stream));
     ix->text_words = (n * bits + 63) / 64 + 2;
-    KB_OR_BAIL(dev_alloc(ix, &ix->d_text, ix->text_words, true));
-    ix->prof.begin(K_PACK_TEXT, (double)n + (double)n * bits / 8.0);
-    kb::launch_pack_text(d_ranks, n, bits, sigma, ix->text_words, ix->d_text, ix->d_flags, ix->stream);
-    ix->prof.end();
-    if (d_ranks_owned) dev_free(ix, d_ranks_owned);
+    KB_TRY(dev_alloc(ix, &ix->d_text, ix->text_words, true));
+    return KMER_B200_OK;
+}
 
-    // ---- elements
-    ix->elems.resize(n_ks);
-    for (uint32_t i = 0; i < n_ks; ++i) KB_OR_BAIL(build_element(ix, ks[i], ix->elems[i]));
-
+// Scheme tables, device-side descriptor, final synchronisation. ix->elems must be complete.
+int finalize_index(kmer_b200_index *ix) {
+    const uint32_t n_ks = (uint32_t)ix->ks.size();
     // ---- scheme tables (depend on the ks only: cached per process, a multi-k table costs ~50 ms of host time)
     {
         static std::mutex mu;
@@ -577,51 +558,120 @@ int create_impl(const uint8_t *ranks, bool ranks_on_device, uint64_t n, uint32_t
         ix->sum_elem = hit->sum_elem;
         ix->use_multi = hit->use_multi;
     }
-    KB_OR_BAIL(dev_alloc(ix, &ix->d_sum_off, ix->sum_off.size(), true));
-    KB_OR_BAIL(dev_alloc(ix, &ix->d_sum_elem, ix->sum_elem.size(), true));
-    KB_OR_BAIL(dev_alloc(ix, &ix->d_use_multi, ix->use_multi.size(), true));
-    KB_CUDA_OR_BAIL(cudaMemcpyAsync(ix->d_sum_off, ix->sum_off.data(), ix->sum_off.size() * sizeof(uint32_t),
-                                    cudaMemcpyHostToDevice, ix->stream));
-    KB_CUDA_OR_BAIL(cudaMemcpyAsync(ix->d_sum_elem, ix->sum_elem.data(), ix->sum_elem.size(), cudaMemcpyHostToDevice,
-                                    ix->stream));
-    KB_CUDA_OR_BAIL(cudaMemcpyAsync(ix->d_use_multi, ix->use_multi.data(), ix->use_multi.size(), cudaMemcpyHostToDevice,
-                                    ix->stream));
+    KB_TRY(dev_alloc(ix, &ix->d_sum_off, ix->sum_off.size(), true));
+    KB_TRY(dev_alloc(ix, &ix->d_sum_elem, ix->sum_elem.size(), true));
+    KB_TRY(dev_alloc(ix, &ix->d_use_multi, ix->use_multi.size(), true));
+    KB_CUDA_RET(cudaMemcpyAsync(ix->d_sum_off, ix->sum_off.data(), ix->sum_off.size() * sizeof(uint32_t),
+                                cudaMemcpyHostToDevice, ix->stream));
+    KB_CUDA_RET(cudaMemcpyAsync(ix->d_sum_elem, ix->sum_elem.data(), ix->sum_elem.size(), cudaMemcpyHostToDevice,
+                                ix->stream));
+    KB_CUDA_RET(cudaMemcpyAsync(ix->d_use_multi, ix->use_multi.data(), ix->use_multi.size(), cudaMemcpyHostToDevice,
+                                ix->stream));
 
     // ---- device-side index descriptor
     kb::DeviceIndex &D = ix->host_index;
     std::memset(&D, 0, sizeof(D));
-    D.text = kb::PackedText{ix->d_text, n, bits, sigma};
-    D.owned = n - cfg.halo;
-    D.global_base = cfg.shard_begin;
+    D.text = kb::PackedText{ix->d_text, ix->n, ix->bits, ix->sigma};
+    D.owned = ix->n - ix->cfg.halo;
+    D.global_base = ix->cfg.shard_begin;
     D.n_elems = n_ks;
-    D.sharded = sharded ? 1 : 0;
+    D.sharded = ix->sharded ? 1 : 0;
     for (uint32_t i = 0; i < n_ks; ++i) D.elem[i] = ix->elems[i].dev;
     D.scheme = kb::SchemeTables{ix->d_sum_off, ix->d_sum_elem, ix->d_use_multi};
     std::memset(D.aux_for_len, 0xFF, sizeof(D.aux_for_len));
     for (uint32_t e = 0; e <= 32; ++e) {
-        // saturating: only compared against 1e7 and used as slab width when < sigma^k <= 2^32
-        const double approx = std::pow((double)sigma, (double)e);
-        D.pow_sigma[e] = approx > 9.0e18 ? (1ull << 63) : fast_pow(sigma, (uint8_t)e);
+        // saturating: only compared against 1e7 and used as slab width when < sigma^k
+        const double approx = std::pow((double)ix->sigma, (double)e);
+        D.pow_sigma[e] = approx > 9.0e18 ? (1ull << 63) : fast_pow(ix->sigma, (uint8_t)e);
     }
     {
         std::vector<uint32_t> order(n_ks);
         for (uint32_t i = 0; i < n_ks; ++i) order[i] = i;
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ks[a] > ks[b]; });
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ix->ks[a] > ix->ks[b]; });
         for (uint32_t i = 0; i < n_ks; ++i) D.elem_by_k_desc[i] = (uint8_t)order[i];
     }
-    KB_OR_BAIL(dev_alloc(ix, &ix->d_index, 1, true));
-    KB_CUDA_OR_BAIL(cudaMemcpyAsync(ix->d_index, &D, sizeof(D), cudaMemcpyHostToDevice, ix->stream));
+    KB_TRY(dev_alloc(ix, &ix->d_index, 1, true));
+    KB_CUDA_RET(cudaMemcpyAsync(ix->d_index, &D, sizeof(D), cudaMemcpyHostToDevice, ix->stream));
 
     // ---- finish: surface asynchronous failures and invalid ranks
-    KB_CUDA_OR_BAIL(cudaMemcpyAsync(ix->h_pinned, ix->d_flags, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ix->stream));
-    KB_CUDA_OR_BAIL(cudaStreamSynchronize(ix->stream));
-    KB_CUDA_OR_BAIL(cudaGetLastError());
+    KB_CUDA_RET(cudaMemcpyAsync(ix->h_pinned, ix->d_flags, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ix->stream));
+    KB_CUDA_RET(cudaStreamSynchronize(ix->stream));
+    KB_CUDA_RET(cudaGetLastError());
     if (reinterpret_cast<uint32_t *>(ix->h_pinned)[0] & 1u)
-        return bail(fail(KMER_B200_ERR_INVALID_RANK, "text contains a rank >= sigma"));
+        return fail(KMER_B200_ERR_INVALID_RANK, "text contains a rank >= sigma");
+    return KMER_B200_OK;
+}
+
+int create_impl(const uint8_t *ranks, bool ranks_on_device, uint64_t n, uint32_t sigma, const uint32_t *ks, uint32_t n_ks,
+                const kmer_b200_config *cfg_in, kmer_b200_index **out) {
+    if (!out) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "out is null");
+    *out = nullptr;
+    if (!ranks) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "ranks is null");
+    kmer_b200_index *ix = nullptr;
+    int s = new_index(n, sigma, ks, n_ks, cfg_in, &ix);
+    auto build = [&]() -> int {
+        DeviceGuard guard(ix->device);
+        // ---- text: H2D (if needed) + pack
+        const uint8_t *d_ranks = ranks;
+        uint8_t *d_ranks_owned = nullptr;
+        if (!ranks_on_device) {
+            KB_TRY(dev_alloc(ix, &d_ranks_owned, n, false));
+            KB_CUDA_RET(cudaMemcpyAsync(d_ranks_owned, ranks, n, cudaMemcpyHostToDevice, ix->stream));
+            d_ranks = d_ranks_owned;
+        }
+        ix->prof.begin(K_PACK_TEXT, (double)n + (double)n * ix->bits / 8.0);
+        kb::launch_pack_text(d_ranks, n, ix->bits, sigma, ix->text_words, ix->d_text, ix->d_flags, ix->stream);
+        ix->prof.end();
+        if (d_ranks_owned) dev_free(ix, d_ranks_owned);
+        // ---- elements
+        ix->elems.resize(n_ks);
+        for (uint32_t i = 0; i < n_ks; ++i) KB_TRY(build_element(ix, ks[i], ix->elems[i]));
+        return finalize_index(ix);
+    };
+    if (s == 0) s = build();
+    if (s != 0) {
+        if (ix) kmer_b200_destroy(ix);
+        return s;
+    }
     *out = ix;
     return KMER_B200_OK;
-#undef KB_OR_BAIL
-#undef KB_CUDA_OR_BAIL
+}
+
+// ---- serialization (the thesis assumes construct-once / load-later but ships no code) --------
+// File = header, packed text words, then per element: a record and the arrays keys, pos, dir. Little-endian,
+// everything 8-byte aligned. Auxiliary elements are not saved (they are rebuilt on demand).
+struct FileHeader {
+    char magic[8];  // "KMERB200"
+    uint32_t version, sigma, bits, n_ks;
+    uint64_t n, text_words, shard_begin, n_total;
+    uint32_t halo, mode;
+    uint32_t ks[kb::kMaxElements];
+};
+struct FileElement {
+    uint32_t k, shift, key_bits, sort_passes, key_bytes, pad;
+    uint64_t n_kmers, dir_entries, key_space;
+};
+constexpr uint32_t kFileVersion = 1;
+constexpr size_t kIoChunk = 64u << 20;
+
+int write_device_array(kmer_b200_index *ix, FILE *f, const void *d_ptr, uint64_t bytes, void *h_buf) {
+    for (uint64_t o = 0; o < bytes; o += kIoChunk) {
+        const size_t c = (size_t)std::min<uint64_t>(kIoChunk, bytes - o);
+        KB_CUDA_RET(cudaMemcpyAsync(h_buf, (const uint8_t *)d_ptr + o, c, cudaMemcpyDeviceToHost, ix->stream));
+        KB_CUDA_RET(cudaStreamSynchronize(ix->stream));
+        if (fwrite(h_buf, 1, c, f) != c) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "short write");
+    }
+    return 0;
+}
+
+int read_device_array(kmer_b200_index *ix, FILE *f, void *d_ptr, uint64_t bytes, void *h_buf) {
+    for (uint64_t o = 0; o < bytes; o += kIoChunk) {
+        const size_t c = (size_t)std::min<uint64_t>(kIoChunk, bytes - o);
+        if (fread(h_buf, 1, c, f) != c) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "truncated index file");
+        KB_CUDA_RET(cudaMemcpyAsync((uint8_t *)d_ptr + o, h_buf, c, cudaMemcpyHostToDevice, ix->stream));
+        KB_CUDA_RET(cudaStreamSynchronize(ix->stream));
+    }
+    return 0;
 }
 
 // Build auxiliary k' = m elements for the sub-k query lengths in `want` (bit m) that have none yet, memory
@@ -886,6 +936,113 @@ int kmer_b200_create(const uint8_t *ranks, uint64_t n, uint32_t sigma, const uin
 int kmer_b200_create_from_device(const uint8_t *d_ranks, uint64_t n, uint32_t sigma, const uint32_t *ks, uint32_t n_ks,
                                  const kmer_b200_config *cfg, kmer_b200_index **out) {
     return create_impl(d_ranks, true, n, sigma, ks, n_ks, cfg, out);
+}
+
+int kmer_b200_save(kmer_b200_index *ix, const char *path) {
+    if (!ix || !path) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
+    DeviceGuard guard(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    FILE *f = std::fopen(path, "wb");
+    if (!f) return fail(KMER_B200_ERR_INVALID_ARGUMENT, std::string("cannot open ") + path);
+    size_t cap = 0;
+    void *h_buf = pinned_get(kIoChunk, &cap);
+    int s = h_buf ? 0 : fail(KMER_B200_ERR_OUT_OF_MEMORY, "pinned host allocation failed");
+    FileHeader h{};
+    std::memcpy(h.magic, "KMERB200", 8);
+    h.version = kFileVersion;
+    h.sigma = ix->sigma;
+    h.bits = ix->bits;
+    h.n_ks = (uint32_t)ix->ks.size();
+    h.n = ix->n;
+    h.text_words = ix->text_words;
+    h.shard_begin = ix->cfg.shard_begin;
+    h.n_total = ix->cfg.n_total;
+    h.halo = ix->cfg.halo;
+    h.mode = ix->cfg.mode;
+    for (uint32_t i = 0; i < h.n_ks; ++i) h.ks[i] = ix->ks[i];
+    if (s == 0 && fwrite(&h, sizeof(h), 1, f) != 1) s = fail(KMER_B200_ERR_INVALID_ARGUMENT, "short write");
+    if (s == 0) s = write_device_array(ix, f, ix->d_text, ix->text_words * 8, h_buf);
+    for (uint32_t i = 0; s == 0 && i < h.n_ks; ++i) {
+        const HostElement &he = ix->elems[i];
+        FileElement fe{he.dev.k, he.dev.shift, he.key_bits, he.sort_passes, he.key_bytes, 0, he.dev.n_kmers,
+                       he.dev.dir_entries, he.dev.key_space};
+        if (fwrite(&fe, sizeof(fe), 1, f) != 1) s = fail(KMER_B200_ERR_INVALID_ARGUMENT, "short write");
+        if (s == 0) s = write_device_array(ix, f, he.d_keys, he.dev.n_kmers * he.key_bytes, h_buf);
+        if (s == 0) s = write_device_array(ix, f, he.d_pos, he.dev.n_kmers * 4, h_buf);
+        if (s == 0) s = write_device_array(ix, f, he.d_dir, he.dev.dir_entries * 4, h_buf);
+    }
+    pinned_put(h_buf, cap);
+    if (std::fclose(f) != 0 && s == 0) s = fail(KMER_B200_ERR_INVALID_ARGUMENT, "close failed");
+    return s;
+}
+
+int kmer_b200_load(const char *path, const kmer_b200_config *cfg_in, kmer_b200_index **out) {
+    if (!path || !out) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    FILE *f = std::fopen(path, "rb");
+    if (!f) return fail(KMER_B200_ERR_INVALID_ARGUMENT, std::string("cannot open ") + path);
+    FileHeader h{};
+    if (fread(&h, sizeof(h), 1, f) != 1 || std::memcmp(h.magic, "KMERB200", 8) != 0 || h.version != kFileVersion ||
+        h.n_ks == 0 || h.n_ks > (uint32_t)kb::kMaxElements) {
+        std::fclose(f);
+        return fail(KMER_B200_ERR_INVALID_ARGUMENT, "not a kmer_b200 index file (or an unknown version)");
+    }
+    kmer_b200_config cfg;
+    if (cfg_in)
+        cfg = *cfg_in;
+    else
+        kmer_b200_config_default(&cfg);
+    cfg.shard_begin = h.shard_begin;  // the geometry is a property of the stored index
+    cfg.n_total = h.n_total;
+    cfg.halo = h.halo;
+    if (!cfg_in) cfg.mode = h.mode;
+    kmer_b200_index *ix = nullptr;
+    int s = new_index(h.n, h.sigma, h.ks, h.n_ks, &cfg, &ix);
+    auto load = [&]() -> int {
+        DeviceGuard guard(ix->device);
+        if (ix->bits != h.bits || ix->text_words != h.text_words)
+            return fail(KMER_B200_ERR_INVALID_ARGUMENT, "index file does not match this build's text packing");
+        size_t cap = 0;
+        void *h_buf = pinned_get(kIoChunk, &cap);
+        if (!h_buf) return fail(KMER_B200_ERR_OUT_OF_MEMORY, "pinned host allocation failed");
+        int r = read_device_array(ix, f, ix->d_text, ix->text_words * 8, h_buf);
+        ix->elems.resize(h.n_ks);
+        for (uint32_t i = 0; r == 0 && i < h.n_ks; ++i) {
+            HostElement &he = ix->elems[i];
+            FileElement fe{};
+            if (fread(&fe, sizeof(fe), 1, f) != 1 || fe.k != h.ks[i] || (fe.key_bytes != 4 && fe.key_bytes != 8) ||
+                fe.n_kmers != h.n - fe.k + 1) {
+                r = fail(KMER_B200_ERR_INVALID_ARGUMENT, "corrupt element record");
+                break;
+            }
+            he.key_bits = fe.key_bits;
+            he.sort_passes = fe.sort_passes;
+            he.key_bytes = fe.key_bytes;
+            uint8_t *keys = nullptr;
+            if ((r = dev_alloc(ix, &keys, fe.n_kmers * fe.key_bytes, true)) != 0) break;
+            he.d_keys = keys;
+            if ((r = dev_alloc(ix, &he.d_pos, fe.n_kmers, true)) != 0) break;
+            if ((r = dev_alloc(ix, &he.d_dir, fe.dir_entries, true)) != 0) break;
+            if ((r = read_device_array(ix, f, he.d_keys, fe.n_kmers * fe.key_bytes, h_buf)) != 0) break;
+            if ((r = read_device_array(ix, f, he.d_pos, fe.n_kmers * 4, h_buf)) != 0) break;
+            if ((r = read_device_array(ix, f, he.d_dir, fe.dir_entries * 4, h_buf)) != 0) break;
+            he.dev = kb::Element{fe.k, fe.shift, fe.n_kmers, fe.dir_entries, fe.key_space, he.d_dir, he.d_keys, he.d_pos,
+                                 fe.key_bytes, 0};
+            he.bytes = fe.n_kmers * (4 + fe.key_bytes) + fe.dir_entries * 4;
+            ix->max_avg_bucket = std::max(ix->max_avg_bucket,
+                                          (double)fe.n_kmers / (double)std::min<uint64_t>(fe.key_space, fe.n_kmers));
+        }
+        pinned_put(h_buf, cap);
+        return r ? r : finalize_index(ix);
+    };
+    if (s == 0) s = load();
+    std::fclose(f);
+    if (s != 0) {
+        if (ix) kmer_b200_destroy(ix);
+        return s;
+    }
+    *out = ix;
+    return KMER_B200_OK;
 }
 
 void kmer_b200_destroy(kmer_b200_index *ix) {

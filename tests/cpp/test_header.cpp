@@ -110,6 +110,18 @@ int main()
         auto r = idx.search(q).to_vector();
         REQUIRE(!r.empty() && r.front() <= 123);
     }
+    // save / load round trip
+    {
+        const char* path = "/tmp/kmer_index_hpp_test.kmerb200";
+        multi.save(path);
+        auto loaded = kmer::kmer_index<alphabet_t, uint32_t, 10, 11, 12>::load(path);
+        std::vector<alphabet_t> q(text.begin() + 4242, text.begin() + 4242 + 17);
+        REQUIRE(loaded.search(q).to_vector() == multi.search(q).to_vector());
+        bool threw = false;
+        try { (void)kmer::kmer_index<alphabet_t, uint32_t, 10>::load(path); } catch (std::invalid_argument const&) { threw = true; }
+        REQUIRE(threw);
+        std::remove(path);
+    }
     std::printf("kmer_index.hpp: all checks passed\n");
     return 0;
 }

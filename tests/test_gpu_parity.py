@@ -235,3 +235,28 @@ def test_heavy_buckets_take_the_warp_path(kb, oracle_mod, sigma, ks):
         assert int((want[0][1:] - want[0][:-1]).max()) > 2048
     with kb.KmerIndex(text, sigma, ks, mode=kb.MODE_CORRECT) as ix:
         assert_results_equal(ix.search_batch(q, off).as_tuple(), oracle_mod.Oracle.truth(text, q, off), label="heavy correct")
+
+
+@pytest.mark.parametrize("sigma,ks", [(4, [12]), (4, [5, 7, 9, 11, 13]), (15, [10]), (27, [5])])
+def test_save_load_round_trip(kb, oracle_mod, tmp_path, sigma, ks):
+    """Construct once, load later: the loaded index answers exactly like the built one (and like the oracle)."""
+    from kmer_index_b200 import synth
+    text = synth.random_text(120_000, sigma, 3)
+    q, off = synth.stress_queries(text, 3000, 1, 45, sigma, 4)
+    path = str(tmp_path / "index.kmerb200")
+    with kb.KmerIndex(text, sigma, ks) as ix:
+        built = ix.search_batch(q, off).as_tuple()
+        arrays = [ix.element_arrays(e) for e in range(len(ks))]
+        ix.save(path)
+    with kb.KmerIndex.load(path) as ld:
+        assert ld.ks == list(ks) and ld.n == text.size
+        assert_results_equal(ld.search_batch(q, off).as_tuple(), built, label="loaded vs built")
+        for e in range(len(ks)):
+            h, p = ld.element_arrays(e)
+            assert np.array_equal(h, arrays[e][0]) and np.array_equal(p, arrays[e][1])
+    with oracle_mod.Oracle(text, sigma, ks) as o:
+        assert_results_equal(built, o.search(q, off), label="built vs oracle")
+    with pytest.raises(kb.KmerB200Error):
+        bad = tmp_path / "bad.bin"
+        bad.write_bytes(b"not an index" * 100)
+        kb.KmerIndex.load(str(bad))
