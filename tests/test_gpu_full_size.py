@@ -1,0 +1,218 @@
+"""GPU parity at the BASELINE.json sizes.
+
+Configs 1, 2, 4 (and config 3 on a query subsample / by counts): bit-exact against the C restatement oracle on
+the full-size text. Config 5 (3 Gbp, 1e8 queries) is beyond what a CPU index can hold, so it is checked
+through size-independent properties: ascending positions, every reported position verified against the text,
+planted queries found, count-only == materialised, determinism (checksum), and an emulated 2-shard run giving
+the same hit set.
+"""
+import numpy as np
+import pytest
+
+from conftest import assert_results_equal
+
+pytestmark = pytest.mark.gpu
+
+TEXT_SEED, QUERY_SEED = 205, 1239
+
+
+@pytest.fixture(scope="module")
+def kb():
+    import kmer_index_b200
+    return kmer_index_b200
+
+
+def _free_host_gb():
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable"):
+                return int(ln.split()[1]) / 1e6
+    except OSError:
+        pass
+    return 0.0
+
+
+FULL = [
+    # label, sigma, ks, n, Q, m_lo, m_hi
+    ("config1", 4, [10], 1_000_000, 10_000, 10, 10),
+    ("config2", 4, [12], 100_000_000, 1_000_000, 13, 100),
+    ("config4_dna15", 15, [8], 50_000_000, 1_000_000, 8, 8),
+    ("config4_aa27", 27, [5], 50_000_000, 1_000_000, 5, 5),
+]
+
+
+@pytest.mark.parametrize("label,sigma,ks,n,Q,m_lo,m_hi", FULL)
+def test_full_size_bit_exact_vs_oracle(kb, oracle_mod, label, sigma, ks, n, Q, m_lo, m_hi):
+    from kmer_index_b200 import synth
+    if _free_host_gb() < 16:
+        pytest.skip("needs ~16 GB of host memory for the CPU oracle at this size")
+    text = synth.random_text(n, sigma, TEXT_SEED)
+    # half BASELINE-style random queries, half planted windows (random queries almost never hit for long m)
+    q1, off1 = synth.random_queries(Q // 2, m_lo, m_hi, sigma, QUERY_SEED)
+    q2, off2 = synth.stress_queries(text, Q - Q // 2, m_lo, m_hi, sigma, QUERY_SEED + 1) if n <= 2_000_000 else \
+        _planted(text, Q - Q // 2, m_lo, m_hi, QUERY_SEED + 1)
+    q = np.concatenate([q1, q2])
+    off = np.concatenate([off1, off2[1:] + off1[-1]])
+    with kb.KmerIndex(text, sigma, ks) as ix:
+        got = ix.search_batch(q, off).as_tuple()
+    with oracle_mod.Oracle(text, sigma, ks) as o:
+        want = o.search(q, off)
+    assert want[1].size > 0
+    assert_results_equal(got, want, label=label)
+
+
+def _planted(text, Q, m_lo, m_hi, seed):
+    """Q windows of the text (vectorised; stress_queries loops in Python and is too slow for 5e5 queries)."""
+    from kmer_index_b200 import synth
+    n = text.size
+    lens = synth.random_lengths(Q, m_lo, m_hi, seed)
+    off = synth.offsets_from_lengths(lens)
+    starts = synth.uniform_below(seed ^ 0xBEEF, 0, Q, n - m_hi).astype(np.int64)
+    starts[::97] = n - lens[::97].astype(np.int64)              # some windows end exactly at the end of the text
+    idx = np.repeat(starts - off[:-1].astype(np.int64), lens.astype(np.int64)) + np.arange(int(off[-1]), dtype=np.int64)
+    return text[idx], off
+
+
+def test_config3_full_text_counts_and_subsample(kb, oracle_mod):
+    """multi_kmer_index<dna4,{5,7,9,11,13}> over 100 Mbp: all 1e6 queries by per-query hit COUNT against the oracle
+    (1.4e10 positions do not fit a CPU result), and a subsample bit for bit."""
+    from kmer_index_b200 import synth
+    if _free_host_gb() < 24:
+        pytest.skip("needs ~24 GB of host memory for the CPU oracle at this size")
+    sigma, ks, n = 4, [5, 7, 9, 11, 13], 100_000_000
+    text = synth.random_text(n, sigma, TEXT_SEED)
+    q, off = synth.random_queries(200_000, 4, 40, sigma, QUERY_SEED)
+    qs, offs = synth.random_queries(3_000, 6, 40, sigma, QUERY_SEED + 2)       # materialised on both sides
+    qp, offp = _planted(text, 20_000, 6, 40, QUERY_SEED + 3)
+    with kb.KmerIndex(text, sigma, ks) as ix, oracle_mod.Oracle(text, sigma, ks) as o:
+        got = ix.search_batch(q, off)
+        w_off, _, w_status = o.search(q, off, keep_positions=False)
+        assert np.array_equal(got.status, w_status)
+        assert np.array_equal(got.offsets, w_off)
+        pos = got.positions
+        # ascending inside every query (sub-k results come from auxiliary elements or the sort kernel)
+        d = np.diff(pos.astype(np.int64))
+        boundaries = got.offsets[1:-1].astype(np.int64) - 1
+        d[boundaries[(boundaries >= 0) & (boundaries < d.size)]] = 1
+        assert (d > 0).all()
+        del got, pos, d
+        assert_results_equal(ix.search_batch(qs, offs).as_tuple(), o.search(qs, offs), label="config3 subsample")
+        assert_results_equal(ix.search_batch(qp, offp).as_tuple(), o.search(qp, offp), label="config3 planted")
+
+
+def test_config5_full_size_properties(kb):
+    """kmer_index<dna4,16> over 3 Gbp, 1e8 queries of length 16-64, all on the device."""
+    import torch
+
+    from kmer_index_b200 import _capi, sharded
+    free, _ = torch.cuda.mem_get_info()
+    if free < 100e9:
+        pytest.skip("needs ~100 GB of device memory")
+    dev = torch.device("cuda", 0)
+    L = _capi.lib()
+    n, Q, m_lo, m_hi, k = 3_000_000_000, 100_000_000, 16, 64, 16
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    sptr = stream.cuda_stream
+    text = torch.empty(n, dtype=torch.uint8, device=dev)
+    _capi.check(L.kmer_b200_synth_ranks_device(text.data_ptr(), n, 0, 4, TEXT_SEED, sptr))
+    g = torch.Generator(device=dev)
+    g.manual_seed(QUERY_SEED)
+    lens = torch.randint(m_lo, m_hi + 1, (Q,), generator=g, device=dev, dtype=torch.int64)
+    off = torch.zeros(Q + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(lens, 0, out=off[1:])
+    n_sym = int(off[-1].item())
+    q = torch.empty(n_sym, dtype=torch.uint8, device=dev)
+    _capi.check(L.kmer_b200_synth_ranks_device(q.data_ptr(), n_sym, 0, 4, QUERY_SEED ^ 0xC0FFEE, sptr))
+    # plant every 50th query: a window of the text (so long queries have true occurrences)
+    planted = torch.arange(0, Q, 50, device=dev)
+    starts = torch.randint(0, n - m_hi, (planted.numel(),), generator=g, device=dev, dtype=torch.int64)
+    p_len = lens[planted]
+    seg = torch.repeat_interleave(torch.arange(planted.numel(), device=dev), p_len)
+    within = torch.arange(int(p_len.sum().item()), device=dev) - torch.repeat_interleave(torch.cumsum(p_len, 0) - p_len, p_len)
+    q[off[planted][seg] + within] = text[starts[seg] + within]
+    torch.cuda.synchronize()
+
+    ix = kb.KmerIndex(None, 4, [k], stream=sptr, text_device_ptr=text.data_ptr(), n=n)
+    try:
+        res = ix.search_batch_device(q.data_ptr(), off.data_ptr(), Q, m_hi)
+        r_off = torch.as_tensor(res.offsets(), device=dev)
+        r_pos = torch.as_tensor(res.positions(), device=dev).view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+        r_st = torch.as_tensor(res.status(), device=dev)
+        torch.cuda.synchronize()
+        hits = int(r_off[-1].item())
+        assert hits == r_pos.numel() and hits > planted.numel() // 4
+        counts = r_off[1:] - r_off[:-1]
+        # (1) status: THROW exactly for rest in 1..4 among queries that are OK-or-throw; no hits on non-OK
+        rest = lens % k
+        assert int(((r_st != 0) & (counts != 0)).sum().item()) == 0
+        assert int(((r_st == 1) & ~((rest >= 1) & (rest <= 4))).sum().item()) == 0
+        # (2) ascending inside every query
+        d = r_pos[1:] - r_pos[:-1]
+        inner = torch.ones(hits - 1, dtype=torch.bool, device=dev)
+        ends = r_off[1:-1] - 1
+        ends = ends[(ends >= 0) & (ends < hits - 1)]
+        inner[ends] = False
+        assert bool((d[inner] > 0).all().item())
+        # (3) every reported position is a true occurrence of a prefix of the query it belongs to:
+        #     verify the first 16 symbols and the last 16 symbols of the claimed match against the text
+        qid = torch.repeat_interleave(torch.arange(Q, device=dev), counts)
+        for shift_from_end in (False, True):
+            for j in range(0, 16, 5):
+                o = (lens[qid] - 1 - j) if shift_from_end else torch.full_like(qid, j)
+                # lengths 53..63 run the reference's defective plan (only the parts are constrained)
+                ok_len = (lens[qid] <= 52) | (lens[qid] == 64)
+                a = text[r_pos + o]
+                b = q[off[qid] + o]
+                assert bool((a[ok_len] == b[ok_len]).all().item())
+        # (4) planted queries whose plan is correct in the reference and does not throw are found at their origin
+        pl_ok = (r_st[planted] == 0) & ((p_len <= 52) | (p_len == 64))
+        lo = r_off[planted]
+        hi = r_off[planted + 1]
+        found = torch.zeros(planted.numel(), dtype=torch.bool, device=dev)
+        width = int((hi - lo).max().item())
+        for j in range(width):
+            idx = torch.clamp(lo + j, max=hits - 1)
+            found |= (lo + j < hi) & (r_pos[idx] == starts)
+        assert bool(found[pl_ok].all().item())
+        # (5) count-only pass agrees; (6) deterministic across runs
+        checksum = int((r_pos * (qid + 1)).sum().item())
+        res2 = ix.count_batch_device(q.data_ptr(), off.data_ptr(), Q, m_hi)
+        assert torch.equal(torch.as_tensor(res2.offsets(), device=dev), r_off)
+        res2.free()
+        res3 = ix.search_batch_device(q.data_ptr(), off.data_ptr(), Q, m_hi)
+        p3 = torch.as_tensor(res3.positions(), device=dev).view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+        torch.cuda.synchronize()
+        assert int((p3 * (qid + 1)).sum().item()) == checksum
+        res3.free()
+        st_single, off_single = r_st.clone(), r_off.clone()
+        res.free()
+    finally:
+        ix.close()
+    del r_pos, qid, d, inner
+
+    # (7) two position-range shards on the same GPU (built one after the other) give the same offsets and status
+    per_shard = []
+    shards = [sharded.shard_range(n, 2, r, halo=m_hi - 1) for r in range(2)]
+    masks, pend, idxs = [], [], []
+    try:
+        for s in shards:
+            sx = kb.KmerIndex(None, 4, [k], stream=sptr, text_device_ptr=text.data_ptr() + s.begin, n=s.length,
+                              shard_begin=s.begin, n_total=n, halo=s.halo)
+            idxs.append(sx)
+            m = torch.zeros(Q, dtype=torch.int32, device=dev)
+            pend.append(sx.search_sharded_begin(q.data_ptr(), off.data_ptr(), Q, m_hi, m.data_ptr()))
+            masks.append(m)
+        torch.cuda.synchronize()
+        present = (masks[0] + masks[1]).to(torch.int32)
+        total = torch.zeros(Q, dtype=torch.int64, device=dev)
+        for sx, p in zip(idxs, pend):
+            r = sx.search_sharded_finish(p, present.data_ptr(), Q)
+            o = torch.as_tensor(r.offsets(), device=dev)
+            total += o[1:] - o[:-1]
+            assert torch.equal(torch.as_tensor(r.status(), device=dev), st_single)
+            r.free()
+        assert torch.equal(total, off_single[1:] - off_single[:-1])
+    finally:
+        for sx in idxs:
+            sx.close()
