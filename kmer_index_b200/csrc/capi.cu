@@ -190,6 +190,7 @@ struct kmer_b200_result {
     uint32_t *positions = nullptr;
     uint8_t *status = nullptr;
     size_t cap_offsets = 0, cap_positions = 0, cap_status = 0;  // host buffers: byte capacities
+    bool positions_pageable = false;  // very large position lists live in plain malloc memory
 };
 
 namespace {
@@ -342,7 +343,12 @@ int build_element(kmer_b200_index *ix, uint32_t k, HostElement &he, bool auxilia
     const uint64_t n_kmers = ix->n - k + 1;
     const uint64_t key_space = fast_pow(ix->sigma, (uint8_t)k);
     he.key_bits = std::max<uint32_t>(1, bit_length(key_space - 1));
-    he.sort_passes = (he.key_bits + kRadixBitsMax - 1) / kRadixBitsMax;
+    uint32_t digit_bits = kRadixBitsMax;
+    if (const char *env = std::getenv("KMER_B200_DIGIT_BITS")) {  // tuning experiment: narrower digits, more passes
+        const int b = std::atoi(env);
+        if (b >= 4 && b <= kRadixBitsMax) digit_bits = (uint32_t)b;
+    }
+    he.sort_passes = (he.key_bits + digit_bits - 1) / digit_bits;
     const uint32_t bits_per_pass = (he.key_bits + he.sort_passes - 1) / he.sort_passes;
     const uint32_t mask = (1u << bits_per_pass) - 1;
     const uint32_t n_tiles = (uint32_t)((n_kmers + sort_tile_size() - 1) / sort_tile_size());
@@ -1198,7 +1204,15 @@ int kmer_b200_search_batch(kmer_b200_index *ix, const uint8_t *q_ranks, const ui
     res->n_positions = dres->n_positions;
     res->offsets = (uint64_t *)pinned_get((Q + 1) * sizeof(uint64_t), &res->cap_offsets);
     res->status = (uint8_t *)pinned_get(Q, &res->cap_status);
-    res->positions = (uint32_t *)pinned_get(res->n_positions * sizeof(uint32_t), &res->cap_positions);
+    // pinning tens of gigabytes is slow and can starve the host: beyond 8 GiB the positions go to pageable memory
+    const size_t pos_bytes = res->n_positions * sizeof(uint32_t);
+    if (pos_bytes > (8ull << 30)) {
+        res->positions = (uint32_t *)std::malloc(pos_bytes);
+        res->positions_pageable = true;
+        res->cap_positions = pos_bytes;
+    } else {
+        res->positions = (uint32_t *)pinned_get(pos_bytes, &res->cap_positions);
+    }
     if (!res->offsets || !res->status || !res->positions) {
         kmer_b200_result_free(dres);
         kmer_b200_result_free(res);
@@ -1236,7 +1250,10 @@ void kmer_b200_result_free(kmer_b200_result *r) {
         dev_free(ix, r->status);
     } else {
         pinned_put(r->offsets, r->cap_offsets);
-        pinned_put(r->positions, r->cap_positions);
+        if (r->positions_pageable)
+            std::free(r->positions);
+        else
+            pinned_put(r->positions, r->cap_positions);
         pinned_put(r->status, r->cap_status);
     }
     delete r;
