@@ -71,7 +71,7 @@ def cpu_reference_sample(wl, steps: int, warmup: int):
     sigma, ks, (m_lo, m_hi) = wl["sigma"], wl["ks"], wl["m"]
     cores = os.cpu_count() or 1
     n = min(wl["n"], 5_000_000)
-    Q = min(wl["Q"], 20_000 if m_hi > max(ks) else 1_000_000)
+    Q = min(wl["Q"], 200_000 if m_hi > max(ks) else 1_000_000)   # seconds of reference search per step
     text = synth.random_text(n, sigma, TEXT_SEED)
     q, off = synth.random_queries(Q, m_lo, m_hi, sigma, QUERY_SEED)
     use_ref = bindings.have_reference() and bindings.Reference.supported(sigma, ks)
