@@ -40,7 +40,7 @@ WORKLOADS = {
     "c4b": dict(name="kmer_index<aa27,k=5> 50 M symbols, 1e6 queries len 5", sigma=27, ks=[5], n=50_000_000, Q=1_000_000,
                 m=(5, 5)),
     "c5": dict(name="kmer_index<dna4,k=16> 3 Gbp, 1e8 queries len 16-64", sigma=4, ks=[16], n=3_000_000_000,
-               Q=100_000_000, m=(16, 64)),
+               Q=100_000_000, m=(16, 64), ref_Q=200_000),
 }
 TEXT_SEED, QUERY_SEED = 205, 1239
 
@@ -71,7 +71,8 @@ def cpu_reference_sample(wl, steps: int, warmup: int):
     sigma, ks, (m_lo, m_hi) = wl["sigma"], wl["ks"], wl["m"]
     cores = os.cpu_count() or 1
     n = min(wl["n"], 5_000_000)
-    Q = min(wl["Q"], 200_000 if m_hi > max(ks) else 1_000_000)   # seconds of reference search per step
+    # seconds of reference search per step: its rest handling probes up to sigma^(k-rest) buckets per query
+    Q = min(wl["Q"], wl.get("ref_Q", 20_000 if m_hi > max(ks) else 1_000_000))
     text = synth.random_text(n, sigma, TEXT_SEED)
     q, off = synth.random_queries(Q, m_lo, m_hi, sigma, QUERY_SEED)
     use_ref = bindings.have_reference() and bindings.Reference.supported(sigma, ks)
