@@ -820,7 +820,8 @@ int search_begin(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off,
 
     cudaMemsetAsync(ix->d_flags, 0, 4 * sizeof(uint32_t), st);
     ix->prof.begin(K_SEARCH_COUNT, 0);
-    launch_search(a, d_present4 ? kPassCountDeferred : (a.gather_count ? kPassCountAccount : kPassCount), st);
+    launch_search(a, d_present4 ? (a.gather_count ? kPassCountDeferredAccount : kPassCountDeferred)
+                                : (a.gather_count ? kPassCountAccount : kPassCount), st);
     ix->prof.end();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return bail(fail(KMER_B200_ERR_CUDA, std::string("search (count pass): ") + cudaGetErrorString(e)));

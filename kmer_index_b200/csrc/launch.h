@@ -31,7 +31,8 @@ enum SearchPass : int {
     kPassWrite = 1,
     kPassPresence = 2,
     kPassCountAccount = 3,   // count + gather accounting
-    kPassCountDeferred = 4   // sharded: count + per-part presence flags, whole-text rule applied afterwards
+    kPassCountDeferred = 4,  // sharded: count + per-part presence flags, whole-text rule applied afterwards
+    kPassCountDeferredAccount = 5
 };
 
 struct SearchArgs {

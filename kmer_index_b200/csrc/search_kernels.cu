@@ -138,8 +138,9 @@ constexpr uint32_t kHeavyCandidates = 2048;
 // HEAVY = true: the second launch (G = 32) over the heavy list; never hands a query off again.
 template <int PASS_, int G, bool HEAVY>
 __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t q, uint64_t *smem_q) {
-    constexpr bool kAccount = PASS_ == kPassCountAccount;  // count pass that also sums the gathered sectors
-    constexpr bool kDefer = PASS_ == kPassCountDeferred;   // count pass that leaves the whole-text rule for later
+    // count pass variants: + sum of the gathered sectors; + whole-text rule left for the epilogue (sharded)
+    constexpr bool kAccount = PASS_ == kPassCountAccount || PASS_ == kPassCountDeferredAccount;
+    constexpr bool kDefer = PASS_ == kPassCountDeferred || PASS_ == kPassCountDeferredAccount;
     constexpr int PASS = (kAccount || kDefer) ? (int)kPassCount : PASS_;
     const int lane = threadIdx.x & 31;
     const int gl = threadIdx.x & (G - 1);          // lane inside the group
@@ -414,6 +415,10 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
             a.defer[q] = rule ? (uint8_t)(0x40u | (throw_after ? 0x80u : 0u) | (nparts <= 8 ? nparts : 63u)) : 0;
         }
         if (rule && throw_after) {  // either THROW or empty: no hits in both cases
+            if (kAccount) {
+                for (int o = G >> 1; o > 0; o >>= 1) n_gather += __shfl_xor_sync(gmask, n_gather, o, G);
+                if (gl == 0) atomicAdd(a.gather_count, (unsigned long long)n_gather);
+            }
             if (gl == 0) {
                 a.counts[q] = 0;
                 a.status[q] = KMER_B200_QUERY_OK;
@@ -697,30 +702,35 @@ void launch_search(const SearchArgs &args, SearchPass pass, cudaStream_t stream)
         if (pass == kPassCount) launch_search_pg<kPassCount, 1>(args, stream);
         if (pass == kPassCountAccount) launch_search_pg<kPassCountAccount, 1>(args, stream);
         if (pass == kPassCountDeferred) launch_search_pg<kPassCountDeferred, 1>(args, stream);
+        if (pass == kPassCountDeferredAccount) launch_search_pg<kPassCountDeferredAccount, 1>(args, stream);
         if (pass == kPassWrite) launch_search_pg<kPassWrite, 1>(args, stream);
         if (pass == kPassPresence) launch_search_pg<kPassPresence, 1>(args, stream);
     } else if (args.group == 2) {
         if (pass == kPassCount) launch_search_pg<kPassCount, 2>(args, stream);
         if (pass == kPassCountAccount) launch_search_pg<kPassCountAccount, 2>(args, stream);
         if (pass == kPassCountDeferred) launch_search_pg<kPassCountDeferred, 2>(args, stream);
+        if (pass == kPassCountDeferredAccount) launch_search_pg<kPassCountDeferredAccount, 2>(args, stream);
         if (pass == kPassWrite) launch_search_pg<kPassWrite, 2>(args, stream);
         if (pass == kPassPresence) launch_search_pg<kPassPresence, 2>(args, stream);
     } else if (args.group == 4) {
         if (pass == kPassCount) launch_search_pg<kPassCount, 4>(args, stream);
         if (pass == kPassCountAccount) launch_search_pg<kPassCountAccount, 4>(args, stream);
         if (pass == kPassCountDeferred) launch_search_pg<kPassCountDeferred, 4>(args, stream);
+        if (pass == kPassCountDeferredAccount) launch_search_pg<kPassCountDeferredAccount, 4>(args, stream);
         if (pass == kPassWrite) launch_search_pg<kPassWrite, 4>(args, stream);
         if (pass == kPassPresence) launch_search_pg<kPassPresence, 4>(args, stream);
     } else if (args.group == 8) {
         if (pass == kPassCount) launch_search_pg<kPassCount, 8>(args, stream);
         if (pass == kPassCountAccount) launch_search_pg<kPassCountAccount, 8>(args, stream);
         if (pass == kPassCountDeferred) launch_search_pg<kPassCountDeferred, 8>(args, stream);
+        if (pass == kPassCountDeferredAccount) launch_search_pg<kPassCountDeferredAccount, 8>(args, stream);
         if (pass == kPassWrite) launch_search_pg<kPassWrite, 8>(args, stream);
         if (pass == kPassPresence) launch_search_pg<kPassPresence, 8>(args, stream);
     } else {
         if (pass == kPassCount) launch_search_pg<kPassCount, 32>(args, stream);
         if (pass == kPassCountAccount) launch_search_pg<kPassCountAccount, 32>(args, stream);
         if (pass == kPassCountDeferred) launch_search_pg<kPassCountDeferred, 32>(args, stream);
+        if (pass == kPassCountDeferredAccount) launch_search_pg<kPassCountDeferredAccount, 32>(args, stream);
         if (pass == kPassWrite) launch_search_pg<kPassWrite, 32>(args, stream);
         if (pass == kPassPresence) launch_search_pg<kPassPresence, 32>(args, stream);
     }
