@@ -90,6 +90,14 @@ int kmer_b200_create(const uint8_t *ranks, uint64_t n, uint32_t sigma, const uin
 int kmer_b200_create_from_device(const uint8_t *d_ranks, uint64_t n, uint32_t sigma, const uint32_t *ks,
                                  uint32_t n_ks, const kmer_b200_config *cfg, kmer_b200_index **out);
 
+/* Character input (the step before the path: real texts are characters, e.g. FASTA records). lut256 maps every
+   byte value to its rank; bytes that are not in the alphabet must map to a value >= sigma and make the call
+   fail with KMER_B200_ERR_INVALID_RANK. The translation runs on the device, fused in front of the packing. */
+int kmer_b200_create_from_text(const char *text, uint64_t n, const uint8_t *lut256, uint32_t sigma, const uint32_t *ks,
+                               uint32_t n_ks, const kmer_b200_config *cfg, kmer_b200_index **out);
+int kmer_b200_search_batch_text(kmer_b200_index *index, const char *q_chars, const uint64_t *q_offsets,
+                                uint64_t n_queries, const uint8_t *lut256, uint32_t mode, kmer_b200_result **out);
+
 void kmer_b200_destroy(kmer_b200_index *index);
 
 /* ---- serialization: construct once, load later (the thesis assumes it, thesis/content/02_implementation.tex:44-46,

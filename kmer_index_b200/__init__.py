@@ -17,10 +17,24 @@ from ._capi import (MODE_CORRECT, MODE_DEFAULT, MODE_REFERENCE_EXACT, QUERY_OK, 
                     QUERY_TOO_LONG_FOR_SHARD, QUERY_UNDEFINED, KmerB200Error)
 
 __all__ = ["KmerIndex", "make_kmer_index", "BatchResult", "fast_pow", "kmer_hash", "choose_best_k", "scheme_for_ks",
+           "char_lut", "ALPHABET_CHARS",
            "MODE_REFERENCE_EXACT", "MODE_CORRECT", "KmerB200Error", "ALPHABETS"]
 
 # alphabet sizes of the seqan3 alphabets the reference is used with
 ALPHABETS = {"dna4": 4, "dna5": 5, "dna15": 15, "aa27": 27}
+# their characters in rank order (seqan3's rank order is the alphabetical order of the character set)
+ALPHABET_CHARS = {"dna4": "ACGT", "dna5": "ACGNT", "dna15": "ABCDGHKMNRSTVWY", "aa27": "ABCDEFGHIJKLMNOPQRSTUVWXYZ*"}
+
+
+def char_lut(alphabet: str) -> np.ndarray:
+    """256-entry character -> rank table for kmer_b200_create_from_text / search_batch_text; characters outside
+    the alphabet map to 255 (rejected as an invalid rank). Case-insensitive."""
+    chars = ALPHABET_CHARS.get(alphabet, alphabet)
+    lut = np.full(256, 255, dtype=np.uint8)
+    for r, c in enumerate(chars):
+        lut[ord(c.upper())] = r
+        lut[ord(c.lower())] = r
+    return lut
 
 
 def fast_pow(base: int, exp: int) -> int:
@@ -141,7 +155,7 @@ class KmerIndex:
     def __init__(self, text, sigma: int, ks: Sequence[int], *, mode: int = MODE_REFERENCE_EXACT, device: int = -1,
                  stream: int | None = None, profile: bool = False, shard_begin: int = 0, n_total: int = 0,
                  halo: int = 0, directory_bits: int = 0, text_device_ptr: int | None = None, n: int | None = None,
-                 aux_elements: bool = True):
+                 aux_elements: bool = True, lut: np.ndarray | None = None):
         L = _capi.lib()
         self._L = L
         self._h = C.c_void_p()
@@ -164,6 +178,15 @@ class KmerIndex:
             _capi.check(L.kmer_b200_create_from_device(C.c_void_p(text_device_ptr), self.n, self.sigma,
                                                        ks_a.ctypes.data_as(_capi.u32p), ks_a.size, C.byref(cfg),
                                                        C.byref(self._h)))
+        elif lut is not None:    # `text` is characters (bytes / str / uint8 array of character codes)
+            raw = text.encode() if isinstance(text, str) else bytes(text) if isinstance(text, (bytes, bytearray)) else None
+            t = np.frombuffer(raw, dtype=np.uint8) if raw is not None else np.ascontiguousarray(np.asarray(text, dtype=np.uint8))
+            lut = np.ascontiguousarray(np.asarray(lut, dtype=np.uint8))
+            self.n = int(t.size)
+            self._lut = lut
+            _capi.check(L.kmer_b200_create_from_text(t.ctypes.data_as(C.c_char_p), t.size, lut.ctypes.data_as(_capi.u8p),
+                                                     self.sigma, ks_a.ctypes.data_as(_capi.u32p), ks_a.size,
+                                                     C.byref(cfg), C.byref(self._h)))
         else:
             t = np.ascontiguousarray(np.asarray(text, dtype=np.uint8))
             self.n = int(t.size)
@@ -235,6 +258,27 @@ class KmerIndex:
         out = BatchResult(offsets.copy(), positions.copy(), status.copy())
         L.kmer_b200_result_free(r)
         return out
+
+    def search_batch_text(self, queries, lut: np.ndarray | None = None, mode: int = MODE_DEFAULT) -> BatchResult:
+        """Batch of character queries (list of str/bytes); translated to ranks on the device."""
+        L = self._L
+        lut = np.ascontiguousarray(np.asarray(lut if lut is not None else self._lut, dtype=np.uint8))
+        raw = [x.encode() if isinstance(x, str) else bytes(x) for x in queries]
+        off = np.zeros(len(raw) + 1, dtype=np.uint64)
+        np.cumsum([len(x) for x in raw], out=off[1:])
+        q = np.frombuffer(b"".join(raw), dtype=np.uint8)
+        r = C.c_void_p()
+        _capi.check(L.kmer_b200_search_batch_text(self._h, q.ctypes.data_as(C.c_char_p), off.ctypes.data, len(raw),
+                                                  lut.ctypes.data_as(_capi.u8p), mode, C.byref(r)))
+        Q = len(raw)
+        total = L.kmer_b200_result_n_positions(r)
+        offsets = np.ctypeslib.as_array(C.cast(L.kmer_b200_result_offsets(r), _capi.u64p), shape=(Q + 1,)).copy()
+        status = (np.ctypeslib.as_array(C.cast(L.kmer_b200_result_status(r), _capi.u8p), shape=(Q,)).copy()
+                  if Q else np.zeros(0, dtype=np.uint8))
+        positions = (np.ctypeslib.as_array(C.cast(L.kmer_b200_result_positions(r), _capi.u32p), shape=(total,)).copy()
+                     if total else np.zeros(0, dtype=np.uint32))
+        L.kmer_b200_result_free(r)
+        return BatchResult(offsets, positions, status)
 
     def search(self, query, mode: int = MODE_DEFAULT) -> np.ndarray:
         """kmer_index::search(query).to_vector() for one query; raises ValueError where the reference throws

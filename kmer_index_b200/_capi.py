@@ -48,6 +48,10 @@ SYMBOLS = {
                                    C.POINTER(C.c_void_p)]),
     "kmer_b200_create_from_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, u32p, C.c_uint32,
                                                C.POINTER(Config), C.POINTER(C.c_void_p)]),
+    "kmer_b200_create_from_text": (C.c_int, [C.c_char_p, C.c_uint64, u8p, C.c_uint32, u32p, C.c_uint32,
+                                             C.POINTER(Config), C.POINTER(C.c_void_p)]),
+    "kmer_b200_search_batch_text": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_uint64, u8p, C.c_uint32,
+                                              C.POINTER(C.c_void_p)]),
     "kmer_b200_destroy": (None, [C.c_void_p]),
     "kmer_b200_save": (C.c_int, [C.c_void_p, C.c_char_p]),
     "kmer_b200_load": (C.c_int, [C.c_char_p, C.POINTER(Config), C.POINTER(C.c_void_p)]),

@@ -608,8 +608,37 @@ int finalize_index(kmer_b200_index *ix) {
     return KMER_B200_OK;
 }
 
+// characters -> ranks through a 256-entry table, in place (real inputs are characters)
+__global__ void __launch_bounds__(256) translate_kernel(uint8_t *__restrict__ data, uint64_t n, const uint8_t *__restrict__ lut) {
+    __shared__ uint8_t s_lut[256];
+    s_lut[threadIdx.x] = lut[threadIdx.x];
+    __syncthreads();
+    const uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (i0 + 16 <= n) {
+        uint4 v = *reinterpret_cast<const uint4 *>(data + i0);
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            w[j] = (uint32_t)s_lut[w[j] & 0xFF] | ((uint32_t)s_lut[(w[j] >> 8) & 0xFF] << 8) |
+                   ((uint32_t)s_lut[(w[j] >> 16) & 0xFF] << 16) | ((uint32_t)s_lut[w[j] >> 24] << 24);
+        *reinterpret_cast<uint4 *>(data + i0) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+        for (uint64_t i = i0; i < n; ++i) data[i] = s_lut[data[i]];
+    }
+}
+
+int translate_on_device(kmer_b200_index *ix, uint8_t *d_data, uint64_t n, const uint8_t *lut256) {
+    uint8_t *d_lut = nullptr;
+    KB_TRY(dev_alloc(ix, &d_lut, 256, false));
+    KB_CUDA(cudaMemcpyAsync(d_lut, lut256, 256, cudaMemcpyHostToDevice, ix->stream));
+    if (n) translate_kernel<<<(unsigned)((n + 4095) / 4096), 256, 0, ix->stream>>>(d_data, n, d_lut);
+    dev_free(ix, d_lut);
+    KB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int create_impl(const uint8_t *ranks, bool ranks_on_device, uint64_t n, uint32_t sigma, const uint32_t *ks, uint32_t n_ks,
-                const kmer_b200_config *cfg_in, kmer_b200_index **out) {
+                const kmer_b200_config *cfg_in, kmer_b200_index **out, const uint8_t *lut256 = nullptr) {
     if (!out) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "out is null");
     *out = nullptr;
     if (!ranks) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "ranks is null");
@@ -624,6 +653,7 @@ int create_impl(const uint8_t *ranks, bool ranks_on_device, uint64_t n, uint32_t
             KB_TRY(dev_alloc(ix, &d_ranks_owned, n, false));
             KB_CUDA_RET(cudaMemcpyAsync(d_ranks_owned, ranks, n, cudaMemcpyHostToDevice, ix->stream));
             d_ranks = d_ranks_owned;
+            if (lut256) KB_TRY(translate_on_device(ix, d_ranks_owned, n, lut256));  // invalid characters map to >= sigma
         }
         ix->prof.begin(K_PACK_TEXT, (double)n + (double)n * ix->bits / 8.0);
         kb::launch_pack_text(d_ranks, n, ix->bits, sigma, ix->text_words, ix->d_text, ix->d_flags, ix->stream);
@@ -1164,8 +1194,8 @@ int kmer_b200_presence_batch_device(kmer_b200_index *ix, const uint8_t *d_q, con
     return KMER_B200_OK;
 }
 
-int kmer_b200_search_batch(kmer_b200_index *ix, const uint8_t *q_ranks, const uint64_t *q_offsets, uint64_t Q,
-                           uint32_t mode, kmer_b200_result **out) {
+static int search_batch_host(kmer_b200_index *ix, const uint8_t *q_ranks, const uint64_t *q_offsets, uint64_t Q,
+                             uint32_t mode, const uint8_t *lut256, kmer_b200_result **out) {
     if (!ix || !out || !q_offsets) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
     *out = nullptr;
     DeviceGuard guard(ix->device);
@@ -1182,6 +1212,7 @@ int kmer_b200_search_batch(kmer_b200_index *ix, const uint8_t *q_ranks, const ui
     // offsets are rebased on the device side by passing q_ranks - q_offsets[0]
     KB_CUDA(cudaMemcpyAsync(d_off, q_offsets, (Q + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     if (n_sym) KB_CUDA(cudaMemcpyAsync(d_q, q_ranks + q_offsets[0], n_sym, cudaMemcpyHostToDevice, st));
+    if (lut256) KB_TRY(translate_on_device(ix, d_q, n_sym, lut256));
     KB_CUDA(cudaMemsetAsync(d_max, 0, sizeof(unsigned long long), st));
     if (Q) max_len_kernel<<<(unsigned)std::min<uint64_t>((Q + 255) / 256, 148 * 8), 256, 0, st>>>(d_off, Q, d_max);
     KB_CUDA(cudaMemcpyAsync(&ix->h_pinned[2], d_max, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
@@ -1232,6 +1263,23 @@ int kmer_b200_search_batch(kmer_b200_index *ix, const uint8_t *q_ranks, const ui
     }
     *out = res;
     return KMER_B200_OK;
+}
+
+int kmer_b200_search_batch(kmer_b200_index *ix, const uint8_t *q_ranks, const uint64_t *q_offsets, uint64_t Q,
+                           uint32_t mode, kmer_b200_result **out) {
+    return search_batch_host(ix, q_ranks, q_offsets, Q, mode, nullptr, out);
+}
+
+int kmer_b200_search_batch_text(kmer_b200_index *ix, const char *q_chars, const uint64_t *q_offsets, uint64_t Q,
+                                const uint8_t *lut256, uint32_t mode, kmer_b200_result **out) {
+    if (!lut256) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "lut256 is null");
+    return search_batch_host(ix, reinterpret_cast<const uint8_t *>(q_chars), q_offsets, Q, mode, lut256, out);
+}
+
+int kmer_b200_create_from_text(const char *text, uint64_t n, const uint8_t *lut256, uint32_t sigma, const uint32_t *ks,
+                               uint32_t n_ks, const kmer_b200_config *cfg, kmer_b200_index **out) {
+    if (!lut256) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "lut256 is null");
+    return create_impl(reinterpret_cast<const uint8_t *>(text), false, n, sigma, ks, n_ks, cfg, out, lut256);
 }
 
 uint64_t kmer_b200_result_n_queries(const kmer_b200_result *r) { return r ? r->n_queries : 0; }

@@ -260,3 +260,24 @@ def test_save_load_round_trip(kb, oracle_mod, tmp_path, sigma, ks):
         bad = tmp_path / "bad.bin"
         bad.write_bytes(b"not an index" * 100)
         kb.KmerIndex.load(str(bad))
+
+
+@pytest.mark.parametrize("alphabet,ks", [("dna4", [12]), ("dna15", [8]), ("aa27", [5])])
+def test_character_input_matches_rank_input(kb, alphabet, ks):
+    """Texts/queries given as characters (device-side translation through a 256-entry table) == given as ranks."""
+    from kmer_index_b200 import synth
+    sigma = kb.ALPHABETS[alphabet]
+    chars = np.frombuffer(kb.ALPHABET_CHARS[alphabet].encode(), dtype=np.uint8)
+    text = synth.random_text(100_003, sigma, 8)
+    q, off = synth.stress_queries(text, 500, 1, 30, sigma, 9)
+    queries = [chars[q[int(off[i]):int(off[i + 1])]].tobytes() for i in range(off.size - 1)]
+    queries[3] = queries[3].lower()                       # case-insensitive
+    lut = kb.char_lut(alphabet)
+    with kb.KmerIndex(text, sigma, ks) as a, kb.KmerIndex(chars[text].tobytes(), sigma, ks, lut=lut) as b:
+        want = a.search_batch(q, off).as_tuple()
+        assert_results_equal(b.search_batch_text(queries).as_tuple(), want, label="chars")
+        assert_results_equal(b.search_batch(q, off).as_tuple(), want, label="ranks on char-built index")
+        with pytest.raises(kb.KmerB200Error):
+            b.search_batch_text([b"ACG?T"])
+    with pytest.raises(kb.KmerB200Error):
+        kb.KmerIndex(b"ACGTNACGT" * 10, 4, [3], lut=kb.char_lut("dna4"))   # N is not in dna4
