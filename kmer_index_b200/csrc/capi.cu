@@ -1206,6 +1206,17 @@ static int search_batch_host(kmer_b200_index *ix, const uint8_t *q_ranks, const 
     uint8_t *d_q = nullptr;
     uint64_t *d_off = nullptr;
     unsigned long long *d_max = nullptr;
+    struct Staging {  // the device copies of the batch are released on every exit path
+        kmer_b200_index *ix;
+        uint8_t *&q;
+        uint64_t *&off;
+        unsigned long long *&mx;
+        ~Staging() {
+            dev_free(ix, q);
+            dev_free(ix, off);
+            dev_free(ix, mx);
+        }
+    } staging{ix, d_q, d_off, d_max};
     KB_TRY(dev_alloc(ix, &d_q, n_sym, false));
     KB_TRY(dev_alloc(ix, &d_off, Q + 1, false));
     KB_TRY(dev_alloc(ix, &d_max, 1, false));
@@ -1220,9 +1231,6 @@ static int search_batch_host(kmer_b200_index *ix, const uint8_t *q_ranks, const 
     const uint64_t max_len = ix->h_pinned[2];
     kmer_b200_result *dres = nullptr;
     int s = search_device_impl(ix, d_q - q_offsets[0], d_off, Q, max_len, mode, nullptr, 0, kFlavorFull, &dres);
-    dev_free(ix, d_q);
-    dev_free(ix, d_off);
-    dev_free(ix, d_max);
     if (s != 0) return s;
     // device result -> pinned host buffers
     kmer_b200_result *res = new (std::nothrow) kmer_b200_result();
