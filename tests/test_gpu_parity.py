@@ -281,3 +281,55 @@ def test_character_input_matches_rank_input(kb, alphabet, ks):
             b.search_batch_text([b"ACG?T"])
     with pytest.raises(kb.KmerB200Error):
         kb.KmerIndex(b"ACGTNACGT" * 10, 4, [3], lut=kb.char_lut("dna4"))   # N is not in dna4
+
+
+@pytest.mark.parametrize("sigma,ks", [(4, [12]), (4, [9, 13]), (27, [5]), (4, [3])])
+def test_long_queries_up_to_the_table_limit(kb, oracle_mod, sigma, ks):
+    """Queries of hundreds to 9999 symbols (kmer_index.hpp:401: the scheme table covers lengths < 10000): many
+    parts per query, packed query staged over several rounds, a full warp per query."""
+    from kmer_index_b200 import synth
+    text = synth.random_text(60_000, sigma, 12)
+    text[30_000:42_000] = np.resize(text[100:160], 12_000)        # a long periodic stretch: multi-part matches exist
+    lens = [200, 777, 1024, 2047, 4999, 9998, 9999, 10000, 10001]
+    qs = []
+    for i, m in enumerate(lens * 3):
+        start = [0, 30_000 + 17, 60_000 - m if m <= 60_000 else 0][i % 3]
+        piece = text[start:start + m]
+        if piece.size < m:
+            piece = np.resize(piece, m)
+        qs.append(piece.copy())
+    qs[5][-1] ^= 1                                                  # a near miss
+    q = np.concatenate(qs)
+    off = np.zeros(len(qs) + 1, dtype=np.uint64)
+    np.cumsum([x.size for x in qs], out=off[1:])
+    with kb.KmerIndex(text, sigma, ks) as ix, oracle_mod.Oracle(text, sigma, ks) as o:
+        got = ix.search_batch(q, off).as_tuple()
+        want = o.search(q, off)
+        ub = o.last_ub
+    assert_results_equal(got, want, label=f"long {ks}")
+    assert set(want[2].tolist()) >= {0, 1, 2}                      # OK, THROW (m > 10000) and UNDEFINED (m == 10000)
+    with kb.KmerIndex(text, sigma, ks, mode=kb.MODE_CORRECT) as ix:
+        keep = np.array([x.size < 10000 for x in qs])
+        got = ix.search_batch(q, off).as_tuple()
+        truth = oracle_mod.Oracle.truth(text, q, off)
+        for i in np.flatnonzero(keep):
+            assert np.array_equal(got[1][int(got[0][i]):int(got[0][i + 1])], truth[1][int(truth[0][i]):int(truth[0][i + 1])]), i
+    del ub
+
+
+@pytest.mark.parametrize("directory_bits", [12, 18, 30])
+def test_sparse_directory_and_accounting_variants(kb, oracle_mod, directory_bits):
+    """directory_bits caps the directory (hash >> shift indexing + binary search in the sorted hashes); profile=2
+    runs the count pass that also sums the gathered sectors. Neither may change a result."""
+    from kmer_index_b200 import synth
+    text = synth.random_text(200_000, 4, 21)
+    q, off = synth.stress_queries(text, 4000, 1, 60, 4, 22)
+    with oracle_mod.Oracle(text, 4, [12]) as o:
+        want = o.search(q, off)
+    with kb.KmerIndex(text, 4, [12], directory_bits=directory_bits, profile=2) as ix:
+        info = ix.element_info(0)
+        assert info.directory_shift == max(0, 24 - directory_bits)
+        assert_results_equal(ix.search_batch(q, off).as_tuple(), want, label=f"dir_bits={directory_bits}")
+        assert ix.last_search_gathers > 0
+        st = ix.stats()
+        assert st["search_count"]["launches"] >= 1 and st["search_count"]["device_ms"] > 0
