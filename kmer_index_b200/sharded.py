@@ -176,15 +176,26 @@ def search_device(ix, q_ptr: int, off_ptr: int, Q: int, max_len: int, world: int
         hits = res.n_positions
         res.free()
         return hits
+    import os
     import torch.distributed as dist
     rank = dist.get_rank()
+    trace = os.environ.get("KMER_B200_TRACE") and rank == 0
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if trace else None
+    if trace:
+        ev[0].record()
     res = _search_shard(ix, q_ptr, off_ptr, Q, max_len, world, dev)
+    if trace:
+        ev[1].record()
     offsets = torch.as_tensor(res.offsets(), device=dev)
     positions = (torch.as_tensor(res.positions(), device=dev) if res.n_positions
                  else torch.empty(0, dtype=torch.int32, device=dev))
     g_off, final = merge_to_rank0(offsets, positions, world, rank, dist)
     hits = int(g_off[-1].item()) if rank == 0 else 0
+    if trace:
+        ev[2].record()
     torch.cuda.current_stream().synchronize()
+    if trace:
+        print(f"[trace] shard search {ev[0].elapsed_time(ev[1]):.2f} ms, merge {ev[1].elapsed_time(ev[2]):.2f} ms", flush=True)
     res.free()
     return hits
 
