@@ -313,8 +313,8 @@ def run_ours(args, wl):
             if it >= min(args.warmup, 1):
                 eb.append(ev[0].elapsed_time(ev[1]))
                 es.append(ev[1].elapsed_time(ev[2]))
-        # sharded: only rank 0 reads the query batch from the host (NCCL broadcast to the others)
-        h2d_q = n_sym + (Q + 1) * 8 if (world == 1 or rank == 0) else 0
+        # sharded: every rank uploads 1/world of the query batch (then NCCL all-gather)
+        h2d_q = (n_sym + (Q + 1) * 8) // world
         e2e = {"build_ms": float(np.mean(eb)), "search_ms": float(np.mean(es)), "h2d": n_local + h2d_q, "d2h": d2h}
         del h_text, h_q, h_off
 
