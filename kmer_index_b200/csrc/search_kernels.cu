@@ -771,13 +771,17 @@ __device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t *t
     return r;
 }
 
+// Each warp owns 512 consecutive counts and reads them as 16 coalesced rounds of 32.
 __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const uint64_t *__restrict__ v, uint64_t n,
                                                                    uint64_t *__restrict__ block_sums) {
-    const uint64_t base = (uint64_t)blockIdx.x * kScanBlock + (uint64_t)threadIdx.x * kScanPerThread;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t wbase = (uint64_t)blockIdx.x * kScanBlock + (uint64_t)warp * (32 * kScanPerThread);
     uint64_t s = 0;
 #pragma unroll
-    for (int j = 0; j < kScanPerThread; ++j)
-        if (base + j < n) s += v[base + j];
+    for (int r = 0; r < kScanPerThread; ++r) {
+        const uint64_t i = wbase + r * 32 + lane;
+        if (i < n) s += v[i];
+    }
     uint64_t total;
     block_exclusive_scan(s, &total);
     if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
@@ -803,20 +807,40 @@ __global__ void __launch_bounds__(kScanThreads) scan_block_sums_kernel(uint64_t 
 
 __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(uint64_t *__restrict__ v, uint64_t n,
                                                                   const uint64_t *__restrict__ block_sums) {
-    const uint64_t base = (uint64_t)blockIdx.x * kScanBlock + (uint64_t)threadIdx.x * kScanPerThread;
+    // coalesced rounds -> shared memory -> each lane scans its 16 consecutive values -> back the same way.
+    // Row stride 17 keeps the blocked accesses at most 2-way bank conflicted.
+    constexpr int kRow = kScanPerThread + 1;
+    __shared__ uint64_t tile[kScanThreads / 32][32 * kRow];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t wbase = (uint64_t)blockIdx.x * kScanBlock + (uint64_t)warp * (32 * kScanPerThread);
+    uint64_t *mine = tile[warp];
+#pragma unroll
+    for (int r = 0; r < kScanPerThread; ++r) {
+        const int e = r * 32 + lane;  // element of the warp's segment
+        const uint64_t i = wbase + e;
+        mine[(e / kScanPerThread) * kRow + (e % kScanPerThread)] = i < n ? v[i] : 0;
+    }
+    __syncwarp();
     uint64_t x[kScanPerThread];
     uint64_t s = 0;
 #pragma unroll
     for (int j = 0; j < kScanPerThread; ++j) {
-        x[j] = base + j < n ? v[base + j] : 0;
+        x[j] = mine[lane * kRow + j];
         s += x[j];
     }
     uint64_t total;
     uint64_t run = block_exclusive_scan(s, &total) + block_sums[blockIdx.x];
 #pragma unroll
     for (int j = 0; j < kScanPerThread; ++j) {
-        if (base + j < n) v[base + j] = run;
+        mine[lane * kRow + j] = run;
         run += x[j];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < kScanPerThread; ++r) {
+        const int e = r * 32 + lane;
+        const uint64_t i = wbase + e;
+        if (i < n) v[i] = mine[(e / kScanPerThread) * kRow + (e % kScanPerThread)];
     }
 }
 
