@@ -844,6 +844,7 @@ int search_begin(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off,
     a.defer = p->d_defer;
     a.heavy = p->d_heavy;
     a.bits = ix->bits;
+    a.single_k = ix->ks.size() == 1;
     a.error_flag = ix->d_flags;
     a.gather_count = ix->cfg.profile >= 2 ? ix->d_gathers : nullptr;  // profile = 2: also count gathered sectors
     if (a.gather_count) cudaMemsetAsync(ix->d_gathers, 0, sizeof(unsigned long long), st);
@@ -1186,6 +1187,7 @@ int kmer_b200_presence_batch_device(kmer_b200_index *ix, const uint8_t *d_q, con
     a.present = present_format == 0 ? (uint64_t *)d_present : nullptr;
     a.present4 = present_format == 1 ? (uint32_t *)d_present : nullptr;
     a.bits = ix->bits;
+    a.single_k = ix->ks.size() == 1;
     a.error_flag = ix->d_flags;
     ix->prof.begin(K_SEARCH_PRESENCE, 0);
     launch_search(a, kPassPresence, ix->stream);

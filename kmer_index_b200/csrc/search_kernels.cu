@@ -136,7 +136,7 @@ __device__ __forceinline__ uint64_t load8(const uint8_t *p, uint32_t n_valid, bo
 constexpr uint32_t kHeavyCandidates = 2048;
 
 // HEAVY = true: the second launch (G = 32) over the heavy list; never hands a query off again.
-template <int PASS_, int G, bool HEAVY>
+template <int PASS_, int G, bool HEAVY, bool SINGLE>
 __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t q, uint64_t *smem_q) {
     // count pass variants: + sum of the gathered sectors; + whole-text rule left for the epilogue (sharded)
     constexpr bool kAccount = PASS_ == kPassCountAccount || PASS_ == kPassCountDeferredAccount;
@@ -250,23 +250,34 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
     const uint8_t *S = nullptr;
     if (a.mode == KMER_B200_MODE_CORRECT) {
         // any element answers correctly; take the largest k <= m (fewest candidates), else the smallest k
-        e0 = ix.elem_by_k_desc[ix.n_elems - 1];
-        for (uint32_t i = 0; i < ix.n_elems; ++i) {
-            const uint32_t e = ix.elem_by_k_desc[i];
-            if (ix.elem[e].k <= m) {
-                e0 = e;
-                break;
+        if (!SINGLE) {
+            e0 = ix.elem_by_k_desc[ix.n_elems - 1];
+            for (uint32_t i = 0; i < ix.n_elems; ++i) {
+                const uint32_t e = ix.elem_by_k_desc[i];
+                if (ix.elem[e].k <= m) {
+                    e0 = e;
+                    break;
+                }
             }
         }
         k0 = ix.elem[e0].k;
         kind = (m == k0) ? kExact : (m > k0 ? kContig : kSubK);
     } else {
-        const uint32_t s_off = ix.scheme.sum_off[m];
-        const uint32_t s_len = ix.scheme.sum_off[m + 1] - s_off;
-        S = ix.scheme.sum_elem + s_off;
-        e0 = S[0];
-        k0 = ix.elem[e0].k;
-        const bool multi = ix.scheme.use_multi[m] && ix.n_elems > 1;  // kmer_index.hpp:512
+        // single-k index: the table row is [k] for every length and the facade dispatches straight to the element
+        // (kmer_index.hpp:512-513); SINGLE compiles the multi-k plans out (fewer live registers, fewer spills)
+        uint32_t s_len = 1;
+        bool multi = false;
+        if (SINGLE) {
+            e0 = 0;
+            k0 = ix.elem[0].k;
+        } else {
+            const uint32_t s_off = ix.scheme.sum_off[m];
+            s_len = ix.scheme.sum_off[m + 1] - s_off;
+            S = ix.scheme.sum_elem + s_off;
+            e0 = S[0];
+            k0 = ix.elem[e0].k;
+            multi = ix.scheme.use_multi[m] && ix.n_elems > 1;  // kmer_index.hpp:512
+        }
         if (!multi) {
             // kmer_index_element<k0>::search, kmer_index.hpp:193-346
             if (m == k0) {
@@ -505,7 +516,7 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
         if (!need_presence) {
             // contiguous plan (or exact lookup): any element finds the same occurrences, so seed from the one with
             // the largest k <= m (the shortest candidate list); the rest of the query is compared against the text
-            if (kind == kContig) {
+            if (!SINGLE && kind == kContig) {
                 for (uint32_t i = 0; i < ix.n_elems; ++i) {
                     const uint32_t e = ix.elem_by_k_desc[i];
                     if (ix.elem[e].k <= m) {
@@ -522,7 +533,7 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
             }
             seed.lo = __shfl_sync(gmask, seed.lo, 0, G);
             seed.cnt = __shfl_sync(gmask, seed.cnt, 0, G);
-        } else if (kind == kBuggySingle && ix.n_elems > 1) {
+        } else if (!SINGLE && kind == kBuggySingle && ix.n_elems > 1) {
             // the last full part and the rest are one contiguous stretch of k0 + rest symbols: an element with a
             // larger k (multi-k index) gives a shorter candidate list for it
             const uint32_t last = (P - 1) * k0;
@@ -622,41 +633,49 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
 #undef GBALLOT
 }
 
-template <int PASS, int G>
+template <int PASS, int G, bool SINGLE>
 __global__ void __launch_bounds__(kSearchThreads, KB_SEARCH_MIN_BLOCKS) search_kernel(const SearchArgs a) {
     constexpr int kGroups = kSearchThreads / G;
     extern __shared__ uint64_t smem_q[];
     const uint64_t q = (uint64_t)blockIdx.x * kGroups + threadIdx.x / G;
-    if (q < a.n_queries) search_query<PASS, G, false>(a, q, smem_q);
+    if (q < a.n_queries) search_query<PASS, G, false, SINGLE>(a, q, smem_q);
 }
 
 // second launch of a pass: one warp per query of the heavy list (a.heavy[0] = length, a.heavy[1..] = query ids)
-template <int PASS>
+template <int PASS, bool SINGLE>
 __global__ void __launch_bounds__(kSearchThreads) search_heavy_kernel(const SearchArgs a) {
     constexpr int kGroups = kSearchThreads / 32;
     extern __shared__ uint64_t smem_q[];
     const uint32_t n_heavy = a.heavy[0];
     for (uint32_t i = blockIdx.x * kGroups + threadIdx.x / 32; i < n_heavy; i += gridDim.x * kGroups) {
-        search_query<PASS, 32, true>(a, (uint64_t)a.heavy[1 + i], smem_q);
+        search_query<PASS, 32, true, SINGLE>(a, (uint64_t)a.heavy[1 + i], smem_q);
         __syncwarp();
     }
 }
 
-template <int PASS, int G>
-static void launch_search_pg(const SearchArgs &args, cudaStream_t stream) {
+template <int PASS, int G, bool SINGLE>
+static void launch_search_pgs(const SearchArgs &args, cudaStream_t stream) {
     constexpr int kGroups = kSearchThreads / G;
     const uint64_t blocks = (args.n_queries + kGroups - 1) / kGroups;
     const size_t smem = (size_t)kGroups * args.q_words * sizeof(uint64_t);
-    cudaFuncSetAttribute(search_kernel<PASS, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    search_kernel<PASS, G><<<(unsigned)blocks, kSearchThreads, smem, stream>>>(args);
+    cudaFuncSetAttribute(search_kernel<PASS, G, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    search_kernel<PASS, G, SINGLE><<<(unsigned)blocks, kSearchThreads, smem, stream>>>(args);
     if (G < 32 && args.heavy != nullptr && PASS != kPassPresence) {
         // queries with long candidate lists, if any (the list length lives on the device: fixed grid, no host sync)
         SearchArgs h = args;
         h.q_words = search_q_words(32, args.bits, args.max_len);
         const size_t hsmem = (size_t)(kSearchThreads / 32) * h.q_words * sizeof(uint64_t);
-        cudaFuncSetAttribute(search_heavy_kernel<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem);
-        search_heavy_kernel<PASS><<<148 * 2, kSearchThreads, hsmem, stream>>>(h);
+        cudaFuncSetAttribute(search_heavy_kernel<PASS, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem);
+        search_heavy_kernel<PASS, SINGLE><<<148 * 2, kSearchThreads, hsmem, stream>>>(h);
     }
+}
+
+template <int PASS, int G>
+static void launch_search_pg(const SearchArgs &args, cudaStream_t stream) {
+    if (args.single_k)
+        launch_search_pgs<PASS, G, true>(args, stream);
+    else
+        launch_search_pgs<PASS, G, false>(args, stream);
 }
 
 // epilogue of the deferred count pass: the whole-text presence rule (kmer_index.hpp:216-227, :234 -> :119)
