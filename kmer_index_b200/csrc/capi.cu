@@ -155,6 +155,7 @@ struct kmer_b200_index {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;  // host-batch pipeline: H2D / D2H engines next to `stream`
     kmer_b200_config cfg{};
     uint64_t n = 0;
     uint32_t sigma = 0, bits = 0;
@@ -1196,6 +1197,136 @@ int kmer_b200_presence_batch_device(kmer_b200_index *ix, const uint8_t *d_q, con
     return KMER_B200_OK;
 }
 
+__global__ void __launch_bounds__(256) add_base_kernel(uint64_t *__restrict__ v, uint64_t n, uint64_t base) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] += base;
+}
+
+// Large host batches are pipelined in chunks of queries: the H2D copy of chunk c+1 (copy engine), the search of
+// chunk c (SMs) and the D2H copy of chunk c-1's offsets and status (the other copy engine) run concurrently, so
+// the call costs about as much as moving its bytes over PCIe once. Position lists stay on the device until the
+// last chunk is done (their total size is only known then) and are copied out in one sweep.
+static int search_batch_host_pipelined(kmer_b200_index *ix, const uint8_t *q_ranks, const uint64_t *q_offsets, uint64_t Q,
+                                       uint32_t mode, kmer_b200_result **out) {
+    constexpr int kChunks = 8;
+    cudaStream_t st = ix->stream;
+    if (!ix->copy_in) {
+        // stream creation costs milliseconds: the two copy streams are created once per device and shared
+        // (searches on one device are short critical sections; the per-index mutex orders a handle's own work)
+        static std::mutex mu;
+        static cudaStream_t cached[64][2] = {};
+        std::lock_guard<std::mutex> lock(mu);
+        const int d = ix->device & 63;
+        if (!cached[d][0]) {
+            KB_CUDA(cudaStreamCreateWithFlags(&cached[d][0], cudaStreamNonBlocking));
+            KB_CUDA(cudaStreamCreateWithFlags(&cached[d][1], cudaStreamNonBlocking));
+        }
+        ix->copy_in = cached[d][0];
+        ix->copy_out = cached[d][1];
+    }
+    const uint64_t n_sym = q_offsets[Q] - q_offsets[0];
+    uint8_t *d_q = nullptr;
+    uint64_t *d_off = nullptr;
+    unsigned long long *d_max = nullptr;
+    kmer_b200_result *chunk_res[kChunks] = {};
+    cudaEvent_t ev_in[kChunks] = {}, ev_done[kChunks] = {};
+    kmer_b200_result *res = nullptr;
+    auto cleanup = [&](int code) {
+        cudaStreamSynchronize(ix->copy_in);
+        cudaStreamSynchronize(ix->copy_out);
+        cudaStreamSynchronize(st);
+        for (int c = 0; c < kChunks; ++c) {
+            if (chunk_res[c]) kmer_b200_result_free(chunk_res[c]);
+            if (ev_in[c]) cudaEventDestroy(ev_in[c]);
+            if (ev_done[c]) cudaEventDestroy(ev_done[c]);
+        }
+        dev_free(ix, d_q);
+        dev_free(ix, d_off);
+        dev_free(ix, d_max);
+        if (code != 0 && res) kmer_b200_result_free(res);
+        return code;
+    };
+    if (dev_alloc(ix, &d_q, n_sym, false) || dev_alloc(ix, &d_off, Q + 1, false) || dev_alloc(ix, &d_max, kChunks, false))
+        return cleanup(KMER_B200_ERR_OUT_OF_MEMORY);
+    // the allocations above are ordered on `st`; the copy streams must not touch them earlier
+    cudaEvent_t ev_alloc;
+    cudaEventCreateWithFlags(&ev_alloc, cudaEventDisableTiming);
+    cudaMemsetAsync(d_max, 0, kChunks * sizeof(unsigned long long), st);
+    cudaEventRecord(ev_alloc, st);
+    cudaStreamWaitEvent(ix->copy_in, ev_alloc, 0);
+    cudaStreamWaitEvent(ix->copy_out, ev_alloc, 0);
+    cudaEventDestroy(ev_alloc);
+
+    res = new (std::nothrow) kmer_b200_result();
+    if (!res) return cleanup(fail(KMER_B200_ERR_OUT_OF_MEMORY, "host allocation failed"));
+    res->index = ix;
+    res->on_device = false;
+    res->n_queries = Q;
+    res->offsets = (uint64_t *)pinned_get((Q + 1) * sizeof(uint64_t), &res->cap_offsets);
+    res->status = (uint8_t *)pinned_get(Q, &res->cap_status);
+    if (!res->offsets || !res->status) return cleanup(fail(KMER_B200_ERR_OUT_OF_MEMORY, "pinned host allocation failed"));
+
+    // enqueue every chunk's H2D now; the copy engine works through them while the chunks are searched
+    const uint64_t per = (Q + kChunks - 1) / kChunks;
+    uint64_t c0[kChunks + 1];
+    for (int c = 0; c <= kChunks; ++c) c0[c] = std::min<uint64_t>((uint64_t)c * per, Q);
+    for (int c = 0; c < kChunks; ++c) {
+        const uint64_t qa = c0[c], qb = c0[c + 1];
+        cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming);
+        if (qb > qa) {
+            // offsets [qa, qb] (the shared boundary entry is copied by both neighbours: same value)
+            cudaMemcpyAsync(d_off + qa, q_offsets + qa, (qb - qa + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ix->copy_in);
+            const uint64_t s0 = q_offsets[qa] - q_offsets[0], s1 = q_offsets[qb] - q_offsets[0];
+            if (s1 > s0) cudaMemcpyAsync(d_q + s0, q_ranks + q_offsets[qa], s1 - s0, cudaMemcpyHostToDevice, ix->copy_in);
+        }
+        cudaEventRecord(ev_in[c], ix->copy_in);
+    }
+    uint64_t base = 0;
+    for (int c = 0; c < kChunks; ++c) {
+        const uint64_t qa = c0[c], qb = c0[c + 1], Qc = qb - qa;
+        if (Qc == 0) continue;
+        cudaStreamWaitEvent(st, ev_in[c], 0);
+        max_len_kernel<<<(unsigned)std::min<uint64_t>((Qc + 255) / 256, 148 * 8), 256, 0, st>>>(d_off + qa, Qc, d_max + c);
+        cudaMemcpyAsync(&ix->h_pinned[2], d_max + c, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return cleanup(fail(KMER_B200_ERR_CUDA, std::string("search (H2D): ") + cudaGetErrorString(e)));
+        const uint64_t max_len = ix->h_pinned[2];
+        int s = search_device_impl(ix, d_q - q_offsets[0], d_off + qa, Qc, max_len, mode, nullptr, 0, kFlavorFull, &chunk_res[c]);
+        if (s != 0) return cleanup(s);
+        kmer_b200_result *cr = chunk_res[c];
+        if (base) add_base_kernel<<<(unsigned)((Qc + 1 + 255) / 256), 256, 0, st>>>(cr->offsets, Qc + 1, base);
+        cudaEventRecord(ev_done[c], st);
+        cudaStreamWaitEvent(ix->copy_out, ev_done[c], 0);
+        // the last entry of a chunk's offsets equals the first of the next one: copy Qc entries, the final total below
+        cudaMemcpyAsync(res->offsets + qa, cr->offsets, Qc * sizeof(uint64_t), cudaMemcpyDeviceToHost, ix->copy_out);
+        cudaMemcpyAsync(res->status + qa, cr->status, Qc, cudaMemcpyDeviceToHost, ix->copy_out);
+        base += cr->n_positions;
+    }
+    res->n_positions = base;
+    const size_t pos_bytes = base * sizeof(uint32_t);
+    if (pos_bytes > (8ull << 30)) {
+        res->positions = (uint32_t *)std::malloc(pos_bytes);
+        res->positions_pageable = true;
+        res->cap_positions = pos_bytes;
+    } else {
+        res->positions = (uint32_t *)pinned_get(pos_bytes, &res->cap_positions);
+    }
+    if (!res->positions) return cleanup(fail(KMER_B200_ERR_OUT_OF_MEMORY, "host allocation for the positions failed"));
+    uint64_t at = 0;
+    for (int c = 0; c < kChunks; ++c) {
+        if (!chunk_res[c] || !chunk_res[c]->n_positions) continue;
+        cudaMemcpyAsync(res->positions + at, chunk_res[c]->positions, chunk_res[c]->n_positions * sizeof(uint32_t),
+                        cudaMemcpyDeviceToHost, ix->copy_out);
+        at += chunk_res[c]->n_positions;
+    }
+    cudaError_t e = cudaStreamSynchronize(ix->copy_out);
+    res->offsets[Q] = base;
+    if (e != cudaSuccess) return cleanup(fail(KMER_B200_ERR_CUDA, std::string("search (D2H): ") + cudaGetErrorString(e)));
+    *out = res;
+    return cleanup(0);
+}
+
 static int search_batch_host(kmer_b200_index *ix, const uint8_t *q_ranks, const uint64_t *q_offsets, uint64_t Q,
                              uint32_t mode, const uint8_t *lut256, kmer_b200_result **out) {
     if (!ix || !out || !q_offsets) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
@@ -1205,6 +1336,9 @@ static int search_batch_host(kmer_b200_index *ix, const uint8_t *q_ranks, const 
     cudaStream_t st = ix->stream;
     const uint64_t n_sym = q_offsets[Q] - q_offsets[0];
     if (n_sym && !q_ranks) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "q_ranks is null");
+    // batches whose transfer dominates (>= 256 MiB over PCIe) are pipelined in chunks
+    if (!lut256 && Q >= (1u << 18) && n_sym + Q * 17 >= (256ull << 20) && !std::getenv("KMER_B200_NO_PIPELINE"))
+        return search_batch_host_pipelined(ix, q_ranks, q_offsets, Q, mode, out);
     uint8_t *d_q = nullptr;
     uint64_t *d_off = nullptr;
     unsigned long long *d_max = nullptr;

@@ -73,6 +73,29 @@ def _planted(text, Q, m_lo, m_hi, seed):
     return text[idx], off
 
 
+def test_pipelined_host_batch_equals_plain(kb):
+    """Host batches >= 256 MiB are searched in pipelined chunks (H2D / search / D2H overlapped); the result must be
+    the plain path's, offsets included."""
+    import os
+
+    from kmer_index_b200 import synth
+    text = synth.random_text(20_000_000, 4, TEXT_SEED)
+    q1, off1 = synth.random_queries(3_000_000, 12, 100, 4, QUERY_SEED)
+    q2, off2 = _planted(text, 3_000_000, 12, 100, QUERY_SEED + 5)
+    q = np.concatenate([q1, q2])
+    off = np.concatenate([off1, off2[1:] + off1[-1]])
+    assert q.size + 17 * (off.size - 1) >= (256 << 20)
+    with kb.KmerIndex(text, 4, [12]) as ix:
+        piped = ix.search_batch(q, off).as_tuple()
+        os.environ["KMER_B200_NO_PIPELINE"] = "1"
+        try:
+            plain = ix.search_batch(q, off).as_tuple()
+        finally:
+            del os.environ["KMER_B200_NO_PIPELINE"]
+    assert piped[1].size > 500_000
+    assert_results_equal(piped, plain, label="pipelined vs plain")
+
+
 def test_config3_full_text_counts_and_subsample(kb, oracle_mod):
     """multi_kmer_index<dna4,{5,7,9,11,13}> over 100 Mbp: all 1e6 queries by per-query hit COUNT against the oracle
     (1.4e10 positions do not fit a CPU result), and a subsample bit for bit."""
