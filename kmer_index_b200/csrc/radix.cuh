@@ -72,18 +72,29 @@ __device__ __forceinline__ void tile_rank(const KeyT (&key)[kSortItems], uint32_
     for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) (&sm.warp_cnt[0][0])[i] = 0;
     __syncthreads();
 
+    // phase A: the same-digit lane masks of all items (independent vote chains: the scheduler overlaps them);
+    // kept packed in local_pos[r] = lanes-below count | group size << 8 | leader << 16 | valid << 17
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
         const uint32_t d = (uint32_t)(key[r] >> shift) & mask;
         const bool valid = FULL || e0 + r * 32 < count;
         const uint32_t peers = match_digit<BITS>(d, FULL ? 0xFFFFFFFFu : __ballot_sync(0xFFFFFFFFu, valid));
         const uint32_t lower = peers & lt_mask;
+        local_pos[r] = (uint32_t)__popc(lower) | ((uint32_t)__popc(peers) << 8) | ((lower == 0 ? 1u : 0u) << 16) |
+                       ((valid ? 1u : 0u) << 17);
+    }
+    // phase B: per-warp counters, in item order (the leader of each group bumps the counter of its digit)
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const uint32_t d = (uint32_t)(key[r] >> shift) & mask;
+        const uint32_t packed = local_pos[r];
+        const bool valid = FULL || ((packed >> 17) & 1u);
         uint32_t pre = 0;
         if (valid) pre = my_cnt[d];
         __syncwarp();
-        if (valid && lower == 0) my_cnt[d] = pre + __popc(peers);
+        if (valid && ((packed >> 16) & 1u)) my_cnt[d] = pre + ((packed >> 8) & 0xFFu);
         __syncwarp();
-        local_pos[r] = pre + __popc(lower);
+        local_pos[r] = pre + (packed & 0xFFu);
     }
     __syncthreads();
 
