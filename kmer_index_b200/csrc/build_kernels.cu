@@ -103,6 +103,27 @@ struct TextSource {  // key(i) = hash of the k-mer starting at symbol i; value(i
     __device__ __forceinline__ void prefetch_vals(uint64_t, uint32_t) const {}
 };
 
+// k-mers wider than one 64-bit window (k * bits > 64: aa27 k >= 9, dna5 k >= 17 ...; keys are then always 64-bit):
+// every key is a Horner walk over two windows, so there is no word sharing between a thread's items to exploit.
+struct WideTextSource {
+    using key_type = uint64_t;
+    PackedText text;
+    uint32_t k;
+    __device__ __forceinline__ uint64_t key(uint64_t i) const { return key_at(text.words, i, k, text.bits, text.sigma); }
+    template <bool FULL>
+    __device__ __forceinline__ void load_keys(uint64_t first, uint32_t avail, uint64_t (&out)[kSortItems]) const {
+#pragma unroll
+        for (int r = 0; r < kSortItems; ++r) out[r] = (FULL || (uint32_t)(r * 32) < avail) ? key(first + r * 32) : 0ull;
+    }
+    template <bool FULL>
+    __device__ __forceinline__ void load_vals(uint64_t first, uint32_t, uint32_t (&out)[kSortItems]) const {
+#pragma unroll
+        for (int r = 0; r < kSortItems; ++r) out[r] = (uint32_t)first + r * 32;
+    }
+    template <bool FULL>
+    __device__ __forceinline__ void prefetch_vals(uint64_t, uint32_t) const {}
+};
+
 template <typename KeyT>
 struct PairSource {  // materialised (key, value) pairs
     using key_type = KeyT;
@@ -512,6 +533,10 @@ void launch_column_scan(uint32_t *d_tile_hist, uint32_t n_tiles, uint32_t *d_chu
 void launch_hist_text(const PackedText &text, uint32_t k, uint64_t n_kmers, uint32_t shift, uint32_t mask,
                       uint32_t *d_tile_hist, cudaStream_t stream) {
     const uint32_t n_tiles = (uint32_t)((n_kmers + kSortTile - 1) / kSortTile);
+    if (k * text.bits > 64) {  // no sliding window: one two-window hash per k-mer
+        radix_hist_kernel<<<n_tiles, kSortThreads, 0, stream>>>(WideTextSource{text, k}, n_kmers, shift, mask, d_tile_hist);
+        return;
+    }
     radix_hist_text_kernel<<<n_tiles, kSortThreads, 0, stream>>>(text, k, n_kmers, shift, mask, d_tile_hist);
 }
 
@@ -530,7 +555,9 @@ void launch_hist_pairs(const void *d_keys, uint32_t key_bytes, uint64_t n, uint3
 void launch_scatter_text(const PackedText &text, uint32_t k, uint32_t key_bytes, uint64_t n_kmers, uint32_t shift,
                          uint32_t mask, const uint32_t *d_tile_base, void *d_out_keys, uint32_t *d_out_vals,
                          cudaStream_t stream) {
-    if (key_bytes == 8)
+    if (k * text.bits > 64)
+        launch_scatter(WideTextSource{text, k}, n_kmers, shift, mask, d_tile_base, (uint64_t *)d_out_keys, d_out_vals, stream);
+    else if (key_bytes == 8)
         launch_scatter(TextSource<uint64_t>{text, k}, n_kmers, shift, mask, d_tile_base, (uint64_t *)d_out_keys, d_out_vals, stream);
     else
         launch_scatter(TextSource<uint32_t>{text, k}, n_kmers, shift, mask, d_tile_base, (uint32_t *)d_out_keys, d_out_vals, stream);

@@ -467,8 +467,6 @@ int new_index(uint64_t n, uint32_t sigma, const uint32_t *ks, uint32_t n_ks, con
         // static_assert(k > 0 and k < 64 / log2(sigma)), kmer_index.hpp:42-43
         if (k == 0 || !((double)k < 64.0 / std::log2((double)sigma)))
             return fail(KMER_B200_ERR_INVALID_ARGUMENT, "k must satisfy 0 < k < 64 / log2(sigma) (kmer_index.hpp:42)");
-        if (k * bits > 64)
-            return fail(KMER_B200_ERR_UNSUPPORTED, "k * bits-per-symbol must be <= 64 (one 64-bit text window per k-mer) in this build");
         for (uint32_t j = 0; j < i; ++j)
             if (ks[j] == k) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "duplicate k");
         k_max = std::max(k_max, k);
@@ -586,7 +584,7 @@ int finalize_index(kmer_b200_index *ix) {
     for (uint32_t i = 0; i < n_ks; ++i) D.elem[i] = ix->elems[i].dev;
     D.scheme = kb::SchemeTables{ix->d_sum_off, ix->d_sum_elem, ix->d_use_multi};
     std::memset(D.aux_for_len, 0xFF, sizeof(D.aux_for_len));
-    for (uint32_t e = 0; e <= 32; ++e) {
+    for (uint32_t e = 0; e < 64; ++e) {
         // saturating: only compared against 1e7 and used as slab width when < sigma^k
         const double approx = std::pow((double)ix->sigma, (double)e);
         D.pow_sigma[e] = approx > 9.0e18 ? (1ull << 63) : fast_pow(ix->sigma, (uint8_t)e);

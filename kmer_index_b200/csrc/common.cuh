@@ -48,6 +48,24 @@ __device__ __forceinline__ uint64_t key_from_window(uint64_t w, uint32_t k, uint
     return h;
 }
 
+// Hash of the k symbols starting at symbol `sym`, for any legal k (kmer_index.hpp:42-43). k * bits can exceed one
+// window only for alphabets that are not a power of two (aa27 k >= 9, dna5 k >= 17; sigma^k < 2^64 keeps k * bits
+// < 64 otherwise): the Horner walk then continues into a second window (k * bits <= 128 always).
+template <typename WordPtr>
+__device__ __forceinline__ uint64_t key_at(WordPtr words, uint64_t sym, uint32_t k, uint32_t bits, uint32_t sigma) {
+    const uint64_t w0 = window64(words, sym, bits);
+    const uint32_t spw = 64 / bits;
+    if (k <= spw) return key_from_window(w0, k, bits, sigma);
+    const uint64_t w1 = window64(words, sym + spw, bits);
+    const uint64_t mask = (1ull << bits) - 1;
+    uint64_t h = 0;
+#pragma unroll 1
+    for (uint32_t i = 0; i < spw; ++i) h = h * sigma + ((w0 >> (64 - bits * (i + 1))) & mask);
+#pragma unroll 1
+    for (uint32_t i = 0; i < k - spw; ++i) h = h * sigma + ((w1 >> (64 - bits * (i + 1))) & mask);
+    return h;
+}
+
 // ---------------------------------------------------------------------------------------------
 // One index element (one k): the CSR form of the reference's
 // robin_hood::unordered_map<hash, std::vector<position>> (kmer_index.hpp:52).
@@ -90,7 +108,7 @@ struct DeviceIndex {
     uint32_t sharded;
     Element elem[kMaxElements];
     SchemeTables scheme;
-    uint64_t pow_sigma[33];  // sigma^e for e <= 32 (saturating at 2^63)
+    uint64_t pow_sigma[64];  // sigma^e for e < 64 (saturating at 2^63)
     uint8_t elem_by_k_desc[kMaxElements];  // element indices ordered by k descending (_all_ks, :410)
     // Auxiliary elements (slots n_elems..): an index with k' = m built on demand for a query length m that the
     // plan answers by prefix enumeration (m < k). The bucket of the whole query in the k' = m index IS the

@@ -366,7 +366,7 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
                     d = j * ix.elem[S[0]].k;  // expected at text offset j * k_0 (:535,544)
                 }
                 const Element &E = ix.elem[e];
-                const uint64_t key = key_from_window(window64(qw, (uint64_t)o, T.bits), E.k, T.bits, T.sigma);
+                const uint64_t key = key_at(qw, (uint64_t)o, E.k, T.bits, T.sigma);
                 rg = bucket_of(E, key);
                 if (kAccount) n_gather += 1 + (E.shift ? 1 : 0);
             }
@@ -481,7 +481,7 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
         // get_position_for_all_kmer_with_prefix (kmer_index.hpp:115-148): the buckets of all hashes in
         // [prefix_hash, prefix_hash + sigma^(k-m)) are one contiguous slab of the sorted position array
         const uint64_t width = ix.pow_sigma[k0 - m];
-        const uint64_t lo_key = key_from_window(window64(qw, 0, T.bits), m, T.bits, T.sigma) * width;
+        const uint64_t lo_key = key_at(qw, 0, m, T.bits, T.sigma) * width;
         const uint64_t slo = lower_bound_key(E0, lo_key);
         const uint64_t shi = lower_bound_key(E0, lo_key + width);
         if (shi - slo > 1) unsorted = element_key(E0, slo) != element_key(E0, shi - 1);
@@ -527,7 +527,7 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
             }
             const Element &E = ix.elem[seed_e];
             if (gl == 0) {
-                const uint64_t key = key_from_window(window64(qw, 0, T.bits), E.k, T.bits, T.sigma);
+                const uint64_t key = key_at(qw, 0, E.k, T.bits, T.sigma);
                 seed = bucket_of(E, key);
                 if (kAccount) n_gather += 1 + (E.shift ? 1 : 0);
             }
@@ -549,7 +549,7 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
                 Range alt{0, 0};
                 if (gl == 0) {
                     const Element &E = ix.elem[e];
-                    alt = bucket_of(E, key_from_window(window64(qw, (uint64_t)last, T.bits), E.k, T.bits, T.sigma));
+                    alt = bucket_of(E, key_at(qw, (uint64_t)last, E.k, T.bits, T.sigma));
                     if (kAccount) n_gather += 1 + (E.shift ? 1 : 0);
                 }
                 alt.lo = __shfl_sync(gmask, alt.lo, 0, G);

@@ -127,6 +127,11 @@ namespace
         KREF_TRY(dna5, 4)
         KREF_TRY(aa27, 3)
         KREF_TRY(aa27, 9, 10)
+        // k-mers wider than 64 packed bits / hashes wider than 32 bits
+        KREF_TRY(aa27, 12)
+        KREF_TRY(dna5, 18)
+        KREF_TRY(dna4, 20)
+        KREF_TRY(dna15, 16)
         return nullptr;
     }
 }

@@ -76,6 +76,28 @@ def main():
     case("tm_dna15_k10_11_12", t, 15, [10, 11, 12], q, off)
     q, off = synth.stress_queries(t, 400, 1, 9, 15, 1242)
     case("tm_dna15_k5_6_7", t, 15, [5, 6, 7], q, off)
+    # k-mers wider than one 64-bit packed window (aa27 k >= 9, dna5 k >= 17) and hashes wider than 32 bits
+    low27 = np.where(low == 0, 3, 26).astype(np.uint8)
+    q, off = synth.stress_queries(low27, 500, 5, 40, 27, 1243, low_sigma=2)
+    q = np.where(q == 0, 3, np.where(q == 1, 26, q)).astype(np.uint8)
+    case("wide_low_aa27_k12", low27, 27, [12], q, off)
+    case("wide_low_aa27_k9_10", low27, 27, [9, 10], q, off)
+    t = synth.random_text(20000, 27, 208)
+    q, off = synth.stress_queries(t, 500, 8, 40, 27, 1244)
+    case("wide_aa27_k12", t, 27, [12], q, off)
+    case("wide_aa27_k9_10", t, 27, [9, 10], q, off)
+    t = synth.random_text(20000, 5, 209)
+    q, off = synth.stress_queries(t, 500, 10, 60, 5, 1245)
+    case("wide_dna5_k18", t, 5, [18], q, off)
+    low5 = np.where(low == 0, 2, 4).astype(np.uint8)
+    q, off = synth.stress_queries(low5, 500, 10, 60, 5, 1246, low_sigma=2)
+    q = np.where(q == 0, 2, np.where(q == 1, 4, q)).astype(np.uint8)
+    case("wide_low_dna5_k18", low5, 5, [18], q, off)
+    q, off = synth.stress_queries(low, 500, 9, 70, 4, 1247, low_sigma=2)
+    case("wide_low_dna4_k20", low, 4, [20], q, off)
+    t = synth.random_text(20000, 15, 210)
+    q, off = synth.stress_queries(t, 400, 12, 40, 15, 1248)
+    case("wide_dna15_k16", t, 15, [16], q, off)
     # fast_pow (fast_pow.hpp:46-93) and choose_best_k (choose_best_k.hpp:12-60)
     bases = np.array([0, 1, 2, 3, 4, 5, 15, 27, 255, 65537, 2 ** 32 + 1], dtype=np.uint64)
     exps = np.arange(0, 80, dtype=np.uint8)

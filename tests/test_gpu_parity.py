@@ -14,22 +14,10 @@ def kb():
     return kmer_index_b200
 
 
-def build_or_skip(kb, text, sigma, ks, **kw):
-    """Builds the index; a k-mer wider than one 64-bit text window (k * bits-per-symbol > 64, e.g. aa27 k >= 9)
-    is a documented gap of this build ('Limits') and must fail loudly with ERR_UNSUPPORTED."""
-    try:
-        return kb.KmerIndex(text, sigma, ks, **kw)
-    except kb.KmerB200Error as e:
-        bits = 2 if sigma <= 4 else 4 if sigma <= 16 else 8
-        if e.code == -5 and max(ks) * bits > 64:
-            pytest.skip(f"sigma={sigma} k={max(ks)}: k-mers wider than 64 packed bits are not built yet")
-        raise
-
-
 @pytest.mark.parametrize("name", golden_cases())
 def test_cuda_matches_golden(kb, name):
     g = load_golden(name)
-    with build_or_skip(kb, g["text"], int(g["sigma"]), g["ks"].tolist()) as ix:
+    with kb.KmerIndex(g["text"], int(g["sigma"]), g["ks"].tolist()) as ix:
         got = ix.search_batch(g["q"], g["q_off"]).as_tuple()
         assert_results_equal(got, (g["r_off"], g["r_pos"], g["r_status"]), skip=g["ub"].astype(bool), label=name)
         flat, o_ = g["scheme_flat"], 0
@@ -43,7 +31,7 @@ def test_cuda_matches_golden(kb, name):
 def test_cuda_matches_oracle_on_golden_inputs_including_ub(kb, oracle_mod, name):
     """On UB-flagged queries the product's defined behaviour is the oracle's ('not equal')."""
     g = load_golden(name)
-    with build_or_skip(kb, g["text"], int(g["sigma"]), g["ks"].tolist()) as ix, \
+    with kb.KmerIndex(g["text"], int(g["sigma"]), g["ks"].tolist()) as ix, \
             oracle_mod.Oracle(g["text"], int(g["sigma"]), g["ks"].tolist()) as o:
         assert_results_equal(ix.search_batch(g["q"], g["q_off"]).as_tuple(), o.search(g["q"], g["q_off"]), label=name)
 
@@ -53,7 +41,10 @@ def test_cuda_matches_oracle_on_golden_inputs_including_ub(kb, oracle_mod, name)
                                         (4, [1], 5000), (5, [13], 300_000), (4, [3, 9, 16], 200_000),
                                         # hashes wider than 32 bits
                                         (4, [20], 300_000), (4, [31], 100_000), (15, [12], 200_000), (15, [16], 50_000),
-                                        (27, [8], 100_000), (4, [12, 24], 100_000)])
+                                        (27, [8], 100_000), (4, [12, 24], 100_000),
+                                        # k-mers wider than one 64-bit packed window (two-window hash)
+                                        (27, [9], 200_000), (27, [13], 100_000), (5, [17], 200_000), (5, [27], 50_000),
+                                        (3, [40], 50_000), (2, [63], 20_000), (17, [15], 50_000), (27, [5, 9, 12], 50_000)])
 def test_csr_matches_oracle(kb, oracle_mod, sigma, ks, n):
     """The index itself: positions stably sorted by hash == the reference's buckets in hash order."""
     from kmer_index_b200 import synth
@@ -84,6 +75,11 @@ CASES = [
     ("dna15_k10", 15, [10], 300_000, 6000, 5, 30),
     ("dna15_multi", 15, [10, 11, 12], 300_000, 6000, 5, 40),
     ("dna4_mixed", 4, [9, 21], 300_000, 6000, 5, 70),
+    # k-mers wider than one 64-bit packed window (aa27 k >= 9, dna5 k >= 17)
+    ("aa27_k12", 27, [12], 300_000, 6000, 6, 40),
+    ("aa27_k9_10", 27, [9, 10], 300_000, 6000, 5, 45),
+    ("dna5_k20", 5, [20], 300_000, 6000, 12, 70),
+    ("dna5_k13_18_27", 5, [13, 18, 27], 200_000, 6000, 10, 90),
 ]
 
 
@@ -107,7 +103,8 @@ def test_cuda_matches_oracle(kb, oracle_mod, label, sigma, ks, n, Q, m_lo, m_hi,
 
 
 @pytest.mark.parametrize("sigma,ks,n,m_hi", [(4, [12], 200_000, 60), (4, [5, 7, 9, 11, 13], 200_000, 45),
-                                             (15, [8], 100_000, 30), (4, [16], 100_000, 70)])
+                                             (15, [8], 100_000, 30), (4, [16], 100_000, 70),
+                                             (27, [12], 100_000, 40), (5, [18], 100_000, 60)])
 def test_correct_mode_matches_ground_truth(kb, oracle_mod, sigma, ks, n, m_hi):
     from kmer_index_b200 import synth
     text = synth.random_text(n, sigma, 31)
@@ -154,7 +151,8 @@ def test_edge_cases(kb):
 
 @pytest.mark.parametrize("fmt", [0, 1, "fused"])
 @pytest.mark.parametrize("sigma,ks,n,m_lo,m_hi,world", [(4, [16], 400_000, 16, 64, 2), (4, [12], 300_000, 13, 64, 3),
-                                                       (4, [5, 7, 9, 11, 13], 200_000, 4, 40, 2), (15, [8], 200_000, 3, 20, 4)])
+                                                       (4, [5, 7, 9, 11, 13], 200_000, 4, 40, 2), (15, [8], 200_000, 3, 20, 4),
+                                                       (27, [12], 200_000, 8, 40, 2)])
 def test_sharded_search_emulated_on_one_gpu(kb, oracle_mod, sigma, ks, n, m_lo, m_hi, world, fmt):
     """The sharded path (position-range shards with halo, presence OR, global-presence search, rank-order merge)
     run as `world` indices on one GPU must equal the unsharded reference-exact result."""
@@ -237,7 +235,7 @@ def test_heavy_buckets_take_the_warp_path(kb, oracle_mod, sigma, ks):
         assert_results_equal(ix.search_batch(q, off).as_tuple(), oracle_mod.Oracle.truth(text, q, off), label="heavy correct")
 
 
-@pytest.mark.parametrize("sigma,ks", [(4, [12]), (4, [5, 7, 9, 11, 13]), (15, [10]), (27, [5])])
+@pytest.mark.parametrize("sigma,ks", [(4, [12]), (4, [5, 7, 9, 11, 13]), (15, [10]), (27, [5]), (27, [12])])
 def test_save_load_round_trip(kb, oracle_mod, tmp_path, sigma, ks):
     """Construct once, load later: the loaded index answers exactly like the built one (and like the oracle)."""
     from kmer_index_b200 import synth
