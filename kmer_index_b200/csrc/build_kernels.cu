@@ -350,14 +350,14 @@ __device__ __forceinline__ void scatter_tile(const Source &src, uint64_t tile_be
     // keys live in registers through the ranking; values are fetched afterwards (prefetched to L2 meanwhile),
     // which keeps the 32-bit kernel at <= 64 registers so two CTAs share an SM and overlap each other's phases
     KeyT key[kSortItems];
-    uint32_t local_pos[kSortItems];
+    uint32_t local_pos2[kSortItems / 2];  // two 16-bit tile positions per register
     src.template load_keys<FULL>(tile_begin + e0, count - min(count, e0), key);
     src.template prefetch_vals<FULL>(tile_begin + e0, count - min(count, e0));
 #ifdef KB_ABL_NORANK  // timing ablation (profiles/README.md): identity placement instead of ranking
-    for (int r = 0; r < kSortItems; ++r) local_pos[r] = e0 + r * 32;
+    for (int r = 0; r < kSortItems; ++r) local_pos2[r >> 1] = (r & 1) ? (local_pos2[r >> 1] | ((e0 + r * 32) << 16)) : (e0 + r * 32);
     if (tid < kRadix) sm.delta[tid] = (uint32_t)tile_begin;
 #else
-    tile_rank<BITS, FULL>(key, count, shift, mask, local_pos, sm.rank);
+    tile_rank<BITS, FULL>(key, count, shift, mask, local_pos2, sm.rank);
     if (tid < kRadix) sm.delta[tid] = tile_base_row[tid] - sm.rank.excl[tid];
 #endif
     {
@@ -365,7 +365,7 @@ __device__ __forceinline__ void scatter_tile(const Source &src, uint64_t tile_be
         src.template load_vals<FULL>(tile_begin + e0, count - min(count, e0), val);
 #pragma unroll
         for (int r = 0; r < kSortItems; ++r)
-            if (FULL || e0 + r * 32 < count) sm.put(local_pos[r], key[r], val[r]);
+            if (FULL || e0 + r * 32 < count) sm.put((local_pos2[r >> 1] >> (16 * (r & 1))) & 0xFFFFu, key[r], val[r]);
     }
     __syncthreads();
 #ifdef KB_ABL_NOOUT  // timing ablation (profiles/README.md): skip the global stores

@@ -56,12 +56,14 @@ __device__ __forceinline__ uint32_t match_digit(uint32_t d, uint32_t peers) {
 // Stable rank of this thread's kSortItems keys inside the tile by digit (key >> shift) & mask (BITS >= the
 // digit width). Item r of this thread is tile element ((warp * kSortItems + r) * 32 + lane); with FULL = false
 // elements >= count are ignored. On return
-//   local_pos[r] = position of item r in the tile's digit-sorted order (undefined for ignored items),
+//   local_pos2[r / 2] holds, in its 16-bit half r % 2, the position of item r in the tile's digit-sorted order
+//                     (tile positions are < 2^13; undefined for ignored items) -- two per register keeps the
+//                     kernel inside its 64-register budget without spilling,
 //   sm.count[d]  = number of items with digit d, sm.excl[d] = exclusive prefix of count.
 // All kSortThreads threads must call. Ends with a __syncthreads().
 template <int BITS, bool FULL, typename KeyT>
 __device__ __forceinline__ void tile_rank(const KeyT (&key)[kSortItems], uint32_t count, uint32_t shift,
-                                          uint32_t mask, uint32_t (&local_pos)[kSortItems], RankSmem &sm) {
+                                          uint32_t mask, uint32_t (&local_pos2)[kSortItems / 2], RankSmem &sm) {
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
@@ -73,28 +75,35 @@ __device__ __forceinline__ void tile_rank(const KeyT (&key)[kSortItems], uint32_
     __syncthreads();
 
     // phase A: the same-digit lane masks of all items (independent vote chains: the scheduler overlaps them);
-    // kept packed in local_pos[r] = lanes-below count | group size << 8 | leader << 16 | valid << 17
+    // kept packed per item as lanes-below count (5 bits) | group size << 5 (6 bits) | valid << 11
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
         const uint32_t d = (uint32_t)(key[r] >> shift) & mask;
         const bool valid = FULL || e0 + r * 32 < count;
         const uint32_t peers = match_digit<BITS>(d, FULL ? 0xFFFFFFFFu : __ballot_sync(0xFFFFFFFFu, valid));
-        const uint32_t lower = peers & lt_mask;
-        local_pos[r] = (uint32_t)__popc(lower) | ((uint32_t)__popc(peers) << 8) | ((lower == 0 ? 1u : 0u) << 16) |
-                       ((valid ? 1u : 0u) << 17);
+        const uint32_t info = (uint32_t)__popc(peers & lt_mask) | ((uint32_t)__popc(peers) << 5) | ((valid ? 1u : 0u) << 11);
+        if (r & 1)
+            local_pos2[r >> 1] |= info << 16;
+        else
+            local_pos2[r >> 1] = info;
     }
-    // phase B: per-warp counters, in item order (the leader of each group bumps the counter of its digit)
+    // phase B: per-warp counters, in item order (the lowest lane of each group bumps the counter of its digit)
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
         const uint32_t d = (uint32_t)(key[r] >> shift) & mask;
-        const uint32_t packed = local_pos[r];
-        const bool valid = FULL || ((packed >> 17) & 1u);
+        const uint32_t info = (local_pos2[r >> 1] >> (16 * (r & 1))) & 0xFFFFu;
+        const bool valid = FULL || ((info >> 11) & 1u);
+        const uint32_t below = info & 31u;
         uint32_t pre = 0;
         if (valid) pre = my_cnt[d];
         __syncwarp();
-        if (valid && ((packed >> 16) & 1u)) my_cnt[d] = pre + ((packed >> 8) & 0xFFu);
+        if (valid && below == 0) my_cnt[d] = pre + ((info >> 5) & 63u);
         __syncwarp();
-        local_pos[r] = pre + (packed & 0xFFu);
+        const uint32_t pos = pre + below;
+        if (r & 1)
+            local_pos2[r >> 1] = (local_pos2[r >> 1] & 0xFFFFu) | (pos << 16);
+        else
+            local_pos2[r >> 1] = (local_pos2[r >> 1] & 0xFFFF0000u) | pos;
     }
     __syncthreads();
 
@@ -130,7 +139,8 @@ __device__ __forceinline__ void tile_rank(const KeyT (&key)[kSortItems], uint32_
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
         const uint32_t d = (uint32_t)(key[r] >> shift) & mask;
-        if (FULL || e0 + r * 32 < count) local_pos[r] += my_cnt[d];
+        // no carry between the halves: every final position is < kSortTile <= 2^16
+        if (FULL || e0 + r * 32 < count) local_pos2[r >> 1] += my_cnt[d] << (16 * (r & 1));
     }
     __syncthreads();
 }

@@ -983,18 +983,18 @@ __global__ void __launch_bounds__(kSortThreads, 1)
             __syncthreads();
             for (uint64_t t0 = 0; t0 < len; t0 += kSortTile) {
                 const uint32_t count = (uint32_t)min((uint64_t)kSortTile, len - t0);
-                uint32_t val[kSortItems], local_pos[kSortItems];
+                uint32_t val[kSortItems], local_pos2[kSortItems / 2];
 #pragma unroll
                 for (int r = 0; r < kSortItems; ++r) {
                     const uint32_t e = (uint32_t)((warp * kSortItems + r) * 32 + lane);
                     val[r] = e < count ? src[t0 + e] : 0u;
                 }
-                tile_rank<8, false, uint32_t>(val, count, shift, 0xFFu, local_pos, sm.rank);
+                tile_rank<8, false, uint32_t>(val, count, shift, 0xFFu, local_pos2, sm.rank);
 #pragma unroll
                 for (int r = 0; r < kSortItems; ++r) {
                     const uint32_t e = (uint32_t)((warp * kSortItems + r) * 32 + lane);
                     const uint32_t d = (val[r] >> shift) & 0xFF;
-                    if (e < count) dst[sm.base[d] + (local_pos[r] - sm.rank.excl[d])] = val[r];
+                    if (e < count) dst[sm.base[d] + (((local_pos2[r >> 1] >> (16 * (r & 1))) & 0xFFFFu) - sm.rank.excl[d])] = val[r];
                 }
                 __syncthreads();
                 if (tid < kRadix) sm.base[tid] += sm.rank.count[tid];
