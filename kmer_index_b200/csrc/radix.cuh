@@ -53,6 +53,18 @@ __device__ __forceinline__ uint32_t match_digit(uint32_t d, uint32_t peers) {
     return peers;
 }
 
+// The digit of a key. BYTE: a byte-aligned 8-bit digit of a 32-bit key (shift in {0, 8, 16, 24}, mask == 0xFF) is one
+// PRMT instead of a shift and a mask.
+template <bool BYTE, typename KeyT>
+__device__ __forceinline__ uint32_t digit_of(KeyT key, uint32_t shift, uint32_t mask) {
+    if constexpr (BYTE) {
+        static_assert(sizeof(KeyT) == 4, "byte digits are taken from 32-bit keys");
+        return __byte_perm((uint32_t)key, 0u, 0x4440u | (shift >> 3));
+    } else {
+        return (uint32_t)(key >> shift) & mask;
+    }
+}
+
 // Stable rank of this thread's kSortItems keys inside the tile by digit (key >> shift) & mask (BITS >= the
 // digit width). Item r of this thread is tile element ((warp * kSortItems + r) * 32 + lane); with FULL = false
 // elements >= count are ignored. On return
@@ -61,7 +73,7 @@ __device__ __forceinline__ uint32_t match_digit(uint32_t d, uint32_t peers) {
 //                     kernel inside its 64-register budget without spilling,
 //   sm.count[d]  = number of items with digit d, sm.excl[d] = exclusive prefix of count.
 // All kSortThreads threads must call. Ends with a __syncthreads().
-template <int BITS, bool FULL, typename KeyT>
+template <int BITS, bool FULL, typename KeyT, bool BYTE = false>
 __device__ __forceinline__ void tile_rank(const KeyT (&key)[kSortItems], uint32_t count, uint32_t shift,
                                           uint32_t mask, uint32_t (&local_pos2)[kSortItems / 2], RankSmem &sm) {
     const int tid = threadIdx.x;
@@ -78,7 +90,7 @@ __device__ __forceinline__ void tile_rank(const KeyT (&key)[kSortItems], uint32_
     // kept packed per item as lanes-below count (5 bits) | group size << 5 (6 bits) | valid << 11
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
-        const uint32_t d = (uint32_t)(key[r] >> shift) & mask;
+        const uint32_t d = digit_of<BYTE>(key[r], shift, mask);
         const bool valid = FULL || e0 + r * 32 < count;
         const uint32_t peers = match_digit<BITS>(d, FULL ? 0xFFFFFFFFu : __ballot_sync(0xFFFFFFFFu, valid));
         const uint32_t info = (uint32_t)__popc(peers & lt_mask) | ((uint32_t)__popc(peers) << 5) | ((valid ? 1u : 0u) << 11);
@@ -90,7 +102,7 @@ __device__ __forceinline__ void tile_rank(const KeyT (&key)[kSortItems], uint32_
     // phase B: per-warp counters, in item order (the lowest lane of each group bumps the counter of its digit)
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
-        const uint32_t d = (uint32_t)(key[r] >> shift) & mask;
+        const uint32_t d = digit_of<BYTE>(key[r], shift, mask);
         const uint32_t info = (local_pos2[r >> 1] >> (16 * (r & 1))) & 0xFFFFu;
         const bool valid = FULL || ((info >> 11) & 1u);
         const uint32_t below = info & 31u;
@@ -138,7 +150,7 @@ __device__ __forceinline__ void tile_rank(const KeyT (&key)[kSortItems], uint32_
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
-        const uint32_t d = (uint32_t)(key[r] >> shift) & mask;
+        const uint32_t d = digit_of<BYTE>(key[r], shift, mask);
         // no carry between the halves: every final position is < kSortTile <= 2^16
         if (FULL || e0 + r * 32 < count) local_pos2[r >> 1] += my_cnt[d] << (16 * (r & 1));
     }
