@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--scale", type=float, default=1.0, help="shrink n and Q (development only; invalid as a result)")
+    ap.add_argument("--text-symbols", type=int, default=0, help="override the text length only (development only; invalid as a result)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--count-only", action="store_true", help="time search without materialising positions")
@@ -208,6 +209,8 @@ def run_ours(args, wl):
 
     sigma, ks = wl["sigma"], wl["ks"]
     n = max(int(wl["n"] * args.scale), 4 * max(ks))
+    if args.text_symbols:
+        n = args.text_symbols
     Q = max(int(wl["Q"] * args.scale), 1)
     m_lo, m_hi = wl["m"]
     k_max = max(ks)
@@ -356,7 +359,8 @@ def run_ours(args, wl):
             "metric": "search_queries_per_s", "value": Q / (search_ms * 1e-3), "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": build_ms + search_ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": wl["name"] + (f" (scaled x{args.scale})" if args.scale != 1.0 else ""),
+            "config": {"workload": wl["name"] + (f" (scaled x{args.scale})" if args.scale != 1.0 else "")
+                                   + (f" (text overridden to {args.text_symbols} symbols)" if args.text_symbols else ""),
                        "text_symbols": n, "queries": Q, "query_len": [m_lo, m_hi], "sigma": sigma, "ks": ks,
                        "sharding": f"position range x{world}, halo {shard.halo}" if world > 1 else "none",
                        "mode": "reference_exact", "count_only": bool(args.count_only),
@@ -391,7 +395,7 @@ def run_ours(args, wl):
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             key = f"{args.workload}:{name}"
-            if key in traffic and args.scale == 1.0 and world == 1:   # captured on the unsharded workload
+            if key in traffic and args.scale == 1.0 and not args.text_symbols and world == 1:   # captured on the unsharded workload
                 line["roofline"]["traffic"] = traffic[key]["dram_bytes_per_launch"]
                 line["roofline"]["traffic_source"] = traffic[key]["source"]
         except (OSError, ValueError, KeyError):
