@@ -35,6 +35,30 @@ __device__ __forceinline__ uint64_t window64(WordPtr words, uint64_t sym, uint32
     return sh ? ((hi << sh) | (lo >> (64 - sh))) : hi;
 }
 
+// Data-dependent reads of the search (directory, buckets, text windows). On sm_100a a default load that misses L2
+// costs a 128-byte DRAM fetch; the L2::64B qualifier halves that (profiles/tools/gather_variants.cu: 127 -> 64
+// bytes of DRAM traffic per random 8-byte read). The index is immutable while a search runs: non-coherent path.
+__device__ __forceinline__ uint32_t gather32(const uint32_t *p) {
+    uint32_t v;
+    asm("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint64_t gather64(const uint64_t *p) {
+    uint64_t v;
+    asm("ld.global.nc.L2::64B.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+// window64 over the packed text in global memory, read with gather loads
+__device__ __forceinline__ uint64_t text_window64(const uint64_t *words, uint64_t sym, uint32_t bits) {
+    const uint64_t bit = sym * bits;
+    const uint64_t w = bit >> 6;
+    const uint32_t sh = (uint32_t)(bit & 63);
+    const uint64_t hi = gather64(words + w);
+    const uint64_t lo = gather64(words + w + 1);
+    return sh ? ((hi << sh) | (lo >> (64 - sh))) : hi;
+}
+
 // The k-mer hash of the k symbols at the top of window `w` (kmer_index.hpp:56-73).
 // sigma == 4: the 2k-bit field itself. Otherwise Horner over the k symbols (k * bits <= 64).
 __device__ __forceinline__ uint64_t key_from_window(uint64_t w, uint32_t k, uint32_t bits, uint32_t sigma) {
@@ -89,7 +113,8 @@ struct Element {
 };
 
 __device__ __forceinline__ uint64_t element_key(const Element &E, uint64_t i) {
-    return E.key_bytes == 8 ? static_cast<const uint64_t *>(E.keys)[i] : (uint64_t)static_cast<const uint32_t *>(E.keys)[i];
+    return E.key_bytes == 8 ? gather64(static_cast<const uint64_t *>(E.keys) + i)
+                            : (uint64_t)gather32(static_cast<const uint32_t *>(E.keys) + i);
 }
 
 struct SchemeTables {

@@ -37,9 +37,9 @@ struct Range {
 __device__ __forceinline__ uint64_t lower_bound_key(const Element &E, uint64_t key) {
     if (key >= E.key_space) return E.n_kmers;
     const uint64_t t = key >> E.shift;
-    uint64_t lo = E.dir[t];
+    uint64_t lo = gather32(E.dir + t);
     if (E.shift == 0) return lo;
-    uint64_t hi = E.dir[t + 1];
+    uint64_t hi = gather32(E.dir + t + 1);
     while (lo < hi) {
         const uint64_t mid = lo + ((hi - lo) >> 1);
         if (element_key(E, mid) < key)
@@ -53,8 +53,8 @@ __device__ __forceinline__ uint64_t lower_bound_key(const Element &E, uint64_t k
 // the bucket of `key`: the reference's at(hash) (kmer_index.hpp:76-84)
 __device__ __forceinline__ Range bucket_of(const Element &E, uint64_t key) {
     const uint64_t t = key >> E.shift;
-    uint64_t lo = E.dir[t];
-    uint64_t hi = E.dir[t + 1];
+    uint64_t lo = gather32(E.dir + t);
+    uint64_t hi = gather32(E.dir + t + 1);
     if (E.shift != 0) {
         uint64_t a = lo, b = hi;
         while (a < b) {
@@ -85,7 +85,7 @@ __device__ __forceinline__ bool match_span(const PackedText &T, const uint64_t *
     const uint32_t spw = 64 / T.bits;
     while (len) {
         const uint32_t c = len < spw ? len : spw;
-        const uint64_t a = window64(T.words, tpos, T.bits);
+        const uint64_t a = text_window64(T.words, tpos, T.bits);
         const uint64_t b = window64(qw, (uint64_t)qpos, T.bits);
         if ((a ^ b) >> (64 - c * T.bits)) return false;
         tpos += c;
@@ -668,7 +668,7 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
             uint32_t p = 0;
             bool ok = false;
             if (c < seed.cnt) {
-                const uint32_t at = Es.pos[seed.lo + c];
+                const uint32_t at = gather32(Es.pos + seed.lo + c);
                 ok = at >= seed_d;
                 p = at - seed_d;
                 ok = ok && (uint64_t)p < ix.owned;
