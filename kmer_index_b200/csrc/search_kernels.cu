@@ -432,15 +432,30 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
     uint32_t seed_e = e0, seed_d = 0;
     bool all_present = true;
     uint64_t present_mask = 0;
-    if (kind != kSubK && need_presence) {
+    // Every plan goes through the same lookup loop -- the lanes of a warp hold queries of different plans, and a
+    // gather issued from one place is one round trip for all of them. A contiguous plan (or exact lookup) does one
+    // lookup, part 0: any element finds the same occurrences, so it takes the element with the largest k <= m
+    // (the shortest candidate list) and the rest of the query is compared against the text.
+    uint32_t e_first = e0;
+    if (!SINGLE && !need_presence && kind == kContig) {
+        for (uint32_t i = 0; i < ix.n_elems; ++i) {
+            const uint32_t e = ix.elem_by_k_desc[i];
+            if (ix.elem[e].k <= m) {
+                e_first = e;
+                break;
+            }
+        }
+    }
+    const uint32_t n_lookups = need_presence ? nparts : 1;
+    if (kind != kSubK) {
         uint64_t best_cnt = ~0ull;
-        for (uint32_t base = 0; base < nparts; base += G) {
+        for (uint32_t base = 0; base < n_lookups; base += G) {
             const uint32_t j = base + gl;
-            const bool valid = j < nparts;
+            const bool valid = j < n_lookups;
             Range rg{0, 0};
-            uint32_t e = e0, o = j * k0, d = j * k0;
+            uint32_t e = e_first, o = j * k0, d = j * k0;
             if (valid) {
-                if (from_list) {  // `last_k = current_k` is not cumulative, kmer_index.hpp:526
+                if (from_list && need_presence) {  // `last_k = current_k` is not cumulative, kmer_index.hpp:526
                     e = S[j];
                     o = j ? ix.elem[S[j - 1]].k : 0;
                     d = j * ix.elem[S[0]].k;  // expected at text offset j * k_0 (:535,544)
@@ -453,7 +468,7 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
             const uint32_t here = GBALLOT(valid && rg.cnt != 0);
             if (base < 64) present_mask |= (uint64_t)here << base;
             const uint32_t want = GBALLOT(valid);
-            if (here != want) {
+            if (need_presence && here != want) {
                 all_present = false;
                 // stop early only when the local answer is final (unsharded search)
                 if (PASS != kPassPresence && !kDefer && a.present_global == nullptr && a.present_global4 == nullptr) break;
@@ -593,27 +608,7 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
             n_hits += __popc(b);
         }
     } else {
-        if (!need_presence) {
-            // contiguous plan (or exact lookup): any element finds the same occurrences, so seed from the one with
-            // the largest k <= m (the shortest candidate list); the rest of the query is compared against the text
-            if (!SINGLE && kind == kContig) {
-                for (uint32_t i = 0; i < ix.n_elems; ++i) {
-                    const uint32_t e = ix.elem_by_k_desc[i];
-                    if (ix.elem[e].k <= m) {
-                        seed_e = e;
-                        break;
-                    }
-                }
-            }
-            const Element &E = ix.elem[seed_e];
-            if (gl == 0) {
-                const uint64_t key = key_at(qw, 0, E.k, T.bits, T.sigma);
-                seed = bucket_of(E, key);
-                if (kAccount) n_gather += 1 + (E.shift ? 1 : 0);
-            }
-            seed.lo = GSHFL(seed.lo, 0);
-            seed.cnt = GSHFL(seed.cnt, 0);
-        } else if (!SINGLE && kind == kBuggySingle && ix.n_elems > 1) {
+        if (!SINGLE && kind == kBuggySingle && ix.n_elems > 1) {
             // the last full part and the rest are one contiguous stretch of k0 + rest symbols: an element with a
             // larger k (multi-k index) gives a shorter candidate list for it
             const uint32_t last = (P - 1) * k0;
@@ -644,6 +639,7 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
         const Element &Es = ix.elem[seed_e];
         const uint32_t ks = Es.k;
         const uint32_t kf = from_list ? ix.elem[S[0]].k : k0;  // k of part 0 (text stride of the multi-k defect)
+        const uint32_t n_spans = kind == kExact ? 0u : (kind == kContig ? 1u : (kind == kBuggySingle ? P : nparts));
         bool count_by_range = PASS != kPassWrite && kind == kExact && ix.owned == T.n;
         HAND_OFF_IF_HEAVY(seed.cnt)  // same decision in the count and the write pass
         if (count_by_range) n_hits = seed.cnt;
@@ -674,21 +670,27 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
                 ok = ok && (uint64_t)p < ix.owned;
                 if (kAccount && (((seed.lo + c) & 7) == 0 || c == 0)) ++n_gather;
                 if (kAccount && ok && kind != kExact) n_gather += 1 + (m * T.bits >> 8);
-                if (ok) {
+                // the rest of the plan as text spans (text offset, query offset, length) relative to the match start;
+                // one loop for every plan, so the text reads of a warp's lanes are issued together
+                for (uint32_t sp = 0; ok && sp < n_spans; ++sp) {
+                    uint32_t dt, qo, ln;
                     if (kind == kContig) {
-                        ok = match_span(T, qw, (uint64_t)p + ks, ks, m - ks);
-                    } else if (kind == kBuggySingle) {
-                        const uint32_t last = (P - 1) * k0;  // query offset of the last full part
-                        ok = match_span(T, qw, (uint64_t)p, 0, k0);
-                        for (uint32_t j = 1; ok && j + 1 < P; ++j) ok = match_span(T, qw, (uint64_t)p + j * k0, last, k0);
-                        if (ok) ok = match_span(T, qw, (uint64_t)p + last, last, k0 + rest);
-                    } else if (kind == kMultiSum) {
-                        // part i is read at query offset k_{i-1} and expected at text offset i*k_0
+                        dt = ks, qo = ks, ln = m - ks;
+                    } else if (SINGLE || kind == kBuggySingle) {
+                        // part 0 in place, the middle parts compared against the LAST part (kmer_index.hpp:314),
+                        // then the last part and the rest as one stretch
+                        const uint32_t last = (P - 1) * k0;
+                        dt = sp == 0 ? 0 : (sp + 1 == P ? last : sp * k0);
+                        qo = sp == 0 ? 0 : last;
+                        ln = sp + 1 == P ? k0 + rest : k0;
+                    } else {
+                        // part i is read at query offset k_{i-1} and expected at text offset i * k_0
                         // (kmer_index.hpp:526 and :535,544)
-                        ok = match_span(T, qw, (uint64_t)p, 0, kf);
-                        for (uint32_t i = 1; ok && i < nparts; ++i)
-                            ok = match_span(T, qw, (uint64_t)p + (uint64_t)i * kf, ix.elem[S[i - 1]].k, ix.elem[S[i]].k);
+                        dt = sp * kf;
+                        qo = sp ? ix.elem[S[sp - 1]].k : 0;
+                        ln = ix.elem[S[sp]].k;
                     }
+                    ok = match_span(T, qw, (uint64_t)p + dt, qo, ln);
                 }
             }
             const uint32_t b = GBALLOT(ok);
