@@ -785,7 +785,10 @@ struct PendingSearch {
     uint8_t *d_defer = nullptr;
     uint64_t *d_block_sums = nullptr;
     uint32_t *d_heavy = nullptr;  // [0] = count, [1..Q] = ids of queries with long candidate lists
+    uint32_t *d_hits = nullptr;   // [0] = count, [1..Q] = ids of queries with hits (what the write pass visits)
     void release() {
+        dev_free(ix, d_hits);
+        d_hits = nullptr;
         dev_free(ix, d_unsorted);
         dev_free(ix, d_defer);
         dev_free(ix, d_block_sums);
@@ -820,9 +823,11 @@ int search_begin(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off,
     };
     if (dev_alloc(ix, &res->offsets, Q + 1, false) || dev_alloc(ix, &res->status, Q, false) ||
         dev_alloc(ix, &p->d_unsorted, Q, false) || dev_alloc(ix, &p->d_block_sums, offsets_scan_blocks(Q) + 1, false) ||
-        (d_present4 && dev_alloc(ix, &p->d_defer, Q, false)) || dev_alloc(ix, &p->d_heavy, Q + 1, false))
+        (d_present4 && dev_alloc(ix, &p->d_defer, Q, false)) || dev_alloc(ix, &p->d_heavy, Q + 1, false) ||
+        dev_alloc(ix, &p->d_hits, Q + 1, false))
         return bail(KMER_B200_ERR_OUT_OF_MEMORY);
     cudaMemsetAsync(p->d_heavy, 0, sizeof(uint32_t), st);
+    cudaMemsetAsync(p->d_hits, 0, sizeof(uint32_t), st);
 
     SearchArgs &a = p->args;
     a = SearchArgs{};
@@ -842,6 +847,7 @@ int search_begin(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off,
     a.present4 = d_present4;
     a.defer = p->d_defer;
     a.heavy = p->d_heavy;
+    a.hits = p->d_hits;
     a.bits = ix->bits;
     a.single_k = ix->ks.size() == 1;
     a.error_flag = ix->d_flags;

@@ -45,6 +45,7 @@ struct SearchArgs {
     uint32_t bits;                   // bits per packed symbol (to size the heavy launch's staging)
     uint32_t single_k;               // the index has one element: launch the kernels compiled without the multi-k plans
     uint32_t *heavy;                 // device or null, u32[1 + Q]: [0] = number of heavy queries, then their ids
+    uint32_t *hits;                  // device or null, u32[1 + Q]: [0] = number of queries with hits (count pass), then their ids
     uint32_t q_words;                // packed words reserved per query in shared memory (search_q_words)
     uint32_t max_len;                // longest query the shared-memory reservation (and the shard halo) allows
     const uint64_t *present_global;  // device or null: OR over shards of the presence masks (format 0)

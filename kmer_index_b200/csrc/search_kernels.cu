@@ -710,6 +710,15 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
         const bool flag = unsorted && n_hits > 1;
         a.unsorted[q] = flag ? 1 : 0;
         if (flag) atomicAdd(a.error_flag + 1, 1u);  // number of segments the sort pass has to visit
+        if (!HEAVY && a.hits != nullptr && n_hits > 0) {
+            // the write pass only visits the queries listed here (one atomic per set of lanes arriving together)
+            const uint32_t act = __activemask();
+            const int leader = __ffs(act) - 1;
+            uint32_t slot = 0;
+            if (lane == leader) slot = atomicAdd(a.hits, (uint32_t)__popc(act));
+            slot = __shfl_sync(act, slot, leader) + __popc(act & ((1u << lane) - 1));
+            a.hits[1 + slot] = (uint32_t)q;
+        }
     }
 #undef HAND_OFF_IF_HEAVY
 #undef GBALLOT
@@ -722,6 +731,19 @@ __global__ void __launch_bounds__(kSearchThreads, KB_SEARCH_MIN_BLOCKS) search_k
     extern __shared__ uint64_t smem_q[];
     const uint64_t q = (uint64_t)blockIdx.x * kGroups + threadIdx.x / G;
     if (q < a.n_queries) search_query<PASS, G, false, SINGLE>(a, q, smem_q);
+}
+
+// write pass over the queries the count pass listed as having hits (a.hits[0] = length, a.hits[1..] = query ids):
+// with random queries over a large key space that is a small share of the batch, and the lanes of a warp are all busy
+template <int G, bool SINGLE>
+__global__ void __launch_bounds__(kSearchThreads, KB_SEARCH_MIN_BLOCKS) search_listed_write_kernel(const SearchArgs a) {
+    constexpr int kGroups = kSearchThreads / G;
+    extern __shared__ uint64_t smem_q[];
+    const uint32_t n_listed = a.hits[0];
+    for (uint64_t i = (uint64_t)blockIdx.x * kGroups + threadIdx.x / G; i < n_listed; i += (uint64_t)gridDim.x * kGroups) {
+        search_query<kPassWrite, G, false, SINGLE>(a, (uint64_t)a.hits[1 + i], smem_q);
+        __syncwarp();
+    }
 }
 
 // second launch of a pass: one warp per query of the heavy list (a.heavy[0] = length, a.heavy[1..] = query ids)
@@ -742,7 +764,13 @@ static void launch_search_pgs(const SearchArgs &args, cudaStream_t stream) {
     const uint64_t blocks = (args.n_queries + kGroups - 1) / kGroups;
     const size_t smem = (size_t)kGroups * args.q_words * sizeof(uint64_t);
     cudaFuncSetAttribute(search_kernel<PASS, G, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    search_kernel<PASS, G, SINGLE><<<(unsigned)blocks, kSearchThreads, smem, stream>>>(args);
+    if (PASS == kPassWrite && args.hits != nullptr) {
+        cudaFuncSetAttribute(search_listed_write_kernel<G, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        search_listed_write_kernel<G, SINGLE>
+            <<<(unsigned)std::min<uint64_t>(blocks, 148 * 8 * 2), kSearchThreads, smem, stream>>>(args);
+    } else {
+        search_kernel<PASS, G, SINGLE><<<(unsigned)blocks, kSearchThreads, smem, stream>>>(args);
+    }
     if (G < 32 && args.heavy != nullptr && PASS != kPassPresence) {
         // queries with long candidate lists, if any (the list length lives on the device: fixed grid, no host sync)
         SearchArgs h = args;
