@@ -128,6 +128,11 @@ int kmer_b200_count_batch_device(kmer_b200_index *index, const uint8_t *d_q_rank
 uint64_t kmer_b200_result_n_queries(const kmer_b200_result *r);
 uint64_t kmer_b200_result_n_positions(const kmer_b200_result *r);
 int kmer_b200_result_on_device(const kmer_b200_result *r);
+/* Device-resident results only (else NULL): a device array u32[1 + n_queries]; element 0 = number n of queries the
+ * count pass found hits for, elements 1..n = their ids in no particular order. A listed query can still have an
+ * empty result (sharded search: the whole-text presence rule is applied after the count pass). Lets a caller that
+ * merges per-shard results touch only the queries that have something to merge. */
+const uint32_t *kmer_b200_result_hit_queries(const kmer_b200_result *r);
 const uint64_t *kmer_b200_result_offsets(const kmer_b200_result *r);   /* [Q+1] */
 const uint32_t *kmer_b200_result_positions(const kmer_b200_result *r); /* [offsets[Q]], NULL if count-only */
 const uint8_t *kmer_b200_result_status(const kmer_b200_result *r);     /* [Q] */

@@ -137,6 +137,11 @@ class DeviceResult:
     def status(self):
         return _DevArray(self.status_ptr, self.n_queries, "|u1", self)
 
+    def hit_queries(self):
+        """int32 view of [n, id_1 .. id_n, ...]: the queries the count pass found hits for (unordered), or None."""
+        ptr = self._L.kmer_b200_result_hit_queries(self._r) or 0
+        return _DevArray(ptr, self.n_queries + 1, "<i4", self) if ptr else None
+
     def free(self):
         if self._r:
             self._L.kmer_b200_result_free(self._r)

@@ -64,6 +64,7 @@ SYMBOLS = {
     "kmer_b200_result_n_queries": (C.c_uint64, [C.c_void_p]),
     "kmer_b200_result_n_positions": (C.c_uint64, [C.c_void_p]),
     "kmer_b200_result_on_device": (C.c_int, [C.c_void_p]),
+    "kmer_b200_result_hit_queries": (C.c_void_p, [C.c_void_p]),
     "kmer_b200_result_offsets": (C.c_void_p, [C.c_void_p]),
     "kmer_b200_result_positions": (C.c_void_p, [C.c_void_p]),
     "kmer_b200_result_status": (C.c_void_p, [C.c_void_p]),

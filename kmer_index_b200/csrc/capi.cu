@@ -190,6 +190,7 @@ struct kmer_b200_result {
     uint64_t *offsets = nullptr;
     uint32_t *positions = nullptr;
     uint8_t *status = nullptr;
+    uint32_t *hit_queries = nullptr;  // device results: [0] = n, [1..n] = ids of the queries the count pass found hits for
     size_t cap_offsets = 0, cap_positions = 0, cap_status = 0;  // host buffers: byte capacities
     bool positions_pageable = false;  // very large position lists live in plain malloc memory
 };
@@ -926,6 +927,8 @@ int search_finish(PendingSearch *p, const uint32_t *d_present4_global, SearchFla
             dev_free(ix, d_tmp);
         }
     }
+    res->hit_queries = p->d_hits;  // stays with the result (the sharded merge works from it)
+    p->d_hits = nullptr;
     p->release();
     e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -1433,6 +1436,7 @@ int kmer_b200_create_from_text(const char *text, uint64_t n, const uint8_t *lut2
 uint64_t kmer_b200_result_n_queries(const kmer_b200_result *r) { return r ? r->n_queries : 0; }
 uint64_t kmer_b200_result_n_positions(const kmer_b200_result *r) { return r ? r->n_positions : 0; }
 int kmer_b200_result_on_device(const kmer_b200_result *r) { return r && r->on_device; }
+const uint32_t *kmer_b200_result_hit_queries(const kmer_b200_result *r) { return (r && r->on_device) ? r->hit_queries : nullptr; }
 const uint64_t *kmer_b200_result_offsets(const kmer_b200_result *r) { return r ? r->offsets : nullptr; }
 const uint32_t *kmer_b200_result_positions(const kmer_b200_result *r) { return r ? r->positions : nullptr; }
 const uint8_t *kmer_b200_result_status(const kmer_b200_result *r) { return r ? r->status : nullptr; }
@@ -1445,6 +1449,7 @@ void kmer_b200_result_free(kmer_b200_result *r) {
         dev_free(ix, r->offsets);
         dev_free(ix, r->positions);
         dev_free(ix, r->status);
+        dev_free(ix, r->hit_queries);
     } else {
         pinned_put(r->offsets, r->cap_offsets);
         if (r->positions_pageable)

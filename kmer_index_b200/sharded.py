@@ -80,19 +80,27 @@ def place_shard(final, shard_offsets, shard_positions, write_base):
     final[write_base[q] + (idx - shard_offsets[q])] = shard_positions
 
 
-def merge_to_rank0(offsets, positions, world: int, rank: int, dist):
+def merge_to_rank0(offsets, positions, world: int, rank: int, dist, hit_ids=None):
     """Gather every shard's (offsets[Q+1], positions) on rank 0 and merge; returns (offsets, positions) on
     rank 0 and (None, None) elsewhere. offsets: int64, positions: a 32-bit integer dtype.
 
     Only queries that have hits on a shard travel: (query id, count) pairs plus the positions. With random
     queries over a k chosen so that sigma^k >~ n almost every per-shard list is empty, so this is a small
-    fraction of the dense count matrix."""
+    fraction of the dense count matrix. `hit_ids` (optional, any order, may contain queries whose list turned out
+    empty): the ids of the queries with hits on this shard, as the count pass lists them
+    (kmer_b200_result_hit_queries) -- without it they are found by scanning all Q counts."""
     import torch
     Q = offsets.numel() - 1
     dev = offsets.device
-    counts = offsets[1:] - offsets[:-1]
-    qids = torch.nonzero(counts).squeeze(1)                      # ascending query ids with >= 1 hit here
-    cnts = counts[qids]
+    if hit_ids is None:
+        counts = offsets[1:] - offsets[:-1]
+        qids = torch.nonzero(counts).squeeze(1)                  # ascending query ids with >= 1 hit here
+        cnts = counts[qids]
+    else:
+        qids = torch.sort(hit_ids.to(torch.int64) & 0xFFFFFFFF).values
+        cnts = offsets[qids + 1] - offsets[qids]
+        keep = cnts > 0
+        qids, cnts = qids[keep], cnts[keep]
     meta = torch.tensor([qids.numel(), positions.numel()], dtype=torch.int64, device=dev)
     all_meta = torch.empty(2 * world, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(all_meta, meta)
@@ -113,13 +121,19 @@ def merge_to_rank0(offsets, positions, world: int, rank: int, dist):
         pos_r = torch.empty(npos, dtype=positions.dtype, device=dev)
         dist.recv(pos_r, src=r)
         shards.append((buf[:nq], buf[nq:], pos_r))
-    total = torch.zeros(Q, dtype=torch.int64, device=dev)
-    for q_r, c_r, _ in shards:
-        total.index_add_(0, q_r, c_r)
-    g_off = torch.zeros(Q + 1, dtype=torch.int64, device=dev)
-    torch.cumsum(total, 0, out=g_off[1:])
+    # global offsets = this shard's own CSR offsets + the other shards' hits in earlier queries: two passes over Q
+    # (a scan and an add); everything else below touches only the queries that have hits somewhere
+    delta = torch.zeros(Q + 1, dtype=torch.int64, device=dev)
+    for q_r, c_r, _ in shards[1:]:
+        if q_r.numel():
+            delta.index_add_(0, q_r + 1, c_r)
+    g_off = torch.cumsum(delta, 0)
+    g_off += offsets
     final = torch.empty(int(g_off[-1].item()), dtype=positions.dtype, device=dev)
-    filled = total.zero_()                                       # reuse: hits of query q already placed
+    for q_r, _, _ in shards[1:]:
+        if q_r.numel():
+            delta[q_r + 1] = 0
+    filled = delta                                               # reuse: hits of query q already placed
     for q_r, c_r, p_r in shards:                                 # rank order == ascending position order
         if p_r.numel() == 0:
             continue
@@ -167,6 +181,16 @@ def _search_shard(ix, q_ptr, off_ptr, Q, max_len, world, dev):
     return ix.search_batch_device_global(q_ptr, off_ptr, Q, max_len, present.data_ptr(), fmt=fmt)
 
 
+def _hit_ids(res, dev):
+    """The ids of the queries the shard's count pass found hits for (device tensor), or None."""
+    import torch
+    listed = res.hit_queries()
+    if listed is None:
+        return None
+    listed = torch.as_tensor(listed, device=dev)
+    return listed[1:1 + int(listed[0].item())]
+
+
 def search_device(ix, q_ptr: int, off_ptr: int, Q: int, max_len: int, world: int, dev, count_only: bool = False) -> int:
     """Whole-job search with queries resident in HBM; returns the total number of hits (on rank 0 when sharded)."""
     import torch
@@ -189,7 +213,7 @@ def search_device(ix, q_ptr: int, off_ptr: int, Q: int, max_len: int, world: int
     offsets = torch.as_tensor(res.offsets(), device=dev)
     positions = (torch.as_tensor(res.positions(), device=dev) if res.n_positions
                  else torch.empty(0, dtype=torch.int32, device=dev))
-    g_off, final = merge_to_rank0(offsets, positions, world, rank, dist)
+    g_off, final = merge_to_rank0(offsets, positions, world, rank, dist, hit_ids=_hit_ids(res, dev))
     hits = int(g_off[-1].item()) if rank == 0 else 0
     if trace:
         ev[2].record()
@@ -248,7 +272,7 @@ def search_host(ix, h_q, h_off, world: int, dev):
     positions = (torch.as_tensor(res.positions(), device=dev) if res.n_positions
                  else torch.empty(0, dtype=torch.int32, device=dev))
     status = torch.as_tensor(res.status(), device=dev)
-    g_off, final = merge_to_rank0(offsets, positions, world, rank, dist)
+    g_off, final = merge_to_rank0(offsets, positions, world, rank, dist, hit_ids=_hit_ids(res, dev))
     h_status = _pinned("status", Q, torch.uint8)
     h_status.copy_(status, non_blocking=True)
     if rank == 0:

@@ -42,7 +42,14 @@ def _worker(rank, world, port, n, halo, out_dir):
     present = torch.from_numpy((counts > 0).astype(np.uint8))
     anywhere = sharded.all_gather_fold(present, world, dist)
     g_off, g_pos = sharded.merge_to_rank0(torch.from_numpy(s_off), torch.from_numpy(s_pos), world, rank, dist)
+    # the same with the hit list the device count pass provides: unordered, as int32, and with some queries
+    # listed whose lists are empty (the presence rule can empty a list after the count pass)
+    listed = np.flatnonzero(counts > 0)
+    extra = np.flatnonzero(counts == 0)[:7]
+    hit_ids = torch.from_numpy(np.random.default_rng(rank).permutation(np.concatenate([listed, extra])).astype(np.int32))
+    h_off, h_pos = sharded.merge_to_rank0(torch.from_numpy(s_off), torch.from_numpy(s_pos), world, rank, dist, hit_ids=hit_ids)
     if rank == 0:
+        assert torch.equal(h_off, g_off) and torch.equal(h_pos, g_pos)
         w_off, w_pos, _ = Oracle.truth(text, q, off)
         ok = (np.array_equal(g_off.numpy().astype(np.uint64), w_off)
               and np.array_equal(g_pos.numpy().astype(np.uint32), w_pos)
