@@ -808,6 +808,8 @@ int search_begin(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off,
     using namespace kb;
     if (mode == UINT32_MAX) mode = ix->cfg.mode;
     if (mode > KMER_B200_MODE_CORRECT) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "unknown mode");
+    // query ids travel as 32-bit values (heavy list, hit list, block indices of the launch)
+    if (Q >= 0xFFFFFFFFull) return fail(KMER_B200_ERR_UNSUPPORTED, "more than 2^32 - 2 queries in one batch: split the batch");
     cudaStream_t st = ix->stream;
     kmer_b200_result *res = new (std::nothrow) kmer_b200_result();
     if (!res) return fail(KMER_B200_ERR_OUT_OF_MEMORY, "host allocation failed");
