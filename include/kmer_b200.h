@@ -161,6 +161,20 @@ int kmer_b200_search_sharded_begin(kmer_b200_index *index, const uint8_t *d_q_ra
                                    uint64_t n_queries, uint64_t max_query_len, uint32_t mode, uint32_t *d_present4,
                                    kmer_b200_pending **out);
 int kmer_b200_search_sharded_finish(kmer_b200_pending *pending, const uint32_t *d_present4_global, kmer_b200_result **out);
+/* Between begin and finish: this shard's per-query hit counts with the whole-text rule applied (u64[Q], valid until
+   finish turns them into offsets) and the list of queries the count pass found hits for (as
+   kmer_b200_result_hit_queries). Lets a shard send its sparse (query id, count) pairs to the merging shard before
+   its own scan and write pass run. Both are device pointers owned by the pending search. */
+int kmer_b200_search_sharded_peek(kmer_b200_pending *pending, const uint32_t *d_present4_global,
+                                  const uint64_t **d_counts_out, const uint32_t **d_hit_queries_out);
+/* Merging on the shard that assembles the result (optional, between begin and finish): add another shard's
+   per-query hit counts -- n (query id, count) pairs, device arrays -- to this shard's counts. d_within_out[i]
+   receives what the count of query d_ids[i] was before the call: with calls made in rank order, the offset of that
+   shard's list inside the query's merged list. After finish, the result's offsets are the merged offsets,
+   n_positions the merged total, this shard's own hits are already in place at the head of every query's range, and
+   the caller copies the other shards' lists to offsets[id] + within. */
+int kmer_b200_search_sharded_add_counts(kmer_b200_pending *pending, const uint32_t *d_present4_global,
+                                        const int64_t *d_ids, const int64_t *d_counts, uint64_t n, int64_t *d_within_out);
 
 /* ---- introspection (parity tests and roofline accounting) */
 typedef struct kmer_b200_element_info {

@@ -335,6 +335,21 @@ class KmerIndex:
         _capi.check(self._L.kmer_b200_search_sharded_finish(pending, C.c_void_p(present4_global_ptr), C.byref(r)))
         return DeviceResult(self._L, r, Q)
 
+    def search_sharded_peek(self, pending, present4_global_ptr: int, Q: int):
+        """(counts, hit list) of a pending sharded search as device array views: int64[Q] per-query counts with the
+        whole-text rule applied, int32[1 + Q] hit list ([0] = n). Valid until search_sharded_finish."""
+        c, h = C.c_void_p(), C.c_void_p()
+        _capi.check(self._L.kmer_b200_search_sharded_peek(pending, C.c_void_p(present4_global_ptr), C.byref(c), C.byref(h)))
+        return _DevArray(c.value, Q, "<i8", self), _DevArray(h.value, Q + 1, "<i4", self)
+
+    def search_sharded_add_counts(self, pending, present4_global_ptr: int, ids_ptr: int, counts_ptr: int, n: int,
+                                  within_ptr: int) -> None:
+        """Between begin and finish on the merging shard: counts[ids] += counts of another shard (int64 device
+        arrays); within receives the previous counts. Raises KmerB200Error(code -5) when the batch needs the
+        segment sort (then merge after finish instead)."""
+        _capi.check(self._L.kmer_b200_search_sharded_add_counts(pending, C.c_void_p(present4_global_ptr), C.c_void_p(ids_ptr),
+                                                                C.c_void_p(counts_ptr), n, C.c_void_p(within_ptr)))
+
     # -- introspection
     def element_info(self, e: int) -> _capi.ElementInfo:
         info = _capi.ElementInfo()

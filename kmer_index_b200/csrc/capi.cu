@@ -787,6 +787,8 @@ struct PendingSearch {
     uint64_t *d_block_sums = nullptr;
     uint32_t *d_heavy = nullptr;  // [0] = count, [1..Q] = ids of queries with long candidate lists
     uint32_t *d_hits = nullptr;   // [0] = count, [1..Q] = ids of queries with hits (what the write pass visits)
+    bool presence_applied = false;  // deferred mode: the whole-text rule has been applied to the counts
+    bool merge_checked = false;     // add_counts: the batch has no segment that the sort pass would have to visit
     void release() {
         dev_free(ix, d_hits);
         d_hits = nullptr;
@@ -867,6 +869,32 @@ int search_begin(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off,
     return KMER_B200_OK;
 }
 
+// deferred mode: the whole-text presence rule (kmer_index.hpp:216-227, :234 -> :119) applied to the counts of the
+// count pass, once the flags of all shards are known
+void apply_presence_rule(PendingSearch *p, const uint32_t *d_present4_global) {
+    kmer_b200_index *ix = p->ix;
+    kb::SearchArgs &a = p->args;
+    ix->prof.begin(K_SEARCH_PRESENCE, 9.0 * a.n_queries);
+    kb::launch_finalize_deferred(p->res->offsets, p->res->status, p->d_defer, d_present4_global, a.n_queries, ix->stream);
+    ix->prof.end();
+    a.present4 = nullptr;
+    a.defer = nullptr;
+    a.present_global4 = d_present4_global;  // the write pass applies the same rule
+    p->presence_applied = true;
+}
+
+// counts[ids[i]] += add[i]; within[i] = what the count was before (the offset of that shard's list inside the
+// query's merged list when shards are added in rank order)
+__global__ void add_counts_kernel(uint64_t *__restrict__ counts, const int64_t *__restrict__ ids,
+                                  const int64_t *__restrict__ add, uint64_t n, uint64_t n_queries,
+                                  int64_t *__restrict__ within) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t q = (uint64_t)ids[i];
+    if (q >= n_queries) return;
+    within[i] = (int64_t)atomicAdd(reinterpret_cast<unsigned long long *>(counts + q), (unsigned long long)add[i]);
+}
+
 // [deferred: apply the whole-text presence rule] -> scan -> write pass -> segment sort
 int search_finish(PendingSearch *p, const uint32_t *d_present4_global, SearchFlavor flavor, kmer_b200_result **out) {
     using namespace kb;
@@ -881,14 +909,9 @@ int search_finish(PendingSearch *p, const uint32_t *d_present4_global, SearchFla
         p->res = nullptr;
         return code;
     };
-    if (p->d_defer) {
+    if (p->d_defer && !p->presence_applied) {
         if (!d_present4_global) return bail(fail(KMER_B200_ERR_INVALID_ARGUMENT, "missing global presence flags"));
-        ix->prof.begin(K_SEARCH_PRESENCE, 9.0 * Q);
-        launch_finalize_deferred(res->offsets, res->status, p->d_defer, d_present4_global, Q, st);
-        ix->prof.end();
-        a.present4 = nullptr;
-        a.defer = nullptr;
-        a.present_global4 = d_present4_global;  // the write pass applies the same rule
+        apply_presence_rule(p, d_present4_global);
     }
     ix->prof.begin(K_OFFSETS_SCAN, 3.0 * 8 * Q, 3);
     launch_offsets_scan(res->offsets, Q, p->d_block_sums, st);
@@ -1178,6 +1201,46 @@ int kmer_b200_search_sharded_finish(kmer_b200_pending *h, const uint32_t *d_pres
     int s = search_finish(&h->p, d_present4_global, kFlavorFull, out);
     delete h;
     return s;
+}
+
+int kmer_b200_search_sharded_peek(kmer_b200_pending *h, const uint32_t *d_present4_global, const uint64_t **d_counts_out,
+                                  const uint32_t **d_hit_queries_out) {
+    if (!h || !d_present4_global || !d_counts_out || !d_hit_queries_out)
+        return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
+    kmer_b200_index *ix = h->p.ix;
+    DeviceGuard guard(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    if (h->p.d_defer && !h->p.presence_applied) apply_presence_rule(&h->p, d_present4_global);
+    *d_counts_out = h->p.res->offsets;  // per-query counts until finish turns them into offsets
+    *d_hit_queries_out = h->p.d_hits;
+    return KMER_B200_OK;
+}
+
+int kmer_b200_search_sharded_add_counts(kmer_b200_pending *h, const uint32_t *d_present4_global, const int64_t *d_ids,
+                                        const int64_t *d_counts, uint64_t n, int64_t *d_within_out) {
+    if (!h || !d_present4_global || (n && (!d_ids || !d_counts || !d_within_out)))
+        return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
+    kmer_b200_index *ix = h->p.ix;
+    DeviceGuard guard(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    if (!h->p.merge_checked) {
+        // results that still need the segment sort (sub-k slabs without an auxiliary element) are sorted over
+        // [offsets[q], offsets[q + 1]), which must then hold this shard's hits only: the caller merges afterwards
+        uint32_t n_unsorted = 0;
+        cudaError_t e = cudaMemcpyAsync(&n_unsorted, ix->d_flags + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ix->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
+        if (e != cudaSuccess) return fail(KMER_B200_ERR_CUDA, std::string("add_counts: ") + cudaGetErrorString(e));
+        if (n_unsorted != 0)
+            return fail(KMER_B200_ERR_UNSUPPORTED, "this batch needs the segment sort: merge after kmer_b200_search_sharded_finish");
+        h->p.merge_checked = true;
+    }
+    if (h->p.d_defer && !h->p.presence_applied) apply_presence_rule(&h->p, d_present4_global);
+    if (n)
+        add_counts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ix->stream>>>(h->p.res->offsets, d_ids, d_counts, n,
+                                                                               h->p.args.n_queries, d_within_out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(KMER_B200_ERR_CUDA, std::string("add_counts: ") + cudaGetErrorString(e));
+    return KMER_B200_OK;
 }
 
 int kmer_b200_presence_batch_device(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off, uint64_t Q,

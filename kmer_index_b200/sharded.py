@@ -80,70 +80,116 @@ def place_shard(final, shard_offsets, shard_positions, write_base):
     final[write_base[q] + (idx - shard_offsets[q])] = shard_positions
 
 
-def merge_to_rank0(offsets, positions, world: int, rank: int, dist, hit_ids=None):
-    """Gather every shard's (offsets[Q+1], positions) on rank 0 and merge; returns (offsets, positions) on
-    rank 0 and (None, None) elsewhere. offsets: int64, positions: a 32-bit integer dtype.
-
-    Only queries that have hits on a shard travel: (query id, count) pairs plus the positions. With random
-    queries over a k chosen so that sigma^k >~ n almost every per-shard list is empty, so this is a small
-    fraction of the dense count matrix. `hit_ids` (optional, any order, may contain queries whose list turned out
-    empty): the ids of the queries with hits on this shard, as the count pass lists them
+def sparse_lists(offsets, hit_ids=None):
+    """(ascending ids of the queries with hits, their counts) of one shard's CSR offsets. `hit_ids` (optional, any
+    order, may contain queries whose list turned out empty): the ids as the count pass lists them
     (kmer_b200_result_hit_queries) -- without it they are found by scanning all Q counts."""
     import torch
-    Q = offsets.numel() - 1
-    dev = offsets.device
     if hit_ids is None:
         counts = offsets[1:] - offsets[:-1]
-        qids = torch.nonzero(counts).squeeze(1)                  # ascending query ids with >= 1 hit here
-        cnts = counts[qids]
-    else:
-        qids = torch.sort(hit_ids.to(torch.int64) & 0xFFFFFFFF).values
-        cnts = offsets[qids + 1] - offsets[qids]
-        keep = cnts > 0
-        qids, cnts = qids[keep], cnts[keep]
-    meta = torch.tensor([qids.numel(), positions.numel()], dtype=torch.int64, device=dev)
+        qids = torch.nonzero(counts).squeeze(1)
+        return qids, counts[qids]
+    qids = torch.sort(hit_ids.to(torch.int64) & 0xFFFFFFFF).values
+    cnts = offsets[qids + 1] - offsets[qids]
+    keep = cnts > 0
+    return qids[keep], cnts[keep]
+
+
+def collect_counts_on_rank0(qids, cnts, world: int, rank: int, dist, dev):
+    """Phase 1 of the exchange: only queries that have hits on a shard travel, as (query id, count) pairs. Rank 0
+    returns [(ids, counts, number of positions)] for ranks 1..world-1, the other ranks return None."""
+    import torch
+    meta = torch.stack([torch.tensor(qids.numel(), dtype=torch.int64, device=dev), cnts.sum().to(torch.int64)])
     all_meta = torch.empty(2 * world, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(all_meta, meta)
     all_meta = all_meta.view(world, 2).cpu()
     if rank != 0:
         if qids.numel():
             dist.send(torch.cat([qids, cnts]), dst=0)
-            dist.send(positions, dst=0)
-        return None, None
-    shards = [(qids, cnts, positions)]
+        return None
+    lists = []
     for r in range(1, world):
         nq, npos = int(all_meta[r, 0]), int(all_meta[r, 1])
         if nq == 0:
-            shards.append((qids[:0], cnts[:0], positions[:0]))
+            lists.append((qids[:0], cnts[:0], 0))
             continue
         buf = torch.empty(2 * nq, dtype=torch.int64, device=dev)
         dist.recv(buf, src=r)
-        pos_r = torch.empty(npos, dtype=positions.dtype, device=dev)
-        dist.recv(pos_r, src=r)
-        shards.append((buf[:nq], buf[nq:], pos_r))
+        lists.append((buf[:nq], buf[nq:], npos))
+    return lists
+
+
+def collect_positions_on_rank0(positions, lists, world: int, rank: int, dist):
+    """Phase 2: the positions behind the pairs of phase 1 (a shard's lists back to back, ascending query id).
+    Rank 0 returns [(ids, counts, positions)]."""
+    import torch
+    if rank != 0:
+        if positions.numel():
+            dist.send(positions, dst=0)
+        return None
+    others = []
+    for r, (q_r, c_r, npos) in enumerate(lists, start=1):
+        pos_r = torch.empty(npos, dtype=positions.dtype, device=positions.device)
+        if npos:
+            dist.recv(pos_r, src=r)
+        others.append((q_r, c_r, pos_r))
+    return others
+
+
+def collect_on_rank0(qids, cnts, positions, world: int, rank: int, dist):
+    """Both phases back to back."""
+    lists = collect_counts_on_rank0(qids, cnts, world, rank, dist, positions.device)
+    return collect_positions_on_rank0(positions, lists, world, rank, dist)
+
+
+def place_lists(final, starts, cnts, payload):
+    """final[starts[i] + j] = j-th element of list i, the lists lying back to back in `payload`."""
+    import torch
+    if payload.numel() == 0:
+        return
+    dev = payload.device
+    seg_off = torch.cumsum(cnts, 0) - cnts
+    seg = torch.repeat_interleave(torch.arange(cnts.numel(), device=dev), cnts)
+    idx = torch.arange(payload.numel(), dtype=torch.int64, device=dev)
+    final[starts[seg] + (idx - seg_off[seg])] = payload
+
+
+def merge_lists(offsets, positions, own, others):
+    """Rank 0: this shard's full CSR (offsets[Q+1], positions) + the other shards' sparse lists -> merged CSR.
+    Shards are disjoint ascending position ranges, so a query's merged list is the concatenation in rank order."""
+    import torch
+    Q = offsets.numel() - 1
+    dev = offsets.device
     # global offsets = this shard's own CSR offsets + the other shards' hits in earlier queries: two passes over Q
-    # (a scan and an add); everything else below touches only the queries that have hits somewhere
+    # (a scan and an add); everything else touches only the queries that have hits somewhere
     delta = torch.zeros(Q + 1, dtype=torch.int64, device=dev)
-    for q_r, c_r, _ in shards[1:]:
+    for q_r, c_r, _ in others:
         if q_r.numel():
             delta.index_add_(0, q_r + 1, c_r)
     g_off = torch.cumsum(delta, 0)
     g_off += offsets
     final = torch.empty(int(g_off[-1].item()), dtype=positions.dtype, device=dev)
-    for q_r, _, _ in shards[1:]:
+    for q_r, _, _ in others:
         if q_r.numel():
             delta[q_r + 1] = 0
     filled = delta                                               # reuse: hits of query q already placed
-    for q_r, c_r, p_r in shards:                                 # rank order == ascending position order
+    for q_r, c_r, p_r in [(own[0], own[1], positions)] + list(others):   # rank order == ascending position order
         if p_r.numel() == 0:
             continue
         start = g_off[q_r] + filled[q_r]
         filled.index_add_(0, q_r, c_r)
-        seg_off = torch.cumsum(c_r, 0) - c_r
-        seg = torch.repeat_interleave(torch.arange(q_r.numel(), device=dev), c_r)
-        idx = torch.arange(p_r.numel(), dtype=torch.int64, device=dev)
-        final[start[seg] + (idx - seg_off[seg])] = p_r
+        place_lists(final, start, c_r, p_r)
     return g_off, final
+
+
+def merge_to_rank0(offsets, positions, world: int, rank: int, dist, hit_ids=None):
+    """Gather every shard's (offsets[Q+1], positions) on rank 0 and merge; returns (offsets, positions) on
+    rank 0 and (None, None) elsewhere. offsets: int64, positions: a 32-bit integer dtype."""
+    qids, cnts = sparse_lists(offsets, hit_ids)
+    others = collect_on_rank0(qids, cnts, positions, world, rank, dist)
+    if rank != 0:
+        return None, None
+    return merge_lists(offsets, positions, (qids, cnts), others)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -191,6 +237,83 @@ def _hit_ids(res, dev):
     return listed[1:1 + int(listed[0].item())]
 
 
+def search_merged(ix, q_ptr: int, off_ptr: int, Q: int, max_len: int, world: int, dev, trace=None):
+    """Sharded search of a device-resident batch with the merge on rank 0. Returns (res, offsets, positions):
+    `res` is this shard's DeviceResult (keep it alive while the tensors are used, then free() it); offsets /
+    positions are the MERGED CSR on rank 0 (None elsewhere).
+
+    Fused form (<= 8 indexed parts per query, <= 15 shards): count pass -> all-reduce of the presence flags ->
+    ranks > 0 finish and send their sparse lists -> rank 0 adds their counts to its own BEFORE its offsets scan
+    (kmer_b200_search_sharded_add_counts), so its scan yields the merged offsets, its write pass lands its own hits
+    in place, and only the other shards' lists are copied. Otherwise (or when the batch needs the segment sort):
+    every shard finishes on its own and rank 0 merges the finished CSRs."""
+    import torch
+    import torch.distributed as dist
+    from . import KmerB200Error
+    rank = dist.get_rank()
+    max_parts = max(1, max_len // min(ix.ks))
+    fused = max_parts <= 8 and world <= 15
+
+    def finished(res):
+        offsets = torch.as_tensor(res.offsets(), device=dev)
+        positions = (torch.as_tensor(res.positions(), device=dev) if res.n_positions
+                     else torch.empty(0, dtype=torch.int32, device=dev))
+        return offsets, positions
+
+    if not fused:
+        res = _search_shard(ix, q_ptr, off_ptr, Q, max_len, world, dev)
+        if trace:
+            trace()
+        offsets, positions = finished(res)
+        g_off, final = merge_to_rank0(offsets, positions, world, rank, dist, hit_ids=_hit_ids(res, dev))
+        return res, g_off, final
+
+    present = torch.empty(Q, dtype=torch.int32, device=dev)
+    pending = ix.search_sharded_begin(q_ptr, off_ptr, Q, max_len, present.data_ptr())
+    dist.all_reduce(present, op=dist.ReduceOp.SUM)   # nibble per part: SUM over <= 15 shards acts as OR
+    if rank != 0:
+        # the sparse counts leave before this shard's own scan and write pass, the positions after them
+        counts, listed = ix.search_sharded_peek(pending, present.data_ptr(), Q)
+        counts, listed = torch.as_tensor(counts, device=dev), torch.as_tensor(listed, device=dev)
+        qids = torch.sort(listed[1:1 + int(listed[0].item())].to(torch.int64) & 0xFFFFFFFF).values
+        cnts = counts[qids]
+        keep = cnts > 0
+        qids, cnts = qids[keep], cnts[keep]
+        collect_counts_on_rank0(qids, cnts, world, rank, dist, dev)
+        res = ix.search_sharded_finish(pending, present.data_ptr(), Q)
+        if trace:
+            trace()
+        _offsets, positions = finished(res)
+        collect_positions_on_rank0(positions, None, world, rank, dist)
+        return res, None, None
+    empty64 = torch.empty(0, dtype=torch.int64, device=dev)
+    lists = collect_counts_on_rank0(empty64, empty64, world, rank, dist, dev)
+    within = []
+    try:
+        for q_r, c_r, _ in lists:                        # rank order
+            w = torch.empty(q_r.numel(), dtype=torch.int64, device=dev)
+            q_c, c_c = q_r.contiguous(), c_r.contiguous()
+            ix.search_sharded_add_counts(pending, present.data_ptr(), q_c.data_ptr(), c_c.data_ptr(), q_c.numel(),
+                                         w.data_ptr())
+            within.append(w)
+    except KmerB200Error as e:
+        if e.code != -5 or within:
+            raise
+        within = None   # the batch needs the segment sort over this shard's own lists: merge the finished CSRs
+    res = ix.search_sharded_finish(pending, present.data_ptr(), Q)
+    if trace:
+        trace()
+    offsets, positions = finished(res)
+    others = collect_positions_on_rank0(positions, lists, world, rank, dist)
+    if within is None:
+        g_off, final = merge_lists(offsets, positions, sparse_lists(offsets, _hit_ids(res, dev)), others)
+        return res, g_off, final
+    # offsets and n_positions are the merged ones and this shard's own hits are in place
+    for (q_r, c_r, p_r), w in zip(others, within):
+        place_lists(positions, offsets[q_r] + w, c_r, p_r)
+    return res, offsets, positions
+
+
 def search_device(ix, q_ptr: int, off_ptr: int, Q: int, max_len: int, world: int, dev, count_only: bool = False) -> int:
     """Whole-job search with queries resident in HBM; returns the total number of hits (on rank 0 when sharded)."""
     import torch
@@ -207,13 +330,8 @@ def search_device(ix, q_ptr: int, off_ptr: int, Q: int, max_len: int, world: int
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if trace else None
     if trace:
         ev[0].record()
-    res = _search_shard(ix, q_ptr, off_ptr, Q, max_len, world, dev)
-    if trace:
-        ev[1].record()
-    offsets = torch.as_tensor(res.offsets(), device=dev)
-    positions = (torch.as_tensor(res.positions(), device=dev) if res.n_positions
-                 else torch.empty(0, dtype=torch.int32, device=dev))
-    g_off, final = merge_to_rank0(offsets, positions, world, rank, dist, hit_ids=_hit_ids(res, dev))
+    res, g_off, _final = search_merged(ix, q_ptr, off_ptr, Q, max_len, world, dev,
+                                       trace=(lambda: ev[1].record()) if trace else None)
     hits = int(g_off[-1].item()) if rank == 0 else 0
     if trace:
         ev[2].record()
@@ -267,12 +385,8 @@ def search_host(ix, h_q, h_off, world: int, dev):
     d_q = _upload_sliced(h_q, world, rank, dev, dist)
     d_off = _upload_sliced(h_off, world, rank, dev, dist)
     max_len = int((d_off[1:] - d_off[:-1]).max().item()) if Q else 0
-    res = _search_shard(ix, d_q.data_ptr(), d_off.data_ptr(), Q, max_len, world, dev)
-    offsets = torch.as_tensor(res.offsets(), device=dev)
-    positions = (torch.as_tensor(res.positions(), device=dev) if res.n_positions
-                 else torch.empty(0, dtype=torch.int32, device=dev))
+    res, g_off, final = search_merged(ix, d_q.data_ptr(), d_off.data_ptr(), Q, max_len, world, dev)
     status = torch.as_tensor(res.status(), device=dev)
-    g_off, final = merge_to_rank0(offsets, positions, world, rank, dist, hit_ids=_hit_ids(res, dev))
     h_status = _pinned("status", Q, torch.uint8)
     h_status.copy_(status, non_blocking=True)
     if rank == 0:

@@ -211,6 +211,88 @@ def test_sharded_search_emulated_on_one_gpu(kb, oracle_mod, sigma, ks, n, m_lo, 
     assert want[1].size > 0
 
 
+@pytest.mark.parametrize("sigma,ks,n,m_lo,m_hi,world", [(4, [16], 400_000, 16, 64, 2), (4, [5, 7, 9, 11, 13], 200_000, 4, 40, 3),
+                                                       (27, [12], 200_000, 8, 40, 2), (4, [12], 300_000, 13, 64, 4)])
+def test_sharded_merged_finish_emulated_on_one_gpu(kb, oracle_mod, sigma, ks, n, m_lo, m_hi, world):
+    """Merging inside the finish of shard 0 (kmer_b200_search_sharded_add_counts): the other shards' sparse counts
+    are added before shard 0's offsets scan, its own hits land in place, the other lists are copied behind them.
+    A batch that still needs the segment sort refuses (code -5) and is merged from the finished CSRs instead; the
+    second batch (auxiliary elements built by then) takes the merged path. Both must equal the unsharded result."""
+    import torch
+
+    from kmer_index_b200 import sharded, synth
+    dev = torch.device("cuda", 0)
+    text = synth.random_text(n, sigma, 93)
+    q, off = synth.stress_queries(text, 5000, m_lo, m_hi, sigma, 94)
+    Q = off.size - 1
+    d_q = torch.from_numpy(q).to(dev)
+    d_off = torch.from_numpy(off.view(np.int64)).to(dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    shards = [sharded.shard_range(n, world, r, halo=m_hi - 1) for r in range(world)]
+    idx = [kb.KmerIndex(text[s.begin:s.begin + s.length], sigma, ks, shard_begin=s.begin, n_total=n, halo=s.halo,
+                        stream=stream or None) for s in shards]
+    with oracle_mod.Oracle(text, sigma, ks) as o:
+        want = o.search(q, off)
+    assert want[1].size > 0
+    took_merged_path = False
+    try:
+        for attempt in range(2):
+            masks = [torch.zeros(Q, dtype=torch.int32, device=dev) for _ in idx]
+            pending = [ix.search_sharded_begin(d_q.data_ptr(), d_off.data_ptr(), Q, m_hi, m.data_ptr())
+                       for ix, m in zip(idx, masks)]
+            torch.cuda.synchronize()
+            present = torch.stack(masks).sum(0).to(torch.int32)
+            others, keep = [], []
+            for r in range(1, world):
+                # the sparse counts are available before the shard's own scan and write pass
+                pc, pl = idx[r].search_sharded_peek(pending[r], present.data_ptr(), Q)
+                pc, pl = torch.as_tensor(pc, device=dev), torch.as_tensor(pl, device=dev)
+                early_q = torch.sort(pl[1:1 + int(pl[0].item())].to(torch.int64) & 0xFFFFFFFF).values
+                early_c = pc[early_q].clone()
+                early_q, early_c = early_q[early_c > 0], early_c[early_c > 0]
+                res = idx[r].search_sharded_finish(pending[r], present.data_ptr(), Q)
+                torch.cuda.synchronize()
+                o_r = torch.as_tensor(res.offsets(), device=dev)
+                p_r = (torch.as_tensor(res.positions(), device=dev).clone() if res.n_positions
+                       else torch.empty(0, dtype=torch.int32, device=dev))
+                q_r, c_r = sharded.sparse_lists(o_r, sharded._hit_ids(res, dev))
+                assert torch.equal(q_r, early_q) and torch.equal(c_r, early_c)
+                others.append((q_r.clone(), c_r.clone(), p_r))
+                res.free()
+            within = []
+            try:
+                for q_r, c_r, _ in others:
+                    w = torch.empty(q_r.numel(), dtype=torch.int64, device=dev)
+                    idx[0].search_sharded_add_counts(pending[0], present.data_ptr(), q_r.data_ptr(), c_r.data_ptr(),
+                                                     q_r.numel(), w.data_ptr())
+                    within.append(w)
+                merged = True
+            except kb.KmerB200Error as e:
+                assert e.code == -5 and not within
+                merged = False
+            res0 = idx[0].search_sharded_finish(pending[0], present.data_ptr(), Q)
+            torch.cuda.synchronize()
+            offsets = torch.as_tensor(res0.offsets(), device=dev)
+            positions = (torch.as_tensor(res0.positions(), device=dev) if res0.n_positions
+                         else torch.empty(0, dtype=torch.int32, device=dev))
+            if merged:
+                took_merged_path = True
+                for (q_r, c_r, p_r), w in zip(others, within):
+                    sharded.place_lists(positions, offsets[q_r] + w, c_r, p_r)
+                g_off, final = offsets, positions
+            else:
+                g_off, final = sharded.merge_lists(offsets, positions, sharded.sparse_lists(offsets, sharded._hit_ids(res0, dev)),
+                                                   others)
+            got = (g_off.cpu().numpy().astype(np.uint64), final.cpu().numpy().view(np.uint32),
+                   torch.as_tensor(res0.status(), device=dev).cpu().numpy())
+            res0.free()
+            assert_results_equal(got, want, label=f"merged finish x{world} {ks} attempt {attempt} merged={merged}")
+    finally:
+        for ix in idx:
+            ix.close()
+    assert took_merged_path
+
+
 @pytest.mark.parametrize("sigma,ks", [(4, [12]), (4, [5, 7, 9, 11, 13]), (15, [8]), (4, [20])])
 def test_heavy_buckets_take_the_warp_path(kb, oracle_mod, sigma, ks):
     """A text with one enormous bucket (a long constant run): the index-wide average bucket is ~1, so queries get
