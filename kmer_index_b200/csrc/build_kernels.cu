@@ -79,12 +79,26 @@ struct TextSource {  // key(i) = hash of the k-mer starting at symbol i; value(i
         const uint32_t step = text.bits >> 1;
         const bool pow2 = text.sigma == (1u << text.bits);
         const uint32_t down = 64 - k * text.bits;
+        // power-of-two alphabet and k * bits <= 32 (dna4 k <= 16): the key is the top of ONE 32-bit field of the
+        // three 32-bit pieces (hi(cur), lo(cur), hi(next)) -- one funnel shift instead of a 64-bit window
+        const bool narrow = pow2 && k * text.bits <= 32;
+        const bool low = sh >= 32;
         uint64_t cur = w[0];
 #pragma unroll
         for (int r = 0; r < kSortItems; ++r) {
             // a valid item's two words are inside the (padded) text; invalid items read nothing
             const bool valid = FULL || (uint32_t)(r * 32) < avail;
             const uint64_t next = valid ? w[r * step + 1] : 0ull;
+            if (narrow) {
+                const uint32_t a = low ? (uint32_t)cur : (uint32_t)(cur >> 32);
+                const uint32_t b = low ? (uint32_t)(next >> 32) : (uint32_t)cur;
+                out[r] = valid ? (KeyT)(__funnelshift_l(b, a, sh) >> (down - 32)) : (KeyT)0;
+                if (r + 1 < kSortItems) {
+                    const bool valid_next = FULL || (uint32_t)((r + 1) * 32) < avail;
+                    cur = step == 1 ? next : (valid_next ? w[(r + 1) * step] : 0ull);
+                }
+                continue;
+            }
             const uint64_t win = sh ? ((cur << sh) | (next >> (64 - sh))) : cur;
             const KeyT kk = pow2 ? (KeyT)(win >> down) : (KeyT)key_from_window(win, k, text.bits, text.sigma);
             out[r] = valid ? kk : (KeyT)0;
