@@ -161,6 +161,9 @@ int kmer_b200_search_sharded_begin(kmer_b200_index *index, const uint8_t *d_q_ra
                                    uint64_t n_queries, uint64_t max_query_len, uint32_t mode, uint32_t *d_present4,
                                    kmer_b200_pending **out);
 int kmer_b200_search_sharded_finish(kmer_b200_pending *pending, const uint32_t *d_present4_global, kmer_b200_result **out);
+/* Gives up a search begun with kmer_b200_search_sharded_begin (e.g. the cross-rank exchange failed): releases its
+   device buffers. finish consumes the handle too; call exactly one of the two. */
+void kmer_b200_search_sharded_abort(kmer_b200_pending *pending);
 /* Between begin and finish: this shard's per-query hit counts with the whole-text rule applied (u64[Q], valid until
    finish turns them into offsets) and the list of queries the count pass found hits for (as
    kmer_b200_result_hit_queries). Lets a shard send its sparse (query id, count) pairs to the merging shard before

@@ -335,6 +335,10 @@ class KmerIndex:
         _capi.check(self._L.kmer_b200_search_sharded_finish(pending, C.c_void_p(present4_global_ptr), C.byref(r)))
         return DeviceResult(self._L, r, Q)
 
+    def search_sharded_abort(self, pending) -> None:
+        """Releases a pending sharded search that will not be finished."""
+        self._L.kmer_b200_search_sharded_abort(pending)
+
     def search_sharded_peek(self, pending, present4_global_ptr: int, Q: int):
         """(counts, hit list) of a pending sharded search as device array views: int64[Q] per-query counts with the
         whole-text rule applied, int32[1 + Q] hit list ([0] = n). Valid until search_sharded_finish."""

@@ -76,6 +76,7 @@ SYMBOLS = {
     "kmer_b200_search_sharded_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
                                                  C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "kmer_b200_search_sharded_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "kmer_b200_search_sharded_abort": (None, [C.c_void_p]),
     "kmer_b200_search_sharded_peek": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "kmer_b200_search_sharded_add_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "kmer_b200_n_elements": (C.c_uint32, [C.c_void_p]),

@@ -1203,6 +1203,18 @@ int kmer_b200_search_sharded_finish(kmer_b200_pending *h, const uint32_t *d_pres
     return s;
 }
 
+void kmer_b200_search_sharded_abort(kmer_b200_pending *h) {
+    if (!h) return;
+    kmer_b200_index *ix = h->p.ix;
+    {
+        DeviceGuard guard(ix->device);
+        std::lock_guard<std::mutex> lock(ix->mu);
+        h->p.release();
+    }
+    kmer_b200_result_free(h->p.res);  // takes the device guard itself
+    delete h;
+}
+
 int kmer_b200_search_sharded_peek(kmer_b200_pending *h, const uint32_t *d_present4_global, const uint64_t **d_counts_out,
                                   const uint32_t **d_hit_queries_out) {
     if (!h || !d_present4_global || !d_counts_out || !d_hit_queries_out)

@@ -270,16 +270,21 @@ def search_merged(ix, q_ptr: int, off_ptr: int, Q: int, max_len: int, world: int
 
     present = torch.empty(Q, dtype=torch.int32, device=dev)
     pending = ix.search_sharded_begin(q_ptr, off_ptr, Q, max_len, present.data_ptr())
-    dist.all_reduce(present, op=dist.ReduceOp.SUM)   # nibble per part: SUM over <= 15 shards acts as OR
+    try:
+        dist.all_reduce(present, op=dist.ReduceOp.SUM)   # nibble per part: SUM over <= 15 shards acts as OR
+        if rank != 0:
+            # the sparse counts leave before this shard's own scan and write pass, the positions after them
+            counts, listed = ix.search_sharded_peek(pending, present.data_ptr(), Q)
+            counts, listed = torch.as_tensor(counts, device=dev), torch.as_tensor(listed, device=dev)
+            qids = torch.sort(listed[1:1 + int(listed[0].item())].to(torch.int64) & 0xFFFFFFFF).values
+            cnts = counts[qids]
+            keep = cnts > 0
+            qids, cnts = qids[keep], cnts[keep]
+            collect_counts_on_rank0(qids, cnts, world, rank, dist, dev)
+    except Exception:
+        ix.search_sharded_abort(pending)   # the exchange failed before the finish: do not leak the pending search
+        raise
     if rank != 0:
-        # the sparse counts leave before this shard's own scan and write pass, the positions after them
-        counts, listed = ix.search_sharded_peek(pending, present.data_ptr(), Q)
-        counts, listed = torch.as_tensor(counts, device=dev), torch.as_tensor(listed, device=dev)
-        qids = torch.sort(listed[1:1 + int(listed[0].item())].to(torch.int64) & 0xFFFFFFFF).values
-        cnts = counts[qids]
-        keep = cnts > 0
-        qids, cnts = qids[keep], cnts[keep]
-        collect_counts_on_rank0(qids, cnts, world, rank, dist, dev)
         res = ix.search_sharded_finish(pending, present.data_ptr(), Q)
         if trace:
             trace()
@@ -287,7 +292,11 @@ def search_merged(ix, q_ptr: int, off_ptr: int, Q: int, max_len: int, world: int
         collect_positions_on_rank0(positions, None, world, rank, dist)
         return res, None, None
     empty64 = torch.empty(0, dtype=torch.int64, device=dev)
-    lists = collect_counts_on_rank0(empty64, empty64, world, rank, dist, dev)
+    try:
+        lists = collect_counts_on_rank0(empty64, empty64, world, rank, dist, dev)
+    except Exception:
+        ix.search_sharded_abort(pending)
+        raise
     within = []
     try:
         for q_r, c_r, _ in lists:                        # rank order
@@ -298,6 +307,7 @@ def search_merged(ix, q_ptr: int, off_ptr: int, Q: int, max_len: int, world: int
             within.append(w)
     except KmerB200Error as e:
         if e.code != -5 or within:
+            ix.search_sharded_abort(pending)
             raise
         within = None   # the batch needs the segment sort over this shard's own lists: merge the finished CSRs
     res = ix.search_sharded_finish(pending, present.data_ptr(), Q)

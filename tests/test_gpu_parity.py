@@ -147,6 +147,16 @@ def test_edge_cases(kb):
         # m > 10000 throws in the reference
         with pytest.raises(ValueError):
             ix.search(np.zeros(10001, np.uint8))
+        # a sharded search that is begun and given up leaves the index usable
+        import torch
+        dq = torch.tensor([0, 1, 2, 1, 2, 3], dtype=torch.uint8, device="cuda")
+        doff = torch.tensor([0, 3, 6], dtype=torch.int64, device="cuda")
+        flags = torch.zeros(2, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()   # the index works on its own stream
+        before = ix.device_bytes
+        ix.search_sharded_abort(ix.search_sharded_begin(dq.data_ptr(), doff.data_ptr(), 2, 3, flags.data_ptr()))
+        assert ix.device_bytes == before
+        assert ix.search(np.array([0, 1, 2], np.uint8)).tolist() == [0, 4]
 
 
 @pytest.mark.parametrize("fmt", [0, 1, "fused"])
