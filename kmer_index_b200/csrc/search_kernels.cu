@@ -2,17 +2,18 @@
 // kmer_index_element::search (kmer_index.hpp:193-346) and kmer_index_result::to_vector
 // (kmer_index_result.hpp:244-260).
 //
-// One warp per query. The warp
+// A group of G lanes per query (G = 1, 2, 4, 8 or 32, chosen per batch). The group
 //   1. packs the query into shared memory (same b-bit MSB-first layout as the text),
 //   2. derives the query's plan from its length and the scheme table (which element(s), which parts),
-//   3. hashes all indexed parts in parallel (one lane per part) and gathers their bucket ranges from the
-//      directory -- the reference's early "part absent => empty result" return and its throw for short
-//      rests are decided here, in the reference's order,
-//   4. walks the seed bucket 32 candidates at a time; every lane checks its candidate's remaining
-//      constraints directly against the packed text (the text is the intersection oracle: position x is
-//      in bucket hash(T[x,x+k)) and in no other, so "p + d is in the bucket of part j" is
-//      "T[p+d, p+d+k) == part j"), and hits are compacted with ballot/popc.
-// Results are produced in two passes (count -> exclusive scan -> write) so the output is an exact CSR.
+//   3. looks the parts it needs up in the directory (one lane per part) -- one loop for every plan; the
+//      reference's early "part absent => empty result" return and its throw for short rests are decided
+//      here, in the reference's order,
+//   4. walks the seed bucket G candidates at a time; every lane checks its candidate's remaining
+//      constraints, a list of (text offset, query offset, length) spans, directly against the packed text
+//      (the text is the intersection oracle: position x is in bucket hash(T[x,x+k)) and in no other, so
+//      "p + d is in the bucket of part j" is "T[p+d, p+d+k) == part j"); hits are compacted with ballot/popc.
+// Results are produced in two passes (count -> exclusive scan -> write) so the output is an exact CSR; the count
+// pass lists the queries that have hits and the write pass visits only those.
 #include <algorithm>
 
 #include "radix.cuh"
@@ -201,7 +202,7 @@ __device__ __forceinline__ bool pack_query_lane(const uint8_t *__restrict__ q_ra
     return (inval & 0x8080808080808080ull) != 0;
 }
 
-// One group of G lanes per query (G = 8 for short queries and short buckets, 32 otherwise): the scalar part
+// One group of G lanes per query (one lane up to 64 symbols ... a full warp for long queries or long buckets): the scalar part
 // of a query (plan, status) costs a warp instruction per group, not per warp, and G/32 more queries are in
 // flight per SM to cover the chain of dependent gathers (offsets -> ranks -> directory -> bucket -> text).
 // Candidate lists longer than this are not walked by a small group: the query is appended to the batch's

@@ -80,3 +80,29 @@ def test_merge_offsets_and_place():
     sharded.place_shard(final, torch.tensor([0, 1, 1, 3]), torch.tensor([10, 30, 31], dtype=torch.int32), base[0])
     sharded.place_shard(final, torch.tensor([0, 0, 3, 4]), torch.tensor([20, 21, 22, 32], dtype=torch.int32), base[1])
     assert final.tolist() == [10, 20, 21, 22, 30, 31, 32]
+
+
+def test_sparse_merge_helpers():
+    """sparse_lists / merge_lists / place_lists without a process group: three shards of a 5-query batch."""
+    import torch
+
+    from kmer_index_b200 import sharded
+    # per-shard CSRs (positions already global and ascending per query; shards own ascending position ranges)
+    off = [torch.tensor([0, 2, 2, 3, 3, 3]), torch.tensor([0, 0, 0, 1, 1, 3]), torch.tensor([0, 1, 1, 1, 1, 2])]
+    pos = [torch.tensor([1, 5, 7], dtype=torch.int32), torch.tensor([12, 14, 19], dtype=torch.int32),
+           torch.tensor([21, 28], dtype=torch.int32)]
+    lists = [sharded.sparse_lists(o) for o in off]
+    assert lists[0][0].tolist() == [0, 2] and lists[0][1].tolist() == [2, 1]
+    # the hit list of the count pass: unordered, int32, may name queries whose list is empty
+    q1, c1 = sharded.sparse_lists(off[1], torch.tensor([4, 1, 2], dtype=torch.int32))
+    assert q1.tolist() == [2, 4] and c1.tolist() == [1, 2]
+    others = [(lists[r][0], lists[r][1], pos[r]) for r in (1, 2)]
+    g_off, final = sharded.merge_lists(off[0], pos[0], lists[0], others)
+    assert g_off.tolist() == [0, 3, 3, 5, 5, 8]
+    assert final.tolist() == [1, 5, 21, 7, 12, 14, 19, 28]
+    # the merged-finish form: offsets already merged, own hits in place, the others placed at offsets[q] + within
+    merged = torch.tensor([1, 5, 0, 7, 0, 0, 0, 0], dtype=torch.int32)
+    within = [torch.tensor([1, 0]), torch.tensor([2, 2])]   # what add_counts returns when called in rank order
+    for (q_r, c_r, p_r), w in zip(others, within):
+        sharded.place_lists(merged, g_off[q_r] + w, c_r, p_r)
+    assert merged.tolist() == final.tolist()
