@@ -787,9 +787,16 @@ struct PendingSearch {
     uint64_t *d_block_sums = nullptr;
     uint32_t *d_heavy = nullptr;  // [0] = count, [1..Q] = ids of queries with long candidate lists
     uint32_t *d_hits = nullptr;   // [0] = count, [1..Q] = ids of queries with hits (what the write pass visits)
+    uint32_t *d_flags = nullptr;  // u32[4] of this search: error bits, unsorted-segment count, u64 mask of sub-k lengths w/o aux
+    uint64_t *h_scratch = nullptr;  // pinned, 8 words: [0] total hits, [3] gathers, [4..5] the flag words
+    size_t h_scratch_cap = 0;
     bool presence_applied = false;  // deferred mode: the whole-text rule has been applied to the counts
     bool merge_checked = false;     // add_counts: the batch has no segment that the sort pass would have to visit
     void release() {
+        dev_free(ix, d_flags);
+        d_flags = nullptr;
+        pinned_put(h_scratch, h_scratch_cap);
+        h_scratch = nullptr;
         dev_free(ix, d_hits);
         d_hits = nullptr;
         dev_free(ix, d_unsorted);
@@ -829,8 +836,10 @@ int search_begin(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off,
     if (dev_alloc(ix, &res->offsets, Q + 1, false) || dev_alloc(ix, &res->status, Q, false) ||
         dev_alloc(ix, &p->d_unsorted, Q, false) || dev_alloc(ix, &p->d_block_sums, offsets_scan_blocks(Q) + 1, false) ||
         (d_present4 && dev_alloc(ix, &p->d_defer, Q, false)) || dev_alloc(ix, &p->d_heavy, Q + 1, false) ||
-        dev_alloc(ix, &p->d_hits, Q + 1, false))
+        dev_alloc(ix, &p->d_hits, Q + 1, false) || dev_alloc(ix, &p->d_flags, 4, false))
         return bail(KMER_B200_ERR_OUT_OF_MEMORY);
+    p->h_scratch = (uint64_t *)pinned_get(8 * sizeof(uint64_t), &p->h_scratch_cap);
+    if (!p->h_scratch) return bail(fail(KMER_B200_ERR_OUT_OF_MEMORY, "pinned host allocation failed"));
     cudaMemsetAsync(p->d_heavy, 0, sizeof(uint32_t), st);
     cudaMemsetAsync(p->d_hits, 0, sizeof(uint32_t), st);
 
@@ -855,11 +864,11 @@ int search_begin(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off,
     a.hits = p->d_hits;
     a.bits = ix->bits;
     a.single_k = ix->ks.size() == 1;
-    a.error_flag = ix->d_flags;
+    a.error_flag = p->d_flags;  // per search: a second search on the handle cannot clobber a pending one's flags
     a.gather_count = ix->cfg.profile >= 2 ? ix->d_gathers : nullptr;  // profile = 2: also count gathered sectors
     if (a.gather_count) cudaMemsetAsync(ix->d_gathers, 0, sizeof(unsigned long long), st);
 
-    cudaMemsetAsync(ix->d_flags, 0, 4 * sizeof(uint32_t), st);
+    cudaMemsetAsync(p->d_flags, 0, 4 * sizeof(uint32_t), st);
     ix->prof.begin(K_SEARCH_COUNT, 0);
     launch_search(a, d_present4 ? (a.gather_count ? kPassCountDeferredAccount : kPassCountDeferred)
                                 : (a.gather_count ? kPassCountAccount : kPassCount), st);
@@ -917,19 +926,21 @@ int search_finish(PendingSearch *p, const uint32_t *d_present4_global, SearchFla
     launch_offsets_scan(res->offsets, Q, p->d_block_sums, st);
     ix->prof.end();
     // total hits + flags back to the host: the one synchronisation point of a search
-    cudaMemcpyAsync(&ix->h_pinned[0], res->offsets + Q, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
-    cudaMemcpyAsync(&ix->h_pinned[4], ix->d_flags, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
-    if (a.gather_count) cudaMemcpyAsync(&ix->h_pinned[3], ix->d_gathers, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
+    uint64_t *hs = p->h_scratch;
+    cudaMemcpyAsync(&hs[0], res->offsets + Q, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&hs[4], p->d_flags, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    if (a.gather_count) cudaMemcpyAsync(&hs[3], ix->d_gathers, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
-    if (a.gather_count) ix->last_gathers = ix->h_pinned[3];
+    if (a.gather_count) ix->last_gathers = hs[3];
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
         cudaGetLastError();
         return bail(fail(KMER_B200_ERR_CUDA, std::string("search (count pass): ") + cudaGetErrorString(e)));
     }
-    const uint64_t total = ix->h_pinned[0];
-    const uint32_t *flags = reinterpret_cast<const uint32_t *>(&ix->h_pinned[4]);
-    const uint64_t want_aux = ix->h_pinned[5];  // flags[2..3]: sub-k query lengths answered by slab enumeration
+    const uint64_t total = hs[0];
+    const uint32_t flag_words[2] = {reinterpret_cast<const uint32_t *>(&hs[4])[0], reinterpret_cast<const uint32_t *>(&hs[4])[1]};
+    const uint32_t *flags = flag_words;
+    const uint64_t want_aux = hs[5];  // flags[2..3]: sub-k query lengths answered by slab enumeration
     if (flags[0] & 1u) return bail(fail(KMER_B200_ERR_INVALID_RANK, "a query contains a rank >= sigma"));
     res->n_positions = total;
     // sub-k lengths seen in this batch get an auxiliary k' = m element (kept for later batches); the write pass
@@ -1086,6 +1097,17 @@ int kmer_b200_load(const char *path, const kmer_b200_config *cfg_in, kmer_b200_i
                 r = fail(KMER_B200_ERR_INVALID_ARGUMENT, "corrupt element record");
                 break;
             }
+            {
+                // everything that drives device indexing is recomputed from (sigma, k, shift) and must agree with the file
+                const uint64_t key_space = fast_pow(h.sigma, (uint8_t)fe.k);
+                const uint32_t key_bits = std::max<uint32_t>(1, bit_length(key_space - 1));
+                if (fe.key_space != key_space || fe.key_bits != key_bits || fe.key_bytes != (key_bits > 32 ? 8u : 4u) ||
+                    fe.shift > key_bits || key_bits > 32 + fe.shift || fe.dir_entries != ((key_space - 1) >> fe.shift) + 2 ||
+                    fe.sort_passes == 0 || fe.sort_passes > 64) {
+                    r = fail(KMER_B200_ERR_INVALID_ARGUMENT, "element record inconsistent with sigma / k / shift");
+                    break;
+                }
+            }
             he.key_bits = fe.key_bits;
             he.sort_passes = fe.sort_passes;
             he.key_bytes = fe.key_bytes;
@@ -1097,6 +1119,15 @@ int kmer_b200_load(const char *path, const kmer_b200_config *cfg_in, kmer_b200_i
             if ((r = read_device_array(ix, f, he.d_keys, fe.n_kmers * fe.key_bytes, h_buf)) != 0) break;
             if ((r = read_device_array(ix, f, he.d_pos, fe.n_kmers * 4, h_buf)) != 0) break;
             if ((r = read_device_array(ix, f, he.d_dir, fe.dir_entries * 4, h_buf)) != 0) break;
+            {
+                uint32_t ends[2] = {1, 0};  // dir[0] must be 0 and the last entry n_kmers (a CSR offset array)
+                cudaMemcpyAsync(&ends[0], he.d_dir, 4, cudaMemcpyDeviceToHost, ix->stream);
+                cudaMemcpyAsync(&ends[1], he.d_dir + fe.dir_entries - 1, 4, cudaMemcpyDeviceToHost, ix->stream);
+                if (cudaStreamSynchronize(ix->stream) != cudaSuccess || ends[0] != 0 || ends[1] != (uint32_t)fe.n_kmers) {
+                    r = fail(KMER_B200_ERR_INVALID_ARGUMENT, "corrupt directory in index file");
+                    break;
+                }
+            }
             he.dev = kb::Element{fe.k, fe.shift, fe.n_kmers, fe.dir_entries, fe.key_space, he.d_dir, he.d_keys, he.d_pos,
                                  fe.key_bytes, 0};
             he.bytes = fe.n_kmers * (4 + fe.key_bytes) + fe.dir_entries * 4;
@@ -1239,7 +1270,7 @@ int kmer_b200_search_sharded_add_counts(kmer_b200_pending *h, const uint32_t *d_
         // results that still need the segment sort (sub-k slabs without an auxiliary element) are sorted over
         // [offsets[q], offsets[q + 1]), which must then hold this shard's hits only: the caller merges afterwards
         uint32_t n_unsorted = 0;
-        cudaError_t e = cudaMemcpyAsync(&n_unsorted, ix->d_flags + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ix->stream);
+        cudaError_t e = cudaMemcpyAsync(&n_unsorted, h->p.d_flags + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ix->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
         if (e != cudaSuccess) return fail(KMER_B200_ERR_CUDA, std::string("add_counts: ") + cudaGetErrorString(e));
         if (n_unsorted != 0)

@@ -226,22 +226,25 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
 // a group of one lane needs no warp collectives: they fold to the lane's own value at compile time
 #define GBALLOT(pred) (G == 1 ? ((pred) ? 1u : 0u) : ((__ballot_sync(gmask, (pred)) >> gshift) & gfull))
 #define GSHFL(v, src) (G == 1 ? (v) : __shfl_sync(gmask, (v), (src), G))
-// hand the query to the heavy launch: count passes enlist it (and report no hits for now), the write pass skips it
-#define HAND_OFF_IF_HEAVY(len)                                                        \
-    if (!HEAVY && G < 32 && a.heavy != nullptr && (len) > (uint64_t)kHeavyCandidates) { \
-        if (PASS == kPassCount && gl == 0) {                                          \
-            a.heavy[1 + atomicAdd(a.heavy, 1u)] = (uint32_t)q;                        \
-            a.counts[q] = 0;                                                          \
-            a.status[q] = KMER_B200_QUERY_OK;                                         \
-            a.unsorted[q] = 0;                                                        \
-        }                                                                             \
-        return;                                                                       \
+// hand the query to the heavy launch: the count pass enlists it (and reports no hits for now) and marks it in
+// unsorted[q] bit 1; the write pass follows that mark (below), never its own candidate count -- the two can differ
+// once an auxiliary element has been built between the passes
+#define HAND_OFF_IF_HEAVY(len)                                                                          \
+    if (PASS == kPassCount && !HEAVY && G < 32 && a.heavy != nullptr && (len) > (uint64_t)kHeavyCandidates) { \
+        if (gl == 0) {                                                                                  \
+            a.heavy[1 + atomicAdd(a.heavy, 1u)] = (uint32_t)q;                                          \
+            a.counts[q] = 0;                                                                            \
+            a.status[q] = KMER_B200_QUERY_OK;                                                           \
+            a.unsorted[q] = 2;                                                                          \
+        }                                                                                               \
+        return;                                                                                         \
     }
 
     uint64_t out_base = 0;
     if (PASS == kPassWrite) {
         out_base = a.counts[q];
         if (a.counts[q + 1] == out_base) return;  // nothing to write (also covers every non-OK status)
+        if (!HEAVY && (a.unsorted[q] & 2)) return;  // the count pass gave it to the heavy launch
     }
 
     const DeviceIndex &ix = *a.index;
@@ -709,9 +712,9 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
         a.counts[q] = n_hits;
         a.status[q] = KMER_B200_QUERY_OK;
         const bool flag = unsorted && n_hits > 1;
-        a.unsorted[q] = flag ? 1 : 0;
+        a.unsorted[q] = (flag ? 1 : 0) | (HEAVY ? 2 : 0);
         if (flag) atomicAdd(a.error_flag + 1, 1u);  // number of segments the sort pass has to visit
-        if (!HEAVY && a.hits != nullptr && n_hits > 0) {
+        if (a.hits != nullptr && n_hits > 0) {
             // the write pass only visits the queries listed here (one atomic per set of lanes arriving together)
             const uint32_t act = __activemask();
             const int leader = __ffs(act) - 1;
@@ -1038,7 +1041,7 @@ __global__ void __launch_bounds__(kSortThreads, 1)
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     for (uint64_t q = blockIdx.x; q < n_queries; q += gridDim.x) {
-        if (!unsorted[q]) continue;
+        if (!(unsorted[q] & 1)) continue;
         const uint64_t seg0 = offsets[q];
         const uint64_t len = offsets[q + 1] - seg0;
         if (len < 2) continue;

@@ -100,6 +100,10 @@ class Oracle(_Base):
             L = C.CDLL(ORACLE_SO)
             L.ko_create.restype = C.c_void_p
             L.ko_create.argtypes = [_u8p, C.c_uint64, C.c_uint32, _u32p, C.c_uint32]
+            L.ko_create_restricted.restype = C.c_void_p
+            L.ko_create_restricted.argtypes = [_u8p, C.c_uint64, C.c_uint32, _u32p, C.c_uint32, _u8p, _u64p, C.c_uint64,
+                                               C.c_uint32]
+            L.ko_restricted_misses.restype = C.c_uint64
             L.ko_destroy.argtypes = [C.c_void_p]
             L.ko_search_batch.restype = C.c_int
             L.ko_search_batch.argtypes = [C.c_void_p, _u8p, _u64p, C.c_uint64, C.c_uint32, _u64p, _u8p,
@@ -125,14 +129,22 @@ class Oracle(_Base):
             cls._lib = L
         return cls._lib
 
-    def __init__(self, text, sigma: int, ks):
+    def __init__(self, text, sigma: int, ks, restrict_to=None, n_threads: int = 0):
+        """restrict_to=(q_ranks, q_offsets): hold only the buckets that batch can ask for (ko_create_restricted) --
+        same answers for that batch, a fraction of the memory; `restricted_misses()` must stay 0."""
         super().__init__()
         L = self.lib()
         self.text = _as_u8(text)
         self.sigma = int(sigma)
         self.ks = [int(k) for k in ks]
         ks_a = np.asarray(self.ks, dtype=np.uint32)
-        self._h = L.ko_create(_ptr(self.text, _u8p), self.text.size, self.sigma, _ptr(ks_a, _u32p), ks_a.size)
+        if restrict_to is None:
+            self._h = L.ko_create(_ptr(self.text, _u8p), self.text.size, self.sigma, _ptr(ks_a, _u32p), ks_a.size)
+        else:
+            q, off = _as_u8(restrict_to[0]), _as_u64(restrict_to[1])
+            self._h = L.ko_create_restricted(_ptr(self.text, _u8p), self.text.size, self.sigma, _ptr(ks_a, _u32p),
+                                             ks_a.size, _ptr(q, _u8p), _ptr(off, _u64p), off.size - 1,
+                                             n_threads or (os.cpu_count() or 1))
         if not self._h:
             raise ValueError(f"oracle: illegal index sigma={sigma} ks={ks} n={self.text.size}")
 
@@ -151,6 +163,11 @@ class Oracle(_Base):
         self.last_ub = (status & 0x80) != 0     # queries on which the reference dereferences end() (UB)
         status &= 0x7F
         return _finish(counts, status, pos, total.value, L.ko_free, keep_positions)
+
+    @classmethod
+    def restricted_misses(cls) -> int:
+        """Lookups (process-wide) that asked a restricted index for a bucket it does not hold; must be 0."""
+        return int(cls.lib().ko_restricted_misses())
 
     def element(self, i: int):
         """(sorted hashes, positions stably sorted by hash) of element i (template order)."""

@@ -79,7 +79,11 @@ typedef struct {
     uint64_t *hashes;  /* sorted ascending, one per k-mer start */
     uint32_t *pos;     /* positions, stably sorted by hash  (== concatenated buckets of _data) */
     uint8_t *last_kmer; /* kmer_index.hpp:87,174 */
+    uint64_t *needed;   /* restricted index only (ko_create_restricted): bit h set <=> bucket h is held completely */
 } ko_element;
+
+/* restricted index: number of at()/range lookups that asked for a bucket the index does not hold (must stay 0) */
+static volatile uint64_t ko_restricted_misses_;
 
 typedef struct {
     uint32_t sigma;
@@ -161,6 +165,8 @@ typedef struct {
 /* kmer_index.hpp:76-84  at(hash): pointer to the bucket or null */
 static int element_at(const ko_element *e, uint64_t hash, ko_bucket *out)
 {
+    if (e->needed && !((e->needed[hash >> 6] >> (hash & 63)) & 1))
+        __atomic_add_fetch(&ko_restricted_misses_, 1, __ATOMIC_RELAXED);
     uint64_t lo = 0, hi = e->n_kmers;
     while (lo < hi) {
         uint64_t mid = lo + (hi - lo) / 2;
@@ -431,6 +437,8 @@ static int element_search(const ko_index *ix, const ko_element *e, const uint8_t
     int st = element_prefix(ix, e, q, (uint32_t)m, &pf);
     if (st != KO_OK)
         return st;
+    if (e->needed && !(((e->needed[pf.lower >> 6] >> (pf.lower & 63)) & 1)))
+        __atomic_add_fetch(&ko_restricted_misses_, 1, __ATOMIC_RELAXED);
     uint64_t lo = lower_bound_hash(e, pf.lower), hi = lower_bound_hash(e, pf.upper);
     if (hi > lo)
         result_push(res, e->pos + lo, hi - lo); /* the buckets of hashes [lower, upper), in hash order */
@@ -613,6 +621,179 @@ ko_index *ko_create(const uint8_t *ranks, uint64_t n, uint32_t sigma, const uint
     return ix;
 }
 
+/* ---------------------------------------------------------------- restricted index (still TEST INFRASTRUCTURE)
+   The same index, holding only the buckets a given query batch can ask for: `_data` restricted to the hashes that
+   index_search() / element_search() pass to at() (kmer_index.hpp:76-84) for these queries, plus the hash ranges of
+   their prefix enumerations (:131-144). Every bucket held is complete (all its positions, ascending), so every
+   lookup the batch makes returns exactly what the full index returns; a lookup of a bucket that is not held is
+   counted in ko_restricted_misses() (tests assert 0). This is what lets a CPU check a 10^6-query sample against
+   the 3 Gbp text of BASELINE config 5: one threaded scan of the text instead of a 36 GB sorted pair array.
+   tests/test_oracle_golden.py pins restricted == full on every golden fixture. */
+typedef struct {
+    const uint8_t *text;
+    uint64_t lo, hi; /* k-mer start positions [lo, hi) */
+    uint32_t k, sigma;
+    const uint64_t *needed;
+    uint64_t *hashes; /* thread-local output */
+    uint32_t *pos;
+    uint64_t n, cap;
+} ko_scan_job;
+
+static void *scan_worker(void *arg)
+{
+    ko_scan_job *j = (ko_scan_job *)arg;
+    if (j->lo >= j->hi)
+        return NULL;
+    const uint64_t top = ko_fast_pow(j->sigma, (uint8_t)(j->k - 1));
+    uint64_t h = ko_hash(j->text + j->lo, j->k, j->sigma);
+    for (uint64_t p = j->lo;; ++p) {
+        if ((j->needed[h >> 6] >> (h & 63)) & 1) {
+            if (j->n == j->cap) {
+                j->cap = j->cap ? 2 * j->cap : 4096;
+                j->hashes = (uint64_t *)realloc(j->hashes, j->cap * sizeof(uint64_t));
+                j->pos = (uint32_t *)realloc(j->pos, j->cap * sizeof(uint32_t));
+            }
+            j->hashes[j->n] = h;
+            j->pos[j->n++] = (uint32_t)p;
+        }
+        if (p + 1 >= j->hi)
+            break;
+        h = (h - (uint64_t)j->text[p] * top) * j->sigma + j->text[p + j->k];
+    }
+    return NULL;
+}
+
+static void mark_needed(ko_element *e, uint64_t key_space, uint64_t lo, uint64_t hi)
+{
+    if (hi > key_space)
+        hi = key_space;
+    for (uint64_t h = lo; h < hi; ++h)
+        e->needed[h >> 6] |= 1ull << (h & 63);
+}
+
+ko_index *ko_create_restricted(const uint8_t *ranks, uint64_t n, uint32_t sigma, const uint32_t *ks, uint32_t n_ks,
+                               const uint8_t *q, const uint64_t *q_off, uint64_t Q, uint32_t n_threads)
+{
+    if (n_ks == 0 || n_ks > 64)
+        return NULL;
+    for (uint32_t i = 0; i < n_ks; ++i) {
+        if (ks[i] == 0 || ks[i] > 63 || n < ks[i] || !((double)ks[i] < 64.0 / log2((double)sigma)))
+            return NULL;
+        if (pow((double)sigma, (double)ks[i]) > 68719476736.0) /* the bucket bitmap: at most 2^36 bits = 8 GB */
+            return NULL;
+    }
+    if (n_threads == 0)
+        n_threads = 1;
+    if (n_threads > 256)
+        n_threads = 256;
+    ko_index *ix = (ko_index *)calloc(1, sizeof(ko_index));
+    ix->sigma = sigma;
+    ix->n = n;
+    ix->text = (uint8_t *)malloc(n);
+    memcpy(ix->text, ranks, n);
+    ix->n_ks = n_ks;
+    memcpy(ix->ks, ks, n_ks * sizeof(uint32_t));
+    ix->elems = (ko_element *)calloc(n_ks, sizeof(ko_element));
+    choose_search_scheme(ix);
+    uint64_t key_space[64];
+    for (uint32_t i = 0; i < n_ks; ++i) {
+        ko_element *e = &ix->elems[i];
+        e->k = ks[i];
+        key_space[i] = ko_fast_pow(sigma, (uint8_t)ks[i]);
+        e->needed = (uint64_t *)calloc(key_space[i] / 64 + 2, sizeof(uint64_t));
+        e->last_kmer = (uint8_t *)malloc(ks[i]);
+        memcpy(e->last_kmer, ix->text + n - ks[i], ks[i]);
+        if (!e->needed)
+            return NULL;
+    }
+    /* the lookups of index_search (kmer_index.hpp:505-558) / element_search (:193-346), without their early returns */
+    for (uint64_t i = 0; i < Q; ++i) {
+        const uint8_t *qq = q + q_off[i];
+        const uint64_t m = q_off[i + 1] - q_off[i];
+        if (m == 0 || m >= KO_QUERY_SIZE_RANGE)
+            continue;
+        const uint8_t *S = ix->sum_ks + ix->sum_off[m];
+        const uint64_t s = ix->sum_off[m + 1] - ix->sum_off[m];
+        if (!ix->use_multi[m] || n_ks == 1) {
+            uint32_t ei = 0;
+            for (uint32_t c = 0; c < n_ks; ++c)
+                if (ks[c] == S[0])
+                    ei = c;
+            ko_element *e = &ix->elems[ei];
+            const uint64_t k = e->k;
+            if (m >= k) { /* :198-205, :216-227: at(hash) of every full part */
+                for (uint64_t j = 0; j < m / k; ++j) {
+                    const uint64_t h = ko_hash(qq + j * k, (uint32_t)k, sigma);
+                    mark_needed(e, key_space[ei], h, h + 1);
+                }
+            } else if (!((double)ko_fast_pow(sigma, (uint8_t)(k - m)) > 1e7)) { /* :342-345 -> :131-144 */
+                uint64_t lower = 0;
+                for (uint64_t c = 0; c < m; ++c)
+                    lower += (uint64_t)qq[c] * ko_fast_pow(sigma, (uint8_t)(k - c - 1));
+                mark_needed(e, key_space[ei], lower, lower + ko_fast_pow(sigma, (uint8_t)(k - m)));
+            }
+        } else { /* :516-527, `last_k = current_k` */
+            uint64_t last_k = 0;
+            for (uint64_t c = 0; c < s; ++c) {
+                uint32_t ei = 0;
+                for (uint32_t d = 0; d < n_ks; ++d)
+                    if (ks[d] == S[c])
+                        ei = d;
+                if (last_k + S[c] <= m) {
+                    const uint64_t h = ko_hash(qq + last_k, S[c], sigma);
+                    mark_needed(&ix->elems[ei], key_space[ei], h, h + 1);
+                }
+                last_k = S[c];
+            }
+        }
+    }
+    /* create (:154-179) restricted to the needed buckets: threaded scan, chunks concatenated in text order */
+    for (uint32_t i = 0; i < n_ks; ++i) {
+        ko_element *e = &ix->elems[i];
+        const uint64_t n_kmers = n - e->k + 1;
+        ko_scan_job jobs[256];
+        pthread_t th[256];
+        for (uint32_t t = 0; t < n_threads; ++t) {
+            memset(&jobs[t], 0, sizeof(ko_scan_job));
+            jobs[t].text = ix->text;
+            jobs[t].lo = n_kmers * t / n_threads;
+            jobs[t].hi = n_kmers * (t + 1) / n_threads;
+            jobs[t].k = e->k;
+            jobs[t].sigma = sigma;
+            jobs[t].needed = e->needed;
+            pthread_create(&th[t], NULL, scan_worker, &jobs[t]);
+        }
+        uint64_t kept = 0;
+        for (uint32_t t = 0; t < n_threads; ++t) {
+            pthread_join(th[t], NULL);
+            kept += jobs[t].n;
+        }
+        e->n_kmers = kept;
+        e->hashes = (uint64_t *)malloc((kept ? kept : 1) * sizeof(uint64_t));
+        e->pos = (uint32_t *)malloc((kept ? kept : 1) * sizeof(uint32_t));
+        uint64_t o = 0, max_key = 0;
+        for (uint32_t t = 0; t < n_threads; ++t) {
+            if (jobs[t].n) {
+                memcpy(e->hashes + o, jobs[t].hashes, jobs[t].n * sizeof(uint64_t));
+                memcpy(e->pos + o, jobs[t].pos, jobs[t].n * sizeof(uint32_t));
+            }
+            o += jobs[t].n;
+            free(jobs[t].hashes);
+            free(jobs[t].pos);
+        }
+        for (uint64_t c = 0; c < kept; ++c)
+            if (e->hashes[c] > max_key)
+                max_key = e->hashes[c];
+        sort_pairs(e->hashes, e->pos, kept, max_key);
+    }
+    return ix;
+}
+
+uint64_t ko_restricted_misses(void)
+{
+    return ko_restricted_misses_;
+}
+
 void ko_destroy(ko_index *ix)
 {
     if (!ix)
@@ -621,6 +802,7 @@ void ko_destroy(ko_index *ix)
         free(ix->elems[i].hashes);
         free(ix->elems[i].pos);
         free(ix->elems[i].last_kmer);
+        free(ix->elems[i].needed);
     }
     free(ix->elems);
     free(ix->text);

@@ -222,7 +222,8 @@ def test_sharded_search_emulated_on_one_gpu(kb, oracle_mod, sigma, ks, n, m_lo, 
 
 
 @pytest.mark.parametrize("sigma,ks,n,m_lo,m_hi,world", [(4, [16], 400_000, 16, 64, 2), (4, [5, 7, 9, 11, 13], 200_000, 4, 40, 3),
-                                                       (27, [12], 200_000, 8, 40, 2), (4, [12], 300_000, 13, 64, 4)])
+                                                       (27, [12], 200_000, 8, 40, 2), (4, [12], 300_000, 13, 64, 4),
+                                                       (4, [12], 150_001, 13, 48, 2), (4, [5, 7, 9, 11, 13], 150_001, 4, 40, 3)])
 def test_sharded_merged_finish_emulated_on_one_gpu(kb, oracle_mod, sigma, ks, n, m_lo, m_hi, world):
     """Merging inside the finish of shard 0 (kmer_b200_search_sharded_add_counts): the other shards' sparse counts
     are added before shard 0's offsets scan, its own hits land in place, the other lists are copied behind them.
@@ -234,6 +235,13 @@ def test_sharded_merged_finish_emulated_on_one_gpu(kb, oracle_mod, sigma, ks, n,
     dev = torch.device("cuda", 0)
     text = synth.random_text(n, sigma, 93)
     q, off = synth.stress_queries(text, 5000, m_lo, m_hi, sigma, 94)
+    if n == 150_001:
+        # a 70 000-symbol constant run: queries inside it have candidate lists far beyond 2048 entries and are
+        # answered by the warp-per-query ("heavy") launch -- they must reach the hit list the merge works from
+        text[20_000:90_000] = 0
+        lens = (off[1:] - off[:-1]).astype(np.int64)
+        for i in range(0, 900, 3):
+            q[int(off[i]):int(off[i]) + int(lens[i])] = 0
     Q = off.size - 1
     d_q = torch.from_numpy(q).to(dev)
     d_off = torch.from_numpy(off.view(np.int64)).to(dev)

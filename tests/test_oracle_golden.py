@@ -64,3 +64,35 @@ def test_oracle_matches_live_reference(oracle_mod, sigma, ks, mmax):
         got = o.search(q, off)
         want = r.search(q, off)
         assert_results_equal(got, want, skip=o.last_ub, label=f"sigma={sigma} ks={ks}")
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_restricted_oracle_equals_full_on_golden(oracle_mod, name):
+    """ko_create_restricted (the index holding only the buckets a batch can ask for -- what makes the 3 Gbp
+    config-5 check affordable on a CPU) answers every golden batch exactly like the full restatement and like
+    the fixture generated from the compiled reference; no lookup may reach a bucket it does not hold."""
+    g = load_golden(name)
+    sigma, ks = int(g["sigma"]), g["ks"].tolist()
+    if any(float(sigma) ** k > 2.0 ** 36 for k in ks):
+        with pytest.raises(ValueError):
+            oracle_mod.Oracle(g["text"], sigma, ks, restrict_to=(g["q"], g["q_off"]))
+        return
+    before = oracle_mod.Oracle.restricted_misses()
+    with oracle_mod.Oracle(g["text"], sigma, ks, restrict_to=(g["q"], g["q_off"]), n_threads=3) as o:
+        got = o.search(g["q"], g["q_off"])
+        assert np.array_equal(o.last_ub, g["ub"].astype(bool))
+    assert oracle_mod.Oracle.restricted_misses() == before
+    assert_results_equal(got, (g["r_off"], g["r_pos"], g["r_status"]), skip=g["ub"].astype(bool), label=name)
+
+
+def test_restricted_oracle_equals_full_on_random_text(oracle_mod):
+    from kmer_index_b200 import synth
+    text = synth.random_text(3_000_000, 4, 77)
+    q, off = synth.stress_queries(text, 4000, 10, 64, 4, 78)
+    with oracle_mod.Oracle(text, 4, [16]) as full, oracle_mod.Oracle(text, 4, [16], restrict_to=(q, off)) as part:
+        want = full.search(q, off)
+        got = part.search(q, off)
+        assert part.element(0)[0].size < full.element(0)[0].size // 50
+    assert want[1].size > 1000
+    assert_results_equal(got, want, label="restricted vs full")
+    assert oracle_mod.Oracle.restricted_misses() == 0
