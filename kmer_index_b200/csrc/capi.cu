@@ -338,18 +338,15 @@ void build_scheme(SchemeHost *ix) {
     }
 }
 
-int build_element(kmer_b200_index *ix, uint32_t k, HostElement &he, bool auxiliary = false) {
+// Sorters: both leave he.d_keys (sorted hashes) and he.d_pos (positions stably sorted by hash).
+// (a) tiled LSD sort: per-tile histograms + column scan + scatter per pass, (hash, position) in separate arrays.
+//     Used for 64-bit hashes and k-mers wider than one packed window.
+int sort_element_tiled(kmer_b200_index *ix, uint32_t k, HostElement &he, uint32_t digit_bits) {
     using namespace kb;
     cudaStream_t st = ix->stream;
     Profiler &pf = ix->prof;
     const uint64_t n_kmers = ix->n - k + 1;
-    const uint64_t key_space = fast_pow(ix->sigma, (uint8_t)k);
-    he.key_bits = std::max<uint32_t>(1, bit_length(key_space - 1));
-    uint32_t digit_bits = kRadixBitsMax;
-    if (const char *env = std::getenv("KMER_B200_DIGIT_BITS")) {  // tuning experiment: narrower digits, more passes
-        const int b = std::atoi(env);
-        if (b >= 4 && b <= kRadixBitsMax) digit_bits = (uint32_t)b;
-    }
+    const uint32_t key_bytes = he.key_bytes;
     he.sort_passes = (he.key_bits + digit_bits - 1) / digit_bits;
     const uint32_t bits_per_pass = (he.key_bits + he.sort_passes - 1) / he.sort_passes;
     const uint32_t mask = (1u << bits_per_pass) - 1;
@@ -357,10 +354,6 @@ int build_element(kmer_b200_index *ix, uint32_t k, HostElement &he, bool auxilia
     const uint32_t n_chunks = (n_tiles + scan_chunk_tiles() - 1) / scan_chunk_tiles();
     const double text_bytes = (double)n_kmers * ix->bits / 8.0;
     const double hist_bytes = (double)n_tiles * kRadix * 4;
-
-    // 32-bit hashes while sigma^k <= 2^32 (all BASELINE configs), 64-bit above
-    const uint32_t key_bytes = he.key_bits > 32 ? 8 : 4;
-    he.key_bytes = key_bytes;
     void *keys[2] = {nullptr, nullptr};
     uint32_t *vals[2] = {nullptr, nullptr};
     uint32_t *tile_hist = nullptr, *chunk_sums = nullptr;
@@ -410,6 +403,113 @@ int build_element(kmer_b200_index *ix, uint32_t k, HostElement &he, bool auxilia
     dev_free(ix, chunk_sums);
     he.d_keys = keys[cur];
     he.d_pos = vals[cur];
+    return 0;
+}
+
+// (b) single-sweep sort (onesweep.cu): 32-bit hashes. All digit histograms up front from the text, then one scatter
+//     kernel per pass (bulk-copy tile loads, decoupled look-back, 8-byte (hash, position) records between passes).
+int sort_element_onesweep(kmer_b200_index *ix, uint32_t k, HostElement &he, uint32_t digit_bits) {
+    using namespace kb;
+    cudaStream_t st = ix->stream;
+    Profiler &pf = ix->prof;
+    const uint64_t n_kmers = ix->n - k + 1;
+    PackedText text{ix->d_text, ix->n, ix->bits, ix->sigma};
+    // digit width: equal shares of the hash bits; for a power-of-two alphabet a whole number of symbols, so that a
+    // digit is a c-mer of the text and one c-mer histogram yields every pass's digit histogram
+    const bool pow2 = ix->sigma == (1u << ix->bits);
+    uint32_t passes = (he.key_bits + digit_bits - 1) / digit_bits;
+    uint32_t w = (he.key_bits + passes - 1) / passes;
+    if (pow2) {
+        w = (w + ix->bits - 1) / ix->bits * ix->bits;
+        if (w > (uint32_t)kRadixBitsMax) w = kRadixBitsMax / ix->bits * ix->bits;
+        passes = (he.key_bits + w - 1) / w;
+    }
+    if (passes > 8) return fail(KMER_B200_ERR_UNSUPPORTED, "more than 8 digit passes");
+    he.sort_passes = passes;
+    const uint32_t mask = (1u << w) - 1;
+    const uint32_t n_tiles = (uint32_t)((n_kmers + sort_tile_size() - 1) / sort_tile_size());
+    const double text_bytes = (double)n_kmers * ix->bits / 8.0;
+    const double status_bytes = 2.0 * (double)n_tiles * kRadix * 8;  // aggregate + inclusive word per (tile, digit)
+
+    uint64_t *status = nullptr;
+    uint32_t *scratch = nullptr;  // [0, 2048): histogram scratch, [2048, 4096): digit bases, [4096, 4104): tile counters
+    uint2 *pairs[2] = {nullptr, nullptr};
+    uint32_t *keys = nullptr, *pos = nullptr;
+    auto cleanup = [&](int code) {
+        dev_free(ix, status);
+        dev_free(ix, scratch);
+        dev_free(ix, pairs[0]);
+        dev_free(ix, pairs[1]);
+        if (code != 0) {
+            dev_free(ix, keys);
+            dev_free(ix, pos);
+        }
+        return code;
+    };
+    if (dev_alloc(ix, &status, (uint64_t)n_tiles * kRadix, false) || dev_alloc(ix, &scratch, 4096 + 8, false))
+        return cleanup(KMER_B200_ERR_OUT_OF_MEMORY);
+    cudaMemsetAsync(status, 0, (uint64_t)n_tiles * kRadix * sizeof(uint64_t), st);
+    cudaMemsetAsync(scratch + 4096, 0, 8 * sizeof(uint32_t), st);
+    uint32_t *digit_base = scratch + 2048, *counters = scratch + 4096;
+
+    pf.begin(K_HIST_TEXT, text_bytes, 2);
+    launch_digit_histograms(text, k, n_kmers, passes, w, he.key_bits, pow2, scratch, digit_base, st);
+    pf.end();
+
+    int cur = -1;
+    for (uint32_t p = 0; p < passes; ++p) {
+        const bool last = p + 1 == passes;
+        uint2 *out_pairs = nullptr;
+        if (last) {
+            // the buffer that is neither read nor written by this pass goes first: the peak stays at two pair buffers
+            if (cur >= 0 && pairs[cur ^ 1]) {
+                dev_free(ix, pairs[cur ^ 1]);
+                pairs[cur ^ 1] = nullptr;
+            }
+            if (dev_alloc(ix, &pos, n_kmers, true) || dev_alloc(ix, &keys, n_kmers, true)) return cleanup(KMER_B200_ERR_OUT_OF_MEMORY);
+        } else {
+            const int nxt = cur < 0 ? 0 : cur ^ 1;
+            if (!pairs[nxt] && dev_alloc(ix, &pairs[nxt], n_kmers + 2, false)) return cleanup(KMER_B200_ERR_OUT_OF_MEMORY);
+            out_pairs = pairs[nxt];
+        }
+        const double out_bytes = last ? 8.0 * n_kmers : 8.0 * n_kmers;
+        if (p == 0) {
+            pf.begin(K_SCATTER_TEXT, text_bytes + out_bytes + status_bytes);
+            launch_onesweep_pass(&text, k, nullptr, n_kmers, 0, mask, 1, digit_base, status, counters, out_pairs, keys, pos, st);
+        } else {
+            pf.begin(K_SCATTER_PAIRS, 8.0 * n_kmers + out_bytes + status_bytes);
+            launch_onesweep_pass(nullptr, k, pairs[cur], n_kmers, p * w, mask, p + 1, digit_base + p * kRadix, status, counters + p,
+                                 out_pairs, keys, pos, st);
+        }
+        pf.end();
+        if (!last) cur = cur < 0 ? 0 : cur ^ 1;
+    }
+    KB_CUDA(cudaGetLastError());
+    he.d_keys = keys;
+    he.d_pos = pos;
+    return cleanup(0);
+}
+
+int build_element(kmer_b200_index *ix, uint32_t k, HostElement &he, bool auxiliary = false) {
+    using namespace kb;
+    cudaStream_t st = ix->stream;
+    Profiler &pf = ix->prof;
+    const uint64_t n_kmers = ix->n - k + 1;
+    const uint64_t key_space = fast_pow(ix->sigma, (uint8_t)k);
+    he.key_bits = std::max<uint32_t>(1, bit_length(key_space - 1));
+    uint32_t digit_bits = kRadixBitsMax;
+    if (const char *env = std::getenv("KMER_B200_DIGIT_BITS")) {  // tuning experiment: narrower digits, more passes
+        const int b = std::atoi(env);
+        if (b >= 4 && b <= kRadixBitsMax) digit_bits = (uint32_t)b;
+    }
+    // 32-bit hashes while sigma^k <= 2^32 (all BASELINE configs), 64-bit above
+    const uint32_t key_bytes = he.key_bits > 32 ? 8 : 4;
+    he.key_bytes = key_bytes;
+    if (key_bytes == 4 && k * ix->bits <= 64 && !std::getenv("KMER_B200_LEGACY_SORT")) {
+        KB_TRY(sort_element_onesweep(ix, k, he, digit_bits));
+    } else {
+        KB_TRY(sort_element_tiled(ix, k, he, digit_bits));
+    }
 
     // directory: dense (shift 0) while the key space is at most ~4x the number of k-mers
     uint32_t shift = 0;
@@ -427,6 +527,13 @@ int build_element(kmer_b200_index *ix, uint32_t k, HostElement &he, bool auxilia
     launch_directory_fill(he.d_keys, key_bytes, n_kmers, shift, dir_entries, he.d_dir, st);
     pf.end();
     KB_CUDA(cudaGetLastError());
+    if (shift == 0) {
+        // dense directory: at(h) is [dir[h], dir[h + 1]) and nothing reads the sorted hashes again (the one place that
+        // wants a hash of an entry, the sub-k slab check, recomputes it from the text): 4 bytes per k-mer of HBM back
+        dev_free(ix, (uint8_t *)he.d_keys);
+        he.d_keys = nullptr;
+        ix->device_bytes -= n_kmers * key_bytes;
+    }
 
     he.dev.k = k;
     he.dev.shift = shift;
@@ -437,7 +544,7 @@ int build_element(kmer_b200_index *ix, uint32_t k, HostElement &he, bool auxilia
     he.dev.keys = he.d_keys;
     he.dev.pos = he.d_pos;
     he.dev.key_bytes = key_bytes;
-    he.bytes = n_kmers * (sizeof(uint32_t) + key_bytes) + dir_entries * sizeof(uint32_t);
+    he.bytes = n_kmers * (sizeof(uint32_t) + (he.d_keys ? key_bytes : 0)) + dir_entries * sizeof(uint32_t);
     if (!auxiliary)
         ix->max_avg_bucket = std::max(ix->max_avg_bucket, (double)n_kmers / (double)std::min<uint64_t>(key_space, n_kmers));
     return 0;
@@ -684,10 +791,10 @@ struct FileHeader {
     uint32_t ks[kb::kMaxElements];
 };
 struct FileElement {
-    uint32_t k, shift, key_bits, sort_passes, key_bytes, pad;
+    uint32_t k, shift, key_bits, sort_passes, key_bytes, has_keys;
     uint64_t n_kmers, dir_entries, key_space;
 };
-constexpr uint32_t kFileVersion = 1;
+constexpr uint32_t kFileVersion = 2;  // 2: an element's sorted hashes are optional (FileElement::has_keys)
 constexpr size_t kIoChunk = 64u << 20;
 
 int write_device_array(kmer_b200_index *ix, FILE *f, const void *d_ptr, uint64_t bytes, void *h_buf) {
@@ -986,6 +1093,12 @@ int search_device_impl(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *
     return search_finish(&p, nullptr, flavor, out);
 }
 
+__global__ void hashes_from_text_kernel(kb::PackedText text, uint32_t k, const uint32_t *__restrict__ pos, uint64_t n,
+                                        uint64_t *__restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = kb::key_at(text.words, (uint64_t)pos[i], k, text.bits, text.sigma);
+}
+
 __global__ void max_len_kernel(const uint64_t *__restrict__ off, uint64_t Q, unsigned long long *out) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long m = 0;
@@ -1046,10 +1159,10 @@ int kmer_b200_save(kmer_b200_index *ix, const char *path) {
     if (s == 0) s = write_device_array(ix, f, ix->d_text, ix->text_words * 8, h_buf);
     for (uint32_t i = 0; s == 0 && i < h.n_ks; ++i) {
         const HostElement &he = ix->elems[i];
-        FileElement fe{he.dev.k, he.dev.shift, he.key_bits, he.sort_passes, he.key_bytes, 0, he.dev.n_kmers,
+        FileElement fe{he.dev.k, he.dev.shift, he.key_bits, he.sort_passes, he.key_bytes, he.d_keys ? 1u : 0u, he.dev.n_kmers,
                        he.dev.dir_entries, he.dev.key_space};
         if (fwrite(&fe, sizeof(fe), 1, f) != 1) s = fail(KMER_B200_ERR_INVALID_ARGUMENT, "short write");
-        if (s == 0) s = write_device_array(ix, f, he.d_keys, he.dev.n_kmers * he.key_bytes, h_buf);
+        if (s == 0 && he.d_keys) s = write_device_array(ix, f, he.d_keys, he.dev.n_kmers * he.key_bytes, h_buf);
         if (s == 0) s = write_device_array(ix, f, he.d_pos, he.dev.n_kmers * 4, h_buf);
         if (s == 0) s = write_device_array(ix, f, he.d_dir, he.dev.dir_entries * 4, h_buf);
     }
@@ -1103,7 +1216,7 @@ int kmer_b200_load(const char *path, const kmer_b200_config *cfg_in, kmer_b200_i
                 const uint32_t key_bits = std::max<uint32_t>(1, bit_length(key_space - 1));
                 if (fe.key_space != key_space || fe.key_bits != key_bits || fe.key_bytes != (key_bits > 32 ? 8u : 4u) ||
                     fe.shift > key_bits || key_bits > 32 + fe.shift || fe.dir_entries != ((key_space - 1) >> fe.shift) + 2 ||
-                    fe.sort_passes == 0 || fe.sort_passes > 64) {
+                    fe.sort_passes == 0 || fe.sort_passes > 64 || fe.has_keys > 1 || (fe.shift != 0 && !fe.has_keys)) {
                     r = fail(KMER_B200_ERR_INVALID_ARGUMENT, "element record inconsistent with sigma / k / shift");
                     break;
                 }
@@ -1112,11 +1225,11 @@ int kmer_b200_load(const char *path, const kmer_b200_config *cfg_in, kmer_b200_i
             he.sort_passes = fe.sort_passes;
             he.key_bytes = fe.key_bytes;
             uint8_t *keys = nullptr;
-            if ((r = dev_alloc(ix, &keys, fe.n_kmers * fe.key_bytes, true)) != 0) break;
+            if (fe.has_keys && (r = dev_alloc(ix, &keys, fe.n_kmers * fe.key_bytes, true)) != 0) break;
             he.d_keys = keys;
             if ((r = dev_alloc(ix, &he.d_pos, fe.n_kmers, true)) != 0) break;
             if ((r = dev_alloc(ix, &he.d_dir, fe.dir_entries, true)) != 0) break;
-            if ((r = read_device_array(ix, f, he.d_keys, fe.n_kmers * fe.key_bytes, h_buf)) != 0) break;
+            if (fe.has_keys && (r = read_device_array(ix, f, he.d_keys, fe.n_kmers * fe.key_bytes, h_buf)) != 0) break;
             if ((r = read_device_array(ix, f, he.d_pos, fe.n_kmers * 4, h_buf)) != 0) break;
             if ((r = read_device_array(ix, f, he.d_dir, fe.dir_entries * 4, h_buf)) != 0) break;
             {
@@ -1130,7 +1243,7 @@ int kmer_b200_load(const char *path, const kmer_b200_config *cfg_in, kmer_b200_i
             }
             he.dev = kb::Element{fe.k, fe.shift, fe.n_kmers, fe.dir_entries, fe.key_space, he.d_dir, he.d_keys, he.d_pos,
                                  fe.key_bytes, 0};
-            he.bytes = fe.n_kmers * (4 + fe.key_bytes) + fe.dir_entries * 4;
+            he.bytes = fe.n_kmers * (4 + (fe.has_keys ? fe.key_bytes : 0)) + fe.dir_entries * 4;
             ix->max_avg_bucket = std::max(ix->max_avg_bucket,
                                           (double)fe.n_kmers / (double)std::min<uint64_t>(fe.key_space, fe.n_kmers));
         }
@@ -1402,7 +1515,7 @@ static int search_batch_host_pipelined(kmer_b200_index *ix, const uint8_t *q_ran
         const uint64_t qa = c0[c], qb = c0[c + 1], Qc = qb - qa;
         if (Qc == 0) continue;
         cudaStreamWaitEvent(st, ev_in[c], 0);
-        max_len_kernel<<<(unsigned)std::min<uint64_t>((Qc + 255) / 256, 148 * 8), 256, 0, st>>>(d_off + qa, Qc, d_max + c);
+        max_len_kernel<<<(unsigned)std::min<uint64_t>((Qc + 255) / 256, (uint64_t)kb::device_sm_count() * 8), 256, 0, st>>>(d_off + qa, Qc, d_max + c);
         cudaMemcpyAsync(&ix->h_pinned[2], d_max + c, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
         cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) return cleanup(fail(KMER_B200_ERR_CUDA, std::string("search (H2D): ") + cudaGetErrorString(e)));
@@ -1476,7 +1589,7 @@ static int search_batch_host(kmer_b200_index *ix, const uint8_t *q_ranks, const 
     if (n_sym) KB_CUDA(cudaMemcpyAsync(d_q, q_ranks + q_offsets[0], n_sym, cudaMemcpyHostToDevice, st));
     if (lut256) KB_TRY(translate_on_device(ix, d_q, n_sym, lut256));
     KB_CUDA(cudaMemsetAsync(d_max, 0, sizeof(unsigned long long), st));
-    if (Q) max_len_kernel<<<(unsigned)std::min<uint64_t>((Q + 255) / 256, 148 * 8), 256, 0, st>>>(d_off, Q, d_max);
+    if (Q) max_len_kernel<<<(unsigned)std::min<uint64_t>((Q + 255) / 256, (uint64_t)kb::device_sm_count() * 8), 256, 0, st>>>(d_off, Q, d_max);
     KB_CUDA(cudaMemcpyAsync(&ix->h_pinned[2], d_max, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     KB_CUDA(cudaStreamSynchronize(st));
     const uint64_t max_len = ix->h_pinned[2];
@@ -1598,6 +1711,18 @@ int kmer_b200_element_hashes(kmer_b200_index *ix, uint32_t e, uint64_t *out, uin
     DeviceGuard guard(ix->device);
     const HostElement &he = ix->elems[e];
     const uint64_t n = std::min<uint64_t>(cap, he.dev.n_kmers);
+    if (!he.d_keys) {  // dense directory: the sorted hashes are not kept; recompute them from the text at pos[i]
+        uint64_t *d_tmp = nullptr;
+        KB_TRY(dev_alloc(ix, &d_tmp, n, false));
+        if (n)
+            hashes_from_text_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ix->stream>>>(
+                kb::PackedText{ix->d_text, ix->n, ix->bits, ix->sigma}, he.dev.k, he.d_pos, n, d_tmp);
+        cudaError_t e = cudaMemcpyAsync(out, d_tmp, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ix->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
+        dev_free(ix, d_tmp);
+        if (e != cudaSuccess) return fail(KMER_B200_ERR_CUDA, cudaGetErrorString(e));
+        return KMER_B200_OK;
+    }
     if (he.key_bytes == 8) {
         KB_CUDA(cudaMemcpyAsync(out, he.d_keys, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ix->stream));
         KB_CUDA(cudaStreamSynchronize(ix->stream));

@@ -96,8 +96,9 @@ __device__ __forceinline__ uint64_t key_at(WordPtr words, uint64_t sym, uint32_t
 //   pos[n_kmers]   all k-mer start positions, stably sorted by hash (bucket = run of equal hashes,
 //                  ascending positions inside, as push_back in text order yields, kmer_index.hpp:165)
 //   dir[entries]   dir[j] = number of k-mers with (hash >> shift) < j      (entries = (max_hash >> shift) + 2)
-//   keys[n_kmers]  the sorted hashes (always kept: sub-k slabs and shift > 0 lookups read them);
-//                  32-bit while sigma^k <= 2^32, 64-bit otherwise (then shift > 0: the directory stays <= 2^32)
+//   keys[n_kmers]  the sorted hashes, kept only when the directory is not dense (shift > 0: lookups finish with a
+//                  binary search in them); null for a dense directory -- a hash is then recomputed from the text at
+//                  pos[i] where one is needed. 32-bit while sigma^k <= 2^32, 64-bit otherwise.
 // ---------------------------------------------------------------------------------------------
 struct Element {
     uint32_t k;
@@ -115,6 +116,11 @@ struct Element {
 __device__ __forceinline__ uint64_t element_key(const Element &E, uint64_t i) {
     return E.key_bytes == 8 ? gather64(static_cast<const uint64_t *>(E.keys) + i)
                             : (uint64_t)gather32(static_cast<const uint32_t *>(E.keys) + i);
+}
+// same, for elements that may not hold their hashes (dense directory): recomputed from the text at pos[i]
+__device__ __forceinline__ uint64_t element_key_or_text(const PackedText &T, const Element &E, uint64_t i) {
+    if (E.keys != nullptr) return element_key(E, i);
+    return key_at(T.words, (uint64_t)gather32(E.pos + i), E.k, T.bits, T.sigma);
 }
 
 struct SchemeTables {

@@ -24,6 +24,28 @@ void launch_directory_fill(const void *d_keys, uint32_t key_bytes, uint64_t n_km
                            uint32_t *d_dir, cudaStream_t stream);
 uint32_t sort_tile_size();
 uint32_t scan_chunk_tiles();
+// ---- single-sweep sorter for 32-bit hashes (onesweep.cu)
+// global digit histograms of every pass -> d_digit_base[p][256] (exclusive prefixes); d_hist_scratch: 8 * 256 u32.
+// from_cmers: power-of-two alphabet with w_bits a multiple of the symbol width (one c-mer histogram serves all passes)
+void launch_digit_histograms(const PackedText &text, uint32_t k, uint64_t n_kmers, uint32_t n_passes, uint32_t w_bits,
+                             uint32_t key_bits, bool from_cmers, uint32_t *d_hist_scratch, uint32_t *d_digit_base,
+                             cudaStream_t stream);
+// one scatter pass. text != null: pass 0 (hashes from the packed text, positions generated); else pairs in.
+// d_out_pairs == null: final pass, writes d_out_vals (+ d_out_keys when non-null). d_status: zeroed u64[n_tiles][256]
+// shared by the passes of one sort (tag = pass + 1); d_tile_counter: one zeroed u32 per pass.
+void launch_onesweep_pass(const PackedText *text, uint32_t k, const uint2 *d_in_pairs, uint64_t n, uint32_t shift, uint32_t mask,
+                          uint32_t tag, const uint32_t *d_digit_base, uint64_t *d_status, uint32_t *d_tile_counter,
+                          uint2 *d_out_pairs, uint32_t *d_out_keys, uint32_t *d_out_vals, cudaStream_t stream);
+uint32_t device_sm_count();
+// key-range parts: (hash - lo, position) pairs of the k-mers with hash in [lo, hi), in position order.
+// count -> launch_offsets_scan over the u64 tile counts -> write
+uint32_t filter_tiles(uint64_t n_kmers);
+void launch_owned_count(const PackedText &text, uint32_t k, uint64_t n_kmers, uint64_t lo, uint64_t hi, uint64_t *d_tile_counts,
+                        cudaStream_t stream);
+void launch_owned_write(const PackedText &text, uint32_t k, uint64_t n_kmers, uint64_t lo, uint64_t hi, const uint64_t *d_tile_offsets,
+                        uint2 *d_out, cudaStream_t stream);
+void launch_digit_histograms_pairs(const uint2 *d_pairs, uint64_t n, uint32_t n_passes, uint32_t w_bits, uint32_t *d_hist_scratch,
+                                   uint32_t *d_digit_base, cudaStream_t stream);
 
 // ---- search
 enum SearchPass : int {

@@ -583,7 +583,7 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
         const uint64_t lo_key = key_at(qw, 0, m, T.bits, T.sigma) * width;
         const uint64_t slo = lower_bound_key(E0, lo_key);
         const uint64_t shi = lower_bound_key(E0, lo_key + width);
-        if (shi - slo > 1) unsorted = element_key(E0, slo) != element_key(E0, shi - 1);
+        if (shi - slo > 1) unsorted = element_key_or_text(T, E0, slo) != element_key_or_text(T, E0, shi - 1);
         const bool count_by_range = PASS != kPassWrite && ix.owned == T.n;  // unsharded: every hit is owned
         HAND_OFF_IF_HEAVY(shi - slo)  // same decision in the count and the write pass
         if (count_by_range) n_hits = shi - slo;
@@ -771,7 +771,7 @@ static void launch_search_pgs(const SearchArgs &args, cudaStream_t stream) {
     if (PASS == kPassWrite && args.hits != nullptr) {
         cudaFuncSetAttribute(search_listed_write_kernel<G, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         search_listed_write_kernel<G, SINGLE>
-            <<<(unsigned)std::min<uint64_t>(blocks, 148 * 8 * 2), kSearchThreads, smem, stream>>>(args);
+            <<<(unsigned)std::min<uint64_t>(blocks, (uint64_t)device_sm_count() * 8 * 2), kSearchThreads, smem, stream>>>(args);
     } else {
         search_kernel<PASS, G, SINGLE><<<(unsigned)blocks, kSearchThreads, smem, stream>>>(args);
     }
@@ -781,7 +781,7 @@ static void launch_search_pgs(const SearchArgs &args, cudaStream_t stream) {
         h.q_words = search_q_words(32, args.bits, args.max_len);
         const size_t hsmem = (size_t)(kSearchThreads / 32) * h.q_words * sizeof(uint64_t);
         cudaFuncSetAttribute(search_heavy_kernel<PASS, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem);
-        search_heavy_kernel<PASS, SINGLE><<<148 * 2, kSearchThreads, hsmem, stream>>>(h);
+        search_heavy_kernel<PASS, SINGLE><<<device_sm_count() * 2, kSearchThreads, hsmem, stream>>>(h);
     }
 }
 
@@ -1005,7 +1005,7 @@ __global__ void __launch_bounds__(256) gather_probe_kernel(const uint64_t *__res
 
 void launch_gather_probe(const uint64_t *d_table, uint64_t n_words, uint64_t n_gathers, uint64_t *d_sink,
                          cudaStream_t stream) {
-    gather_probe_kernel<<<148 * 16, 256, 0, stream>>>(d_table, n_words, n_gathers, d_sink);
+    gather_probe_kernel<<<device_sm_count() * 16, 256, 0, stream>>>(d_table, n_words, n_gathers, d_sink);
 }
 
 uint64_t offsets_scan_blocks(uint64_t n_queries) { return (n_queries + kScanBlock - 1) / kScanBlock; }
@@ -1129,7 +1129,7 @@ void launch_segment_sort(uint32_t *d_positions, uint32_t *d_tmp, const uint64_t 
                          uint64_t n_queries, uint32_t key_bits, cudaStream_t stream) {
     if (n_queries == 0) return;
     cudaFuncSetAttribute(segment_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SegSortSmem));
-    const uint64_t blocks = n_queries < 148ull * 64 ? n_queries : 148ull * 64;
+    const uint64_t blocks = n_queries < (uint64_t)device_sm_count() * 64 ? n_queries : (uint64_t)device_sm_count() * 64;
     segment_sort_kernel<<<(unsigned)blocks, kSortThreads, sizeof(SegSortSmem), stream>>>(d_positions, d_tmp, d_offsets,
                                                                                         d_unsorted, n_queries, key_bits);
 }

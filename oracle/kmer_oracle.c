@@ -844,7 +844,11 @@ static void *search_worker(void *arg)
         j->status[i] = (uint8_t)(st | (ko_ub_seen ? KO_UB_FLAG : 0));
         uint32_t *v = NULL;
         uint64_t c = 0;
-        if (st == KO_OK)
+        if (st == KO_OK && !j->keep && r.bypass) {
+            /* count only: a bypass result (exact-k, sub-k) is every element of its buckets (kmer_index_result.hpp:250) */
+            for (uint64_t b = 0; b < r.n_buckets; ++b)
+                c += r.buckets[b].len;
+        } else if (st == KO_OK)
             c = result_to_vector(&r, &v);
         j->counts[i] = c;
         if (j->keep && c) {

@@ -104,23 +104,98 @@ def test_config3_full_text_counts_and_subsample(kb, oracle_mod):
         pytest.skip("needs ~24 GB of host memory for the CPU oracle at this size")
     sigma, ks, n = 4, [5, 7, 9, 11, 13], 100_000_000
     text = synth.random_text(n, sigma, TEXT_SEED)
-    q, off = synth.random_queries(200_000, 4, 40, sigma, QUERY_SEED)
+    q, off = synth.random_queries(1_000_000, 4, 40, sigma, QUERY_SEED)    # the BASELINE batch, all of it
     qs, offs = synth.random_queries(3_000, 6, 40, sigma, QUERY_SEED + 2)       # materialised on both sides
     qp, offp = _planted(text, 20_000, 6, 40, QUERY_SEED + 3)
     with kb.KmerIndex(text, sigma, ks) as ix, oracle_mod.Oracle(text, sigma, ks) as o:
-        got = ix.search_batch(q, off)
+        import torch
+        dev = torch.device("cuda", 0)
+        # all 10^6 queries: per-query count and status from the device count pass (the 1.4e10 positions of the full
+        # batch are 56 GB -- they stay unmaterialised on both sides)
+        d_q = torch.from_numpy(q).to(dev)
+        d_off = torch.from_numpy(off.view(np.int64)).to(dev)
+        torch.cuda.synchronize()
+        res = ix.count_batch_device(d_q.data_ptr(), d_off.data_ptr(), off.size - 1, 40)
+        c_off = torch.as_tensor(res.offsets(), device=dev).cpu().numpy().astype(np.uint64)
+        c_status = torch.as_tensor(res.status(), device=dev).cpu().numpy()
+        res.free()
+        del d_q, d_off
         w_off, _, w_status = o.search(q, off, keep_positions=False)
-        assert np.array_equal(got.status, w_status)
-        assert np.array_equal(got.offsets, w_off)
+        assert np.array_equal(c_status, w_status)
+        assert np.array_equal(c_off, w_off)
+        assert int(w_off[-1]) > 10_000_000_000
+        # the first 2*10^5 of them materialised: same counts, ascending inside every query
+        sub = 200_000
+        got = ix.search_batch(q[:int(off[sub])], off[:sub + 1], copy=False)
+        assert np.array_equal(got.status, w_status[:sub])
+        assert np.array_equal(got.offsets, w_off[:sub + 1])
         pos = got.positions
         # ascending inside every query (sub-k results come from auxiliary elements or the sort kernel)
         d = np.diff(pos.astype(np.int64))
         boundaries = got.offsets[1:-1].astype(np.int64) - 1
         d[boundaries[(boundaries >= 0) & (boundaries < d.size)]] = 1
         assert (d > 0).all()
-        del got, pos, d
+        del pos, d
+        got.free()
         assert_results_equal(ix.search_batch(qs, offs).as_tuple(), o.search(qs, offs), label="config3 subsample")
         assert_results_equal(ix.search_batch(qp, offp).as_tuple(), o.search(qp, offp), label="config3 planted")
+
+
+def test_config5_full_text_sample_bit_exact_vs_oracle(kb, oracle_mod):
+    """kmer_index<dna4,16> over the full 3 Gbp text of config 5 against the CPU restatement on the SAME text, for a
+    10^6-query sample: half BASELINE-random, half windows of the text (every length 16-64, some ending exactly at
+    n), so the defective 53-63 plan and the rest-1..4 THROW rule are exercised with non-empty truth. The oracle holds
+    only the buckets this batch can ask for (ko_create_restricted, pinned to the full restatement on the CPU), which
+    is what makes 3 Gbp affordable on the host: one threaded scan of the text."""
+    import torch
+
+    from kmer_index_b200 import _capi, synth
+    free, _ = torch.cuda.mem_get_info()
+    if free < 100e9:
+        pytest.skip("needs ~100 GB of device memory")
+    if _free_host_gb() < 14:
+        print("SKIPPED: config-5 full-size oracle comparison needs ~14 GB of host memory, have %.1f" % _free_host_gb())
+        pytest.skip("needs ~14 GB of host memory")
+    dev = torch.device("cuda", 0)
+    L = _capi.lib()
+    n, k, m_lo, m_hi = 3_000_000_000, 16, 16, 64
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    sptr = stream.cuda_stream
+    d_text = torch.empty(n, dtype=torch.uint8, device=dev)
+    _capi.check(L.kmer_b200_synth_ranks_device(d_text.data_ptr(), n, 0, 4, TEXT_SEED, sptr))
+    torch.cuda.synchronize()
+    text = d_text.cpu().numpy()
+    assert np.array_equal(text[:4096], synth.random_text(4096, 4, TEXT_SEED))           # device generator == host generator
+    Q = 1_000_000
+    q1, off1 = synth.random_queries(Q // 2, m_lo, m_hi, 4, QUERY_SEED)
+    q2, off2 = _planted(text, Q - Q // 2, m_lo, m_hi, QUERY_SEED + 1)
+    q = np.concatenate([q1, q2])
+    off = np.concatenate([off1, off2[1:] + off1[-1]])
+    lens = (off[1:] - off[:-1]).astype(np.int64)
+    assert set(lens[Q // 2:].tolist()) == set(range(m_lo, m_hi + 1))
+    ix = kb.KmerIndex(None, 4, [k], stream=sptr, text_device_ptr=d_text.data_ptr(), n=n)
+    try:
+        del d_text
+        got = ix.search_batch(q, off).as_tuple()
+        got_correct = ix.search_batch(q, off, mode=kb.MODE_CORRECT).as_tuple()
+    finally:
+        ix.close()
+    with oracle_mod.Oracle(text, 4, [k], restrict_to=(q, off)) as o:
+        want = o.search(q, off)
+        ub = o.last_ub
+    assert oracle_mod.Oracle.restricted_misses() == 0
+    assert_results_equal(got, want, skip=ub, label="config5 full text")
+    planted_lens, planted_status = lens[Q // 2:], want[2][Q // 2:]
+    planted_counts = (want[0][1:] - want[0][:-1])[Q // 2:]
+    rest = planted_lens % k
+    # the sample does exercise what it is meant to: THROW with all parts present, non-empty defective plans
+    assert int(((planted_status == 1) & (rest >= 1) & (rest <= 4)).sum()) > 1000
+    assert int((planted_counts[(planted_lens >= 53) & (planted_lens <= 63)] > 0).sum()) > 1000
+    assert int((want[0][1:] - want[0][:-1])[:Q // 2].sum()) > 1000                        # random queries with hits
+    # CORRECT mode: every planted window is found at its origin; sorted lists
+    c_off, c_pos, _ = got_correct
+    assert int(((c_off[1:] - c_off[:-1])[Q // 2:] == 0).sum()) == 0
 
 
 def test_config5_full_size_properties(kb):
