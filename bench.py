@@ -40,7 +40,7 @@ WORKLOADS = {
     "c4b": dict(name="kmer_index<aa27,k=5> 50 M symbols, 1e6 queries len 5", sigma=27, ks=[5], n=50_000_000, Q=1_000_000,
                 m=(5, 5)),
     "c5": dict(name="kmer_index<dna4,k=16> 3 Gbp, 1e8 queries len 16-64", sigma=4, ks=[16], n=3_000_000_000,
-               Q=100_000_000, m=(16, 64), ref_Q=200_000),
+               Q=100_000_000, m=(16, 64), ref_Q=1_000_000),
 }
 TEXT_SEED, QUERY_SEED = 205, 1239
 
@@ -57,6 +57,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--count-only", action="store_true", help="time search without materialising positions")
+    ap.add_argument("--multi", default="replicated", choices=["replicated", "position-range"],
+                    help="N > 1: 'replicated' = every GPU sorts one key-range part, the parts are all-gathered over NVLink "
+                         "into the whole index on every GPU and each GPU answers 1/N of the batch; 'position-range' = text "
+                         "shards with halo, every GPU searches the whole batch, hit lists merged on rank 0")
     return ap.parse_args()
 
 
@@ -64,14 +68,18 @@ def parse_args():
 # reference arm / cpu_baseline: the reference's own CPU implementation on a bounded sample
 # ------------------------------------------------------------------------------------------------------------
 def cpu_reference_sample(wl, steps: int, warmup: int):
-    """Times build + search of the reference on the host cores. The sample keeps the workload's alphabet,
-    ks and query-length range but shrinks the text and the batch so one step is ~10 s of CPU work."""
+    """Times the reference's build + search on the host cores. The sample keeps the workload's alphabet, ks and
+    query-length range; the text is capped at 50 M symbols (the reference's hash map does not fit / finish beyond that on
+    a bench budget) and the batch at ref_Q queries per step. The reference index is built ONCE (its build is
+    single-threaded per k: ~20 s at 50 Mbp) and every step searches the same batch on it; search value = median."""
+    import platform
+
     from kmer_index_b200 import synth
     from oracle import bindings
 
     sigma, ks, (m_lo, m_hi) = wl["sigma"], wl["ks"], wl["m"]
     cores = os.cpu_count() or 1
-    n = min(wl["n"], 5_000_000)
+    n = min(wl["n"], 50_000_000)
     # seconds of reference search per step: its rest handling probes up to sigma^(k-rest) buckets per query
     Q = min(wl["Q"], wl.get("ref_Q", 20_000 if m_hi > max(ks) else 1_000_000))
     text = synth.random_text(n, sigma, TEXT_SEED)
@@ -79,35 +87,47 @@ def cpu_reference_sample(wl, steps: int, warmup: int):
     use_ref = bindings.have_reference() and bindings.Reference.supported(sigma, ks)
     if not use_ref:
         bindings.build()
-    b_times, s_times = [], []
+    if use_ref:
+        idx = bindings.Reference(text, sigma, ks, n_threads=cores)  # make_kmer_index<ks...>(text, hw threads)
+        tb = idx.build_seconds
+    else:
+        t0 = time.perf_counter()
+        idx = bindings.Oracle(text, sigma, ks)
+        tb = time.perf_counter() - t0
+    s_times = []
     for it in range(warmup + steps):
         if use_ref:
-            idx = bindings.Reference(text, sigma, ks, n_threads=cores)  # make_kmer_index<ks...>(text, hw threads)
-            tb = idx.build_seconds
             idx.search(q, off, n_threads=cores, keep_positions=True)    # striped over the reference thread_pool
             ts = idx.search_seconds
         else:
             t0 = time.perf_counter()
-            idx = bindings.Oracle(text, sigma, ks)
-            tb = time.perf_counter() - t0
-            t0 = time.perf_counter()
             idx.search(q, off, n_threads=cores)
             ts = time.perf_counter() - t0
-        idx.close()
         if it >= warmup:
-            b_times.append(tb)
             s_times.append(ts)
-    tb, ts = float(np.mean(b_times)), float(np.mean(s_times))
+    idx.close()
+    ts = float(np.median(s_times))
     build_threads = min(len(ks), cores)  # the reference parallelises the build over k only (kmer_index.hpp:487-490)
+    cpu_model = ""
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                cpu_model = ln.split(":", 1)[1].strip()
+                break
+    except OSError:
+        cpu_model = platform.processor()
     return {
         "kind": "reference" if use_ref else "port",
         "cores": cores,
+        "cpu": cpu_model,
         "search_qps": Q / ts,
+        "search_qps_spread": [Q / max(s_times), Q / min(s_times)],
         "build_bases_per_s": n / tb,
         "build_threads": build_threads,
-        "ms_per_step": (tb + ts) * 1e3,
-        "sample": f"text {n} of {wl['n']} symbols, {Q} of {wl['Q']} random queries len {m_lo}-{m_hi}; "
-                  f"build on {build_threads} thread(s) (one per k), search striped over {cores} threads",
+        "ms_per_step": ts * 1e3,
+        "sample": f"text {n} of {wl['n']} symbols, {Q} of {wl['Q']} random queries len {m_lo}-{m_hi}; index built once "
+                  f"({tb:.1f} s on {build_threads} thread(s), one per k) outside the step loop, every step searches the batch "
+                  f"striped over {cores} threads; value = median of {len(s_times)} steps",
     }
 
 
@@ -124,7 +144,8 @@ def run_reference(args, wl):
         "build": {"metric": "build_gbases_per_s", "value": r["build_bases_per_s"] / 1e9, "unit": "Gbases/s",
                   "threads": r["build_threads"]},
         "cpu_baseline": {"value": r["search_qps"], "unit": "queries/s", "cores": r["cores"], "kind": r["kind"],
-                         "sample": r["sample"], "build_gbases_per_s": r["build_bases_per_s"] / 1e9},
+                         "sample": r["sample"], "build_gbases_per_s": r["build_bases_per_s"] / 1e9, "cpu": r["cpu"],
+                         "search_qps_min_max": r["search_qps_spread"]},
         "e2e": {"value": r["search_qps"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -214,26 +235,35 @@ def run_ours(args, wl):
     Q = max(int(wl["Q"] * args.scale), 1)
     m_lo, m_hi = wl["m"]
     k_max = max(ks)
+    replicated = world > 1 and args.multi == "replicated"
 
-    # ---- this rank's slice of the text: k-mer/match starts [begin, end), plus a halo of m_hi - 1 symbols
-    shard = sharded.shard_range(n, world, rank, halo=max(m_hi, k_max) - 1)
+    # ---- the text. position-range: this rank's slice (k-mer/match starts [begin, end) plus a halo of m_hi - 1 symbols);
+    # replicated: the whole text on every rank (each rank sorts only its key-range part of it)
+    shard = sharded.shard_range(n, 1 if replicated else world, 0 if replicated else rank, halo=max(m_hi, k_max) - 1)
     n_local = shard.length
     text = torch.empty(n_local, dtype=torch.uint8, device=dev)
     _capi.check(L.kmer_b200_synth_ranks_device(text.data_ptr(), n_local, shard.begin, sigma, TEXT_SEED, sptr))
 
-    # ---- the query batch (identical on every rank: "queries are broadcast")
+    # ---- the query batch: Q queries defined by the seeds alone. position-range: every rank holds all of them
+    # ("queries are broadcast"); replicated: rank r holds queries [r Q / N, (r + 1) Q / N)
     g = torch.Generator(device=dev)
     g.manual_seed(QUERY_SEED)
     lens = torch.randint(m_lo, m_hi + 1, (Q,), generator=g, device=dev, dtype=torch.int64)
-    q_off = torch.zeros(Q + 1, dtype=torch.int64, device=dev)
-    torch.cumsum(lens, 0, out=q_off[1:])
+    q_lo, q_hi = (rank * Q // world, (rank + 1) * Q // world) if replicated else (0, Q)
+    sym_lo = int(lens[:q_lo].sum().item())
+    Ql = q_hi - q_lo
+    q_off = torch.zeros(Ql + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(lens[q_lo:q_hi], 0, out=q_off[1:])
     n_sym = int(q_off[-1].item())
     del lens
     q = torch.empty(n_sym, dtype=torch.uint8, device=dev)
-    _capi.check(L.kmer_b200_synth_ranks_device(q.data_ptr(), n_sym, 0, sigma, QUERY_SEED ^ 0xC0FFEE, sptr))
+    _capi.check(L.kmer_b200_synth_ranks_device(q.data_ptr(), n_sym, sym_lo, sigma, QUERY_SEED ^ 0xC0FFEE, sptr))
     torch.cuda.synchronize()
 
     def make_index(profile, text_ptr=None, host_text=None):
+        if replicated:
+            return kb.KmerIndex(host_text, sigma, ks, stream=sptr, profile=profile, device=local_rank,
+                                text_device_ptr=text_ptr, n=n_local, key_part=rank, key_parts=world)
         return kb.KmerIndex(host_text, sigma, ks, stream=sptr, profile=profile, device=local_rank,
                             shard_begin=shard.begin, n_total=n if world > 1 else 0, halo=shard.halo,
                             text_device_ptr=text_ptr, n=n_local)
@@ -243,30 +273,38 @@ def run_ours(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def search_resident(ix, count_only):
+        if replicated:
+            return sharded.search_device(ix, q.data_ptr(), q_off.data_ptr(), Ql, m_hi, 1, dev, count_only=count_only)
+        return sharded.search_device(ix, q.data_ptr(), q_off.data_ptr(), Q, m_hi, world, dev, count_only=count_only)
+
     def device_step(profile):
-        """build + search with inputs resident in HBM; returns (build_ms, search_ms, hits, stats)."""
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        """build + search with inputs resident in HBM; returns (build_ms, gather_ms, search_ms, hits, stats)."""
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         e[0].record(stream)
         ix = make_index(profile, text_ptr=text.data_ptr())
         e[1].record(stream)
-        hits = sharded.search_device(ix, q.data_ptr(), q_off.data_ptr(), Q, m_hi, world, dev,
-                                     count_only=args.count_only)
+        if replicated:
+            sharded.assemble_replicated(ix, world, rank, dist, dev)   # NCCL all-gather of the parts: part of the build
         e[2].record(stream)
+        hits = search_resident(ix, args.count_only)
+        e[3].record(stream)
         torch.cuda.synchronize()
         stats = ix.stats() if profile else None
         ix.close()
-        return e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), hits, stats
+        return e[0].elapsed_time(e[2]), e[1].elapsed_time(e[2]), e[2].elapsed_time(e[3]), hits, stats
 
     # ---- warm-up, then exactly K timed steps between barriers
     sampler = ClockSampler(local_rank) if rank == 0 else None   # started early: nvidia-smi needs ~1 s to come up
     for _ in range(args.warmup):
         device_step(False)
     barrier()
-    b_ms, s_ms, stats_acc, hits = [], [], {}, 0
+    b_ms, g_ms, s_ms, stats_acc, hits = [], [], [], {}, 0
     t_region = time.perf_counter()
     for _ in range(args.steps):
-        tb, ts, hits, st = device_step(True)
+        tb, tg, ts, hits, st = device_step(True)
         b_ms.append(tb)
+        g_ms.append(tg)
         s_ms.append(ts)
         for name, v in st.items():
             a = stats_acc.setdefault(name, {"launches": 0, "device_ms": 0.0, "algorithmic_bytes": 0.0})
@@ -276,14 +314,25 @@ def run_ours(args, wl):
     t_region = time.perf_counter() - t_region
     clocks = sampler.stop() if sampler else None
 
-    # ---- outside the timed region: algorithmic gathers of the batch (profile = 2 counts the 32-byte sectors
-    # the search must fetch at data-dependent addresses) and the device's random-gather ceiling
+    # ---- outside the timed region: result fingerprint (hits, status histogram, position checksum -- identical for
+    # every N and both multi-GPU modes), algorithmic gathers of the batch (profile = 2 counts the 32-byte sectors the
+    # search must fetch at data-dependent addresses) and the device's random-gather ceiling
     gathers = gather_peak = None
-    if rank == 0 or world > 1:
-        ix = make_index(2, text_ptr=text.data_ptr())
-        sharded.search_device(ix, q.data_ptr(), q_off.data_ptr(), Q, m_hi, world, dev, count_only=True)
-        gathers = ix.last_search_gathers
-        ix.close()
+    ix = make_index(2, text_ptr=text.data_ptr())
+    if replicated:
+        sharded.assemble_replicated(ix, world, rank, dist, dev)
+    search_resident(ix, True)
+    gathers = ix.last_search_gathers
+    fp = sharded.fingerprint(ix, q.data_ptr(), q_off.data_ptr(), Ql if replicated else Q, m_hi,
+                             1 if replicated else world, dev, q_lo)
+    ix.close()
+    if replicated:
+        t = torch.tensor([fp["hits"], fp["checksum"]] + fp["status_hist"] + [gathers], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)   # int64 sums wrap: the checksum is defined modulo 2^64
+        t = [int(x) for x in t.cpu()]
+        fp = {"hits": t[0], "checksum": t[1], "status_hist": t[2:6]}
+        gathers = t[6]
+        hits = fp["hits"]
     if rank == 0:
         try:
             gather_peak = kb.gather_probe(16 << 30, 1 << 29, sptr)
@@ -303,21 +352,23 @@ def run_ours(args, wl):
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             ev[0].record(stream)
             ix = make_index(False, host_text=h_text.numpy())
+            if replicated:
+                sharded.assemble_replicated(ix, world, rank, dist, dev)
             ev[1].record(stream)
-            if world == 1:
-                res = sharded.search_host(ix, h_q.numpy(), h_off.numpy().view(np.uint64), world, dev)
+            if world == 1 or replicated:
+                res = sharded.search_host(ix, h_q.numpy(), h_off.numpy().view(np.uint64), 1, dev)
             else:
                 res = sharded.search_host(ix, h_q, h_off, world, dev)
             ev[2].record(stream)
             torch.cuda.synchronize()
-            d2h = (Q + 1) * 8 + Q + 4 * int(res.positions.size)
+            d2h = (Ql + 1) * 8 + Ql + 4 * int(res.positions.size)
             res.free()
             ix.close()
             if it >= min(args.warmup, 1):
                 eb.append(ev[0].elapsed_time(ev[1]))
                 es.append(ev[1].elapsed_time(ev[2]))
-        # sharded: every rank uploads 1/world of the query batch (then NCCL all-gather)
-        h2d_q = (n_sym + (Q + 1) * 8) // world
+        # position-range: every rank uploads 1/world of the query batch (then NCCL all-gather); replicated: its own slice
+        h2d_q = (n_sym + (Ql + 1) * 8) // (1 if replicated else world)
         e2e = {"build_ms": float(np.mean(eb)), "search_ms": float(np.mean(es)), "h2d": n_local + h2d_q, "d2h": d2h}
         del h_text, h_q, h_off
 
@@ -330,12 +381,13 @@ def run_ours(args, wl):
         return float(t.item())
 
     build_ms = max_over_ranks(float(np.mean(b_ms)))
+    gather_ms = max_over_ranks(float(np.mean(g_ms)))
     search_ms = max_over_ranks(float(np.mean(s_ms)))
     if e2e:
         e2e["build_ms"] = max_over_ranks(e2e["build_ms"])
         e2e["search_ms"] = max_over_ranks(e2e["search_ms"])
         if world > 1:   # bytes per step over all ranks
-            t = torch.tensor([e2e["h2d"], e2e["d2h"] if rank == 0 else 0], dtype=torch.float64, device=dev)
+            t = torch.tensor([e2e["h2d"], e2e["d2h"] if (rank == 0 or replicated) else 0], dtype=torch.float64, device=dev)
             dist.all_reduce(t)
             e2e["h2d"], e2e["d2h"] = int(t[0].item()), int(t[1].item())
 
@@ -355,6 +407,14 @@ def run_ours(args, wl):
                        "algorithmic_gbs": (v["algorithmic_bytes"] / (v["device_ms"] * 1e-3) / 1e9) if v["device_ms"] > 0 and
                        v["algorithmic_bytes"] > 0 else None}
                    for k, v in stats_acc.items() if v["launches"]}
+        for v in kernels.values():
+            v["frac_of_hbm_peak"] = v["algorithmic_gbs"] / peak if v["algorithmic_gbs"] else None
+        sharding = "none"
+        if replicated:
+            sharding = (f"replicated index x{world}: every GPU sorts one key-range part of the hashes, parts all-gathered "
+                        f"over NCCL (inside build_ms), each GPU answers 1/{world} of the batch")
+        elif world > 1:
+            sharding = f"position range x{world}, halo {shard.halo}, every GPU searches the whole batch, merge on rank 0"
         line = {
             "metric": "search_queries_per_s", "value": Q / (search_ms * 1e-3), "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": build_ms + search_ms,
@@ -362,13 +422,13 @@ def run_ours(args, wl):
             "config": {"workload": wl["name"] + (f" (scaled x{args.scale})" if args.scale != 1.0 else "")
                                    + (f" (text overridden to {args.text_symbols} symbols)" if args.text_symbols else ""),
                        "text_symbols": n, "queries": Q, "query_len": [m_lo, m_hi], "sigma": sigma, "ks": ks,
-                       "sharding": f"position range x{world}, halo {shard.halo}" if world > 1 else "none",
+                       "sharding": sharding,
                        "mode": "reference_exact", "count_only": bool(args.count_only),
                        "l2": "inputs larger than L2 (text, index and batch are each >> 126 MB)" if n * 4 > 2e8 else
                              "inputs smaller than L2; step rebuilds the index so no data is reused across steps"},
             "build": {"metric": "build_gbases_per_s", "value": n / (build_ms * 1e-3) / 1e9, "unit": "Gbases/s",
-                      "ms": build_ms},
-            "search": {"ms": search_ms, "hits": int(hits)},
+                      "ms": build_ms, "nccl_gather_ms": gather_ms if replicated else 0.0},
+            "search": {"ms": search_ms, "hits": int(hits), "checksum": fp["checksum"], "status_hist": fp["status_hist"]},
             "roofline": {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "avg_launch_ms": st["device_ms"] / launches,
@@ -378,19 +438,35 @@ def run_ours(args, wl):
             "clocks": clocks,
             "wall_s_timed_region": t_region,
         }
+        # whole build against the HBM peak on both byte models of SURVEY.md 8d
+        build_keys = ("pack_text", "radix_hist_text", "radix_hist_pairs", "column_scan", "radix_scatter_text",
+                      "radix_scatter_pairs", "directory_fill")
+        lsd_bytes = sum(stats_acc[k]["algorithmic_bytes"] for k in build_keys if k in stats_acc) / args.steps
+        bits = 2 if sigma <= 4 else 4 if sigma <= 16 else 8
+        must_move = sum((n_local - k + 1) * (bits / 8.0 + 4.0) + 4.0 * min(sigma ** k, 8 * n_local) for k in ks)
+        kernel_build_ms = sum(stats_acc[k]["device_ms"] for k in build_keys if k in stats_acc) / args.steps
+        if kernel_build_ms > 0:
+            line["roofline_build"] = {
+                "ms": kernel_build_ms, "lsd_model_bytes": lsd_bytes, "must_move_bytes": must_move,
+                "lsd_model_frac": lsd_bytes / (kernel_build_ms * 1e-3) / 1e9 / peak,
+                "must_move_frac": must_move / (kernel_build_ms * 1e-3) / 1e9 / peak,
+                "note": "rank 0's kernels; lsd_model = bytes an LSD radix build moves with this pass structure, must_move = "
+                        "text in + positions out + directory out"}
         # search roofline: sectors gathered per second against the measured random-gather ceiling
         s_ms = stats_acc.get("search_count", {"device_ms": 0.0})["device_ms"] / args.steps
         if gathers and gather_peak and s_ms > 0:
-            rate = gathers / (s_ms * 1e-3)
+            g_rank0 = gathers / (world if replicated else 1)
+            rate = g_rank0 / (s_ms * 1e-3)
             line["roofline_search"] = {"kernel": "search_count", "bound": "hbm", "achieved": rate * 32 / 1e9,
                                        "peak": gather_peak * 32 / 1e9, "unit": "GB/s", "frac": rate / gather_peak,
+                                       "frac_of_hbm_peak_32B_sectors": rate * 32 / 1e9 / peak,
                                        "traffic": None, "sectors_per_query": gathers / Q,
                                        "gather_peak_sectors_per_s": gather_peak,
                                        "peak_source": "measured here: kmer_b200_gather_probe, independent 8-byte reads from a "
                                                       "16 GiB table (random-gather ceiling; 32-byte sectors x gathers/s)",
                                        "avg_launch_ms": s_ms, "rank": 0}
             if name.startswith("search"):
-                # the step is search-dominated (sharded runs): the dominant kernel's roofline is the gather one
+                # the step is search-dominated: the dominant kernel's roofline is the gather one
                 line["roofline"] = dict(line["roofline_search"])
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -398,6 +474,10 @@ def run_ours(args, wl):
             if key in traffic and args.scale == 1.0 and not args.text_symbols and world == 1:   # captured on the unsharded workload
                 line["roofline"]["traffic"] = traffic[key]["dram_bytes_per_launch"]
                 line["roofline"]["traffic_source"] = traffic[key]["source"]
+            skey = f"{args.workload}:search_count"
+            if "roofline_search" in line and skey in traffic and args.scale == 1.0 and world == 1:
+                line["roofline_search"]["traffic"] = traffic[skey]["dram_bytes_per_launch"]
+                line["roofline_search"]["traffic_source"] = traffic[skey]["source"]
         except (OSError, ValueError, KeyError):
             pass
         if e2e:
@@ -406,10 +486,11 @@ def run_ours(args, wl):
                            "search_ms": e2e["search_ms"], "build_ms": e2e["build_ms"],
                            "build_gbases_per_s": n / (e2e["build_ms"] * 1e-3) / 1e9}
         if not args.no_cpu_baseline and world == 1:
-            r = cpu_reference_sample(wl, 1, 0)
+            r = cpu_reference_sample(wl, 3, 0)
             line["cpu_baseline"] = {"value": r["search_qps"], "unit": "queries/s", "cores": r["cores"], "kind": r["kind"],
                                     "sample": r["sample"], "build_gbases_per_s": r["build_bases_per_s"] / 1e9,
-                                    "build_threads": r["build_threads"]}
+                                    "build_threads": r["build_threads"], "cpu": r["cpu"],
+                                    "search_qps_min_max": r["search_qps_spread"]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define KMER_B200_ABI_VERSION 1
+#define KMER_B200_ABI_VERSION 2
 
 typedef enum kmer_b200_status {
     KMER_B200_OK = 0,
@@ -68,6 +68,14 @@ typedef struct kmer_b200_config {
                                 2 = additionally count the 32-byte sectors each search gathers */
     uint32_t reserved;       /* bit 0: never build auxiliary k' = m elements for sub-k query lengths (saves memory;
                                 those results are then sorted by the segment-sort kernel instead) */
+    /* Key-range parts (multi-GPU build of a REPLICATED index). key_parts > 1: `ranks` is the whole text, but every
+       element indexes only the k-mers whose hash lies in part key_part of key_parts equal slices of [0, sigma^k):
+       1/key_parts of the sorting work per GPU. The parts are concatenated into the full index (part r's position
+       array behind part r-1's, directory entries offset by the k-mers of the earlier parts) and handed back with
+       kmer_b200_adopt_element; until then the index answers with the hits of its own part only. 32-bit hashes,
+       dense directories. 0 or 1: the whole key space. */
+    uint32_t key_part;
+    uint32_t key_parts;
 } kmer_b200_config;
 
 typedef struct kmer_b200_index kmer_b200_index;
@@ -178,6 +186,24 @@ int kmer_b200_search_sharded_peek(kmer_b200_pending *pending, const uint32_t *d_
    the caller copies the other shards' lists to offsets[id] + within. */
 int kmer_b200_search_sharded_add_counts(kmer_b200_pending *pending, const uint32_t *d_present4_global,
                                         const int64_t *d_ids, const int64_t *d_counts, uint64_t n, int64_t *d_within_out);
+
+/* ---- key-range parts: export a part, adopt the assembled whole (see kmer_b200_config.key_parts) */
+typedef struct kmer_b200_part {
+    uint64_t key_lo, key_hi;     /* the hashes this part indexes: [key_lo, key_hi) */
+    uint64_t n_kmers;            /* k-mers in the part = length of d_positions */
+    uint64_t directory_entries;  /* key_hi - key_lo + 1 (dense); entry j = number of the part's k-mers with hash - key_lo < j */
+    const uint32_t *d_positions; /* device, stably sorted by hash */
+    const uint32_t *d_directory; /* device */
+} kmer_b200_part;
+int kmer_b200_element_part(const kmer_b200_index *index, uint32_t element, kmer_b200_part *out);
+/* d_dst[j] = directory[j] + base for j < n (n <= directory_entries): the part's directory as a slice of the whole
+   index's, `base` = number of k-mers in the parts before this one. Enqueued on the index's stream. */
+int kmer_b200_export_directory(kmer_b200_index *index, uint32_t element, uint64_t base, uint64_t n, uint32_t *d_dst);
+/* Replace the element's arrays by the assembled whole: d_positions[n_kmers] (n_kmers = n - k + 1) and the dense
+   directory d_directory[sigma^k + 1], both device arrays that stay owned by the caller and must outlive the index.
+   The element then covers the whole key space. */
+int kmer_b200_adopt_element(kmer_b200_index *index, uint32_t element, const uint32_t *d_positions, uint64_t n_kmers,
+                            const uint32_t *d_directory, uint64_t directory_entries);
 
 /* ---- introspection (parity tests and roofline accounting) */
 typedef struct kmer_b200_element_info {

@@ -160,7 +160,7 @@ class KmerIndex:
     def __init__(self, text, sigma: int, ks: Sequence[int], *, mode: int = MODE_REFERENCE_EXACT, device: int = -1,
                  stream: int | None = None, profile: bool = False, shard_begin: int = 0, n_total: int = 0,
                  halo: int = 0, directory_bits: int = 0, text_device_ptr: int | None = None, n: int | None = None,
-                 aux_elements: bool = True, lut: np.ndarray | None = None):
+                 aux_elements: bool = True, lut: np.ndarray | None = None, key_part: int = 0, key_parts: int = 0):
         L = _capi.lib()
         self._L = L
         self._h = C.c_void_p()
@@ -177,6 +177,8 @@ class KmerIndex:
         cfg.halo = halo
         cfg.directory_bits = directory_bits
         cfg.reserved = 0 if aux_elements else 1   # bit 0: no auxiliary k' = m elements for sub-k lengths
+        cfg.key_part, cfg.key_parts = key_part, key_parts   # key-range part of a multi-GPU build (sharded.build_replicated)
+        self._adopted = []                                   # arrays handed over with adopt_element: kept alive here
         ks_a = np.asarray(self.ks, dtype=np.uint32)
         if text_device_ptr is not None:
             self.n = int(n)
@@ -208,6 +210,7 @@ class KmerIndex:
         L = _capi.lib()
         self = cls.__new__(cls)
         self._L = L
+        self._adopted = []
         self._h = C.c_void_p()
         cfg = _capi.Config()
         L.kmer_b200_config_default(C.byref(cfg))
@@ -225,6 +228,7 @@ class KmerIndex:
         if getattr(self, "_h", None):
             self._L.kmer_b200_destroy(self._h)
             self._h = None
+            self._adopted = []
 
     def __del__(self):
         try:
@@ -353,6 +357,23 @@ class KmerIndex:
         segment sort (then merge after finish instead)."""
         _capi.check(self._L.kmer_b200_search_sharded_add_counts(pending, C.c_void_p(present4_global_ptr), C.c_void_p(ids_ptr),
                                                                 C.c_void_p(counts_ptr), n, C.c_void_p(within_ptr)))
+
+    # -- key-range parts (multi-GPU build of a replicated index)
+    def element_part(self, e: int) -> _capi.Part:
+        part = _capi.Part()
+        _capi.check(self._L.kmer_b200_element_part(self._h, e, C.byref(part)))
+        return part
+
+    def export_directory(self, e: int, base: int, n: int, dst_ptr: int) -> None:
+        """dst[j] = part directory[j] + base for j < n (device pointer), on the index's stream."""
+        _capi.check(self._L.kmer_b200_export_directory(self._h, e, base, n, C.c_void_p(dst_ptr)))
+
+    def adopt_element(self, e: int, positions, directory) -> None:
+        """Hand the assembled whole element (device tensors: int32 positions[n - k + 1], directory[sigma^k + 1]) to
+        the index; the tensors are kept alive by this object."""
+        _capi.check(self._L.kmer_b200_adopt_element(self._h, e, C.c_void_p(positions.data_ptr()), positions.numel(),
+                                                    C.c_void_p(directory.data_ptr()), directory.numel()))
+        self._adopted.append((positions, directory))
 
     # -- introspection
     def element_info(self, e: int) -> _capi.ElementInfo:

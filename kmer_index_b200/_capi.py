@@ -25,13 +25,18 @@ QUERY_TOO_LONG_FOR_SHARD = 3
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("mode", C.c_uint32), ("stream", C.c_void_p), ("shard_begin", C.c_uint64),
                 ("n_total", C.c_uint64), ("halo", C.c_uint32), ("directory_bits", C.c_uint32),
-                ("profile", C.c_uint32), ("reserved", C.c_uint32)]
+                ("profile", C.c_uint32), ("reserved", C.c_uint32), ("key_part", C.c_uint32), ("key_parts", C.c_uint32)]
 
 
 class ElementInfo(C.Structure):
     _fields_ = [("k", C.c_uint32), ("key_bits", C.c_uint32), ("directory_shift", C.c_uint32),
                 ("sort_passes", C.c_uint32), ("n_kmers", C.c_uint64), ("directory_entries", C.c_uint64),
                 ("device_bytes", C.c_uint64)]
+
+
+class Part(C.Structure):
+    _fields_ = [("key_lo", C.c_uint64), ("key_hi", C.c_uint64), ("n_kmers", C.c_uint64), ("directory_entries", C.c_uint64),
+                ("d_positions", C.c_void_p), ("d_directory", C.c_void_p)]
 
 
 class KernelStat(C.Structure):
@@ -79,6 +84,9 @@ SYMBOLS = {
     "kmer_b200_search_sharded_abort": (None, [C.c_void_p]),
     "kmer_b200_search_sharded_peek": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "kmer_b200_search_sharded_add_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "kmer_b200_element_part": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(Part)]),
+    "kmer_b200_export_directory": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "kmer_b200_adopt_element": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
     "kmer_b200_n_elements": (C.c_uint32, [C.c_void_p]),
     "kmer_b200_element_info_get": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(ElementInfo)]),
     "kmer_b200_element_positions": (C.c_int, [C.c_void_p, C.c_uint32, u32p, C.c_uint64]),
@@ -112,7 +120,7 @@ def lib() -> C.CDLL:
             fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if L.kmer_b200_abi_version() != 1:
+        if L.kmer_b200_abi_version() != 2:
             raise RuntimeError("libkmer_b200.so ABI version mismatch")
         _lib = L
     return _lib

@@ -9,8 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkmer_b200.so")
-SOURCES = ["capi.cu", "build_kernels.cu", "onesweep.cu", "search_kernels.cu", "synth.cu"]
-HEADERS = ["common.cuh", "radix.cuh", "launch.h", os.path.join("..", "..", "include", "kmer_b200.h")]
+SOURCES = ["capi.cu", "build_kernels.cu", "onesweep.cu", "search_kernels.cu", "synth.cu", "host_pack.cpp"]
+HEADERS = ["common.cuh", "radix.cuh", "launch.h", "host_pack.h", os.path.join("..", "..", "include", "kmer_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall", "-Xptxas", "-v"]
 
@@ -38,8 +38,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     log = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(build_dir, src[:-3] + ".o")
+        obj = os.path.join(build_dir, os.path.splitext(src)[0] + ".o")
         extra = os.environ.get("KMER_B200_NVCC_EXTRA", "").split()   # tuning experiments, e.g. -DKB_SEARCH_MIN_BLOCKS=6
+        if src.endswith(".cpp"):   # plain host code (the query packer): x86-64-v3 for BMI2 PEXT
+            extra = [*extra, "-Xcompiler", "-march=x86-64-v3"]
         cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
@@ -52,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         sys.stderr.write("\n".join(log))
         raise RuntimeError(f"nvcc failed on {failed}")
-    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-lpthread"]
     subprocess.run(cmd, check=True)
     with open(os.path.join(build_dir, "ptxas.log"), "w") as f:
         f.write("\n".join(log))

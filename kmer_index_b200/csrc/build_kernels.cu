@@ -64,6 +64,7 @@ void launch_pack_text(const uint8_t *d_ranks, uint64_t n, uint32_t bits, uint32_
 template <typename KeyT>
 struct TextSource {  // key(i) = hash of the k-mer starting at symbol i; value(i) = i
     using key_type = KeyT;
+    static constexpr bool kAtomicMatch = true;  // see tile_rank: the hash extraction already loads the ALU pipe
     PackedText text;
     uint32_t k;
     __device__ __forceinline__ KeyT key(uint64_t i) const {
@@ -121,6 +122,7 @@ struct TextSource {  // key(i) = hash of the k-mer starting at symbol i; value(i
 // every key is a Horner walk over two windows, so there is no word sharing between a thread's items to exploit.
 struct WideTextSource {
     using key_type = uint64_t;
+    static constexpr bool kAtomicMatch = true;
     PackedText text;
     uint32_t k;
     __device__ __forceinline__ uint64_t key(uint64_t i) const { return key_at(text.words, i, k, text.bits, text.sigma); }
@@ -141,6 +143,7 @@ struct WideTextSource {
 template <typename KeyT>
 struct PairSource {  // materialised (key, value) pairs
     using key_type = KeyT;
+    static constexpr bool kAtomicMatch = false;
     const KeyT *keys;
     const uint32_t *vals;
     __device__ __forceinline__ KeyT key(uint64_t i) const { return keys[i]; }
@@ -365,11 +368,12 @@ __global__ void __launch_bounds__(kRadix) column_apply_kernel(uint32_t *__restri
 // destination).
 // ------------------------------------------------------------------------------------------------
 // (key, value) staged in digit order. 32-bit keys: one 64-bit shared-memory access per element.
-template <typename KeyT>
+template <typename KeyT, bool ATOMIC>
 struct ScatterSmem;
-template <>
-struct ScatterSmem<uint32_t> {
+template <bool ATOMIC>
+struct ScatterSmem<uint32_t, ATOMIC> {
     RankSmem rank;
+    uint32_t warp_msk[ATOMIC ? kSortWarps : 1][kRadix];  // only the shared-memory match (tile_rank) uses it
     uint32_t delta[kRadix];
     uint2 kv[kSortTile];
     __device__ __forceinline__ void put(uint32_t i, uint32_t k, uint32_t v) { kv[i] = make_uint2(k, v); }
@@ -379,9 +383,10 @@ struct ScatterSmem<uint32_t> {
         v = e.y;
     }
 };
-template <>
-struct ScatterSmem<uint64_t> {
+template <bool ATOMIC>
+struct ScatterSmem<uint64_t, ATOMIC> {
     RankSmem rank;
+    uint32_t warp_msk[ATOMIC ? kSortWarps : 1][kRadix];
     uint32_t delta[kRadix];
     uint64_t keys[kSortTile];
     uint32_t vals[kSortTile];
@@ -400,7 +405,7 @@ __device__ __forceinline__ void scatter_tile(const Source &src, uint64_t tile_be
                                              uint32_t mask, const uint32_t *__restrict__ tile_base_row,
                                              typename Source::key_type *__restrict__ out_keys,
                                              uint32_t *__restrict__ out_vals,
-                                             ScatterSmem<typename Source::key_type> &sm) {
+                                             ScatterSmem<typename Source::key_type, Source::kAtomicMatch> &sm) {
     using KeyT = typename Source::key_type;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -416,7 +421,7 @@ __device__ __forceinline__ void scatter_tile(const Source &src, uint64_t tile_be
     for (int r = 0; r < kSortItems; ++r) local_pos2[r >> 1] = (r & 1) ? (local_pos2[r >> 1] | ((e0 + r * 32) << 16)) : (e0 + r * 32);
     if (tid < kRadix) sm.delta[tid] = (uint32_t)tile_begin;
 #else
-    tile_rank<BITS, FULL, KeyT, BYTE>(key, count, shift, mask, local_pos2, sm.rank);
+    tile_rank<BITS, FULL, KeyT, BYTE, Source::kAtomicMatch>(key, count, shift, mask, local_pos2, sm.rank, sm.warp_msk);
     if (tid < kRadix) sm.delta[tid] = tile_base_row[tid] - sm.rank.excl[tid];
 #endif
     {
@@ -459,7 +464,7 @@ __global__ void __launch_bounds__(kSortThreads, sizeof(typename Source::key_type
                          const uint32_t *__restrict__ tile_base, typename Source::key_type *__restrict__ out_keys,
                          uint32_t *__restrict__ out_vals) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    auto &sm = *reinterpret_cast<ScatterSmem<typename Source::key_type> *>(smem_raw);
+    auto &sm = *reinterpret_cast<ScatterSmem<typename Source::key_type, Source::kAtomicMatch> *>(smem_raw);
     const uint64_t tile_begin = (uint64_t)blockIdx.x * kSortTile;
     const uint32_t count = (uint32_t)min((uint64_t)kSortTile, n - tile_begin);
     const uint32_t *row = tile_base + (uint64_t)blockIdx.x * kRadix;
@@ -657,7 +662,7 @@ void launch_directory_fill(const void *d_keys, uint32_t key_bytes, uint64_t n_km
 template <typename Source, int BITS, bool BYTE>
 static void launch_scatter_bits(const Source &src, uint64_t n, uint32_t shift, uint32_t mask, const uint32_t *d_tile_base,
                                 typename Source::key_type *d_out_keys, uint32_t *d_out_vals, cudaStream_t stream) {
-    using Smem = ScatterSmem<typename Source::key_type>;
+    using Smem = ScatterSmem<typename Source::key_type, Source::kAtomicMatch>;
     const uint32_t n_tiles = (uint32_t)((n + kSortTile - 1) / kSortTile);
     // per-device attribute; cheap enough to set on every launch
     cudaFuncSetAttribute(radix_scatter_kernel<Source, BITS, BYTE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));

@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 
+#include "host_pack.h"
 #include "launch.h"
 #include "radix.cuh"
 
@@ -145,9 +146,22 @@ struct HostElement {
     uint32_t sort_passes = 0;
     uint64_t bytes = 0;
     uint32_t *d_dir = nullptr, *d_pos = nullptr;
-    void *d_keys = nullptr;  // uint32_t or uint64_t hashes (key_bytes)
+    void *d_keys = nullptr;  // uint32_t or uint64_t hashes (key_bytes); null for a dense directory
     uint32_t key_bytes = 4;
+    bool adopted = false;    // pos / dir belong to the caller (kmer_b200_adopt_element)
 };
+
+// the hash range element `k` of this index covers: all of [0, sigma^k), or one of cfg.key_parts equal slices
+struct KeyRange {
+    uint64_t lo, hi;
+};
+KeyRange key_range_of(const kmer_b200_config &cfg, uint64_t key_space) {
+    if (cfg.key_parts <= 1) return KeyRange{0, key_space};
+    uint64_t width = (key_space + cfg.key_parts - 1) / cfg.key_parts;
+    width = (width + 63) / 64 * 64;
+    const uint64_t lo = std::min<uint64_t>((uint64_t)cfg.key_part * width, key_space);
+    return KeyRange{lo, std::min<uint64_t>(lo + width, key_space)};
+}
 
 }  // namespace
 
@@ -341,14 +355,43 @@ void build_scheme(SchemeHost *ix) {
 // Sorters: both leave he.d_keys (sorted hashes) and he.d_pos (positions stably sorted by hash).
 // (a) tiled LSD sort: per-tile histograms + column scan + scatter per pass, (hash, position) in separate arrays.
 //     Used for 64-bit hashes and k-mers wider than one packed window.
-int sort_element_tiled(kmer_b200_index *ix, uint32_t k, HostElement &he, uint32_t digit_bits) {
+int sort_element_tiled(kmer_b200_index *ix, uint32_t k, HostElement &he, uint32_t digit_bits, KeyRange part, uint64_t *n_sorted) {
     using namespace kb;
     cudaStream_t st = ix->stream;
     Profiler &pf = ix->prof;
-    const uint64_t n_kmers = ix->n - k + 1;
+    const uint64_t n_text_kmers = ix->n - k + 1;
     const uint32_t key_bytes = he.key_bytes;
-    he.sort_passes = (he.key_bits + digit_bits - 1) / digit_bits;
-    const uint32_t bits_per_pass = (he.key_bits + he.sort_passes - 1) / he.sort_passes;
+    const bool partial = part.lo != 0 || part.hi != fast_pow(ix->sigma, (uint8_t)k);
+    PackedText text{ix->d_text, ix->n, ix->bits, ix->sigma};
+    // a key-range part: the text is first filtered into the (hash - lo, position) pairs of the part, in position order
+    uint64_t n_kmers = n_text_kmers;
+    uint32_t sort_bits = he.key_bits;
+    void *f_keys = nullptr;
+    uint32_t *f_vals = nullptr;
+    if (partial) {
+        const uint32_t ft = filter_tiles(n_text_kmers);
+        uint64_t *tile_counts = nullptr, *block_sums = nullptr;
+        KB_TRY(dev_alloc(ix, &tile_counts, (uint64_t)ft + 1, false));
+        KB_TRY(dev_alloc(ix, &block_sums, offsets_scan_blocks(ft) + 1, false));
+        pf.begin(K_HIST_TEXT, (double)n_text_kmers * ix->bits / 8.0);
+        launch_owned_count(text, k, n_text_kmers, part.lo, part.hi, tile_counts, st);
+        pf.end();
+        launch_offsets_scan(tile_counts, ft, block_sums, st);
+        KB_CUDA(cudaMemcpyAsync(&ix->h_pinned[6], tile_counts + ft, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        KB_CUDA(cudaStreamSynchronize(st));
+        n_kmers = ix->h_pinned[6];
+        KB_TRY(dev_alloc(ix, (uint8_t **)&f_keys, std::max<uint64_t>(n_kmers, 1) * key_bytes, true));
+        KB_TRY(dev_alloc(ix, &f_vals, std::max<uint64_t>(n_kmers, 1), true));
+        pf.begin(K_SCATTER_TEXT, (double)n_text_kmers * ix->bits / 8.0 + 8.0 * n_kmers);
+        launch_owned_write(text, k, n_text_kmers, part.lo, part.hi, tile_counts, (uint32_t *)f_keys, f_vals, st);
+        pf.end();
+        dev_free(ix, tile_counts);
+        dev_free(ix, block_sums);
+        sort_bits = std::max<uint32_t>(1, bit_length(part.hi - part.lo - 1));
+    }
+    *n_sorted = n_kmers;
+    he.sort_passes = (sort_bits + digit_bits - 1) / digit_bits;
+    const uint32_t bits_per_pass = (sort_bits + he.sort_passes - 1) / he.sort_passes;
     const uint32_t mask = (1u << bits_per_pass) - 1;
     const uint32_t n_tiles = (uint32_t)((n_kmers + sort_tile_size() - 1) / sort_tile_size());
     const uint32_t n_chunks = (n_tiles + scan_chunk_tiles() - 1) / scan_chunk_tiles();
@@ -357,25 +400,30 @@ int sort_element_tiled(kmer_b200_index *ix, uint32_t k, HostElement &he, uint32_
     void *keys[2] = {nullptr, nullptr};
     uint32_t *vals[2] = {nullptr, nullptr};
     uint32_t *tile_hist = nullptr, *chunk_sums = nullptr;
-    auto alloc_keys = [&](void **p) { return dev_alloc(ix, (uint8_t **)p, n_kmers * key_bytes, true); };
-    KB_TRY(alloc_keys(&keys[0]));
-    KB_TRY(dev_alloc(ix, &vals[0], n_kmers, true));
-    KB_TRY(dev_alloc(ix, &tile_hist, (uint64_t)n_tiles * kRadix, false));
-    KB_TRY(dev_alloc(ix, &chunk_sums, (uint64_t)n_chunks * kRadix, false));
-
-    PackedText text{ix->d_text, ix->n, ix->bits, ix->sigma};
-    // pass 0: keys come straight from the packed text
-    pf.begin(K_HIST_TEXT, text_bytes + hist_bytes);
-    launch_hist_text(text, k, n_kmers, 0, mask, tile_hist, st);
-    pf.end();
-    pf.begin(K_COLUMN_SCAN, 3 * hist_bytes, 3);
-    launch_column_scan(tile_hist, n_tiles, chunk_sums, st);
-    pf.end();
-    pf.begin(K_SCATTER_TEXT, text_bytes + hist_bytes + (4.0 + key_bytes) * n_kmers);
-    launch_scatter_text(text, k, key_bytes, n_kmers, 0, mask, tile_hist, keys[0], vals[0], st);
-    pf.end();
+    auto alloc_keys = [&](void **p) { return dev_alloc(ix, (uint8_t **)p, std::max<uint64_t>(n_kmers, 1) * key_bytes, true); };
+    KB_TRY(dev_alloc(ix, &tile_hist, (uint64_t)std::max(n_tiles, 1u) * kRadix, false));
+    KB_TRY(dev_alloc(ix, &chunk_sums, (uint64_t)std::max(n_chunks, 1u) * kRadix, false));
     int cur = 0;
-    for (uint32_t p = 1; p < he.sort_passes; ++p) {
+    uint32_t first_pair_pass = 1;
+    if (partial) {
+        keys[0] = f_keys;  // every pass runs over the filtered pairs
+        vals[0] = f_vals;
+        first_pair_pass = 0;
+    } else {
+        KB_TRY(alloc_keys(&keys[0]));
+        KB_TRY(dev_alloc(ix, &vals[0], n_kmers, true));
+        // pass 0: keys come straight from the packed text
+        pf.begin(K_HIST_TEXT, text_bytes + hist_bytes);
+        launch_hist_text(text, k, n_kmers, 0, mask, tile_hist, st);
+        pf.end();
+        pf.begin(K_COLUMN_SCAN, 3 * hist_bytes, 3);
+        launch_column_scan(tile_hist, n_tiles, chunk_sums, st);
+        pf.end();
+        pf.begin(K_SCATTER_TEXT, text_bytes + hist_bytes + (4.0 + key_bytes) * n_kmers);
+        launch_scatter_text(text, k, key_bytes, n_kmers, 0, mask, tile_hist, keys[0], vals[0], st);
+        pf.end();
+    }
+    for (uint32_t p = first_pair_pass; p < he.sort_passes && n_kmers > 0; ++p) {
         const int nxt = cur ^ 1;
         if (!keys[nxt]) {
             KB_TRY(alloc_keys(&keys[nxt]));
@@ -397,7 +445,7 @@ int sort_element_tiled(kmer_b200_index *ix, uint32_t k, HostElement &he, uint32_
     if (keys[cur ^ 1]) {
         dev_free(ix, (uint8_t *)keys[cur ^ 1]);
         dev_free(ix, vals[cur ^ 1]);
-        ix->device_bytes -= n_kmers * (sizeof(uint32_t) + key_bytes);
+        ix->device_bytes -= std::max<uint64_t>(n_kmers, 1) * (sizeof(uint32_t) + key_bytes);
     }
     dev_free(ix, tile_hist);
     dev_free(ix, chunk_sums);
@@ -408,7 +456,7 @@ int sort_element_tiled(kmer_b200_index *ix, uint32_t k, HostElement &he, uint32_
 
 // (b) single-sweep sort (onesweep.cu): 32-bit hashes. All digit histograms up front from the text, then one scatter
 //     kernel per pass (bulk-copy tile loads, decoupled look-back, 8-byte (hash, position) records between passes).
-int sort_element_onesweep(kmer_b200_index *ix, uint32_t k, HostElement &he, uint32_t digit_bits) {
+int sort_element_onesweep(kmer_b200_index *ix, uint32_t k, HostElement &he, uint32_t digit_bits, uint64_t *n_sorted) {
     using namespace kb;
     cudaStream_t st = ix->stream;
     Profiler &pf = ix->prof;
@@ -487,6 +535,7 @@ int sort_element_onesweep(kmer_b200_index *ix, uint32_t k, HostElement &he, uint
     KB_CUDA(cudaGetLastError());
     he.d_keys = keys;
     he.d_pos = pos;
+    *n_sorted = n_kmers;
     return cleanup(0);
 }
 
@@ -505,26 +554,44 @@ int build_element(kmer_b200_index *ix, uint32_t k, HostElement &he, bool auxilia
     // 32-bit hashes while sigma^k <= 2^32 (all BASELINE configs), 64-bit above
     const uint32_t key_bytes = he.key_bits > 32 ? 8 : 4;
     he.key_bytes = key_bytes;
-    if (key_bytes == 4 && k * ix->bits <= 64 && !std::getenv("KMER_B200_LEGACY_SORT")) {
-        KB_TRY(sort_element_onesweep(ix, k, he, digit_bits));
+    const KeyRange part = key_range_of(ix->cfg, key_space);
+    const bool partial = ix->cfg.key_parts > 1;
+    if (partial && (key_bytes != 4 || k * ix->bits > 64))
+        return fail(KMER_B200_ERR_UNSUPPORTED, "key-range parts need 32-bit hashes (sigma^k <= 2^32)");
+    // directory and sorted hashes are relative to part.lo; max_rel = the largest relative hash (2^64 - 1 when sigma^k
+    // "overflows" to 0 in fast_pow, i.e. sigma = 2, k = 63)
+    const uint64_t max_rel = (partial ? part.hi - part.lo : key_space) - 1;
+    uint64_t n_part = n_kmers;                       // k-mers in the part
+    const char *sorter = std::getenv("KMER_B200_SORT");  // "onesweep": the single-sweep experiment
+    if (!partial && key_bytes == 4 && k * ix->bits <= 64 && sorter && std::strcmp(sorter, "onesweep") == 0) {
+        KB_TRY(sort_element_onesweep(ix, k, he, digit_bits, &n_part));
     } else {
-        KB_TRY(sort_element_tiled(ix, k, he, digit_bits));
+        KB_TRY(sort_element_tiled(ix, k, he, digit_bits, part, &n_part));
     }
 
-    // directory: dense (shift 0) while the key space is at most ~4x the number of k-mers
+    // directory: dense (shift 0) while the key space is at most ~4x the number of k-mers -- or whenever it is affordable:
+    // a position-range shard (or a key-range part) holds 1/N of the k-mers but must not answer most lookups with a
+    // binary search in the sorted hashes just because of that
     uint32_t shift = 0;
+    const uint32_t part_bits = std::max<uint32_t>(1, bit_length(max_rel));
     if (ix->cfg.directory_bits) {
-        if (he.key_bits > ix->cfg.directory_bits) shift = he.key_bits - ix->cfg.directory_bits;
+        if (part_bits > ix->cfg.directory_bits) shift = part_bits - ix->cfg.directory_bits;
     } else {
-        uint32_t want = bit_length(n_kmers) + 1;
+        uint32_t want = bit_length(n_part) + 1;
         if (want < 16) want = 16;
-        if (he.key_bits > want) shift = he.key_bits - want;
+        if (part_bits > want) {
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            const bool affordable = (ix->sharded || partial) && max_rel < (1ull << 33) && max_rel * 4ull + (1ull << 30) < free_b / 3;
+            if (!affordable) shift = part_bits - want;
+        }
     }
-    if (he.key_bits > 32 + shift) shift = he.key_bits - 32;  // directory indices stay below 2^32
-    const uint64_t dir_entries = ((key_space - 1) >> shift) + 2;
+    if (partial && shift != 0) return fail(KMER_B200_ERR_UNSUPPORTED, "key-range parts need a dense directory");
+    if (part_bits > 32 + shift) shift = part_bits - 32;  // directory indices stay below 2^32
+    const uint64_t dir_entries = (max_rel >> shift) + 2;
     KB_TRY(dev_alloc(ix, &he.d_dir, dir_entries, true));
-    pf.begin(K_DIRECTORY_FILL, (double)key_bytes * n_kmers + 4.0 * dir_entries);
-    launch_directory_fill(he.d_keys, key_bytes, n_kmers, shift, dir_entries, he.d_dir, st);
+    pf.begin(K_DIRECTORY_FILL, (double)key_bytes * n_part + 4.0 * dir_entries);
+    launch_directory_fill(he.d_keys, key_bytes, n_part, shift, dir_entries, he.d_dir, st);
     pf.end();
     KB_CUDA(cudaGetLastError());
     if (shift == 0) {
@@ -532,19 +599,21 @@ int build_element(kmer_b200_index *ix, uint32_t k, HostElement &he, bool auxilia
         // wants a hash of an entry, the sub-k slab check, recomputes it from the text): 4 bytes per k-mer of HBM back
         dev_free(ix, (uint8_t *)he.d_keys);
         he.d_keys = nullptr;
-        ix->device_bytes -= n_kmers * key_bytes;
+        ix->device_bytes -= std::max<uint64_t>(n_part, 1) * key_bytes;
     }
 
     he.dev.k = k;
     he.dev.shift = shift;
-    he.dev.n_kmers = n_kmers;
+    he.dev.n_kmers = n_part;
     he.dev.dir_entries = dir_entries;
     he.dev.key_space = key_space;
     he.dev.dir = he.d_dir;
     he.dev.keys = he.d_keys;
     he.dev.pos = he.d_pos;
     he.dev.key_bytes = key_bytes;
-    he.bytes = n_kmers * (sizeof(uint32_t) + (he.d_keys ? key_bytes : 0)) + dir_entries * sizeof(uint32_t);
+    he.dev.key_lo = partial ? part.lo : 0;
+    he.dev.key_hi = partial ? part.hi : UINT64_MAX;
+    he.bytes = n_part * (sizeof(uint32_t) + (he.d_keys ? key_bytes : 0)) + dir_entries * sizeof(uint32_t);
     if (!auxiliary)
         ix->max_avg_bucket = std::max(ix->max_avg_bucket, (double)n_kmers / (double)std::min<uint64_t>(key_space, n_kmers));
     return 0;
@@ -595,6 +664,8 @@ int new_index(uint64_t n, uint32_t sigma, const uint32_t *ks, uint32_t n_ks, con
     if (sharded && !reaches_end && cfg.halo + 1 < k_max)
         return fail(KMER_B200_ERR_INVALID_ARGUMENT, "interior shards need halo >= max k - 1");
 
+    if (cfg.key_parts > 1 && cfg.key_part >= cfg.key_parts) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "key_part must be < key_parts");
+    if (cfg.key_parts > 1 && sharded) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "key-range parts index the whole text: no position-range shard");
     int device = cfg.device;
     if (device < 0) {
         cudaError_t e = cudaGetDevice(&device);
@@ -918,9 +989,16 @@ struct PendingSearch {
 
 // count pass. d_present4 != nullptr: deferred mode -- the per-part presence flags go to d_present4 and the
 // whole-text presence rule is applied later by search_finish().
+// queries packed before they reached the device (host threads of the host-buffer search): see SearchArgs::q_packed
+struct PackedQueries {
+    const uint64_t *d_words;
+    const uint16_t *d_lens;
+    uint32_t stride;
+};
+
 int search_begin(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off, uint64_t Q, uint64_t max_len,
                  uint32_t mode, const void *d_present_global, uint32_t present_format, uint32_t *d_present4,
-                 PendingSearch *p) {
+                 PendingSearch *p, const PackedQueries *packed = nullptr) {
     using namespace kb;
     if (mode == UINT32_MAX) mode = ix->cfg.mode;
     if (mode > KMER_B200_MODE_CORRECT) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "unknown mode");
@@ -956,6 +1034,11 @@ int search_begin(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off,
     a.index = ix->d_index;
     a.q_ranks = d_q;
     a.q_offsets = d_off;
+    if (packed) {
+        a.q_packed = packed->d_words;
+        a.q_lens16 = packed->d_lens;
+        a.q_stride = packed->stride;
+    }
     a.n_queries = Q;
     a.mode = mode;
     a.present_global = present_format == 0 ? (const uint64_t *)d_present_global : nullptr;
@@ -1087,9 +1170,9 @@ int search_finish(PendingSearch *p, const uint32_t *d_present4_global, SearchFla
 // queries already on the device; result stays on the device
 int search_device_impl(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off, uint64_t Q, uint64_t max_len,
                        uint32_t mode, const void *d_present_global, uint32_t present_format, SearchFlavor flavor,
-                       kmer_b200_result **out) {
+                       kmer_b200_result **out, const PackedQueries *packed = nullptr) {
     PendingSearch p;
-    KB_TRY(search_begin(ix, d_q, d_off, Q, max_len, mode, d_present_global, present_format, nullptr, &p));
+    KB_TRY(search_begin(ix, d_q, d_off, Q, max_len, mode, d_present_global, present_format, nullptr, &p, packed));
     return search_finish(&p, nullptr, flavor, out);
 }
 
@@ -1135,6 +1218,7 @@ int kmer_b200_create_from_device(const uint8_t *d_ranks, uint64_t n, uint32_t si
 
 int kmer_b200_save(kmer_b200_index *ix, const char *path) {
     if (!ix || !path) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
+    if (ix->cfg.key_parts > 1) return fail(KMER_B200_ERR_UNSUPPORTED, "a key-range part is not a whole index: assemble it first");
     DeviceGuard guard(ix->device);
     std::lock_guard<std::mutex> lock(ix->mu);
     FILE *f = std::fopen(path, "wb");
@@ -1242,7 +1326,7 @@ int kmer_b200_load(const char *path, const kmer_b200_config *cfg_in, kmer_b200_i
                 }
             }
             he.dev = kb::Element{fe.k, fe.shift, fe.n_kmers, fe.dir_entries, fe.key_space, he.d_dir, he.d_keys, he.d_pos,
-                                 fe.key_bytes, 0};
+                                 fe.key_bytes, 0, 0, UINT64_MAX};
             he.bytes = fe.n_kmers * (4 + (fe.has_keys ? fe.key_bytes : 0)) + fe.dir_entries * 4;
             ix->max_avg_bucket = std::max(ix->max_avg_bucket,
                                           (double)fe.n_kmers / (double)std::min<uint64_t>(fe.key_space, fe.n_kmers));
@@ -1266,9 +1350,11 @@ void kmer_b200_destroy(kmer_b200_index *ix) {
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     ix->prof.resolve();
     for (auto &he : ix->elems) {
-        dev_free(ix, he.d_dir);
+        if (!he.adopted) {
+            dev_free(ix, he.d_dir);
+            dev_free(ix, he.d_pos);
+        }
         dev_free(ix, (uint8_t *)he.d_keys);
-        dev_free(ix, he.d_pos);
     }
     dev_free(ix, ix->d_text);
     dev_free(ix, ix->d_sum_off);
@@ -1425,6 +1511,12 @@ int kmer_b200_presence_batch_device(kmer_b200_index *ix, const uint8_t *d_q, con
     return KMER_B200_OK;
 }
 
+__global__ void __launch_bounds__(256) add_base32_kernel(const uint32_t *__restrict__ src, uint64_t n, uint32_t base,
+                                                         uint32_t *__restrict__ dst) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i] + base;
+}
+
 __global__ void __launch_bounds__(256) add_base_kernel(uint64_t *__restrict__ v, uint64_t n, uint64_t base) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) v[i] += base;
@@ -1555,6 +1647,196 @@ static int search_batch_host_pipelined(kmer_b200_index *ix, const uint8_t *q_ran
     return cleanup(0);
 }
 
+// Large host batches, packed on the host: the batch is cut into chunks of queries; the host threads pack chunk c + 2
+// (1 byte per rank -> b-bit words, fixed stride, plus 16-bit lengths: a third of the bytes for dna4) while chunk c + 1
+// crosses PCIe and chunk c is searched; offsets and status of finished chunks leave on the other copy engine. The input
+// may be pageable memory: the packers read it directly, only the packed staging ring is pinned. The call costs about
+// as much as the slower of "pack the batch once with all host cores" and "move the packed bytes once".
+static int search_batch_host_packed(kmer_b200_index *ix, const uint8_t *q_ranks, const uint64_t *q_offsets, uint64_t Q,
+                                    uint32_t mode, kmer_b200_result **out) {
+    constexpr int kChunks = 16, kRing = 3;
+    cudaStream_t st = ix->stream;
+    if (!ix->copy_in) {
+        static std::mutex mu;
+        static cudaStream_t cached[64][2] = {};
+        std::lock_guard<std::mutex> lock(mu);
+        const int d = ix->device & 63;
+        if (!cached[d][0]) {
+            KB_CUDA(cudaStreamCreateWithFlags(&cached[d][0], cudaStreamNonBlocking));
+            KB_CUDA(cudaStreamCreateWithFlags(&cached[d][1], cudaStreamNonBlocking));
+        }
+        ix->copy_in = cached[d][0];
+        ix->copy_out = cached[d][1];
+    }
+    kb::HostPool &pool = kb::HostPool::instance();
+    const unsigned T = pool.threads();
+    const uint32_t spw = 64 / ix->bits;
+    const uint64_t per = (Q + kChunks - 1) / kChunks;
+    uint64_t c0[kChunks + 1];
+    for (int c = 0; c <= kChunks; ++c) c0[c] = std::min<uint64_t>((uint64_t)c * per, Q);
+
+    // pinned staging ring: lengths first (their maximum fixes the chunk's stride), then the packed words
+    const uint64_t max_stride = 16;
+    uint16_t *h_lens[kRing] = {};
+    uint64_t *h_words[kRing] = {};
+    size_t cap_lens[kRing] = {}, cap_words[kRing] = {};
+    uint64_t *d_words[kChunks] = {};
+    uint16_t *d_lens[kChunks] = {};
+    uint32_t stride[kChunks] = {};
+    uint64_t max_len[kChunks] = {};
+    kmer_b200_result *chunk_res[kChunks] = {};
+    cudaEvent_t ev_in[kChunks] = {}, ev_done[kChunks] = {}, ev_slot[kRing] = {};
+    kmer_b200_result *res = nullptr;
+    std::vector<uint64_t> part_max(T * 4);
+    std::vector<uint8_t> part_ok(T * 4);
+    bool unsupported = false, bad_rank = false;
+    auto cleanup = [&](int code) {
+        pool.wait();
+        cudaStreamSynchronize(ix->copy_in);
+        cudaStreamSynchronize(ix->copy_out);
+        cudaStreamSynchronize(st);
+        for (int c = 0; c < kChunks; ++c) {
+            if (chunk_res[c]) kmer_b200_result_free(chunk_res[c]);
+            if (ev_in[c]) cudaEventDestroy(ev_in[c]);
+            if (ev_done[c]) cudaEventDestroy(ev_done[c]);
+            dev_free(ix, d_words[c]);
+            dev_free(ix, d_lens[c]);
+        }
+        for (int r = 0; r < kRing; ++r) {
+            if (ev_slot[r]) cudaEventDestroy(ev_slot[r]);
+            pinned_put(h_lens[r], cap_lens[r]);
+            pinned_put(h_words[r], cap_words[r]);
+        }
+        if (code != 0 && res) kmer_b200_result_free(res);
+        return code;
+    };
+    for (int r = 0; r < kRing; ++r) {
+        h_lens[r] = (uint16_t *)pinned_get(per * sizeof(uint16_t), &cap_lens[r]);
+        h_words[r] = (uint64_t *)pinned_get(per * 4 * sizeof(uint64_t), &cap_words[r]);  // grown when a chunk needs more
+        if (!h_lens[r] || !h_words[r]) return cleanup(fail(KMER_B200_ERR_OUT_OF_MEMORY, "pinned host allocation failed"));
+        cudaEventCreateWithFlags(&ev_slot[r], cudaEventDisableTiming);
+    }
+    for (int c = 0; c < kChunks; ++c) {
+        cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming);
+    }
+    res = new (std::nothrow) kmer_b200_result();
+    if (!res) return cleanup(fail(KMER_B200_ERR_OUT_OF_MEMORY, "host allocation failed"));
+    res->index = ix;
+    res->on_device = false;
+    res->n_queries = Q;
+    res->offsets = (uint64_t *)pinned_get((Q + 1) * sizeof(uint64_t), &res->cap_offsets);
+    res->status = (uint8_t *)pinned_get(Q, &res->cap_status);
+    if (!res->offsets || !res->status) return cleanup(fail(KMER_B200_ERR_OUT_OF_MEMORY, "pinned host allocation failed"));
+
+    // stage 1 of chunk c (blocking, short): lengths + longest query -> stride; stage 2 (asynchronous): pack
+    auto start_pack = [&](int c) -> int {
+        const uint64_t qa = c0[c], qb = c0[c + 1];
+        if (qb == qa) return 0;
+        const int slot = c % kRing;
+        if (c >= kRing) cudaEventSynchronize(ev_slot[slot]);  // the slot's previous H2D has left the staging buffers
+        pool.run(T * 4, [&, qa, qb, slot](unsigned t) { part_max[t] = kb::query_lengths_host(q_offsets, qa, qb, h_lens[slot], t, T * 4); });
+        uint64_t mx = 0;
+        for (uint64_t v : part_max) mx = std::max(mx, v);
+        max_len[c] = mx;
+        stride[c] = (uint32_t)std::max<uint64_t>(1, (mx + spw - 1) / spw);
+        if (mx > 65535 || stride[c] > max_stride) {
+            unsupported = true;
+            return 0;
+        }
+        const size_t need = (qb - qa) * stride[c] * sizeof(uint64_t);
+        if (need > cap_words[slot]) {
+            pinned_put(h_words[slot], cap_words[slot]);
+            h_words[slot] = (uint64_t *)pinned_get(need, &cap_words[slot]);
+            if (!h_words[slot]) return fail(KMER_B200_ERR_OUT_OF_MEMORY, "pinned host allocation failed");
+        }
+        std::fill(part_ok.begin(), part_ok.end(), 1);
+        const uint32_t sc = stride[c];
+        pool.submit(T * 4, [&, qa, qb, slot, sc](unsigned t) {
+            part_ok[t] = kb::pack_queries_host(q_ranks, q_offsets, qa, qb, ix->bits, ix->sigma, sc, h_words[slot], t, T * 4) ? 1 : 0;
+        });
+        return 0;
+    };
+    auto finish_pack_and_upload = [&](int c) -> int {
+        const uint64_t qa = c0[c], qb = c0[c + 1];
+        pool.wait();
+        if (qb == qa || unsupported) return 0;
+        for (uint8_t ok : part_ok) bad_rank = bad_rank || !ok;
+        const int slot = c % kRing;
+        const uint64_t Qc = qb - qa;
+        KB_TRY(dev_alloc(ix, &d_words[c], Qc * stride[c], false));
+        KB_TRY(dev_alloc(ix, &d_lens[c], Qc, false));
+        cudaEvent_t ev_alloc;  // the allocations are ordered on `st`
+        cudaEventCreateWithFlags(&ev_alloc, cudaEventDisableTiming);
+        cudaEventRecord(ev_alloc, st);
+        cudaStreamWaitEvent(ix->copy_in, ev_alloc, 0);
+        cudaEventDestroy(ev_alloc);
+        cudaMemcpyAsync(d_words[c], h_words[slot], Qc * stride[c] * sizeof(uint64_t), cudaMemcpyHostToDevice, ix->copy_in);
+        cudaMemcpyAsync(d_lens[c], h_lens[slot], Qc * sizeof(uint16_t), cudaMemcpyHostToDevice, ix->copy_in);
+        cudaEventRecord(ev_in[c], ix->copy_in);
+        cudaEventRecord(ev_slot[slot], ix->copy_in);
+        return 0;
+    };
+
+    {
+        cudaEvent_t ev0;  // the copy-out stream must not run ahead of work already queued on `st`
+        cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming);
+        cudaEventRecord(ev0, st);
+        cudaStreamWaitEvent(ix->copy_out, ev0, 0);
+        cudaEventDestroy(ev0);
+    }
+    if (int s = start_pack(0)) return cleanup(s);
+    if (int s = finish_pack_and_upload(0)) return cleanup(s);
+    if (kChunks > 1)
+        if (int s = start_pack(1)) return cleanup(s);
+    uint64_t base = 0;
+    for (int c = 0; c < kChunks && !unsupported; ++c) {
+        if (c + 1 < kChunks) {
+            if (int s = finish_pack_and_upload(c + 1)) return cleanup(s);
+            if (c + 2 < kChunks)
+                if (int s = start_pack(c + 2)) return cleanup(s);
+        }
+        if (unsupported || bad_rank) break;
+        const uint64_t qa = c0[c], qb = c0[c + 1], Qc = qb - qa;
+        if (Qc == 0) continue;
+        cudaStreamWaitEvent(st, ev_in[c], 0);
+        PackedQueries pk{d_words[c], d_lens[c], stride[c]};
+        int s = search_device_impl(ix, nullptr, nullptr, Qc, max_len[c], mode, nullptr, 0, kFlavorFull, &chunk_res[c], &pk);
+        if (s != 0) return cleanup(s);
+        kmer_b200_result *cr = chunk_res[c];
+        if (base) add_base_kernel<<<(unsigned)((Qc + 1 + 255) / 256), 256, 0, st>>>(cr->offsets, Qc + 1, base);
+        cudaEventRecord(ev_done[c], st);
+        cudaStreamWaitEvent(ix->copy_out, ev_done[c], 0);
+        cudaMemcpyAsync(res->offsets + qa, cr->offsets, Qc * sizeof(uint64_t), cudaMemcpyDeviceToHost, ix->copy_out);
+        cudaMemcpyAsync(res->status + qa, cr->status, Qc, cudaMemcpyDeviceToHost, ix->copy_out);
+        base += cr->n_positions;
+    }
+    if (bad_rank) return cleanup(fail(KMER_B200_ERR_INVALID_RANK, "a query contains a rank >= sigma"));
+    if (unsupported) return cleanup(KMER_B200_ERR_UNSUPPORTED);  // the caller falls back to the unpacked pipeline
+    res->n_positions = base;
+    const size_t pos_bytes = base * sizeof(uint32_t);
+    if (pos_bytes > (8ull << 30)) {
+        res->positions = (uint32_t *)std::malloc(pos_bytes);
+        res->positions_pageable = true;
+        res->cap_positions = pos_bytes;
+    } else {
+        res->positions = (uint32_t *)pinned_get(pos_bytes, &res->cap_positions);
+    }
+    if (!res->positions) return cleanup(fail(KMER_B200_ERR_OUT_OF_MEMORY, "host allocation for the positions failed"));
+    uint64_t at = 0;
+    for (int c = 0; c < kChunks; ++c) {
+        if (!chunk_res[c] || !chunk_res[c]->n_positions) continue;
+        cudaMemcpyAsync(res->positions + at, chunk_res[c]->positions, chunk_res[c]->n_positions * sizeof(uint32_t),
+                        cudaMemcpyDeviceToHost, ix->copy_out);
+        at += chunk_res[c]->n_positions;
+    }
+    cudaError_t e = cudaStreamSynchronize(ix->copy_out);
+    res->offsets[Q] = base;
+    if (e != cudaSuccess) return cleanup(fail(KMER_B200_ERR_CUDA, std::string("search (D2H): ") + cudaGetErrorString(e)));
+    *out = res;
+    return cleanup(0);
+}
+
 static int search_batch_host(kmer_b200_index *ix, const uint8_t *q_ranks, const uint64_t *q_offsets, uint64_t Q,
                              uint32_t mode, const uint8_t *lut256, kmer_b200_result **out) {
     if (!ix || !out || !q_offsets) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
@@ -1565,8 +1847,22 @@ static int search_batch_host(kmer_b200_index *ix, const uint8_t *q_ranks, const 
     const uint64_t n_sym = q_offsets[Q] - q_offsets[0];
     if (n_sym && !q_ranks) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "q_ranks is null");
     // batches whose transfer dominates (>= 256 MiB over PCIe) are pipelined in chunks
-    if (!lut256 && Q >= (1u << 18) && n_sym + Q * 17 >= (256ull << 20) && !std::getenv("KMER_B200_NO_PIPELINE"))
+    if (!lut256 && Q >= (1u << 18) && n_sym + Q * 17 >= (256ull << 20) && !std::getenv("KMER_B200_NO_PIPELINE")) {
+        // Which pipeline: pinned input crosses PCIe as it is (the copy engine reads it at ~55 GB/s; 16 host cores pack
+        // ~30 GB/s of variable-length queries, measured on the GPU box, so packing first would be slower). Pageable
+        // input cannot be DMA-ed directly -- the driver would stage it at a fraction of that rate -- so the host threads
+        // pack it straight out of the caller's memory into a pinned ring (a third of the bytes for dna4).
+        // KMER_B200_HOST_PACK=1 / 0 forces the choice.
+        cudaPointerAttributes attr{};
+        bool pageable = cudaPointerGetAttributes(&attr, q_ranks) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
+        cudaGetLastError();
+        if (const char *env = std::getenv("KMER_B200_HOST_PACK")) pageable = std::atoi(env) != 0;
+        if (pageable) {
+            const int s = search_batch_host_packed(ix, q_ranks, q_offsets, Q, mode, out);
+            if (s != KMER_B200_ERR_UNSUPPORTED) return s;  // queries longer than 16 packed words: the unpacked pipeline
+        }
         return search_batch_host_pipelined(ix, q_ranks, q_offsets, Q, mode, out);
+    }
     uint8_t *d_q = nullptr;
     uint64_t *d_off = nullptr;
     unsigned long long *d_max = nullptr;
@@ -1730,8 +2026,78 @@ int kmer_b200_element_hashes(kmer_b200_index *ix, uint32_t e, uint64_t *out, uin
         std::vector<uint32_t> tmp(n);
         KB_CUDA(cudaMemcpyAsync(tmp.data(), he.d_keys, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ix->stream));
         KB_CUDA(cudaStreamSynchronize(ix->stream));
-        for (uint64_t i = 0; i < n; ++i) out[i] = tmp[i];
+        for (uint64_t i = 0; i < n; ++i) out[i] = tmp[i] + he.dev.key_lo;
     }
+    return KMER_B200_OK;
+}
+
+int kmer_b200_element_part(const kmer_b200_index *ix, uint32_t e, kmer_b200_part *out) {
+    if (!ix || !out || e >= ix->ks.size()) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad element");
+    const HostElement &he = ix->elems[e];
+    if (he.dev.shift != 0) return fail(KMER_B200_ERR_UNSUPPORTED, "parts are exported from dense directories only");
+    out->key_lo = he.dev.key_lo;
+    out->key_hi = he.dev.key_hi == UINT64_MAX ? he.dev.key_space : he.dev.key_hi;
+    out->n_kmers = he.dev.n_kmers;
+    out->directory_entries = he.dev.dir_entries;
+    out->d_positions = he.d_pos;
+    out->d_directory = he.d_dir;
+    return KMER_B200_OK;
+}
+
+int kmer_b200_export_directory(kmer_b200_index *ix, uint32_t e, uint64_t base, uint64_t n, uint32_t *d_dst) {
+    if (!ix || !d_dst || e >= ix->ks.size() || n > ix->elems[e].dev.dir_entries)
+        return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad argument");
+    DeviceGuard guard(ix->device);
+    if (n) add_base32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ix->stream>>>(ix->elems[e].d_dir, n, (uint32_t)base, d_dst);
+    KB_CUDA(cudaGetLastError());
+    return KMER_B200_OK;
+}
+
+int kmer_b200_adopt_element(kmer_b200_index *ix, uint32_t e, const uint32_t *d_positions, uint64_t n_kmers,
+                            const uint32_t *d_directory, uint64_t directory_entries) {
+    if (!ix || !d_positions || !d_directory || e >= ix->ks.size()) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad argument");
+    HostElement &he = ix->elems[e];
+    if (n_kmers != ix->n - he.dev.k + 1 || directory_entries != he.dev.key_space + 1)
+        return fail(KMER_B200_ERR_INVALID_ARGUMENT, "adopt: array sizes do not describe the whole index (n - k + 1 positions, sigma^k + 1 directory entries)");
+    DeviceGuard guard(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    if (!he.adopted) {
+        dev_free(ix, he.d_dir);
+        dev_free(ix, he.d_pos);
+        ix->device_bytes -= he.bytes;
+    }
+    dev_free(ix, (uint8_t *)he.d_keys);
+    he.d_keys = nullptr;
+    he.adopted = true;
+    he.d_pos = const_cast<uint32_t *>(d_positions);
+    he.d_dir = const_cast<uint32_t *>(d_directory);
+    he.dev.shift = 0;
+    he.dev.n_kmers = n_kmers;
+    he.dev.dir_entries = directory_entries;
+    he.dev.dir = he.d_dir;
+    he.dev.keys = nullptr;
+    he.dev.pos = he.d_pos;
+    he.dev.key_lo = 0;
+    he.dev.key_hi = UINT64_MAX;
+    he.bytes = n_kmers * 4 + directory_entries * 4;
+    ix->host_index.elem[e] = he.dev;
+    bool all = true;
+    for (size_t i = 0; i < ix->ks.size(); ++i) all = all && ix->elems[i].adopted;
+    if (all) {
+        // the index is whole again: elements built from now on (auxiliary k' = m elements) cover the whole key space;
+        // those built for the part are dropped
+        ix->cfg.key_parts = 0;
+        ix->cfg.key_part = 0;
+        for (size_t i = ix->ks.size(); i < ix->elems.size(); ++i) {
+            dev_free(ix, ix->elems[i].d_dir);
+            dev_free(ix, ix->elems[i].d_pos);
+            dev_free(ix, (uint8_t *)ix->elems[i].d_keys);
+        }
+        ix->elems.resize(ix->ks.size());
+        std::memset(ix->host_index.aux_for_len, 0xFF, sizeof(ix->host_index.aux_for_len));
+    }
+    KB_CUDA(cudaMemcpyAsync(ix->d_index, &ix->host_index, sizeof(kb::DeviceIndex), cudaMemcpyHostToDevice, ix->stream));
+    KB_CUDA(cudaStreamSynchronize(ix->stream));
     return KMER_B200_OK;
 }
 

@@ -111,6 +111,8 @@ struct Element {
     const uint32_t *pos;
     uint32_t key_bytes;  // 4 or 8
     uint32_t pad_;
+    uint64_t key_lo, key_hi;  // the element indexes the k-mers with hash in [key_lo, key_hi): a key-range part of a
+                              // multi-GPU build, else [0, 2^64 - 1]; dir and keys are relative to key_lo
 };
 
 __device__ __forceinline__ uint64_t element_key(const Element &E, uint64_t i) {

@@ -1,0 +1,185 @@
+// See host_pack.h. Plain C++ (no CUDA): compiled by the host compiler through nvcc.
+#include "host_pack.h"
+
+#include <immintrin.h>
+
+#include <algorithm>
+#include <condition_variable>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace kb {
+
+struct HostPool::Impl {
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::function<void(unsigned)> fn;
+    unsigned n_tasks = 0, next = 0, running = 0;
+    uint64_t generation = 0;
+    bool stop = false;
+
+    void loop() {
+        uint64_t seen = 0;
+        std::unique_lock<std::mutex> lock(mu);
+        for (;;) {
+            cv_work.wait(lock, [&] { return stop || (generation != seen && next < n_tasks); });
+            if (stop) return;
+            while (next < n_tasks) {
+                const unsigned i = next++;
+                ++running;
+                lock.unlock();
+                fn(i);
+                lock.lock();
+                --running;
+            }
+            seen = generation;
+            if (running == 0) cv_done.notify_all();
+        }
+    }
+};
+
+HostPool::HostPool() : impl_(new Impl) {
+    unsigned n = std::thread::hardware_concurrency();
+    n = std::max(1u, std::min(n, 32u));
+    for (unsigned t = 0; t < n; ++t) impl_->workers.emplace_back([this] { impl_->loop(); });
+}
+
+HostPool::~HostPool() {
+    {
+        std::lock_guard<std::mutex> lock(impl_->mu);
+        impl_->stop = true;
+    }
+    impl_->cv_work.notify_all();
+    for (auto &w : impl_->workers) w.join();
+    delete impl_;
+}
+
+HostPool &HostPool::instance() {
+    static HostPool pool;
+    return pool;
+}
+
+unsigned HostPool::threads() const { return (unsigned)impl_->workers.size(); }
+
+void HostPool::submit(unsigned n_tasks, std::function<void(unsigned)> fn) {
+    std::unique_lock<std::mutex> lock(impl_->mu);
+    impl_->cv_done.wait(lock, [&] { return impl_->next >= impl_->n_tasks && impl_->running == 0; });
+    impl_->fn = std::move(fn);
+    impl_->n_tasks = n_tasks;
+    impl_->next = 0;
+    ++impl_->generation;
+    lock.unlock();
+    impl_->cv_work.notify_all();
+}
+
+void HostPool::wait() {
+    std::unique_lock<std::mutex> lock(impl_->mu);
+    impl_->cv_done.wait(lock, [&] { return impl_->next >= impl_->n_tasks && impl_->running == 0; });
+}
+
+uint64_t query_lengths_host(const uint64_t *q_offsets, uint64_t q_begin, uint64_t q_end, uint16_t *lens, unsigned part,
+                            unsigned n_parts) {
+    const uint64_t n = q_end - q_begin;
+    const uint64_t lo = q_begin + n * part / n_parts, hi = q_begin + n * (part + 1) / n_parts;
+    uint64_t mx = 0;
+    for (uint64_t i = lo; i < hi; ++i) {
+        const uint64_t m = q_offsets[i + 1] - q_offsets[i];
+        lens[i - q_begin] = (uint16_t)m;
+        mx = std::max(mx, m);
+    }
+    return mx;
+}
+
+namespace {
+
+// 8 ranks (byte j = symbol j) -> 8 * bits bits, symbol 0 on top. This file is compiled for x86-64-v3 (BMI2: one PEXT
+// per 8 symbols); the shift-and-mask form is the portable fallback.
+template <int BITS>
+inline uint64_t pack8(uint64_t v) {
+#if defined(__BMI2__)
+    constexpr uint64_t mask = BITS == 2 ? 0x0303030303030303ull : BITS == 4 ? 0x0F0F0F0F0F0F0F0Full : ~0ull;
+    return _pext_u64(__builtin_bswap64(v), mask);
+#else
+    uint64_t r = 0;
+    for (int j = 0; j < 8; ++j) r |= ((v >> (8 * j)) & ((1ull << BITS) - 1)) << (BITS * (7 - j));
+    return r;
+#endif
+}
+
+// `safe_end`: reading 8 bytes at any address below it is inside the caller's buffer (a query's last chunk is fetched
+// with one unconditional 8-byte load and masked, instead of a variable-length copy)
+template <int BITS>
+bool pack_range(const uint8_t *q_ranks, const uint64_t *q_offsets, uint64_t q_begin, uint64_t lo, uint64_t hi, uint32_t sigma,
+                uint32_t stride, uint64_t *words, const uint8_t *safe_end) {
+    constexpr uint32_t SPW = 64 / BITS;  // symbols per word
+    constexpr uint32_t CPW = SPW / 8;    // 8-symbol chunks per word
+    const uint64_t guard = (uint64_t)(0x80u - (sigma > 128 ? 128u : sigma)) * 0x0101010101010101ull;
+    uint64_t inval = 0;  // bit 7 of a byte ends up set <=> that rank is >= sigma (sigma <= 128)
+    bool bad = false;
+    uint64_t off = q_offsets[lo];
+    for (uint64_t i = lo; i < hi; ++i) {
+        const uint64_t next = q_offsets[i + 1];
+        const uint8_t *src = q_ranks + off;
+        const uint32_t m = (uint32_t)(next - off);
+        off = next;
+        uint64_t *dst = words + (i - q_begin) * stride;
+        const uint32_t n_words = (m + SPW - 1) / SPW;
+        uint32_t w = 0;
+        if (src + (size_t)n_words * SPW + 8 <= safe_end) {
+            // branch-free per word: always CPW 8-byte loads (those behind the query's end are masked to zero; they stay
+            // inside the batch buffer), one PEXT each
+            for (; w < n_words; ++w) {
+                const uint8_t *p = src + w * SPW;
+                const int32_t left = (int32_t)(m - w * SPW);  // symbols of the query from this word on, >= 1
+                uint64_t acc = 0;
+#pragma GCC unroll 8
+                for (uint32_t c = 0; c < CPW; ++c) {
+                    uint64_t v;
+                    std::memcpy(&v, p + 8 * c, 8);
+                    const int32_t l = left - (int32_t)(8 * c);
+                    const uint64_t keep = l >= 8 ? ~0ull : (l <= 0 ? 0ull : ((1ull << (8 * l)) - 1));
+                    v &= keep;
+                    inval |= (v + guard) | v;
+                    acc |= pack8<BITS>(v) << (64 - 8 * BITS * (c + 1));
+                }
+                dst[w] = acc;
+            }
+        } else {  // the last few queries of the batch: byte by byte
+            for (; w < n_words; ++w) {
+                uint64_t acc = 0;
+                for (uint32_t c = 0; c < CPW; ++c) {
+                    uint64_t v = 0;
+                    for (uint32_t j = 0; j < 8; ++j) {
+                        const uint32_t sidx = w * SPW + 8 * c + j;
+                        if (sidx < m) v |= (uint64_t)src[sidx] << (8 * j);
+                    }
+                    inval |= (v + guard) | v;
+                    acc |= pack8<BITS>(v) << (64 - 8 * BITS * (c + 1));
+                }
+                dst[w] = acc;
+            }
+        }
+        for (; w < stride; ++w) dst[w] = 0;
+        if (sigma > 128)
+            for (uint32_t j = 0; j < m; ++j) bad |= src[j] >= sigma;
+    }
+    if (sigma <= 128) bad = (inval & 0x8080808080808080ull) != 0;
+    return !bad;
+}
+
+}  // namespace
+
+bool pack_queries_host(const uint8_t *q_ranks, const uint64_t *q_offsets, uint64_t q_begin, uint64_t q_end, uint32_t bits,
+                       uint32_t sigma, uint32_t stride, uint64_t *words, unsigned part, unsigned n_parts) {
+    const uint64_t n = q_end - q_begin;
+    const uint64_t lo = q_begin + n * part / n_parts, hi = q_begin + n * (part + 1) / n_parts;
+    const uint8_t *safe_end = q_ranks + q_offsets[q_end];  // the batch's last byte + 1 (the buffer may end there)
+    if (bits == 2) return pack_range<2>(q_ranks, q_offsets, q_begin, lo, hi, sigma, stride, words, safe_end);
+    if (bits == 4) return pack_range<4>(q_ranks, q_offsets, q_begin, lo, hi, sigma, stride, words, safe_end);
+    return pack_range<8>(q_ranks, q_offsets, q_begin, lo, hi, sigma, stride, words, safe_end);
+}
+
+}  // namespace kb

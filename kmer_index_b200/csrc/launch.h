@@ -43,7 +43,7 @@ uint32_t filter_tiles(uint64_t n_kmers);
 void launch_owned_count(const PackedText &text, uint32_t k, uint64_t n_kmers, uint64_t lo, uint64_t hi, uint64_t *d_tile_counts,
                         cudaStream_t stream);
 void launch_owned_write(const PackedText &text, uint32_t k, uint64_t n_kmers, uint64_t lo, uint64_t hi, const uint64_t *d_tile_offsets,
-                        uint2 *d_out, cudaStream_t stream);
+                        uint32_t *d_out_keys, uint32_t *d_out_vals, cudaStream_t stream);
 void launch_digit_histograms_pairs(const uint2 *d_pairs, uint64_t n, uint32_t n_passes, uint32_t w_bits, uint32_t *d_hist_scratch,
                                    uint32_t *d_digit_base, cudaStream_t stream);
 
@@ -61,6 +61,12 @@ struct SearchArgs {
     const DeviceIndex *index;        // device pointer
     const uint8_t *q_ranks;          // device
     const uint64_t *q_offsets;       // device, [Q + 1]
+    // alternative input (q_packed != null; q_ranks / q_offsets unused): queries already packed like the text, b bits
+    // per symbol MSB-first, query i in words [i * q_stride, (i + 1) * q_stride), its length in q_lens16[i]; ranks were
+    // validated by the packer (host threads of kmer_b200_search_batch)
+    const uint64_t *q_packed;
+    const uint16_t *q_lens16;
+    uint32_t q_stride;
     uint64_t n_queries;
     uint32_t mode;                   // kmer_b200_mode
     uint32_t group;                  // lanes per query: 1, 2, 4, 8 or 32

@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(kFilterThreads) owned_count_kernel(PackedText 
 
 __global__ void __launch_bounds__(kFilterThreads) owned_write_kernel(PackedText text, uint32_t k, uint64_t n_kmers, uint64_t lo,
                                                                       uint64_t hi, const uint64_t *__restrict__ tile_offsets,
-                                                                      uint2 *__restrict__ out) {
+                                                                      uint32_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals) {
     __shared__ uint32_t warp_sums[kFilterThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t keys[kFilterItems];
@@ -552,10 +552,14 @@ __global__ void __launch_bounds__(kFilterThreads) owned_write_kernel(PackedText 
     __syncthreads();
     uint32_t before = incl - c;
     for (int w = 0; w < warp; ++w) before += warp_sums[w];
-    uint2 *o = out + tile_offsets[blockIdx.x] + before;
+    uint64_t o = tile_offsets[blockIdx.x] + before;
 #pragma unroll
     for (int j = 0; j < kFilterItems; ++j)
-        if ((m >> j) & 1u) *o++ = make_uint2(keys[j], (uint32_t)(i0 + j));
+        if ((m >> j) & 1u) {
+            out_keys[o] = keys[j];
+            out_vals[o] = (uint32_t)(i0 + j);
+            ++o;
+        }
 }
 
 // ghist[p][v] over a pair array (all passes in one sweep)
@@ -619,8 +623,9 @@ void launch_owned_count(const PackedText &text, uint32_t k, uint64_t n_kmers, ui
 }
 
 void launch_owned_write(const PackedText &text, uint32_t k, uint64_t n_kmers, uint64_t lo, uint64_t hi, const uint64_t *d_tile_offsets,
-                        uint2 *d_out, cudaStream_t stream) {
-    owned_write_kernel<<<filter_tiles(n_kmers), kFilterThreads, 0, stream>>>(text, k, n_kmers, lo, hi, d_tile_offsets, d_out);
+                        uint32_t *d_out_keys, uint32_t *d_out_vals, cudaStream_t stream) {
+    owned_write_kernel<<<filter_tiles(n_kmers), kFilterThreads, 0, stream>>>(text, k, n_kmers, lo, hi, d_tile_offsets, d_out_keys,
+                                                                            d_out_vals);
 }
 
 void launch_digit_histograms_pairs(const uint2 *d_pairs, uint64_t n, uint32_t n_passes, uint32_t w_bits, uint32_t *d_hist_scratch,

@@ -73,9 +73,10 @@ __device__ __forceinline__ uint32_t digit_of(KeyT key, uint32_t shift, uint32_t 
 //                     kernel inside its 64-register budget without spilling,
 //   sm.count[d]  = number of items with digit d, sm.excl[d] = exclusive prefix of count.
 // All kSortThreads threads must call. Ends with a __syncthreads().
-template <int BITS, bool FULL, typename KeyT, bool BYTE = false>
+template <int BITS, bool FULL, typename KeyT, bool BYTE = false, bool ATOMIC_MATCH = false>
 __device__ __forceinline__ void tile_rank(const KeyT (&key)[kSortItems], uint32_t count, uint32_t shift,
-                                          uint32_t mask, uint32_t (&local_pos2)[kSortItems / 2], RankSmem &sm) {
+                                          uint32_t mask, uint32_t (&local_pos2)[kSortItems / 2], RankSmem &sm,
+                                          uint32_t (*warp_msk)[kRadix] = nullptr) {
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
@@ -83,6 +84,45 @@ __device__ __forceinline__ void tile_rank(const KeyT (&key)[kSortItems], uint32_
     const uint32_t e0 = (uint32_t)(warp * kSortItems * 32 + lane);
     uint32_t *my_cnt = sm.warp_cnt[warp];
 
+  if constexpr (ATOMIC_MATCH) {
+    // The scatter passes are bound by instruction issue (ALU pipe), not by memory: the vote-based match costs 3 ALU
+    // instructions per digit bit and item. Here the match runs on the shared-memory pipe instead: every lane ORs its
+    // lane bit into the warp's mask word of its digit, reads the mask (= the same-digit lanes) and the digit's running
+    // counter back, and the lowest lane of each group adds the group's size and clears the mask. Measured on config 5:
+    // the text-sourced pass (which also spends ALU on extracting hashes) 16.7 -> 15.4 ms, the pair passes 13.3 -> 15.7 ms
+    // (they become shared-memory bound) -- so only the text-sourced pass uses it.
+    uint32_t *my_msk = warp_msk[warp];  // ATOMIC_MATCH: per warp and digit, the lanes holding that digit in this round
+#pragma unroll
+    for (int i = 0; i < kRadix / 32; ++i) {
+        my_cnt[i * 32 + lane] = 0;
+        my_msk[i * 32 + lane] = 0;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const uint32_t d = digit_of<BYTE>(key[r], shift, mask);
+        const bool valid = FULL || e0 + r * 32 < count;
+        if (valid) atomicOr(&my_msk[d], 1u << lane);
+        __syncwarp();
+        uint32_t peers = 0, pre = 0;
+        if (valid) {
+            peers = my_msk[d];
+            pre = my_cnt[d];
+        }
+        __syncwarp();
+        const uint32_t below = (uint32_t)__popc(peers & lt_mask);
+        if (valid && below == 0) {
+            my_cnt[d] = pre + (uint32_t)__popc(peers);
+            my_msk[d] = 0;
+        }
+        __syncwarp();
+        const uint32_t pos = pre + below;
+        if (r & 1)
+            local_pos2[r >> 1] |= pos << 16;
+        else
+            local_pos2[r >> 1] = pos;
+    }
+  } else {
     for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) (&sm.warp_cnt[0][0])[i] = 0;
     __syncthreads();
 
@@ -117,6 +157,7 @@ __device__ __forceinline__ void tile_rank(const KeyT (&key)[kSortItems], uint32_
         else
             local_pos2[r >> 1] = (local_pos2[r >> 1] & 0xFFFF0000u) | pos;
     }
+  }
     __syncthreads();
 
     // per digit: exclusive prefix over warps, total count, exclusive prefix over digits

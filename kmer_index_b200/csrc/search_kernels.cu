@@ -36,7 +36,9 @@ struct Range {
 
 // index of the first sorted k-mer of element E whose hash is >= key (key may equal key_space)
 __device__ __forceinline__ uint64_t lower_bound_key(const Element &E, uint64_t key) {
-    if (key >= E.key_space) return E.n_kmers;
+    if (key >= E.key_space || key >= E.key_hi) return E.n_kmers;
+    if (key <= E.key_lo) return 0;
+    key -= E.key_lo;
     const uint64_t t = key >> E.shift;
     uint64_t lo = gather32(E.dir + t);
     if (E.shift == 0) return lo;
@@ -53,6 +55,8 @@ __device__ __forceinline__ uint64_t lower_bound_key(const Element &E, uint64_t k
 
 // the bucket of `key`: the reference's at(hash) (kmer_index.hpp:76-84)
 __device__ __forceinline__ Range bucket_of(const Element &E, uint64_t key) {
+    if (key < E.key_lo || key >= E.key_hi) return Range{0, 0};  // another part's hash
+    key -= E.key_lo;
     const uint64_t t = key >> E.shift;
     uint64_t lo = gather32(E.dir + t);
     uint64_t hi = gather32(E.dir + t + 1);
@@ -250,9 +254,10 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
     const DeviceIndex &ix = *a.index;
     const PackedText T = ix.text;
     uint64_t *qw = smem_q + (size_t)group * a.q_words;
-    const uint64_t off0 = a.q_offsets[q];
-    const uint64_t m64 = a.q_offsets[q + 1] - off0;
-    const uint64_t q_total = a.q_offsets[a.n_queries];  // symbols in q_ranks: bounds the 16-byte reads
+    const bool packed_in = a.q_packed != nullptr;
+    const uint64_t off0 = packed_in ? 0 : a.q_offsets[q];
+    const uint64_t m64 = packed_in ? (uint64_t)a.q_lens16[q] : a.q_offsets[q + 1] - off0;
+    const uint64_t q_total = packed_in ? 0 : a.q_offsets[a.n_queries];  // symbols in q_ranks: bounds the 16-byte reads
 
     uint32_t status = KMER_B200_QUERY_OK;
     if (m64 == 0) {
@@ -286,7 +291,17 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
     // A chunk is 8 symbols (one 8-byte load); `lpw` chunks make one 64-bit word. Each lane takes `cpl`
     // consecutive chunks per round so that a round always covers whole words; lanes sharing a word combine
     // their parts with xor-shuffles.
-    {
+    if (packed_in) {
+        // the caller packed the query already: copy its words (and the two zero words the window reads rely on)
+        const uint32_t n_words = (m * T.bits + 63) / 64;
+        const uint64_t *src = a.q_packed + q * a.q_stride;
+        for (uint32_t w = gl; w < n_words; w += G) qw[w] = src[w];
+        if (gl == 0) {
+            qw[n_words] = 0;
+            qw[n_words + 1] = 0;
+        }
+        if (G > 1) __syncwarp(gmask);
+    } else {
         const uint8_t *qr = a.q_ranks + off0;
         const uint32_t lpw = 8 / T.bits;                          // chunks per word: 4, 2, 1
         const uint32_t cpl = lpw > (uint32_t)G ? lpw / G : 1;     // chunks per lane and round

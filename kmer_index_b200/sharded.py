@@ -352,6 +352,95 @@ def search_device(ix, q_ptr: int, off_ptr: int, Q: int, max_len: int, world: int
     return hits
 
 
+# ----------------------------------------------------------------------------------------------------------
+# replicated index, partitioned build: every rank sorts the k-mers of ONE key-range part (1/world of the work),
+# the parts are all-gathered over NVLink into the whole index on every rank, and each rank then answers its own
+# slice of the query batch with no per-query exchange at all
+# ----------------------------------------------------------------------------------------------------------
+def _dev_view(ptr: int, n: int, dev):
+    """int32 torch view of n 32-bit words of device memory owned by the library."""
+    import torch
+
+    class _V:
+        __cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+    return torch.as_tensor(_V(), device=dev) if n else torch.empty(0, dtype=torch.int32, device=dev)
+
+
+def assemble_replicated(ix, world: int, rank: int, dist, dev, timing=None):
+    """`ix` was built with key_part=rank, key_parts=world on the torch current stream: all-gather every element's
+    part (positions behind the earlier parts' positions, directory entries offset by the earlier parts' k-mer counts)
+    and hand the whole arrays to the index (kmer_b200_adopt_element). Afterwards ix is a complete, replicated index."""
+    import torch
+    for e, k in enumerate(ix.ks):
+        part = ix.element_part(e)
+        n_kmers = ix.n - k + 1
+        key_space = ix.sigma ** k
+        meta = torch.tensor([part.n_kmers, part.key_lo, part.key_hi], dtype=torch.int64, device=dev)
+        all_meta = torch.empty(3 * world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(all_meta, meta)
+        all_meta = all_meta.view(world, 3).cpu()
+        counts = [int(x) for x in all_meta[:, 0]]
+        los = [int(x) for x in all_meta[:, 1]]
+        his = [int(x) for x in all_meta[:, 2]]
+        bases = [sum(counts[:r]) for r in range(world)]
+        assert sum(counts) == n_kmers, (counts, n_kmers)
+        pos_full = torch.empty(n_kmers, dtype=torch.int32, device=dev)
+        dir_full = torch.empty(key_space + 1, dtype=torch.int32, device=dev)
+        # this rank's slices: positions copied, directory exported with the base added (one fused kernel)
+        if counts[rank]:
+            pos_full[bases[rank]:bases[rank] + counts[rank]].copy_(_dev_view(part.d_positions, counts[rank], dev))
+        last = rank == world - 1
+        n_dir = his[rank] - los[rank] + (1 if last else 0)
+        ix.export_directory(e, bases[rank], n_dir, dir_full.data_ptr() + 4 * los[rank])
+        widths = {his[r] - los[r] for r in range(world)}
+        if len(widths) == 1 and his[-1] == key_space and los[0] == 0:
+            width = his[0] - los[0]
+            mine = dir_full[los[rank]:los[rank] + width].clone()
+            dist.all_gather_into_tensor(dir_full[:key_space], mine)
+            if not last:
+                dir_full[key_space:].fill_(n_kmers)
+        else:
+            for r in range(world):
+                hi_r = his[r] + (1 if r == world - 1 else 0)
+                if hi_r > los[r]:
+                    dist.broadcast(dir_full[los[r]:hi_r], src=r)
+        for r in range(world):
+            if counts[r]:
+                dist.broadcast(pos_full[bases[r]:bases[r] + counts[r]], src=r)
+        ix.adopt_element(e, pos_full, dir_full)
+
+
+def fingerprint(ix, q_ptr: int, off_ptr: int, Q: int, max_len: int, world: int, dev, first_query_id: int = 0):
+    """{hits, status histogram, position checksum} of a device-resident batch: sum over all hits of
+    position * (global query id + 1) modulo 2^64 -- a property of the result alone, so every N and every multi-GPU
+    mode must print the same values. Position-range sharding: computed on rank 0 from the merged CSR (other ranks
+    return zeros). Verification code outside any timed region (torch ops are fine here)."""
+    import torch
+    if world == 1:
+        res = ix.search_batch_device(q_ptr, off_ptr, Q, max_len)
+        off = torch.as_tensor(res.offsets(), device=dev)
+        pos = (torch.as_tensor(res.positions(), device=dev).to(torch.int64) & 0xFFFFFFFF if res.n_positions
+               else torch.empty(0, dtype=torch.int64, device=dev))
+        status = torch.as_tensor(res.status(), device=dev)
+    else:
+        import torch.distributed as dist
+        res, off, pos = search_merged(ix, q_ptr, off_ptr, Q, max_len, world, dev)
+        status = torch.as_tensor(res.status(), device=dev)
+        if dist.get_rank() != 0:
+            torch.cuda.current_stream().synchronize()
+            res.free()
+            return {"hits": 0, "checksum": 0, "status_hist": [0, 0, 0, 0]}
+        pos = pos.to(torch.int64) & 0xFFFFFFFF
+    counts = off[1:] - off[:-1]
+    qid = torch.repeat_interleave(torch.arange(first_query_id + 1, first_query_id + Q + 1, device=dev), counts)
+    checksum = int((pos * qid).sum().item()) if pos.numel() else 0
+    hist = torch.bincount(status.to(torch.int64), minlength=4)[:4]
+    out = {"hits": int(off[-1].item()), "checksum": checksum, "status_hist": [int(x) for x in hist.cpu()]}
+    torch.cuda.current_stream().synchronize()
+    res.free()
+    return out
+
+
 _pinned_cache: dict = {}
 
 

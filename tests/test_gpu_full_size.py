@@ -86,14 +86,25 @@ def test_pipelined_host_batch_equals_plain(kb):
     off = np.concatenate([off1, off2[1:] + off1[-1]])
     assert q.size + 17 * (off.size - 1) >= (256 << 20)
     with kb.KmerIndex(text, 4, [12]) as ix:
-        piped = ix.search_batch(q, off).as_tuple()
+        packed = ix.search_batch(q, off).as_tuple()          # pageable numpy input: packed on the host threads, pipelined
+        os.environ["KMER_B200_HOST_PACK"] = "0"
+        try:
+            piped = ix.search_batch(q, off).as_tuple()       # 1-byte ranks over PCIe, chunks pipelined
+        finally:
+            del os.environ["KMER_B200_HOST_PACK"]
         os.environ["KMER_B200_NO_PIPELINE"] = "1"
         try:
             plain = ix.search_batch(q, off).as_tuple()
         finally:
             del os.environ["KMER_B200_NO_PIPELINE"]
+        bad = q.copy()
+        bad[q.size // 2] = 4                                  # a rank >= sigma must be reported, not packed away
+        with pytest.raises(kb.KmerB200Error) as e:
+            ix.search_batch(bad, off)
+        assert e.value.code == -4
     assert piped[1].size > 500_000
     assert_results_equal(piped, plain, label="pipelined vs plain")
+    assert_results_equal(packed, plain, label="host-packed pipeline vs plain")
 
 
 def test_config3_full_text_counts_and_subsample(kb, oracle_mod):
@@ -165,11 +176,20 @@ def test_config5_full_text_sample_bit_exact_vs_oracle(kb, oracle_mod):
     d_text = torch.empty(n, dtype=torch.uint8, device=dev)
     _capi.check(L.kmer_b200_synth_ranks_device(d_text.data_ptr(), n, 0, 4, TEXT_SEED, sptr))
     torch.cuda.synchronize()
+    assert np.array_equal(d_text[:4096].cpu().numpy(), synth.random_text(4096, 4, TEXT_SEED))   # device generator == host generator
+    # a stretch of period 16 (one random 16-mer repeated): windows inside it satisfy the defective plans non-trivially
+    p_lo, p_len = 1_500_000_000, 1 << 16
+    d_text[p_lo:p_lo + p_len] = d_text[p_lo:p_lo + 16].repeat(p_len // 16)
     text = d_text.cpu().numpy()
-    assert np.array_equal(text[:4096], synth.random_text(4096, 4, TEXT_SEED))           # device generator == host generator
     Q = 1_000_000
     q1, off1 = synth.random_queries(Q // 2, m_lo, m_hi, 4, QUERY_SEED)
     q2, off2 = _planted(text, Q - Q // 2, m_lo, m_hi, QUERY_SEED + 1)
+    n_periodic = 4096                                          # the last planted windows come from the periodic stretch
+    lens2 = (off2[1:] - off2[:-1]).astype(np.int64)
+    for j in range(n_periodic):
+        i = lens2.size - 1 - j
+        s0 = p_lo + 16 + (j * 7) % 4096
+        q2[int(off2[i]):int(off2[i + 1])] = text[s0:s0 + int(lens2[i])]
     q = np.concatenate([q1, q2])
     off = np.concatenate([off1, off2[1:] + off1[-1]])
     lens = (off[1:] - off[:-1]).astype(np.int64)
@@ -191,7 +211,11 @@ def test_config5_full_text_sample_bit_exact_vs_oracle(kb, oracle_mod):
     rest = planted_lens % k
     # the sample does exercise what it is meant to: THROW with all parts present, non-empty defective plans
     assert int(((planted_status == 1) & (rest >= 1) & (rest <= 4)).sum()) > 1000
-    assert int((planted_counts[(planted_lens >= 53) & (planted_lens <= 63)] > 0).sum()) > 1000
+    # lengths 53-63 run the reference's defective plan (kmer_index.hpp:314): on a random text a planted window is NOT
+    # found by it (false negative) -- reproduced bit for bit above; the periodic stretch below makes the plan non-empty
+    defect = (planted_lens >= 53) & (planted_lens <= 63)
+    assert int((planted_counts[defect] > 0).sum()) >= n_periodic // 8
+    assert int((planted_counts[defect] == 0).sum()) > 1000
     assert int((want[0][1:] - want[0][:-1])[:Q // 2].sum()) > 1000                        # random queries with hits
     # CORRECT mode: every planted window is found at its origin; sorted lists
     c_off, c_pos, _ = got_correct

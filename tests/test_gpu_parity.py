@@ -311,6 +311,58 @@ def test_sharded_merged_finish_emulated_on_one_gpu(kb, oracle_mod, sigma, ks, n,
     assert took_merged_path
 
 
+@pytest.mark.parametrize("sigma,ks,n,parts", [(4, [12], 300_000, 4), (4, [16], 400_000, 8), (4, [5, 7, 9, 11, 13], 200_000, 3),
+                                               (15, [8], 200_000, 2), (27, [5], 150_000, 5)])
+def test_key_range_parts_assemble_to_the_whole_index(kb, oracle_mod, sigma, ks, n, parts):
+    """Multi-GPU build of a replicated index, emulated on one GPU: `parts` indices, each holding the k-mers of one
+    key-range part, are concatenated (positions part after part, directory entries offset by the earlier parts'
+    k-mer counts) and adopted -- the result must equal the index built in one piece, CSR and answers. Before the
+    adoption a part answers with exactly its own share of every hit list."""
+    import torch
+
+    from kmer_index_b200 import sharded, synth
+    dev = torch.device("cuda", 0)
+    text = synth.random_text(n, sigma, 71)
+    text[1000:1400] = 0                                      # a long bucket that lands in one part
+    q, off = synth.stress_queries(text, 4000, 1, 48, sigma, 72)
+    stream = torch.cuda.current_stream().cuda_stream
+    idx = [kb.KmerIndex(text, sigma, ks, key_part=r, key_parts=parts, stream=stream or None) for r in range(parts)]
+    try:
+        with oracle_mod.Oracle(text, sigma, ks) as o:
+            want = o.search(q, off)
+            want_csr = [o.element(e) for e in range(len(ks))]
+        exact = (off[1:] - off[:-1]) == ks[0] if len(ks) == 1 else None
+        if exact is not None:
+            # exact-k queries: the bucket of the query lives in exactly one part; the parts' hit counts add up
+            per_part = [ix.search_batch(q, off) for ix in idx]
+            total = sum((r.offsets[1:] - r.offsets[:-1]).astype(np.int64) for r in per_part)
+            assert np.array_equal(total[exact], (want[0][1:] - want[0][:-1]).astype(np.int64)[exact])
+        for e, k in enumerate(ks):
+            ps = [ix.element_part(e) for ix in idx]
+            assert sum(p.n_kmers for p in ps) == n - k + 1
+            assert ps[0].key_lo == 0 and ps[-1].key_hi == sigma ** k
+            pos_full = torch.empty(n - k + 1, dtype=torch.int32, device=dev)
+            dir_full = torch.empty(sigma ** k + 1, dtype=torch.int32, device=dev)
+            base = 0
+            for r, (ix, p) in enumerate(zip(idx, ps)):
+                assert p.key_hi - p.key_lo + 1 == p.directory_entries
+                if r:
+                    assert p.key_lo == ps[r - 1].key_hi
+                pos_full[base:base + p.n_kmers].copy_(sharded._dev_view(p.d_positions, p.n_kmers, dev))
+                n_dir = p.key_hi - p.key_lo + (1 if r == parts - 1 else 0)
+                ix.export_directory(e, base, n_dir, dir_full.data_ptr() + 4 * p.key_lo)
+                base += p.n_kmers
+            torch.cuda.synchronize()
+            idx[0].adopt_element(e, pos_full, dir_full)
+            h, p_ = idx[0].element_arrays(e)
+            assert np.array_equal(p_, want_csr[e][1]) and np.array_equal(h, want_csr[e][0])
+        for attempt in range(2):     # the second batch runs with the auxiliary elements the first one built
+            assert_results_equal(idx[0].search_batch(q, off).as_tuple(), want, label=f"assembled {ks} x{parts}/{attempt}")
+    finally:
+        for ix in idx:
+            ix.close()
+
+
 @pytest.mark.parametrize("sigma,ks", [(4, [12]), (4, [5, 7, 9, 11, 13]), (15, [8]), (4, [20])])
 def test_heavy_buckets_take_the_warp_path(kb, oracle_mod, sigma, ks):
     """A text with one enormous bucket (a long constant run): the index-wide average bucket is ~1, so queries get

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(kb):
     missing = sorted(declared - exported)
     assert not missing, f"declared in include/kmer_b200.h but not exported: {missing}"
     assert declared == set(_capi.SYMBOLS), sorted(declared ^ set(_capi.SYMBOLS))
-    assert _capi.lib().kmer_b200_abi_version() == 1
+    assert _capi.lib().kmer_b200_abi_version() == 2
 
 
 def test_no_oracle_or_cpu_fallback_in_product(kb):
