@@ -76,6 +76,13 @@ typedef struct kmer_b200_config {
        dense directories. 0 or 1: the whole key space. */
     uint32_t key_part;
     uint32_t key_parts;
+    /* Several GPUs behind ONE handle, one process (n_devices > 1; `device` is then ignored): kmer_b200_create builds
+       a key-range part on each device in parallel (one host thread per device), exchanges the parts between the devices
+       over peer copies (NVLink) so that every device holds the whole index, and kmer_b200_search_batch stripes a host
+       batch over the devices -- each uploads its slice of the queries over its own PCIe link, searches it, and returns
+       its slice of the result. The entry points that take device pointers are not available on such a handle. */
+    const int32_t *device_ids;
+    uint32_t n_devices;
 } kmer_b200_config;
 
 typedef struct kmer_b200_index kmer_b200_index;
@@ -122,6 +129,11 @@ int kmer_b200_load(const char *path, const kmer_b200_config *cfg, kmer_b200_inde
    and status[Q] (kmer_b200_query_status). mode: a kmer_b200_mode, or UINT32_MAX for the index default. */
 int kmer_b200_search_batch(kmer_b200_index *index, const uint8_t *q_ranks, const uint64_t *q_offsets, uint64_t n_queries,
                            uint32_t mode, kmer_b200_result **out);
+
+/* Same for queries that live in separate host buffers (std::vector<std::vector<alphabet_t>>): q_ptrs[i] points to the
+   q_lens[i] ranks of query i. The library gathers them with its host thread pool -- no per-symbol copy by the caller. */
+int kmer_b200_search_batch_ptrs(kmer_b200_index *index, const uint8_t *const *q_ptrs, const uint64_t *q_lens,
+                                uint64_t n_queries, uint32_t mode, kmer_b200_result **out);
 
 /* Same with queries resident in device memory and the result left in device memory.
    max_query_len must be >= the longest query in the batch. */

@@ -19,6 +19,10 @@
 //     begin()/end() iterate the positions (the reference's iterator does not compile).
 //   * search(std::vector<alphabet_t>&&) returns its result (the reference's has no return statement).
 //   * n_threads is accepted and ignored; extend_query_size_range() is rejected above 10000.
+//   * texts and queries held in contiguous storage of 1-byte alphabet objects (std::vector<kmer::dna4>, seqan3
+//     alphabets) are handed to the library as they are -- the object's byte IS its rank -- without a per-symbol copy.
+//   * an index can span several GPUs: kmer_index(text, devices) builds it from key-range parts on all of them and
+//     search_batch() stripes the batch over them (kmer_b200_config.device_ids).
 //   * the alphabet requirement is `a.to_rank()` plus kmer::alphabet_size<A>; seqan3 alphabets satisfy it when
 //     seqan3 is available, kmer::dna4 / dna5 / dna15 / aa27 below are rank-only stand-ins.
 #pragma once
@@ -104,19 +108,52 @@ namespace kmer
 
         enum class BYPASS_BITMASK : bool { YES = true, NO = false };   // kmer_index_result.hpp:11 (kept for source compat)
 
-        // kmer_index_result.hpp:14-272
+        // kmer_index_result.hpp:14-272. The reference's result points into the index (bucket pointers + a bitmask of
+        // usable entries, or the BYPASS flag); this one owns its candidates, keeps the same mask surface
+        // (should_use / should_not_use, kmer_index_result.hpp:262-270) and to_vector() filters and sorts as :244-260.
+        // Results returned by search() arrive finished: ascending positions, bypass set.
         template<typename position_t>
         class kmer_index_result
         {
-            std::vector<position_t> _positions;   // ascending
+            std::vector<position_t> _positions;
+            std::vector<bool> _bitmask;           // unused when _bypass
+            bool _bypass = true;
 
         public:
-            kmer_index_result() = default;
+            kmer_index_result() = default;                                                          // :203-205
             explicit kmer_index_result(std::vector<position_t> sorted_positions) : _positions(std::move(sorted_positions)) {}
+            // :207-217  one bucket, every entry usable (zero_or_one = true) or not, optionally bypassing the mask
+            kmer_index_result(std::vector<position_t> const* bucket, bool zero_or_one = true, BYPASS_BITMASK bypass = BYPASS_BITMASK::NO)
+                : _positions(bucket ? *bucket : std::vector<position_t>{}), _bitmask(_positions.size(), zero_or_one),
+                  _bypass(bypass == BYPASS_BITMASK::YES) {}
+            // :219-236  several buckets, concatenated
+            kmer_index_result(std::vector<std::vector<position_t> const*> const& buckets, BYPASS_BITMASK bypass = BYPASS_BITMASK::YES)
+                : _bypass(bypass == BYPASS_BITMASK::YES)
+            {
+                for (auto const* b : buckets)
+                    if (b) _positions.insert(_positions.end(), b->begin(), b->end());
+                _bitmask.assign(_positions.size(), true);
+            }
 
-            std::size_t size() const noexcept { return _positions.size(); }
-            bool empty() const noexcept { return _positions.empty(); }
-            std::vector<position_t> to_vector() const { return _positions; }
+            void should_use(std::size_t i) { _bitmask.at(i) = true; }                                // :262-265
+            void should_not_use(std::size_t i) { _bitmask.at(i) = false; }                           // :267-270
+
+            // number of hits (the reference counts mask bits and so reports 0 for bypass results, a defect: :239-242)
+            std::size_t size() const noexcept
+            {
+                return _bypass ? _positions.size() : std::size_t(std::count(_bitmask.begin(), _bitmask.end(), true));
+            }
+            bool empty() const noexcept { return size() == 0; }
+            std::vector<position_t> to_vector() const                                                // :244-260
+            {
+                std::vector<position_t> out;
+                out.reserve(_positions.size());
+                for (std::size_t i = 0; i < _positions.size(); ++i)
+                    if (_bypass || _bitmask[i]) out.push_back(_positions[i]);
+                if (!std::is_sorted(out.begin(), out.end())) std::sort(out.begin(), out.end());
+                return out;
+            }
+            // iteration over the hits (the reference's iterator does not compile: :98-101,166,182)
             auto begin() const noexcept { return _positions.begin(); }
             auto end() const noexcept { return _positions.end(); }
         };
@@ -130,6 +167,12 @@ namespace kmer
                 throw std::invalid_argument("kmer_b200: " + msg);
             throw std::runtime_error("kmer_b200 (" + std::to_string(status) + "): " + msg);
         }
+
+        // contiguous storage of 1-byte alphabet objects whose byte is the rank: usable as the library's rank buffer
+        template<typename range_t>
+        inline constexpr bool ranks_in_place =
+            std::ranges::contiguous_range<range_t> && sizeof(std::ranges::range_value_t<range_t>) == 1 &&
+            std::is_trivially_copyable_v<std::ranges::range_value_t<range_t>>;
 
         template<typename range_t>
         std::vector<std::uint8_t> to_ranks(range_t const& r)
@@ -182,16 +225,47 @@ namespace kmer
         explicit kmer_index(text_t& text, std::size_t /*n_threads*/ = 1, kmer_b200_mode mode = KMER_B200_MODE_REFERENCE_EXACT,
                             int device = -1)
         {
+            build(text, mode, device, nullptr, 0);
+        }
+
+        // the same index replicated over several GPUs (built from key-range parts, one per GPU); search_batch() stripes
+        // its batch over them
+        template<std::ranges::range text_t>
+        kmer_index(text_t& text, std::vector<int> const& devices, kmer_b200_mode mode = KMER_B200_MODE_REFERENCE_EXACT)
+        {
+            std::vector<std::int32_t> ids(devices.begin(), devices.end());
+            build(text, mode, ids.empty() ? -1 : ids[0], ids.data(), std::uint32_t(ids.size()));
+        }
+
+    private:
+        template<typename text_t>
+        void build(text_t& text, kmer_b200_mode mode, int device, std::int32_t const* ids, std::uint32_t n_ids)
+        {
             static constexpr std::uint32_t k_list[] = {std::uint32_t(ks)...};
-            auto ranks = detail::to_ranks(text);
             kmer_b200_config cfg;
             kmer_b200_config_default(&cfg);
             cfg.mode = mode;
             cfg.device = device;
-            detail::check(kmer_b200_create(ranks.data(), ranks.size(), std::uint32_t(alphabet_size<alphabet_t>), k_list,
-                                           sizeof...(ks), &cfg, &_handle));
+            if (n_ids > 1)
+            {
+                cfg.device_ids = ids;
+                cfg.n_devices = n_ids;
+            }
+            if constexpr (detail::ranks_in_place<text_t>)
+            {
+                // std::vector<alphabet_t> of 1-byte alphabet objects: the storage is the rank array
+                detail::check(kmer_b200_create(reinterpret_cast<std::uint8_t const*>(std::ranges::data(text)), std::ranges::size(text),
+                                               std::uint32_t(alphabet_size<alphabet_t>), k_list, sizeof...(ks), &cfg, &_handle));
+            }
+            else
+            {
+                auto ranks = detail::to_ranks(text);
+                detail::check(kmer_b200_create(ranks.data(), ranks.size(), std::uint32_t(alphabet_size<alphabet_t>), k_list,
+                                               sizeof...(ks), &cfg, &_handle));
+            }
         }
 
+    public:
         // construct once, load later: kmer_index<...>::load(path) restores an index written by save(path)
         void save(std::string const& path) const { detail::check(kmer_b200_save(_handle, path.c_str())); }
         static kmer_index load(std::string const& path, kmer_b200_mode mode = KMER_B200_MODE_REFERENCE_EXACT, int device = -1)
@@ -240,16 +314,32 @@ namespace kmer
         template<std::ranges::range queries_t>
         kmer_batch_result<position_t> search_batch(queries_t const& queries) const
         {
-            std::vector<std::uint8_t> ranks;
-            std::vector<std::uint64_t> offsets{0};
-            for (auto const& q : queries)
-            {
-                for (auto const& c : q)
-                    ranks.push_back(static_cast<std::uint8_t>(c.to_rank()));
-                offsets.push_back(ranks.size());
-            }
+            using query_t = std::remove_cvref_t<std::ranges::range_reference_t<queries_t const>>;
             kmer_b200_result* r = nullptr;
-            detail::check(kmer_b200_search_batch(_handle, ranks.data(), offsets.data(), offsets.size() - 1, UINT32_MAX, &r));
+            if constexpr (detail::ranks_in_place<query_t> && std::is_lvalue_reference_v<std::ranges::range_reference_t<queries_t const>>)
+            {
+                // queries in their own contiguous 1-byte storage: hand over pointers, the library gathers them in parallel
+                std::vector<std::uint8_t const*> ptrs;
+                std::vector<std::uint64_t> lens;
+                for (auto const& q : queries)
+                {
+                    ptrs.push_back(reinterpret_cast<std::uint8_t const*>(std::ranges::data(q)));
+                    lens.push_back(std::ranges::size(q));
+                }
+                detail::check(kmer_b200_search_batch_ptrs(_handle, ptrs.data(), lens.data(), ptrs.size(), UINT32_MAX, &r));
+            }
+            else
+            {
+                std::vector<std::uint8_t> ranks;
+                std::vector<std::uint64_t> offsets{0};
+                for (auto const& q : queries)
+                {
+                    for (auto const& c : q)
+                        ranks.push_back(static_cast<std::uint8_t>(c.to_rank()));
+                    offsets.push_back(ranks.size());
+                }
+                detail::check(kmer_b200_search_batch(_handle, ranks.data(), offsets.data(), offsets.size() - 1, UINT32_MAX, &r));
+            }
             kmer_batch_result<position_t> out;
             const std::uint64_t n_q = kmer_b200_result_n_queries(r), n_p = kmer_b200_result_n_positions(r);
             out.offsets.assign(kmer_b200_result_offsets(r), kmer_b200_result_offsets(r) + n_q + 1);
@@ -258,6 +348,17 @@ namespace kmer
                 out.positions.assign(kmer_b200_result_positions(r), kmer_b200_result_positions(r) + n_p);
             kmer_b200_result_free(r);
             return out;
+        }
+
+        // kmer_index_element::search_k (kmer_index.hpp:182-190): the bucket of the k symbols starting at `it`, for one
+        // of the index's ks; empty when the k-mer does not occur (the reference returns a null pointer)
+        template<std::size_t k, typename iterator_t>
+        result_t search_k(iterator_t it) const
+        {
+            static_assert(((k == ks) || ...), "search_k<k>: k is not one of this index's ks");
+            std::vector<alphabet_t> kmer_symbols;
+            for (std::size_t i = 0; i < k; ++i, ++it) kmer_symbols.push_back(*it);
+            return search(kmer_symbols);
         }
 
         // kmer_index.hpp:505-558. A batch of one: correct, but a GPU is fed with search_batch().

@@ -160,7 +160,8 @@ class KmerIndex:
     def __init__(self, text, sigma: int, ks: Sequence[int], *, mode: int = MODE_REFERENCE_EXACT, device: int = -1,
                  stream: int | None = None, profile: bool = False, shard_begin: int = 0, n_total: int = 0,
                  halo: int = 0, directory_bits: int = 0, text_device_ptr: int | None = None, n: int | None = None,
-                 aux_elements: bool = True, lut: np.ndarray | None = None, key_part: int = 0, key_parts: int = 0):
+                 aux_elements: bool = True, lut: np.ndarray | None = None, key_part: int = 0, key_parts: int = 0,
+                 devices: Sequence[int] | None = None):
         L = _capi.lib()
         self._L = L
         self._h = C.c_void_p()
@@ -179,6 +180,10 @@ class KmerIndex:
         cfg.reserved = 0 if aux_elements else 1   # bit 0: no auxiliary k' = m elements for sub-k lengths
         cfg.key_part, cfg.key_parts = key_part, key_parts   # key-range part of a multi-GPU build (sharded.build_replicated)
         self._adopted = []                                   # arrays handed over with adopt_element: kept alive here
+        if devices is not None and len(devices) > 1:         # several GPUs behind this one handle (host batches only)
+            self._device_ids = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+            cfg.device_ids = C.cast(self._device_ids, C.POINTER(C.c_int32))
+            cfg.n_devices = len(devices)
         ks_a = np.asarray(self.ks, dtype=np.uint32)
         if text_device_ptr is not None:
             self.n = int(n)

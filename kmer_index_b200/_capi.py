@@ -25,7 +25,8 @@ QUERY_TOO_LONG_FOR_SHARD = 3
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("mode", C.c_uint32), ("stream", C.c_void_p), ("shard_begin", C.c_uint64),
                 ("n_total", C.c_uint64), ("halo", C.c_uint32), ("directory_bits", C.c_uint32),
-                ("profile", C.c_uint32), ("reserved", C.c_uint32), ("key_part", C.c_uint32), ("key_parts", C.c_uint32)]
+                ("profile", C.c_uint32), ("reserved", C.c_uint32), ("key_part", C.c_uint32), ("key_parts", C.c_uint32),
+                ("device_ids", C.POINTER(C.c_int32)), ("n_devices", C.c_uint32)]
 
 
 class ElementInfo(C.Structure):
@@ -62,6 +63,8 @@ SYMBOLS = {
     "kmer_b200_load": (C.c_int, [C.c_char_p, C.POINTER(Config), C.POINTER(C.c_void_p)]),
     "kmer_b200_search_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32,
                                          C.POINTER(C.c_void_p)]),
+    "kmer_b200_search_batch_ptrs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32,
+                                              C.POINTER(C.c_void_p)]),
     "kmer_b200_search_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
                                                 C.c_uint32, C.POINTER(C.c_void_p)]),
     "kmer_b200_count_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,

@@ -8,6 +8,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "host_pack.h"
@@ -148,7 +149,7 @@ struct HostElement {
     uint32_t *d_dir = nullptr, *d_pos = nullptr;
     void *d_keys = nullptr;  // uint32_t or uint64_t hashes (key_bytes); null for a dense directory
     uint32_t key_bytes = 4;
-    bool adopted = false;    // pos / dir belong to the caller (kmer_b200_adopt_element)
+    int adopted = 0;         // 1: pos / dir belong to the caller (kmer_b200_adopt_element); 2: assembled by the library, owned
 };
 
 // the hash range element `k` of this index covers: all of [0, sigma^k), or one of cfg.key_parts equal slices
@@ -195,7 +196,12 @@ struct kmer_b200_index {
     Profiler prof;
     std::mutex mu;  // serialises searches on one handle (they share the stream and the flag words)
     size_t h_pinned_cap = 0;
+    // a multi-device handle (cfg.n_devices > 1) owns one whole index per device and nothing else
+    std::vector<kmer_b200_index *> replicas;
 };
+
+static inline kmer_b200_index *primary(kmer_b200_index *ix) { return (ix && !ix->replicas.empty()) ? ix->replicas[0] : ix; }
+static inline const kmer_b200_index *primary(const kmer_b200_index *ix) { return (ix && !ix->replicas.empty()) ? ix->replicas[0] : ix; }
 
 struct kmer_b200_result {
     kmer_b200_index *index = nullptr;
@@ -1206,18 +1212,29 @@ int kmer_b200_abi_version(void) { return KMER_B200_ABI_VERSION; }
 
 const char *kmer_b200_last_error(void) { return g_last_error.c_str(); }
 
+static int create_multi(const uint8_t *ranks, uint64_t n, uint32_t sigma, const uint32_t *ks, uint32_t n_ks,
+                        const kmer_b200_config *cfg, kmer_b200_index **out, const uint8_t *lut256);
+static int search_batch_multi(kmer_b200_index *group, const uint8_t *q_ranks, const uint64_t *q_offsets, uint64_t Q, uint32_t mode,
+                              const uint8_t *lut256, kmer_b200_result **out);
+#define KB_NOT_ON_GROUP(ix)                                                                                         \
+    if ((ix) && !(ix)->replicas.empty())                                                                            \
+        return fail(KMER_B200_ERR_UNSUPPORTED, "device-pointer entry points are not available on a multi-device handle")
+
 int kmer_b200_create(const uint8_t *ranks, uint64_t n, uint32_t sigma, const uint32_t *ks, uint32_t n_ks,
                      const kmer_b200_config *cfg, kmer_b200_index **out) {
+    if (cfg && cfg->n_devices > 1) return create_multi(ranks, n, sigma, ks, n_ks, cfg, out, nullptr);
     return create_impl(ranks, false, n, sigma, ks, n_ks, cfg, out);
 }
 
 int kmer_b200_create_from_device(const uint8_t *d_ranks, uint64_t n, uint32_t sigma, const uint32_t *ks, uint32_t n_ks,
                                  const kmer_b200_config *cfg, kmer_b200_index **out) {
+    if (cfg && cfg->n_devices > 1) return fail(KMER_B200_ERR_UNSUPPORTED, "a multi-device index is built from a host text");
     return create_impl(d_ranks, true, n, sigma, ks, n_ks, cfg, out);
 }
 
 int kmer_b200_save(kmer_b200_index *ix, const char *path) {
     if (!ix || !path) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
+    ix = primary(ix);  // every device of a multi-device handle holds the whole index
     if (ix->cfg.key_parts > 1) return fail(KMER_B200_ERR_UNSUPPORTED, "a key-range part is not a whole index: assemble it first");
     DeviceGuard guard(ix->device);
     std::lock_guard<std::mutex> lock(ix->mu);
@@ -1346,11 +1363,16 @@ int kmer_b200_load(const char *path, const kmer_b200_config *cfg_in, kmer_b200_i
 
 void kmer_b200_destroy(kmer_b200_index *ix) {
     if (!ix) return;
+    if (!ix->replicas.empty()) {
+        for (kmer_b200_index *r : ix->replicas) kmer_b200_destroy(r);
+        delete ix;
+        return;
+    }
     DeviceGuard guard(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     ix->prof.resolve();
     for (auto &he : ix->elems) {
-        if (!he.adopted) {
+        if (he.adopted != 1) {
             dev_free(ix, he.d_dir);
             dev_free(ix, he.d_pos);
         }
@@ -1374,6 +1396,7 @@ void kmer_b200_destroy(kmer_b200_index *ix) {
 
 int kmer_b200_search_batch_device(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off, uint64_t Q,
                                   uint64_t max_len, uint32_t mode, kmer_b200_result **out) {
+    KB_NOT_ON_GROUP(ix);
     if (!ix || !out || (!d_off)) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
     *out = nullptr;
     DeviceGuard guard(ix->device);
@@ -1383,6 +1406,7 @@ int kmer_b200_search_batch_device(kmer_b200_index *ix, const uint8_t *d_q, const
 
 int kmer_b200_count_batch_device(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off, uint64_t Q,
                                  uint64_t max_len, uint32_t mode, kmer_b200_result **out) {
+    KB_NOT_ON_GROUP(ix);
     if (!ix || !out || (!d_off)) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
     *out = nullptr;
     DeviceGuard guard(ix->device);
@@ -1393,6 +1417,7 @@ int kmer_b200_count_batch_device(kmer_b200_index *ix, const uint8_t *d_q, const 
 int kmer_b200_search_batch_device_global(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off, uint64_t Q,
                                          uint64_t max_len, uint32_t mode, const void *d_present_global,
                                          uint32_t present_format, kmer_b200_result **out) {
+    KB_NOT_ON_GROUP(ix);
     if (!ix || !out || !d_off || !d_present_global || present_format > 1)
         return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad argument");
     *out = nullptr;
@@ -1407,6 +1432,7 @@ struct kmer_b200_pending {
 
 int kmer_b200_search_sharded_begin(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off, uint64_t Q,
                                    uint64_t max_len, uint32_t mode, uint32_t *d_present4, kmer_b200_pending **out) {
+    KB_NOT_ON_GROUP(ix);
     if (!ix || !out || !d_off || !d_present4) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
     *out = nullptr;
     DeviceGuard guard(ix->device);
@@ -1487,6 +1513,7 @@ int kmer_b200_search_sharded_add_counts(kmer_b200_pending *h, const uint32_t *d_
 
 int kmer_b200_presence_batch_device(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off, uint64_t Q,
                                     uint64_t max_len, uint32_t mode, void *d_present, uint32_t present_format) {
+    KB_NOT_ON_GROUP(ix);
     using namespace kb;
     if (!ix || !d_off || !d_present || present_format > 1) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad argument");
     if (mode == UINT32_MAX) mode = ix->cfg.mode;
@@ -1841,6 +1868,7 @@ static int search_batch_host(kmer_b200_index *ix, const uint8_t *q_ranks, const 
                              uint32_t mode, const uint8_t *lut256, kmer_b200_result **out) {
     if (!ix || !out || !q_offsets) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
     *out = nullptr;
+    if (!ix->replicas.empty()) return search_batch_multi(ix, q_ranks, q_offsets, Q, mode, lut256, out);
     DeviceGuard guard(ix->device);
     std::lock_guard<std::mutex> lock(ix->mu);
     cudaStream_t st = ix->stream;
@@ -1938,6 +1966,45 @@ int kmer_b200_search_batch(kmer_b200_index *ix, const uint8_t *q_ranks, const ui
     return search_batch_host(ix, q_ranks, q_offsets, Q, mode, nullptr, out);
 }
 
+int kmer_b200_search_batch_ptrs(kmer_b200_index *ix, const uint8_t *const *q_ptrs, const uint64_t *q_lens, uint64_t Q,
+                                uint32_t mode, kmer_b200_result **out) {
+    if (!ix || !out || (Q && (!q_ptrs || !q_lens))) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    // gather into one buffer with the host threads (offsets by a two-level prefix sum), then the ordinary host batch
+    kb::HostPool &pool = kb::HostPool::instance();
+    const unsigned T = std::max(1u, pool.threads());
+    std::vector<uint64_t> offsets(Q + 1), part_sum(T + 1, 0);
+    pool.run(T, [&](unsigned t) {
+        uint64_t s = 0;
+        for (uint64_t i = Q * t / T; i < Q * (t + 1) / T; ++i) s += q_lens[i];
+        part_sum[t + 1] = s;
+    });
+    for (unsigned t = 0; t < T; ++t) part_sum[t + 1] += part_sum[t];
+    const uint64_t total = part_sum[T];
+    uint8_t *ranks = (uint8_t *)std::malloc(std::max<uint64_t>(total, 1) + 8);
+    if (!ranks) return fail(KMER_B200_ERR_OUT_OF_MEMORY, "host allocation failed");
+    bool null_query = false;
+    pool.run(T, [&](unsigned t) {
+        uint64_t o = part_sum[t];
+        for (uint64_t i = Q * t / T; i < Q * (t + 1) / T; ++i) {
+            offsets[i] = o;
+            if (q_lens[i]) {
+                if (!q_ptrs[i]) {
+                    null_query = true;
+                    continue;
+                }
+                std::memcpy(ranks + o, q_ptrs[i], q_lens[i]);
+            }
+            o += q_lens[i];
+        }
+    });
+    offsets[Q] = total;
+    int s = null_query ? fail(KMER_B200_ERR_INVALID_ARGUMENT, "a query pointer is null")
+                       : search_batch_host(ix, ranks, offsets.data(), Q, mode, nullptr, out);
+    std::free(ranks);
+    return s;
+}
+
 int kmer_b200_search_batch_text(kmer_b200_index *ix, const char *q_chars, const uint64_t *q_offsets, uint64_t Q,
                                 const uint8_t *lut256, uint32_t mode, kmer_b200_result **out) {
     if (!lut256) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "lut256 is null");
@@ -1947,6 +2014,7 @@ int kmer_b200_search_batch_text(kmer_b200_index *ix, const char *q_chars, const 
 int kmer_b200_create_from_text(const char *text, uint64_t n, const uint8_t *lut256, uint32_t sigma, const uint32_t *ks,
                                uint32_t n_ks, const kmer_b200_config *cfg, kmer_b200_index **out) {
     if (!lut256) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "lut256 is null");
+    if (cfg && cfg->n_devices > 1) return create_multi(reinterpret_cast<const uint8_t *>(text), n, sigma, ks, n_ks, cfg, out, lut256);
     return create_impl(reinterpret_cast<const uint8_t *>(text), false, n, sigma, ks, n_ks, cfg, out, lut256);
 }
 
@@ -1978,9 +2046,10 @@ void kmer_b200_result_free(kmer_b200_result *r) {
     delete r;
 }
 
-uint32_t kmer_b200_n_elements(const kmer_b200_index *ix) { return ix ? (uint32_t)ix->ks.size() : 0; }
+uint32_t kmer_b200_n_elements(const kmer_b200_index *ix) { return ix ? (uint32_t)primary(ix)->ks.size() : 0; }
 
 int kmer_b200_element_info_get(const kmer_b200_index *ix, uint32_t e, kmer_b200_element_info *out) {
+    ix = primary(ix);
     if (!ix || !out || e >= ix->elems.size()) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad element");
     const HostElement &he = ix->elems[e];
     out->k = he.dev.k;
@@ -1994,6 +2063,7 @@ int kmer_b200_element_info_get(const kmer_b200_index *ix, uint32_t e, kmer_b200_
 }
 
 int kmer_b200_element_positions(kmer_b200_index *ix, uint32_t e, uint32_t *out, uint64_t cap) {
+    ix = primary(ix);
     if (!ix || !out || e >= ix->elems.size()) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad element");
     DeviceGuard guard(ix->device);
     const uint64_t n = std::min<uint64_t>(cap, ix->elems[e].dev.n_kmers);
@@ -2003,6 +2073,7 @@ int kmer_b200_element_positions(kmer_b200_index *ix, uint32_t e, uint32_t *out, 
 }
 
 int kmer_b200_element_hashes(kmer_b200_index *ix, uint32_t e, uint64_t *out, uint64_t cap) {
+    ix = primary(ix);
     if (!ix || !out || e >= ix->elems.size()) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad element");
     DeviceGuard guard(ix->device);
     const HostElement &he = ix->elems[e];
@@ -2032,6 +2103,7 @@ int kmer_b200_element_hashes(kmer_b200_index *ix, uint32_t e, uint64_t *out, uin
 }
 
 int kmer_b200_element_part(const kmer_b200_index *ix, uint32_t e, kmer_b200_part *out) {
+    ix = primary(ix);
     if (!ix || !out || e >= ix->ks.size()) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad element");
     const HostElement &he = ix->elems[e];
     if (he.dev.shift != 0) return fail(KMER_B200_ERR_UNSUPPORTED, "parts are exported from dense directories only");
@@ -2045,6 +2117,7 @@ int kmer_b200_element_part(const kmer_b200_index *ix, uint32_t e, kmer_b200_part
 }
 
 int kmer_b200_export_directory(kmer_b200_index *ix, uint32_t e, uint64_t base, uint64_t n, uint32_t *d_dst) {
+    ix = primary(ix);
     if (!ix || !d_dst || e >= ix->ks.size() || n > ix->elems[e].dev.dir_entries)
         return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad argument");
     DeviceGuard guard(ix->device);
@@ -2053,22 +2126,22 @@ int kmer_b200_export_directory(kmer_b200_index *ix, uint32_t e, uint64_t base, u
     return KMER_B200_OK;
 }
 
-int kmer_b200_adopt_element(kmer_b200_index *ix, uint32_t e, const uint32_t *d_positions, uint64_t n_kmers,
-                            const uint32_t *d_directory, uint64_t directory_entries) {
+static int adopt_element_impl(kmer_b200_index *ix, uint32_t e, const uint32_t *d_positions, uint64_t n_kmers,
+                              const uint32_t *d_directory, uint64_t directory_entries, int ownership) {
     if (!ix || !d_positions || !d_directory || e >= ix->ks.size()) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad argument");
     HostElement &he = ix->elems[e];
     if (n_kmers != ix->n - he.dev.k + 1 || directory_entries != he.dev.key_space + 1)
         return fail(KMER_B200_ERR_INVALID_ARGUMENT, "adopt: array sizes do not describe the whole index (n - k + 1 positions, sigma^k + 1 directory entries)");
     DeviceGuard guard(ix->device);
     std::lock_guard<std::mutex> lock(ix->mu);
-    if (!he.adopted) {
+    if (he.adopted != 1) {
         dev_free(ix, he.d_dir);
         dev_free(ix, he.d_pos);
         ix->device_bytes -= he.bytes;
     }
     dev_free(ix, (uint8_t *)he.d_keys);
     he.d_keys = nullptr;
-    he.adopted = true;
+    he.adopted = ownership;
     he.d_pos = const_cast<uint32_t *>(d_positions);
     he.d_dir = const_cast<uint32_t *>(d_directory);
     he.dev.shift = 0;
@@ -2080,9 +2153,10 @@ int kmer_b200_adopt_element(kmer_b200_index *ix, uint32_t e, const uint32_t *d_p
     he.dev.key_lo = 0;
     he.dev.key_hi = UINT64_MAX;
     he.bytes = n_kmers * 4 + directory_entries * 4;
+    if (ownership == 2) ix->device_bytes += he.bytes;
     ix->host_index.elem[e] = he.dev;
     bool all = true;
-    for (size_t i = 0; i < ix->ks.size(); ++i) all = all && ix->elems[i].adopted;
+    for (size_t i = 0; i < ix->ks.size(); ++i) all = all && ix->elems[i].adopted != 0;
     if (all) {
         // the index is whole again: elements built from now on (auxiliary k' = m elements) cover the whole key space;
         // those built for the part are dropped
@@ -2101,7 +2175,227 @@ int kmer_b200_adopt_element(kmer_b200_index *ix, uint32_t e, const uint32_t *d_p
     return KMER_B200_OK;
 }
 
+int kmer_b200_adopt_element(kmer_b200_index *ix, uint32_t e, const uint32_t *d_positions, uint64_t n_kmers,
+                            const uint32_t *d_directory, uint64_t directory_entries) {
+    if (ix && !ix->replicas.empty()) return fail(KMER_B200_ERR_UNSUPPORTED, "not available on a multi-device handle");
+    return adopt_element_impl(ix, e, d_positions, n_kmers, d_directory, directory_entries, 1);
+}
+
+// ---- several devices behind one handle (kmer_b200_config.n_devices > 1) ----------------------------------------------
+// Build: one host thread per device builds that device's key-range part from the host text (its own H2D over its own
+// PCIe link, 1 / N of the sorting work); then every part is pushed to every other device with peer copies, so all
+// devices end up with the whole index. Indices that cannot be cut into key-range parts (64-bit hashes) are simply built
+// whole on every device.
+static int create_multi(const uint8_t *ranks, uint64_t n, uint32_t sigma, const uint32_t *ks, uint32_t n_ks,
+                        const kmer_b200_config *cfg_in, kmer_b200_index **out, const uint8_t *lut256) {
+    if (!out) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "out is null");
+    *out = nullptr;
+    const uint32_t N = cfg_in->n_devices;
+    if (!cfg_in->device_ids || N > 64) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "device_ids is null or n_devices > 64");
+    if (cfg_in->n_total || cfg_in->shard_begin || cfg_in->halo || cfg_in->key_parts > 1 || cfg_in->stream)
+        return fail(KMER_B200_ERR_INVALID_ARGUMENT, "a multi-device index takes the whole text and its own streams");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(KMER_B200_ERR_CUDA, "no usable CUDA device (libkmer_b200 has no CPU fallback)");
+    }
+    std::vector<int> ids(cfg_in->device_ids, cfg_in->device_ids + N);
+    for (uint32_t i = 0; i < N; ++i) {
+        if (ids[i] < 0 || ids[i] >= count) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "device id out of range");
+        for (uint32_t j = 0; j < i; ++j)
+            if (ids[j] == ids[i]) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "duplicate device id");
+    }
+    {
+        DeviceGuard keep(ids[0]);
+        for (uint32_t i = 0; i < N; ++i) {
+            cudaSetDevice(ids[i]);
+            for (uint32_t j = 0; j < N; ++j)
+                if (j != i) cudaDeviceEnablePeerAccess(ids[j], 0);  // direct NVLink copies; staged through the host otherwise
+            cudaGetLastError();
+        }
+    }
+    std::vector<kmer_b200_index *> reps(N, nullptr);
+    std::vector<int> rc(N, 0);
+    std::vector<std::string> err(N);
+    auto build_all = [&](uint32_t parts) {
+        std::vector<std::thread> th;
+        for (uint32_t i = 0; i < N; ++i)
+            th.emplace_back([&, i] {
+                kmer_b200_config c = *cfg_in;
+                c.device = ids[i];
+                c.n_devices = 0;
+                c.device_ids = nullptr;
+                c.key_part = parts > 1 ? i : 0;
+                c.key_parts = parts > 1 ? parts : 0;
+                rc[i] = create_impl(ranks, false, n, sigma, ks, n_ks, &c, &reps[i], lut256);
+                if (rc[i] != 0) err[i] = g_last_error;
+            });
+        for (auto &t : th) t.join();
+    };
+    auto destroy_all = [&] {
+        for (auto &r : reps) {
+            kmer_b200_destroy(r);
+            r = nullptr;
+        }
+    };
+    build_all(N);
+    bool parts = true;
+    for (uint32_t i = 0; i < N; ++i)
+        if (rc[i] == KMER_B200_ERR_UNSUPPORTED) parts = false;
+    if (!parts) {  // no key-range parts for this index: every device builds the whole of it
+        destroy_all();
+        build_all(1);
+    }
+    for (uint32_t i = 0; i < N; ++i)
+        if (rc[i] != 0) {
+            const int code = rc[i];
+            const std::string msg = err[i];
+            destroy_all();
+            return fail(code, msg);
+        }
+    auto bail = [&](int code, const std::string &msg) {
+        destroy_all();
+        return fail(code, msg);
+    };
+    for (uint32_t e = 0; parts && e < n_ks; ++e) {
+        const uint64_t n_kmers = n - ks[e] + 1;
+        const uint64_t key_space = reps[0]->elems[e].dev.key_space;
+        std::vector<uint64_t> base(N + 1, 0);
+        for (uint32_t i = 0; i < N; ++i) base[i + 1] = base[i] + reps[i]->elems[e].dev.n_kmers;
+        if (base[N] != n_kmers) return bail(KMER_B200_ERR_CUDA, "multi-device build: the parts do not add up to the whole index");
+        std::vector<uint32_t *> pos_full(N, nullptr), dir_full(N, nullptr);
+        for (uint32_t d = 0; d < N; ++d) {
+            DeviceGuard g(ids[d]);
+            if (dev_alloc(reps[d], &pos_full[d], n_kmers, false) || dev_alloc(reps[d], &dir_full[d], key_space + 1, false))
+                return bail(KMER_B200_ERR_OUT_OF_MEMORY, g_last_error);
+        }
+        // every device: its own part into its own whole arrays (positions copied, directory offset by the earlier parts)
+        std::vector<uint64_t> lo(N), n_dir(N);
+        for (uint32_t i = 0; i < N; ++i) {
+            DeviceGuard g(ids[i]);
+            const HostElement &he = reps[i]->elems[e];
+            lo[i] = he.dev.key_lo;
+            n_dir[i] = he.dev.key_hi - he.dev.key_lo + (i + 1 == N ? 1 : 0);
+            const uint64_t cnt = he.dev.n_kmers;
+            if (cnt) cudaMemcpyAsync(pos_full[i] + base[i], he.d_pos, cnt * 4, cudaMemcpyDeviceToDevice, reps[i]->stream);
+            if (n_dir[i])
+                add_base32_kernel<<<(unsigned)((n_dir[i] + 255) / 256), 256, 0, reps[i]->stream>>>(he.d_dir, n_dir[i], (uint32_t)base[i],
+                                                                                                  dir_full[i] + lo[i]);
+        }
+        for (uint32_t i = 0; i < N; ++i) {
+            DeviceGuard g(ids[i]);
+            if (cudaStreamSynchronize(reps[i]->stream) != cudaSuccess) return bail(KMER_B200_ERR_CUDA, "multi-device build: part export failed");
+        }
+        // ... and pushed to every other device (NVLink peer copies, all sources at once)
+        for (uint32_t i = 0; i < N; ++i) {
+            DeviceGuard g(ids[i]);
+            const uint64_t cnt = base[i + 1] - base[i];
+            for (uint32_t d = 0; d < N; ++d) {
+                if (d == i) continue;
+                if (cnt) cudaMemcpyPeerAsync(pos_full[d] + base[i], ids[d], pos_full[i] + base[i], ids[i], cnt * 4, reps[i]->stream);
+                if (n_dir[i]) cudaMemcpyPeerAsync(dir_full[d] + lo[i], ids[d], dir_full[i] + lo[i], ids[i], n_dir[i] * 4, reps[i]->stream);
+            }
+        }
+        for (uint32_t i = 0; i < N; ++i) {
+            DeviceGuard g(ids[i]);
+            if (cudaStreamSynchronize(reps[i]->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+                return bail(KMER_B200_ERR_CUDA, "multi-device build: peer copy failed");
+        }
+        for (uint32_t d = 0; d < N; ++d) {
+            const int s = adopt_element_impl(reps[d], e, pos_full[d], n_kmers, dir_full[d], key_space + 1, 2);
+            if (s != 0) return bail(s, g_last_error);
+        }
+    }
+    kmer_b200_index *group = new (std::nothrow) kmer_b200_index();
+    if (!group) return bail(KMER_B200_ERR_OUT_OF_MEMORY, "host allocation failed");
+    group->device = ids[0];
+    group->cfg = *cfg_in;
+    group->cfg.device_ids = nullptr;
+    group->n = n;
+    group->sigma = sigma;
+    group->bits = reps[0]->bits;
+    group->ks.assign(ks, ks + n_ks);
+    group->replicas = reps;
+    *out = group;
+    return KMER_B200_OK;
+}
+
+// A host batch on a multi-device handle: device i takes the queries [Q i / N, Q (i + 1) / N) -- its own upload, search
+// and download, all devices at once -- and the slices are concatenated into one result.
+static int search_batch_multi(kmer_b200_index *group, const uint8_t *q_ranks, const uint64_t *q_offsets, uint64_t Q, uint32_t mode,
+                              const uint8_t *lut256, kmer_b200_result **out) {
+    const uint32_t N = (uint32_t)group->replicas.size();
+    std::vector<kmer_b200_result *> part(N, nullptr);
+    std::vector<int> rc(N, 0);
+    std::vector<std::string> err(N);
+    std::vector<uint64_t> q0(N + 1);
+    for (uint32_t i = 0; i <= N; ++i) q0[i] = Q * i / N;
+    {
+        std::vector<std::thread> th;
+        for (uint32_t i = 0; i < N; ++i)
+            th.emplace_back([&, i] {
+                rc[i] = search_batch_host(group->replicas[i], q_ranks, q_offsets + q0[i], q0[i + 1] - q0[i], mode, lut256, &part[i]);
+                if (rc[i] != 0) err[i] = g_last_error;
+            });
+        for (auto &t : th) t.join();
+    }
+    auto free_parts = [&] {
+        for (auto *r : part) kmer_b200_result_free(r);
+    };
+    for (uint32_t i = 0; i < N; ++i)
+        if (rc[i] != 0) {
+            const int code = rc[i];
+            const std::string msg = err[i];
+            free_parts();
+            return fail(code, msg);
+        }
+    kmer_b200_result *res = new (std::nothrow) kmer_b200_result();
+    if (!res) {
+        free_parts();
+        return fail(KMER_B200_ERR_OUT_OF_MEMORY, "host allocation failed");
+    }
+    res->index = group;
+    res->on_device = false;
+    res->n_queries = Q;
+    std::vector<uint64_t> p0(N + 1, 0);
+    for (uint32_t i = 0; i < N; ++i) p0[i + 1] = p0[i] + part[i]->n_positions;
+    res->n_positions = p0[N];
+    res->offsets = (uint64_t *)pinned_get((Q + 1) * sizeof(uint64_t), &res->cap_offsets);
+    res->status = (uint8_t *)pinned_get(Q, &res->cap_status);
+    const size_t pos_bytes = p0[N] * sizeof(uint32_t);
+    if (pos_bytes > (8ull << 30)) {
+        res->positions = (uint32_t *)std::malloc(pos_bytes);
+        res->positions_pageable = true;
+        res->cap_positions = pos_bytes;
+    } else {
+        res->positions = (uint32_t *)pinned_get(pos_bytes, &res->cap_positions);
+    }
+    if (!res->offsets || !res->status || !res->positions) {
+        free_parts();
+        kmer_b200_result_free(res);
+        return fail(KMER_B200_ERR_OUT_OF_MEMORY, "host allocation failed");
+    }
+    {
+        std::vector<std::thread> th;
+        for (uint32_t i = 0; i < N; ++i)
+            th.emplace_back([&, i] {
+                const uint64_t Qi = q0[i + 1] - q0[i];
+                const uint64_t *so = part[i]->offsets;
+                uint64_t *dof = res->offsets + q0[i];
+                for (uint64_t j = 0; j < Qi; ++j) dof[j] = so[j] + p0[i];
+                if (Qi) std::memcpy(res->status + q0[i], part[i]->status, Qi);
+                if (part[i]->n_positions) std::memcpy(res->positions + p0[i], part[i]->positions, part[i]->n_positions * sizeof(uint32_t));
+            });
+        for (auto &t : th) t.join();
+    }
+    res->offsets[Q] = p0[N];
+    free_parts();
+    *out = res;
+    return KMER_B200_OK;
+}
+
 uint64_t kmer_b200_scheme(const kmer_b200_index *ix, uint64_t m, uint32_t *out_ks, uint64_t cap, int *use_multi) {
+    ix = primary(ix);
     if (!ix || m >= kb::kQuerySizeRange) return 0;
     const uint32_t o = ix->sum_off[m], len = ix->sum_off[m + 1] - o;
     for (uint32_t i = 0; i < len && i < cap && out_ks; ++i) out_ks[i] = ix->ks[ix->sum_elem[o + i]];
@@ -2130,6 +2424,7 @@ uint64_t kmer_b200_scheme_for_ks(const uint32_t *ks, uint32_t n_ks, uint64_t m, 
 }
 
 uint32_t kmer_b200_stats(kmer_b200_index *ix, kmer_b200_kernel_stat *out, uint32_t cap) {
+    ix = primary(ix);  // a multi-device handle reports its first device
     if (!ix) return 0;
     DeviceGuard guard(ix->device);
     ix->prof.resolve();
@@ -2148,13 +2443,22 @@ uint32_t kmer_b200_stats(kmer_b200_index *ix, kmer_b200_kernel_stat *out, uint32
 
 void kmer_b200_stats_reset(kmer_b200_index *ix) {
     if (!ix) return;
+    if (!ix->replicas.empty()) {
+        for (kmer_b200_index *r : ix->replicas) kmer_b200_stats_reset(r);
+        return;
+    }
     DeviceGuard guard(ix->device);
     ix->prof.reset();
 }
 
-uint64_t kmer_b200_device_bytes(const kmer_b200_index *ix) { return ix ? ix->device_bytes : 0; }
+uint64_t kmer_b200_device_bytes(const kmer_b200_index *ix) {
+    if (!ix) return 0;
+    uint64_t total = ix->device_bytes;
+    for (const kmer_b200_index *r : ix->replicas) total += r->device_bytes;  // all devices of a multi-device handle
+    return total;
+}
 
-uint64_t kmer_b200_last_search_gathers(const kmer_b200_index *ix) { return ix ? ix->last_gathers : 0; }
+uint64_t kmer_b200_last_search_gathers(const kmer_b200_index *ix) { return ix ? primary(ix)->last_gathers : 0; }
 
 int kmer_b200_gather_probe(uint64_t table_bytes, uint64_t n_gathers, void *stream, double *ms_out) {
     if (!ms_out || table_bytes < 4096 || n_gathers == 0) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad probe arguments");

@@ -398,7 +398,7 @@ def assemble_replicated(ix, world: int, rank: int, dist, dev, timing=None):
             mine = dir_full[los[rank]:los[rank] + width].clone()
             dist.all_gather_into_tensor(dir_full[:key_space], mine)
             if not last:
-                dir_full[key_space:].fill_(n_kmers)
+                dir_full[key_space:].fill_(n_kmers - (1 << 32) if n_kmers >= (1 << 31) else n_kmers)   # uint32 bit pattern
         else:
             for r in range(world):
                 hi_r = his[r] + (1 if r == world - 1 else 0)

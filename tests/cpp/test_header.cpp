@@ -101,6 +101,45 @@ int main()
         for (size_t i = 0; i < qs.size(); ++i)
             REQUIRE(batch[i].to_vector() == scan(text, qs[i]));
     }
+    // the reference's result surface (kmer_index_result.hpp:203-270): bucket + mask, should_use / should_not_use
+    {
+        std::vector<uint32_t> bucket{40, 10, 30, 20};
+        kmer::detail::kmer_index_result<uint32_t> r(&bucket, false);
+        REQUIRE(r.size() == 0 && r.to_vector().empty());
+        r.should_use(0);
+        r.should_use(3);
+        REQUIRE((r.to_vector() == std::vector<uint32_t>{20, 40}));
+        r.should_not_use(0);
+        REQUIRE((r.to_vector() == std::vector<uint32_t>{20}));
+        std::vector<uint32_t> other{5};
+        std::vector<std::vector<uint32_t> const*> buckets{&bucket, &other};
+        kmer::detail::kmer_index_result<uint32_t> many(buckets);
+        REQUIRE((many.to_vector() == std::vector<uint32_t>{5, 10, 20, 30, 40}));
+        // element-level exact lookup from an iterator (kmer_index.hpp:182-190)
+        REQUIRE(single.search_k<10>(text.begin() + 321).to_vector() ==
+                scan(text, std::vector<alphabet_t>(text.begin() + 321, text.begin() + 331)));
+        REQUIRE(multi.search_k<11>(text.begin() + 99).to_vector() ==
+                scan(text, std::vector<alphabet_t>(text.begin() + 99, text.begin() + 110)));
+    }
+    // one index over all the GPUs of the box (kmer_b200_config.device_ids): same answers as the one-device index
+    {
+        int n_dev = 0;
+        if (std::getenv("KMER_B200_TEST_DEVICES")) n_dev = std::atoi(std::getenv("KMER_B200_TEST_DEVICES"));
+        if (n_dev >= 2)
+        {
+            std::vector<int> devices;
+            for (int d = 0; d < n_dev; ++d) devices.push_back(d);
+            kmer::kmer_index<alphabet_t, uint32_t, 10, 11, 12> wide(text, devices);
+            std::vector<std::vector<alphabet_t>> qs;
+            for (int i = 0; i < 2000; ++i) {
+                size_t m = 5 + i % 15, start = next_u32() % (text.size() - m + 1);
+                qs.emplace_back(text.begin() + start, text.begin() + start + m);
+            }
+            auto a = wide.search_batch(qs), b = multi.search_batch(qs);
+            REQUIRE(a.offsets == b.offsets && a.positions == b.positions && a.status == b.status);
+            std::printf("multi-device index over %d GPUs: ok\n", n_dev);
+        }
+    }
     // other alphabets
     {
         std::vector<kmer::dna15> t15(50000);

@@ -26,6 +26,8 @@ def test_header_compiles_and_links(tmp_path):
 @pytest.mark.gpu
 def test_header_runs(tmp_path):
     exe = _compile(tmp_path)
-    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    import torch
+    env = dict(os.environ, KMER_B200_TEST_DEVICES=str(min(torch.cuda.device_count(), 4)))
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stderr + out.stdout
     assert "all checks passed" in out.stdout
