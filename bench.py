@@ -57,10 +57,12 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--count-only", action="store_true", help="time search without materialising positions")
-    ap.add_argument("--multi", default="replicated", choices=["replicated", "position-range"],
-                    help="N > 1: 'replicated' = every GPU sorts one key-range part, the parts are all-gathered over NVLink "
-                         "into the whole index on every GPU and each GPU answers 1/N of the batch; 'position-range' = text "
-                         "shards with halo, every GPU searches the whole batch, hit lists merged on rank 0")
+    ap.add_argument("--multi", default="routed", choices=["routed", "replicated", "position-range"],
+                    help="N > 1: 'routed' = every GPU keeps one key-range part of the index, each GPU routes its 1/N of the "
+                         "batch to the owners of the queries' first k-mers and gets the results back (three all-to-alls); "
+                         "'replicated' = the parts are all-gathered over NVLink into the whole index on every GPU and each GPU "
+                         "answers 1/N of the batch locally; 'position-range' = text shards with halo, every GPU searches the "
+                         "whole batch, hit lists merged on rank 0")
     return ap.parse_args()
 
 
@@ -235,11 +237,13 @@ def run_ours(args, wl):
     Q = max(int(wl["Q"] * args.scale), 1)
     m_lo, m_hi = wl["m"]
     k_max = max(ks)
-    replicated = world > 1 and args.multi == "replicated"
+    routed = world > 1 and args.multi == "routed" and len(ks) == 1 and m_lo >= ks[0]
+    replicated = world > 1 and (args.multi == "replicated" or (args.multi == "routed" and not routed))
+    parted = routed or replicated   # the index is built from key-range parts; every rank holds the whole text and 1/N of the batch
 
     # ---- the text. position-range: this rank's slice (k-mer/match starts [begin, end) plus a halo of m_hi - 1 symbols);
     # replicated: the whole text on every rank (each rank sorts only its key-range part of it)
-    shard = sharded.shard_range(n, 1 if replicated else world, 0 if replicated else rank, halo=max(m_hi, k_max) - 1)
+    shard = sharded.shard_range(n, 1 if parted else world, 0 if parted else rank, halo=max(m_hi, k_max) - 1)
     n_local = shard.length
     text = torch.empty(n_local, dtype=torch.uint8, device=dev)
     _capi.check(L.kmer_b200_synth_ranks_device(text.data_ptr(), n_local, shard.begin, sigma, TEXT_SEED, sptr))
@@ -249,7 +253,7 @@ def run_ours(args, wl):
     g = torch.Generator(device=dev)
     g.manual_seed(QUERY_SEED)
     lens = torch.randint(m_lo, m_hi + 1, (Q,), generator=g, device=dev, dtype=torch.int64)
-    q_lo, q_hi = (rank * Q // world, (rank + 1) * Q // world) if replicated else (0, Q)
+    q_lo, q_hi = (rank * Q // world, (rank + 1) * Q // world) if parted else (0, Q)
     sym_lo = int(lens[:q_lo].sum().item())
     Ql = q_hi - q_lo
     q_off = torch.zeros(Ql + 1, dtype=torch.int64, device=dev)
@@ -261,7 +265,7 @@ def run_ours(args, wl):
     torch.cuda.synchronize()
 
     def make_index(profile, text_ptr=None, host_text=None):
-        if replicated:
+        if parted:
             return kb.KmerIndex(host_text, sigma, ks, stream=sptr, profile=profile, device=local_rank,
                                 text_device_ptr=text_ptr, n=n_local, key_part=rank, key_parts=world)
         return kb.KmerIndex(host_text, sigma, ks, stream=sptr, profile=profile, device=local_rank,
@@ -273,7 +277,19 @@ def run_ours(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def finish_build(ix):
+        """the cross-GPU part of the build: all-gather of the parts (replicated) or of the presence bitmap (routed)"""
+        if replicated:
+            sharded.assemble_replicated(ix, world, rank, dist, dev)
+        elif routed:
+            sharded.share_presence(ix, world, rank, dist, dev)
+
     def search_resident(ix, count_only):
+        if routed:
+            res = sharded.search_routed(ix, q.data_ptr(), q_off.data_ptr(), Ql, m_hi, -(-Q // world), world, rank, dist, dev)
+            h = res.n_positions
+            res.free()
+            return h
         if replicated:
             return sharded.search_device(ix, q.data_ptr(), q_off.data_ptr(), Ql, m_hi, 1, dev, count_only=count_only)
         return sharded.search_device(ix, q.data_ptr(), q_off.data_ptr(), Q, m_hi, world, dev, count_only=count_only)
@@ -284,8 +300,7 @@ def run_ours(args, wl):
         e[0].record(stream)
         ix = make_index(profile, text_ptr=text.data_ptr())
         e[1].record(stream)
-        if replicated:
-            sharded.assemble_replicated(ix, world, rank, dist, dev)   # NCCL all-gather of the parts: part of the build
+        finish_build(ix)   # NCCL: part of the build
         e[2].record(stream)
         hits = search_resident(ix, args.count_only)
         e[3].record(stream)
@@ -319,14 +334,17 @@ def run_ours(args, wl):
     # search must fetch at data-dependent addresses) and the device's random-gather ceiling
     gathers = gather_peak = None
     ix = make_index(2, text_ptr=text.data_ptr())
-    if replicated:
-        sharded.assemble_replicated(ix, world, rank, dist, dev)
+    finish_build(ix)
     search_resident(ix, True)
     gathers = ix.last_search_gathers
-    fp = sharded.fingerprint(ix, q.data_ptr(), q_off.data_ptr(), Ql if replicated else Q, m_hi,
-                             1 if replicated else world, dev, q_lo)
+    if routed:
+        fp = sharded.fingerprint_of(sharded.search_routed(ix, q.data_ptr(), q_off.data_ptr(), Ql, m_hi, -(-Q // world), world, rank,
+                                                          dist, dev), Ql, dev, q_lo)
+    else:
+        fp = sharded.fingerprint(ix, q.data_ptr(), q_off.data_ptr(), Ql if replicated else Q, m_hi,
+                                 1 if replicated else world, dev, q_lo)
     ix.close()
-    if replicated:
+    if parted:
         t = torch.tensor([fp["hits"], fp["checksum"]] + fp["status_hist"] + [gathers], dtype=torch.int64, device=dev)
         dist.all_reduce(t)   # int64 sums wrap: the checksum is defined modulo 2^64
         t = [int(x) for x in t.cpu()]
@@ -352,10 +370,11 @@ def run_ours(args, wl):
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             ev[0].record(stream)
             ix = make_index(False, host_text=h_text.numpy())
-            if replicated:
-                sharded.assemble_replicated(ix, world, rank, dist, dev)
+            finish_build(ix)
             ev[1].record(stream)
-            if world == 1 or replicated:
+            if routed:
+                res = sharded.search_routed_host(ix, h_q, h_off, -(-Q // world), m_hi, world, rank, dist, dev)
+            elif world == 1 or replicated:
                 res = sharded.search_host(ix, h_q.numpy(), h_off.numpy().view(np.uint64), 1, dev)
             else:
                 res = sharded.search_host(ix, h_q, h_off, world, dev)
@@ -368,7 +387,7 @@ def run_ours(args, wl):
                 eb.append(ev[0].elapsed_time(ev[1]))
                 es.append(ev[1].elapsed_time(ev[2]))
         # position-range: every rank uploads 1/world of the query batch (then NCCL all-gather); replicated: its own slice
-        h2d_q = (n_sym + (Ql + 1) * 8) // (1 if replicated else world)
+        h2d_q = (n_sym + (Ql + 1) * 8) // (1 if parted else world)
         e2e = {"build_ms": float(np.mean(eb)), "search_ms": float(np.mean(es)), "h2d": n_local + h2d_q, "d2h": d2h}
         del h_text, h_q, h_off
 
@@ -387,7 +406,7 @@ def run_ours(args, wl):
         e2e["build_ms"] = max_over_ranks(e2e["build_ms"])
         e2e["search_ms"] = max_over_ranks(e2e["search_ms"])
         if world > 1:   # bytes per step over all ranks
-            t = torch.tensor([e2e["h2d"], e2e["d2h"] if (rank == 0 or replicated) else 0], dtype=torch.float64, device=dev)
+            t = torch.tensor([e2e["h2d"], e2e["d2h"] if (rank == 0 or parted) else 0], dtype=torch.float64, device=dev)
             dist.all_reduce(t)
             e2e["h2d"], e2e["d2h"] = int(t[0].item()), int(t[1].item())
 
@@ -410,7 +429,11 @@ def run_ours(args, wl):
         for v in kernels.values():
             v["frac_of_hbm_peak"] = v["algorithmic_gbs"] / peak if v["algorithmic_gbs"] else None
         sharding = "none"
-        if replicated:
+        if routed:
+            sharding = (f"partitioned index x{world}: every GPU keeps one key-range part of the hashes (+ the packed text and a "
+                        f"presence bitmap), holds 1/{world} of the batch, routes each query to the owner of its first k-mer and "
+                        f"gets the results back (three NCCL all-to-alls inside search_ms)")
+        elif replicated:
             sharding = (f"replicated index x{world}: every GPU sorts one key-range part of the hashes, parts all-gathered "
                         f"over NCCL (inside build_ms), each GPU answers 1/{world} of the batch")
         elif world > 1:
@@ -427,7 +450,7 @@ def run_ours(args, wl):
                        "l2": "inputs larger than L2 (text, index and batch are each >> 126 MB)" if n * 4 > 2e8 else
                              "inputs smaller than L2; step rebuilds the index so no data is reused across steps"},
             "build": {"metric": "build_gbases_per_s", "value": n / (build_ms * 1e-3) / 1e9, "unit": "Gbases/s",
-                      "ms": build_ms, "nccl_gather_ms": gather_ms if replicated else 0.0},
+                      "ms": build_ms, "nccl_ms": gather_ms if parted else 0.0},
             "search": {"ms": search_ms, "hits": int(hits), "checksum": fp["checksum"], "status_hist": fp["status_hist"]},
             "roofline": {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
@@ -455,7 +478,7 @@ def run_ours(args, wl):
         # search roofline: sectors gathered per second against the measured random-gather ceiling
         s_ms = stats_acc.get("search_count", {"device_ms": 0.0})["device_ms"] / args.steps
         if gathers and gather_peak and s_ms > 0:
-            g_rank0 = gathers / (world if replicated else 1)
+            g_rank0 = gathers / (world if parted else 1)
             rate = g_rank0 / (s_ms * 1e-3)
             line["roofline_search"] = {"kernel": "search_count", "bound": "hbm", "achieved": rate * 32 / 1e9,
                                        "peak": gather_peak * 32 / 1e9, "unit": "GB/s", "frac": rate / gather_peak,

@@ -217,6 +217,48 @@ int kmer_b200_export_directory(kmer_b200_index *index, uint32_t element, uint64_
 int kmer_b200_adopt_element(kmer_b200_index *index, uint32_t element, const uint32_t *d_positions, uint64_t n_kmers,
                             const uint32_t *d_directory, uint64_t directory_entries);
 
+/* ---- key-range multi-GPU search: the index stays partitioned (one key-range part per GPU, no assembly), queries
+   travel to the GPU that owns the hash of their first k symbols and results travel back. Single-k indices with 32-bit
+   hashes; queries no shorter than k. Each rank drives these calls and moves the blocks between them with three
+   equal-/variable-split all-to-all collectives (kmer_index_b200/sharded.py: search_routed):
+
+     origin   kmer_b200_route_queries_device   its slice of the batch -> n_parts send blocks          --all-to-all-->
+     owner    kmer_b200_search_routed_device   received blocks -> search -> return blocks + positions  --all-to-all x2-->
+     origin   kmer_b200_unroute_device         return blocks + positions -> CSR result of its slice
+
+   Whole-text rules of the reference (a part of the query absent anywhere => empty; rest too short => throw) are
+   decided by the owner from a presence bitmap over the whole key space: every part exports its slice
+   (kmer_b200_presence_export), the slices are all-gathered, the whole bitmap is attached (kmer_b200_presence_attach). */
+typedef struct kmer_b200_route_plan {
+    uint32_t n_parts;            /* GPUs = index parts */
+    uint32_t stride;             /* 64-bit words per packed query */
+    uint32_t capacity;           /* records per block (the same on every rank) */
+    uint32_t reserved;
+    uint64_t block_bytes;        /* one send block; send / receive buffers hold n_parts of them */
+    uint64_t return_block_bytes; /* one return block */
+} kmer_b200_route_plan;
+/* n_queries: the largest per-rank batch slice; capacity = n_queries / n_parts * slack + 1024 (slack <= 0: 1.25) */
+int kmer_b200_route_plan_make(const kmer_b200_index *index, uint64_t n_queries, uint64_t max_query_len, uint32_t n_parts,
+                              double slack, kmer_b200_route_plan *out);
+/* d_status[Q]: 0xFF for routed queries, else the status decided at the origin (empty / over-long queries).
+   sent_counts[n_parts] (host): records per block; a count above plan->capacity means that block overflowed (nothing
+   was lost on the device side only if the caller re-plans with a larger capacity and routes again). */
+int kmer_b200_route_queries_device(kmer_b200_index *index, const uint8_t *d_q_ranks, const uint64_t *d_q_offsets, uint64_t n_queries,
+                                   uint32_t mode, const kmer_b200_route_plan *plan, uint8_t *d_send_blocks, uint8_t *d_status,
+                                   uint32_t *sent_counts);
+/* position_splits[n_parts] (host): how many positions of the result belong to each origin, in block order; the result's
+   position array is the send buffer of the positions all-to-all. */
+int kmer_b200_search_routed_device(kmer_b200_index *index, uint8_t *d_received_blocks, const kmer_b200_route_plan *plan, uint32_t mode,
+                                   uint8_t *d_return_blocks, uint64_t *position_splits, kmer_b200_result **out);
+int kmer_b200_unroute_device(kmer_b200_index *index, uint8_t *d_send_blocks, uint8_t *d_received_return_blocks,
+                             const kmer_b200_route_plan *plan, const uint32_t *sent_counts, const uint32_t *d_received_positions,
+                             const uint64_t *received_position_splits, uint64_t n_queries, const uint8_t *d_status,
+                             kmer_b200_result **out);
+/* bit h of the bitmap = hash h occurs in the text; the bitmap has sigma^k bits rounded up to 64-bit words (+1 word) */
+uint64_t kmer_b200_presence_words(const kmer_b200_index *index, uint32_t element);
+int kmer_b200_presence_export(kmer_b200_index *index, uint32_t element, uint64_t *d_bitmap);
+int kmer_b200_presence_attach(kmer_b200_index *index, uint32_t element, const uint64_t *d_bitmap);
+
 /* ---- introspection (parity tests and roofline accounting) */
 typedef struct kmer_b200_element_info {
     uint32_t k;

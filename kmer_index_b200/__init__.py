@@ -380,6 +380,47 @@ class KmerIndex:
                                                     C.c_void_p(directory.data_ptr()), directory.numel()))
         self._adopted.append((positions, directory))
 
+    # -- key-range multi-GPU search: routing (sharded.search_routed drives these)
+    def route_plan(self, n_queries: int, max_len: int, n_parts: int, slack: float = 0.0) -> _capi.RoutePlan:
+        plan = _capi.RoutePlan()
+        _capi.check(self._L.kmer_b200_route_plan_make(self._h, n_queries, max_len, n_parts, slack, C.byref(plan)))
+        return plan
+
+    def route_queries(self, q_ptr: int, off_ptr: int, Q: int, plan, send_ptr: int, status_ptr: int, mode: int = MODE_DEFAULT):
+        counts = (C.c_uint32 * plan.n_parts)()
+        _capi.check(self._L.kmer_b200_route_queries_device(self._h, C.c_void_p(q_ptr), C.c_void_p(off_ptr), Q, mode, C.byref(plan),
+                                                           C.c_void_p(send_ptr), C.c_void_p(status_ptr), counts))
+        return [int(x) for x in counts]
+
+    def search_routed(self, recv_ptr: int, plan, return_ptr: int, mode: int = MODE_DEFAULT):
+        splits = (C.c_uint64 * plan.n_parts)()
+        r = C.c_void_p()
+        _capi.check(self._L.kmer_b200_search_routed_device(self._h, C.c_void_p(recv_ptr), C.byref(plan), mode, C.c_void_p(return_ptr),
+                                                           splits, C.byref(r)))
+        total = sum(int(x) for x in splits)
+        res = DeviceResult(self._L, r, 0)
+        res.n_positions = total
+        return res, [int(x) for x in splits]
+
+    def unroute(self, send_ptr: int, ret_ptr: int, plan, sent_counts, recv_pos_ptr: int, recv_splits, Q: int, status_ptr: int):
+        sc = (C.c_uint32 * plan.n_parts)(*sent_counts)
+        rs = (C.c_uint64 * plan.n_parts)(*recv_splits)
+        r = C.c_void_p()
+        _capi.check(self._L.kmer_b200_unroute_device(self._h, C.c_void_p(send_ptr), C.c_void_p(ret_ptr), C.byref(plan), sc,
+                                                     C.c_void_p(recv_pos_ptr), rs, Q, C.c_void_p(status_ptr), C.byref(r)))
+        return DeviceResult(self._L, r, Q)
+
+    def presence_words(self, e: int) -> int:
+        return int(self._L.kmer_b200_presence_words(self._h, e))
+
+    def presence_export(self, e: int, bitmap_ptr: int) -> None:
+        _capi.check(self._L.kmer_b200_presence_export(self._h, e, C.c_void_p(bitmap_ptr)))
+
+    def presence_attach(self, e: int, bitmap) -> None:
+        """bitmap: int64 device tensor of presence_words(e) words (kept alive by this object), or None to detach."""
+        _capi.check(self._L.kmer_b200_presence_attach(self._h, e, C.c_void_p(bitmap.data_ptr() if bitmap is not None else 0)))
+        self._adopted.append(bitmap)
+
     # -- introspection
     def element_info(self, e: int) -> _capi.ElementInfo:
         info = _capi.ElementInfo()

@@ -40,6 +40,11 @@ class Part(C.Structure):
                 ("d_positions", C.c_void_p), ("d_directory", C.c_void_p)]
 
 
+class RoutePlan(C.Structure):
+    _fields_ = [("n_parts", C.c_uint32), ("stride", C.c_uint32), ("capacity", C.c_uint32), ("reserved", C.c_uint32),
+                ("block_bytes", C.c_uint64), ("return_block_bytes", C.c_uint64)]
+
+
 class KernelStat(C.Structure):
     _fields_ = [("name", C.c_char_p), ("launches", C.c_uint64), ("device_ms", C.c_double),
                 ("algorithmic_bytes", C.c_double)]
@@ -90,6 +95,16 @@ SYMBOLS = {
     "kmer_b200_element_part": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(Part)]),
     "kmer_b200_export_directory": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]),
     "kmer_b200_adopt_element": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
+    "kmer_b200_route_plan_make": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_double, C.POINTER(RoutePlan)]),
+    "kmer_b200_route_queries_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(RoutePlan),
+                                                 C.c_void_p, C.c_void_p, u32p]),
+    "kmer_b200_search_routed_device": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(RoutePlan), C.c_uint32, C.c_void_p, u64p,
+                                                 C.POINTER(C.c_void_p)]),
+    "kmer_b200_unroute_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(RoutePlan), u32p, C.c_void_p, u64p,
+                                           C.c_uint64, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "kmer_b200_presence_words": (C.c_uint64, [C.c_void_p, C.c_uint32]),
+    "kmer_b200_presence_export": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
+    "kmer_b200_presence_attach": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
     "kmer_b200_n_elements": (C.c_uint32, [C.c_void_p]),
     "kmer_b200_element_info_get": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(ElementInfo)]),
     "kmer_b200_element_positions": (C.c_int, [C.c_void_p, C.c_uint32, u32p, C.c_uint64]),

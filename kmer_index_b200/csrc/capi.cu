@@ -1,6 +1,8 @@
 // C ABI of libkmer_b200.so (include/kmer_b200.h): host-side orchestration of the build and search kernels.
 // No CPU fallback anywhere: every computing entry point needs a CUDA device.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1876,14 +1878,43 @@ static int search_batch_host(kmer_b200_index *ix, const uint8_t *q_ranks, const 
     if (n_sym && !q_ranks) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "q_ranks is null");
     // batches whose transfer dominates (>= 256 MiB over PCIe) are pipelined in chunks
     if (!lut256 && Q >= (1u << 18) && n_sym + Q * 17 >= (256ull << 20) && !std::getenv("KMER_B200_NO_PIPELINE")) {
-        // Which pipeline: pinned input crosses PCIe as it is (the copy engine reads it at ~55 GB/s; 16 host cores pack
-        // ~30 GB/s of variable-length queries, measured on the GPU box, so packing first would be slower). Pageable
-        // input cannot be DMA-ed directly -- the driver would stage it at a fraction of that rate -- so the host threads
-        // pack it straight out of the caller's memory into a pinned ring (a third of the bytes for dna4).
+        // Which pipeline. Pageable input cannot be DMA-ed directly (the driver would stage it at a fraction of the link
+        // rate): the host threads pack it straight out of the caller's memory into a pinned ring (a third of the bytes
+        // for dna4). Pinned input crosses PCIe as it is at ~55 GB/s unless this host packs faster than that, which is
+        // measured once per process on a sample of the first large batch (AVX2 packer, all pool threads; other
+        // processes sharing the cores -- one per GPU under torchrun -- lower the rate and so switch the packing off).
         // KMER_B200_HOST_PACK=1 / 0 forces the choice.
         cudaPointerAttributes attr{};
         bool pageable = cudaPointerGetAttributes(&attr, q_ranks) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
         cudaGetLastError();
+        if (!pageable) {
+            static std::atomic<int> pack_wins{-1};  // -1 unknown, 0 no, 1 yes
+            if (pack_wins.load() < 0) {
+                kb::HostPool &pool = kb::HostPool::instance();
+                const unsigned T = pool.threads();
+                const uint64_t Qs = std::min<uint64_t>(Q, 1u << 22);
+                const uint32_t spw = 64 / ix->bits;
+                std::vector<uint16_t> lens(Qs);
+                std::vector<uint64_t> part_max(T * 4, 0);
+                pool.run(T * 4, [&](unsigned t) { part_max[t] = kb::query_lengths_host(q_offsets, 0, Qs, lens.data(), t, T * 4); });
+                uint64_t mx = 1;
+                for (uint64_t v : part_max) mx = std::max(mx, v);
+                const uint64_t stride = (mx + spw - 1) / spw;
+                int wins = 0;
+                if (stride <= 16) {
+                    std::vector<uint64_t> words(Qs * stride);
+                    const auto t0 = std::chrono::steady_clock::now();
+                    pool.run(T * 4, [&](unsigned t) {
+                        kb::pack_queries_host(q_ranks, q_offsets, 0, Qs, ix->bits, ix->sigma, (uint32_t)stride, words.data(), t, T * 4);
+                    });
+                    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                    const double in_bytes = (double)(q_offsets[Qs] - q_offsets[0]) + 8.0 * Qs;
+                    wins = in_bytes / sec > 75e9 ? 1 : 0;  // must beat the ~55 GB/s link with margin (the pack also shares memory bandwidth with the DMA)
+                }
+                pack_wins.store(wins);
+            }
+            pageable = pack_wins.load() == 1;
+        }
         if (const char *env = std::getenv("KMER_B200_HOST_PACK")) pageable = std::atoi(env) != 0;
         if (pageable) {
             const int s = search_batch_host_packed(ix, q_ranks, q_offsets, Q, mode, out);
@@ -2179,6 +2210,207 @@ int kmer_b200_adopt_element(kmer_b200_index *ix, uint32_t e, const uint32_t *d_p
                             const uint32_t *d_directory, uint64_t directory_entries) {
     if (ix && !ix->replicas.empty()) return fail(KMER_B200_ERR_UNSUPPORTED, "not available on a multi-device handle");
     return adopt_element_impl(ix, e, d_positions, n_kmers, d_directory, directory_entries, 1);
+}
+
+// ---- key-range multi-GPU search: routing (route_kernels.cu) -----------------------------------------------------------
+static int routable(const kmer_b200_index *ix) {
+    if (!ix) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null index");
+    if (!ix->replicas.empty()) return fail(KMER_B200_ERR_UNSUPPORTED, "not available on a multi-device handle");
+    if (ix->ks.size() != 1 || ix->elems[0].key_bytes != 4 || ix->elems[0].dev.shift != 0)
+        return fail(KMER_B200_ERR_UNSUPPORTED, "query routing needs a single-k index with 32-bit hashes and a dense directory");
+    return 0;
+}
+
+int kmer_b200_route_plan_make(const kmer_b200_index *ix, uint64_t n_queries, uint64_t max_query_len, uint32_t n_parts, double slack,
+                              kmer_b200_route_plan *out) {
+    KB_TRY(routable(ix));
+    if (!out || n_parts == 0 || n_parts > (uint32_t)kb::kMaxParts) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad argument");
+    const uint32_t spw = 64 / ix->bits;
+    const uint64_t stride = std::max<uint64_t>(1, (std::max<uint64_t>(max_query_len, 1) + spw - 1) / spw);
+    if (stride > 16 || max_query_len > 65535) return fail(KMER_B200_ERR_UNSUPPORTED, "queries longer than 16 packed words are not routed");
+    if (slack <= 0) slack = 1.25;
+    const uint64_t cap = (uint64_t)((double)(n_queries / n_parts + 1) * slack) + 1024;
+    if (cap >= 0xFFFFFFFFull) return fail(KMER_B200_ERR_UNSUPPORTED, "batch too large: split it");
+    out->n_parts = n_parts;
+    out->stride = (uint32_t)stride;
+    out->capacity = (uint32_t)std::min<uint64_t>(cap, n_queries + 1024);
+    out->reserved = 0;
+    out->block_bytes = kb::route_block_bytes(out->capacity, out->stride);
+    out->return_block_bytes = kb::route_return_block_bytes(out->capacity);
+    return KMER_B200_OK;
+}
+
+int kmer_b200_route_queries_device(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off, uint64_t Q, uint32_t mode,
+                                   const kmer_b200_route_plan *plan, uint8_t *d_send_blocks, uint8_t *d_status, uint32_t *sent_counts) {
+    KB_TRY(routable(ix));
+    if (!plan || !d_send_blocks || !sent_counts || (Q && (!d_off || !d_status))) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
+    if (mode == UINT32_MAX) mode = ix->cfg.mode;
+    DeviceGuard guard(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    cudaStream_t st = ix->stream;
+    uint32_t *d_flags = nullptr;
+    KB_TRY(dev_alloc(ix, &d_flags, 1, false));
+    cudaMemsetAsync(d_flags, 0, sizeof(uint32_t), st);
+    KB_CUDA(cudaMemset2DAsync(d_send_blocks, plan->block_bytes, 0, 64, plan->n_parts, st));  // the block headers
+    kb::RouteArgs a{};
+    a.q_ranks = d_q;
+    a.q_offsets = d_off;
+    a.n_queries = Q;
+    a.mode = mode;
+    a.bits = ix->bits;
+    a.sigma = ix->sigma;
+    a.k = ix->ks[0];
+    {
+        kmer_b200_config c = ix->cfg;
+        c.key_part = 0;
+        c.key_parts = plan->n_parts;
+        a.part_width = std::max<uint64_t>(1, key_range_of(c, ix->elems[0].dev.key_space).hi);  // part 0's upper bound = the width
+    }
+    a.n_parts = plan->n_parts;
+    a.stride = plan->stride;
+    a.capacity = plan->capacity;
+    a.blocks = d_send_blocks;
+    a.block_bytes = plan->block_bytes;
+    a.status = d_status;
+    a.flags = d_flags;
+    kb::launch_route_pack(a, st);
+    uint32_t flags = 0;
+    KB_CUDA(cudaMemcpy2DAsync(sent_counts, sizeof(uint32_t), d_send_blocks, plan->block_bytes, sizeof(uint32_t), plan->n_parts,
+                              cudaMemcpyDeviceToHost, st));
+    KB_CUDA(cudaMemcpyAsync(&flags, d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    KB_CUDA(cudaStreamSynchronize(st));
+    dev_free(ix, d_flags);
+    KB_CUDA(cudaGetLastError());
+    if (flags & 1u) return fail(KMER_B200_ERR_INVALID_RANK, "a query contains a rank >= sigma");
+    if (flags & 2u) return fail(KMER_B200_ERR_UNSUPPORTED, "the batch holds a query shorter than k (or longer than the plan's stride): not routable");
+    return KMER_B200_OK;  // counts above plan->capacity: the caller re-plans (all ranks together) and routes again
+}
+
+int kmer_b200_search_routed_device(kmer_b200_index *ix, uint8_t *d_recv_blocks, const kmer_b200_route_plan *plan, uint32_t mode,
+                                   uint8_t *d_return_blocks, uint64_t *position_splits, kmer_b200_result **out) {
+    KB_TRY(routable(ix));
+    if (!plan || !d_recv_blocks || !d_return_blocks || !position_splits || !out) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    DeviceGuard guard(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    cudaStream_t st = ix->stream;
+    const uint32_t N = plan->n_parts;
+    uint32_t counts[kb::kMaxParts] = {};
+    KB_CUDA(cudaMemcpy2DAsync(counts, sizeof(uint32_t), d_recv_blocks, plan->block_bytes, sizeof(uint32_t), N, cudaMemcpyDeviceToHost, st));
+    KB_CUDA(cudaStreamSynchronize(st));
+    kb::RoutePrefix pfx{};
+    for (uint32_t b = 0; b < N; ++b) {
+        if (counts[b] > plan->capacity) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "received block with more records than its capacity");
+        pfx.p[b + 1] = pfx.p[b] + counts[b];
+    }
+    const uint64_t Qr = pfx.p[N];
+    uint64_t *d_words = nullptr;
+    uint16_t *d_lens = nullptr;
+    KB_TRY(dev_alloc(ix, &d_words, Qr * plan->stride, false));
+    KB_TRY(dev_alloc(ix, &d_lens, Qr, false));
+    kb::launch_compact_blocks(d_recv_blocks, plan->block_bytes, N, plan->capacity, plan->stride, pfx, d_words, d_lens, st);
+    PackedQueries pk{d_words, d_lens, plan->stride};
+    kmer_b200_result *res = nullptr;
+    const uint64_t max_len = (uint64_t)plan->stride * (64 / ix->bits);
+    int s = search_device_impl(ix, nullptr, nullptr, Qr, max_len, mode, nullptr, 0, kFlavorFull, &res, &pk);
+    dev_free(ix, d_words);
+    dev_free(ix, d_lens);
+    if (s != 0) return s;
+    kb::launch_pack_return(res->offsets, res->status, pfx, N, d_return_blocks, plan->return_block_bytes, plan->capacity, st);
+    cudaError_t e = cudaMemcpy2DAsync(position_splits, sizeof(uint64_t), d_return_blocks + 8, plan->return_block_bytes, sizeof(uint64_t), N,
+                                      cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        kmer_b200_result_free(res);
+        return fail(KMER_B200_ERR_CUDA, std::string("search_routed: ") + cudaGetErrorString(e));
+    }
+    *out = res;
+    return KMER_B200_OK;
+}
+
+int kmer_b200_unroute_device(kmer_b200_index *ix, uint8_t *d_send_blocks, uint8_t *d_ret_blocks, const kmer_b200_route_plan *plan,
+                             const uint32_t *sent_counts, const uint32_t *d_recv_positions, const uint64_t *recv_splits, uint64_t Q,
+                             const uint8_t *d_status, kmer_b200_result **out) {
+    KB_TRY(routable(ix));
+    if (!plan || !d_send_blocks || !d_ret_blocks || !sent_counts || !recv_splits || !out || (Q && !d_status))
+        return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    DeviceGuard guard(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    cudaStream_t st = ix->stream;
+    const uint32_t N = plan->n_parts;
+    kb::RoutePrefix sent{};
+    kb::RoutePrefix64 seg{};
+    for (uint32_t b = 0; b < N; ++b) {
+        sent.p[b + 1] = sent.p[b] + sent_counts[b];
+        seg.p[b + 1] = seg.p[b] + recv_splits[b];
+    }
+    kmer_b200_result *res = new (std::nothrow) kmer_b200_result();
+    if (!res) return fail(KMER_B200_ERR_OUT_OF_MEMORY, "host allocation failed");
+    res->index = ix;
+    res->on_device = true;
+    res->n_queries = Q;
+    uint64_t *d_block_sums = nullptr;
+    auto bail = [&](int code) {
+        dev_free(ix, d_block_sums);
+        kmer_b200_result_free(res);
+        return code;
+    };
+    if (dev_alloc(ix, &res->offsets, Q + 1, false) || dev_alloc(ix, &res->status, Q, false) ||
+        dev_alloc(ix, &d_block_sums, kb::offsets_scan_blocks(Q) + 1, false))
+        return bail(KMER_B200_ERR_OUT_OF_MEMORY);
+    cudaMemsetAsync(res->offsets, 0, (Q + 1) * sizeof(uint64_t), st);
+    if (Q) cudaMemcpyAsync(res->status, d_status, Q, cudaMemcpyDeviceToDevice, st);
+    kb::launch_unroute_counts(d_send_blocks, plan->block_bytes, plan->stride, d_ret_blocks, plan->return_block_bytes, plan->capacity, N, sent,
+                              res->offsets, res->status, st);
+    kb::launch_offsets_scan(res->offsets, Q, d_block_sums, st);
+    uint64_t total = 0;
+    cudaError_t e = cudaMemcpyAsync(&total, res->offsets + Q, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return bail(fail(KMER_B200_ERR_CUDA, std::string("unroute: ") + cudaGetErrorString(e)));
+    if (total != seg.p[N]) return bail(fail(KMER_B200_ERR_INVALID_ARGUMENT, "unroute: the return blocks and the received positions disagree"));
+    res->n_positions = total;
+    if (total) {
+        if (!d_recv_positions) return bail(fail(KMER_B200_ERR_INVALID_ARGUMENT, "null positions"));
+        if (dev_alloc(ix, &res->positions, total, false)) return bail(KMER_B200_ERR_OUT_OF_MEMORY);
+        kb::launch_unroute_place(d_send_blocks, plan->block_bytes, plan->stride, d_ret_blocks, plan->return_block_bytes, plan->capacity, N, sent,
+                                 seg, d_recv_positions, res->offsets, res->positions, st);
+    }
+    dev_free(ix, d_block_sums);
+    d_block_sums = nullptr;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return bail(fail(KMER_B200_ERR_CUDA, std::string("unroute: ") + cudaGetErrorString(e)));
+    *out = res;
+    return KMER_B200_OK;
+}
+
+uint64_t kmer_b200_presence_words(const kmer_b200_index *ix, uint32_t e) {
+    ix = primary(ix);
+    if (!ix || e >= ix->ks.size()) return 0;
+    return (ix->elems[e].dev.key_space + 63) / 64 + 1;
+}
+
+int kmer_b200_presence_export(kmer_b200_index *ix, uint32_t e, uint64_t *d_bitmap) {
+    if (!ix || !d_bitmap || e >= ix->ks.size() || !ix->replicas.empty()) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad argument");
+    const HostElement &he = ix->elems[e];
+    if (he.dev.shift != 0) return fail(KMER_B200_ERR_UNSUPPORTED, "presence bitmaps come from dense directories");
+    DeviceGuard guard(ix->device);
+    const uint64_t lo = he.dev.key_lo, hi = he.dev.key_hi == UINT64_MAX ? he.dev.key_space : he.dev.key_hi;
+    if (lo % 64) return fail(KMER_B200_ERR_UNSUPPORTED, "part boundary not on a 64-hash boundary");
+    kb::launch_presence_bits(he.d_dir, hi - lo, d_bitmap + lo / 64, ix->stream);
+    KB_CUDA(cudaGetLastError());
+    return KMER_B200_OK;
+}
+
+int kmer_b200_presence_attach(kmer_b200_index *ix, uint32_t e, const uint64_t *d_bitmap) {
+    if (!ix || e >= ix->ks.size() || !ix->replicas.empty()) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad argument");
+    DeviceGuard guard(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    ix->host_index.presence[e] = d_bitmap;  // caller-owned; null detaches
+    KB_CUDA(cudaMemcpyAsync(ix->d_index, &ix->host_index, sizeof(kb::DeviceIndex), cudaMemcpyHostToDevice, ix->stream));
+    KB_CUDA(cudaStreamSynchronize(ix->stream));
+    return KMER_B200_OK;
 }
 
 // ---- several devices behind one handle (kmer_b200_config.n_devices > 1) ----------------------------------------------

@@ -148,6 +148,9 @@ struct DeviceIndex {
     // sorted union of the sigma^(k-m) buckets the reference enumerates (kmer_index.hpp:138-144) plus the
     // end-of-text positions of check_last_kmer (:90-112), so the result is identical and needs no sort.
     uint8_t aux_for_len[64];  // element slot for query length m < 64, 0xFF = none
+    // key-range multi-GPU search: per element, a bitmap over the WHOLE key space (bit h = hash h occurs in the text),
+    // or null. With it a part answers "does this part of the query occur anywhere" for hashes other parts own.
+    const uint64_t *presence[kMaxElements];
 };
 
 }  // namespace kb

@@ -102,6 +102,42 @@ uint64_t offsets_scan_blocks(uint64_t n_queries);
 void launch_segment_sort(uint32_t *d_positions, uint32_t *d_tmp, const uint64_t *d_offsets, const uint8_t *d_unsorted,
                          uint64_t n_queries, uint32_t key_bits, cudaStream_t stream);
 
+// ---- query routing of the key-range multi-GPU search (route_kernels.cu)
+constexpr int kMaxParts = 64;
+struct RoutePrefix {
+    uint32_t p[kMaxParts + 1];  // p[b] = records in the blocks before block b
+};
+struct RoutePrefix64 {
+    uint64_t p[kMaxParts + 1];
+};
+struct RouteArgs {
+    const uint8_t *q_ranks;     // device: this rank's slice of the batch
+    const uint64_t *q_offsets;  // device, [Q + 1]
+    uint64_t n_queries;
+    uint32_t mode, bits, sigma, k;
+    uint64_t part_width;        // hashes per index part
+    uint32_t n_parts, stride, capacity;
+    uint8_t *blocks;            // device: n_parts send blocks (counts zeroed)
+    uint64_t block_bytes;
+    uint8_t *status;            // device, [Q]: 0xFF = routed (the owner decides), else the status decided here
+    uint32_t *flags;            // device u32: bit 0 = rank >= sigma, bit 1 = a query cannot be routed, bit 2 = a block overflowed
+};
+uint64_t route_block_bytes(uint32_t capacity, uint32_t stride);
+uint64_t route_return_block_bytes(uint32_t capacity);
+void launch_route_pack(const RouteArgs &a, cudaStream_t stream);
+void launch_compact_blocks(uint8_t *d_blocks, uint64_t block_bytes, uint32_t n_parts, uint32_t capacity, uint32_t stride,
+                           const RoutePrefix &pfx, uint64_t *d_words, uint16_t *d_lens, cudaStream_t stream);
+void launch_pack_return(const uint64_t *d_offsets, const uint8_t *d_status, const RoutePrefix &pfx, uint32_t n_parts, uint8_t *d_ret_blocks,
+                        uint64_t ret_bytes, uint32_t capacity, cudaStream_t stream);
+void launch_unroute_counts(uint8_t *d_send_blocks, uint64_t block_bytes, uint32_t stride, uint8_t *d_ret_blocks, uint64_t ret_bytes,
+                           uint32_t capacity, uint32_t n_parts, const RoutePrefix &sent, uint64_t *d_counts, uint8_t *d_status,
+                           cudaStream_t stream);
+void launch_unroute_place(uint8_t *d_send_blocks, uint64_t block_bytes, uint32_t stride, uint8_t *d_ret_blocks, uint64_t ret_bytes,
+                          uint32_t capacity, uint32_t n_parts, const RoutePrefix &sent, const RoutePrefix64 &seg, const uint32_t *d_recv_pos,
+                          const uint64_t *d_offsets, uint32_t *d_positions, cudaStream_t stream);
+// bit h - lo of d_bits_at_lo = the part's directory says hash h occurs (n_keys = hi - lo hashes)
+void launch_presence_bits(const uint32_t *d_dir, uint64_t n_keys, uint64_t *d_bits_at_lo, cudaStream_t stream);
+
 // ---- random-gather calibration (the denominator of the search roofline)
 void launch_gather_probe(const uint64_t *d_table, uint64_t n_words, uint64_t n_gathers, uint64_t *d_sink, cudaStream_t stream);
 

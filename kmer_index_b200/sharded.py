@@ -410,6 +410,95 @@ def assemble_replicated(ix, world: int, rank: int, dist, dev, timing=None):
         ix.adopt_element(e, pos_full, dir_full)
 
 
+# ----------------------------------------------------------------------------------------------------------
+# partitioned index, routed queries: rank r keeps index part r (the k-mers whose hash lies in the r-th slice of the key
+# space) and the whole packed text; a query is answered by the owner of the hash of its first k symbols. Three
+# all-to-all exchanges move queries out and results back; nothing is replicated except a presence bitmap.
+# ----------------------------------------------------------------------------------------------------------
+def share_presence(ix, world: int, rank: int, dist, dev):
+    """Every rank exports the presence bits of its key-range part; the parts are summed (disjoint bits: a sum is an OR)
+    into the whole bitmap, which is attached to the index. Once per index."""
+    import torch
+    for e in range(len(ix.ks)):
+        bits = torch.zeros(ix.presence_words(e), dtype=torch.int64, device=dev)
+        ix.presence_export(e, bits.data_ptr())
+        dist.all_reduce(bits, op=dist.ReduceOp.SUM)   # the parts' words are disjoint (part boundaries are multiples of 64 hashes)
+        ix.presence_attach(e, bits)
+
+
+def search_routed(ix, q_ptr: int, off_ptr: int, Q: int, max_len: int, plan_queries: int, world: int, rank: int, dist, dev,
+                  timing=None):
+    """Routed search of this rank's slice of the batch (Q queries, device-resident) on a partitioned index prepared with
+    share_presence(). plan_queries: the largest slice over all ranks (every rank must pass the same value). Returns the
+    DeviceResult of the slice (offsets / positions / status in batch order)."""
+    import torch
+    slack = 0.0
+    while True:
+        plan = ix.route_plan(plan_queries, max_len, world, slack)
+        send = torch.empty(world * plan.block_bytes, dtype=torch.uint8, device=dev)
+        status = torch.empty(max(Q, 1), dtype=torch.uint8, device=dev)
+        sent = ix.route_queries(q_ptr, off_ptr, Q, plan, send.data_ptr(), status.data_ptr())
+        # a send block that overflowed anywhere makes every rank re-plan with room for the largest block seen
+        need = torch.tensor([max(sent)], dtype=torch.int64, device=dev)
+        dist.all_reduce(need, op=dist.ReduceOp.MAX)
+        need = int(need.item())
+        if need <= plan.capacity:
+            break
+        slack = 1.05 * need * world / max(plan_queries, 1) + 0.05
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send)
+    ret_send = torch.empty(world * plan.return_block_bytes, dtype=torch.uint8, device=dev)
+    ret_recv = torch.empty_like(ret_send)
+    res, pos_splits = ix.search_routed(recv.data_ptr(), plan, ret_send.data_ptr())
+    dist.all_to_all_single(ret_recv, ret_send)
+    recv_splits = [int(x) for x in ret_recv.view(world, plan.return_block_bytes)[:, 8:16].contiguous().view(torch.int64).flatten().cpu()]
+    pos_send = (torch.as_tensor(res.positions(), device=dev) if res.n_positions else torch.empty(0, dtype=torch.int32, device=dev))
+    pos_recv = torch.empty(sum(recv_splits), dtype=torch.int32, device=dev)
+    dist.all_to_all_single(pos_recv, pos_send, output_split_sizes=recv_splits, input_split_sizes=pos_splits)
+    out = ix.unroute(send.data_ptr(), ret_recv.data_ptr(), plan, sent, pos_recv.data_ptr(), recv_splits, Q, status.data_ptr())
+    torch.cuda.current_stream().synchronize()
+    res.free()
+    return out
+
+
+def search_routed_host(ix, h_q, h_off, plan_queries: int, max_len: int, world: int, rank: int, dist, dev):
+    """Routed search of this rank's slice given as pinned host tensors (uint8 ranks, int64 offsets): H2D of the slice,
+    routed search, D2H of the slice's result into pinned memory."""
+    import torch
+    from . import BatchResult
+    Q = h_off.numel() - 1
+    d_q = h_q.to(dev, non_blocking=True)
+    d_off = h_off.to(dev, non_blocking=True)
+    res = search_routed(ix, d_q.data_ptr(), d_off.data_ptr(), Q, max_len, plan_queries, world, rank, dist, dev)
+    h_goff = _pinned("r_offsets", Q + 1, torch.int64)
+    h_status = _pinned("r_status", Q, torch.uint8)
+    h_pos = _pinned("r_positions", res.n_positions, torch.int32)
+    h_goff.copy_(torch.as_tensor(res.offsets(), device=dev), non_blocking=True)
+    h_status.copy_(torch.as_tensor(res.status(), device=dev), non_blocking=True)
+    if res.n_positions:
+        h_pos.copy_(torch.as_tensor(res.positions(), device=dev), non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    res.free()
+    return BatchResult(h_goff.numpy().view(np.uint64), h_pos.numpy().view(np.uint32), h_status.numpy())
+
+
+def fingerprint_of(res, Q: int, dev, first_query_id: int = 0):
+    """fingerprint() of a finished DeviceResult (frees it)."""
+    import torch
+    off = torch.as_tensor(res.offsets(), device=dev)
+    pos = (torch.as_tensor(res.positions(), device=dev).to(torch.int64) & 0xFFFFFFFF if res.n_positions
+           else torch.empty(0, dtype=torch.int64, device=dev))
+    status = torch.as_tensor(res.status(), device=dev)
+    counts = off[1:] - off[:-1]
+    qid = torch.repeat_interleave(torch.arange(first_query_id + 1, first_query_id + Q + 1, device=dev), counts)
+    checksum = int((pos * qid).sum().item()) if pos.numel() else 0
+    hist = torch.bincount(status.to(torch.int64), minlength=4)[:4]
+    out = {"hits": int(off[-1].item()), "checksum": checksum, "status_hist": [int(x) for x in hist.cpu()]}
+    torch.cuda.current_stream().synchronize()
+    res.free()
+    return out
+
+
 def fingerprint(ix, q_ptr: int, off_ptr: int, Q: int, max_len: int, world: int, dev, first_query_id: int = 0):
     """{hits, status histogram, position checksum} of a device-resident batch: sum over all hits of
     position * (global query id + 1) modulo 2^64 -- a property of the result alone, so every N and every multi-GPU

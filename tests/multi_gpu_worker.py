@@ -3,7 +3,9 @@ compared bit for bit with the CPU oracle on rank 0:
   * position-range shards (+ halo), every rank searches the whole batch, presence flags all-reduced, merged CSR
     assembled on rank 0 (kmer_index_b200.sharded.search_merged) -- the real send/recv + add_counts + place path;
   * replicated index: every rank sorts one key-range part, parts all-gathered (sharded.assemble_replicated), every
-    rank answers its slice of the batch.
+    rank answers its slice of the batch;
+  * partitioned index, routed queries (sharded.search_routed): every rank keeps its key-range part, queries travel to
+    the owner of their first k-mer and results travel back.
 Prints one line 'MULTI_GPU_PARITY_OK <world>' from rank 0 on success."""
 import os
 import sys
@@ -90,6 +92,26 @@ def main():
             w_sum = w_sum - (1 << 64) if w_sum >= (1 << 63) else w_sum
             assert fp["hits"] == int(want[0][-1]) == int(t[0]) and fp["checksum"] == w_sum == int(t[1]), (fp, w_sum, t)
             assert fp["status_hist"] == [int(x) for x in t[2:6]] == [int((want[2] == s).sum()) for s in range(4)]
+        # ---- partitioned index, routed queries (single-k indices): three all-to-all exchanges, nothing replicated
+        if len(ks) == 1 and m_lo >= ks[0]:
+            ix = kb.KmerIndex(text, sigma, ks, stream=sptr, device=local, key_part=rank, key_parts=world)
+            sharded.share_presence(ix, world, rank, dist, dev)
+            sl_off = (d_off[lo:hi + 1] - d_off[lo]).contiguous()
+            for attempt in range(2):
+                out = sharded.search_routed(ix, d_q.data_ptr() + int(off[lo]), sl_off.data_ptr(), hi - lo, m_hi, -(-Q // world),
+                                            world, rank, dist, dev)
+                mine = (torch.as_tensor(out.offsets(), device=dev).cpu().numpy().astype(np.uint64),
+                        torch.as_tensor(out.positions(), device=dev).cpu().numpy().view(np.uint32) if out.n_positions
+                        else np.zeros(0, np.uint32), torch.as_tensor(out.status(), device=dev).cpu().numpy())
+                out.free()
+                parts = [None] * world
+                dist.all_gather_object(parts, mine)
+                if rank == 0:
+                    g_off = np.concatenate([[0]] + [np.asarray(p[0][1:], dtype=np.uint64) + np.uint64(sum(int(x[0][-1]) for x in parts[:i]))
+                                                    for i, p in enumerate(parts)]).astype(np.uint64)
+                    got = (g_off, np.concatenate([p[1] for p in parts]), np.concatenate([p[2] for p in parts]))
+                    assert_results_equal(got, want, label=f"routed x{world} {ks} attempt {attempt}")
+            ix.close()
         dist.barrier()
     if rank == 0:
         print(f"MULTI_GPU_PARITY_OK {world}", flush=True)

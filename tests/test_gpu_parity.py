@@ -363,6 +363,99 @@ def test_key_range_parts_assemble_to_the_whole_index(kb, oracle_mod, sigma, ks, 
             ix.close()
 
 
+@pytest.mark.parametrize("sigma,k,n,m_hi,parts,mode", [(4, 16, 500_000, 64, 4, 0), (4, 12, 300_000, 100, 3, 0), (4, 12, 300_000, 60, 8, 1),
+                                                        (15, 8, 200_000, 40, 2, 0), (27, 5, 150_000, 24, 5, 0)])
+def test_routed_search_on_key_range_parts_emulated(kb, oracle_mod, sigma, k, n, m_hi, parts, mode):
+    """The partitioned multi-GPU search, all ranks emulated on one GPU: `parts` indices each hold one key-range part,
+    every "rank" routes its slice of the batch to the owners of the queries' first k-mers (send blocks), owners search
+    what they received and send results back, origins restore batch order. The three all-to-all exchanges are plain
+    tensor copies here. Result must equal the oracle (REFERENCE_EXACT incl. the whole-text presence rules through the
+    shared bitmap; CORRECT against the plain scan)."""
+    import torch
+
+    from kmer_index_b200 import synth
+    dev = torch.device("cuda", 0)
+    text = synth.random_text(n, sigma, 61)
+    text[5000:9000] = np.resize(text[100:100 + k], 4000)      # a periodic stretch: the defective plans become non-empty
+    text[20_000:24_000] = 0                                    # and a long bucket
+    q, off = synth.stress_queries(text, 6000, k, m_hi, sigma, 62)
+    Q = off.size - 1
+    stream = torch.cuda.current_stream().cuda_stream
+    idx = [kb.KmerIndex(text, sigma, [k], key_part=r, key_parts=parts, stream=stream or None, mode=mode) for r in range(parts)]
+    try:
+        if mode == 0:
+            with oracle_mod.Oracle(text, sigma, [k]) as o:
+                want = o.search(q, off)
+        else:
+            want = oracle_mod.Oracle.truth(text, q, off)
+        # presence bitmap: every part exports its slice, the slices are disjoint -> sum == or
+        words = idx[0].presence_words(0)
+        bits = torch.zeros(words, dtype=torch.int64, device=dev)
+        for ix in idx:
+            part = torch.zeros(words, dtype=torch.int64, device=dev)
+            ix.presence_export(0, part.data_ptr())
+            bits += part
+        for ix in idx:
+            ix.presence_attach(0, bits)
+        for attempt in range(2):
+            slack = 0.0 if attempt == 0 else 0.01              # the second round starts with blocks that overflow
+            lo = [r * Q // parts for r in range(parts + 1)]
+            d_q = torch.from_numpy(q).to(dev)
+            d_off = [torch.from_numpy((off[lo[r]:lo[r + 1] + 1] - off[lo[r]]).view(np.int64)).to(dev) for r in range(parts)]
+            q_ptr = [d_q.data_ptr() + int(off[lo[r]]) for r in range(parts)]
+            Ql = [lo[r + 1] - lo[r] for r in range(parts)]
+            plan_q = max(Ql)
+            while True:
+                plan = idx[0].route_plan(plan_q, m_hi, parts, slack)
+                send = [torch.empty(parts * plan.block_bytes, dtype=torch.uint8, device=dev) for _ in range(parts)]
+                status = [torch.empty(max(Ql[r], 1), dtype=torch.uint8, device=dev) for r in range(parts)]
+                sent = [idx[r].route_queries(q_ptr[r], d_off[r].data_ptr(), Ql[r], plan, send[r].data_ptr(), status[r].data_ptr())
+                        for r in range(parts)]
+                need = max(max(s) for s in sent)
+                if need <= plan.capacity:
+                    break
+                assert attempt == 1
+                slack = 1.05 * need * parts / plan_q + 0.05
+            B, RB = plan.block_bytes, plan.return_block_bytes
+            recv = [torch.cat([send[r][o * B:(o + 1) * B] for r in range(parts)]) for o in range(parts)]       # all-to-all
+            ret_send, owner_res, pos_splits = [], [], []
+            for o in range(parts):
+                rs = torch.empty(parts * RB, dtype=torch.uint8, device=dev)
+                res, splits = idx[o].search_routed(recv[o].data_ptr(), plan, rs.data_ptr())
+                ret_send.append(rs)
+                owner_res.append(res)
+                pos_splits.append(splits)
+            torch.cuda.synchronize()
+            got_off, got_pos, got_st = [np.zeros(1, np.uint64)], [], []
+            for r in range(parts):
+                ret_recv = torch.cat([ret_send[o][r * RB:(r + 1) * RB] for o in range(parts)])                # all-to-all
+                recv_splits = [pos_splits[o][r] for o in range(parts)]
+                chunks = []
+                for o in range(parts):
+                    p_o = (torch.as_tensor(owner_res[o].positions(), device=dev) if owner_res[o].n_positions
+                           else torch.empty(0, dtype=torch.int32, device=dev))
+                    a = sum(pos_splits[o][:r])
+                    chunks.append(p_o[a:a + pos_splits[o][r]])
+                pos_recv = torch.cat(chunks) if chunks else torch.empty(0, dtype=torch.int32, device=dev)     # all-to-all-v
+                out = idx[r].unroute(send[r].data_ptr(), ret_recv.data_ptr(), plan, sent[r], pos_recv.data_ptr(), recv_splits, Ql[r],
+                                     status[r].data_ptr())
+                torch.cuda.synchronize()
+                o_ = torch.as_tensor(out.offsets(), device=dev).cpu().numpy().astype(np.uint64)
+                got_off.append(o_[1:] + got_off[-1][-1])
+                got_pos.append(torch.as_tensor(out.positions(), device=dev).cpu().numpy().view(np.uint32) if out.n_positions
+                               else np.zeros(0, np.uint32))
+                got_st.append(torch.as_tensor(out.status(), device=dev).cpu().numpy())
+                out.free()
+            for res in owner_res:
+                res.free()
+            got = (np.concatenate(got_off), np.concatenate(got_pos), np.concatenate(got_st))
+            assert_results_equal(got, want, label=f"routed x{parts} k={k} mode={mode} attempt {attempt}")
+        assert want[1].size > 1000
+    finally:
+        for ix in idx:
+            ix.close()
+
+
 @pytest.mark.parametrize("sigma,ks", [(4, [12]), (4, [5, 7, 9, 11, 13]), (15, [8]), (4, [20])])
 def test_heavy_buckets_take_the_warp_path(kb, oracle_mod, sigma, ks):
     """A text with one enormous bucket (a long constant run): the index-wide average bucket is ~1, so queries get
