@@ -57,7 +57,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--count-only", action="store_true", help="time search without materialising positions")
-    ap.add_argument("--multi", default="routed", choices=["routed", "replicated", "position-range"],
+    ap.add_argument("--multi", default="replicated", choices=["routed", "replicated", "position-range"],
                     help="N > 1: 'routed' = every GPU keeps one key-range part of the index, each GPU routes its 1/N of the "
                          "batch to the owners of the queries' first k-mers and gets the results back (three all-to-alls); "
                          "'replicated' = the parts are all-gathered over NVLink into the whole index on every GPU and each GPU "

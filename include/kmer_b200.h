@@ -113,6 +113,26 @@ int kmer_b200_create_from_text(const char *text, uint64_t n, const uint8_t *lut2
 int kmer_b200_search_batch_text(kmer_b200_index *index, const char *q_chars, const uint64_t *q_offsets,
                                 uint64_t n_queries, const uint8_t *lut256, uint32_t mode, kmer_b200_result **out);
 
+/* FASTA / FASTQ input. The file's bytes are parsed on the device: header lines, line breaks (FASTQ: the
+   '+' and quality lines too) are dropped, sequence characters are translated through lut256 (a character outside the
+   alphabet fails with KMER_B200_ERR_INVALID_RANK), all records are concatenated into one rank text that stays in device
+   memory -- feed it to kmer_b200_create_from_device -- and a record table maps positions back. format: 0 = by the
+   first byte ('>' / ';' FASTA, '@' FASTQ), 1 = FASTA, 2 = FASTQ (four lines per record). */
+typedef struct kmer_b200_records kmer_b200_records;
+int kmer_b200_parse_sequences(const char *data, uint64_t n_bytes, const uint8_t *lut256, uint32_t sigma, uint32_t format,
+                              const kmer_b200_config *cfg, kmer_b200_records **out);
+uint64_t kmer_b200_records_count(const kmer_b200_records *r);
+uint64_t kmer_b200_records_symbols(const kmer_b200_records *r);            /* length of the concatenated text */
+const uint64_t *kmer_b200_records_starts(const kmer_b200_records *r);      /* host, [count + 1]: first symbol of each record */
+const uint64_t *kmer_b200_records_header_offsets(const kmer_b200_records *r); /* host, [count]: byte offset of the record's header
+                                                                              line in `data`; UINT64_MAX for a headerless first record */
+const uint8_t *kmer_b200_records_ranks_device(const kmer_b200_records *r); /* device, [symbols] */
+/* positions (as returned by a search on the concatenated text) -> record index and offset inside it. query_len > 0:
+   a match that runs over the end of its record is not a match of any sequence: record_out = UINT32_MAX for it. */
+int kmer_b200_records_locate(const kmer_b200_records *r, const uint32_t *positions, uint64_t n, uint64_t query_len,
+                             uint32_t *record_out, uint32_t *offset_out);
+void kmer_b200_records_free(kmer_b200_records *r);
+
 void kmer_b200_destroy(kmer_b200_index *index);
 
 /* ---- serialization: construct once, load later (the thesis assumes it, thesis/content/02_implementation.tex:44-46,
@@ -280,6 +300,24 @@ int kmer_b200_element_hashes(kmer_b200_index *index, uint32_t element, uint64_t 
 /* Row m of the scheme table (_optimal_nk_sum[m], _use_multi_search_scheme[m]; kmer_index.hpp:404-476).
    Returns the number of summands and writes up to cap of them. */
 uint64_t kmer_b200_scheme(const kmer_b200_index *index, uint64_t m, uint32_t *out_ks, uint64_t cap, int *use_multi);
+
+/* The plan the search runs for a query of length m: which element seeds the candidate list, how many
+   directory lookups it needs, and -- from the bucket statistics measured on THIS index -- how many candidates and
+   32-byte sectors that costs for a query whose seed k-mer occurs. mode REFERENCE_EXACT follows the reference's table
+   (choose_search_scheme, kmer_index.hpp:407-476) where the result depends on it and otherwise seeds from the largest
+   k <= m like CORRECT does; CORRECT always seeds from the largest k <= m (the shortest buckets) and verifies the rest of
+   the query against the text, which makes every length as cheap as the exact-k lookup plus one text window. */
+typedef struct kmer_b200_plan_row {
+    uint32_t m;
+    uint32_t kind;      /* 0 exact bucket, 1 prefix slab (m < every usable k), 2 contiguous verify, 3 the reference's plan for
+                           >= 3 parts + rest (kmer_index.hpp:314), 4 the reference's multi-k sum plan (:526,535), 5 throws */
+    uint32_t seed_k;    /* k of the element that supplies the candidates */
+    uint32_t n_lookups; /* directory lookups per query */
+    double expected_candidates; /* per query whose seed occurs: mean occupied bucket (or slab) length of the seed element */
+    double expected_sectors;    /* lookups + candidate list + text windows, in 32-byte sectors */
+} kmer_b200_plan_row;
+/* rows for m = m_lo .. m_hi (out has m_hi - m_lo + 1 entries). The first call measures the bucket statistics on the device. */
+int kmer_b200_plan_table(kmer_b200_index *index, uint32_t mode, uint32_t m_lo, uint32_t m_hi, kmer_b200_plan_row *out);
 
 /* The same row computed on the host from the ks alone (no device, no index needed). */
 uint64_t kmer_b200_scheme_for_ks(const uint32_t *ks, uint32_t n_ks, uint64_t m, uint32_t *out_ks, uint64_t cap,

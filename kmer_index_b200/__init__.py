@@ -16,7 +16,7 @@ from . import _capi
 from ._capi import (MODE_CORRECT, MODE_DEFAULT, MODE_REFERENCE_EXACT, QUERY_OK, QUERY_THROW_INVALID_ARGUMENT,
                     QUERY_TOO_LONG_FOR_SHARD, QUERY_UNDEFINED, KmerB200Error)
 
-__all__ = ["KmerIndex", "make_kmer_index", "BatchResult", "fast_pow", "kmer_hash", "choose_best_k", "scheme_for_ks",
+__all__ = ["KmerIndex", "make_kmer_index", "BatchResult", "Records", "parse_sequences", "fast_pow", "kmer_hash", "choose_best_k", "scheme_for_ks",
            "char_lut", "ALPHABET_CHARS",
            "MODE_REFERENCE_EXACT", "MODE_CORRECT", "KmerB200Error", "ALPHABETS"]
 
@@ -110,6 +110,76 @@ class BatchResult:
         return self.offsets, self.positions, self.status
 
 
+class Records:
+    """Sequences parsed from FASTA / FASTQ bytes on the device (kmer_b200_parse_sequences): one concatenated rank text in
+    HBM plus the record table. `index(ks)` builds a KmerIndex over it; `locate` maps hit positions to (record, offset)."""
+
+    def __init__(self, handle, data: bytes, sigma: int):
+        L = _capi.lib()
+        self._L, self._h, self._data, self.sigma = L, handle, data, sigma
+        n = int(L.kmer_b200_records_count(handle))
+        self.n_symbols = int(L.kmer_b200_records_symbols(handle))
+        self.starts = np.ctypeslib.as_array(L.kmer_b200_records_starts(handle), shape=(n + 1,)).copy()
+        self.header_offsets = (np.ctypeslib.as_array(L.kmer_b200_records_header_offsets(handle), shape=(n,)).copy()
+                               if n else np.zeros(0, np.uint64))
+
+    def __len__(self) -> int:
+        return int(self.header_offsets.size)
+
+    def name(self, i: int) -> str:
+        """The header line of record i without its marker ('' for a headerless first record)."""
+        o = int(self.header_offsets[i])
+        if o == 0xFFFFFFFFFFFFFFFF:
+            return ""
+        end = self._data.find(b"\n", o)
+        return self._data[o + 1:end if end >= 0 else len(self._data)].rstrip(b"\r").decode(errors="replace")
+
+    def index(self, ks: Sequence[int], **kw) -> "KmerIndex":
+        return KmerIndex(None, self.sigma, ks, text_device_ptr=int(self._L.kmer_b200_records_ranks_device(self._h)),
+                         n=self.n_symbols, **kw)
+
+    def locate(self, positions, query_len: int = 0):
+        """(record, offset) of each position; record == 0xFFFFFFFF where a match of query_len symbols would run over the
+        end of its record (an artefact of concatenating the records)."""
+        p = np.ascontiguousarray(np.asarray(positions, dtype=np.uint32))
+        rec = np.zeros(p.size, dtype=np.uint32)
+        off = np.zeros(p.size, dtype=np.uint32)
+        _capi.check(self._L.kmer_b200_records_locate(self._h, p.ctypes.data_as(_capi.u32p), p.size, query_len,
+                                                     rec.ctypes.data_as(_capi.u32p), off.ctypes.data_as(_capi.u32p)))
+        return rec, off
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.kmer_b200_records_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def parse_sequences(data, alphabet: str = "dna4", fmt: int = 0, device: int = -1, stream: int | None = None) -> Records:
+    """FASTA / FASTQ bytes -> Records (parsed on the device). fmt: 0 = by the first byte, 1 = FASTA, 2 = FASTQ."""
+    L = _capi.lib()
+    raw = data.encode() if isinstance(data, str) else bytes(data)
+    sigma = ALPHABETS[alphabet]
+    lut = np.ascontiguousarray(char_lut(alphabet))
+    cfg = _capi.Config()
+    L.kmer_b200_config_default(C.byref(cfg))
+    cfg.device, cfg.stream = device, stream
+    h = C.c_void_p()
+    _capi.check(L.kmer_b200_parse_sequences(raw, len(raw), lut.ctypes.data_as(_capi.u8p), sigma, fmt, C.byref(cfg), C.byref(h)))
+    return Records(h, raw, sigma)
+
+
 class _DevArray:
     """Zero-copy view of device memory for torch.as_tensor / cupy via __cuda_array_interface__."""
 
@@ -172,6 +242,7 @@ class KmerIndex:
         cfg.device = device
         cfg.mode = mode
         cfg.stream = stream
+        self.stream = stream          # None: the library made a private stream for this index
         cfg.profile = int(profile)   # 1: per-kernel CUDA-event times; 2: also count gathered sectors per search
         cfg.shard_begin = shard_begin
         cfg.n_total = n_total
@@ -441,6 +512,16 @@ class KmerIndex:
         multi = C.c_int(0)
         n = self._L.kmer_b200_scheme(self._h, m, out.ctypes.data_as(_capi.u32p), out.size, C.byref(multi))
         return [int(x) for x in out[:n]], bool(multi.value)
+
+    PLAN_KINDS = ("exact bucket", "prefix slab", "contiguous verify", "reference :314 plan", "reference multi-k sum plan", "throws")
+
+    def plan_table(self, m_lo: int, m_hi: int, mode: int = MODE_DEFAULT) -> list[dict]:
+        """The plan per query length (kmer_b200_plan_table): kind, seed k, lookups, expected candidates / sectors from
+        the bucket statistics measured on this index."""
+        rows = (_capi.PlanRow * (m_hi - m_lo + 1))()
+        _capi.check(self._L.kmer_b200_plan_table(self._h, mode, m_lo, m_hi, rows))
+        return [{"m": int(r.m), "kind": self.PLAN_KINDS[r.kind], "seed_k": int(r.seed_k), "lookups": int(r.n_lookups),
+                 "candidates": float(r.expected_candidates), "sectors": float(r.expected_sectors)} for r in rows]
 
     def stats(self) -> dict:
         arr = (_capi.KernelStat * 32)()

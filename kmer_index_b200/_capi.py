@@ -45,6 +45,11 @@ class RoutePlan(C.Structure):
                 ("block_bytes", C.c_uint64), ("return_block_bytes", C.c_uint64)]
 
 
+class PlanRow(C.Structure):
+    _fields_ = [("m", C.c_uint32), ("kind", C.c_uint32), ("seed_k", C.c_uint32), ("n_lookups", C.c_uint32),
+                ("expected_candidates", C.c_double), ("expected_sectors", C.c_double)]
+
+
 class KernelStat(C.Structure):
     _fields_ = [("name", C.c_char_p), ("launches", C.c_uint64), ("device_ms", C.c_double),
                 ("algorithmic_bytes", C.c_double)]
@@ -63,6 +68,15 @@ SYMBOLS = {
                                              C.POINTER(Config), C.POINTER(C.c_void_p)]),
     "kmer_b200_search_batch_text": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_uint64, u8p, C.c_uint32,
                                               C.POINTER(C.c_void_p)]),
+    "kmer_b200_parse_sequences": (C.c_int, [C.c_char_p, C.c_uint64, u8p, C.c_uint32, C.c_uint32, C.POINTER(Config),
+                                            C.POINTER(C.c_void_p)]),
+    "kmer_b200_records_count": (C.c_uint64, [C.c_void_p]),
+    "kmer_b200_records_symbols": (C.c_uint64, [C.c_void_p]),
+    "kmer_b200_records_starts": (u64p, [C.c_void_p]),
+    "kmer_b200_records_header_offsets": (u64p, [C.c_void_p]),
+    "kmer_b200_records_ranks_device": (C.c_void_p, [C.c_void_p]),
+    "kmer_b200_records_locate": (C.c_int, [C.c_void_p, u32p, C.c_uint64, C.c_uint64, u32p, u32p]),
+    "kmer_b200_records_free": (None, [C.c_void_p]),
     "kmer_b200_destroy": (None, [C.c_void_p]),
     "kmer_b200_save": (C.c_int, [C.c_void_p, C.c_char_p]),
     "kmer_b200_load": (C.c_int, [C.c_char_p, C.POINTER(Config), C.POINTER(C.c_void_p)]),
@@ -110,6 +124,7 @@ SYMBOLS = {
     "kmer_b200_element_positions": (C.c_int, [C.c_void_p, C.c_uint32, u32p, C.c_uint64]),
     "kmer_b200_element_hashes": (C.c_int, [C.c_void_p, C.c_uint32, u64p, C.c_uint64]),
     "kmer_b200_scheme": (C.c_uint64, [C.c_void_p, C.c_uint64, u32p, C.c_uint64, C.POINTER(C.c_int)]),
+    "kmer_b200_plan_table": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PlanRow)]),
     "kmer_b200_scheme_for_ks": (C.c_uint64, [u32p, C.c_uint32, C.c_uint64, u32p, C.c_uint64, C.POINTER(C.c_int)]),
     "kmer_b200_stats": (C.c_uint32, [C.c_void_p, C.POINTER(KernelStat), C.c_uint32]),
     "kmer_b200_stats_reset": (None, [C.c_void_p]),

@@ -64,7 +64,7 @@ void launch_pack_text(const uint8_t *d_ranks, uint64_t n, uint32_t bits, uint32_
 template <typename KeyT>
 struct TextSource {  // key(i) = hash of the k-mer starting at symbol i; value(i) = i
     using key_type = KeyT;
-    static constexpr bool kAtomicMatch = true;  // see tile_rank: the hash extraction already loads the ALU pipe
+    static constexpr uint32_t kAtomicItems = 0xFFFFu;  // see tile_rank: the hash extraction already loads the ALU pipe
     PackedText text;
     uint32_t k;
     __device__ __forceinline__ KeyT key(uint64_t i) const {
@@ -122,7 +122,7 @@ struct TextSource {  // key(i) = hash of the k-mer starting at symbol i; value(i
 // every key is a Horner walk over two windows, so there is no word sharing between a thread's items to exploit.
 struct WideTextSource {
     using key_type = uint64_t;
-    static constexpr bool kAtomicMatch = true;
+    static constexpr uint32_t kAtomicItems = 0xFFFFu;
     PackedText text;
     uint32_t k;
     __device__ __forceinline__ uint64_t key(uint64_t i) const { return key_at(text.words, i, k, text.bits, text.sigma); }
@@ -143,7 +143,10 @@ struct WideTextSource {
 template <typename KeyT>
 struct PairSource {  // materialised (key, value) pairs
     using key_type = KeyT;
-    static constexpr bool kAtomicMatch = false;
+#ifndef KB_PAIR_ATOMIC_ITEMS
+#define KB_PAIR_ATOMIC_ITEMS 0u  // tuning: which of a thread's 16 items are matched through shared memory in the pair passes
+#endif
+    static constexpr uint32_t kAtomicItems = KB_PAIR_ATOMIC_ITEMS;
     const KeyT *keys;
     const uint32_t *vals;
     __device__ __forceinline__ KeyT key(uint64_t i) const { return keys[i]; }
@@ -405,7 +408,7 @@ __device__ __forceinline__ void scatter_tile(const Source &src, uint64_t tile_be
                                              uint32_t mask, const uint32_t *__restrict__ tile_base_row,
                                              typename Source::key_type *__restrict__ out_keys,
                                              uint32_t *__restrict__ out_vals,
-                                             ScatterSmem<typename Source::key_type, Source::kAtomicMatch> &sm) {
+                                             ScatterSmem<typename Source::key_type, (Source::kAtomicItems != 0)> &sm) {
     using KeyT = typename Source::key_type;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -421,7 +424,7 @@ __device__ __forceinline__ void scatter_tile(const Source &src, uint64_t tile_be
     for (int r = 0; r < kSortItems; ++r) local_pos2[r >> 1] = (r & 1) ? (local_pos2[r >> 1] | ((e0 + r * 32) << 16)) : (e0 + r * 32);
     if (tid < kRadix) sm.delta[tid] = (uint32_t)tile_begin;
 #else
-    tile_rank<BITS, FULL, KeyT, BYTE, Source::kAtomicMatch>(key, count, shift, mask, local_pos2, sm.rank, sm.warp_msk);
+    tile_rank<BITS, FULL, KeyT, BYTE, Source::kAtomicItems>(key, count, shift, mask, local_pos2, sm.rank, sm.warp_msk);
     if (tid < kRadix) sm.delta[tid] = tile_base_row[tid] - sm.rank.excl[tid];
 #endif
     {
@@ -464,7 +467,7 @@ __global__ void __launch_bounds__(kSortThreads, sizeof(typename Source::key_type
                          const uint32_t *__restrict__ tile_base, typename Source::key_type *__restrict__ out_keys,
                          uint32_t *__restrict__ out_vals) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    auto &sm = *reinterpret_cast<ScatterSmem<typename Source::key_type, Source::kAtomicMatch> *>(smem_raw);
+    auto &sm = *reinterpret_cast<ScatterSmem<typename Source::key_type, (Source::kAtomicItems != 0)> *>(smem_raw);
     const uint64_t tile_begin = (uint64_t)blockIdx.x * kSortTile;
     const uint32_t count = (uint32_t)min((uint64_t)kSortTile, n - tile_begin);
     const uint32_t *row = tile_base + (uint64_t)blockIdx.x * kRadix;
@@ -662,7 +665,7 @@ void launch_directory_fill(const void *d_keys, uint32_t key_bytes, uint64_t n_km
 template <typename Source, int BITS, bool BYTE>
 static void launch_scatter_bits(const Source &src, uint64_t n, uint32_t shift, uint32_t mask, const uint32_t *d_tile_base,
                                 typename Source::key_type *d_out_keys, uint32_t *d_out_vals, cudaStream_t stream) {
-    using Smem = ScatterSmem<typename Source::key_type, Source::kAtomicMatch>;
+    using Smem = ScatterSmem<typename Source::key_type, (Source::kAtomicItems != 0)>;
     const uint32_t n_tiles = (uint32_t)((n + kSortTile - 1) / kSortTile);
     // per-device attribute; cheap enough to set on every launch
     cudaFuncSetAttribute(radix_scatter_kernel<Source, BITS, BYTE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));

@@ -151,6 +151,7 @@ struct HostElement {
     uint32_t *d_dir = nullptr, *d_pos = nullptr;
     void *d_keys = nullptr;  // uint32_t or uint64_t hashes (key_bytes); null for a dense directory
     uint32_t key_bytes = 4;
+    uint64_t n_occupied = 0;  // distinct hashes (non-empty buckets), measured on first use by kmer_b200_plan_table
     int adopted = 0;         // 1: pos / dir belong to the caller (kmer_b200_adopt_element); 2: assembled by the library, owned
 };
 
@@ -2212,6 +2213,149 @@ int kmer_b200_adopt_element(kmer_b200_index *ix, uint32_t e, const uint32_t *d_p
     return adopt_element_impl(ix, e, d_positions, n_kmers, d_directory, directory_entries, 1);
 }
 
+// ---- FASTA / FASTQ parsing (fastx_kernels.cu) ---------------------------------------------------------------------
+struct kmer_b200_records {
+    int device = 0;
+    uint8_t *d_ranks = nullptr;
+    uint64_t n_symbols = 0;
+    std::vector<uint64_t> starts;          // [count + 1]
+    std::vector<uint64_t> header_offsets;  // [count]
+};
+
+int kmer_b200_parse_sequences(const char *data, uint64_t n_bytes, const uint8_t *lut256, uint32_t sigma, uint32_t format,
+                              const kmer_b200_config *cfg, kmer_b200_records **out) {
+    if (!data || !lut256 || !out || format > 2 || sigma < 2 || sigma > 256) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad argument");
+    *out = nullptr;
+    if (n_bytes == 0) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "empty input");
+    if (format == 0) format = data[0] == '@' ? 2 : 1;
+    int device = cfg ? cfg->device : -1;
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(KMER_B200_ERR_CUDA, "no usable CUDA device (libkmer_b200 has no CPU fallback)");
+    }
+    DeviceGuard guard(device);
+    cudaStream_t st = cfg && cfg->stream ? (cudaStream_t)cfg->stream : nullptr;
+    const uint64_t tiles = kb::fastx_tiles(n_bytes);
+    uint8_t *d_data = nullptr, *d_lut = nullptr, *d_ranks = nullptr;
+    uint64_t *d_nl = nullptr, *d_kept = nullptr, *d_recs = nullptr, *d_sums = nullptr, *d_rec_sym = nullptr, *d_rec_hdr = nullptr;
+    int64_t *d_last = nullptr;
+    uint32_t *d_err = nullptr;
+    auto release = [&](int code) {
+        cudaFreeAsync(d_data, st);
+        cudaFreeAsync(d_lut, st);
+        cudaFreeAsync(d_nl, st);
+        cudaFreeAsync(d_kept, st);
+        cudaFreeAsync(d_recs, st);
+        cudaFreeAsync(d_sums, st);
+        cudaFreeAsync(d_rec_sym, st);
+        cudaFreeAsync(d_rec_hdr, st);
+        cudaFreeAsync(d_last, st);
+        cudaFreeAsync(d_err, st);
+        if (code != 0) cudaFreeAsync(d_ranks, st);
+        cudaStreamSynchronize(st);
+        cudaGetLastError();
+        return code;
+    };
+#define KB_FX(expr)                                                                                                        \
+    do {                                                                                                                   \
+        cudaError_t _e = (expr);                                                                                           \
+        if (_e != cudaSuccess) {                                                                                           \
+            cudaGetLastError();                                                                                            \
+            return release(fail(_e == cudaErrorMemoryAllocation ? KMER_B200_ERR_OUT_OF_MEMORY : KMER_B200_ERR_CUDA,        \
+                                std::string(#expr) + ": " + cudaGetErrorString(_e)));                                      \
+        }                                                                                                                  \
+    } while (0)
+    KB_FX(cudaMallocAsync((void **)&d_data, n_bytes, st));
+    KB_FX(cudaMallocAsync((void **)&d_lut, 256, st));
+    KB_FX(cudaMallocAsync((void **)&d_nl, (tiles + 1) * 8, st));
+    KB_FX(cudaMallocAsync((void **)&d_kept, (tiles + 1) * 8, st));
+    KB_FX(cudaMallocAsync((void **)&d_recs, (tiles + 1) * 8, st));
+    KB_FX(cudaMallocAsync((void **)&d_sums, (kb::offsets_scan_blocks(tiles) + 1) * 8, st));
+    KB_FX(cudaMallocAsync((void **)&d_last, tiles * 8, st));
+    KB_FX(cudaMallocAsync((void **)&d_err, 4, st));
+    KB_FX(cudaMemcpyAsync(d_data, data, n_bytes, cudaMemcpyHostToDevice, st));
+    KB_FX(cudaMemcpyAsync(d_lut, lut256, 256, cudaMemcpyHostToDevice, st));
+    KB_FX(cudaMemsetAsync(d_err, 0, 4, st));
+    kb::launch_fastx_tile_stats(d_data, n_bytes, d_nl, d_last, st);
+    kb::launch_offsets_scan(d_nl, tiles, d_sums, st);  // -> line feeds before each tile
+    kb::launch_fastx_count(d_data, n_bytes, format, d_nl, d_last, d_kept, d_recs, st);
+    kb::launch_offsets_scan(d_kept, tiles, d_sums, st);
+    kb::launch_offsets_scan(d_recs, tiles, d_sums, st);
+    uint64_t totals[2] = {0, 0};
+    KB_FX(cudaMemcpyAsync(&totals[0], d_kept + tiles, 8, cudaMemcpyDeviceToHost, st));
+    KB_FX(cudaMemcpyAsync(&totals[1], d_recs + tiles, 8, cudaMemcpyDeviceToHost, st));
+    KB_FX(cudaStreamSynchronize(st));
+    const uint64_t n_sym = totals[0], n_rec = totals[1];
+    KB_FX(cudaMallocAsync((void **)&d_ranks, std::max<uint64_t>(n_sym, 1), st));
+    KB_FX(cudaMallocAsync((void **)&d_rec_sym, std::max<uint64_t>(n_rec, 1) * 8, st));
+    KB_FX(cudaMallocAsync((void **)&d_rec_hdr, std::max<uint64_t>(n_rec, 1) * 8, st));
+    kb::launch_fastx_write(d_data, n_bytes, format, d_nl, d_last, d_kept, d_recs, d_lut, sigma, d_ranks, d_rec_sym, d_rec_hdr, d_err, st);
+    kmer_b200_records *r = new (std::nothrow) kmer_b200_records();
+    if (!r) return release(fail(KMER_B200_ERR_OUT_OF_MEMORY, "host allocation failed"));
+    std::vector<uint64_t> sym(n_rec), hdr(n_rec);
+    uint32_t err = 0;
+    cudaError_t e = cudaSuccess;
+    if (n_rec) {
+        e = cudaMemcpyAsync(sym.data(), d_rec_sym, n_rec * 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hdr.data(), d_rec_hdr, n_rec * 8, cudaMemcpyDeviceToHost, st);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess || (err & 1u)) {
+        delete r;
+        return release(e != cudaSuccess ? fail(KMER_B200_ERR_CUDA, std::string("parse_sequences: ") + cudaGetErrorString(e))
+                                        : fail(KMER_B200_ERR_INVALID_RANK, "a sequence character is not in the alphabet"));
+    }
+    r->device = device;
+    r->d_ranks = d_ranks;
+    r->n_symbols = n_sym;
+    if (n_rec == 0 || sym[0] > 0) {  // sequence before the first header line: an unnamed first record
+        r->starts.push_back(0);
+        r->header_offsets.push_back(UINT64_MAX);
+    }
+    for (uint64_t i = 0; i < n_rec; ++i) {
+        r->starts.push_back(sym[i]);
+        r->header_offsets.push_back(hdr[i]);
+    }
+    r->starts.push_back(n_sym);
+    *out = r;
+    return release(0);
+#undef KB_FX
+}
+
+uint64_t kmer_b200_records_count(const kmer_b200_records *r) { return r ? r->header_offsets.size() : 0; }
+uint64_t kmer_b200_records_symbols(const kmer_b200_records *r) { return r ? r->n_symbols : 0; }
+const uint64_t *kmer_b200_records_starts(const kmer_b200_records *r) { return r ? r->starts.data() : nullptr; }
+const uint64_t *kmer_b200_records_header_offsets(const kmer_b200_records *r) { return r ? r->header_offsets.data() : nullptr; }
+const uint8_t *kmer_b200_records_ranks_device(const kmer_b200_records *r) { return r ? r->d_ranks : nullptr; }
+
+int kmer_b200_records_locate(const kmer_b200_records *r, const uint32_t *positions, uint64_t n, uint64_t query_len,
+                             uint32_t *record_out, uint32_t *offset_out) {
+    if (!r || (n && (!positions || !record_out || !offset_out))) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
+    const std::vector<uint64_t> &s = r->starts;
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t p = positions[i];
+        const size_t rec = (size_t)(std::upper_bound(s.begin(), s.end(), p) - s.begin()) - 1;
+        if (rec + 1 >= s.size()) {
+            record_out[i] = UINT32_MAX;
+            offset_out[i] = 0;
+            continue;
+        }
+        record_out[i] = (query_len && p + query_len > s[rec + 1]) ? UINT32_MAX : (uint32_t)rec;
+        offset_out[i] = (uint32_t)(p - s[rec]);
+    }
+    return KMER_B200_OK;
+}
+
+void kmer_b200_records_free(kmer_b200_records *r) {
+    if (!r) return;
+    DeviceGuard guard(r->device);
+    cudaFree(r->d_ranks);
+    cudaGetLastError();
+    delete r;
+}
+
 // ---- key-range multi-GPU search: routing (route_kernels.cu) -----------------------------------------------------------
 static int routable(const kmer_b200_index *ix) {
     if (!ix) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null index");
@@ -2633,6 +2777,126 @@ uint64_t kmer_b200_scheme(const kmer_b200_index *ix, uint64_t m, uint32_t *out_k
     for (uint32_t i = 0; i < len && i < cap && out_ks; ++i) out_ks[i] = ix->ks[ix->sum_elem[o + i]];
     if (use_multi) *use_multi = ix->use_multi[m];
     return len;
+}
+
+// non-empty buckets of an element: dense directory -> entries that differ from their successor; else run starts of the hashes
+template <typename T>
+__global__ void __launch_bounds__(256) count_steps_kernel(const T *__restrict__ v, uint64_t n, unsigned long long *out) {
+    // number of i in [0, n) with v[i + 1] != v[i]
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t c = 0;
+    for (; i < n; i += (uint64_t)gridDim.x * blockDim.x) c += v[i + 1] != v[i];
+    c = __reduce_add_sync(0xFFFFFFFFu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
+
+static int element_occupancy(kmer_b200_index *ix, HostElement &he) {
+    if (he.n_occupied || he.dev.n_kmers == 0) return 0;
+    unsigned long long *d_cnt = nullptr;
+    KB_TRY(dev_alloc(ix, &d_cnt, 1, false));
+    cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), ix->stream);
+    const unsigned grid = kb::device_sm_count() * 16;
+    if (he.dev.shift == 0)
+        count_steps_kernel<<<grid, 256, 0, ix->stream>>>(he.d_dir, he.dev.dir_entries - 1, d_cnt);
+    else if (he.key_bytes == 8)
+        count_steps_kernel<<<grid, 256, 0, ix->stream>>>((const uint64_t *)he.d_keys, he.dev.n_kmers - 1, d_cnt);
+    else
+        count_steps_kernel<<<grid, 256, 0, ix->stream>>>((const uint32_t *)he.d_keys, he.dev.n_kmers - 1, d_cnt);
+    unsigned long long c = 0;
+    KB_CUDA(cudaMemcpyAsync(&c, d_cnt, sizeof(c), cudaMemcpyDeviceToHost, ix->stream));
+    KB_CUDA(cudaStreamSynchronize(ix->stream));
+    dev_free(ix, d_cnt);
+    he.n_occupied = he.dev.shift == 0 ? c : c + 1;  // run starts = steps + 1
+    return 0;
+}
+
+int kmer_b200_plan_table(kmer_b200_index *ix, uint32_t mode, uint32_t m_lo, uint32_t m_hi, kmer_b200_plan_row *out) {
+    ix = primary(ix);
+    if (!ix || !out || m_lo == 0 || m_hi < m_lo) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad argument");
+    if (mode == UINT32_MAX) mode = ix->cfg.mode;
+    DeviceGuard guard(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    const uint32_t n_ks = (uint32_t)ix->ks.size();
+    for (uint32_t e = 0; e < n_ks; ++e) KB_TRY(element_occupancy(ix, ix->elems[e]));
+    auto mean_bucket = [&](uint32_t e) {
+        const HostElement &he = ix->elems[e];
+        return he.n_occupied ? (double)he.dev.n_kmers / (double)he.n_occupied : 0.0;
+    };
+    auto largest_k_at_most = [&](uint32_t m, uint32_t *e_out) {  // element with the largest k <= m
+        bool found = false;
+        for (uint32_t e = 0; e < n_ks; ++e)
+            if (ix->ks[e] <= m && (!found || ix->ks[e] > ix->ks[*e_out])) {
+                *e_out = e;
+                found = true;
+            }
+        return found;
+    };
+    const double sym_per_sector = 256.0 / ix->bits;
+    for (uint32_t m = m_lo; m <= m_hi; ++m) {
+        kmer_b200_plan_row &r = out[m - m_lo];
+        r = kmer_b200_plan_row{};
+        r.m = m;
+        uint32_t e0 = 0, k0 = 0;
+        bool throws = false, defective = false, multi_sum = false, sub_k = false;
+        uint32_t n_lookups = 1;
+        if (mode == KMER_B200_MODE_CORRECT) {
+            if (!largest_k_at_most(m, &e0)) {  // shorter than every k: the smallest k's prefix slab
+                for (uint32_t e = 1; e < n_ks; ++e)
+                    if (ix->ks[e] < ix->ks[e0]) e0 = e;
+                sub_k = true;
+            }
+            k0 = ix->ks[e0];
+        } else {
+            if (m >= kb::kQuerySizeRange) {
+                r.kind = 5;
+                continue;
+            }
+            const uint32_t so = ix->sum_off[m], sl = ix->sum_off[m + 1] - so;
+            e0 = ix->sum_elem[so];
+            k0 = ix->ks[e0];
+            const bool multi = ix->use_multi[m] && n_ks > 1;
+            if (!multi) {
+                if (m < k0) {
+                    sub_k = true;
+                    throws = std::pow((double)ix->sigma, (double)(k0 - m)) > 1e7;  // kmer_index.hpp:119-122
+                } else if (m > k0) {
+                    const uint32_t P = m / k0, rest = m % k0;
+                    const bool throw_after = rest > 0 && std::pow((double)ix->sigma, (double)(k0 - rest)) > 1e7;
+                    defective = rest != 0 && P > 2;
+                    if (throw_after) throws = true;  // once every full part occurs somewhere
+                    if (throw_after || defective) n_lookups = P;
+                }
+            } else if (sl >= 3) {
+                multi_sum = true;
+                n_lookups = sl;
+            }
+            // contiguous plans give the same occurrences from any element: the largest k <= m has the shortest buckets
+            if (!sub_k && !defective && !multi_sum) {
+                uint32_t e = e0;
+                if (largest_k_at_most(m, &e)) e0 = e, k0 = ix->ks[e];
+            }
+        }
+        r.seed_k = k0;
+        r.n_lookups = n_lookups;
+        if (throws && (sub_k || n_lookups == 1)) {
+            r.kind = 5;
+            r.expected_sectors = n_lookups;
+            continue;
+        }
+        if (sub_k) {
+            r.kind = 1;
+            r.expected_candidates = (double)ix->elems[e0].dev.n_kmers / std::pow((double)ix->sigma, (double)m);
+            r.n_lookups = 2;
+            r.expected_sectors = 2 + r.expected_candidates / 8.0;
+            continue;
+        }
+        r.kind = throws ? 5 : (m == k0 ? 0 : (defective ? 3 : (multi_sum ? 4 : 2)));
+        r.expected_candidates = mean_bucket(e0);
+        const double verify = m == k0 ? 0.0 : 1.0 + std::floor((double)m / sym_per_sector);
+        r.expected_sectors = n_lookups * (ix->elems[e0].dev.shift ? 2.0 : 1.0) + std::ceil(r.expected_candidates / 8.0) +
+                             r.expected_candidates * verify;
+    }
+    return KMER_B200_OK;
 }
 
 uint64_t kmer_b200_scheme_for_ks(const uint32_t *ks, uint32_t n_ks, uint64_t m, uint32_t *out_ks, uint64_t cap,

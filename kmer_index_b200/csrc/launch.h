@@ -138,6 +138,16 @@ void launch_unroute_place(uint8_t *d_send_blocks, uint64_t block_bytes, uint32_t
 // bit h - lo of d_bits_at_lo = the part's directory says hash h occurs (n_keys = hi - lo hashes)
 void launch_presence_bits(const uint32_t *d_dir, uint64_t n_keys, uint64_t *d_bits_at_lo, cudaStream_t stream);
 
+// ---- FASTA / FASTQ parsing on the device (fastx_kernels.cu)
+uint64_t fastx_tiles(uint64_t n_bytes);
+// d_nl_count[tiles] (u64): line feeds per tile; d_last_nl[tiles]: position of the last line feed before each tile (-1: none)
+void launch_fastx_tile_stats(const uint8_t *d_data, uint64_t n, uint64_t *d_nl_count, int64_t *d_last_nl, cudaStream_t stream);
+void launch_fastx_count(const uint8_t *d_data, uint64_t n, uint32_t format, const uint64_t *d_nl_before, const int64_t *d_last_nl,
+                        uint64_t *d_kept, uint64_t *d_recs, cudaStream_t stream);
+void launch_fastx_write(const uint8_t *d_data, uint64_t n, uint32_t format, const uint64_t *d_nl_before, const int64_t *d_last_nl,
+                        const uint64_t *d_kept_off, const uint64_t *d_recs_off, const uint8_t *d_lut, uint32_t sigma, uint8_t *d_ranks,
+                        uint64_t *d_rec_start_symbol, uint64_t *d_rec_header_byte, uint32_t *d_error_flag, cudaStream_t stream);
+
 // ---- random-gather calibration (the denominator of the search roofline)
 void launch_gather_probe(const uint64_t *d_table, uint64_t n_words, uint64_t n_gathers, uint64_t *d_sink, cudaStream_t stream);
 

@@ -536,6 +536,9 @@ __global__ void __launch_bounds__(kFilterThreads) owned_count_kernel(PackedText 
 __global__ void __launch_bounds__(kFilterThreads) owned_write_kernel(PackedText text, uint32_t k, uint64_t n_kmers, uint64_t lo,
                                                                       uint64_t hi, const uint64_t *__restrict__ tile_offsets,
                                                                       uint32_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals) {
+    // the tile's owned pairs are compacted in shared memory (position order) and leave as two coalesced streams
+    extern __shared__ uint32_t s_stage[];  // keys[kFilterTile], vals[kFilterTile]
+    uint32_t *s_keys = s_stage, *s_vals = s_stage + kFilterTile;
     __shared__ uint32_t warp_sums[kFilterThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t keys[kFilterItems];
@@ -550,16 +553,25 @@ __global__ void __launch_bounds__(kFilterThreads) owned_write_kernel(PackedText 
     }
     if (lane == 31) warp_sums[warp] = incl;
     __syncthreads();
-    uint32_t before = incl - c;
-    for (int w = 0; w < warp; ++w) before += warp_sums[w];
-    uint64_t o = tile_offsets[blockIdx.x] + before;
+    uint32_t before = incl - c, total = 0;
+#pragma unroll
+    for (int w = 0; w < kFilterThreads / 32; ++w) {
+        if (w < warp) before += warp_sums[w];
+        total += warp_sums[w];
+    }
 #pragma unroll
     for (int j = 0; j < kFilterItems; ++j)
         if ((m >> j) & 1u) {
-            out_keys[o] = keys[j];
-            out_vals[o] = (uint32_t)(i0 + j);
-            ++o;
+            s_keys[before] = keys[j];
+            s_vals[before] = (uint32_t)(i0 + j);
+            ++before;
         }
+    __syncthreads();
+    const uint64_t base = tile_offsets[blockIdx.x];
+    for (uint32_t i = tid; i < total; i += kFilterThreads) {
+        out_keys[base + i] = s_keys[i];
+        out_vals[base + i] = s_vals[i];
+    }
 }
 
 // ghist[p][v] over a pair array (all passes in one sweep)
@@ -624,8 +636,10 @@ void launch_owned_count(const PackedText &text, uint32_t k, uint64_t n_kmers, ui
 
 void launch_owned_write(const PackedText &text, uint32_t k, uint64_t n_kmers, uint64_t lo, uint64_t hi, const uint64_t *d_tile_offsets,
                         uint32_t *d_out_keys, uint32_t *d_out_vals, cudaStream_t stream) {
-    owned_write_kernel<<<filter_tiles(n_kmers), kFilterThreads, 0, stream>>>(text, k, n_kmers, lo, hi, d_tile_offsets, d_out_keys,
-                                                                            d_out_vals);
+    const size_t smem = 2 * kFilterTile * sizeof(uint32_t);
+    cudaFuncSetAttribute(owned_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    owned_write_kernel<<<filter_tiles(n_kmers), kFilterThreads, smem, stream>>>(text, k, n_kmers, lo, hi, d_tile_offsets, d_out_keys,
+                                                                               d_out_vals);
 }
 
 void launch_digit_histograms_pairs(const uint2 *d_pairs, uint64_t n, uint32_t n_passes, uint32_t w_bits, uint32_t *d_hist_scratch,

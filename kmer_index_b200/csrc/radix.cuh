@@ -73,7 +73,7 @@ __device__ __forceinline__ uint32_t digit_of(KeyT key, uint32_t shift, uint32_t 
 //                     kernel inside its 64-register budget without spilling,
 //   sm.count[d]  = number of items with digit d, sm.excl[d] = exclusive prefix of count.
 // All kSortThreads threads must call. Ends with a __syncthreads().
-template <int BITS, bool FULL, typename KeyT, bool BYTE = false, bool ATOMIC_MATCH = false>
+template <int BITS, bool FULL, typename KeyT, bool BYTE = false, uint32_t ATOMIC_ITEMS = 0>
 __device__ __forceinline__ void tile_rank(const KeyT (&key)[kSortItems], uint32_t count, uint32_t shift,
                                           uint32_t mask, uint32_t (&local_pos2)[kSortItems / 2], RankSmem &sm,
                                           uint32_t (*warp_msk)[kRadix] = nullptr) {
@@ -84,6 +84,9 @@ __device__ __forceinline__ void tile_rank(const KeyT (&key)[kSortItems], uint32_
     const uint32_t e0 = (uint32_t)(warp * kSortItems * 32 + lane);
     uint32_t *my_cnt = sm.warp_cnt[warp];
 
+  // ATOMIC_ITEMS: bit r set = item r is matched through shared memory (below), clear = by votes (match_digit)
+  constexpr bool ATOMIC_MATCH = (ATOMIC_ITEMS & 0xFFFFu) == 0xFFFFu;
+  constexpr bool HYBRID_MATCH = ATOMIC_ITEMS != 0 && !ATOMIC_MATCH;
   if constexpr (ATOMIC_MATCH) {
     // The scatter passes are bound by instruction issue (ALU pipe), not by memory: the vote-based match costs 3 ALU
     // instructions per digit bit and item. Here the match runs on the shared-memory pipe instead: every lane ORs its
@@ -121,6 +124,64 @@ __device__ __forceinline__ void tile_rank(const KeyT (&key)[kSortItems], uint32_
             local_pos2[r >> 1] |= pos << 16;
         else
             local_pos2[r >> 1] = pos;
+    }
+  } else if constexpr (HYBRID_MATCH) {
+    // some items by votes (ALU pipe), the others through shared memory (LSU pipe): both pipes work
+    uint32_t *my_msk = warp_msk[warp];
+#pragma unroll
+    for (int i = 0; i < kRadix / 32; ++i) {
+        my_cnt[i * 32 + lane] = 0;
+        my_msk[i * 32 + lane] = 0;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        if ((ATOMIC_ITEMS >> r) & 1u) continue;
+        const uint32_t d = digit_of<BYTE>(key[r], shift, mask);
+        const bool valid = FULL || e0 + r * 32 < count;
+        const uint32_t peers = match_digit<BITS>(d, FULL ? 0xFFFFFFFFu : __ballot_sync(0xFFFFFFFFu, valid));
+        const uint32_t info = (uint32_t)__popc(peers & lt_mask) | ((uint32_t)__popc(peers) << 5) | ((valid ? 1u : 0u) << 11);
+        if (r & 1)
+            local_pos2[r >> 1] = (local_pos2[r >> 1] & 0xFFFFu) | (info << 16);
+        else
+            local_pos2[r >> 1] = (local_pos2[r >> 1] & 0xFFFF0000u) | info;
+    }
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const uint32_t d = digit_of<BYTE>(key[r], shift, mask);
+        uint32_t pos;
+        if ((ATOMIC_ITEMS >> r) & 1u) {
+            const bool valid = FULL || e0 + r * 32 < count;
+            if (valid) atomicOr(&my_msk[d], 1u << lane);
+            __syncwarp();
+            uint32_t peers = 0, pre = 0;
+            if (valid) {
+                peers = my_msk[d];
+                pre = my_cnt[d];
+            }
+            __syncwarp();
+            const uint32_t below = (uint32_t)__popc(peers & lt_mask);
+            if (valid && below == 0) {
+                my_cnt[d] = pre + (uint32_t)__popc(peers);
+                my_msk[d] = 0;
+            }
+            __syncwarp();
+            pos = pre + below;
+        } else {
+            const uint32_t info = (local_pos2[r >> 1] >> (16 * (r & 1))) & 0xFFFFu;
+            const bool valid = FULL || ((info >> 11) & 1u);
+            const uint32_t below = info & 31u;
+            uint32_t pre = 0;
+            if (valid) pre = my_cnt[d];
+            __syncwarp();
+            if (valid && below == 0) my_cnt[d] = pre + ((info >> 5) & 63u);
+            __syncwarp();
+            pos = pre + below;
+        }
+        if (r & 1)
+            local_pos2[r >> 1] = (local_pos2[r >> 1] & 0xFFFFu) | (pos << 16);
+        else
+            local_pos2[r >> 1] = (local_pos2[r >> 1] & 0xFFFF0000u) | pos;
     }
   } else {
     for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) (&sm.warp_cnt[0][0])[i] = 0;

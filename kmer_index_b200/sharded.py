@@ -29,6 +29,17 @@ class Shard:
     halo: int      # symbols borrowed from the next shard (0 on the last shard)
 
 
+def _same_stream(ix):
+    """The multi-GPU paths interleave library launches (on the index's stream) with torch / NCCL work (on torch's current
+    stream) without further synchronisation: both must be the SAME stream. Create the index with
+    stream=torch.cuda.current_stream().cuda_stream from inside a `with torch.cuda.stream(s)` / after set_stream(s)."""
+    import torch
+    cur = torch.cuda.current_stream().cuda_stream
+    if getattr(ix, "stream", None) != cur or not cur:
+        raise ValueError("multi-GPU search: the index must be created on torch's current (non-default) CUDA stream "
+                         f"(index stream {getattr(ix, 'stream', None)}, current stream {cur})")
+
+
 def shard_range(n: int, world: int, rank: int, halo: int) -> Shard:
     """Position-range partition of a text of n symbols; the halo is clipped at the end of the text."""
     per = -(-n // world)
@@ -247,6 +258,7 @@ def search_merged(ix, q_ptr: int, off_ptr: int, Q: int, max_len: int, world: int
     (kmer_b200_search_sharded_add_counts), so its scan yields the merged offsets, its write pass lands its own hits
     in place, and only the other shards' lists are copied. Otherwise (or when the batch needs the segment sort):
     every shard finishes on its own and rank 0 merges the finished CSRs."""
+    _same_stream(ix)
     import torch
     import torch.distributed as dist
     from . import KmerB200Error
@@ -370,6 +382,7 @@ def assemble_replicated(ix, world: int, rank: int, dist, dev, timing=None):
     """`ix` was built with key_part=rank, key_parts=world on the torch current stream: all-gather every element's
     part (positions behind the earlier parts' positions, directory entries offset by the earlier parts' k-mer counts)
     and hand the whole arrays to the index (kmer_b200_adopt_element). Afterwards ix is a complete, replicated index."""
+    _same_stream(ix)
     import torch
     for e, k in enumerate(ix.ks):
         part = ix.element_part(e)
@@ -392,21 +405,25 @@ def assemble_replicated(ix, world: int, rank: int, dist, dev, timing=None):
         last = rank == world - 1
         n_dir = his[rank] - los[rank] + (1 if last else 0)
         ix.export_directory(e, bases[rank], n_dir, dir_full.data_ptr() + 4 * los[rank])
-        widths = {his[r] - los[r] for r in range(world)}
-        if len(widths) == 1 and his[-1] == key_space and los[0] == 0:
-            width = his[0] - los[0]
-            mine = dir_full[los[rank]:los[rank] + width].clone()
-            dist.all_gather_into_tensor(dir_full[:key_space], mine)
-            if not last:
-                dir_full[key_space:].fill_(n_kmers - (1 << 32) if n_kmers >= (1 << 31) else n_kmers)   # uint32 bit pattern
-        else:
-            for r in range(world):
-                hi_r = his[r] + (1 if r == world - 1 else 0)
-                if hi_r > los[r]:
-                    dist.broadcast(dir_full[los[r]:hi_r], src=r)
+        # exchange: every rank pushes its two slices to every other rank and receives theirs, ALL pairs in one NCCL group
+        # (point-to-point all-gather-v: the slices differ in size, and a single group keeps every NVLink direction busy --
+        # a sequence of broadcasts, one root at a time, reached 290 GB/s on two GPUs, this form about twice that)
+        ops = []
         for r in range(world):
+            if r == rank:
+                continue
+            hi_r = his[r] + (1 if r == world - 1 else 0)
+            if n_dir:
+                ops.append(dist.P2POp(dist.isend, dir_full[los[rank]:los[rank] + n_dir], r))
+            if hi_r > los[r]:
+                ops.append(dist.P2POp(dist.irecv, dir_full[los[r]:hi_r], r))
+            if counts[rank]:
+                ops.append(dist.P2POp(dist.isend, pos_full[bases[rank]:bases[rank] + counts[rank]], r))
             if counts[r]:
-                dist.broadcast(pos_full[bases[r]:bases[r] + counts[r]], src=r)
+                ops.append(dist.P2POp(dist.irecv, pos_full[bases[r]:bases[r] + counts[r]], r))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
         ix.adopt_element(e, pos_full, dir_full)
 
 
@@ -418,6 +435,7 @@ def assemble_replicated(ix, world: int, rank: int, dist, dev, timing=None):
 def share_presence(ix, world: int, rank: int, dist, dev):
     """Every rank exports the presence bits of its key-range part; the parts are summed (disjoint bits: a sum is an OR)
     into the whole bitmap, which is attached to the index. Once per index."""
+    _same_stream(ix)
     import torch
     for e in range(len(ix.ks)):
         bits = torch.zeros(ix.presence_words(e), dtype=torch.int64, device=dev)
@@ -431,6 +449,7 @@ def search_routed(ix, q_ptr: int, off_ptr: int, Q: int, max_len: int, plan_queri
     """Routed search of this rank's slice of the batch (Q queries, device-resident) on a partitioned index prepared with
     share_presence(). plan_queries: the largest slice over all ranks (every rank must pass the same value). Returns the
     DeviceResult of the slice (offsets / positions / status in batch order)."""
+    _same_stream(ix)
     import torch
     slack = 0.0
     while True:

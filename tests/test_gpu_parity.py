@@ -393,8 +393,11 @@ def test_routed_search_on_key_range_parts_emulated(kb, oracle_mod, sigma, k, n, 
         bits = torch.zeros(words, dtype=torch.int64, device=dev)
         for ix in idx:
             part = torch.zeros(words, dtype=torch.int64, device=dev)
-            ix.presence_export(0, part.data_ptr())
+            torch.cuda.synchronize()
+            ix.presence_export(0, part.data_ptr())      # enqueued on the index's own stream
+            torch.cuda.synchronize()
             bits += part
+        torch.cuda.synchronize()
         for ix in idx:
             ix.presence_attach(0, bits)
         for attempt in range(2):
@@ -576,3 +579,70 @@ def test_sparse_directory_and_accounting_variants(kb, oracle_mod, directory_bits
         assert ix.last_search_gathers > 0
         st = ix.stats()
         assert st["search_count"]["launches"] >= 1 and st["search_count"]["device_ms"] > 0
+
+
+def _fasta(records, width, crlf=False, comments=False):
+    nl = b"\r\n" if crlf else b"\n"
+    out = []
+    for name, seq in records:
+        out.append(b">" + name + nl)
+        if comments:
+            out.append(b";a comment line" + nl)
+        for i in range(0, len(seq), width):
+            out.append(seq[i:i + width] + nl)
+    return b"".join(out)
+
+
+@pytest.mark.parametrize("variant", ["fasta", "fasta-crlf-comments", "fasta-no-final-newline", "fasta-headerless-start", "fastq"])
+def test_fasta_fastq_parsed_on_the_device(kb, variant):
+    """Multi-record FASTA / FASTQ bytes -> concatenated ranks + record table (device parser) == a plain Python parser;
+    an index over the records finds every planted window in its record, and matches that span a record boundary are
+    recognisable."""
+    from kmer_index_b200 import synth
+    chars = np.frombuffer(b"ACGT", dtype=np.uint8)
+    rng = np.random.default_rng(5)
+    lens = [3000, 1, 64, 70_001, 2047, 2048, 2049, 10, 500_000]
+    seqs = [chars[synth.random_text(m, 4, 100 + i)].tobytes() for i, m in enumerate(lens)]
+    seqs[3] = seqs[3].lower()                                       # soft-masked: case-insensitive table
+    recs = [(f"rec{i} some description".encode(), s) for i, s in enumerate(seqs)]
+    if variant == "fastq":
+        data = b"".join(b"@" + n + b"\n" + s + b"\n+\n" + bytes(rng.integers(33, 74, len(s), dtype=np.uint8)) + b"\n" for n, s in recs)
+    else:
+        data = _fasta(recs, 61, crlf="crlf" in variant, comments="comments" in variant)
+        if variant == "fasta-no-final-newline":
+            data = data.rstrip(b"\n")
+        if variant == "fasta-headerless-start":
+            data = seqs[0][:100] + b"\n" + data
+            recs = [(b"", seqs[0][:100])] + recs
+    want = np.concatenate([np.frombuffer(s.upper(), dtype=np.uint8) for _, s in recs])
+    want = np.searchsorted(chars, want).astype(np.uint8)
+    want_starts = np.concatenate([[0], np.cumsum([len(s) for _, s in recs])]).astype(np.uint64)
+    with kb.parse_sequences(data, "dna4") as r:
+        assert len(r) == len(recs) and r.n_symbols == want.size
+        assert np.array_equal(r.starts, want_starts)
+        for i, (name, _) in enumerate(recs):
+            assert r.name(i).encode() == name
+        with r.index([12]) as ix:
+            h, p = ix.element_arrays(0)
+            qs, truth = [], []
+            for i in (0, 3, 8, len(recs) - 1):
+                s0 = int(want_starts[i]) + 7
+                qs.append(want[s0:s0 + 36])           # 3 x k: a length on which the reference's plan is the correct one
+                truth.append((i, 7))
+            q = np.concatenate(qs)
+            off = np.arange(0, 36 * len(qs) + 1, 36, dtype=np.uint64)
+            res = ix.search_batch(q, off)
+            for j, (rec_i, o_i) in enumerate(truth):
+                pos = res.to_vector(j)
+                rec, o = r.locate(pos, 36)
+                assert (rec_i, o_i) in set(zip(rec.tolist(), o.tolist()))
+            # a window that starts 5 symbols before a record boundary only exists because records are concatenated
+            s0 = int(want_starts[1]) - 5
+            res = ix.search_batch(want[s0:s0 + 24], np.array([0, 24], dtype=np.uint64))
+            rec, _ = r.locate(res.to_vector(0), 24)
+            assert rec.size >= 1 and (rec == 0xFFFFFFFF).any()
+    with kb.KmerIndex(want, 4, [12]) as ref:
+        h2, p2 = ref.element_arrays(0)
+    assert np.array_equal(p, p2) and np.array_equal(h, h2)
+    with pytest.raises(kb.KmerB200Error):
+        kb.parse_sequences(b">x\nACGTNACGT\n", "dna4")            # N is not in dna4
