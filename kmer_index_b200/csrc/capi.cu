@@ -1191,6 +1191,17 @@ __global__ void hashes_from_text_kernel(kb::PackedText text, uint32_t k, const u
     if (i < n) out[i] = kb::key_at(text.words, (uint64_t)pos[i], k, text.bits, text.sigma);
 }
 
+// non-empty buckets of an element: dense directory -> entries that differ from their successor; else run starts of the hashes
+template <typename T>
+__global__ void __launch_bounds__(256) count_steps_kernel(const T *__restrict__ v, uint64_t n, unsigned long long *out) {
+    // number of i in [0, n) with v[i + 1] != v[i]
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t c = 0;
+    for (; i < n; i += (uint64_t)gridDim.x * blockDim.x) c += v[i + 1] != v[i];
+    c = __reduce_add_sync(0xFFFFFFFFu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
+
 __global__ void max_len_kernel(const uint64_t *__restrict__ off, uint64_t Q, unsigned long long *out) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long m = 0;
@@ -2777,17 +2788,6 @@ uint64_t kmer_b200_scheme(const kmer_b200_index *ix, uint64_t m, uint32_t *out_k
     for (uint32_t i = 0; i < len && i < cap && out_ks; ++i) out_ks[i] = ix->ks[ix->sum_elem[o + i]];
     if (use_multi) *use_multi = ix->use_multi[m];
     return len;
-}
-
-// non-empty buckets of an element: dense directory -> entries that differ from their successor; else run starts of the hashes
-template <typename T>
-__global__ void __launch_bounds__(256) count_steps_kernel(const T *__restrict__ v, uint64_t n, unsigned long long *out) {
-    // number of i in [0, n) with v[i + 1] != v[i]
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t c = 0;
-    for (; i < n; i += (uint64_t)gridDim.x * blockDim.x) c += v[i + 1] != v[i];
-    c = __reduce_add_sync(0xFFFFFFFFu, c);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
 }
 
 static int element_occupancy(kmer_b200_index *ix, HostElement &he) {
