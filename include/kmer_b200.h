@@ -231,6 +231,12 @@ int kmer_b200_element_part(const kmer_b200_index *index, uint32_t element, kmer_
 /* d_dst[j] = directory[j] + base for j < n (n <= directory_entries): the part's directory as a slice of the whole
    index's, `base` = number of k-mers in the parts before this one. Enqueued on the index's stream. */
 int kmer_b200_export_directory(kmer_b200_index *index, uint32_t element, uint64_t base, uint64_t n, uint32_t *d_dst);
+/* The part's directory as bucket sizes, one byte per hash of [key_lo, key_hi) -- a quarter of the bytes to move between
+   GPUs. *n_large_out = buckets holding 255 or more k-mers (their size does not fit: ship the directory itself then). */
+int kmer_b200_export_bucket_sizes(kmer_b200_index *index, uint32_t element, uint8_t *d_sizes, uint64_t *n_large_out);
+/* The whole directory d_directory[n_keys + 1] from the bucket sizes of all n_keys hashes (exclusive prefix sum; the last
+   entry is the total). Runs on the index's stream. */
+int kmer_b200_directory_from_sizes(kmer_b200_index *index, const uint8_t *d_sizes, uint64_t n_keys, uint32_t *d_directory);
 /* Replace the element's arrays by the assembled whole: d_positions[n_kmers] (n_kmers = n - k + 1) and the dense
    directory d_directory[sigma^k + 1], both device arrays that stay owned by the caller and must outlive the index.
    The element then covers the whole key space. */

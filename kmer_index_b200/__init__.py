@@ -444,6 +444,16 @@ class KmerIndex:
         """dst[j] = part directory[j] + base for j < n (device pointer), on the index's stream."""
         _capi.check(self._L.kmer_b200_export_directory(self._h, e, base, n, C.c_void_p(dst_ptr)))
 
+    def export_bucket_sizes(self, e: int, sizes_ptr: int) -> int:
+        """The part's directory as one byte per bucket (device pointer, key_hi - key_lo bytes); returns the number of
+        buckets too large for a byte (> 0: ship the directory itself)."""
+        n_large = C.c_uint64(0)
+        _capi.check(self._L.kmer_b200_export_bucket_sizes(self._h, e, C.c_void_p(sizes_ptr), C.byref(n_large)))
+        return int(n_large.value)
+
+    def directory_from_sizes(self, sizes_ptr: int, n_keys: int, directory_ptr: int) -> None:
+        _capi.check(self._L.kmer_b200_directory_from_sizes(self._h, C.c_void_p(sizes_ptr), n_keys, C.c_void_p(directory_ptr)))
+
     def adopt_element(self, e: int, positions, directory) -> None:
         """Hand the assembled whole element (device tensors: int32 positions[n - k + 1], directory[sigma^k + 1]) to
         the index; the tensors are kept alive by this object."""

@@ -877,24 +877,63 @@ struct FileElement {
 constexpr uint32_t kFileVersion = 2;  // 2: an element's sorted hashes are optional (FileElement::has_keys)
 constexpr size_t kIoChunk = 64u << 20;
 
+// Double-buffered: h_buf holds two halves of kIoChunk bytes; the copy of chunk c + 1 runs while chunk c is written to
+// (or read from) the file, so the file I/O and the PCIe copy overlap instead of alternating.
 int write_device_array(kmer_b200_index *ix, FILE *f, const void *d_ptr, uint64_t bytes, void *h_buf) {
-    for (uint64_t o = 0; o < bytes; o += kIoChunk) {
-        const size_t c = (size_t)std::min<uint64_t>(kIoChunk, bytes - o);
-        KB_CUDA_RET(cudaMemcpyAsync(h_buf, (const uint8_t *)d_ptr + o, c, cudaMemcpyDeviceToHost, ix->stream));
-        KB_CUDA_RET(cudaStreamSynchronize(ix->stream));
-        if (fwrite(h_buf, 1, c, f) != c) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "short write");
+    uint8_t *half[2] = {(uint8_t *)h_buf, (uint8_t *)h_buf + kIoChunk};
+    cudaEvent_t ev[2];
+    cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+    int status = 0;
+    const uint64_t n_chunks = (bytes + kIoChunk - 1) / kIoChunk;
+    auto chunk_bytes = [&](uint64_t c) { return (size_t)std::min<uint64_t>(kIoChunk, bytes - c * kIoChunk); };
+    if (n_chunks) {
+        cudaMemcpyAsync(half[0], (const uint8_t *)d_ptr, chunk_bytes(0), cudaMemcpyDeviceToHost, ix->stream);
+        cudaEventRecord(ev[0], ix->stream);
     }
-    return 0;
+    for (uint64_t c = 0; c < n_chunks && status == 0; ++c) {
+        if (c + 1 < n_chunks) {
+            cudaMemcpyAsync(half[(c + 1) & 1], (const uint8_t *)d_ptr + (c + 1) * kIoChunk, chunk_bytes(c + 1), cudaMemcpyDeviceToHost,
+                            ix->stream);
+            cudaEventRecord(ev[(c + 1) & 1], ix->stream);
+        }
+        if (cudaEventSynchronize(ev[c & 1]) != cudaSuccess) status = fail(KMER_B200_ERR_CUDA, "save: device to host copy failed");
+        else if (fwrite(half[c & 1], 1, chunk_bytes(c), f) != chunk_bytes(c)) status = fail(KMER_B200_ERR_INVALID_ARGUMENT, "short write");
+    }
+    cudaStreamSynchronize(ix->stream);
+    cudaEventDestroy(ev[0]);
+    cudaEventDestroy(ev[1]);
+    return status;
 }
 
 int read_device_array(kmer_b200_index *ix, FILE *f, void *d_ptr, uint64_t bytes, void *h_buf) {
-    for (uint64_t o = 0; o < bytes; o += kIoChunk) {
-        const size_t c = (size_t)std::min<uint64_t>(kIoChunk, bytes - o);
-        if (fread(h_buf, 1, c, f) != c) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "truncated index file");
-        KB_CUDA_RET(cudaMemcpyAsync((uint8_t *)d_ptr + o, h_buf, c, cudaMemcpyHostToDevice, ix->stream));
-        KB_CUDA_RET(cudaStreamSynchronize(ix->stream));
+    uint8_t *half[2] = {(uint8_t *)h_buf, (uint8_t *)h_buf + kIoChunk};
+    cudaEvent_t ev[2];
+    cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+    bool used[2] = {false, false};
+    int status = 0;
+    const uint64_t n_chunks = (bytes + kIoChunk - 1) / kIoChunk;
+    for (uint64_t c = 0; c < n_chunks && status == 0; ++c) {
+        const int h = (int)(c & 1);
+        const size_t cb = (size_t)std::min<uint64_t>(kIoChunk, bytes - c * kIoChunk);
+        if (used[h]) cudaEventSynchronize(ev[h]);  // the half's previous upload has left it
+        if (fread(half[h], 1, cb, f) != cb) {
+            status = fail(KMER_B200_ERR_INVALID_ARGUMENT, "truncated index file");
+            break;
+        }
+        if (cudaMemcpyAsync((uint8_t *)d_ptr + c * kIoChunk, half[h], cb, cudaMemcpyHostToDevice, ix->stream) != cudaSuccess) {
+            cudaGetLastError();
+            status = fail(KMER_B200_ERR_CUDA, "load: host to device copy failed");
+            break;
+        }
+        cudaEventRecord(ev[h], ix->stream);
+        used[h] = true;
     }
-    return 0;
+    if (cudaStreamSynchronize(ix->stream) != cudaSuccess && status == 0) status = fail(KMER_B200_ERR_CUDA, "load: host to device copy failed");
+    cudaEventDestroy(ev[0]);
+    cudaEventDestroy(ev[1]);
+    return status;
 }
 
 // Build auxiliary k' = m elements for the sub-k query lengths in `want` (bit m) that have none yet, memory
@@ -1063,6 +1102,9 @@ int search_begin(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off,
     a.hits = p->d_hits;
     a.bits = ix->bits;
     a.single_k = ix->ks.size() == 1;
+    a.lean_ok = a.single_k && ix->sigma == 4 && ix->elems[0].dev.shift == 0 && ix->elems[0].key_bytes == 4 && !d_present4 &&
+                !d_present_global && ix->cfg.profile < 2 && ix->host_index.presence[0] == nullptr &&
+                !std::getenv("KMER_B200_NO_LEAN");
     a.error_flag = p->d_flags;  // per search: a second search on the handle cannot clobber a pending one's flags
     a.gather_count = ix->cfg.profile >= 2 ? ix->d_gathers : nullptr;  // profile = 2: also count gathered sectors
     if (a.gather_count) cudaMemsetAsync(ix->d_gathers, 0, sizeof(unsigned long long), st);
@@ -1255,7 +1297,7 @@ int kmer_b200_save(kmer_b200_index *ix, const char *path) {
     FILE *f = std::fopen(path, "wb");
     if (!f) return fail(KMER_B200_ERR_INVALID_ARGUMENT, std::string("cannot open ") + path);
     size_t cap = 0;
-    void *h_buf = pinned_get(kIoChunk, &cap);
+    void *h_buf = pinned_get(2 * kIoChunk, &cap);
     int s = h_buf ? 0 : fail(KMER_B200_ERR_OUT_OF_MEMORY, "pinned host allocation failed");
     FileHeader h{};
     std::memcpy(h.magic, "KMERB200", 8);
@@ -1313,7 +1355,7 @@ int kmer_b200_load(const char *path, const kmer_b200_config *cfg_in, kmer_b200_i
         if (ix->bits != h.bits || ix->text_words != h.text_words)
             return fail(KMER_B200_ERR_INVALID_ARGUMENT, "index file does not match this build's text packing");
         size_t cap = 0;
-        void *h_buf = pinned_get(kIoChunk, &cap);
+        void *h_buf = pinned_get(2 * kIoChunk, &cap);
         if (!h_buf) return fail(KMER_B200_ERR_OUT_OF_MEMORY, "pinned host allocation failed");
         int r = read_device_array(ix, f, ix->d_text, ix->text_words * 8, h_buf);
         ix->elems.resize(h.n_ks);
@@ -2165,6 +2207,44 @@ int kmer_b200_export_directory(kmer_b200_index *ix, uint32_t e, uint64_t base, u
         return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad argument");
     DeviceGuard guard(ix->device);
     if (n) add_base32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ix->stream>>>(ix->elems[e].d_dir, n, (uint32_t)base, d_dst);
+    KB_CUDA(cudaGetLastError());
+    return KMER_B200_OK;
+}
+
+int kmer_b200_export_bucket_sizes(kmer_b200_index *ix, uint32_t e, uint8_t *d_sizes, uint64_t *n_large_out) {
+    ix = primary(ix);
+    if (!ix || !d_sizes || !n_large_out || e >= ix->ks.size()) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad argument");
+    const HostElement &he = ix->elems[e];
+    if (he.dev.shift != 0) return fail(KMER_B200_ERR_UNSUPPORTED, "bucket sizes are exported from dense directories only");
+    DeviceGuard guard(ix->device);
+    unsigned long long *d_large = nullptr;
+    KB_TRY(dev_alloc(ix, &d_large, 1, false));
+    cudaMemsetAsync(d_large, 0, sizeof(unsigned long long), ix->stream);
+    kb::launch_bucket_sizes(he.d_dir, he.dev.dir_entries - 1, d_sizes, d_large, ix->stream);
+    unsigned long long large = 0;
+    KB_CUDA(cudaMemcpyAsync(&large, d_large, sizeof(large), cudaMemcpyDeviceToHost, ix->stream));
+    KB_CUDA(cudaStreamSynchronize(ix->stream));
+    dev_free(ix, d_large);
+    *n_large_out = large;
+    return KMER_B200_OK;
+}
+
+int kmer_b200_directory_from_sizes(kmer_b200_index *ix, const uint8_t *d_sizes, uint64_t n_keys, uint32_t *d_directory) {
+    ix = primary(ix);
+    if (!ix || !d_sizes || !d_directory) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
+    DeviceGuard guard(ix->device);
+    const uint64_t tiles = kb::sizes_tiles(n_keys + 1);  // one entry more than hashes: the sizes array is read as n_keys + 1 with a zero tail
+    uint64_t *d_tile = nullptr, *d_sums = nullptr;
+    KB_TRY(dev_alloc(ix, &d_tile, tiles + 1, false));
+    KB_TRY(dev_alloc(ix, &d_sums, kb::offsets_scan_blocks(tiles) + 1, false));
+    kb::launch_sizes_tile_sums(d_sizes, n_keys, d_tile, ix->stream);
+    if (kb::sizes_tiles(n_keys) < tiles) cudaMemsetAsync(d_tile + kb::sizes_tiles(n_keys), 0, sizeof(uint64_t), ix->stream);
+    kb::launch_offsets_scan(d_tile, tiles, d_sums, ix->stream);
+    kb::launch_sizes_to_dir(d_sizes, n_keys, d_tile, d_directory, ix->stream);
+    // the sentinel entry d_directory[n_keys] = total
+    KB_CUDA(cudaMemcpyAsync(d_directory + n_keys, d_tile + tiles, sizeof(uint32_t), cudaMemcpyDeviceToDevice, ix->stream));
+    dev_free(ix, d_tile);
+    dev_free(ix, d_sums);
     KB_CUDA(cudaGetLastError());
     return KMER_B200_OK;
 }

@@ -125,6 +125,61 @@ __device__ __forceinline__ uint64_t element_key_or_text(const PackedText &T, con
     return key_at(T.words, (uint64_t)gather32(E.pos + i), E.k, T.bits, T.sigma);
 }
 
+// ---- directory lookups (the reference's at(hash), kmer_index.hpp:76-84) ------------------------------------------------
+struct Range {
+    uint64_t lo;
+    uint64_t cnt;
+};
+
+// index of the first sorted k-mer of element E whose hash is >= key (key may equal key_space)
+__device__ __forceinline__ uint64_t lower_bound_key(const Element &E, uint64_t key) {
+    if (key >= E.key_space || key >= E.key_hi) return E.n_kmers;
+    if (key <= E.key_lo) return 0;
+    key -= E.key_lo;
+    const uint64_t t = key >> E.shift;
+    uint64_t lo = gather32(E.dir + t);
+    if (E.shift == 0) return lo;
+    uint64_t hi = gather32(E.dir + t + 1);
+    while (lo < hi) {
+        const uint64_t mid = lo + ((hi - lo) >> 1);
+        if (element_key(E, mid) < key)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+// the bucket of `key`: the reference's at(hash) (kmer_index.hpp:76-84)
+__device__ __forceinline__ Range bucket_of(const Element &E, uint64_t key) {
+    if (key < E.key_lo || key >= E.key_hi) return Range{0, 0};  // another part's hash
+    key -= E.key_lo;
+    const uint64_t t = key >> E.shift;
+    uint64_t lo = gather32(E.dir + t);
+    uint64_t hi = gather32(E.dir + t + 1);
+    if (E.shift != 0) {
+        uint64_t a = lo, b = hi;
+        while (a < b) {
+            const uint64_t mid = a + ((b - a) >> 1);
+            if (element_key(E, mid) < key)
+                a = mid + 1;
+            else
+                b = mid;
+        }
+        lo = a;
+        b = hi;
+        while (a < b) {
+            const uint64_t mid = a + ((b - a) >> 1);
+            if (element_key(E, mid) <= key)
+                a = mid + 1;
+            else
+                b = mid;
+        }
+        hi = a;
+    }
+    return Range{lo, hi - lo};
+}
+
 struct SchemeTables {
     // row m of the reference's _optimal_nk_sum / _use_multi_search_scheme (kmer_index.hpp:404-405),
     // with ks replaced by element indices

@@ -72,6 +72,8 @@ struct SearchArgs {
     uint32_t group;                  // lanes per query: 1, 2, 4, 8 or 32
     uint32_t bits;                   // bits per packed symbol (to size the heavy launch's staging)
     uint32_t single_k;               // the index has one element: launch the kernels compiled without the multi-k plans
+    uint32_t lean_ok;                // host-checked: single k, dna4 (2-bit symbols), dense 32-bit directory, plain count pass ->
+                                     // search_lean.cu may take the count pass when max_len <= 128
     uint32_t *heavy;                 // device or null, u32[1 + Q]: [0] = number of heavy queries, then their ids
     uint32_t *hits;                  // device or null, u32[1 + Q]: [0] = number of queries with hits (count pass), then their ids
     uint32_t q_words;                // packed words reserved per query in shared memory (search_q_words)
@@ -147,6 +149,13 @@ void launch_fastx_count(const uint8_t *d_data, uint64_t n, uint32_t format, cons
 void launch_fastx_write(const uint8_t *d_data, uint64_t n, uint32_t format, const uint64_t *d_nl_before, const int64_t *d_last_nl,
                         const uint64_t *d_kept_off, const uint64_t *d_recs_off, const uint8_t *d_lut, uint32_t sigma, uint8_t *d_ranks,
                         uint64_t *d_rec_start_symbol, uint64_t *d_rec_header_byte, uint32_t *d_error_flag, cudaStream_t stream);
+
+// a directory part as one byte per bucket (its size, 255 = "255 or more": counted in *d_n_large), and back: the whole
+// directory as the exclusive prefix sum of all sizes (tile sums -> launch_offsets_scan -> offsets)
+void launch_bucket_sizes(const uint32_t *d_dir, uint64_t n_keys, uint8_t *d_sizes, unsigned long long *d_n_large, cudaStream_t stream);
+uint64_t sizes_tiles(uint64_t n);
+void launch_sizes_tile_sums(const uint8_t *d_sizes, uint64_t n, uint64_t *d_tile_sums, cudaStream_t stream);
+void launch_sizes_to_dir(const uint8_t *d_sizes, uint64_t n, const uint64_t *d_tile_off, uint32_t *d_dir, cudaStream_t stream);
 
 // ---- random-gather calibration (the denominator of the search roofline)
 void launch_gather_probe(const uint64_t *d_table, uint64_t n_words, uint64_t n_gathers, uint64_t *d_sink, cudaStream_t stream);

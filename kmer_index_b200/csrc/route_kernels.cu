@@ -245,4 +245,124 @@ void launch_presence_bits(const uint32_t *d_dir, uint64_t n_keys, uint64_t *d_bi
     presence_bits_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_dir, n_keys, reinterpret_cast<uint32_t *>(d_bits_at_lo));
 }
 
+
+// ---- a directory part as bucket SIZES (1 byte per hash instead of a 4-byte offset) -------------------------------------
+// The replicated multi-GPU build all-gathers every part's directory; on a genome-like text almost every bucket holds a
+// handful of k-mers, so the parts travel as one byte per hash (a quarter of the bytes over NVLink) and every GPU rebuilds
+// the whole directory with a prefix sum. A part with a bucket of 255 or more k-mers reports it and the caller ships
+// that index's directory uncompressed.
+__global__ void __launch_bounds__(256) bucket_sizes_kernel(const uint32_t *__restrict__ dir, uint64_t n_keys, uint8_t *__restrict__ sizes,
+                                                           unsigned long long *__restrict__ n_large) {
+    const uint64_t h0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (h0 >= n_keys) return;
+    uint32_t large = 0, packed = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t c = 0;
+        if (h0 + j < n_keys) c = dir[h0 + j + 1] - dir[h0 + j];
+        if (c >= 255) {
+            c = 255;
+            ++large;
+        }
+        packed |= c << (8 * j);
+    }
+    if (h0 + 4 <= n_keys)
+        *reinterpret_cast<uint32_t *>(sizes + h0) = packed;  // n_keys parts start on multiples of 64 hashes: aligned
+    else
+        for (int j = 0; h0 + j < n_keys; ++j) sizes[h0 + j] = (uint8_t)(packed >> (8 * j));
+    if (large) atomicAdd(n_large, (unsigned long long)large);
+}
+
+void launch_bucket_sizes(const uint32_t *d_dir, uint64_t n_keys, uint8_t *d_sizes, unsigned long long *d_n_large, cudaStream_t stream) {
+    if (n_keys == 0) return;
+    const uint64_t threads = (n_keys + 3) / 4;
+    bucket_sizes_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_dir, n_keys, d_sizes, d_n_large);
+}
+
+constexpr int kSizesTile = 256 * 16;  // sizes per CTA (16 per thread, one 16-byte load)
+
+__device__ __forceinline__ uint32_t sum16(uint4 v) {
+    // sum of the 16 bytes: pairwise via __vsadu4-free arithmetic (bytes are < 256, the sums fit 16 bits per lane pair)
+    uint32_t s = 0;
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s += (w[i] & 0xFF) + ((w[i] >> 8) & 0xFF) + ((w[i] >> 16) & 0xFF) + (w[i] >> 24);
+    return s;
+}
+
+__global__ void __launch_bounds__(256) sizes_tile_sum_kernel(const uint8_t *__restrict__ sizes, uint64_t n, uint64_t *__restrict__ tile_sums) {
+    __shared__ uint32_t warp_sums[8];
+    const uint64_t i0 = (uint64_t)blockIdx.x * kSizesTile + (uint64_t)threadIdx.x * 16;
+    uint32_t s = 0;
+    if (i0 + 16 <= n) {
+        s = sum16(*reinterpret_cast<const uint4 *>(sizes + i0));
+    } else {
+        for (uint64_t i = i0; i < n; ++i) s += sizes[i];
+    }
+    s = __reduce_add_sync(0xFFFFFFFFu, s);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < 8; ++w) t += warp_sums[w];
+        tile_sums[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) sizes_to_dir_kernel(const uint8_t *__restrict__ sizes, uint64_t n, const uint64_t *__restrict__ tile_off,
+                                                           uint32_t *__restrict__ dir) {
+    __shared__ uint32_t warp_sums[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t i0 = (uint64_t)blockIdx.x * kSizesTile + (uint64_t)threadIdx.x * 16;
+    uint8_t b[16];
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) b[j] = 0;
+    if (i0 + 16 <= n) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(sizes + i0);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) b[j] = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
+    } else {
+        for (int j = 0; j < 16 && i0 + j < n; ++j) b[j] = sizes[i0 + j];
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s += b[j];
+    uint32_t incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    uint32_t run = (uint32_t)tile_off[blockIdx.x] + incl - s;  // offsets are < 2^32 (32-bit positions)
+    for (int w = 0; w < warp; ++w) run += warp_sums[w];
+    if (i0 + 16 <= n) {
+        uint32_t o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            o[j] = run;
+            run += b[j];
+        }
+        uint4 *dst = reinterpret_cast<uint4 *>(dir + i0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    } else {
+        for (int j = 0; j < 16 && i0 + j < n; ++j) {
+            dir[i0 + j] = run;
+            run += b[j];
+        }
+    }
+}
+
+uint64_t sizes_tiles(uint64_t n) { return (n + kSizesTile - 1) / kSizesTile; }
+
+void launch_sizes_tile_sums(const uint8_t *d_sizes, uint64_t n, uint64_t *d_tile_sums, cudaStream_t stream) {
+    if (n) sizes_tile_sum_kernel<<<(unsigned)sizes_tiles(n), 256, 0, stream>>>(d_sizes, n, d_tile_sums);
+}
+void launch_sizes_to_dir(const uint8_t *d_sizes, uint64_t n, const uint64_t *d_tile_off, uint32_t *d_dir, cudaStream_t stream) {
+    if (n) sizes_to_dir_kernel<<<(unsigned)sizes_tiles(n), 256, 0, stream>>>(d_sizes, n, d_tile_off, d_dir);
+}
+
 }  // namespace kb

@@ -30,60 +30,6 @@ constexpr int kSearchThreads = kSearchWarps * 32;
 
 enum PlanKind : int { kExact = 0, kSubK = 1, kContig = 2, kBuggySingle = 3, kMultiSum = 4 };
 
-struct Range {
-    uint64_t lo;
-    uint64_t cnt;
-};
-
-// index of the first sorted k-mer of element E whose hash is >= key (key may equal key_space)
-__device__ __forceinline__ uint64_t lower_bound_key(const Element &E, uint64_t key) {
-    if (key >= E.key_space || key >= E.key_hi) return E.n_kmers;
-    if (key <= E.key_lo) return 0;
-    key -= E.key_lo;
-    const uint64_t t = key >> E.shift;
-    uint64_t lo = gather32(E.dir + t);
-    if (E.shift == 0) return lo;
-    uint64_t hi = gather32(E.dir + t + 1);
-    while (lo < hi) {
-        const uint64_t mid = lo + ((hi - lo) >> 1);
-        if (element_key(E, mid) < key)
-            lo = mid + 1;
-        else
-            hi = mid;
-    }
-    return lo;
-}
-
-// the bucket of `key`: the reference's at(hash) (kmer_index.hpp:76-84)
-__device__ __forceinline__ Range bucket_of(const Element &E, uint64_t key) {
-    if (key < E.key_lo || key >= E.key_hi) return Range{0, 0};  // another part's hash
-    key -= E.key_lo;
-    const uint64_t t = key >> E.shift;
-    uint64_t lo = gather32(E.dir + t);
-    uint64_t hi = gather32(E.dir + t + 1);
-    if (E.shift != 0) {
-        uint64_t a = lo, b = hi;
-        while (a < b) {
-            const uint64_t mid = a + ((b - a) >> 1);
-            if (element_key(E, mid) < key)
-                a = mid + 1;
-            else
-                b = mid;
-        }
-        lo = a;
-        b = hi;
-        while (a < b) {
-            const uint64_t mid = a + ((b - a) >> 1);
-            if (element_key(E, mid) <= key)
-                a = mid + 1;
-            else
-                b = mid;
-        }
-        hi = a;
-    }
-    return Range{lo, hi - lo};
-}
-
 // T[tpos, tpos+len) == q[qpos, qpos+len), false if the text span leaves the text
 __device__ __forceinline__ bool match_span(const PackedText &T, const uint64_t *qw, uint64_t tpos, uint32_t qpos,
                                            uint32_t len) {
@@ -143,7 +89,8 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
     if (PASS == kPassWrite) {
         out_base = a.counts[q];
         if (a.counts[q + 1] == out_base) return;  // nothing to write (also covers every non-OK status)
-        if (!HEAVY && (a.unsorted[q] & 2)) return;  // the count pass gave it to the heavy launch
+        if (!HEAVY && G < 32 && (a.unsorted[q] & 2)) return;  // the count pass gave it to the heavy launch (which only follows
+                                                             // a pass of narrower groups: a full-warp pass writes it itself)
     }
 
     const DeviceIndex &ix = *a.index;
@@ -749,8 +696,22 @@ uint32_t search_q_words(uint32_t group, uint32_t bits, uint64_t max_len) {
     return (uint32_t)(rounds * (group * cpl / lpw) + 2);
 }
 
+bool launch_search_count_lean(const SearchArgs &a, cudaStream_t stream);  // search_lean.cu
+
 void launch_search(const SearchArgs &args, SearchPass pass, cudaStream_t stream) {
     if (args.n_queries == 0) return;
+    if (pass == kPassCount && launch_search_count_lean(args, stream)) {
+        // the lean kernel answered what it covers; the queries it listed (prefix slabs, long candidate lists) go to the
+        // general kernel's warp-per-query launch, as after the general count pass
+        SearchArgs h = args;
+        h.q_words = search_q_words(32, args.bits, args.max_len);
+        const size_t hsmem = (size_t)(kSearchThreads / 32) * h.q_words * sizeof(uint64_t);
+        if (args.single_k) {
+            cudaFuncSetAttribute(search_heavy_kernel<kPassCount, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem);
+            search_heavy_kernel<kPassCount, true><<<device_sm_count() * 2, kSearchThreads, hsmem, stream>>>(h);
+        }
+        return;
+    }
     if (args.group == 1) {
         if (pass == kPassCount) launch_search_pg<kPassCount, 1>(args, stream);
         if (pass == kPassCountAccount) launch_search_pg<kPassCountAccount, 1>(args, stream);

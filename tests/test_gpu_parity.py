@@ -363,6 +363,44 @@ def test_key_range_parts_assemble_to_the_whole_index(kb, oracle_mod, sigma, ks, 
             ix.close()
 
 
+@pytest.mark.parametrize("sigma,k,n,parts", [(4, 12, 300_000, 4), (4, 16, 400_000, 8), (4, 10, 3_000_000, 2)])
+def test_directory_parts_travel_as_bucket_sizes(kb, sigma, k, n, parts):
+    """The replicated multi-GPU build ships every part's directory as one byte per bucket and rebuilds the whole
+    directory with a prefix sum: must equal the directory assembled from the 4-byte entries; a bucket of >= 255 k-mers
+    is reported instead of being truncated."""
+    import torch
+
+    from kmer_index_b200 import synth
+    dev = torch.device("cuda", 0)
+    text = synth.random_text(n, sigma, 81)
+    stream = torch.cuda.current_stream().cuda_stream
+    idx = [kb.KmerIndex(text, sigma, [k], key_part=r, key_parts=parts, stream=stream or None) for r in range(parts)]
+    try:
+        key_space = sigma ** k
+        ps = [ix.element_part(0) for ix in idx]
+        dir_a = torch.empty(key_space + 1, dtype=torch.int32, device=dev)
+        sizes = torch.empty(key_space, dtype=torch.uint8, device=dev)
+        base = 0
+        for r, (ix, p) in enumerate(zip(idx, ps)):
+            ix.export_directory(0, base, p.key_hi - p.key_lo + (1 if r == parts - 1 else 0), dir_a.data_ptr() + 4 * p.key_lo)
+            assert ix.export_bucket_sizes(0, sizes.data_ptr() + p.key_lo) == 0
+            base += p.n_kmers
+        torch.cuda.synchronize()
+        dir_b = torch.full((key_space + 1,), -1, dtype=torch.int32, device=dev)
+        idx[0].directory_from_sizes(sizes.data_ptr(), key_space, dir_b.data_ptr())
+        torch.cuda.synchronize()
+        assert torch.equal(dir_a, dir_b)
+        assert int(dir_b[-1].item()) == n - k + 1
+    finally:
+        for ix in idx:
+            ix.close()
+    low = text.copy()
+    low[1000:1400] = 0                                            # one bucket of ~390 k-mers
+    with kb.KmerIndex(low, sigma, [k], key_part=0, key_parts=parts) as ix:
+        scratch = torch.empty(key_space, dtype=torch.uint8, device=dev)
+        assert ix.export_bucket_sizes(0, scratch.data_ptr()) >= 1
+
+
 @pytest.mark.parametrize("sigma,k,n,m_hi,parts,mode", [(4, 16, 500_000, 64, 4, 0), (4, 12, 300_000, 100, 3, 0), (4, 12, 300_000, 60, 8, 1),
                                                         (15, 8, 200_000, 40, 2, 0), (27, 5, 150_000, 24, 5, 0)])
 def test_routed_search_on_key_range_parts_emulated(kb, oracle_mod, sigma, k, n, m_hi, parts, mode):
@@ -625,7 +663,7 @@ def test_fasta_fastq_parsed_on_the_device(kb, variant):
         with r.index([12]) as ix:
             h, p = ix.element_arrays(0)
             qs, truth = [], []
-            for i in (0, 3, 8, len(recs) - 1):
+            for i in [j for j, (_, sq) in enumerate(recs) if len(sq) >= 43][:4] + [len(recs) - 1]:
                 s0 = int(want_starts[i]) + 7
                 qs.append(want[s0:s0 + 36])           # 3 x k: a length on which the reference's plan is the correct one
                 truth.append((i, 7))
