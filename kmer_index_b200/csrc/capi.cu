@@ -2920,12 +2920,16 @@ int kmer_b200_plan_table(kmer_b200_index *ix, uint32_t mode, uint32_t m_lo, uint
         bool throws = false, defective = false, multi_sum = false, sub_k = false;
         uint32_t n_lookups = 1;
         if (mode == KMER_B200_MODE_CORRECT) {
-            if (!largest_k_at_most(m, &e0)) {  // shorter than every k: the smallest k's prefix slab
-                for (uint32_t e = 1; e < n_ks; ++e)
-                    if (ix->ks[e] < ix->ks[e0]) e0 = e;
-                sub_k = true;
-            }
+            // the smallest k >= m (bucket or prefix slab = the result, nothing to verify), else the largest k
+            bool found = false;
+            for (uint32_t e = 0; e < n_ks; ++e)
+                if (ix->ks[e] >= m && (!found || ix->ks[e] < ix->ks[e0])) {
+                    e0 = e;
+                    found = true;
+                }
+            if (!found) largest_k_at_most(m, &e0);
             k0 = ix->ks[e0];
+            sub_k = k0 > m;
         } else {
             if (m >= kb::kQuerySizeRange) {
                 r.kind = 5;

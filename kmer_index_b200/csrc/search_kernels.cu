@@ -190,12 +190,15 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
     bool throw_after = false, from_list = false;
     const uint8_t *S = nullptr;
     if (a.mode == KMER_B200_MODE_CORRECT) {
-        // any element answers correctly; take the largest k <= m (fewest candidates), else the smallest k
+        // any element answers correctly. Planner (measured in profiles/r02/planner_report.md): the
+        // smallest k >= m if there is one -- its bucket (k == m) or prefix slab (k > m) IS the result, n / sigma^m
+        // positions and nothing to verify -- else the largest k, whose buckets are the shortest candidate lists
+        // (n / sigma^k each) to verify against the text.
         if (!SINGLE) {
-            e0 = ix.elem_by_k_desc[ix.n_elems - 1];
-            for (uint32_t i = 0; i < ix.n_elems; ++i) {
+            e0 = ix.elem_by_k_desc[0];
+            for (uint32_t i = ix.n_elems; i-- > 0;) {
                 const uint32_t e = ix.elem_by_k_desc[i];
-                if (ix.elem[e].k <= m) {
+                if (ix.elem[e].k >= m) {
                     e0 = e;
                     break;
                 }

@@ -387,6 +387,7 @@ def test_directory_parts_travel_as_bucket_sizes(kb, sigma, k, n, parts):
             base += p.n_kmers
         torch.cuda.synchronize()
         dir_b = torch.full((key_space + 1,), -1, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()                                  # the index works on its own stream
         idx[0].directory_from_sizes(sizes.data_ptr(), key_space, dir_b.data_ptr())
         torch.cuda.synchronize()
         assert torch.equal(dir_a, dir_b)
