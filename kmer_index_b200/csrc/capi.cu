@@ -1103,8 +1103,7 @@ int search_begin(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off,
     a.bits = ix->bits;
     a.single_k = ix->ks.size() == 1;
     a.lean_ok = a.single_k && ix->sigma == 4 && ix->elems[0].dev.shift == 0 && ix->elems[0].key_bytes == 4 && !d_present4 &&
-                !d_present_global && ix->cfg.profile < 2 && ix->host_index.presence[0] == nullptr &&
-                !std::getenv("KMER_B200_NO_LEAN");
+                !d_present_global && ix->cfg.profile < 2 && !std::getenv("KMER_B200_NO_LEAN");
     a.error_flag = p->d_flags;  // per search: a second search on the handle cannot clobber a pending one's flags
     a.gather_count = ix->cfg.profile >= 2 ? ix->d_gathers : nullptr;  // profile = 2: also count gathered sectors
     if (a.gather_count) cudaMemsetAsync(ix->d_gathers, 0, sizeof(unsigned long long), st);

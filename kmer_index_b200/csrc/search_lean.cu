@@ -166,14 +166,23 @@ __global__ void __launch_bounds__(kLeanThreads, W == 2 ? 6 : 5) search_count_lea
     if ((throw_after || buggy) && all_present) {
         // the reference looks every full part up first (:216-227); only these plans' outcome depends on it
         Range last{0, 0};
+        bool last_foreign = false;
+        const uint64_t *pb = ix.presence[0];
         for (uint32_t j = 1; j < P; ++j) {
-            last = bucket_of(E, window_at<W>(qw, j * k * 2) >> down);
+            const uint64_t key = window_at<W>(qw, j * k * 2) >> down;
+            last_foreign = pb != nullptr && (key < E.key_lo || key >= E.key_hi);
+            if (last_foreign) {
+                // another part's hash (key-range multi-GPU search): presence from the replicated bitmap; it cannot seed
+                last = Range{0, (gather64(pb + (key >> 6)) >> (key & 63)) & 1ull};
+            } else {
+                last = bucket_of(E, key);
+            }
             if (last.cnt == 0) {
                 all_present = false;
                 break;
             }
         }
-        if (all_present && buggy && last.cnt < seed.cnt) {  // seed from the shorter of the two constrained parts
+        if (all_present && buggy && !last_foreign && last.cnt < seed.cnt) {  // seed from the shorter of the two constrained parts
             seed = last;
             seed_d = (P - 1) * k;
         }
