@@ -52,6 +52,22 @@ typedef enum kmer_b200_mode {
     KMER_B200_MODE_CORRECT = 1
 } kmer_b200_mode;
 
+/* kmer_b200_config::reserved */
+enum {
+    /* never build auxiliary k' = m elements for sub-k query lengths (saves memory; those results are then sorted by the
+       segment-sort kernel instead) */
+    KMER_B200_FLAG_NO_AUX = 1,
+    /* Shared-positions multi-k index (the reference's own outlook, thesis/content/04_outlook_and_conclusion.tex:25-45:
+       "every k stores all n positions again"). ONE position array, sorted by the hash of the LARGEST k, serves every k:
+       the bucket of a shorter k-mer is the contiguous slab of the largest-k hashes that start with it, found through the
+       same directory. Device memory of the elements falls by about the number of ks; results are identical. The price:
+       inside a slab the positions are ordered by the following symbols, not by position, so every result seeded from a
+       shorter k is sorted per query after it is written (exact-length and sub-k lookups of short k return whole slabs:
+       expect those to be many times slower than with per-k arrays; DESIGN.md section 8 has the numbers). Implies
+       KMER_B200_FLAG_NO_AUX. Single device, unsharded. Ignored for one k. */
+    KMER_B200_FLAG_SHARED_POSITIONS = 2
+};
+
 typedef struct kmer_b200_config {
     int32_t device;        /* CUDA device ordinal; -1 = the calling thread's current device */
     uint32_t mode;         /* default kmer_b200_mode for searches */
@@ -66,8 +82,7 @@ typedef struct kmer_b200_config {
     uint32_t directory_bits; /* 0 = automatic; otherwise log2 of the directory size cap per element */
     uint32_t profile;        /* 1 = bracket every kernel launch with CUDA events (kmer_b200_stats);
                                 2 = additionally count the 32-byte sectors each search gathers */
-    uint32_t reserved;       /* bit 0: never build auxiliary k' = m elements for sub-k query lengths (saves memory;
-                                those results are then sorted by the segment-sort kernel instead) */
+    uint32_t reserved;       /* flag bits, KMER_B200_FLAG_* below */
     /* Key-range parts (multi-GPU build of a REPLICATED index). key_parts > 1: `ranks` is the whole text, but every
        element indexes only the k-mers whose hash lies in part key_part of key_parts equal slices of [0, sigma^k):
        1/key_parts of the sorting work per GPU. The parts are concatenated into the full index (part r's position

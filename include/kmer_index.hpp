@@ -203,6 +203,9 @@ namespace kmer
         }
     };
 
+    // tag for the shared-positions constructor below
+    inline constexpr struct shared_positions_t {} shared_positions{};
+
     // kmer_index.hpp:350-566
     template<alphabet alphabet_t, typename position_t, std::size_t... ks>
     class kmer_index
@@ -228,6 +231,15 @@ namespace kmer
             build(text, mode, device, nullptr, 0);
         }
 
+        // kmer_index(text, kmer::shared_positions): ONE position array, sorted by the largest k, serves every k (the
+        // thesis' outlook, 04_outlook_and_conclusion.tex:25-45) -- about sizeof...(ks) times less device memory, the same
+        // results, slower lookups through the shorter ks (KMER_B200_FLAG_SHARED_POSITIONS in kmer_b200.h)
+        template<std::ranges::range text_t>
+        kmer_index(text_t& text, shared_positions_t, kmer_b200_mode mode = KMER_B200_MODE_REFERENCE_EXACT, int device = -1)
+        {
+            build(text, mode, device, nullptr, 0, KMER_B200_FLAG_SHARED_POSITIONS);
+        }
+
         // the same index replicated over several GPUs (built from key-range parts, one per GPU); search_batch() stripes
         // its batch over them
         template<std::ranges::range text_t>
@@ -239,13 +251,15 @@ namespace kmer
 
     private:
         template<typename text_t>
-        void build(text_t& text, kmer_b200_mode mode, int device, std::int32_t const* ids, std::uint32_t n_ids)
+        void build(text_t& text, kmer_b200_mode mode, int device, std::int32_t const* ids, std::uint32_t n_ids,
+                   std::uint32_t flags = 0)
         {
             static constexpr std::uint32_t k_list[] = {std::uint32_t(ks)...};
             kmer_b200_config cfg;
             kmer_b200_config_default(&cfg);
             cfg.mode = mode;
             cfg.device = device;
+            cfg.reserved = flags;
             if (n_ids > 1)
             {
                 cfg.device_ids = ids;

@@ -231,7 +231,7 @@ class KmerIndex:
                  stream: int | None = None, profile: bool = False, shard_begin: int = 0, n_total: int = 0,
                  halo: int = 0, directory_bits: int = 0, text_device_ptr: int | None = None, n: int | None = None,
                  aux_elements: bool = True, lut: np.ndarray | None = None, key_part: int = 0, key_parts: int = 0,
-                 devices: Sequence[int] | None = None):
+                 devices: Sequence[int] | None = None, shared_positions: bool = False):
         L = _capi.lib()
         self._L = L
         self._h = C.c_void_p()
@@ -248,7 +248,8 @@ class KmerIndex:
         cfg.n_total = n_total
         cfg.halo = halo
         cfg.directory_bits = directory_bits
-        cfg.reserved = 0 if aux_elements else 1   # bit 0: no auxiliary k' = m elements for sub-k lengths
+        # bit 0: no auxiliary k' = m elements for sub-k lengths; bit 1: ONE position array (the largest k's) serves every k
+        cfg.reserved = (0 if aux_elements else 1) | (2 if shared_positions else 0)
         cfg.key_part, cfg.key_parts = key_part, key_parts   # key-range part of a multi-GPU build (sharded.build_replicated)
         self._adopted = []                                   # arrays handed over with adopt_element: kept alive here
         if devices is not None and len(devices) > 1:         # several GPUs behind this one handle (host batches only)

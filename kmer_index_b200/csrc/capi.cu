@@ -153,7 +153,23 @@ struct HostElement {
     uint32_t key_bytes = 4;
     uint64_t n_occupied = 0;  // distinct hashes (non-empty buckets), measured on first use by kmer_b200_plan_table
     int adopted = 0;         // 1: pos / dir belong to the caller (kmer_b200_adopt_element); 2: assembled by the library, owned
+    bool view = false;       // shared-positions index: no arrays of its own, a prefix view of the largest k's (kb::Element::width)
 };
+
+// Shared-positions multi-k index (kmer_b200_config::reserved bit 1): every element but the one with the largest k becomes
+// a view of that one's arrays. `owner` must be built (or loaded).
+void make_view(HostElement &he, const HostElement &owner, uint32_t k, uint32_t sigma) {
+    he = HostElement{};
+    he.view = true;
+    he.dev = owner.dev;  // dir / keys / pos / shift / n_kmers / key_space / key_bytes are the owner's
+    he.dev.k = k;
+    he.dev.k_phys = owner.dev.k;
+    he.dev.width = fast_pow(sigma, (uint8_t)(owner.dev.k - k));
+    he.key_bits = std::max<uint32_t>(1, bit_length(fast_pow(sigma, (uint8_t)k) - 1));
+    he.key_bytes = owner.key_bytes;
+    he.sort_passes = 0;
+    he.bytes = 0;
+}
 
 // the hash range element `k` of this index covers: all of [0, sigma^k), or one of cfg.key_parts equal slices
 struct KeyRange {
@@ -622,6 +638,8 @@ int build_element(kmer_b200_index *ix, uint32_t k, HostElement &he, bool auxilia
     he.dev.key_bytes = key_bytes;
     he.dev.key_lo = partial ? part.lo : 0;
     he.dev.key_hi = partial ? part.hi : UINT64_MAX;
+    he.dev.k_phys = k;
+    he.dev.width = 1;
     he.bytes = n_part * (sizeof(uint32_t) + (he.d_keys ? key_bytes : 0)) + dir_entries * sizeof(uint32_t);
     if (!auxiliary)
         ix->max_avg_bucket = std::max(ix->max_avg_bucket, (double)n_kmers / (double)std::min<uint64_t>(key_space, n_kmers));
@@ -675,6 +693,13 @@ int new_index(uint64_t n, uint32_t sigma, const uint32_t *ks, uint32_t n_ks, con
 
     if (cfg.key_parts > 1 && cfg.key_part >= cfg.key_parts) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "key_part must be < key_parts");
     if (cfg.key_parts > 1 && sharded) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "key-range parts index the whole text: no position-range shard");
+    if ((cfg.reserved & KMER_B200_FLAG_SHARED_POSITIONS) && n_ks > 1) {
+        if (sharded || cfg.key_parts > 1 || cfg.n_devices > 1)
+            return fail(KMER_B200_ERR_UNSUPPORTED, "a shared-positions index is unsharded and lives on one device");
+        cfg.reserved |= KMER_B200_FLAG_NO_AUX;  // the point is one position array: no per-length copies on demand
+    } else {
+        cfg.reserved &= ~(uint32_t)KMER_B200_FLAG_SHARED_POSITIONS;
+    }
     int device = cfg.device;
     if (device < 0) {
         cudaError_t e = cudaGetDevice(&device);
@@ -848,6 +873,13 @@ int create_impl(const uint8_t *ranks, bool ranks_on_device, uint64_t n, uint32_t
         if (d_ranks_owned) dev_free(ix, d_ranks_owned);
         // ---- elements
         ix->elems.resize(n_ks);
+        if (ix->cfg.reserved & KMER_B200_FLAG_SHARED_POSITIONS) {
+            const uint32_t owner = (uint32_t)(std::max_element(ks, ks + n_ks) - ks);
+            KB_TRY(build_element(ix, ks[owner], ix->elems[owner]));
+            for (uint32_t i = 0; i < n_ks; ++i)
+                if (i != owner) make_view(ix->elems[i], ix->elems[owner], ks[i], sigma);
+            return finalize_index(ix);
+        }
         for (uint32_t i = 0; i < n_ks; ++i) KB_TRY(build_element(ix, ks[i], ix->elems[i]));
         return finalize_index(ix);
     };
@@ -874,7 +906,8 @@ struct FileElement {
     uint32_t k, shift, key_bits, sort_passes, key_bytes, has_keys;
     uint64_t n_kmers, dir_entries, key_space;
 };
-constexpr uint32_t kFileVersion = 2;  // 2: an element's sorted hashes are optional (FileElement::has_keys)
+constexpr uint32_t kFileVersion = 3;  // 2: an element's sorted hashes are optional (FileElement::has_keys bit 0)
+                                      // 3: has_keys bit 1 = a view of the largest k's arrays (shared positions): no arrays follow
 constexpr size_t kIoChunk = 64u << 20;
 
 // Double-buffered: h_buf holds two halves of kIoChunk bytes; the copy of chunk c + 1 runs while chunk c is written to
@@ -985,7 +1018,8 @@ int search_geometry(const kmer_b200_index *ix, uint64_t max_len, uint32_t mode, 
     uint32_t group = len_cap <= 64 ? 1 : len_cap <= 128 ? 2 : len_cap <= 256 ? 4 : len_cap <= 1024 ? 8 : 32;
     if (ix->max_avg_bucket > 8.0) group = std::max(group, 8u);
     if (ix->max_avg_bucket > 64.0) group = 32;
-    if (const char *env = std::getenv("KMER_B200_GROUP")) {  // tuning override: lanes per query
+    if (ix->cfg.reserved & KMER_B200_FLAG_SHARED_POSITIONS) group = 32;  // the kernels with view support are warp-per-query
+    else if (const char *env = std::getenv("KMER_B200_GROUP")) {  // tuning override: lanes per query
         const int g = std::atoi(env);
         if (g == 1 || g == 2 || g == 4 || g == 8 || g == 32) group = (uint32_t)g;
     }
@@ -1052,6 +1086,8 @@ int search_begin(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off,
     if (mode > KMER_B200_MODE_CORRECT) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "unknown mode");
     // query ids travel as 32-bit values (heavy list, hit list, block indices of the launch)
     if (Q >= 0xFFFFFFFFull) return fail(KMER_B200_ERR_UNSUPPORTED, "more than 2^32 - 2 queries in one batch: split the batch");
+    if ((ix->cfg.reserved & KMER_B200_FLAG_SHARED_POSITIONS) && (d_present4 || d_present_global))
+        return fail(KMER_B200_ERR_UNSUPPORTED, "a shared-positions index is unsharded: no cross-shard presence exchange");
     cudaStream_t st = ix->stream;
     kmer_b200_result *res = new (std::nothrow) kmer_b200_result();
     if (!res) return fail(KMER_B200_ERR_OUT_OF_MEMORY, "host allocation failed");
@@ -1102,6 +1138,7 @@ int search_begin(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off,
     a.hits = p->d_hits;
     a.bits = ix->bits;
     a.single_k = ix->ks.size() == 1;
+    a.views = (ix->cfg.reserved & KMER_B200_FLAG_SHARED_POSITIONS) ? 1 : 0;
     a.lean_ok = a.single_k && ix->sigma == 4 && ix->elems[0].dev.shift == 0 && ix->elems[0].key_bytes == 4 && !d_present4 &&
                 !d_present_global && ix->cfg.profile < 2 && !std::getenv("KMER_B200_NO_LEAN");
     a.error_flag = p->d_flags;  // per search: a second search on the handle cannot clobber a pending one's flags
@@ -1186,7 +1223,7 @@ int search_finish(PendingSearch *p, const uint32_t *d_present4_global, SearchFla
     // sub-k lengths seen in this batch get an auxiliary k' = m element (kept for later batches); the write pass
     // below already reads through it, so those results come out sorted and skip the segment sort
     uint64_t aux_missing = want_aux;
-    if (flavor == kFlavorFull && want_aux && ix->cfg.reserved == 0) aux_missing = ensure_aux_elements(ix, want_aux);
+    if (flavor == kFlavorFull && want_aux && !(ix->cfg.reserved & KMER_B200_FLAG_NO_AUX)) aux_missing = ensure_aux_elements(ix, want_aux);
     if (flavor == kFlavorFull && total > 0) {
         if (dev_alloc(ix, &res->positions, total, false)) return bail(KMER_B200_ERR_OUT_OF_MEMORY);
         a.positions = res->positions;
@@ -1317,7 +1354,9 @@ int kmer_b200_save(kmer_b200_index *ix, const char *path) {
         const HostElement &he = ix->elems[i];
         FileElement fe{he.dev.k, he.dev.shift, he.key_bits, he.sort_passes, he.key_bytes, he.d_keys ? 1u : 0u, he.dev.n_kmers,
                        he.dev.dir_entries, he.dev.key_space};
+        if (he.view) fe = FileElement{he.dev.k, 0, he.key_bits, 0, he.key_bytes, 2u, 0, 0, 0};
         if (fwrite(&fe, sizeof(fe), 1, f) != 1) s = fail(KMER_B200_ERR_INVALID_ARGUMENT, "short write");
+        if (he.view) continue;
         if (s == 0 && he.d_keys) s = write_device_array(ix, f, he.d_keys, he.dev.n_kmers * he.key_bytes, h_buf);
         if (s == 0) s = write_device_array(ix, f, he.d_pos, he.dev.n_kmers * 4, h_buf);
         if (s == 0) s = write_device_array(ix, f, he.d_dir, he.dev.dir_entries * 4, h_buf);
@@ -1333,7 +1372,7 @@ int kmer_b200_load(const char *path, const kmer_b200_config *cfg_in, kmer_b200_i
     FILE *f = std::fopen(path, "rb");
     if (!f) return fail(KMER_B200_ERR_INVALID_ARGUMENT, std::string("cannot open ") + path);
     FileHeader h{};
-    if (fread(&h, sizeof(h), 1, f) != 1 || std::memcmp(h.magic, "KMERB200", 8) != 0 || h.version != kFileVersion ||
+    if (fread(&h, sizeof(h), 1, f) != 1 || std::memcmp(h.magic, "KMERB200", 8) != 0 || (h.version != kFileVersion && h.version != 2) ||
         h.n_ks == 0 || h.n_ks > (uint32_t)kb::kMaxElements) {
         std::fclose(f);
         return fail(KMER_B200_ERR_INVALID_ARGUMENT, "not a kmer_b200 index file (or an unknown version)");
@@ -1358,10 +1397,17 @@ int kmer_b200_load(const char *path, const kmer_b200_config *cfg_in, kmer_b200_i
         if (!h_buf) return fail(KMER_B200_ERR_OUT_OF_MEMORY, "pinned host allocation failed");
         int r = read_device_array(ix, f, ix->d_text, ix->text_words * 8, h_buf);
         ix->elems.resize(h.n_ks);
+        const uint32_t owner = (uint32_t)(std::max_element(h.ks, h.ks + h.n_ks) - h.ks);
+        uint32_t n_views = 0;
         for (uint32_t i = 0; r == 0 && i < h.n_ks; ++i) {
             HostElement &he = ix->elems[i];
             FileElement fe{};
-            if (fread(&fe, sizeof(fe), 1, f) != 1 || fe.k != h.ks[i] || (fe.key_bytes != 4 && fe.key_bytes != 8) ||
+            if (fread(&fe, sizeof(fe), 1, f) == 1 && fe.k == h.ks[i] && fe.has_keys == 2 && h.version >= 3 && i != owner) {
+                he.view = true;  // filled in from the owner below
+                ++n_views;
+                continue;
+            }
+            if (fe.k != h.ks[i] || (fe.key_bytes != 4 && fe.key_bytes != 8) ||
                 fe.n_kmers != h.n - fe.k + 1) {
                 r = fail(KMER_B200_ERR_INVALID_ARGUMENT, "corrupt element record");
                 break;
@@ -1398,12 +1444,20 @@ int kmer_b200_load(const char *path, const kmer_b200_config *cfg_in, kmer_b200_i
                 }
             }
             he.dev = kb::Element{fe.k, fe.shift, fe.n_kmers, fe.dir_entries, fe.key_space, he.d_dir, he.d_keys, he.d_pos,
-                                 fe.key_bytes, 0, 0, UINT64_MAX};
+                                 fe.key_bytes, fe.k, 0, UINT64_MAX, 1};
             he.bytes = fe.n_kmers * (4 + (fe.has_keys ? fe.key_bytes : 0)) + fe.dir_entries * 4;
             ix->max_avg_bucket = std::max(ix->max_avg_bucket,
                                           (double)fe.n_kmers / (double)std::min<uint64_t>(fe.key_space, fe.n_kmers));
         }
         pinned_put(h_buf, cap);
+        if (r == 0 && n_views) {
+            if (n_views + 1 != h.n_ks || ix->elems[owner].view) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "corrupt element record");
+            for (uint32_t i = 0; i < h.n_ks; ++i)
+                if (i != owner) make_view(ix->elems[i], ix->elems[owner], h.ks[i], h.sigma);
+            ix->cfg.reserved |= KMER_B200_FLAG_SHARED_POSITIONS | KMER_B200_FLAG_NO_AUX;
+        } else {
+            ix->cfg.reserved &= ~(uint32_t)KMER_B200_FLAG_SHARED_POSITIONS;  // what the file holds decides
+        }
         return r ? r : finalize_index(ix);
     };
     if (s == 0) s = load();
@@ -1571,6 +1625,8 @@ int kmer_b200_presence_batch_device(kmer_b200_index *ix, const uint8_t *d_q, con
     KB_NOT_ON_GROUP(ix);
     using namespace kb;
     if (!ix || !d_off || !d_present || present_format > 1) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad argument");
+    if (ix->cfg.reserved & KMER_B200_FLAG_SHARED_POSITIONS)
+        return fail(KMER_B200_ERR_UNSUPPORTED, "a shared-positions index is unsharded: no cross-shard presence exchange");
     if (mode == UINT32_MAX) mode = ix->cfg.mode;
     DeviceGuard guard(ix->device);
     std::lock_guard<std::mutex> lock(ix->mu);
@@ -2143,12 +2199,24 @@ int kmer_b200_element_info_get(const kmer_b200_index *ix, uint32_t e, kmer_b200_
     out->n_kmers = he.dev.n_kmers;
     out->directory_entries = he.dev.dir_entries;
     out->device_bytes = he.bytes;
+    if (he.view) {  // a prefix view of the largest k's arrays: it owns nothing
+        out->directory_shift = 0;
+        out->n_kmers = ix->n - he.dev.k + 1;
+        out->directory_entries = 0;
+    }
     return KMER_B200_OK;
+}
+
+static int reject_view(const kmer_b200_index *ix, uint32_t e) {
+    if (e < ix->elems.size() && ix->elems[e].view)
+        return fail(KMER_B200_ERR_UNSUPPORTED, "element is a view of the largest k's arrays (shared-positions index)");
+    return 0;
 }
 
 int kmer_b200_element_positions(kmer_b200_index *ix, uint32_t e, uint32_t *out, uint64_t cap) {
     ix = primary(ix);
     if (!ix || !out || e >= ix->elems.size()) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad element");
+    KB_TRY(reject_view(ix, e));
     DeviceGuard guard(ix->device);
     const uint64_t n = std::min<uint64_t>(cap, ix->elems[e].dev.n_kmers);
     KB_CUDA(cudaMemcpyAsync(out, ix->elems[e].d_pos, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ix->stream));
@@ -2159,6 +2227,7 @@ int kmer_b200_element_positions(kmer_b200_index *ix, uint32_t e, uint32_t *out, 
 int kmer_b200_element_hashes(kmer_b200_index *ix, uint32_t e, uint64_t *out, uint64_t cap) {
     ix = primary(ix);
     if (!ix || !out || e >= ix->elems.size()) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad element");
+    KB_TRY(reject_view(ix, e));
     DeviceGuard guard(ix->device);
     const HostElement &he = ix->elems[e];
     const uint64_t n = std::min<uint64_t>(cap, he.dev.n_kmers);
@@ -2189,6 +2258,7 @@ int kmer_b200_element_hashes(kmer_b200_index *ix, uint32_t e, uint64_t *out, uin
 int kmer_b200_element_part(const kmer_b200_index *ix, uint32_t e, kmer_b200_part *out) {
     ix = primary(ix);
     if (!ix || !out || e >= ix->ks.size()) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad element");
+    KB_TRY(reject_view(ix, e));
     const HostElement &he = ix->elems[e];
     if (he.dev.shift != 0) return fail(KMER_B200_ERR_UNSUPPORTED, "parts are exported from dense directories only");
     out->key_lo = he.dev.key_lo;
@@ -2204,6 +2274,7 @@ int kmer_b200_export_directory(kmer_b200_index *ix, uint32_t e, uint64_t base, u
     ix = primary(ix);
     if (!ix || !d_dst || e >= ix->ks.size() || n > ix->elems[e].dev.dir_entries)
         return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad argument");
+    KB_TRY(reject_view(ix, e));
     DeviceGuard guard(ix->device);
     if (n) add_base32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ix->stream>>>(ix->elems[e].d_dir, n, (uint32_t)base, d_dst);
     KB_CUDA(cudaGetLastError());
@@ -2213,6 +2284,7 @@ int kmer_b200_export_directory(kmer_b200_index *ix, uint32_t e, uint64_t base, u
 int kmer_b200_export_bucket_sizes(kmer_b200_index *ix, uint32_t e, uint8_t *d_sizes, uint64_t *n_large_out) {
     ix = primary(ix);
     if (!ix || !d_sizes || !n_large_out || e >= ix->ks.size()) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad argument");
+    KB_TRY(reject_view(ix, e));
     const HostElement &he = ix->elems[e];
     if (he.dev.shift != 0) return fail(KMER_B200_ERR_UNSUPPORTED, "bucket sizes are exported from dense directories only");
     DeviceGuard guard(ix->device);
@@ -2251,6 +2323,7 @@ int kmer_b200_directory_from_sizes(kmer_b200_index *ix, const uint8_t *d_sizes, 
 static int adopt_element_impl(kmer_b200_index *ix, uint32_t e, const uint32_t *d_positions, uint64_t n_kmers,
                               const uint32_t *d_directory, uint64_t directory_entries, int ownership) {
     if (!ix || !d_positions || !d_directory || e >= ix->ks.size()) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad argument");
+    if (ix->cfg.reserved & KMER_B200_FLAG_SHARED_POSITIONS) return fail(KMER_B200_ERR_UNSUPPORTED, "adopt: not on a shared-positions index");
     HostElement &he = ix->elems[e];
     if (n_kmers != ix->n - he.dev.k + 1 || directory_entries != he.dev.key_space + 1)
         return fail(KMER_B200_ERR_INVALID_ARGUMENT, "adopt: array sizes do not describe the whole index (n - k + 1 positions, sigma^k + 1 directory entries)");
@@ -2627,6 +2700,7 @@ uint64_t kmer_b200_presence_words(const kmer_b200_index *ix, uint32_t e) {
 
 int kmer_b200_presence_export(kmer_b200_index *ix, uint32_t e, uint64_t *d_bitmap) {
     if (!ix || !d_bitmap || e >= ix->ks.size() || !ix->replicas.empty()) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad argument");
+    KB_TRY(reject_view(ix, e));
     const HostElement &he = ix->elems[e];
     if (he.dev.shift != 0) return fail(KMER_B200_ERR_UNSUPPORTED, "presence bitmaps come from dense directories");
     DeviceGuard guard(ix->device);
@@ -2639,6 +2713,7 @@ int kmer_b200_presence_export(kmer_b200_index *ix, uint32_t e, uint64_t *d_bitma
 
 int kmer_b200_presence_attach(kmer_b200_index *ix, uint32_t e, const uint64_t *d_bitmap) {
     if (!ix || e >= ix->ks.size() || !ix->replicas.empty()) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad argument");
+    KB_TRY(reject_view(ix, e));
     DeviceGuard guard(ix->device);
     std::lock_guard<std::mutex> lock(ix->mu);
     ix->host_index.presence[e] = d_bitmap;  // caller-owned; null detaches
@@ -2892,6 +2967,8 @@ static int element_occupancy(kmer_b200_index *ix, HostElement &he) {
 int kmer_b200_plan_table(kmer_b200_index *ix, uint32_t mode, uint32_t m_lo, uint32_t m_hi, kmer_b200_plan_row *out) {
     ix = primary(ix);
     if (!ix || !out || m_lo == 0 || m_hi < m_lo) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad argument");
+    if (ix->cfg.reserved & KMER_B200_FLAG_SHARED_POSITIONS)
+        return fail(KMER_B200_ERR_UNSUPPORTED, "plan table: bucket statistics are per element; build the index without shared positions");
     if (mode == UINT32_MAX) mode = ix->cfg.mode;
     DeviceGuard guard(ix->device);
     std::lock_guard<std::mutex> lock(ix->mu);

@@ -110,9 +110,17 @@ struct Element {
     const void *keys;
     const uint32_t *pos;
     uint32_t key_bytes;  // 4 or 8
-    uint32_t pad_;
+    uint32_t k_phys;     // == k, except for a VIEW (below)
     uint64_t key_lo, key_hi;  // the element indexes the k-mers with hash in [key_lo, key_hi): a key-range part of a
                               // multi-GPU build, else [0, 2^64 - 1]; dir and keys are relative to key_lo
+    // Shared-positions multi-k index (thesis outlook 04_outlook_and_conclusion.tex:25-45): only the
+    // element with the largest k (k_phys) owns arrays; a smaller k is a VIEW of them -- dir / keys / pos / shift /
+    // n_kmers / key_space are the owner's, and the bucket of k-mer hash h is the slab of the sigma^(k_phys - k)
+    // consecutive k_phys-mer hashes that start with it: [h * width, (h + 1) * width). Inside a slab the positions are
+    // ordered by the following k_phys - k symbols, not by position, and the last k_phys - k k-mer starts of the text
+    // (where no k_phys-mer starts) are not in it: the search compares those "tail" starts directly and sorts what it
+    // reports. width == 1 for an ordinary element.
+    uint64_t width;
 };
 
 __device__ __forceinline__ uint64_t element_key(const Element &E, uint64_t i) {
@@ -122,7 +130,7 @@ __device__ __forceinline__ uint64_t element_key(const Element &E, uint64_t i) {
 // same, for elements that may not hold their hashes (dense directory): recomputed from the text at pos[i]
 __device__ __forceinline__ uint64_t element_key_or_text(const PackedText &T, const Element &E, uint64_t i) {
     if (E.keys != nullptr) return element_key(E, i);
-    return key_at(T.words, (uint64_t)gather32(E.pos + i), E.k, T.bits, T.sigma);
+    return key_at(T.words, (uint64_t)gather32(E.pos + i), E.k_phys, T.bits, T.sigma);
 }
 
 // ---- directory lookups (the reference's at(hash), kmer_index.hpp:76-84) ------------------------------------------------
@@ -151,7 +159,12 @@ __device__ __forceinline__ uint64_t lower_bound_key(const Element &E, uint64_t k
 }
 
 // the bucket of `key`: the reference's at(hash) (kmer_index.hpp:76-84)
+template <bool VIEWS = false>
 __device__ __forceinline__ Range bucket_of(const Element &E, uint64_t key) {
+    if (VIEWS && E.width != 1) {  // a view: the slab of the owner's hashes that start with `key` (tail starts: see Element)
+        const uint64_t lo = lower_bound_key(E, key * E.width);
+        return Range{lo, lower_bound_key(E, (key + 1) * E.width) - lo};
+    }
     if (key < E.key_lo || key >= E.key_hi) return Range{0, 0};  // another part's hash
     key -= E.key_lo;
     const uint64_t t = key >> E.shift;

@@ -55,7 +55,9 @@ __device__ __forceinline__ bool match_span(const PackedText &T, const uint64_t *
 constexpr uint32_t kHeavyCandidates = 2048;
 
 // HEAVY = true: the second launch (G = 32) over the heavy list; never hands a query off again.
-template <int PASS_, int G, bool HEAVY, bool SINGLE>
+// VIEWS = true: elements may be prefix views of the largest k's arrays (shared-positions index, Element::width); compiled
+// only into the warp-per-query kernels below (search_views_kernel), so the ordinary variants pay nothing for it.
+template <int PASS_, int G, bool HEAVY, bool SINGLE, bool VIEWS = false>
 __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t q, uint64_t *smem_q) {
     // count pass variants: + sum of the gathered sectors; + whole-text rule left for the epilogue (sharded)
     constexpr bool kAccount = PASS_ == kPassCountAccount || PASS_ == kPassCountDeferredAccount;
@@ -293,7 +295,7 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
         return;
     }
     Range seed{0, 0};       // candidate list: positions pos[seed.lo .. +cnt) of element seed_e, match start = pos - seed_d
-    uint32_t seed_e = e0, seed_d = 0;
+    uint32_t seed_e = e0, seed_d = 0, seed_o = 0;  // ... and the seed part sits at query offset seed_o
     bool all_present = true;
     uint64_t present_mask = 0;
     // Every plan goes through the same lookup loop -- the lanes of a warp hold queries of different plans, and a
@@ -319,6 +321,8 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
             Range rg{0, 0};
             uint32_t e = e_first, o = j * k0, d = j * k0;
             bool foreign = false;
+            uint32_t tail_slots = 0;  // views (Element::width): k-mer starts that are compared directly, and whether
+            bool tail_hit = false;    // the part occurs at one of them
             if (valid) {
                 if (from_list && need_presence) {  // `last_k = current_k` is not cumulative, kmer_index.hpp:526
                     e = S[j];
@@ -334,11 +338,16 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
                     foreign = true;
                     rg.cnt = ((gather64(pb + (key >> 6)) >> (key & 63)) & 1ull) ? 1 : 0;
                 } else {
-                    rg = bucket_of(E, key);
+                    rg = bucket_of<VIEWS>(E, key);
+                    if (VIEWS && E.width != 1) {
+                        tail_slots = E.k_phys - E.k;
+                        for (uint32_t t = 0; rg.cnt == 0 && !tail_hit && t < tail_slots; ++t)
+                            tail_hit = match_span(T, qw, T.n - E.k_phys + 1 + t, o, E.k);
+                    }
                 }
                 if (kAccount) n_gather += 1 + (E.shift ? 1 : 0);
             }
-            const uint32_t here = GBALLOT(valid && rg.cnt != 0);
+            const uint32_t here = GBALLOT(valid && (rg.cnt != 0 || tail_hit));
             if (base < 64) present_mask |= (uint64_t)here << base;
             const uint32_t want = GBALLOT(valid);
             if (need_presence && here != want) {
@@ -349,7 +358,7 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
             // seed from the shortest bucket among the parts whose position the plan constrains:
             // all of them, except the middle parts of the kmer_index.hpp:314 defect
             const bool seedable = valid && !foreign && (kind != kBuggySingle || j == 0 || j + 1 == nparts);
-            uint64_t c = seedable ? rg.cnt : ~0ull;
+            uint64_t c = seedable ? rg.cnt + tail_slots : ~0ull;
             uint32_t who = gl;
             for (int off = G >> 1; off > 0; off >>= 1) {
                 const uint64_t oc = __shfl_xor_sync(gmask, c, off, G);
@@ -362,9 +371,10 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
             if (c < best_cnt) {
                 best_cnt = c;
                 seed.lo = GSHFL(rg.lo, who);
-                seed.cnt = c;
+                seed.cnt = VIEWS ? GSHFL(rg.cnt, who) : c;
                 seed_e = GSHFL(e, who);
                 seed_d = GSHFL(d, who);
+                if (VIEWS) seed_o = GSHFL(o, who);
             }
         }
     }
@@ -448,7 +458,8 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
     if (kind == kSubK) {
         // get_position_for_all_kmer_with_prefix (kmer_index.hpp:115-148): the buckets of all hashes in
         // [prefix_hash, prefix_hash + sigma^(k-m)) are one contiguous slab of the sorted position array
-        const uint64_t width = ix.pow_sigma[k0 - m];
+        const uint32_t kp = VIEWS ? E0.k_phys : k0;  // a view enumerates the owner's slab: the same positions, the same tail rule
+        const uint64_t width = ix.pow_sigma[kp - m];
         const uint64_t lo_key = key_at(qw, 0, m, T.bits, T.sigma) * width;
         const uint64_t slo = lower_bound_key(E0, lo_key);
         const uint64_t shi = lower_bound_key(E0, lo_key + width);
@@ -471,10 +482,10 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
             n_hits += __popc(b);
         }
         // check_last_kmer (kmer_index.hpp:90-112): starts in the last k-1 positions, where no k-mer starts
-        for (uint32_t t0 = 0; t0 < k0 - m; t0 += G) {
+        for (uint32_t t0 = 0; t0 < kp - m; t0 += G) {
             const uint32_t t = t0 + gl;
-            const uint64_t p = T.n - k0 + 1 + t;
-            const bool ok = t < k0 - m && p < ix.owned && match_span(T, qw, p, 0, m);
+            const uint64_t p = T.n - kp + 1 + t;
+            const bool ok = t < kp - m && p < ix.owned && match_span(T, qw, p, 0, m);
             const uint32_t b = GBALLOT(ok);
             if (PASS == kPassWrite && ok)
                 a.positions[out_base + n_hits + __popc(b & lt_mask)] = (uint32_t)p + (uint32_t)ix.global_base;
@@ -493,19 +504,20 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
                     break;
                 }
             }
-            if (ix.elem[e].k > k0) {
+            if (ix.elem[e].k > k0 && (!VIEWS || ix.elem[e].width == 1)) {
                 Range alt{0, 0};
                 if (gl == 0) {
                     const Element &E = ix.elem[e];
-                    alt = bucket_of(E, key_at(qw, (uint64_t)last, E.k, T.bits, T.sigma));
+                    alt = bucket_of<VIEWS>(E, key_at(qw, (uint64_t)last, E.k, T.bits, T.sigma));
                     if (kAccount) n_gather += 1 + (E.shift ? 1 : 0);
                 }
                 alt.lo = GSHFL(alt.lo, 0);
                 alt.cnt = GSHFL(alt.cnt, 0);
-                if (alt.cnt < seed.cnt) {
+                if (alt.cnt < seed.cnt + (VIEWS ? ix.elem[seed_e].k_phys - ix.elem[seed_e].k : 0u)) {
                     seed = alt;
                     seed_e = e;
                     seed_d = last;
+                    if (VIEWS) seed_o = last;
                 }
             }
         }
@@ -513,6 +525,10 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
         const uint32_t ks = Es.k;
         const uint32_t kf = from_list ? ix.elem[S[0]].k : k0;  // k of part 0 (text stride of the multi-k defect)
         const uint32_t n_spans = kind == kExact ? 0u : (kind == kContig ? 1u : (kind == kBuggySingle ? P : nparts));
+        // a view's bucket: slab entries first, then the tail starts (all beyond every slab entry), compared directly
+        const uint32_t tail_slots = VIEWS ? Es.k_phys - ks : 0u;
+        const uint64_t n_cand = seed.cnt + tail_slots;
+        unsorted = VIEWS && Es.width != 1 && seed.cnt > 1;
         bool count_by_range = PASS != kPassWrite && kind == kExact && ix.owned == T.n;
         HAND_OFF_IF_HEAVY(seed.cnt)  // same decision in the count and the write pass
         if (count_by_range) n_hits = seed.cnt;
@@ -530,15 +546,23 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
                 for (int j = 0; j < 8; ++j) dst[c + j * G] = v[j] + gb;
             }
             for (; c < seed.cnt; c += G) dst[c] = src[c] + gb;
-            count_by_range = true;  // skips the generic loop below
+            count_by_range = true;  // the generic loop below starts behind the slab
+            n_hits = seed.cnt;
         }
-        for (uint64_t c0 = 0; c0 < seed.cnt && !count_by_range; c0 += G) {
+        for (uint64_t c0 = count_by_range ? seed.cnt : 0; c0 < n_cand; c0 += G) {
             const uint64_t c = c0 + gl;
             uint32_t p = 0;
             bool ok = false;
-            if (c < seed.cnt) {
-                const uint32_t at = gather32(Es.pos + seed.lo + c);
-                ok = at >= seed_d;
+            if (c < n_cand) {
+                uint32_t at;
+                if (!VIEWS || c < seed.cnt) {
+                    at = gather32(Es.pos + seed.lo + c);
+                    ok = true;
+                } else {
+                    at = (uint32_t)(T.n - Es.k_phys + 1 + (c - seed.cnt));
+                    ok = match_span(T, qw, at, seed_o, ks);
+                }
+                ok = ok && at >= seed_d;
                 p = at - seed_d;
                 ok = ok && (uint64_t)p < ix.owned;
                 if (kAccount && (((seed.lo + c) & 7) == 0 || c == 0)) ++n_gather;
@@ -631,6 +655,37 @@ __global__ void __launch_bounds__(kSearchThreads) search_heavy_kernel(const Sear
     }
 }
 
+// Shared-positions index: one warp per query (slabs are long), every pass of the unsharded search.
+template <int PASS>
+__global__ void __launch_bounds__(kSearchThreads) search_views_kernel(const SearchArgs a) {
+    constexpr int kGroups = kSearchThreads / 32;
+    extern __shared__ uint64_t smem_q[];
+    if (PASS == kPassWrite && a.hits != nullptr) {
+        const uint32_t n_listed = a.hits[0];
+        for (uint64_t i = (uint64_t)blockIdx.x * kGroups + threadIdx.x / 32; i < n_listed; i += (uint64_t)gridDim.x * kGroups) {
+            search_query<PASS, 32, false, false, true>(a, (uint64_t)a.hits[1 + i], smem_q);
+            __syncwarp();
+        }
+    } else {
+        for (uint64_t q = (uint64_t)blockIdx.x * kGroups + threadIdx.x / 32; q < a.n_queries; q += (uint64_t)gridDim.x * kGroups) {
+            search_query<PASS, 32, false, false, true>(a, q, smem_q);
+            __syncwarp();
+        }
+    }
+}
+
+template <int PASS>
+static void launch_search_views(const SearchArgs &args, cudaStream_t stream) {
+    SearchArgs h = args;
+    h.group = 32;
+    h.q_words = search_q_words(32, args.bits, args.max_len);
+    constexpr int kGroups = kSearchThreads / 32;
+    const size_t smem = (size_t)kGroups * h.q_words * sizeof(uint64_t);
+    const uint64_t blocks = std::min<uint64_t>((args.n_queries + kGroups - 1) / kGroups, (uint64_t)device_sm_count() * 16);
+    cudaFuncSetAttribute(search_views_kernel<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    search_views_kernel<PASS><<<(unsigned)blocks, kSearchThreads, smem, stream>>>(h);
+}
+
 template <int PASS, int G, bool SINGLE>
 static void launch_search_pgs(const SearchArgs &args, cudaStream_t stream) {
     constexpr int kGroups = kSearchThreads / G;
@@ -703,6 +758,12 @@ bool launch_search_count_lean(const SearchArgs &a, cudaStream_t stream);  // sea
 
 void launch_search(const SearchArgs &args, SearchPass pass, cudaStream_t stream) {
     if (args.n_queries == 0) return;
+    if (args.views) {
+        if (pass == kPassCount) launch_search_views<kPassCount>(args, stream);
+        if (pass == kPassCountAccount) launch_search_views<kPassCountAccount>(args, stream);
+        if (pass == kPassWrite) launch_search_views<kPassWrite>(args, stream);
+        return;  // the sharded passes do not exist for such an index (capi.cu refuses the combination)
+    }
     if (pass == kPassCount && launch_search_count_lean(args, stream)) {
         // the lean kernel answered what it covers; the queries it listed (prefix slabs, long candidate lists) go to the
         // general kernel's warp-per-query launch, as after the general count pass

@@ -140,6 +140,18 @@ int main()
             std::printf("multi-device index over %d GPUs: ok\n", n_dev);
         }
     }
+    // shared-positions index (one position array for all ks): the same answers, also at the end of the text
+    {
+        kmer::kmer_index<alphabet_t, uint32_t, 10, 11, 12> shared(text, kmer::shared_positions);
+        std::vector<std::vector<alphabet_t>> qs;
+        for (int i = 0; i < 2000; ++i) {
+            size_t m = 5 + i % 30, start = next_u32() % (text.size() - m + 1);
+            qs.emplace_back(text.begin() + start, text.begin() + start + m);
+        }
+        for (size_t m = 5; m < 30; ++m) qs.emplace_back(text.end() - m, text.end());
+        auto a = shared.search_batch(qs), b = multi.search_batch(qs);
+        REQUIRE(a.offsets == b.offsets && a.positions == b.positions && a.status == b.status);
+    }
     // other alphabets
     {
         std::vector<kmer::dna15> t15(50000);
