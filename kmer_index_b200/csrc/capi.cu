@@ -1230,7 +1230,8 @@ int search_finish(PendingSearch *p, const uint32_t *d_present4_global, SearchFla
         ix->prof.begin(K_SEARCH_WRITE, 0);
         launch_search(a, kPassWrite, st);
         ix->prof.end();
-        if (flags[1] != 0 && aux_missing != 0) {
+        // results written in slab order: sub-k lengths without an auxiliary element, anything seeded from a view
+        if (flags[1] != 0 && (aux_missing != 0 || a.views)) {
             uint32_t *d_tmp = nullptr;
             if (dev_alloc(ix, &d_tmp, total, false)) return bail(KMER_B200_ERR_OUT_OF_MEMORY);
             const uint32_t key_bits = bit_length(ix->cfg.shard_begin + ix->n);

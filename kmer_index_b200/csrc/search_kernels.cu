@@ -504,7 +504,7 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
                     break;
                 }
             }
-            if (ix.elem[e].k > k0 && (!VIEWS || ix.elem[e].width == 1)) {
+            if (ix.elem[e].k > k0) {
                 Range alt{0, 0};
                 if (gl == 0) {
                     const Element &E = ix.elem[e];
@@ -513,7 +513,10 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
                 }
                 alt.lo = GSHFL(alt.lo, 0);
                 alt.cnt = GSHFL(alt.cnt, 0);
-                if (alt.cnt < seed.cnt + (VIEWS ? ix.elem[seed_e].k_phys - ix.elem[seed_e].k : 0u)) {
+                // (views: a candidate list is the slab plus the tail starts that are compared directly)
+                const uint32_t alt_tail = VIEWS ? ix.elem[e].k_phys - ix.elem[e].k : 0u;
+                const uint32_t cur_tail = VIEWS ? ix.elem[seed_e].k_phys - ix.elem[seed_e].k : 0u;
+                if (alt.cnt + alt_tail < seed.cnt + cur_tail) {
                     seed = alt;
                     seed_e = e;
                     seed_d = last;

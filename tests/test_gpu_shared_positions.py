@@ -103,6 +103,17 @@ def test_shared_positions_correct_mode_matches_ground_truth(kb, oracle_mod, sigm
     assert_results_equal(got, oracle_mod.Oracle.truth(text, q, off), label=f"correct shared {ks}")
 
 
+def test_shared_positions_exact_lengths_only(kb, oracle_mod):
+    """A batch with nothing but lengths that ARE one of the ks: whole slabs of a view, sorted per query."""
+    from kmer_index_b200 import synth
+    n, ks = 1_500_000, [5, 7, 9, 11, 13]
+    text = synth.random_text(n, 4, 41)
+    with kb.KmerIndex(text, 4, ks, shared_positions=True) as ix, oracle_mod.Oracle(text, 4, ks) as o:
+        for m in ks:
+            q, off = synth.stress_queries(text, 500, m, m, 4, 50 + m)
+            assert_results_equal(ix.search_batch(q, off).as_tuple(), o.search(q, off), label=f"exact m={m}")
+
+
 def test_shared_positions_heavy_slabs_and_repetitive_text(kb, oracle_mod):
     """Low-entropy text: slabs of tens of thousands of positions, results that are whole slabs in non-position order."""
     from kmer_index_b200 import synth
@@ -125,7 +136,7 @@ def test_shared_positions_memory_and_save_load(kb, oracle_mod, tmp_path):
         per_k = sum(plain.element_info(e).device_bytes for e in range(len(ks)))
         one = sum(shared.element_info(e).device_bytes for e in range(len(ks)))
         assert one == plain.element_info(ks.index(13)).device_bytes
-        assert one * 3 < per_k          # five position arrays and five directories against one of each
+        assert one * 2 < per_k          # five position arrays and five directories against one of each
         shared.save(path)
         with pytest.raises(kb.KmerB200Error):
             shared.element_arrays(0)    # a view owns no arrays
