@@ -381,6 +381,10 @@ def run_ours(args, wl):
             ev[2].record(stream)
             torch.cuda.synchronize()
             d2h = (Ql + 1) * 8 + Ql + 4 * int(res.positions.size)
+            if not routed and (world == 1 or replicated):
+                # the plain C-ABI host call: the library reports what it actually put on the link (16-bit lengths
+                # instead of offsets, packed ranks for pageable input)
+                abi_h2d, abi_d2h = ix.last_search_transfer()
             res.free()
             ix.close()
             if it >= min(args.warmup, 1):
@@ -388,6 +392,8 @@ def run_ours(args, wl):
                 es.append(ev[1].elapsed_time(ev[2]))
         # position-range: every rank uploads 1/world of the query batch (then NCCL all-gather); replicated: its own slice
         h2d_q = (n_sym + (Ql + 1) * 8) // (1 if parted else world)
+        if not routed and (world == 1 or replicated):
+            h2d_q, d2h = abi_h2d, abi_d2h
         e2e = {"build_ms": float(np.mean(eb)), "search_ms": float(np.mean(es)), "h2d": n_local + h2d_q, "d2h": d2h}
         del h_text, h_q, h_off
 

@@ -360,6 +360,9 @@ uint64_t kmer_b200_device_bytes(const kmer_b200_index *index);
 /* profile = 2 only: number of 32-byte sectors at data-dependent addresses (directory slots, bucket entries,
    text windows) the last search had to gather -- the algorithmic work of the search kernel. */
 uint64_t kmer_b200_last_search_gathers(const kmer_b200_index *index);
+/* Bytes the last kmer_b200_search_batch / _ptrs / _text on this handle moved over PCIe: host to device (ranks as they are
+   or packed, offsets or 16-bit lengths -- whichever the call chose) and device to host (offsets, status, positions). */
+void kmer_b200_last_search_transfer(const kmer_b200_index *index, uint64_t *h2d_bytes, uint64_t *d2h_bytes);
 /* Calibration of the random-gather ceiling: n_gathers independent 8-byte reads at random addresses of a
    table_bytes table (>> L2); *ms_out = device time. sectors/s = n_gathers / time. */
 int kmer_b200_gather_probe(uint64_t table_bytes, uint64_t n_gathers, void *stream, double *ms_out);

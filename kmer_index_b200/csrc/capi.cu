@@ -208,6 +208,7 @@ struct kmer_b200_index {
     uint64_t *h_pinned = nullptr;    // small pinned scratch: [0] total hits, [1] flags, [2] max len, [3] gathers
     unsigned long long *d_gathers = nullptr;  // profile mode: sectors gathered by the last search
     uint64_t last_gathers = 0;
+    uint64_t last_h2d = 0, last_d2h = 0;  // bytes the last host-buffer search moved over PCIe (kmer_b200_last_search_transfer)
     uint64_t device_bytes = 0;
     bool reaches_end = true;  // the local slice ends at the end of the whole text
     bool sharded = false;
@@ -1661,6 +1662,11 @@ __global__ void __launch_bounds__(256) add_base_kernel(uint64_t *__restrict__ v,
     if (i < n) v[i] += base;
 }
 
+__global__ void __launch_bounds__(256) widen_lens_kernel(const uint16_t *__restrict__ lens, uint64_t n, uint64_t *__restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = lens[i];
+}
+
 // Large host batches are pipelined in chunks of queries: the H2D copy of chunk c+1 (copy engine), the search of
 // chunk c (SMs) and the D2H copy of chunk c-1's offsets and status (the other copy engine) run concurrently, so
 // the call costs about as much as moving its bytes over PCIe once. Position lists stay on the device until the
@@ -1687,6 +1693,15 @@ static int search_batch_host_pipelined(kmer_b200_index *ix, const uint8_t *q_ran
     uint8_t *d_q = nullptr;
     uint64_t *d_off = nullptr;
     unsigned long long *d_max = nullptr;
+    // The offsets cross the link as 16-bit lengths (2 bytes per query instead of 8; config 5: 0.6 of 4.8 GB less) and are
+    // rebuilt on the device by a prefix sum. The host threads compute chunk c + 1's lengths while chunk c is in flight;
+    // a chunk with a query of 65 536 symbols or more sends its offsets as they are.
+    const bool lens16 = std::getenv("KMER_B200_NO_LENS16") == nullptr;
+    uint16_t *h_lens = nullptr, *d_lens = nullptr;
+    size_t h_lens_cap = 0;
+    uint64_t *d_scan = nullptr;
+    uint64_t chunk_max[kChunks] = {};
+    bool chunk_lens[kChunks] = {};
     kmer_b200_result *chunk_res[kChunks] = {};
     cudaEvent_t ev_in[kChunks] = {}, ev_done[kChunks] = {};
     kmer_b200_result *res = nullptr;
@@ -1702,11 +1717,21 @@ static int search_batch_host_pipelined(kmer_b200_index *ix, const uint8_t *q_ran
         dev_free(ix, d_q);
         dev_free(ix, d_off);
         dev_free(ix, d_max);
+        dev_free(ix, d_lens);
+        dev_free(ix, d_scan);
+        if (h_lens) pinned_put(h_lens, h_lens_cap);
         if (code != 0 && res) kmer_b200_result_free(res);
         return code;
     };
-    if (dev_alloc(ix, &d_q, n_sym, false) || dev_alloc(ix, &d_off, Q + 1, false) || dev_alloc(ix, &d_max, kChunks, false))
+    const uint64_t per = (Q + kChunks - 1) / kChunks;
+    // every chunk owns per + 1 offsets (its last entry is not shared with the next chunk's first)
+    if (dev_alloc(ix, &d_q, n_sym, false) || dev_alloc(ix, &d_off, Q + 1 + kChunks, false) || dev_alloc(ix, &d_max, kChunks, false))
         return cleanup(KMER_B200_ERR_OUT_OF_MEMORY);
+    if (lens16) {
+        h_lens = (uint16_t *)pinned_get(Q * sizeof(uint16_t), &h_lens_cap);
+        if (!h_lens || dev_alloc(ix, &d_lens, Q, false) || dev_alloc(ix, &d_scan, kb::offsets_scan_blocks(per) + 1, false))
+            return cleanup(fail(KMER_B200_ERR_OUT_OF_MEMORY, "allocation for the query lengths failed"));
+    }
     // the allocations above are ordered on `st`; the copy streams must not touch them earlier
     cudaEvent_t ev_alloc;
     cudaEventCreateWithFlags(&ev_alloc, cudaEventDisableTiming);
@@ -1726,16 +1751,27 @@ static int search_batch_host_pipelined(kmer_b200_index *ix, const uint8_t *q_ran
     if (!res->offsets || !res->status) return cleanup(fail(KMER_B200_ERR_OUT_OF_MEMORY, "pinned host allocation failed"));
 
     // enqueue every chunk's H2D now; the copy engine works through them while the chunks are searched
-    const uint64_t per = (Q + kChunks - 1) / kChunks;
     uint64_t c0[kChunks + 1];
+    uint64_t h2d = n_sym;
     for (int c = 0; c <= kChunks; ++c) c0[c] = std::min<uint64_t>((uint64_t)c * per, Q);
     for (int c = 0; c < kChunks; ++c) {
         const uint64_t qa = c0[c], qb = c0[c + 1];
         cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming);
         if (qb > qa) {
-            // offsets [qa, qb] (the shared boundary entry is copied by both neighbours: same value)
-            cudaMemcpyAsync(d_off + qa, q_offsets + qa, (qb - qa + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ix->copy_in);
+            if (lens16) {
+                kb::HostPool &pool = kb::HostPool::instance();
+                const unsigned T = std::max(1u, std::min(pool.threads(), 64u));
+                uint64_t part_max[64] = {};
+                pool.run(T, [&](unsigned t) { part_max[t] = kb::query_lengths_host(q_offsets, qa, qb, h_lens + qa, t, T); });
+                for (unsigned t = 0; t < T; ++t) chunk_max[c] = std::max(chunk_max[c], part_max[t]);
+                chunk_lens[c] = chunk_max[c] < 65536;
+            }
+            if (chunk_lens[c])
+                cudaMemcpyAsync(d_lens + qa, h_lens + qa, (qb - qa) * sizeof(uint16_t), cudaMemcpyHostToDevice, ix->copy_in);
+            else
+                cudaMemcpyAsync(d_off + qa + c, q_offsets + qa, (qb - qa + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ix->copy_in);
+            h2d += chunk_lens[c] ? (qb - qa) * sizeof(uint16_t) : (qb - qa + 1) * sizeof(uint64_t);
             const uint64_t s0 = q_offsets[qa] - q_offsets[0], s1 = q_offsets[qb] - q_offsets[0];
             if (s1 > s0) cudaMemcpyAsync(d_q + s0, q_ranks + q_offsets[qa], s1 - s0, cudaMemcpyHostToDevice, ix->copy_in);
         }
@@ -1746,12 +1782,21 @@ static int search_batch_host_pipelined(kmer_b200_index *ix, const uint8_t *q_ran
         const uint64_t qa = c0[c], qb = c0[c + 1], Qc = qb - qa;
         if (Qc == 0) continue;
         cudaStreamWaitEvent(st, ev_in[c], 0);
-        max_len_kernel<<<(unsigned)std::min<uint64_t>((Qc + 255) / 256, (uint64_t)kb::device_sm_count() * 8), 256, 0, st>>>(d_off + qa, Qc, d_max + c);
-        cudaMemcpyAsync(&ix->h_pinned[2], d_max + c, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
-        cudaError_t e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) return cleanup(fail(KMER_B200_ERR_CUDA, std::string("search (H2D): ") + cudaGetErrorString(e)));
-        const uint64_t max_len = ix->h_pinned[2];
-        int s = search_device_impl(ix, d_q - q_offsets[0], d_off + qa, Qc, max_len, mode, nullptr, 0, kFlavorFull, &chunk_res[c]);
+        uint64_t *d_off_c = d_off + qa + c;
+        uint64_t max_len = chunk_max[c];
+        if (chunk_lens[c]) {
+            // lengths -> offsets: widen, exclusive scan (the total lands in entry Qc), shift to the batch's numbering
+            widen_lens_kernel<<<(unsigned)((Qc + 255) / 256), 256, 0, st>>>(d_lens + qa, Qc, d_off_c);
+            kb::launch_offsets_scan(d_off_c, Qc, d_scan, st);
+            add_base_kernel<<<(unsigned)((Qc + 1 + 255) / 256), 256, 0, st>>>(d_off_c, Qc + 1, q_offsets[qa]);
+        } else {
+            max_len_kernel<<<(unsigned)std::min<uint64_t>((Qc + 255) / 256, (uint64_t)kb::device_sm_count() * 8), 256, 0, st>>>(d_off_c, Qc, d_max + c);
+            cudaMemcpyAsync(&ix->h_pinned[2], d_max + c, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
+            cudaError_t e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) return cleanup(fail(KMER_B200_ERR_CUDA, std::string("search (H2D): ") + cudaGetErrorString(e)));
+            max_len = ix->h_pinned[2];
+        }
+        int s = search_device_impl(ix, d_q - q_offsets[0], d_off_c, Qc, max_len, mode, nullptr, 0, kFlavorFull, &chunk_res[c]);
         if (s != 0) return cleanup(s);
         kmer_b200_result *cr = chunk_res[c];
         if (base) add_base_kernel<<<(unsigned)((Qc + 1 + 255) / 256), 256, 0, st>>>(cr->offsets, Qc + 1, base);
@@ -1782,6 +1827,8 @@ static int search_batch_host_pipelined(kmer_b200_index *ix, const uint8_t *q_ran
     cudaError_t e = cudaStreamSynchronize(ix->copy_out);
     res->offsets[Q] = base;
     if (e != cudaSuccess) return cleanup(fail(KMER_B200_ERR_CUDA, std::string("search (D2H): ") + cudaGetErrorString(e)));
+    ix->last_h2d = h2d;
+    ix->last_d2h = Q * 9 + pos_bytes;
     *out = res;
     return cleanup(0);
 }
@@ -1794,6 +1841,7 @@ static int search_batch_host_pipelined(kmer_b200_index *ix, const uint8_t *q_ran
 static int search_batch_host_packed(kmer_b200_index *ix, const uint8_t *q_ranks, const uint64_t *q_offsets, uint64_t Q,
                                     uint32_t mode, kmer_b200_result **out) {
     constexpr int kChunks = 16, kRing = 3;
+    uint64_t h2d = 0;
     cudaStream_t st = ix->stream;
     if (!ix->copy_in) {
         static std::mutex mu;
@@ -1912,6 +1960,7 @@ static int search_batch_host_packed(kmer_b200_index *ix, const uint8_t *q_ranks,
         cudaEventDestroy(ev_alloc);
         cudaMemcpyAsync(d_words[c], h_words[slot], Qc * stride[c] * sizeof(uint64_t), cudaMemcpyHostToDevice, ix->copy_in);
         cudaMemcpyAsync(d_lens[c], h_lens[slot], Qc * sizeof(uint16_t), cudaMemcpyHostToDevice, ix->copy_in);
+        h2d += Qc * stride[c] * sizeof(uint64_t) + Qc * sizeof(uint16_t);
         cudaEventRecord(ev_in[c], ix->copy_in);
         cudaEventRecord(ev_slot[slot], ix->copy_in);
         return 0;
@@ -1972,6 +2021,8 @@ static int search_batch_host_packed(kmer_b200_index *ix, const uint8_t *q_ranks,
     cudaError_t e = cudaStreamSynchronize(ix->copy_out);
     res->offsets[Q] = base;
     if (e != cudaSuccess) return cleanup(fail(KMER_B200_ERR_CUDA, std::string("search (D2H): ") + cudaGetErrorString(e)));
+    ix->last_h2d = h2d;
+    ix->last_d2h = Q * 9 + base * sizeof(uint32_t);
     *out = res;
     return cleanup(0);
 }
@@ -2098,6 +2149,8 @@ static int search_batch_host(kmer_b200_index *ix, const uint8_t *q_ranks, const 
         kmer_b200_result_free(res);
         return fail(KMER_B200_ERR_CUDA, std::string("search (D2H): ") + cudaGetErrorString(e));
     }
+    ix->last_h2d = n_sym + (Q + 1) * sizeof(uint64_t);
+    ix->last_d2h = (Q + 1) * sizeof(uint64_t) + Q + res->n_positions * sizeof(uint32_t);
     *out = res;
     return KMER_B200_OK;
 }
@@ -3116,6 +3169,17 @@ uint64_t kmer_b200_device_bytes(const kmer_b200_index *ix) {
 }
 
 uint64_t kmer_b200_last_search_gathers(const kmer_b200_index *ix) { return ix ? primary(ix)->last_gathers : 0; }
+
+void kmer_b200_last_search_transfer(const kmer_b200_index *ix, uint64_t *h2d_bytes, uint64_t *d2h_bytes) {
+    uint64_t in = 0, back = 0;
+    if (ix && !ix->replicas.empty()) {
+        for (const kmer_b200_index *r : ix->replicas) in += r->last_h2d, back += r->last_d2h;
+    } else if (ix) {
+        in = ix->last_h2d, back = ix->last_d2h;
+    }
+    if (h2d_bytes) *h2d_bytes = in;
+    if (d2h_bytes) *d2h_bytes = back;
+}
 
 int kmer_b200_gather_probe(uint64_t table_bytes, uint64_t n_gathers, void *stream, double *ms_out) {
     if (!ms_out || table_bytes < 4096 || n_gathers == 0) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad probe arguments");

@@ -90,11 +90,24 @@ def test_pipelined_host_batch_equals_plain(kb):
         os.environ["KMER_B200_HOST_PACK"] = "0"
         try:
             piped = ix.search_batch(q, off).as_tuple()       # 1-byte ranks over PCIe, chunks pipelined
+            # the offsets crossed the link as 16-bit lengths
+            assert ix.last_search_transfer()[0] == q.size + 2 * (off.size - 1)
+            os.environ["KMER_B200_NO_LENS16"] = "1"
+            piped_off = ix.search_batch(q, off).as_tuple()   # ... and as they are
+            assert ix.last_search_transfer()[0] == q.size + 8 * (off.size - 1 + 8)
+            del os.environ["KMER_B200_NO_LENS16"]
+            # a query of 65 536 symbols or more: its chunk sends offsets, the other chunks lengths (CORRECT mode: the
+            # reference's table stops at 10 000 symbols)
+            q_long = np.concatenate([q, text[1000:71_000]])
+            off_long = np.concatenate([off, [off[-1] + 70_000]]).astype(np.uint64)
+            piped_long = ix.search_batch(q_long, off_long, mode=kb.MODE_CORRECT).as_tuple()
         finally:
-            del os.environ["KMER_B200_HOST_PACK"]
+            os.environ.pop("KMER_B200_HOST_PACK", None)
+            os.environ.pop("KMER_B200_NO_LENS16", None)
         os.environ["KMER_B200_NO_PIPELINE"] = "1"
         try:
             plain = ix.search_batch(q, off).as_tuple()
+            plain_long = ix.search_batch(q_long, off_long, mode=kb.MODE_CORRECT).as_tuple()
         finally:
             del os.environ["KMER_B200_NO_PIPELINE"]
         bad = q.copy()
@@ -104,6 +117,9 @@ def test_pipelined_host_batch_equals_plain(kb):
         assert e.value.code == -4
     assert piped[1].size > 500_000
     assert_results_equal(piped, plain, label="pipelined vs plain")
+    assert_results_equal(piped_off, plain, label="pipelined (offsets as they are) vs plain")
+    assert plain_long[0][-1] - plain_long[0][-2] == 1          # the long query occurs once, at position 1000
+    assert_results_equal(piped_long, plain_long, label="pipelined with a 70 000-symbol query vs plain")
     assert_results_equal(packed, plain, label="host-packed pipeline vs plain")
 
 
