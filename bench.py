@@ -277,10 +277,13 @@ def run_ours(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
+    assemble_marks = []   # (label, event) marks of the last replicated assembly
+
     def finish_build(ix):
         """the cross-GPU part of the build: all-gather of the parts (replicated) or of the presence bitmap (routed)"""
         if replicated:
-            sharded.assemble_replicated(ix, world, rank, dist, dev)
+            assemble_marks.clear()
+            sharded.assemble_replicated(ix, world, rank, dist, dev, timing=assemble_marks)
         elif routed:
             sharded.share_presence(ix, world, rank, dist, dev)
 
@@ -328,6 +331,10 @@ def run_ours(args, wl):
     barrier()
     t_region = time.perf_counter() - t_region
     clocks = sampler.stop() if sampler else None
+    # where the cross-GPU part of the last timed build went (rank 0's stream)
+    assemble_ms = {}
+    for (_, a), (label, b) in zip(assemble_marks, assemble_marks[1:]):
+        assemble_ms[label] = assemble_ms.get(label, 0.0) + a.elapsed_time(b)
 
     # ---- outside the timed region: result fingerprint (hits, status histogram, position checksum -- identical for
     # every N and both multi-GPU modes), algorithmic gathers of the batch (profile = 2 counts the 32-byte sectors the
@@ -456,7 +463,8 @@ def run_ours(args, wl):
                        "l2": "inputs larger than L2 (text, index and batch are each >> 126 MB)" if n * 4 > 2e8 else
                              "inputs smaller than L2; step rebuilds the index so no data is reused across steps"},
             "build": {"metric": "build_gbases_per_s", "value": n / (build_ms * 1e-3) / 1e9, "unit": "Gbases/s",
-                      "ms": build_ms, "nccl_ms": gather_ms if parted else 0.0},
+                      "ms": build_ms, "nccl_ms": gather_ms if parted else 0.0,
+                      **({"assemble_ms_rank0": assemble_ms} if assemble_ms else {})},
             "search": {"ms": search_ms, "hits": int(hits), "checksum": fp["checksum"], "status_hist": fp["status_hist"]},
             "roofline": {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,

@@ -543,13 +543,13 @@ class KmerIndex:
     def stats_reset(self):
         self._L.kmer_b200_stats_reset(self._h)
 
-    @property
     def last_search_transfer(self) -> tuple[int, int]:
         """(host-to-device, device-to-host) bytes the last host-buffer search on this handle moved over PCIe."""
         a, b = C.c_uint64(0), C.c_uint64(0)
         self._L.kmer_b200_last_search_transfer(self._h, C.byref(a), C.byref(b))
         return int(a.value), int(b.value)
 
+    @property
     def last_search_gathers(self) -> int:
         """profile=2: 32-byte sectors the last search gathered at data-dependent addresses."""
         return int(self._L.kmer_b200_last_search_gathers(self._h))

@@ -381,9 +381,18 @@ def _dev_view(ptr: int, n: int, dev):
 def assemble_replicated(ix, world: int, rank: int, dist, dev, timing=None):
     """`ix` was built with key_part=rank, key_parts=world on the torch current stream: all-gather every element's
     part (positions behind the earlier parts' positions, directory entries offset by the earlier parts' k-mer counts)
-    and hand the whole arrays to the index (kmer_b200_adopt_element). Afterwards ix is a complete, replicated index."""
+    and hand the whole arrays to the index (kmer_b200_adopt_element). Afterwards ix is a complete, replicated index.
+    timing: a list that receives (label, CUDA event) marks -- the caller turns consecutive marks into milliseconds."""
     _same_stream(ix)
     import torch
+
+    def mark(label):
+        if timing is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream())
+            timing.append((label, ev))
+
+    mark("start")
     for e, k in enumerate(ix.ks):
         part = ix.element_part(e)
         n_kmers = ix.n - k + 1
@@ -397,6 +406,7 @@ def assemble_replicated(ix, world: int, rank: int, dist, dev, timing=None):
         all_meta = torch.empty(4 * world, dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(all_meta, meta)
         all_meta = all_meta.view(world, 4).cpu()
+        mark("wait_for_parts")   # bucket sizes exported, the slowest rank's part is built
         counts = [int(x) for x in all_meta[:, 0]]
         los = [int(x) for x in all_meta[:, 1]]
         his = [int(x) for x in all_meta[:, 2]]
@@ -418,7 +428,9 @@ def assemble_replicated(ix, world: int, rank: int, dist, dev, timing=None):
         if equal and not any_large:
             sizes_full = torch.empty(key_space, dtype=torch.uint8, device=dev)
             dist.all_gather_into_tensor(sizes_full, sizes)
+            mark("gather_sizes")
             ix.directory_from_sizes(sizes_full.data_ptr(), key_space, dir_full.data_ptr())   # prefix sum on every rank
+            mark("directory_prefix_sum")
             del sizes_full
         elif equal:
             ix.export_directory(e, bases[rank], n_dir, dir_full.data_ptr() + 4 * los[rank])
@@ -447,11 +459,13 @@ def assemble_replicated(ix, world: int, rank: int, dist, dev, timing=None):
             mine = torch.empty(pad, dtype=torch.int32, device=dev)
             mine[:counts[rank]].copy_(pos_full[bases[rank]:bases[rank] + counts[rank]])
             dist.all_gather_into_tensor(staged, mine)
+            mark("gather_positions")
             for r in range(world):
                 if r != rank and counts[r]:
                     pos_full[bases[r]:bases[r] + counts[r]].copy_(staged[r * pad:r * pad + counts[r]])
             del staged, mine
         ix.adopt_element(e, pos_full, dir_full)
+        mark("compact_and_adopt")
 
 
 # ----------------------------------------------------------------------------------------------------------
