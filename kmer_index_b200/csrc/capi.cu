@@ -1759,6 +1759,9 @@ static int search_batch_host_pipelined(kmer_b200_index *ix, const uint8_t *q_ran
         cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming);
         if (qb > qa) {
+            // the ranks first: the copy engine moves them while the host threads compute this chunk's lengths
+            const uint64_t s0 = q_offsets[qa] - q_offsets[0], s1 = q_offsets[qb] - q_offsets[0];
+            if (s1 > s0) cudaMemcpyAsync(d_q + s0, q_ranks + q_offsets[qa], s1 - s0, cudaMemcpyHostToDevice, ix->copy_in);
             if (lens16) {
                 kb::HostPool &pool = kb::HostPool::instance();
                 const unsigned T = std::max(1u, std::min(pool.threads(), 64u));
@@ -1772,8 +1775,6 @@ static int search_batch_host_pipelined(kmer_b200_index *ix, const uint8_t *q_ran
             else
                 cudaMemcpyAsync(d_off + qa + c, q_offsets + qa, (qb - qa + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ix->copy_in);
             h2d += chunk_lens[c] ? (qb - qa) * sizeof(uint16_t) : (qb - qa + 1) * sizeof(uint64_t);
-            const uint64_t s0 = q_offsets[qa] - q_offsets[0], s1 = q_offsets[qb] - q_offsets[0];
-            if (s1 > s0) cudaMemcpyAsync(d_q + s0, q_ranks + q_offsets[qa], s1 - s0, cudaMemcpyHostToDevice, ix->copy_in);
         }
         cudaEventRecord(ev_in[c], ix->copy_in);
     }

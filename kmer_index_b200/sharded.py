@@ -426,18 +426,18 @@ def assemble_replicated(ix, world: int, rank: int, dist, dev, timing=None):
         widths = {his[r] - los[r] for r in range(world)}
         equal = len(widths) == 1 and his[-1] == key_space and los[0] == 0
         pad = max(counts)
-        staged = mine = pos_work = None
+        staged = pos_mine = pos_work = None
         if pad:
             staged = torch.empty(world * pad, dtype=torch.int32, device=dev)
-            mine = torch.empty(pad, dtype=torch.int32, device=dev)
-            mine[:counts[rank]].copy_(pos_full[bases[rank]:bases[rank] + counts[rank]])
+            pos_mine = torch.empty(pad, dtype=torch.int32, device=dev)
+            pos_mine[:counts[rank]].copy_(pos_full[bases[rank]:bases[rank] + counts[rank]])
         if equal and not any_large:
             # both all-gathers are enqueued back to back on NCCL's stream; the prefix sum over the sizes (this stream)
             # runs while the positions are still arriving
             sizes_full = torch.empty(key_space, dtype=torch.uint8, device=dev)
             sizes_work = dist.all_gather_into_tensor(sizes_full, sizes, async_op=True)
             if pad:
-                pos_work = dist.all_gather_into_tensor(staged, mine, async_op=True)
+                pos_work = dist.all_gather_into_tensor(staged, pos_mine, async_op=True)
             sizes_work.wait()
             mark("gather_sizes")
             ix.directory_from_sizes(sizes_full.data_ptr(), key_space, dir_full.data_ptr())   # prefix sum on every rank
@@ -468,12 +468,12 @@ def assemble_replicated(ix, world: int, rank: int, dist, dev, timing=None):
             if pos_work is not None:
                 pos_work.wait()
             else:
-                dist.all_gather_into_tensor(staged, mine)
+                dist.all_gather_into_tensor(staged, pos_mine)
             mark("gather_positions")
             for r in range(world):
                 if r != rank and counts[r]:
                     pos_full[bases[r]:bases[r] + counts[r]].copy_(staged[r * pad:r * pad + counts[r]])
-            del staged, mine
+            del staged, pos_mine
         ix.adopt_element(e, pos_full, dir_full)
         mark("compact_and_adopt")
 
