@@ -359,6 +359,12 @@ uint64_t kmer_b200_device_bytes(const kmer_b200_index *index);
 
 /* profile = 2 only: number of 32-byte sectors at data-dependent addresses (directory slots, bucket entries,
    text windows) the last search had to gather -- the algorithmic work of the search kernel. */
+/* Debug aid (no reference analogue). With KMER_B200_GUARD=1 in the environment every device allocation of the library
+   is bracketed by two 4 KB canary zones that are verified on the device when the allocation is freed: the number of
+   damaged canary bytes seen so far, i.e. stores that landed just outside a buffer. 0 without the variable. The selftest
+   makes two such stores on purpose and checks that they are counted. */
+uint64_t kmer_b200_debug_guard_violations(void);
+int kmer_b200_debug_guard_selftest(void);
 uint64_t kmer_b200_last_search_gathers(const kmer_b200_index *index);
 /* Bytes the last kmer_b200_search_batch / _ptrs / _text on this handle moved over PCIe: host to device (ranks as they are
    or packed, offsets or 16-bit lengths -- whichever the call chose) and device to host (offsets, status, positions). */

@@ -559,6 +559,15 @@ class KmerIndex:
         return int(self._L.kmer_b200_device_bytes(self._h))
 
 
+def guard_violations() -> int:
+    """KMER_B200_GUARD=1 (set before the library is loaded): stores seen just outside a device buffer so far."""
+    return int(_capi.lib().kmer_b200_debug_guard_violations())
+
+
+def guard_selftest() -> None:
+    _capi.check(_capi.lib().kmer_b200_debug_guard_selftest())
+
+
 def make_kmer_index(text, sigma: int, *ks: int, **kw) -> KmerIndex:
     """kmer::make_kmer_index<ks...>(text) (kmer_index.hpp:569-579); position type is uint32."""
     return KmerIndex(text, sigma, ks, **kw)

@@ -131,6 +131,8 @@ SYMBOLS = {
     "kmer_b200_stats": (C.c_uint32, [C.c_void_p, C.POINTER(KernelStat), C.c_uint32]),
     "kmer_b200_stats_reset": (None, [C.c_void_p]),
     "kmer_b200_device_bytes": (C.c_uint64, [C.c_void_p]),
+    "kmer_b200_debug_guard_violations": (C.c_uint64, []),
+    "kmer_b200_debug_guard_selftest": (C.c_int, []),
     "kmer_b200_last_search_gathers": (C.c_uint64, [C.c_void_p]),
     "kmer_b200_last_search_transfer": (None, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "kmer_b200_gather_probe": (C.c_int, [C.c_uint64, C.c_uint64, C.c_void_p, C.POINTER(C.c_double)]),

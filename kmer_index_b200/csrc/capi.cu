@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <unordered_map>
 #include <new>
 #include <string>
 #include <thread>
@@ -248,17 +249,88 @@ struct DeviceGuard {
     }
 };
 
+// ---- guarded allocations (debug aid; compute-sanitizer is not available on every pool) ------------------------------
+// KMER_B200_GUARD=1: every device allocation of the library is bracketed by two 4 KB zones filled with a canary byte,
+// and the zones are verified on the device when the allocation is freed. A store that lands up to 4 KB before or behind
+// any buffer -- scatter destinations, result lists, staging rings -- is counted; kmer_b200_debug_guard_violations()
+// returns the count. Reads are not covered. Off by default: no cost.
+constexpr size_t kGuardBytes = 4096;
+constexpr int kGuardByte = 0xA5;
+bool guard_mode() {
+    static const bool on = [] {
+        const char *e = std::getenv("KMER_B200_GUARD");
+        return e && std::atoi(e) != 0;
+    }();
+    return on;
+}
+std::mutex g_guard_mu;
+std::unordered_map<void *, size_t> g_guard_sizes;     // user pointer -> user bytes
+unsigned long long *g_guard_bad = nullptr;             // pinned, mapped: damaged canary bytes seen so far
+
+__global__ void __launch_bounds__(256) guard_check_kernel(const uint8_t *__restrict__ base, size_t user_bytes,
+                                                          unsigned long long *bad) {
+    unsigned n = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * kGuardBytes; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t at = i < kGuardBytes ? i : kGuardBytes + user_bytes + (i - kGuardBytes);
+        n += base[at] != (uint8_t)kGuardByte;
+    }
+    if (n) atomicAdd_system(bad, (unsigned long long)n);
+}
+
+cudaError_t kb_malloc_async(void **p, size_t bytes, cudaStream_t st) {
+    if (!guard_mode()) return cudaMallocAsync(p, bytes, st);
+    uint8_t *base = nullptr;
+    cudaError_t e = cudaMallocAsync((void **)&base, bytes + 2 * kGuardBytes, st);
+    if (e != cudaSuccess) return e;
+    cudaMemsetAsync(base, kGuardByte, kGuardBytes, st);
+    cudaMemsetAsync(base + kGuardBytes + bytes, kGuardByte, kGuardBytes, st);
+    *p = base + kGuardBytes;
+    std::lock_guard<std::mutex> lock(g_guard_mu);
+    if (!g_guard_bad) {
+        cudaHostAlloc((void **)&g_guard_bad, sizeof(unsigned long long), cudaHostAllocMapped | cudaHostAllocPortable);
+        if (g_guard_bad) *g_guard_bad = 0;
+    }
+    g_guard_sizes[*p] = bytes;
+    return cudaSuccess;
+}
+
+void kb_free_async(void *p, cudaStream_t st) {
+    if (!p) return;
+    if (!guard_mode()) {
+        cudaFreeAsync(p, st);
+        return;
+    }
+    size_t bytes = 0;
+    bool known = false;
+    {
+        std::lock_guard<std::mutex> lock(g_guard_mu);
+        auto it = g_guard_sizes.find(p);
+        if (it != g_guard_sizes.end()) {
+            known = true;
+            bytes = it->second;
+            g_guard_sizes.erase(it);
+        }
+    }
+    if (!known) {  // not ours (never happens for pointers this file allocates)
+        cudaFreeAsync(p, st);
+        return;
+    }
+    uint8_t *base = (uint8_t *)p - kGuardBytes;
+    if (g_guard_bad) guard_check_kernel<<<8, 256, 0, st>>>(base, bytes, g_guard_bad);
+    cudaFreeAsync(base, st);
+}
+
 template <typename T>
 int dev_alloc(kmer_b200_index *ix, T **p, uint64_t count, bool persistent) {
     const size_t bytes = std::max<uint64_t>(count, 1) * sizeof(T);
-    KB_CUDA(cudaMallocAsync((void **)p, bytes, ix->stream));
+    KB_CUDA(kb_malloc_async((void **)p, bytes, ix->stream));
     if (persistent) ix->device_bytes += bytes;
     return 0;
 }
 
 template <typename T>
 void dev_free(kmer_b200_index *ix, T *p) {
-    if (p) cudaFreeAsync((void *)p, ix->stream);
+    if (p) kb_free_async((void *)p, ix->stream);
 }
 
 // Process-wide cache of pinned host buffers (results handed to the caller, small scratch words). Pinned
@@ -2459,17 +2531,17 @@ int kmer_b200_parse_sequences(const char *data, uint64_t n_bytes, const uint8_t 
     int64_t *d_last = nullptr;
     uint32_t *d_err = nullptr;
     auto release = [&](int code) {
-        cudaFreeAsync(d_data, st);
-        cudaFreeAsync(d_lut, st);
-        cudaFreeAsync(d_nl, st);
-        cudaFreeAsync(d_kept, st);
-        cudaFreeAsync(d_recs, st);
-        cudaFreeAsync(d_sums, st);
-        cudaFreeAsync(d_rec_sym, st);
-        cudaFreeAsync(d_rec_hdr, st);
-        cudaFreeAsync(d_last, st);
-        cudaFreeAsync(d_err, st);
-        if (code != 0) cudaFreeAsync(d_ranks, st);
+        kb_free_async(d_data, st);
+        kb_free_async(d_lut, st);
+        kb_free_async(d_nl, st);
+        kb_free_async(d_kept, st);
+        kb_free_async(d_recs, st);
+        kb_free_async(d_sums, st);
+        kb_free_async(d_rec_sym, st);
+        kb_free_async(d_rec_hdr, st);
+        kb_free_async(d_last, st);
+        kb_free_async(d_err, st);
+        if (code != 0) kb_free_async(d_ranks, st);
         cudaStreamSynchronize(st);
         cudaGetLastError();
         return code;
@@ -2483,14 +2555,14 @@ int kmer_b200_parse_sequences(const char *data, uint64_t n_bytes, const uint8_t 
                                 std::string(#expr) + ": " + cudaGetErrorString(_e)));                                      \
         }                                                                                                                  \
     } while (0)
-    KB_FX(cudaMallocAsync((void **)&d_data, n_bytes, st));
-    KB_FX(cudaMallocAsync((void **)&d_lut, 256, st));
-    KB_FX(cudaMallocAsync((void **)&d_nl, (tiles + 1) * 8, st));
-    KB_FX(cudaMallocAsync((void **)&d_kept, (tiles + 1) * 8, st));
-    KB_FX(cudaMallocAsync((void **)&d_recs, (tiles + 1) * 8, st));
-    KB_FX(cudaMallocAsync((void **)&d_sums, (kb::offsets_scan_blocks(tiles) + 1) * 8, st));
-    KB_FX(cudaMallocAsync((void **)&d_last, tiles * 8, st));
-    KB_FX(cudaMallocAsync((void **)&d_err, 4, st));
+    KB_FX(kb_malloc_async((void **)&d_data, n_bytes, st));
+    KB_FX(kb_malloc_async((void **)&d_lut, 256, st));
+    KB_FX(kb_malloc_async((void **)&d_nl, (tiles + 1) * 8, st));
+    KB_FX(kb_malloc_async((void **)&d_kept, (tiles + 1) * 8, st));
+    KB_FX(kb_malloc_async((void **)&d_recs, (tiles + 1) * 8, st));
+    KB_FX(kb_malloc_async((void **)&d_sums, (kb::offsets_scan_blocks(tiles) + 1) * 8, st));
+    KB_FX(kb_malloc_async((void **)&d_last, tiles * 8, st));
+    KB_FX(kb_malloc_async((void **)&d_err, 4, st));
     KB_FX(cudaMemcpyAsync(d_data, data, n_bytes, cudaMemcpyHostToDevice, st));
     KB_FX(cudaMemcpyAsync(d_lut, lut256, 256, cudaMemcpyHostToDevice, st));
     KB_FX(cudaMemsetAsync(d_err, 0, 4, st));
@@ -2504,9 +2576,9 @@ int kmer_b200_parse_sequences(const char *data, uint64_t n_bytes, const uint8_t 
     KB_FX(cudaMemcpyAsync(&totals[1], d_recs + tiles, 8, cudaMemcpyDeviceToHost, st));
     KB_FX(cudaStreamSynchronize(st));
     const uint64_t n_sym = totals[0], n_rec = totals[1];
-    KB_FX(cudaMallocAsync((void **)&d_ranks, std::max<uint64_t>(n_sym, 1), st));
-    KB_FX(cudaMallocAsync((void **)&d_rec_sym, std::max<uint64_t>(n_rec, 1) * 8, st));
-    KB_FX(cudaMallocAsync((void **)&d_rec_hdr, std::max<uint64_t>(n_rec, 1) * 8, st));
+    KB_FX(kb_malloc_async((void **)&d_ranks, std::max<uint64_t>(n_sym, 1), st));
+    KB_FX(kb_malloc_async((void **)&d_rec_sym, std::max<uint64_t>(n_rec, 1) * 8, st));
+    KB_FX(kb_malloc_async((void **)&d_rec_hdr, std::max<uint64_t>(n_rec, 1) * 8, st));
     kb::launch_fastx_write(d_data, n_bytes, format, d_nl, d_last, d_kept, d_recs, d_lut, sigma, d_ranks, d_rec_sym, d_rec_hdr, d_err, st);
     kmer_b200_records *r = new (std::nothrow) kmer_b200_records();
     if (!r) return release(fail(KMER_B200_ERR_OUT_OF_MEMORY, "host allocation failed"));
@@ -2569,7 +2641,9 @@ int kmer_b200_records_locate(const kmer_b200_records *r, const uint32_t *positio
 void kmer_b200_records_free(kmer_b200_records *r) {
     if (!r) return;
     DeviceGuard guard(r->device);
-    cudaFree(r->d_ranks);
+    cudaDeviceSynchronize();
+    kb_free_async(r->d_ranks, nullptr);
+    cudaStreamSynchronize(nullptr);
     cudaGetLastError();
     delete r;
 }
@@ -3167,6 +3241,33 @@ uint64_t kmer_b200_device_bytes(const kmer_b200_index *ix) {
     uint64_t total = ix->device_bytes;
     for (const kmer_b200_index *r : ix->replicas) total += r->device_bytes;  // all devices of a multi-device handle
     return total;
+}
+
+uint64_t kmer_b200_debug_guard_violations(void) {
+    if (!guard_mode() || !g_guard_bad) return 0;
+    int n_dev = 0, prev = 0;
+    cudaGetDeviceCount(&n_dev);
+    cudaGetDevice(&prev);
+    for (int d = 0; d < n_dev; ++d) {  // the checks run on the streams the buffers were freed on
+        cudaSetDevice(d);
+        cudaDeviceSynchronize();
+    }
+    cudaSetDevice(prev);
+    cudaGetLastError();
+    return *reinterpret_cast<volatile unsigned long long *>(g_guard_bad);
+}
+
+int kmer_b200_debug_guard_selftest(void) {
+    // one allocation, one store a byte behind its end, one a byte before its start: both must be counted
+    if (!guard_mode()) return fail(KMER_B200_ERR_UNSUPPORTED, "KMER_B200_GUARD is not set");
+    const uint64_t before = kmer_b200_debug_guard_violations();
+    uint8_t *p = nullptr;
+    KB_CUDA(kb_malloc_async((void **)&p, 1000, nullptr));
+    KB_CUDA(cudaMemsetAsync(p + 1000, 0, 1, nullptr));
+    KB_CUDA(cudaMemsetAsync(p - 1, 0, 1, nullptr));
+    kb_free_async(p, nullptr);
+    return kmer_b200_debug_guard_violations() - before == 2 ? KMER_B200_OK
+                                                             : fail(KMER_B200_ERR_CUDA, "guard zones did not see the stores");
 }
 
 uint64_t kmer_b200_last_search_gathers(const kmer_b200_index *ix) { return ix ? primary(ix)->last_gathers : 0; }

@@ -33,3 +33,8 @@ q15, off15 = synth.stress_queries(t15, 300, 1, 30, 15, 6)
 with kb.KmerIndex(t15, 15, [8]) as ix:
     print("dna15", ix.search_batch(q15, off15).positions.size)
 print("sanitize case done")
+if os.environ.get("KMER_B200_GUARD"):
+    # canary zones around every device allocation of the library, verified at free time (kmer_b200.h)
+    seen = kb.guard_violations()
+    kb.guard_selftest()                 # two deliberate out-of-bounds stores: both must be counted
+    print("guard violations", seen, "selftest ok", kb.guard_violations() - seen == 2)
