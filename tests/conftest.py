@@ -48,3 +48,13 @@ def oracle_mod():
     from oracle import bindings
     bindings.build()
     return bindings
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _guarded_allocations_stay_intact():
+    """KMER_B200_GUARD=1 python -m pytest tests -m gpu: the whole GPU suite with canary zones around every device
+    allocation of the library (include/kmer_b200.h); a store outside a buffer anywhere in the session fails it here."""
+    yield
+    if os.environ.get("KMER_B200_GUARD") and "kmer_index_b200" in sys.modules:
+        import kmer_index_b200
+        assert kmer_index_b200.guard_violations() == 0, "a kernel stored outside one of the library's device buffers"
