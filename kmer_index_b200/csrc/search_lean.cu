@@ -10,6 +10,8 @@
 // (kmer_index.hpp:216-227, :234 -> :119, :314) are evaluated straight from the directory.
 // Queries the lean path does not cover (m < k: prefix slabs; candidate lists beyond kHeavyCandidates) are appended to the
 // batch's "heavy" list and answered by the general kernel's warp-per-query launch, exactly as long buckets already are.
+#include <cstdlib>
+
 #include "launch.h"
 #include "query_pack.cuh"
 
@@ -102,8 +104,8 @@ __device__ __forceinline__ bool match_span_regs(const PackedText &T, const uint6
     return true;
 }
 
-template <int W>
-__global__ void __launch_bounds__(kLeanThreads, W == 2 ? 6 : 5) search_count_lean_kernel(const SearchArgs a) {
+template <int W, int MIN_BLOCKS>
+__global__ void __launch_bounds__(kLeanThreads, MIN_BLOCKS) search_count_lean_kernel(const SearchArgs a) {
     const uint64_t q = (uint64_t)blockIdx.x * kLeanThreads + threadIdx.x;
     if (q >= a.n_queries) return;
     const int lane = threadIdx.x & 31;
@@ -242,10 +244,21 @@ __global__ void __launch_bounds__(kLeanThreads, W == 2 ? 6 : 5) search_count_lea
 bool launch_search_count_lean(const SearchArgs &a, cudaStream_t stream) {
     if (!a.lean_ok || a.heavy == nullptr || a.n_queries == 0 || a.max_len > 128) return false;
     const unsigned blocks = (unsigned)((a.n_queries + kLeanThreads - 1) / kLeanThreads);
-    if (a.max_len <= 64)
-        search_count_lean_kernel<2><<<blocks, kLeanThreads, 0, stream>>>(a);
-    else
-        search_count_lean_kernel<4><<<blocks, kLeanThreads, 0, stream>>>(a);
+    // 8 CTAs per SM (32 registers, 84 bytes of spills that stay in L1) against 6 (40 registers, none): the pass is bound by
+    // the latency of its dependent gathers, so the extra resident warps win -- config 5: 5.50 ms against 5.67.
+    // KMER_B200_LEAN_BLOCKS=6 selects the other variant.
+    static const int dense = [] {
+        const char *e = std::getenv("KMER_B200_LEAN_BLOCKS");
+        return e ? std::atoi(e) : 8;
+    }();
+    if (a.max_len <= 64) {
+        if (dense == 8)
+            search_count_lean_kernel<2, 8><<<blocks, kLeanThreads, 0, stream>>>(a);
+        else
+            search_count_lean_kernel<2, 6><<<blocks, kLeanThreads, 0, stream>>>(a);
+    } else {
+        search_count_lean_kernel<4, 5><<<blocks, kLeanThreads, 0, stream>>>(a);
+    }
     return true;
 }
 
