@@ -57,7 +57,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--count-only", action="store_true", help="time search without materialising positions")
-    ap.add_argument("--multi", default="replicated", choices=["routed", "replicated", "position-range"],
+    ap.add_argument("--multi", default="replicated", choices=["routed", "replicated", "peer", "position-range"],
                     help="N > 1: 'routed' = every GPU keeps one key-range part of the index, each GPU routes its 1/N of the "
                          "batch to the owners of the queries' first k-mers and gets the results back (three all-to-alls); "
                          "'replicated' = the parts are all-gathered over NVLink into the whole index on every GPU and each GPU "
@@ -238,7 +238,10 @@ def run_ours(args, wl):
     m_lo, m_hi = wl["m"]
     k_max = max(ks)
     routed = world > 1 and args.multi == "routed" and len(ks) == 1 and m_lo >= ks[0]
-    replicated = world > 1 and (args.multi == "replicated" or (args.multi == "routed" and not routed))
+    # 'peer': like 'replicated' for the search (each GPU answers 1/N of the batch from a whole directory) but the position
+    # array stays in the parts the GPUs sorted, mapped into every rank over NVLink (sharded.assemble_peer)
+    peer = world > 1 and args.multi == "peer"
+    replicated = world > 1 and (peer or args.multi == "replicated" or (args.multi == "routed" and not routed))
     parted = routed or replicated   # the index is built from key-range parts; every rank holds the whole text and 1/N of the batch
 
     # ---- the text. position-range: this rank's slice (k-mer/match starts [begin, end) plus a halo of m_hi - 1 symbols);
@@ -278,10 +281,15 @@ def run_ours(args, wl):
         torch.cuda.synchronize()
 
     assemble_marks = []   # (label, event) marks of the last replicated assembly
+    # shared position buffers of the peer mode: mapped once, like a communicator, reused by every build
+    peer_buffers = sharded.PeerPositions(world, rank, dist, dev) if peer else None
 
     def finish_build(ix):
         """the cross-GPU part of the build: all-gather of the parts (replicated) or of the presence bitmap (routed)"""
-        if replicated:
+        if peer:
+            assemble_marks.clear()
+            sharded.assemble_peer(ix, world, rank, dist, dev, peer_buffers, timing=assemble_marks)
+        elif replicated:
             assemble_marks.clear()
             sharded.assemble_replicated(ix, world, rank, dist, dev, timing=assemble_marks)
         elif routed:
@@ -446,6 +454,10 @@ def run_ours(args, wl):
             sharding = (f"partitioned index x{world}: every GPU keeps one key-range part of the hashes (+ the packed text and a "
                         f"presence bitmap), holds 1/{world} of the batch, routes each query to the owner of its first k-mer and "
                         f"gets the results back (three NCCL all-to-alls inside search_ms)")
+        elif peer:
+            sharding = (f"peer positions x{world}: every GPU sorts one key-range part of the hashes; the directory is "
+                        f"all-gathered (one byte per bucket) and whole on every GPU, the position array stays in the parts, "
+                        f"mapped into every rank over NVLink (CUDA IPC); each GPU answers 1/{world} of the batch")
         elif replicated:
             sharding = (f"replicated index x{world}: every GPU sorts one key-range part of the hashes, parts all-gathered "
                         f"over NCCL (inside build_ms), each GPU answers 1/{world} of the batch")

@@ -257,6 +257,15 @@ int kmer_b200_directory_from_sizes(kmer_b200_index *index, const uint8_t *d_size
    The element then covers the whole key space. */
 int kmer_b200_adopt_element(kmer_b200_index *index, uint32_t element, const uint32_t *d_positions, uint64_t n_kmers,
                             const uint32_t *d_directory, uint64_t directory_entries);
+/* Same, with the position array left in the parts the GPUs built ("peer positions"): part r holds the entries
+   [part_first[r], part_first[r + 1]) of the whole position array (part_first has n_parts + 1 entries, n_parts <= 8; part
+   boundaries are the key-range boundaries, so a bucket never straddles two parts). A part may be another GPU's memory
+   mapped into this process (CUDA IPC); the search then reads those candidates over NVLink. Only the directory -- whole,
+   d_directory as above -- is replicated: the build moves a byte per bucket between the GPUs instead of the positions.
+   The arrays stay the caller's and must outlive the index. */
+int kmer_b200_adopt_element_parts(kmer_b200_index *index, uint32_t element, const uint32_t *const *d_position_parts,
+                                  const uint64_t *part_first, uint32_t n_parts, const uint32_t *d_directory,
+                                  uint64_t directory_entries);
 
 /* ---- key-range multi-GPU search: the index stays partitioned (one key-range part per GPU, no assembly), queries
    travel to the GPU that owns the hash of their first k symbols and results travel back. Single-k indices with 32-bit

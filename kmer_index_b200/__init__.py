@@ -462,6 +462,16 @@ class KmerIndex:
                                                     C.c_void_p(directory.data_ptr()), directory.numel()))
         self._adopted.append((positions, directory))
 
+    def adopt_element_parts(self, e: int, parts, part_first, directory) -> None:
+        """Peer-positions index: `parts` = one int32 device tensor per key-range part (this GPU's own or another GPU's
+        memory mapped into this process), part_first = n_parts + 1 ascending CSR indices, directory = the whole
+        directory on this GPU. Everything passed is kept alive by this object."""
+        ptrs = (C.c_void_p * len(parts))(*[C.c_void_p(t.data_ptr() if t is not None and t.numel() else 0) for t in parts])
+        first = np.asarray(part_first, dtype=np.uint64)
+        _capi.check(self._L.kmer_b200_adopt_element_parts(self._h, e, ptrs, first.ctypes.data_as(_capi.u64p), len(parts),
+                                                          C.c_void_p(directory.data_ptr()), directory.numel()))
+        self._adopted.append((list(parts), directory))
+
     # -- key-range multi-GPU search: routing (sharded.search_routed drives these)
     def route_plan(self, n_queries: int, max_len: int, n_parts: int, slack: float = 0.0) -> _capi.RoutePlan:
         plan = _capi.RoutePlan()

@@ -155,6 +155,7 @@ struct HostElement {
     uint64_t n_occupied = 0;  // distinct hashes (non-empty buckets), measured on first use by kmer_b200_plan_table
     int adopted = 0;         // 1: pos / dir belong to the caller (kmer_b200_adopt_element); 2: assembled by the library, owned
     bool view = false;       // shared-positions index: no arrays of its own, a prefix view of the largest k's (kb::Element::width)
+    bool in_parts = false;   // peer-positions index: the positions stay in the caller's per-GPU parts (kb::Element::pos_part)
 };
 
 // Shared-positions multi-k index (kmer_b200_config::reserved bit 1): every element but the one with the largest k becomes
@@ -1402,6 +1403,8 @@ int kmer_b200_save(kmer_b200_index *ix, const char *path) {
     if (!ix || !path) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
     ix = primary(ix);  // every device of a multi-device handle holds the whole index
     if (ix->cfg.key_parts > 1) return fail(KMER_B200_ERR_UNSUPPORTED, "a key-range part is not a whole index: assemble it first");
+    for (const HostElement &he : ix->elems)
+        if (he.in_parts) return fail(KMER_B200_ERR_UNSUPPORTED, "the positions of this index live in several GPUs' memory: save a replicated index");
     DeviceGuard guard(ix->device);
     std::lock_guard<std::mutex> lock(ix->mu);
     FILE *f = std::fopen(path, "wb");
@@ -2337,6 +2340,8 @@ int kmer_b200_element_info_get(const kmer_b200_index *ix, uint32_t e, kmer_b200_
 static int reject_view(const kmer_b200_index *ix, uint32_t e) {
     if (e < ix->elems.size() && ix->elems[e].view)
         return fail(KMER_B200_ERR_UNSUPPORTED, "element is a view of the largest k's arrays (shared-positions index)");
+    if (e < ix->elems.size() && ix->elems[e].in_parts)
+        return fail(KMER_B200_ERR_UNSUPPORTED, "the element's positions live in per-GPU parts (peer-positions index)");
     return 0;
 }
 
@@ -2501,6 +2506,85 @@ int kmer_b200_adopt_element(kmer_b200_index *ix, uint32_t e, const uint32_t *d_p
                             const uint32_t *d_directory, uint64_t directory_entries) {
     if (ix && !ix->replicas.empty()) return fail(KMER_B200_ERR_UNSUPPORTED, "not available on a multi-device handle");
     return adopt_element_impl(ix, e, d_positions, n_kmers, d_directory, directory_entries, 1);
+}
+
+int kmer_b200_adopt_element_parts(kmer_b200_index *ix, uint32_t e, const uint32_t *const *d_position_parts,
+                                  const uint64_t *part_first, uint32_t n_parts, const uint32_t *d_directory,
+                                  uint64_t directory_entries) {
+    if (!ix || !d_position_parts || !part_first || !d_directory || e >= ix->ks.size())
+        return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad argument");
+    if (!ix->replicas.empty()) return fail(KMER_B200_ERR_UNSUPPORTED, "not available on a multi-device handle");
+    if (ix->cfg.reserved & KMER_B200_FLAG_SHARED_POSITIONS) return fail(KMER_B200_ERR_UNSUPPORTED, "adopt: not on a shared-positions index");
+    if (n_parts == 0 || n_parts > (uint32_t)kb::kMaxPosParts) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "adopt: 1 to 8 parts");
+    HostElement &he = ix->elems[e];
+    const uint64_t n_kmers = ix->n - he.dev.k + 1;
+    if (part_first[0] != 0 || part_first[n_parts] != n_kmers || directory_entries != he.dev.key_space + 1 || n_kmers > 0xFFFFFFFFull)
+        return fail(KMER_B200_ERR_INVALID_ARGUMENT, "adopt: the parts do not describe the whole index (n - k + 1 positions, sigma^k + 1 directory entries)");
+    for (uint32_t r = 0; r < n_parts; ++r)
+        if (part_first[r + 1] < part_first[r] || (part_first[r + 1] > part_first[r] && !d_position_parts[r]))
+            return fail(KMER_B200_ERR_INVALID_ARGUMENT, "adopt: part boundaries must ascend and non-empty parts need a pointer");
+    DeviceGuard guard(ix->device);
+    // parts in other GPUs' memory (mapped into this process by the caller, e.g. CUDA IPC): this device must be allowed
+    // to read them from a kernel
+    for (uint32_t r = 0; r < n_parts; ++r) {
+        if (part_first[r + 1] == part_first[r]) continue;
+        cudaPointerAttributes attr{};
+        if (cudaPointerGetAttributes(&attr, d_position_parts[r]) != cudaSuccess || attr.type != cudaMemoryTypeDevice) {
+            cudaGetLastError();
+            return fail(KMER_B200_ERR_INVALID_ARGUMENT, "adopt: a part is not device memory");
+        }
+        if (attr.device == ix->device) continue;
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, ix->device, attr.device);
+        if (!can) return fail(KMER_B200_ERR_UNSUPPORTED, "adopt: this device cannot read the device that holds a part");
+        const cudaError_t pe = cudaDeviceEnablePeerAccess(attr.device, 0);
+        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) {
+            cudaGetLastError();
+            return fail(KMER_B200_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(pe));
+        }
+        cudaGetLastError();
+    }
+    std::lock_guard<std::mutex> lock(ix->mu);
+    if (he.adopted != 1) {
+        dev_free(ix, he.d_dir);
+        dev_free(ix, he.d_pos);
+        ix->device_bytes -= he.bytes;
+    }
+    dev_free(ix, (uint8_t *)he.d_keys);
+    he.d_keys = nullptr;
+    he.adopted = 1;
+    he.in_parts = true;
+    he.d_pos = nullptr;
+    he.d_dir = const_cast<uint32_t *>(d_directory);
+    he.dev.shift = 0;
+    he.dev.n_kmers = n_kmers;
+    he.dev.dir_entries = directory_entries;
+    he.dev.dir = he.d_dir;
+    he.dev.keys = nullptr;
+    he.dev.pos = nullptr;
+    he.dev.key_lo = 0;
+    he.dev.key_hi = UINT64_MAX;
+    he.dev.n_pos_parts = n_parts;
+    for (uint32_t r = 0; r <= n_parts; ++r) he.dev.part_first[r] = (uint32_t)part_first[r];
+    for (uint32_t r = 0; r < n_parts; ++r) he.dev.pos_part[r] = d_position_parts[r];
+    he.bytes = directory_entries * 4;
+    ix->host_index.elem[e] = he.dev;
+    bool all = true;
+    for (size_t i = 0; i < ix->ks.size(); ++i) all = all && ix->elems[i].adopted != 0;
+    if (all) {
+        ix->cfg.key_parts = 0;
+        ix->cfg.key_part = 0;
+        for (size_t i = ix->ks.size(); i < ix->elems.size(); ++i) {
+            dev_free(ix, ix->elems[i].d_dir);
+            dev_free(ix, ix->elems[i].d_pos);
+            dev_free(ix, (uint8_t *)ix->elems[i].d_keys);
+        }
+        ix->elems.resize(ix->ks.size());
+        std::memset(ix->host_index.aux_for_len, 0xFF, sizeof(ix->host_index.aux_for_len));
+    }
+    KB_CUDA(cudaMemcpyAsync(ix->d_index, &ix->host_index, sizeof(kb::DeviceIndex), cudaMemcpyHostToDevice, ix->stream));
+    KB_CUDA(cudaStreamSynchronize(ix->stream));
+    return KMER_B200_OK;
 }
 
 // ---- FASTA / FASTQ parsing (fastx_kernels.cu) ---------------------------------------------------------------------

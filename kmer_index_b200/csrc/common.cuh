@@ -9,6 +9,7 @@
 namespace kb {
 
 constexpr int kMaxElements = 32;
+constexpr int kMaxPosParts = 8;  // Element::pos_part
 constexpr uint32_t kQuerySizeRange = 10000;  // kmer_index.hpp:401
 
 // ---------------------------------------------------------------------------------------------
@@ -121,7 +122,23 @@ struct Element {
     // (where no k_phys-mer starts) are not in it: the search compares those "tail" starts directly and sorts what it
     // reports. width == 1 for an ordinary element.
     uint64_t width;
+    // Peer-positions multi-GPU index (n_pos_parts > 0, pos == null): the position array stays cut into the key-range
+    // parts the GPUs built -- part r holds the CSR entries [part_first[r], part_first[r + 1]) in pos_part[r], which is
+    // this GPU's memory for one r and another GPU's memory, mapped over NVLink, for the others. Part boundaries are
+    // bucket boundaries, so a bucket lies in one part. The directory is whole on every GPU.
+    uint32_t n_pos_parts;
+    uint32_t part_first[kMaxPosParts + 1];
+    const uint32_t *pos_part[kMaxPosParts];
 };
+
+// address of CSR entry i of element E
+__device__ __forceinline__ const uint32_t *pos_ptr(const Element &E, uint64_t i) {
+    if (E.n_pos_parts == 0) return E.pos + i;
+    uint32_t r = 0;
+#pragma unroll
+    for (uint32_t j = 1; j < (uint32_t)kMaxPosParts; ++j) r += (j < E.n_pos_parts && i >= (uint64_t)E.part_first[j]) ? 1u : 0u;
+    return E.pos_part[r] + (i - E.part_first[r]);
+}
 
 __device__ __forceinline__ uint64_t element_key(const Element &E, uint64_t i) {
     return E.key_bytes == 8 ? gather64(static_cast<const uint64_t *>(E.keys) + i)
@@ -130,7 +147,7 @@ __device__ __forceinline__ uint64_t element_key(const Element &E, uint64_t i) {
 // same, for elements that may not hold their hashes (dense directory): recomputed from the text at pos[i]
 __device__ __forceinline__ uint64_t element_key_or_text(const PackedText &T, const Element &E, uint64_t i) {
     if (E.keys != nullptr) return element_key(E, i);
-    return key_at(T.words, (uint64_t)gather32(E.pos + i), E.k_phys, T.bits, T.sigma);
+    return key_at(T.words, (uint64_t)gather32(pos_ptr(E, i)), E.k_phys, T.bits, T.sigma);
 }
 
 // ---- directory lookups (the reference's at(hash), kmer_index.hpp:76-84) ------------------------------------------------

@@ -472,7 +472,7 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
             uint32_t p = 0;
             bool ok = false;
             if (c < shi) {
-                p = E0.pos[c];
+                p = *pos_ptr(E0, c);  // a slab spans buckets, so it may span parts
                 ok = (uint64_t)p < ix.owned;
                 if (kAccount && ((c & 7) == 0 || c == slo)) ++n_gather;
             }
@@ -537,7 +537,7 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
         if (count_by_range) n_hits = seed.cnt;
         if (PASS == kPassWrite && kind == kExact && ix.owned == T.n) {
             // the whole bucket is the result: a plain copy with 8 independent loads in flight per lane
-            const uint32_t *src = Es.pos + seed.lo;
+            const uint32_t *src = pos_ptr(Es, seed.lo);
             uint32_t *dst = a.positions + out_base;
             const uint32_t gb = (uint32_t)ix.global_base;
             uint64_t c = gl;
@@ -552,6 +552,8 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
             count_by_range = true;  // the generic loop below starts behind the slab
             n_hits = seed.cnt;
         }
+        // a bucket lies in one part of a peer-positions index; a view's slab (VIEWS) only exists on a whole array
+        const uint32_t *cand = pos_ptr(Es, seed.lo);
         for (uint64_t c0 = count_by_range ? seed.cnt : 0; c0 < n_cand; c0 += G) {
             const uint64_t c = c0 + gl;
             uint32_t p = 0;
@@ -559,7 +561,7 @@ __device__ __forceinline__ void search_query(const SearchArgs &a, const uint64_t
             if (c < n_cand) {
                 uint32_t at;
                 if (!VIEWS || c < seed.cnt) {
-                    at = gather32(Es.pos + seed.lo + c);
+                    at = gather32(cand + c);
                     ok = true;
                 } else {
                     at = (uint32_t)(T.n - Es.k_phys + 1 + (c - seed.cnt));

@@ -209,8 +209,9 @@ __global__ void __launch_bounds__(kLeanThreads, MIN_BLOCKS) search_count_lean_ke
         n_hits = seed.cnt;
     } else {
         const uint32_t last_q = (P - 1) * k;
+        const uint32_t *cand = pos_ptr(E, seed.lo);  // a bucket lies in one part of a peer-positions index
         for (uint64_t c = 0; c < seed.cnt; ++c) {
-            const uint32_t at = gather32(E.pos + seed.lo + c);
+            const uint32_t at = gather32(cand + c);
             if (at < seed_d) continue;
             const uint64_t p = at - seed_d;
             if (p >= ix.owned) continue;

@@ -479,6 +479,118 @@ def assemble_replicated(ix, world: int, rank: int, dist, dev, timing=None):
 
 
 # ----------------------------------------------------------------------------------------------------------
+# peer positions: the directory is replicated (it travels as one byte per bucket), the position array stays where it was
+# sorted -- every rank maps the other ranks' parts into its address space (CUDA IPC) and the search reads the candidates
+# of a foreign bucket over NVLink. The build moves 1/4 of the bytes of the replicated form; a query still touches no
+# collective.
+# ----------------------------------------------------------------------------------------------------------
+class PeerPositions:
+    """Per-element position buffers of all ranks, mapped into every rank. Created once (like a communicator) and reused
+    by every build; a buffer is re-made -- collectively -- when some rank's part outgrows it."""
+
+    def __init__(self, world: int, rank: int, dist, dev):
+        self.world, self.rank, self.dist, self.dev = world, rank, dist, dev
+        self.mine = {}     # element -> this rank's buffer (int32 tensor)
+        self.views = {}    # element -> [tensor per rank], views[rank] is self.mine
+        self.capacity = {}
+
+    def ensure(self, e: int, need: int):
+        """Collective: every rank passes the same `need` (the largest part over all ranks)."""
+        import torch
+        if self.capacity.get(e, 0) >= need:
+            return
+        cap = int(need * 1.02) + 1024
+        self.views.pop(e, None)
+        self.mine.pop(e, None)
+        mine = torch.empty(cap, dtype=torch.int32, device=self.dev)
+        handle = mine.untyped_storage()._share_cuda_()
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, handle)
+        views = []
+        for r in range(self.world):
+            if r == self.rank:
+                views.append(mine)
+                continue
+            st = torch.UntypedStorage._new_shared_cuda(*handles[r])
+            views.append(torch.empty(0, dtype=torch.int32, device=st.device).set_(st, 0, (cap,)))
+        self.mine[e], self.views[e], self.capacity[e] = mine, views, cap
+        torch.cuda.synchronize()
+        self.dist.barrier()
+
+
+def assemble_peer(ix, world: int, rank: int, dist, dev, peers: PeerPositions, timing=None):
+    """`ix` was built with key_part=rank, key_parts=world on the torch current stream. Every rank copies its part's
+    positions into its shared buffer, the directory is all-gathered as bucket sizes and prefix-summed on every rank,
+    and the index adopts (own part, the other ranks' mapped parts, whole directory). Needs dense directories whose
+    buckets fit a byte on every rank or ships 4-byte directory entries instead."""
+    _same_stream(ix)
+    import torch
+
+    def mark(label):
+        if timing is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream())
+            timing.append((label, ev))
+
+    mark("start")
+    for e, k in enumerate(ix.ks):
+        part = ix.element_part(e)
+        n_kmers = ix.n - k + 1
+        key_space = ix.sigma ** k
+        width_mine = part.key_hi - part.key_lo
+        sizes = torch.empty(max(width_mine, 1), dtype=torch.uint8, device=dev)
+        n_large = ix.export_bucket_sizes(e, sizes.data_ptr())
+        meta = torch.tensor([part.n_kmers, part.key_lo, part.key_hi, n_large], dtype=torch.int64, device=dev)
+        all_meta = torch.empty(4 * world, dtype=torch.int64, device=dev)
+        # also the fence between the previous index and this one: no rank overwrites its shared buffer before every
+        # rank's stream has passed its last search
+        dist.all_gather_into_tensor(all_meta, meta)
+        all_meta = all_meta.view(world, 4).cpu()
+        mark("wait_for_parts")
+        counts = [int(x) for x in all_meta[:, 0]]
+        los = [int(x) for x in all_meta[:, 1]]
+        his = [int(x) for x in all_meta[:, 2]]
+        any_large = int(all_meta[:, 3].sum()) > 0
+        bases = [sum(counts[:r]) for r in range(world)]
+        assert sum(counts) == n_kmers, (counts, n_kmers)
+        peers.ensure(e, max(counts))
+        if counts[rank]:
+            peers.mine[e][:counts[rank]].copy_(_dev_view(part.d_positions, counts[rank], dev))
+        dir_full = torch.empty(key_space + 1, dtype=torch.int32, device=dev)
+        widths = {his[r] - los[r] for r in range(world)}
+        equal = len(widths) == 1 and his[-1] == key_space and los[0] == 0
+        if equal and not any_large:
+            sizes_full = torch.empty(key_space, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(sizes_full, sizes)
+            mark("gather_sizes")
+            ix.directory_from_sizes(sizes_full.data_ptr(), key_space, dir_full.data_ptr())
+            mark("directory_prefix_sum")
+            del sizes_full
+        else:
+            last = rank == world - 1
+            n_dir = his[rank] - los[rank] + (1 if last else 0)
+            ix.export_directory(e, bases[rank], n_dir, dir_full.data_ptr() + 4 * los[rank])
+            ops = []
+            for r in range(world):
+                if r == rank:
+                    continue
+                hi_r = his[r] + (1 if r == world - 1 else 0)
+                if n_dir:
+                    ops.append(dist.P2POp(dist.isend, dir_full[los[rank]:los[rank] + n_dir], r))
+                if hi_r > los[r]:
+                    ops.append(dist.P2POp(dist.irecv, dir_full[los[r]:hi_r], r))
+            if ops:
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+            mark("gather_directory")
+        del sizes
+        # every rank's copy into its shared buffer precedes its contribution to the directory exchange in stream
+        # order, so once the exchange has completed here the other ranks' parts are in place
+        ix.adopt_element_parts(e, [peers.views[e][r][:counts[r]] for r in range(world)], bases + [n_kmers], dir_full)
+        mark("adopt")
+
+
+# ----------------------------------------------------------------------------------------------------------
 # partitioned index, routed queries: rank r keeps index part r (the k-mers whose hash lies in the r-th slice of the key
 # space) and the whole packed text; a query is answered by the owner of the hash of its first k symbols. Three
 # all-to-all exchanges move queries out and results back; nothing is replicated except a presence bitmap.

@@ -2,6 +2,7 @@
 compared bit for bit with the CPU oracle on rank 0:
   * position-range shards (+ halo), every rank searches the whole batch, presence flags all-reduced, merged CSR
     assembled on rank 0 (kmer_index_b200.sharded.search_merged) -- the real send/recv + add_counts + place path;
+  * peer positions: the same parts, only the directory replicated, positions read from the owners over NVLink
   * replicated index: every rank sorts one key-range part, parts all-gathered (sharded.assemble_replicated), every
     rank answers its slice of the batch;
   * partitioned index, routed queries (sharded.search_routed): every rank keeps its key-range part, queries travel to
@@ -32,6 +33,7 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
+    peer_buffers = sharded.PeerPositions(world, rank, dist, dev)
     cases = [(4, [16], 2_000_000, 16, 64, False), (4, [12], 600_000, 13, 64, True), (4, [5, 7, 9, 11, 13], 300_000, 4, 40, False)]
     for sigma, ks, n, m_lo, m_hi, heavy in cases:
         text = synth.random_text(n, sigma, 31)
@@ -92,6 +94,25 @@ def main():
             w_sum = w_sum - (1 << 64) if w_sum >= (1 << 63) else w_sum
             assert fp["hits"] == int(want[0][-1]) == int(t[0]) and fp["checksum"] == w_sum == int(t[1]), (fp, w_sum, t)
             assert fp["status_hist"] == [int(x) for x in t[2:6]] == [int((want[2] == s).sum()) for s in range(4)]
+        # ---- peer positions: whole directory everywhere, the position array left in the ranks' parts and read over
+        # NVLink; built twice on the same shared buffers (the second build must not disturb a search still running)
+        for attempt in range(2):
+            ix = kb.KmerIndex(text, sigma, ks, stream=sptr, device=local, key_part=rank, key_parts=world)
+            sharded.assemble_peer(ix, world, rank, dist, dev, peer_buffers)
+            mine = ix.search_batch(q[int(off[lo]):int(off[hi])], off[lo:hi + 1] - off[lo]).as_tuple()
+            fp_p = sharded.fingerprint(ix, d_q.data_ptr() + int(off[lo]), (d_off[lo:hi + 1] - d_off[lo]).contiguous().data_ptr(),
+                                       hi - lo, m_hi, 1, dev, lo)
+            ix.close()
+            parts = [None] * world
+            dist.all_gather_object(parts, mine)
+            tp = torch.tensor([fp_p["hits"], fp_p["checksum"]], dtype=torch.int64, device=dev)
+            dist.all_reduce(tp)
+            if rank == 0:
+                g_off = np.concatenate([[0]] + [np.asarray(p[0][1:], dtype=np.uint64) + np.uint64(sum(int(x[0][-1]) for x in parts[:i]))
+                                                for i, p in enumerate(parts)]).astype(np.uint64)
+                got = (g_off, np.concatenate([p[1] for p in parts]), np.concatenate([p[2] for p in parts]))
+                assert_results_equal(got, want, label=f"peer positions x{world} {ks} attempt {attempt}")
+                assert int(tp[0]) == fp["hits"] and int(tp[1]) == fp["checksum"]
         # ---- partitioned index, routed queries (single-k indices): three all-to-all exchanges, nothing replicated
         if len(ks) == 1 and m_lo >= ks[0]:
             ix = kb.KmerIndex(text, sigma, ks, stream=sptr, device=local, key_part=rank, key_parts=world)
