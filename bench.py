@@ -61,7 +61,8 @@ def parse_args():
                     help="N > 1: 'routed' = every GPU keeps one key-range part of the index, each GPU routes its 1/N of the "
                          "batch to the owners of the queries' first k-mers and gets the results back (three all-to-alls); "
                          "'replicated' = the parts are all-gathered over NVLink into the whole index on every GPU and each GPU "
-                         "answers 1/N of the batch locally; 'position-range' = text shards with halo, every GPU searches the "
+                         "answers 1/N of the batch locally; 'peer' = only the directory is replicated, the position parts stay "
+                         "where they were sorted and are read over NVLink (CUDA IPC mappings); 'position-range' = text shards with halo, every GPU searches the "
                          "whole batch, hit lists merged on rank 0")
     return ap.parse_args()
 
@@ -541,6 +542,8 @@ def run_ours(args, wl):
                                     "build_threads": r["build_threads"], "cpu": r["cpu"],
                                     "search_qps_min_max": r["search_qps_spread"]}
         print(json.dumps(line), flush=True)
+    if peer_buffers is not None:
+        peer_buffers.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -266,6 +266,13 @@ int kmer_b200_adopt_element(kmer_b200_index *index, uint32_t element, const uint
 int kmer_b200_adopt_element_parts(kmer_b200_index *index, uint32_t element, const uint32_t *const *d_position_parts,
                                   const uint64_t *part_first, uint32_t n_parts, const uint32_t *d_directory,
                                   uint64_t directory_entries);
+/* Device buffers that other processes (one per GPU) can map: create = a plain device allocation on `device` plus its
+   64-byte CUDA IPC handle; open = map a buffer created by another process into this one, readable by kernels running on
+   `device` (peer access over NVLink is enabled on the way); release = unmap (opened != 0) or free (opened == 0). These
+   carry the position parts of kmer_b200_adopt_element_parts between the ranks of a multi-process job. */
+int kmer_b200_peer_buffer_create(int device, uint64_t bytes, void **d_ptr, uint8_t *handle64);
+int kmer_b200_peer_buffer_open(int device, const uint8_t *handle64, void **d_ptr);
+int kmer_b200_peer_buffer_release(int device, void *d_ptr, int opened);
 
 /* ---- key-range multi-GPU search: the index stays partitioned (one key-range part per GPU, no assembly), queries
    travel to the GPU that owns the hash of their first k symbols and results travel back. Single-k indices with 32-bit

@@ -463,10 +463,12 @@ class KmerIndex:
         self._adopted.append((positions, directory))
 
     def adopt_element_parts(self, e: int, parts, part_first, directory) -> None:
-        """Peer-positions index: `parts` = one int32 device tensor per key-range part (this GPU's own or another GPU's
-        memory mapped into this process), part_first = n_parts + 1 ascending CSR indices, directory = the whole
-        directory on this GPU. Everything passed is kept alive by this object."""
-        ptrs = (C.c_void_p * len(parts))(*[C.c_void_p(t.data_ptr() if t is not None and t.numel() else 0) for t in parts])
+        """Peer-positions index: `parts` = one int32 device tensor -- or raw device pointer -- per key-range part (this
+        GPU's own or another GPU's memory mapped into this process with peer_buffer_open), part_first = n_parts + 1
+        ascending CSR indices, directory = the whole directory on this GPU. Tensors passed are kept alive by this
+        object; raw pointers must outlive the index."""
+        ptrs = (C.c_void_p * len(parts))(*[C.c_void_p(int(t) if isinstance(t, int) else (t.data_ptr() if t is not None else 0))
+                                            for t in parts])
         first = np.asarray(part_first, dtype=np.uint64)
         _capi.check(self._L.kmer_b200_adopt_element_parts(self._h, e, ptrs, first.ctypes.data_as(_capi.u64p), len(parts),
                                                           C.c_void_p(directory.data_ptr()), directory.numel()))
@@ -567,6 +569,25 @@ class KmerIndex:
     @property
     def device_bytes(self) -> int:
         return int(self._L.kmer_b200_device_bytes(self._h))
+
+
+def peer_buffer_create(device: int, n_bytes: int) -> tuple[int, bytes]:
+    """A device buffer other processes can map: (device pointer, 64-byte CUDA IPC handle)."""
+    p = C.c_void_p()
+    h = C.create_string_buffer(64)
+    _capi.check(_capi.lib().kmer_b200_peer_buffer_create(device, n_bytes, C.byref(p), h))
+    return int(p.value), h.raw
+
+
+def peer_buffer_open(device: int, handle: bytes) -> int:
+    """Map a buffer another process made with peer_buffer_create; kernels on `device` can read it (NVLink)."""
+    p = C.c_void_p()
+    _capi.check(_capi.lib().kmer_b200_peer_buffer_open(device, handle, C.byref(p)))
+    return int(p.value)
+
+
+def peer_buffer_release(device: int, ptr: int, opened: bool) -> None:
+    _capi.check(_capi.lib().kmer_b200_peer_buffer_release(device, C.c_void_p(ptr), 1 if opened else 0))
 
 
 def guard_violations() -> int:

@@ -111,6 +111,9 @@ SYMBOLS = {
     "kmer_b200_export_bucket_sizes": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, u64p]),
     "kmer_b200_directory_from_sizes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "kmer_b200_adopt_element": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
+    "kmer_b200_peer_buffer_create": (C.c_int, [C.c_int, C.c_uint64, C.POINTER(C.c_void_p), C.c_char_p]),
+    "kmer_b200_peer_buffer_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "kmer_b200_peer_buffer_release": (C.c_int, [C.c_int, C.c_void_p, C.c_int]),
     "kmer_b200_adopt_element_parts": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), u64p, C.c_uint32, C.c_void_p,
                                                 C.c_uint64]),
     "kmer_b200_route_plan_make": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_double, C.POINTER(RoutePlan)]),

@@ -2534,6 +2534,8 @@ int kmer_b200_adopt_element_parts(kmer_b200_index *ix, uint32_t e, const uint32_
             return fail(KMER_B200_ERR_INVALID_ARGUMENT, "adopt: a part is not device memory");
         }
         if (attr.device == ix->device) continue;
+        // (memory opened with kmer_b200_peer_buffer_open is readable already; this covers parts on other devices of
+        // THIS process)
         int can = 0;
         cudaDeviceCanAccessPeer(&can, ix->device, attr.device);
         if (!can) return fail(KMER_B200_ERR_UNSUPPORTED, "adopt: this device cannot read the device that holds a part");
@@ -2585,6 +2587,49 @@ int kmer_b200_adopt_element_parts(kmer_b200_index *ix, uint32_t e, const uint32_
     KB_CUDA(cudaMemcpyAsync(ix->d_index, &ix->host_index, sizeof(kb::DeviceIndex), cudaMemcpyHostToDevice, ix->stream));
     KB_CUDA(cudaStreamSynchronize(ix->stream));
     return KMER_B200_OK;
+}
+
+// ---- device buffers shared between processes (one process per GPU): what the peer-positions index reads over NVLink --
+int kmer_b200_peer_buffer_create(int device, uint64_t bytes, void **d_ptr, uint8_t *handle64) {
+    if (!d_ptr || !handle64) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    DeviceGuard guard(device);
+    void *p = nullptr;
+    KB_CUDA(cudaMalloc(&p, std::max<uint64_t>(bytes, 256)));  // a plain allocation: pool memory cannot be exported
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(p);
+        return fail(KMER_B200_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+    }
+    std::memcpy(handle64, &h, 64);
+    *d_ptr = p;
+    return KMER_B200_OK;
+}
+
+int kmer_b200_peer_buffer_open(int device, const uint8_t *handle64, void **d_ptr) {
+    if (!d_ptr || !handle64) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
+    DeviceGuard guard(device);  // mapped into the context of the device whose kernels will read it
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, 64);
+    void *p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(KMER_B200_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+    }
+    *d_ptr = p;
+    return KMER_B200_OK;
+}
+
+int kmer_b200_peer_buffer_release(int device, void *d_ptr, int opened) {
+    if (!d_ptr) return KMER_B200_OK;
+    DeviceGuard guard(device);
+    cudaDeviceSynchronize();
+    const cudaError_t e = opened ? cudaIpcCloseMemHandle(d_ptr) : cudaFree(d_ptr);
+    cudaGetLastError();
+    return e == cudaSuccess ? KMER_B200_OK : fail(KMER_B200_ERR_CUDA, cudaGetErrorString(e));
 }
 
 // ---- FASTA / FASTQ parsing (fastx_kernels.cu) ---------------------------------------------------------------------

@@ -485,37 +485,48 @@ def assemble_replicated(ix, world: int, rank: int, dist, dev, timing=None):
 # collective.
 # ----------------------------------------------------------------------------------------------------------
 class PeerPositions:
-    """Per-element position buffers of all ranks, mapped into every rank. Created once (like a communicator) and reused
-    by every build; a buffer is re-made -- collectively -- when some rank's part outgrows it."""
+    """Per-element position buffers of all ranks, mapped into every rank (kmer_b200_peer_buffer_*: plain device
+    allocations exported and opened through CUDA IPC). Created once (like a communicator) and reused by every build; a
+    buffer is re-made -- collectively -- when some rank's part outgrows it."""
 
     def __init__(self, world: int, rank: int, dist, dev):
         self.world, self.rank, self.dist, self.dev = world, rank, dist, dev
-        self.mine = {}     # element -> this rank's buffer (int32 tensor)
-        self.views = {}    # element -> [tensor per rank], views[rank] is self.mine
-        self.capacity = {}
+        self.ptrs = {}      # element -> [device pointer per rank]; ptrs[e][rank] is this rank's own buffer
+        self.capacity = {}  # element -> entries per buffer
+
+    def _release(self, e: int):
+        import torch
+        from . import peer_buffer_release
+        if e not in self.ptrs:
+            return
+        torch.cuda.synchronize()
+        self.dist.barrier()          # nobody reads a buffer that is about to go away
+        for r, p in enumerate(self.ptrs[e]):
+            if r != self.rank:
+                peer_buffer_release(self.dev.index, p, True)
+        self.dist.barrier()          # every mapping is closed before the owner frees
+        peer_buffer_release(self.dev.index, self.ptrs[e][self.rank], False)
+        del self.ptrs[e], self.capacity[e]
 
     def ensure(self, e: int, need: int):
         """Collective: every rank passes the same `need` (the largest part over all ranks)."""
         import torch
+        from . import peer_buffer_create, peer_buffer_open
         if self.capacity.get(e, 0) >= need:
             return
+        self._release(e)
         cap = int(need * 1.02) + 1024
-        self.views.pop(e, None)
-        self.mine.pop(e, None)
-        mine = torch.empty(cap, dtype=torch.int32, device=self.dev)
-        handle = mine.untyped_storage()._share_cuda_()
+        mine, handle = peer_buffer_create(self.dev.index, cap * 4)
         handles = [None] * self.world
         self.dist.all_gather_object(handles, handle)
-        views = []
-        for r in range(self.world):
-            if r == self.rank:
-                views.append(mine)
-                continue
-            st = torch.UntypedStorage._new_shared_cuda(*handles[r])
-            views.append(torch.empty(0, dtype=torch.int32, device=st.device).set_(st, 0, (cap,)))
-        self.mine[e], self.views[e], self.capacity[e] = mine, views, cap
+        self.ptrs[e] = [mine if r == self.rank else peer_buffer_open(self.dev.index, handles[r]) for r in range(self.world)]
+        self.capacity[e] = cap
         torch.cuda.synchronize()
         self.dist.barrier()
+
+    def close(self):
+        for e in list(self.ptrs):
+            self._release(e)
 
 
 def assemble_peer(ix, world: int, rank: int, dist, dev, peers: PeerPositions, timing=None):
@@ -555,7 +566,7 @@ def assemble_peer(ix, world: int, rank: int, dist, dev, peers: PeerPositions, ti
         assert sum(counts) == n_kmers, (counts, n_kmers)
         peers.ensure(e, max(counts))
         if counts[rank]:
-            peers.mine[e][:counts[rank]].copy_(_dev_view(part.d_positions, counts[rank], dev))
+            _dev_view(peers.ptrs[e][rank], counts[rank], dev).copy_(_dev_view(part.d_positions, counts[rank], dev))
         dir_full = torch.empty(key_space + 1, dtype=torch.int32, device=dev)
         widths = {his[r] - los[r] for r in range(world)}
         equal = len(widths) == 1 and his[-1] == key_space and los[0] == 0
@@ -586,7 +597,7 @@ def assemble_peer(ix, world: int, rank: int, dist, dev, peers: PeerPositions, ti
         del sizes
         # every rank's copy into its shared buffer precedes its contribution to the directory exchange in stream
         # order, so once the exchange has completed here the other ranks' parts are in place
-        ix.adopt_element_parts(e, [peers.views[e][r][:counts[r]] for r in range(world)], bases + [n_kmers], dir_full)
+        ix.adopt_element_parts(e, [int(p) for p in peers.ptrs[e]], bases + [n_kmers], dir_full)
         mark("adopt")
 
 

@@ -134,6 +134,7 @@ def main():
                     assert_results_equal(got, want, label=f"routed x{world} {ks} attempt {attempt}")
             ix.close()
         dist.barrier()
+    peer_buffers.close()
     if rank == 0:
         print(f"MULTI_GPU_PARITY_OK {world}", flush=True)
     dist.destroy_process_group()
