@@ -388,6 +388,9 @@ void kmer_b200_last_search_transfer(const kmer_b200_index *index, uint64_t *h2d_
 /* Calibration of the random-gather ceiling: n_gathers independent 8-byte reads at random addresses of a
    table_bytes table (>> L2); *ms_out = device time. sectors/s = n_gathers / time. */
 int kmer_b200_gather_probe(uint64_t table_bytes, uint64_t n_gathers, void *stream, double *ms_out);
+/* The same probe over a table the caller provides (device memory of this GPU, or another GPU's memory mapped with
+   kmer_b200_peer_buffer_open: the random-read rate over NVLink). */
+int kmer_b200_gather_probe_at(const void *d_table, uint64_t table_bytes, uint64_t n_gathers, void *stream, double *ms_out);
 
 /* ---- scalar helpers kept from the reference API */
 /* kmer::detail::fast_pow (fast_pow.hpp:46-93): base^exp mod 2^64, 0 when exp >= 63 and base != 1 */

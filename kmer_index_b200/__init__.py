@@ -571,6 +571,13 @@ class KmerIndex:
         return int(self._L.kmer_b200_device_bytes(self._h))
 
 
+def gather_probe_at(ptr: int, table_bytes: int, n_gathers: int = 1 << 26, stream: int | None = None) -> float:
+    """Independent 8-byte reads per second from the given device table (local memory or a mapped peer buffer)."""
+    ms = C.c_double(0)
+    _capi.check(_capi.lib().kmer_b200_gather_probe_at(C.c_void_p(ptr), table_bytes, n_gathers, C.c_void_p(stream), C.byref(ms)))
+    return n_gathers / (ms.value * 1e-3)
+
+
 def peer_buffer_create(device: int, n_bytes: int) -> tuple[int, bytes]:
     """A device buffer other processes can map: (device pointer, 64-byte CUDA IPC handle)."""
     p = C.c_void_p()

@@ -1213,6 +1213,14 @@ int search_begin(kmer_b200_index *ix, const uint8_t *d_q, const uint64_t *d_off,
     a.bits = ix->bits;
     a.single_k = ix->ks.size() == 1;
     a.views = (ix->cfg.reserved & KMER_B200_FLAG_SHARED_POSITIONS) ? 1 : 0;
+    {
+        // element 0's position parts travel in the launch parameters (constant bank): the lean kernel resolves a part
+        // without touching memory
+        const kb::Element &E0 = ix->elems[0].dev;
+        a.parts0.n = E0.n_pos_parts;
+        for (int r = 0; r <= kb::kMaxPosParts; ++r) a.parts0.first[r] = E0.part_first[r];
+        for (int r = 0; r < kb::kMaxPosParts; ++r) a.parts0.ptr[r] = E0.pos_part[r];
+    }
     a.lean_ok = a.single_k && ix->sigma == 4 && ix->elems[0].dev.shift == 0 && ix->elems[0].key_bytes == 4 && !d_present4 &&
                 !d_present_global && ix->cfg.profile < 2 && !std::getenv("KMER_B200_NO_LEAN");
     a.error_flag = p->d_flags;  // per search: a second search on the handle cannot clobber a pending one's flags
@@ -2595,7 +2603,11 @@ int kmer_b200_peer_buffer_create(int device, uint64_t bytes, void **d_ptr, uint8
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
     DeviceGuard guard(device);
     void *p = nullptr;
-    KB_CUDA(cudaMalloc(&p, std::max<uint64_t>(bytes, 256)));  // a plain allocation: pool memory cannot be exported
+    // A plain allocation (pool memory cannot be exported) whose size is a multiple of 2 MiB: measured on B200
+    // (profiles/tools/ipc_probe.py), an imported allocation of any other size is mapped with small pages and random reads
+    // from it run at 0.1 G/s instead of 6.8 G/s.
+    bytes = (std::max<uint64_t>(bytes, 1) + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+    KB_CUDA(cudaMalloc(&p, bytes));
     cudaIpcMemHandle_t h;
     const cudaError_t e = cudaIpcGetMemHandle(&h, p);
     if (e != cudaSuccess) {
@@ -3433,6 +3445,30 @@ int kmer_b200_gather_probe(uint64_t table_bytes, uint64_t n_gathers, void *strea
     cudaEventDestroy(a);
     cudaEventDestroy(b);
     cudaFree(table);
+    cudaFree(sink);
+    if (e != cudaSuccess) return fail(KMER_B200_ERR_CUDA, cudaGetErrorString(e));
+    *ms_out = ms;
+    return KMER_B200_OK;
+}
+
+int kmer_b200_gather_probe_at(const void *d_table, uint64_t table_bytes, uint64_t n_gathers, void *stream, double *ms_out) {
+    if (!ms_out || !d_table || table_bytes < 4096 || n_gathers == 0) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad probe arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint64_t *sink = nullptr;
+    const uint64_t n_words = table_bytes / 8;
+    KB_CUDA(cudaMalloc((void **)&sink, 8));
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    kb::launch_gather_probe((const uint64_t *)d_table, n_words, std::min<uint64_t>(n_gathers, 1u << 24), sink, st);  // warm-up
+    cudaEventRecord(a, st);
+    kb::launch_gather_probe((const uint64_t *)d_table, n_words, n_gathers, sink, st);
+    cudaEventRecord(b, st);
+    cudaError_t e = cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
     cudaFree(sink);
     if (e != cudaSuccess) return fail(KMER_B200_ERR_CUDA, cudaGetErrorString(e));
     *ms_out = ms;

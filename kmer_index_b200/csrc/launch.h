@@ -74,6 +74,11 @@ struct SearchArgs {
     uint32_t single_k;               // the index has one element: launch the kernels compiled without the multi-k plans
     uint32_t lean_ok;                // host-checked: single k, dna4 (2-bit symbols), dense 32-bit directory, plain count pass ->
                                      // search_lean.cu may take the count pass when max_len <= 128
+    struct {                         // Element::n_pos_parts / part_first / pos_part of element 0 (peer-positions index)
+        uint32_t n;
+        uint32_t first[kMaxPosParts + 1];
+        const uint32_t *ptr[kMaxPosParts];
+    } parts0;
     uint32_t views;                  // shared-positions index (Element::width != 1 exists): the warp-per-query kernels compiled
                                      // with view support run every pass
     uint32_t *heavy;                 // device or null, u32[1 + Q]: [0] = number of heavy queries, then their ids

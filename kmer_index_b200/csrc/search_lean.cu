@@ -209,7 +209,14 @@ __global__ void __launch_bounds__(kLeanThreads, MIN_BLOCKS) search_count_lean_ke
         n_hits = seed.cnt;
     } else {
         const uint32_t last_q = (P - 1) * k;
-        const uint32_t *cand = pos_ptr(E, seed.lo);  // a bucket lies in one part of a peer-positions index
+        // a bucket lies in one part of a peer-positions index; the part table sits in the launch parameters
+        const uint32_t *cand = E.pos + seed.lo;
+        if (a.parts0.n != 0 && seed.cnt != 0) {
+            uint32_t r = 0;
+#pragma unroll
+            for (uint32_t j = 1; j < (uint32_t)kMaxPosParts; ++j) r += (j < a.parts0.n && seed.lo >= (uint64_t)a.parts0.first[j]) ? 1u : 0u;
+            cand = a.parts0.ptr[r] + (seed.lo - a.parts0.first[r]);
+        }
         for (uint64_t c = 0; c < seed.cnt; ++c) {
             const uint32_t at = gather32(cand + c);
             if (at < seed_d) continue;

@@ -1,51 +1,37 @@
 #!/usr/bin/env python
-"""Can one torchrun rank map another rank's device buffer (CUDA IPC through torch's storage sharing) and read it from
-a kernel? Prints the per-rank result and the P2P read bandwidth. Used to decide on the peer-positions multi-GPU mode."""
+"""Random-read rate from another rank's device buffer mapped through CUDA IPC (kmer_b200_peer_buffer_*), next to the
+same reads from local memory: what the peer-positions search pays per foreign candidate list. Run under torchrun."""
 import os
-import time
 
 import torch
 import torch.distributed as dist
 
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import kmer_index_b200 as kb  # noqa: E402
+
 
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
-    dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    n = 1 << 28
-    mine = torch.full((n,), rank + 1, dtype=torch.int32, device=dev)
-    handle = mine.untyped_storage()._share_cuda_()
+    n_bytes = int(os.environ.get("PROBE_BYTES", 4 << 30))
+    mine, handle = kb.peer_buffer_create(local, n_bytes)
     handles = [None] * world
     dist.all_gather_object(handles, handle)
-    peers = []
-    for r in range(world):
-        if r == rank:
-            peers.append(mine)
-            continue
-        st = torch.UntypedStorage._new_shared_cuda(*handles[r])
-        peers.append(torch.empty(0, dtype=torch.int32, device=dev).set_(st, 0, (n,)))
+    other = kb.peer_buffer_open(local, handles[(rank + 1) % world])
     torch.cuda.synchronize()
     dist.barrier()
-    ok = all(int(peers[r][12345].item()) == r + 1 and int(peers[r][-1].item()) == r + 1 for r in range(world))
-    other = peers[(rank + 1) % world]
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(5):
-        s = other.sum()
-    torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / 5
-    idx = torch.randint(0, n, (1 << 24,), device=dev)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(5):
-        g = other[idx]
-    torch.cuda.synchronize()
-    dg = (time.perf_counter() - t0) / 5
-    print(f"rank {rank}: peers readable {ok}; streaming read of a peer {n * 4 / dt / 1e9:.0f} GB/s; "
-          f"random 4-byte reads from a peer {idx.numel() / dg / 1e9:.2f} G/s (ptr {other.data_ptr():#x})", flush=True)
+    here = kb.gather_probe_at(mine, n_bytes)
+    there = kb.gather_probe_at(other, n_bytes)
+    print(f"rank {rank}: local {here / 1e9:.2f} G reads/s, peer (IPC mapping of rank {(rank + 1) % world}) {there / 1e9:.2f} G reads/s",
+          flush=True)
     dist.barrier()
-    del peers, other
+    kb.peer_buffer_release(local, other, True)
+    dist.barrier()
+    kb.peer_buffer_release(local, mine, False)
     dist.destroy_process_group()
 
 

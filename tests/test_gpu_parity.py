@@ -363,6 +363,48 @@ def test_key_range_parts_assemble_to_the_whole_index(kb, oracle_mod, sigma, ks, 
             ix.close()
 
 
+@pytest.mark.parametrize("sigma,ks,n,parts", [(4, [12], 300_000, 4), (4, [16], 400_000, 8), (4, [5, 7, 9, 11, 13], 200_000, 3)])
+def test_positions_left_in_parts_answer_like_the_whole_index(kb, oracle_mod, sigma, ks, n, parts):
+    """Peer-positions multi-GPU index, emulated on one GPU: the directory is assembled whole, the position array stays
+    in the key-range parts (here: separate buffers of the same GPU) and kmer_b200_adopt_element_parts points at them."""
+    import torch
+
+    from kmer_index_b200 import sharded, synth
+    dev = torch.device("cuda", 0)
+    text = synth.random_text(n, sigma, 73)
+    text[1000:4400] = 0                                      # a bucket beyond the heavy threshold, in one part
+    q, off = synth.stress_queries(text, 4000, 1, 48, sigma, 74)
+    stream = torch.cuda.current_stream().cuda_stream
+    idx = [kb.KmerIndex(text, sigma, ks, key_part=r, key_parts=parts, stream=stream or None) for r in range(parts)]
+    try:
+        with oracle_mod.Oracle(text, sigma, ks) as o:
+            want = o.search(q, off)
+        for e, k in enumerate(ks):
+            ps = [ix.element_part(e) for ix in idx]
+            bufs, first = [], [0]
+            dir_full = torch.empty(sigma ** k + 1, dtype=torch.int32, device=dev)
+            for r, (ix, p) in enumerate(zip(idx, ps)):
+                buf = torch.empty(max(p.n_kmers, 1), dtype=torch.int32, device=dev)
+                if p.n_kmers:
+                    buf[:p.n_kmers].copy_(sharded._dev_view(p.d_positions, p.n_kmers, dev))
+                bufs.append(buf)
+                n_dir = p.key_hi - p.key_lo + (1 if r == parts - 1 else 0)
+                ix.export_directory(e, first[-1], n_dir, dir_full.data_ptr() + 4 * p.key_lo)
+                first.append(first[-1] + p.n_kmers)
+            torch.cuda.synchronize()
+            idx[0].adopt_element_parts(e, bufs, first, dir_full)
+            with pytest.raises(kb.KmerB200Error):
+                idx[0].element_arrays(e)                     # the positions are not one array any more
+        for attempt in range(2):
+            assert_results_equal(idx[0].search_batch(q, off).as_tuple(), want, label=f"positions in parts {ks} x{parts}/{attempt}")
+        if len(ks) == 1:
+            assert_results_equal(idx[0].search_batch(q, off, mode=kb.MODE_CORRECT).as_tuple(), oracle_mod.Oracle.truth(text, q, off),
+                                 label="positions in parts, CORRECT mode")
+    finally:
+        for ix in idx:
+            ix.close()
+
+
 @pytest.mark.parametrize("sigma,k,n,parts", [(4, 12, 300_000, 4), (4, 16, 400_000, 8), (4, 10, 3_000_000, 2)])
 def test_directory_parts_travel_as_bucket_sizes(kb, sigma, k, n, parts):
     """The replicated multi-GPU build ships every part's directory as one byte per bucket and rebuilds the whole
