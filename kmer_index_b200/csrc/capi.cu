@@ -2516,12 +2516,12 @@ int kmer_b200_adopt_element(kmer_b200_index *ix, uint32_t e, const uint32_t *d_p
     return adopt_element_impl(ix, e, d_positions, n_kmers, d_directory, directory_entries, 1);
 }
 
-int kmer_b200_adopt_element_parts(kmer_b200_index *ix, uint32_t e, const uint32_t *const *d_position_parts,
-                                  const uint64_t *part_first, uint32_t n_parts, const uint32_t *d_directory,
-                                  uint64_t directory_entries) {
+// library_owned: the multi-device handle's own assembly -- the directory was allocated by the library and this index's own
+// part (he.d_pos, one of the parts) stays its property; otherwise everything passed belongs to the caller.
+static int adopt_parts_impl(kmer_b200_index *ix, uint32_t e, const uint32_t *const *d_position_parts, const uint64_t *part_first,
+                            uint32_t n_parts, const uint32_t *d_directory, uint64_t directory_entries, bool library_owned) {
     if (!ix || !d_position_parts || !part_first || !d_directory || e >= ix->ks.size())
         return fail(KMER_B200_ERR_INVALID_ARGUMENT, "bad argument");
-    if (!ix->replicas.empty()) return fail(KMER_B200_ERR_UNSUPPORTED, "not available on a multi-device handle");
     if (ix->cfg.reserved & KMER_B200_FLAG_SHARED_POSITIONS) return fail(KMER_B200_ERR_UNSUPPORTED, "adopt: not on a shared-positions index");
     if (n_parts == 0 || n_parts > (uint32_t)kb::kMaxPosParts) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "adopt: 1 to 8 parts");
     HostElement &he = ix->elems[e];
@@ -2557,14 +2557,14 @@ int kmer_b200_adopt_element_parts(kmer_b200_index *ix, uint32_t e, const uint32_
     std::lock_guard<std::mutex> lock(ix->mu);
     if (he.adopted != 1) {
         dev_free(ix, he.d_dir);
-        dev_free(ix, he.d_pos);
+        if (!library_owned) dev_free(ix, he.d_pos);
         ix->device_bytes -= he.bytes;
     }
     dev_free(ix, (uint8_t *)he.d_keys);
     he.d_keys = nullptr;
-    he.adopted = 1;
+    he.adopted = library_owned ? 2 : 1;
     he.in_parts = true;
-    he.d_pos = nullptr;
+    if (!library_owned) he.d_pos = nullptr;  // (library_owned: still this index's part, freed with the index)
     he.d_dir = const_cast<uint32_t *>(d_directory);
     he.dev.shift = 0;
     he.dev.n_kmers = n_kmers;
@@ -2578,6 +2578,11 @@ int kmer_b200_adopt_element_parts(kmer_b200_index *ix, uint32_t e, const uint32_
     for (uint32_t r = 0; r <= n_parts; ++r) he.dev.part_first[r] = (uint32_t)part_first[r];
     for (uint32_t r = 0; r < n_parts; ++r) he.dev.pos_part[r] = d_position_parts[r];
     he.bytes = directory_entries * 4;
+    if (library_owned) {
+        for (uint32_t r = 0; r < n_parts; ++r)
+            if (d_position_parts[r] == he.d_pos) he.bytes += (part_first[r + 1] - part_first[r]) * 4;
+        ix->device_bytes += he.bytes;
+    }
     ix->host_index.elem[e] = he.dev;
     bool all = true;
     for (size_t i = 0; i < ix->ks.size(); ++i) all = all && ix->elems[i].adopted != 0;
@@ -2595,6 +2600,13 @@ int kmer_b200_adopt_element_parts(kmer_b200_index *ix, uint32_t e, const uint32_
     KB_CUDA(cudaMemcpyAsync(ix->d_index, &ix->host_index, sizeof(kb::DeviceIndex), cudaMemcpyHostToDevice, ix->stream));
     KB_CUDA(cudaStreamSynchronize(ix->stream));
     return KMER_B200_OK;
+}
+
+int kmer_b200_adopt_element_parts(kmer_b200_index *ix, uint32_t e, const uint32_t *const *d_position_parts,
+                                  const uint64_t *part_first, uint32_t n_parts, const uint32_t *d_directory,
+                                  uint64_t directory_entries) {
+    if (ix && !ix->replicas.empty()) return fail(KMER_B200_ERR_UNSUPPORTED, "not available on a multi-device handle");
+    return adopt_parts_impl(ix, e, d_position_parts, part_first, n_parts, d_directory, directory_entries, false);
 }
 
 // ---- device buffers shared between processes (one process per GPU): what the peer-positions index reads over NVLink --
@@ -3074,6 +3086,74 @@ static int create_multi(const uint8_t *ranks, uint64_t n, uint32_t sigma, const 
         std::vector<uint64_t> base(N + 1, 0);
         for (uint32_t i = 0; i < N; ++i) base[i + 1] = base[i] + reps[i]->elems[e].dev.n_kmers;
         if (base[N] != n_kmers) return bail(KMER_B200_ERR_CUDA, "multi-device build: the parts do not add up to the whole index");
+        // Preferred assembly (up to 8 devices, no bucket beyond 254 entries, equal key ranges): the positions stay where
+        // they were sorted -- every device reads the other devices' parts over NVLink (peer access, same process) -- and
+        // only the directory is made whole everywhere, shipped as one byte per bucket and prefix-summed on arrival.
+        if (N <= (uint32_t)kb::kMaxPosParts) {
+            std::vector<uint8_t *> sizes(N, nullptr), sizes_full(N, nullptr);
+            std::vector<uint32_t *> dir_whole(N, nullptr);
+            auto drop = [&] {
+                for (uint32_t d = 0; d < N; ++d) {
+                    DeviceGuard g(ids[d]);
+                    dev_free(reps[d], sizes[d]);
+                    dev_free(reps[d], sizes_full[d]);
+                    sizes[d] = sizes_full[d] = nullptr;
+                }
+            };
+            bool ok = true;
+            uint64_t width0 = reps[0]->elems[e].dev.key_hi - reps[0]->elems[e].dev.key_lo;
+            for (uint32_t i = 0; ok && i < N; ++i) {
+                DeviceGuard g(ids[i]);
+                const HostElement &he = reps[i]->elems[e];
+                const uint64_t w = he.dev.key_hi - he.dev.key_lo;
+                ok = he.dev.shift == 0 && he.dev.key_lo == (uint64_t)i * width0 && (w == width0 || i + 1 == N);
+                uint64_t n_large = 0;
+                if (ok) ok = dev_alloc(reps[i], &sizes[i], std::max<uint64_t>(w, 1), false) == 0 &&
+                             kmer_b200_export_bucket_sizes(reps[i], e, sizes[i], &n_large) == 0 && n_large == 0;
+            }
+            for (uint32_t d = 0; ok && d < N; ++d) {
+                DeviceGuard g(ids[d]);
+                ok = dev_alloc(reps[d], &sizes_full[d], key_space, false) == 0 && dev_alloc(reps[d], &dir_whole[d], key_space + 1, false) == 0;
+                if (ok) ok = cudaStreamSynchronize(reps[d]->stream) == cudaSuccess;  // the allocations exist before peers write them
+            }
+            for (uint32_t i = 0; ok && i < N; ++i) {
+                DeviceGuard g(ids[i]);
+                const HostElement &he = reps[i]->elems[e];
+                const uint64_t w = he.dev.key_hi - he.dev.key_lo;
+                for (uint32_t d = 0; w && d < N; ++d)
+                    cudaMemcpyPeerAsync(sizes_full[d] + he.dev.key_lo, ids[d], sizes[i], ids[i], w, reps[i]->stream);
+            }
+            for (uint32_t i = 0; ok && i < N; ++i) {
+                DeviceGuard g(ids[i]);
+                ok = cudaStreamSynchronize(reps[i]->stream) == cudaSuccess && cudaGetLastError() == cudaSuccess;
+            }
+            for (uint32_t d = 0; ok && d < N; ++d) {
+                DeviceGuard g(ids[d]);
+                ok = kmer_b200_directory_from_sizes(reps[d], sizes_full[d], key_space, dir_whole[d]) == 0;
+            }
+            if (ok) {
+                std::vector<const uint32_t *> part_ptrs(N);
+                for (uint32_t i = 0; i < N; ++i) part_ptrs[i] = reps[i]->elems[e].d_pos;
+                for (uint32_t d = 0; ok && d < N; ++d) {
+                    DeviceGuard g(ids[d]);
+                    ok = cudaStreamSynchronize(reps[d]->stream) == cudaSuccess &&
+                         adopt_parts_impl(reps[d], e, part_ptrs.data(), base.data(), N, dir_whole[d], key_space + 1, true) == 0;
+                    if (ok) dir_whole[d] = nullptr;  // the index owns it now
+                }
+                if (!ok) {
+                    drop();
+                    return bail(KMER_B200_ERR_CUDA, "multi-device build: adopting the parts failed: " + g_last_error);
+                }
+                drop();
+                continue;
+            }
+            cudaGetLastError();
+            drop();
+            for (uint32_t d = 0; d < N; ++d) {
+                DeviceGuard g(ids[d]);
+                dev_free(reps[d], dir_whole[d]);
+            }
+        }
         std::vector<uint32_t *> pos_full(N, nullptr), dir_full(N, nullptr);
         for (uint32_t d = 0; d < N; ++d) {
             DeviceGuard g(ids[d]);
