@@ -3028,12 +3028,31 @@ static int create_multi(const uint8_t *ranks, uint64_t n, uint32_t sigma, const 
         for (uint32_t j = 0; j < i; ++j)
             if (ids[j] == ids[i]) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "duplicate device id");
     }
+    bool pool_shared = true;  // every device may read the other devices' pool allocations from a kernel
     {
         DeviceGuard keep(ids[0]);
         for (uint32_t i = 0; i < N; ++i) {
             cudaSetDevice(ids[i]);
             for (uint32_t j = 0; j < N; ++j)
                 if (j != i) cudaDeviceEnablePeerAccess(ids[j], 0);  // direct NVLink copies; staged through the host otherwise
+            cudaGetLastError();
+            // the library allocates from the device's stream-ordered pool, which peer access does not cover by itself:
+            // kernels on the other devices read this device's position part
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, ids[i]) == cudaSuccess) {
+                std::vector<cudaMemAccessDesc> acc;
+                for (uint32_t j = 0; j < N; ++j) {
+                    if (j == i) continue;
+                    cudaMemAccessDesc d{};
+                    d.location.type = cudaMemLocationTypeDevice;
+                    d.location.id = ids[j];
+                    d.flags = cudaMemAccessFlagsProtReadWrite;
+                    acc.push_back(d);
+                }
+                if (!acc.empty() && cudaMemPoolSetAccess(pool, acc.data(), acc.size()) != cudaSuccess) pool_shared = false;
+            } else {
+                pool_shared = false;
+            }
             cudaGetLastError();
         }
     }
@@ -3089,7 +3108,7 @@ static int create_multi(const uint8_t *ranks, uint64_t n, uint32_t sigma, const 
         // Preferred assembly (up to 8 devices, no bucket beyond 254 entries, equal key ranges): the positions stay where
         // they were sorted -- every device reads the other devices' parts over NVLink (peer access, same process) -- and
         // only the directory is made whole everywhere, shipped as one byte per bucket and prefix-summed on arrival.
-        if (N <= (uint32_t)kb::kMaxPosParts) {
+        if (N <= (uint32_t)kb::kMaxPosParts && pool_shared) {
             std::vector<uint8_t *> sizes(N, nullptr), sizes_full(N, nullptr);
             std::vector<uint32_t *> dir_whole(N, nullptr);
             auto drop = [&] {
