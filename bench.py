@@ -381,6 +381,7 @@ def run_ours(args, wl):
         h_off = q_off.cpu().pin_memory()
         eb, es = [], []
         d2h = 0
+        host_path = None
         for it in range(min(args.warmup, 1) + args.steps):
             barrier()
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -401,6 +402,7 @@ def run_ours(args, wl):
                 # the plain C-ABI host call: the library reports what it actually put on the link (16-bit lengths
                 # instead of offsets, packed ranks for pageable input)
                 abi_h2d, abi_d2h = ix.last_search_transfer()
+                host_path = ix.last_search_host_path()
             res.free()
             ix.close()
             if it >= min(args.warmup, 1):
@@ -410,7 +412,8 @@ def run_ours(args, wl):
         h2d_q = (n_sym + (Ql + 1) * 8) // (1 if parted else world)
         if not routed and (world == 1 or replicated):
             h2d_q, d2h = abi_h2d, abi_d2h
-        e2e = {"build_ms": float(np.mean(eb)), "search_ms": float(np.mean(es)), "h2d": n_local + h2d_q, "d2h": d2h}
+        e2e = {"build_ms": float(np.mean(eb)), "search_ms": float(np.mean(es)), "h2d": n_local + h2d_q, "d2h": d2h,
+               "host_path": host_path}
         del h_text, h_q, h_off
 
     # ---- max over ranks
@@ -535,6 +538,8 @@ def run_ours(args, wl):
                            "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
                            "search_ms": e2e["search_ms"], "build_ms": e2e["build_ms"],
                            "build_gbases_per_s": n / (e2e["build_ms"] * 1e-3) / 1e9}
+            if e2e.get("host_path"):   # which host pipeline kmer_b200_search_batch chose (rank 0's view)
+                line["e2e"]["host_path"] = e2e["host_path"]
         if not args.no_cpu_baseline and world == 1:
             r = cpu_reference_sample(wl, 3, 0)
             line["cpu_baseline"] = {"value": r["search_qps"], "unit": "queries/s", "cores": r["cores"], "kind": r["kind"],

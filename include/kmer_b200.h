@@ -385,12 +385,24 @@ uint64_t kmer_b200_last_search_gathers(const kmer_b200_index *index);
 /* Bytes the last kmer_b200_search_batch / _ptrs / _text on this handle moved over PCIe: host to device (ranks as they are
    or packed, offsets or 16-bit lengths -- whichever the call chose) and device to host (offsets, status, positions). */
 void kmer_b200_last_search_transfer(const kmer_b200_index *index, uint64_t *h2d_bytes, uint64_t *d2h_bytes);
+/* Which host pipeline that call took: 0 = one copy each way (small batches), 1 = chunks of 1-byte ranks, 2 = chunks packed
+   query by query on the host threads, 3 = chunks packed as a stream on the host threads (+ raw_pct percent of the chunks
+   sent as 1-byte ranks at the same time; pack_gbs = the host's measured streaming pack rate, 0 when not needed). */
+void kmer_b200_last_search_host_path(const kmer_b200_index *index, uint32_t *pipeline, uint32_t *raw_pct, double *pack_gbs);
 /* Calibration of the random-gather ceiling: n_gathers independent 8-byte reads at random addresses of a
    table_bytes table (>> L2); *ms_out = device time. sectors/s = n_gathers / time. */
 int kmer_b200_gather_probe(uint64_t table_bytes, uint64_t n_gathers, void *stream, double *ms_out);
 /* The same probe over a table the caller provides (device memory of this GPU, or another GPU's memory mapped with
    kmer_b200_peer_buffer_open: the random-read rate over NVLink). */
 int kmer_b200_gather_probe_at(const void *d_table, uint64_t table_bytes, uint64_t n_gathers, void *stream, double *ms_out);
+
+/* Host-side helper of kmer_b200_search_batch, exposed for tests and for callers that keep batches packed: n ranks
+   (1 byte each) -> the device's b-bit MSB-first words (b = 2 for sigma <= 4, 4 for sigma <= 16, else 8), query
+   boundaries ignored; packed with all threads of the library's host pool. words must hold
+   kmer_b200_host_pack_stream_words(n, sigma) entries. Returns KMER_B200_ERR_INVALID_RANK when a rank >= sigma was seen.
+   Needs no device. */
+uint64_t kmer_b200_host_pack_stream_words(uint64_t n, uint32_t sigma);
+int kmer_b200_host_pack_stream(const uint8_t *ranks, uint64_t n, uint32_t sigma, uint64_t *words);
 
 /* ---- scalar helpers kept from the reference API */
 /* kmer::detail::fast_pow (fast_pow.hpp:46-93): base^exp mod 2^64, 0 when exp >= 63 and base != 1 */

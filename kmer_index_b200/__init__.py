@@ -561,6 +561,13 @@ class KmerIndex:
         self._L.kmer_b200_last_search_transfer(self._h, C.byref(a), C.byref(b))
         return int(a.value), int(b.value)
 
+    def last_search_host_path(self) -> dict:
+        """Which host pipeline the last host-buffer search took (kmer_b200_last_search_host_path)."""
+        a, b, r = C.c_uint32(0), C.c_uint32(0), C.c_double(0)
+        self._L.kmer_b200_last_search_host_path(self._h, C.byref(a), C.byref(b), C.byref(r))
+        names = {0: "single copy", 1: "raw chunks", 2: "per-query host pack", 3: "streaming host pack + raw chunks"}
+        return {"pipeline": names.get(int(a.value), str(a.value)), "raw_chunk_pct": int(b.value), "host_pack_gbs": float(r.value)}
+
     @property
     def last_search_gathers(self) -> int:
         """profile=2: 32-byte sectors the last search gathered at data-dependent addresses."""
@@ -595,6 +602,16 @@ def peer_buffer_open(device: int, handle: bytes) -> int:
 
 def peer_buffer_release(device: int, ptr: int, opened: bool) -> None:
     _capi.check(_capi.lib().kmer_b200_peer_buffer_release(device, C.c_void_p(ptr), 1 if opened else 0))
+
+
+def host_pack_stream(ranks, sigma: int) -> np.ndarray:
+    """1-byte ranks -> the device's b-bit MSB-first words (query boundaries ignored), packed by the library's host
+    thread pool: what a large host batch is turned into before it crosses PCIe. Needs no device."""
+    r = np.ascontiguousarray(np.asarray(ranks, dtype=np.uint8))
+    L = _capi.lib()
+    words = np.empty(int(L.kmer_b200_host_pack_stream_words(r.size, sigma)), dtype=np.uint64)
+    _capi.check(L.kmer_b200_host_pack_stream(r.ctypes.data_as(_capi.u8p), r.size, sigma, words.ctypes.data_as(_capi.u64p)))
+    return words
 
 
 def guard_violations() -> int:

@@ -140,8 +140,11 @@ SYMBOLS = {
     "kmer_b200_debug_guard_selftest": (C.c_int, []),
     "kmer_b200_last_search_gathers": (C.c_uint64, [C.c_void_p]),
     "kmer_b200_last_search_transfer": (None, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "kmer_b200_last_search_host_path": (None, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_double)]),
     "kmer_b200_gather_probe": (C.c_int, [C.c_uint64, C.c_uint64, C.c_void_p, C.POINTER(C.c_double)]),
     "kmer_b200_gather_probe_at": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.POINTER(C.c_double)]),
+    "kmer_b200_host_pack_stream_words": (C.c_uint64, [C.c_uint64, C.c_uint32]),
+    "kmer_b200_host_pack_stream": (C.c_int, [u8p, C.c_uint64, C.c_uint32, u64p]),
     "kmer_b200_fast_pow": (C.c_uint64, [C.c_uint64, C.c_uint8]),
     "kmer_b200_hash": (C.c_uint64, [u8p, C.c_uint32, C.c_uint32]),
     "kmer_b200_choose_best_k": (C.c_uint64, [u64p, C.c_uint64, C.c_uint64, u64p]),

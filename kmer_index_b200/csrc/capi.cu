@@ -211,6 +211,9 @@ struct kmer_b200_index {
     unsigned long long *d_gathers = nullptr;  // profile mode: sectors gathered by the last search
     uint64_t last_gathers = 0;
     uint64_t last_h2d = 0, last_d2h = 0;  // bytes the last host-buffer search moved over PCIe (kmer_b200_last_search_transfer)
+    uint32_t last_host_path = 0, last_raw_pct = 0;  // which host pipeline it took (kmer_b200_last_search_host_path)
+    double last_pack_gbs = 0;
+    uint32_t host_sharers = 1;  // devices of a multi-device handle searching at the same time: they share the host packers
     uint64_t device_bytes = 0;
     bool reaches_end = true;  // the local slice ends at the end of the whole text
     bool sharded = false;
@@ -923,6 +926,158 @@ int translate_on_device(kmer_b200_index *ix, uint8_t *d_data, uint64_t n, const 
     return 0;
 }
 
+// The two copy streams of a device (H2D / D2H next to the compute stream). Stream creation costs milliseconds: they
+// are created once per device and shared (host calls on one device are short critical sections; the per-index mutex
+// orders a handle's own work).
+static int ensure_copy_streams(kmer_b200_index *ix) {
+    if (ix->copy_in) return 0;
+    static std::mutex mu;
+    static cudaStream_t cached[64][2] = {};
+    std::lock_guard<std::mutex> lock(mu);
+    const int d = ix->device & 63;
+    if (!cached[d][0]) {
+        KB_CUDA(cudaStreamCreateWithFlags(&cached[d][0], cudaStreamNonBlocking));
+        KB_CUDA(cudaStreamCreateWithFlags(&cached[d][1], cudaStreamNonBlocking));
+    }
+    ix->copy_in = cached[d][0];
+    ix->copy_out = cached[d][1];
+    return 0;
+}
+
+// Streaming pack rate of this host (input bytes per second, all pool threads), measured once per process on the first
+// large batch: decides how many chunks of a pinned batch travel raw (search_batch_host_stream).
+static double stream_pack_rate(const uint8_t *ranks, uint64_t n, uint32_t bits, uint32_t sigma) {
+    static std::mutex mu;
+    static double rate = 0;
+    std::lock_guard<std::mutex> lock(mu);
+    if (rate > 0) return rate;
+    kb::HostPool &pool = kb::HostPool::instance();
+    const unsigned T = pool.threads();
+    const uint64_t ns = std::min<uint64_t>(n, 256ull << 20);
+    std::vector<uint64_t> words(kb::pack_stream_words(ns, bits) + 1, 0);
+    double best = 1e30;
+    for (int rep = 0; rep < 2; ++rep) {  // the first pass warms the pool and the pages
+        const auto t0 = std::chrono::steady_clock::now();
+        pool.run(T * 4, [&](unsigned t) { kb::pack_stream_host(ranks, ns, bits, sigma, words.data(), t, T * 4); });
+        best = std::min(best, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    }
+    rate = std::max(1e8, (double)ns / best);
+    return rate;
+}
+
+// The share of raw chunks that makes "pack the stream chunks" and "move all chunks over the link" take equally long:
+// x = packed share, x / r = ((1 - x) + x b / 8) / L. The packers lose some memory bandwidth to the DMA: r is derated.
+static uint32_t raw_chunk_percent(double pack_rate, uint32_t bits) {
+    double link = 52e9;
+    if (const char *env = std::getenv("KMER_B200_LINK_GBS")) link = std::max(1.0, std::atof(env)) * 1e9;
+    const double r = 0.85 * pack_rate;
+    const double x = (1.0 / link) / (1.0 / r + (1.0 - bits / 8.0) / link);
+    const double raw = 100.0 * (1.0 - std::min(1.0, x));
+    return (uint32_t)std::max(0.0, std::min(100.0, raw + 0.5));
+}
+
+// A large host text (2- or 4-bit alphabets) on its way to ix->d_text: cut into chunks of whole words; the host threads
+// pack chunk after chunk as a stream (kb::pack_stream_host) into a pinned ring whose slots are copied straight into
+// their place in the packed text, and -- pinned input only -- the copy engine moves the other chunks as 1-byte ranks at
+// the same time (all enqueued up front; pack_text_kernel turns each into words when it has arrived). A third to a half
+// of the PCIe time of the plain upload for pinned input; for pageable input (std::vector storage handed over by the C++
+// header) the staged copy of the driver is replaced by packing straight out of the caller's memory. On return the whole
+// packed text, padding included, is ordered on ix->stream. KMER_B200_ERR_UNSUPPORTED: the caller uploads the plain way.
+constexpr uint32_t kFlagPlainTextUpload = 1u << 31;  // internal bit of kmer_b200_config.reserved (create_multi sets it)
+
+static int upload_text_stream(kmer_b200_index *ix, const uint8_t *ranks, uint64_t n) {
+    constexpr int kRing = 3;
+    const uint32_t bits = ix->bits, spw = 64 / bits;
+    // the devices of a multi-device handle are built at the same time, each over its own PCIe link: N packers of the
+    // whole text would only compete for the host cores
+    if ((bits != 2 && bits != 4) || n < (128ull << 20) || (ix->cfg.reserved & kFlagPlainTextUpload) ||
+        std::getenv("KMER_B200_NO_TEXT_PIPELINE"))
+        return KMER_B200_ERR_UNSUPPORTED;
+    KB_TRY(ensure_copy_streams(ix));
+    cudaPointerAttributes attr{};
+    const bool pageable = cudaPointerGetAttributes(&attr, ranks) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
+    cudaGetLastError();
+    uint32_t raw_pct = 0;
+    if (!pageable) {
+        raw_pct = raw_chunk_percent(stream_pack_rate(ranks, n, bits, ix->sigma), bits);
+        if (const char *env = std::getenv("KMER_B200_HOST_RAW_PCT")) raw_pct = (uint32_t)std::max(0, std::min(100, std::atoi(env)));
+    }
+    const uint64_t chunk = 32ull << 20;  // symbols per chunk: a multiple of every spw
+    const uint64_t n_chunks = (n + chunk - 1) / chunk;
+    std::vector<uint8_t> raw(n_chunks, 0);
+    uint64_t n_raw = 0;
+    {
+        uint32_t acc = raw_pct ? 99 : 0;
+        for (uint64_t c = 0; c < n_chunks; ++c) {
+            acc += raw_pct;
+            if (acc >= 100) raw[c] = 1, acc -= 100, ++n_raw;
+        }
+    }
+    kb::HostPool &pool = kb::HostPool::instance();
+    const unsigned T = pool.threads();
+    cudaStream_t st = ix->stream;
+    uint8_t *d_raw = nullptr;  // the raw chunks, back to back
+    uint64_t *h_words[kRing] = {};
+    size_t cap_words[kRing] = {};
+    cudaEvent_t ev_slot[kRing] = {}, ev = nullptr;
+    auto cleanup = [&](int code) {
+        cudaStreamSynchronize(ix->copy_in);
+        if (code != 0) cudaStreamSynchronize(st);
+        for (int r = 0; r < kRing; ++r) {
+            if (ev_slot[r]) cudaEventDestroy(ev_slot[r]);
+            pinned_put(h_words[r], cap_words[r]);
+        }
+        if (ev) cudaEventDestroy(ev);
+        dev_free(ix, d_raw);
+        return code;
+    };
+    for (int r = 0; r < kRing; ++r) {
+        h_words[r] = (uint64_t *)pinned_get(chunk / spw * sizeof(uint64_t), &cap_words[r]);
+        if (!h_words[r]) return cleanup(fail(KMER_B200_ERR_OUT_OF_MEMORY, "pinned host allocation failed"));
+        cudaEventCreateWithFlags(&ev_slot[r], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (n_raw && dev_alloc(ix, &d_raw, n_raw * chunk, false)) return cleanup(KMER_B200_ERR_OUT_OF_MEMORY);
+    // the padding words behind the text; the allocations (ordered on st) before the copy stream touches them
+    const uint64_t n_words = kb::pack_stream_words(n, bits);
+    cudaMemsetAsync(ix->d_text + n_words, 0, (ix->text_words - n_words) * sizeof(uint64_t), st);
+    cudaEventRecord(ev, st);
+    cudaStreamWaitEvent(ix->copy_in, ev, 0);
+    // raw chunks: all enqueued now, the copy engine works through them while the host threads pack
+    uint64_t at = 0;
+    ix->prof.begin(K_PACK_TEXT, (double)n + (double)n * bits / 8.0, n_raw);
+    for (uint64_t c = 0; c < n_chunks; ++c) {
+        if (!raw[c]) continue;
+        const uint64_t s0 = c * chunk, len = std::min(chunk, n - s0);
+        cudaMemcpyAsync(d_raw + at, ranks + s0, len, cudaMemcpyHostToDevice, ix->copy_in);
+        cudaEventRecord(ev, ix->copy_in);
+        cudaStreamWaitEvent(st, ev, 0);
+        kb::launch_pack_text(d_raw + at, len, bits, ix->sigma, kb::pack_stream_words(len, bits), ix->d_text + s0 / spw, ix->d_flags, st);
+        at += chunk;
+    }
+    ix->prof.end();
+    bool bad_rank = false;
+    std::vector<uint8_t> ok(T * 4, 1);
+    uint64_t used = 0;
+    for (uint64_t c = 0; c < n_chunks; ++c) {
+        if (raw[c]) continue;
+        const int slot = (int)(used % kRing);
+        if (used >= kRing) cudaEventSynchronize(ev_slot[slot]);
+        ++used;
+        const uint64_t s0 = c * chunk, len = std::min(chunk, n - s0);
+        pool.run(T * 4, [&](unsigned t) { ok[t] = kb::pack_stream_host(ranks + s0, len, bits, ix->sigma, h_words[slot], t, T * 4) ? 1 : 0; });
+        for (uint8_t v : ok) bad_rank = bad_rank || !v;
+        if (bad_rank) break;
+        cudaMemcpyAsync(ix->d_text + s0 / spw, h_words[slot], kb::pack_stream_words(len, bits) * sizeof(uint64_t), cudaMemcpyHostToDevice,
+                        ix->copy_in);
+        cudaEventRecord(ev_slot[slot], ix->copy_in);
+    }
+    if (bad_rank) return cleanup(fail(KMER_B200_ERR_INVALID_RANK, "text contains a rank >= sigma"));
+    cudaEventRecord(ev, ix->copy_in);
+    cudaStreamWaitEvent(st, ev, 0);
+    return cleanup(0);
+}
+
 int create_impl(const uint8_t *ranks, bool ranks_on_device, uint64_t n, uint32_t sigma, const uint32_t *ks, uint32_t n_ks,
                 const kmer_b200_config *cfg_in, kmer_b200_index **out, const uint8_t *lut256 = nullptr) {
     if (!out) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "out is null");
@@ -935,16 +1090,23 @@ int create_impl(const uint8_t *ranks, bool ranks_on_device, uint64_t n, uint32_t
         // ---- text: H2D (if needed) + pack
         const uint8_t *d_ranks = ranks;
         uint8_t *d_ranks_owned = nullptr;
-        if (!ranks_on_device) {
-            KB_TRY(dev_alloc(ix, &d_ranks_owned, n, false));
-            KB_CUDA_RET(cudaMemcpyAsync(d_ranks_owned, ranks, n, cudaMemcpyHostToDevice, ix->stream));
-            d_ranks = d_ranks_owned;
-            if (lut256) KB_TRY(translate_on_device(ix, d_ranks_owned, n, lut256));  // invalid characters map to >= sigma
+        int piped = KMER_B200_ERR_UNSUPPORTED;
+        if (!ranks_on_device && !lut256) {  // large host texts: packed by the host threads / pipelined over PCIe
+            piped = upload_text_stream(ix, ranks, n);
+            if (piped != 0 && piped != KMER_B200_ERR_UNSUPPORTED) return piped;
         }
-        ix->prof.begin(K_PACK_TEXT, (double)n + (double)n * ix->bits / 8.0);
-        kb::launch_pack_text(d_ranks, n, ix->bits, sigma, ix->text_words, ix->d_text, ix->d_flags, ix->stream);
-        ix->prof.end();
-        if (d_ranks_owned) dev_free(ix, d_ranks_owned);
+        if (piped != 0) {
+            if (!ranks_on_device) {
+                KB_TRY(dev_alloc(ix, &d_ranks_owned, n, false));
+                KB_CUDA_RET(cudaMemcpyAsync(d_ranks_owned, ranks, n, cudaMemcpyHostToDevice, ix->stream));
+                d_ranks = d_ranks_owned;
+                if (lut256) KB_TRY(translate_on_device(ix, d_ranks_owned, n, lut256));  // invalid characters map to >= sigma
+            }
+            ix->prof.begin(K_PACK_TEXT, (double)n + (double)n * ix->bits / 8.0);
+            kb::launch_pack_text(d_ranks, n, ix->bits, sigma, ix->text_words, ix->d_text, ix->d_flags, ix->stream);
+            ix->prof.end();
+            if (d_ranks_owned) dev_free(ix, d_ranks_owned);
+        }
         // ---- elements
         ix->elems.resize(n_ks);
         if (ix->cfg.reserved & KMER_B200_FLAG_SHARED_POSITIONS) {
@@ -1750,6 +1912,31 @@ __global__ void __launch_bounds__(256) widen_lens_kernel(const uint16_t *__restr
     if (i < n) out[i] = lens[i];
 }
 
+// A stream of packed symbols (query boundaries ignored: kb::pack_stream_host) -> the fixed-stride per-query words the
+// search kernels take (SearchArgs::q_packed). One thread per output word: a funnel shift of two stream words, the
+// symbols behind the query's end zeroed. `off` = symbol offsets of the queries inside the stream.
+__global__ void __launch_bounds__(256) align_stream_kernel(const uint64_t *__restrict__ stream, const uint64_t *__restrict__ off,
+                                                           const uint16_t *__restrict__ lens, uint64_t n_queries, uint32_t stride,
+                                                           uint32_t bits, uint64_t *__restrict__ out) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_queries * stride) return;
+    const uint64_t q = idx / stride;
+    const uint32_t w = (uint32_t)(idx - q * stride);
+    const uint32_t spw = 64 / bits;
+    const uint32_t m = lens[q];
+    uint64_t v = 0;
+    if (w * spw < m) {
+        const uint64_t bit = (off[q] + (uint64_t)w * spw) * bits;
+        const uint64_t j = bit >> 6;
+        const uint32_t r = (uint32_t)(bit & 63);
+        v = stream[j] << r;
+        if (r) v |= stream[j + 1] >> (64 - r);  // the stream carries one word of padding
+        const uint32_t n_valid = min(spw, m - w * spw);
+        if (n_valid < spw) v &= ~0ull << (64 - bits * n_valid);
+    }
+    out[idx] = v;
+}
+
 // Large host batches are pipelined in chunks of queries: the H2D copy of chunk c+1 (copy engine), the search of
 // chunk c (SMs) and the D2H copy of chunk c-1's offsets and status (the other copy engine) run concurrently, so
 // the call costs about as much as moving its bytes over PCIe once. Position lists stay on the device until the
@@ -1758,20 +1945,7 @@ static int search_batch_host_pipelined(kmer_b200_index *ix, const uint8_t *q_ran
                                        uint32_t mode, kmer_b200_result **out) {
     constexpr int kChunks = 8;
     cudaStream_t st = ix->stream;
-    if (!ix->copy_in) {
-        // stream creation costs milliseconds: the two copy streams are created once per device and shared
-        // (searches on one device are short critical sections; the per-index mutex orders a handle's own work)
-        static std::mutex mu;
-        static cudaStream_t cached[64][2] = {};
-        std::lock_guard<std::mutex> lock(mu);
-        const int d = ix->device & 63;
-        if (!cached[d][0]) {
-            KB_CUDA(cudaStreamCreateWithFlags(&cached[d][0], cudaStreamNonBlocking));
-            KB_CUDA(cudaStreamCreateWithFlags(&cached[d][1], cudaStreamNonBlocking));
-        }
-        ix->copy_in = cached[d][0];
-        ix->copy_out = cached[d][1];
-    }
+    KB_TRY(ensure_copy_streams(ix));
     const uint64_t n_sym = q_offsets[Q] - q_offsets[0];
     uint8_t *d_q = nullptr;
     uint64_t *d_off = nullptr;
@@ -1927,18 +2101,7 @@ static int search_batch_host_packed(kmer_b200_index *ix, const uint8_t *q_ranks,
     constexpr int kChunks = 16, kRing = 3;
     uint64_t h2d = 0;
     cudaStream_t st = ix->stream;
-    if (!ix->copy_in) {
-        static std::mutex mu;
-        static cudaStream_t cached[64][2] = {};
-        std::lock_guard<std::mutex> lock(mu);
-        const int d = ix->device & 63;
-        if (!cached[d][0]) {
-            KB_CUDA(cudaStreamCreateWithFlags(&cached[d][0], cudaStreamNonBlocking));
-            KB_CUDA(cudaStreamCreateWithFlags(&cached[d][1], cudaStreamNonBlocking));
-        }
-        ix->copy_in = cached[d][0];
-        ix->copy_out = cached[d][1];
-    }
+    KB_TRY(ensure_copy_streams(ix));
     kb::HostPool &pool = kb::HostPool::instance();
     const unsigned T = pool.threads();
     const uint32_t spw = 64 / ix->bits;
@@ -2111,6 +2274,249 @@ static int search_batch_host_packed(kmer_b200_index *ix, const uint8_t *q_ranks,
     return cleanup(0);
 }
 
+// Large host batches, round 2's final form. Per-query packing on the host cores costs more than the PCIe bytes it saves
+// (search_batch_host_packed: 16 cores pack ~30 GB/s of variable-length queries, the link moves 55 GB/s). What the host
+// cores do fast is a pure streaming pack of the concatenated ranks, query boundaries ignored (kb::pack_stream_host: 128
+// ranks -> 32 bytes in ten AVX2 instructions, memory-bound); cutting that stream into per-query words is a ~1 ms kernel on
+// the device (align_stream_kernel). The batch is cut into chunks of queries of two kinds that keep BOTH resources busy:
+//   * stream chunks: lengths + streaming pack by the pool (asynchronous), then (bits / 8) of the bytes over PCIe;
+//   * raw chunks (pinned input only, `raw_pct` percent of the chunks): the copy engine moves the caller's 1-byte ranks
+//     as they are while the pool packs the next stream chunk -- no host work beyond the 16-bit lengths.
+// Chunk c + 2 is packed / enqueued while chunk c + 1 crosses the link and chunk c is searched; offsets and status of
+// finished chunks leave on the other copy engine. Results are identical to the plain path's (tests/test_gpu_full_size.py).
+static int search_batch_host_stream(kmer_b200_index *ix, const uint8_t *q_ranks, const uint64_t *q_offsets, uint64_t Q,
+                                    uint32_t mode, uint32_t raw_pct, kmer_b200_result **out) {
+    constexpr int kChunks = 24, kRing = 3;
+    if (ix->bits != 2 && ix->bits != 4) return KMER_B200_ERR_UNSUPPORTED;
+    uint64_t h2d = 0;
+    cudaStream_t st = ix->stream;
+    KB_TRY(ensure_copy_streams(ix));
+    kb::HostPool &pool = kb::HostPool::instance();
+    const unsigned T = pool.threads();
+    const uint32_t bits = ix->bits, spw = 64 / bits;
+    const uint64_t per = (Q + kChunks - 1) / kChunks;
+    uint64_t c0[kChunks + 1];
+    for (int c = 0; c <= kChunks; ++c) c0[c] = std::min<uint64_t>((uint64_t)c * per, Q);
+    // which chunks travel raw: spread evenly (error diffusion), the first one among them -- the copy engine starts on it at
+    // once while the pool packs chunk 1
+    bool raw[kChunks] = {};
+    {
+        uint32_t acc = raw_pct ? 99 : 0;
+        for (int c = 0; c < kChunks; ++c) {
+            acc += std::min(raw_pct, 100u);
+            if (acc >= 100) {
+                raw[c] = true;
+                acc -= 100;
+            }
+        }
+    }
+
+    const uint64_t max_stride = 16;
+    uint16_t *h_lens[kRing] = {};
+    uint64_t *h_words[kRing] = {};
+    size_t cap_lens[kRing] = {}, cap_words[kRing] = {};
+    void *d_in[kChunks] = {};        // raw chunk: its ranks; stream chunk: its packed stream (+ one word of padding)
+    uint64_t *d_words[kChunks] = {}; // stream chunk: per-query words after the alignment
+    uint16_t *d_lens[kChunks] = {};
+    uint64_t *d_off[kChunks] = {};   // chunk-relative symbol offsets, rebuilt from the lengths on the device
+    uint64_t *d_scan = nullptr;
+    uint32_t stride[kChunks] = {};
+    uint64_t max_len[kChunks] = {}, n_stream_words[kChunks] = {};
+    kmer_b200_result *chunk_res[kChunks] = {};
+    cudaEvent_t ev_in[kChunks] = {}, ev_done[kChunks] = {}, ev_slot[kRing] = {};
+    kmer_b200_result *res = nullptr;
+    std::vector<uint64_t> part_max(T * 4);
+    std::vector<uint8_t> part_ok(T * 4, 1);
+    bool unsupported = false, bad_rank = false;
+    auto cleanup = [&](int code) {
+        pool.wait();
+        cudaStreamSynchronize(ix->copy_in);
+        cudaStreamSynchronize(ix->copy_out);
+        cudaStreamSynchronize(st);
+        for (int c = 0; c < kChunks; ++c) {
+            if (chunk_res[c]) kmer_b200_result_free(chunk_res[c]);
+            if (ev_in[c]) cudaEventDestroy(ev_in[c]);
+            if (ev_done[c]) cudaEventDestroy(ev_done[c]);
+            dev_free(ix, (uint8_t *)d_in[c]);
+            dev_free(ix, d_words[c]);
+            dev_free(ix, d_lens[c]);
+            dev_free(ix, d_off[c]);
+        }
+        dev_free(ix, d_scan);
+        for (int r = 0; r < kRing; ++r) {
+            if (ev_slot[r]) cudaEventDestroy(ev_slot[r]);
+            pinned_put(h_lens[r], cap_lens[r]);
+            pinned_put(h_words[r], cap_words[r]);
+        }
+        if (code != 0 && res) kmer_b200_result_free(res);
+        return code;
+    };
+    for (int r = 0; r < kRing; ++r) {
+        h_lens[r] = (uint16_t *)pinned_get(per * sizeof(uint16_t), &cap_lens[r]);
+        h_words[r] = (uint64_t *)pinned_get(per * 2 * sizeof(uint64_t), &cap_words[r]);  // grown when a chunk needs more
+        if (!h_lens[r] || !h_words[r]) return cleanup(fail(KMER_B200_ERR_OUT_OF_MEMORY, "pinned host allocation failed"));
+        cudaEventCreateWithFlags(&ev_slot[r], cudaEventDisableTiming);
+    }
+    for (int c = 0; c < kChunks; ++c) {
+        cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming);
+    }
+    if (dev_alloc(ix, &d_scan, kb::offsets_scan_blocks(per) + 1, false)) return cleanup(KMER_B200_ERR_OUT_OF_MEMORY);
+    res = new (std::nothrow) kmer_b200_result();
+    if (!res) return cleanup(fail(KMER_B200_ERR_OUT_OF_MEMORY, "host allocation failed"));
+    res->index = ix;
+    res->on_device = false;
+    res->n_queries = Q;
+    res->offsets = (uint64_t *)pinned_get((Q + 1) * sizeof(uint64_t), &res->cap_offsets);
+    res->status = (uint8_t *)pinned_get(Q, &res->cap_status);
+    if (!res->offsets || !res->status) return cleanup(fail(KMER_B200_ERR_OUT_OF_MEMORY, "pinned host allocation failed"));
+
+    // device buffers are allocated in stream order on `st`; the copy-in stream must not touch them earlier
+    auto fence_allocations = [&] {
+        cudaEvent_t ev_alloc;
+        cudaEventCreateWithFlags(&ev_alloc, cudaEventDisableTiming);
+        cudaEventRecord(ev_alloc, st);
+        cudaStreamWaitEvent(ix->copy_in, ev_alloc, 0);
+        cudaEventDestroy(ev_alloc);
+    };
+    // stage 1 of chunk c: lengths + longest query (blocking, short). A raw chunk is then handed to the copy engine at
+    // once; a stream chunk's pack is started on the pool (asynchronous) and uploaded by finish()
+    auto start = [&](int c) -> int {
+        const uint64_t qa = c0[c], qb = c0[c + 1], Qc = qb - qa;
+        if (Qc == 0 || unsupported) return 0;
+        const int slot = c % kRing;
+        if (c >= kRing) cudaEventSynchronize(ev_slot[slot]);  // the slot's previous H2D has left the staging buffers
+        pool.run(T * 4, [&, qa, qb, slot](unsigned t) { part_max[t] = kb::query_lengths_host(q_offsets, qa, qb, h_lens[slot], t, T * 4); });
+        uint64_t mx = 0;
+        for (uint64_t v : part_max) mx = std::max(mx, v);
+        max_len[c] = mx;
+        stride[c] = (uint32_t)std::max<uint64_t>(1, (mx + spw - 1) / spw);
+        if (mx > 65535 || (!raw[c] && stride[c] > max_stride)) {
+            unsupported = true;
+            return 0;
+        }
+        const uint64_t n_sym = q_offsets[qb] - q_offsets[qa];
+        KB_TRY(dev_alloc(ix, &d_lens[c], Qc, false));
+        KB_TRY(dev_alloc(ix, &d_off[c], Qc + 1, false));
+        if (raw[c]) {
+            uint8_t *d_raw = nullptr;
+            KB_TRY(dev_alloc(ix, &d_raw, n_sym, false));
+            d_in[c] = d_raw;
+            fence_allocations();
+            if (n_sym) cudaMemcpyAsync(d_raw, q_ranks + q_offsets[qa], n_sym, cudaMemcpyHostToDevice, ix->copy_in);
+            cudaMemcpyAsync(d_lens[c], h_lens[slot], Qc * sizeof(uint16_t), cudaMemcpyHostToDevice, ix->copy_in);
+            h2d += n_sym + Qc * sizeof(uint16_t);
+            cudaEventRecord(ev_in[c], ix->copy_in);
+            cudaEventRecord(ev_slot[slot], ix->copy_in);
+            return 0;
+        }
+        n_stream_words[c] = kb::pack_stream_words(n_sym, bits);
+        const size_t need = (n_stream_words[c] + 1) * sizeof(uint64_t);
+        if (need > cap_words[slot]) {
+            pinned_put(h_words[slot], cap_words[slot]);
+            h_words[slot] = (uint64_t *)pinned_get(need, &cap_words[slot]);
+            if (!h_words[slot]) return fail(KMER_B200_ERR_OUT_OF_MEMORY, "pinned host allocation failed");
+        }
+        std::fill(part_ok.begin(), part_ok.end(), 1);
+        const uint8_t *src = q_ranks + q_offsets[qa];
+        pool.submit(T * 4, [&, src, n_sym, slot](unsigned t) {
+            part_ok[t] = kb::pack_stream_host(src, n_sym, bits, ix->sigma, h_words[slot], t, T * 4) ? 1 : 0;
+        });
+        return 0;
+    };
+    auto finish = [&](int c) -> int {
+        const uint64_t qa = c0[c], qb = c0[c + 1], Qc = qb - qa;
+        if (Qc == 0 || raw[c]) return 0;
+        pool.wait();
+        if (unsupported) return 0;
+        for (uint8_t ok : part_ok) bad_rank = bad_rank || !ok;
+        const int slot = c % kRing;
+        h_words[slot][n_stream_words[c]] = 0;  // the padding word align_stream_kernel may read
+        uint64_t *d_stream = nullptr;
+        KB_TRY(dev_alloc(ix, &d_stream, n_stream_words[c] + 1, false));
+        d_in[c] = d_stream;
+        KB_TRY(dev_alloc(ix, &d_words[c], Qc * stride[c], false));
+        fence_allocations();
+        cudaMemcpyAsync(d_stream, h_words[slot], (n_stream_words[c] + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ix->copy_in);
+        cudaMemcpyAsync(d_lens[c], h_lens[slot], Qc * sizeof(uint16_t), cudaMemcpyHostToDevice, ix->copy_in);
+        h2d += (n_stream_words[c] + 1) * sizeof(uint64_t) + Qc * sizeof(uint16_t);
+        cudaEventRecord(ev_in[c], ix->copy_in);
+        cudaEventRecord(ev_slot[slot], ix->copy_in);
+        return 0;
+    };
+
+    {
+        cudaEvent_t ev0;  // the copy-out stream must not run ahead of work already queued on `st`
+        cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming);
+        cudaEventRecord(ev0, st);
+        cudaStreamWaitEvent(ix->copy_out, ev0, 0);
+        cudaEventDestroy(ev0);
+    }
+    if (int s = start(0)) return cleanup(s);
+    if (int s = finish(0)) return cleanup(s);
+    if (kChunks > 1)
+        if (int s = start(1)) return cleanup(s);
+    uint64_t base = 0;
+    for (int c = 0; c < kChunks && !unsupported; ++c) {
+        if (c + 1 < kChunks) {
+            if (int s = finish(c + 1)) return cleanup(s);
+            if (c + 2 < kChunks)
+                if (int s = start(c + 2)) return cleanup(s);
+        }
+        if (unsupported || bad_rank) break;
+        const uint64_t qa = c0[c], qb = c0[c + 1], Qc = qb - qa;
+        if (Qc == 0) continue;
+        cudaStreamWaitEvent(st, ev_in[c], 0);
+        // lengths -> chunk-relative offsets: widen, exclusive scan (the total lands in entry Qc)
+        widen_lens_kernel<<<(unsigned)((Qc + 255) / 256), 256, 0, st>>>(d_lens[c], Qc, d_off[c]);
+        kb::launch_offsets_scan(d_off[c], Qc, d_scan, st);
+        int s;
+        if (raw[c]) {
+            s = search_device_impl(ix, (const uint8_t *)d_in[c], d_off[c], Qc, max_len[c], mode, nullptr, 0, kFlavorFull, &chunk_res[c]);
+        } else {
+            const uint64_t n_out = Qc * stride[c];
+            align_stream_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>((const uint64_t *)d_in[c], d_off[c], d_lens[c], Qc,
+                                                                                stride[c], bits, d_words[c]);
+            PackedQueries pk{d_words[c], d_lens[c], stride[c]};
+            s = search_device_impl(ix, nullptr, nullptr, Qc, max_len[c], mode, nullptr, 0, kFlavorFull, &chunk_res[c], &pk);
+        }
+        if (s != 0) return cleanup(s);
+        kmer_b200_result *cr = chunk_res[c];
+        if (base) add_base_kernel<<<(unsigned)((Qc + 1 + 255) / 256), 256, 0, st>>>(cr->offsets, Qc + 1, base);
+        cudaEventRecord(ev_done[c], st);
+        cudaStreamWaitEvent(ix->copy_out, ev_done[c], 0);
+        cudaMemcpyAsync(res->offsets + qa, cr->offsets, Qc * sizeof(uint64_t), cudaMemcpyDeviceToHost, ix->copy_out);
+        cudaMemcpyAsync(res->status + qa, cr->status, Qc, cudaMemcpyDeviceToHost, ix->copy_out);
+        base += cr->n_positions;
+    }
+    if (bad_rank) return cleanup(fail(KMER_B200_ERR_INVALID_RANK, "a query contains a rank >= sigma"));
+    if (unsupported) return cleanup(KMER_B200_ERR_UNSUPPORTED);  // the caller falls back to the unpacked pipeline
+    res->n_positions = base;
+    const size_t pos_bytes = base * sizeof(uint32_t);
+    if (pos_bytes > (8ull << 30)) {
+        res->positions = (uint32_t *)std::malloc(pos_bytes);
+        res->positions_pageable = true;
+        res->cap_positions = pos_bytes;
+    } else {
+        res->positions = (uint32_t *)pinned_get(pos_bytes, &res->cap_positions);
+    }
+    if (!res->positions) return cleanup(fail(KMER_B200_ERR_OUT_OF_MEMORY, "host allocation for the positions failed"));
+    uint64_t at = 0;
+    for (int c = 0; c < kChunks; ++c) {
+        if (!chunk_res[c] || !chunk_res[c]->n_positions) continue;
+        cudaMemcpyAsync(res->positions + at, chunk_res[c]->positions, chunk_res[c]->n_positions * sizeof(uint32_t),
+                        cudaMemcpyDeviceToHost, ix->copy_out);
+        at += chunk_res[c]->n_positions;
+    }
+    cudaError_t e = cudaStreamSynchronize(ix->copy_out);
+    res->offsets[Q] = base;
+    if (e != cudaSuccess) return cleanup(fail(KMER_B200_ERR_CUDA, std::string("search (D2H): ") + cudaGetErrorString(e)));
+    ix->last_h2d = h2d;
+    ix->last_d2h = Q * 9 + base * sizeof(uint32_t);
+    *out = res;
+    return cleanup(0);
+}
+
 static int search_batch_host(kmer_b200_index *ix, const uint8_t *q_ranks, const uint64_t *q_offsets, uint64_t Q,
                              uint32_t mode, const uint8_t *lut256, kmer_b200_result **out) {
     if (!ix || !out || !q_offsets) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument");
@@ -2123,16 +2529,19 @@ static int search_batch_host(kmer_b200_index *ix, const uint8_t *q_ranks, const 
     if (n_sym && !q_ranks) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "q_ranks is null");
     // batches whose transfer dominates (>= 256 MiB over PCIe) are pipelined in chunks
     if (!lut256 && Q >= (1u << 18) && n_sym + Q * 17 >= (256ull << 20) && !std::getenv("KMER_B200_NO_PIPELINE")) {
-        // Which pipeline. Pageable input cannot be DMA-ed directly (the driver would stage it at a fraction of the link
-        // rate): the host threads pack it straight out of the caller's memory into a pinned ring (a third of the bytes
-        // for dna4). Pinned input crosses PCIe as it is at ~55 GB/s unless this host packs faster than that, which is
-        // measured once per process on a sample of the first large batch (AVX2 packer, all pool threads; other
-        // processes sharing the cores -- one per GPU under torchrun -- lower the rate and so switch the packing off).
-        // KMER_B200_HOST_PACK=1 / 0 forces the choice.
+        // Which pipeline. 2- and 4-bit alphabets: search_batch_host_stream -- the host threads pack chunks of the batch as a
+        // stream (a quarter / half of the bytes), and when the input is pinned the copy engine moves the other chunks as
+        // they are at the same time; the share of raw chunks comes from the host's streaming pack rate, measured once per
+        // process on the first large batch (other processes sharing the cores -- one per GPU under torchrun -- lower the
+        // rate and so raise the share). Pageable input cannot be DMA-ed directly (the driver would stage it at a fraction
+        // of the link rate): every chunk is packed straight out of the caller's memory into a pinned ring. 8-bit alphabets
+        // (nothing to gain from packing) and batches the streaming pipeline refuses (a query >= 65 536 symbols) keep round
+        // 2's first two pipelines: per-query packing for pageable input, raw chunks for pinned input.
         cudaPointerAttributes attr{};
         bool pageable = cudaPointerGetAttributes(&attr, q_ranks) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
         cudaGetLastError();
-        if (!pageable) {
+        const bool input_pageable = pageable;
+        if (!pageable && ix->bits == 8) {  // (2- and 4-bit alphabets take the streaming pipeline below)
             static std::atomic<int> pack_wins{-1};  // -1 unknown, 0 no, 1 yes
             if (pack_wins.load() < 0) {
                 kb::HostPool &pool = kb::HostPool::instance();
@@ -2160,11 +2569,32 @@ static int search_batch_host(kmer_b200_index *ix, const uint8_t *q_ranks, const 
             }
             pageable = pack_wins.load() == 1;
         }
-        if (const char *env = std::getenv("KMER_B200_HOST_PACK")) pageable = std::atoi(env) != 0;
+        // KMER_B200_HOST_PACK: 0 = raw chunks only, 1 = per-query packing on the host, 2 = streaming pack only,
+        // 3 = streaming pack + raw chunks (KMER_B200_HOST_RAW_PCT percent of the chunks, default from the calibration)
+        int forced = -1;
+        if (const char *env = std::getenv("KMER_B200_HOST_PACK")) forced = std::atoi(env);
+        const bool can_stream = ix->bits == 2 || ix->bits == 4;
+        if ((forced < 0 && can_stream) || forced == 2 || forced == 3) {
+            uint32_t raw_pct = 0;
+            double rate = 0;
+            if (!input_pageable && forced != 2) {
+                rate = stream_pack_rate(q_ranks + q_offsets[0], n_sym, ix->bits, ix->sigma);
+                raw_pct = raw_chunk_percent(rate / std::max(1u, ix->host_sharers), ix->bits);
+                if (const char *env = std::getenv("KMER_B200_HOST_RAW_PCT")) raw_pct = (uint32_t)std::max(0, std::min(100, std::atoi(env)));
+            }
+            const int s = search_batch_host_stream(ix, q_ranks, q_offsets, Q, mode, raw_pct, out);
+            if (s != KMER_B200_ERR_UNSUPPORTED) {
+                ix->last_host_path = 3, ix->last_raw_pct = raw_pct, ix->last_pack_gbs = rate / 1e9;
+                return s;
+            }
+        }
+        if (forced >= 0) pageable = forced == 1;
         if (pageable) {
             const int s = search_batch_host_packed(ix, q_ranks, q_offsets, Q, mode, out);
+            ix->last_host_path = 2, ix->last_raw_pct = 0, ix->last_pack_gbs = 0;
             if (s != KMER_B200_ERR_UNSUPPORTED) return s;  // queries longer than 16 packed words: the unpacked pipeline
         }
+        ix->last_host_path = 1, ix->last_raw_pct = 100, ix->last_pack_gbs = 0;
         return search_batch_host_pipelined(ix, q_ranks, q_offsets, Q, mode, out);
     }
     uint8_t *d_q = nullptr;
@@ -2235,6 +2665,7 @@ static int search_batch_host(kmer_b200_index *ix, const uint8_t *q_ranks, const 
     }
     ix->last_h2d = n_sym + (Q + 1) * sizeof(uint64_t);
     ix->last_d2h = (Q + 1) * sizeof(uint64_t) + Q + res->n_positions * sizeof(uint32_t);
+    ix->last_host_path = 0, ix->last_raw_pct = 100, ix->last_pack_gbs = 0;
     *out = res;
     return KMER_B200_OK;
 }
@@ -3069,6 +3500,7 @@ static int create_multi(const uint8_t *ranks, uint64_t n, uint32_t sigma, const 
                 c.device_ids = nullptr;
                 c.key_part = parts > 1 ? i : 0;
                 c.key_parts = parts > 1 ? parts : 0;
+                c.reserved |= kFlagPlainTextUpload;
                 rc[i] = create_impl(ranks, false, n, sigma, ks, n_ks, &c, &reps[i], lut256);
                 if (rc[i] != 0) err[i] = g_last_error;
             });
@@ -3219,6 +3651,7 @@ static int create_multi(const uint8_t *ranks, uint64_t n, uint32_t sigma, const 
     kmer_b200_index *group = new (std::nothrow) kmer_b200_index();
     if (!group) return bail(KMER_B200_ERR_OUT_OF_MEMORY, "host allocation failed");
     group->device = ids[0];
+    for (kmer_b200_index *r : reps) r->host_sharers = N;
     group->cfg = *cfg_in;
     group->cfg.device_ids = nullptr;
     group->n = n;
@@ -3511,6 +3944,29 @@ int kmer_b200_debug_guard_selftest(void) {
 }
 
 uint64_t kmer_b200_last_search_gathers(const kmer_b200_index *ix) { return ix ? primary(ix)->last_gathers : 0; }
+
+void kmer_b200_last_search_host_path(const kmer_b200_index *ix, uint32_t *pipeline, uint32_t *raw_pct, double *pack_gbs) {
+    const kmer_b200_index *p = ix && !ix->replicas.empty() ? ix->replicas[0] : ix;
+    if (pipeline) *pipeline = p ? p->last_host_path : 0;
+    if (raw_pct) *raw_pct = p ? p->last_raw_pct : 0;
+    if (pack_gbs) *pack_gbs = p ? p->last_pack_gbs : 0;
+}
+
+uint64_t kmer_b200_host_pack_stream_words(uint64_t n, uint32_t sigma) {
+    return kb::pack_stream_words(n, sigma <= 4 ? 2 : (sigma <= 16 ? 4 : 8));
+}
+
+int kmer_b200_host_pack_stream(const uint8_t *ranks, uint64_t n, uint32_t sigma, uint64_t *words) {
+    if ((n && !ranks) || !words || sigma < 2 || sigma > 256) return fail(KMER_B200_ERR_INVALID_ARGUMENT, "null argument or sigma out of range");
+    const uint32_t bits = sigma <= 4 ? 2 : (sigma <= 16 ? 4 : 8);
+    kb::HostPool &pool = kb::HostPool::instance();
+    const unsigned parts = std::max(1u, std::min(pool.threads() * 4, 256u));
+    std::vector<uint8_t> ok(parts, 1);
+    pool.run(parts, [&](unsigned t) { ok[t] = kb::pack_stream_host(ranks, n, bits, sigma, words, t, parts) ? 1 : 0; });
+    for (uint8_t v : ok)
+        if (!v) return fail(KMER_B200_ERR_INVALID_RANK, "a rank is >= sigma");
+    return KMER_B200_OK;
+}
 
 void kmer_b200_last_search_transfer(const kmer_b200_index *ix, uint64_t *h2d_bytes, uint64_t *d2h_bytes) {
     uint64_t in = 0, back = 0;

@@ -35,4 +35,14 @@ uint64_t query_lengths_host(const uint64_t *q_offsets, uint64_t q_begin, uint64_
 bool pack_queries_host(const uint8_t *q_ranks, const uint64_t *q_offsets, uint64_t q_begin, uint64_t q_end, uint32_t bits,
                        uint32_t sigma, uint32_t stride, uint64_t *words, unsigned part, unsigned n_parts);
 
+
+// Streaming pack of a contiguous run of n ranks, query boundaries ignored: symbol s lands in bits
+// [64 - bits (s % spw + 1), 64 - bits (s % spw)) of words[s / spw]; the unused low bits of the last word are zero. The
+// device cuts the stream into per-query words afterwards (align_stream_kernel, capi.cu), which costs it ~1 ms per 10^8
+// queries -- per-query work on the host cores costs 50x that. `part` of `n_parts`: the slice of the words this call
+// writes (pack_stream_words(n, bits) in all). Returns false when a rank >= sigma was seen.
+uint64_t pack_stream_words(uint64_t n, uint32_t bits);
+bool pack_stream_host(const uint8_t *ranks, uint64_t n, uint32_t bits, uint32_t sigma, uint64_t *words, unsigned part,
+                      unsigned n_parts);
+
 }  // namespace kb

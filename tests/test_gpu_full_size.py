@@ -85,8 +85,39 @@ def test_pipelined_host_batch_equals_plain(kb):
     q = np.concatenate([q1, q2])
     off = np.concatenate([off1, off2[1:] + off1[-1]])
     assert q.size + 17 * (off.size - 1) >= (256 << 20)
+    import torch
+    pin_q, pin_off = torch.from_numpy(q).pin_memory(), torch.from_numpy(off).pin_memory()
     with kb.KmerIndex(text, 4, [12]) as ix:
-        packed = ix.search_batch(q, off).as_tuple()          # pageable numpy input: packed on the host threads, pipelined
+        # pageable numpy input: packed as a stream on the host threads, cut into per-query words on the device
+        packed = ix.search_batch(q, off).as_tuple()
+        path = ix.last_search_host_path()
+        assert path["pipeline"].startswith("streaming") and path["raw_chunk_pct"] == 0, path
+        assert ix.last_search_transfer()[0] < q.size // 4 + 2 * (off.size - 1) + 4096
+        # pinned input: part of the chunks cross the link as 1-byte ranks while the host threads pack the others
+        mixed_auto = ix.search_batch(pin_q.numpy(), pin_off.numpy()).as_tuple()
+        path_auto = ix.last_search_host_path()
+        assert path_auto["pipeline"].startswith("streaming") and path_auto["host_pack_gbs"] > 0, path_auto
+        os.environ["KMER_B200_HOST_PACK"] = "3"
+        mixed = {}
+        try:
+            for pct in (0, 30, 50, 100):
+                os.environ["KMER_B200_HOST_RAW_PCT"] = str(pct)
+                mixed[pct] = ix.search_batch(pin_q.numpy(), pin_off.numpy()).as_tuple()
+                assert ix.last_search_host_path()["raw_chunk_pct"] == pct
+            os.environ["KMER_B200_HOST_RAW_PCT"] = "50"
+            bad = pin_q.numpy().copy()
+            for at in (5, q.size // 2, q.size - 7):          # in a raw chunk or a stream chunk: reported either way
+                bad[at] = 4
+                with pytest.raises(kb.KmerB200Error) as e:
+                    ix.search_batch(torch.from_numpy(bad).pin_memory().numpy(), pin_off.numpy())
+                assert e.value.code == -4
+                bad[at] = q[at]
+            os.environ["KMER_B200_HOST_PACK"] = "1"
+            packed_per_query = ix.search_batch(q, off).as_tuple()   # round 2's first host packer: query by query
+            assert ix.last_search_host_path()["pipeline"].startswith("per-query")
+        finally:
+            os.environ.pop("KMER_B200_HOST_PACK", None)
+            os.environ.pop("KMER_B200_HOST_RAW_PCT", None)
         os.environ["KMER_B200_HOST_PACK"] = "0"
         try:
             piped = ix.search_batch(q, off).as_tuple()       # 1-byte ranks over PCIe, chunks pipelined
@@ -120,7 +151,11 @@ def test_pipelined_host_batch_equals_plain(kb):
     assert_results_equal(piped_off, plain, label="pipelined (offsets as they are) vs plain")
     assert plain_long[0][-1] - plain_long[0][-2] == 1          # the long query occurs once, at position 1000
     assert_results_equal(piped_long, plain_long, label="pipelined with a 70 000-symbol query vs plain")
-    assert_results_equal(packed, plain, label="host-packed pipeline vs plain")
+    assert_results_equal(packed, plain, label="stream-packed pipeline (pageable input) vs plain")
+    assert_results_equal(packed_per_query, plain, label="per-query host-packed pipeline vs plain")
+    assert_results_equal(mixed_auto, plain, label=f"stream-packed + raw chunks ({path_auto}) vs plain")
+    for pct, got in mixed.items():
+        assert_results_equal(got, plain, label=f"stream-packed + {pct} % raw chunks vs plain")
 
 
 def test_config3_full_text_counts_and_subsample(kb, oracle_mod):

@@ -94,3 +94,36 @@ def test_shard_geometry():
     for a, b in zip(shards, shards[1:]):
         assert a.end == b.begin and a.halo == min(halo, n - a.end) and a.length == a.end - a.begin + a.halo
     assert sum(s.end - s.begin for s in shards) == n
+
+
+def _pack_stream_reference(ranks: np.ndarray, bits: int) -> np.ndarray:
+    """symbol s in bits [64 - bits (s % spw + 1), 64 - bits (s % spw)) of word s // spw"""
+    spw = 64 // bits
+    n_words = (ranks.size + spw - 1) // spw
+    padded = np.zeros(n_words * spw, dtype=np.uint64)
+    padded[:ranks.size] = ranks
+    shifts = (np.uint64(64) - np.uint64(bits) * (np.arange(spw, dtype=np.uint64) + np.uint64(1)))
+    return np.bitwise_or.reduce(padded.reshape(n_words, spw) << shifts, axis=1) if n_words else np.zeros(0, dtype=np.uint64)
+
+
+@pytest.mark.parametrize("sigma,bits", [(4, 2), (3, 2), (5, 4), (16, 4), (27, 8), (200, 8)])
+def test_host_stream_pack_matches_the_bit_layout(kb, sigma, bits):
+    """The host side of large kmer_b200_search_batch calls: 1-byte ranks -> b-bit MSB-first words, query boundaries
+    ignored (csrc/host_pack.cpp, AVX2 for 2 and 4 bits). Every length class around the vector loops' steps, unaligned
+    sources, and the rank check."""
+    rng = np.random.default_rng(5)
+    sizes = [0, 1, 7, 31, 32, 33, 127, 128, 129, 511, 4096, 4097, 100_003, 1_000_001]
+    for n in sizes:
+        buf = rng.integers(0, sigma, n + 3, dtype=np.uint8)
+        for shift in (0, 3):
+            ranks = buf[shift:shift + n]
+            got = kb.host_pack_stream(ranks, sigma)
+            assert got.size == (n + 64 // bits - 1) // (64 // bits)
+            assert np.array_equal(got, _pack_stream_reference(ranks, bits)), (sigma, n, shift)
+    if sigma < 256:
+        for n, at in [(1, 0), (200, 199), (4096, 77), (100_003, 100_002), (100_003, 50_000)]:
+            bad = rng.integers(0, sigma, n, dtype=np.uint8)
+            bad[at] = sigma
+            with pytest.raises(kb.KmerB200Error) as e:
+                kb.host_pack_stream(bad, sigma)
+            assert e.value.code == -4
