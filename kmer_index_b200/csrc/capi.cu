@@ -2,6 +2,7 @@
 // No CPU fallback anywhere: every computing entry point needs a CUDA device.
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -192,6 +193,7 @@ struct kmer_b200_index {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;  // host-batch pipeline: H2D / D2H engines next to `stream`
+    cudaStream_t copy_in2 = nullptr;                     // second H2D queue (raw chunks of search_batch_host_stream)
     kmer_b200_config cfg{};
     uint64_t n = 0;
     uint32_t sigma = 0, bits = 0;
@@ -932,15 +934,17 @@ int translate_on_device(kmer_b200_index *ix, uint8_t *d_data, uint64_t n, const 
 static int ensure_copy_streams(kmer_b200_index *ix) {
     if (ix->copy_in) return 0;
     static std::mutex mu;
-    static cudaStream_t cached[64][2] = {};
+    static cudaStream_t cached[64][3] = {};
     std::lock_guard<std::mutex> lock(mu);
     const int d = ix->device & 63;
     if (!cached[d][0]) {
         KB_CUDA(cudaStreamCreateWithFlags(&cached[d][0], cudaStreamNonBlocking));
         KB_CUDA(cudaStreamCreateWithFlags(&cached[d][1], cudaStreamNonBlocking));
+        KB_CUDA(cudaStreamCreateWithFlags(&cached[d][2], cudaStreamNonBlocking));
     }
     ix->copy_in = cached[d][0];
     ix->copy_out = cached[d][1];
+    ix->copy_in2 = cached[d][2];
     return 0;
 }
 
@@ -965,22 +969,24 @@ static double stream_pack_rate(const uint8_t *ranks, uint64_t n, uint32_t bits, 
     return rate;
 }
 
-// The share of raw chunks that makes "pack the stream chunks" and "move all chunks over the link" take equally long:
-// x = packed share, x / r = ((1 - x) + x b / 8) / L. The packers lose some memory bandwidth to the DMA: r is derated.
-static uint32_t raw_chunk_percent(double pack_rate, uint32_t bits) {
+// The share of raw chunks that makes the host threads and the link finish together. S symbols in all, P of them packed,
+// Q queries whose 16-bit lengths the host threads compute in either kind of chunk (8 bytes read + 2 written per query;
+// Q = 0 for a text):  host threads (P + 10 Q) / r  =  link (S - P + P b / 8 + 2 Q) / L.  r is the streaming pack rate of
+// this host measured alone, derated: inside the pipeline the packers share the memory system with two DMA streams.
+static uint32_t raw_chunk_percent(double pack_rate, uint32_t bits, uint64_t n_symbols, uint64_t n_queries) {
     double link = 52e9;
     if (const char *env = std::getenv("KMER_B200_LINK_GBS")) link = std::max(1.0, std::atof(env)) * 1e9;
-    const double r = 0.85 * pack_rate;
-    const double x = (1.0 / link) / (1.0 / r + (1.0 - bits / 8.0) / link);
-    const double raw = 100.0 * (1.0 - std::min(1.0, x));
+    const double r = 0.85 * pack_rate, S = (double)std::max<uint64_t>(n_symbols, 1), Q = (double)n_queries;
+    const double P = ((S + 2.0 * Q) / link - 10.0 * Q / r) / (1.0 / r + (1.0 - bits / 8.0) / link);
+    const double raw = 100.0 * (1.0 - std::max(0.0, std::min(1.0, P / S)));
     return (uint32_t)std::max(0.0, std::min(100.0, raw + 0.5));
 }
 
 // A large host text (2- or 4-bit alphabets) on its way to ix->d_text: cut into chunks of whole words; the host threads
 // pack chunk after chunk as a stream (kb::pack_stream_host) into a pinned ring whose slots are copied straight into
 // their place in the packed text, and -- pinned input only -- the copy engine moves the other chunks as 1-byte ranks at
-// the same time (all enqueued up front; pack_text_kernel turns each into words when it has arrived). A third to a half
-// of the PCIe time of the plain upload for pinned input; for pageable input (std::vector storage handed over by the C++
+// the same time (pack_text_kernel turns each into words when it has arrived). Half of the PCIe time of the plain upload
+// for pinned input (config 5: 54 -> 27 ms); for pageable input (std::vector storage handed over by the C++
 // header) the staged copy of the driver is replaced by packing straight out of the caller's memory. On return the whole
 // packed text, padding included, is ordered on ix->stream. KMER_B200_ERR_UNSUPPORTED: the caller uploads the plain way.
 constexpr uint32_t kFlagPlainTextUpload = 1u << 31;  // internal bit of kmer_b200_config.reserved (create_multi sets it)
@@ -990,7 +996,7 @@ static int upload_text_stream(kmer_b200_index *ix, const uint8_t *ranks, uint64_
     const uint32_t bits = ix->bits, spw = 64 / bits;
     // the devices of a multi-device handle are built at the same time, each over its own PCIe link: N packers of the
     // whole text would only compete for the host cores
-    if ((bits != 2 && bits != 4) || n < (128ull << 20) || (ix->cfg.reserved & kFlagPlainTextUpload) ||
+    if ((bits != 2 && bits != 4) || n < (64ull << 20) || (ix->cfg.reserved & kFlagPlainTextUpload) ||
         std::getenv("KMER_B200_NO_TEXT_PIPELINE"))
         return KMER_B200_ERR_UNSUPPORTED;
     KB_TRY(ensure_copy_streams(ix));
@@ -999,7 +1005,7 @@ static int upload_text_stream(kmer_b200_index *ix, const uint8_t *ranks, uint64_
     cudaGetLastError();
     uint32_t raw_pct = 0;
     if (!pageable) {
-        raw_pct = raw_chunk_percent(stream_pack_rate(ranks, n, bits, ix->sigma), bits);
+        raw_pct = raw_chunk_percent(stream_pack_rate(ranks, n, bits, ix->sigma), bits, n, 0);
         if (const char *env = std::getenv("KMER_B200_HOST_RAW_PCT")) raw_pct = (uint32_t)std::max(0, std::min(100, std::atoi(env)));
     }
     const uint64_t chunk = 32ull << 20;  // symbols per chunk: a multiple of every spw
@@ -1043,28 +1049,25 @@ static int upload_text_stream(kmer_b200_index *ix, const uint8_t *ranks, uint64_
     cudaMemsetAsync(ix->d_text + n_words, 0, (ix->text_words - n_words) * sizeof(uint64_t), st);
     cudaEventRecord(ev, st);
     cudaStreamWaitEvent(ix->copy_in, ev, 0);
-    // raw chunks: all enqueued now, the copy engine works through them while the host threads pack
-    uint64_t at = 0;
-    ix->prof.begin(K_PACK_TEXT, (double)n + (double)n * bits / 8.0, n_raw);
-    for (uint64_t c = 0; c < n_chunks; ++c) {
-        if (!raw[c]) continue;
-        const uint64_t s0 = c * chunk, len = std::min(chunk, n - s0);
-        cudaMemcpyAsync(d_raw + at, ranks + s0, len, cudaMemcpyHostToDevice, ix->copy_in);
-        cudaEventRecord(ev, ix->copy_in);
-        cudaStreamWaitEvent(st, ev, 0);
-        kb::launch_pack_text(d_raw + at, len, bits, ix->sigma, kb::pack_stream_words(len, bits), ix->d_text + s0 / spw, ix->d_flags, st);
-        at += chunk;
-    }
-    ix->prof.end();
+    // chunks in text order: a raw chunk costs the host nothing (one enqueue), so the copy engine always has some queued
+    // while the host threads pack; the ring's slots are handed over in the same queue and come back in time
+    uint64_t at = 0, used = 0;
     bool bad_rank = false;
     std::vector<uint8_t> ok(T * 4, 1);
-    uint64_t used = 0;
-    for (uint64_t c = 0; c < n_chunks; ++c) {
-        if (raw[c]) continue;
+    ix->prof.begin(K_PACK_TEXT, (double)n + (double)n * bits / 8.0, n_raw);
+    for (uint64_t c = 0; c < n_chunks && !bad_rank; ++c) {
+        const uint64_t s0 = c * chunk, len = std::min(chunk, n - s0);
+        if (raw[c]) {
+            cudaMemcpyAsync(d_raw + at, ranks + s0, len, cudaMemcpyHostToDevice, ix->copy_in);
+            cudaEventRecord(ev, ix->copy_in);
+            cudaStreamWaitEvent(st, ev, 0);
+            kb::launch_pack_text(d_raw + at, len, bits, ix->sigma, kb::pack_stream_words(len, bits), ix->d_text + s0 / spw, ix->d_flags, st);
+            at += chunk;
+            continue;
+        }
         const int slot = (int)(used % kRing);
         if (used >= kRing) cudaEventSynchronize(ev_slot[slot]);
         ++used;
-        const uint64_t s0 = c * chunk, len = std::min(chunk, n - s0);
         pool.run(T * 4, [&](unsigned t) { ok[t] = kb::pack_stream_host(ranks + s0, len, bits, ix->sigma, h_words[slot], t, T * 4) ? 1 : 0; });
         for (uint8_t v : ok) bad_rank = bad_rank || !v;
         if (bad_rank) break;
@@ -1072,6 +1075,7 @@ static int upload_text_stream(kmer_b200_index *ix, const uint8_t *ranks, uint64_
                         ix->copy_in);
         cudaEventRecord(ev_slot[slot], ix->copy_in);
     }
+    ix->prof.end();
     if (bad_rank) return cleanup(fail(KMER_B200_ERR_INVALID_RANK, "text contains a rank >= sigma"));
     cudaEventRecord(ev, ix->copy_in);
     cudaStreamWaitEvent(st, ev, 0);
@@ -2277,23 +2281,33 @@ static int search_batch_host_packed(kmer_b200_index *ix, const uint8_t *q_ranks,
 // Large host batches, round 2's final form. Per-query packing on the host cores costs more than the PCIe bytes it saves
 // (search_batch_host_packed: 16 cores pack ~30 GB/s of variable-length queries, the link moves 55 GB/s). What the host
 // cores do fast is a pure streaming pack of the concatenated ranks, query boundaries ignored (kb::pack_stream_host: 128
-// ranks -> 32 bytes in ten AVX2 instructions, memory-bound); cutting that stream into per-query words is a ~1 ms kernel on
-// the device (align_stream_kernel). The batch is cut into chunks of queries of two kinds that keep BOTH resources busy:
-//   * stream chunks: lengths + streaming pack by the pool (asynchronous), then (bits / 8) of the bytes over PCIe;
+// ranks -> 32 bytes in ten AVX2 instructions, bound by what a core streams from DRAM: ~100 GB/s on 16 cores); cutting
+// that stream into per-query words is a ~1 ms kernel on the device (align_stream_kernel). The batch is cut into chunks of
+// queries of two kinds that keep BOTH resources busy:
+//   * stream chunks: 16-bit lengths + streaming pack by the pool, then (bits / 8) of the bytes over PCIe;
 //   * raw chunks (pinned input only, `raw_pct` percent of the chunks): the copy engine moves the caller's 1-byte ranks
-//     as they are while the pool packs the next stream chunk -- no host work beyond the 16-bit lengths.
-// Chunk c + 2 is packed / enqueued while chunk c + 1 crosses the link and chunk c is searched; offsets and status of
-// finished chunks leave on the other copy engine. Results are identical to the plain path's (tests/test_gpu_full_size.py).
+//     as they are -- no host work beyond the lengths.
+// A producer thread walks the chunks in order and never waits for the device except for a free slot of the pinned ring:
+// raw chunks are queued on one H2D stream, packed chunks on another, so neither kind waits behind the other. The calling
+// thread searches the chunks in order as they arrive (device buffers are allocated up front, so the producer makes no
+// stream-ordered allocation); offsets and status of finished chunks leave on the D2H stream. Results are identical to
+// the plain path's (tests/test_gpu_full_size.py).
 static int search_batch_host_stream(kmer_b200_index *ix, const uint8_t *q_ranks, const uint64_t *q_offsets, uint64_t Q,
                                     uint32_t mode, uint32_t raw_pct, kmer_b200_result **out) {
-    constexpr int kChunks = 24, kRing = 3;
+    constexpr int kChunks = 24, kRing = 4;
     if (ix->bits != 2 && ix->bits != 4) return KMER_B200_ERR_UNSUPPORTED;
-    uint64_t h2d = 0;
+    // KMER_B200_HOST_TRACE=1: where the time went (ms), printed to stderr at the end of the call
+    const bool trace = std::getenv("KMER_B200_HOST_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto since = [](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+    const auto t_call = now();
+    double t_wait_chunk = 0, t_search = 0;                       // calling thread
+    double t_slot = 0, t_pool = 0, t_enqueue = 0, t_producer = 0;  // producer thread
     cudaStream_t st = ix->stream;
     KB_TRY(ensure_copy_streams(ix));
     kb::HostPool &pool = kb::HostPool::instance();
     const unsigned T = pool.threads();
-    const uint32_t bits = ix->bits, spw = 64 / bits;
+    const uint32_t bits = ix->bits, spw = 64 / bits, sigma = ix->sigma;
     const uint64_t per = (Q + kChunks - 1) / kChunks;
     uint64_t c0[kChunks + 1];
     for (int c = 0; c <= kChunks; ++c) c0[c] = std::min<uint64_t>((uint64_t)c * per, Q);
@@ -2312,30 +2326,40 @@ static int search_batch_host_stream(kmer_b200_index *ix, const uint8_t *q_ranks,
     }
 
     const uint64_t max_stride = 16;
-    uint16_t *h_lens[kRing] = {};
+    uint16_t *h_lens = nullptr;
+    size_t cap_lens = 0;
     uint64_t *h_words[kRing] = {};
-    size_t cap_lens[kRing] = {}, cap_words[kRing] = {};
+    size_t cap_words[kRing] = {};
     void *d_in[kChunks] = {};        // raw chunk: its ranks; stream chunk: its packed stream (+ one word of padding)
     uint64_t *d_words[kChunks] = {}; // stream chunk: per-query words after the alignment
     uint16_t *d_lens[kChunks] = {};
     uint64_t *d_off[kChunks] = {};   // chunk-relative symbol offsets, rebuilt from the lengths on the device
     uint64_t *d_scan = nullptr;
     uint32_t stride[kChunks] = {};
-    uint64_t max_len[kChunks] = {}, n_stream_words[kChunks] = {};
+    uint64_t max_len[kChunks] = {}, n_sym_c[kChunks] = {}, n_stream_words[kChunks] = {};
     kmer_b200_result *chunk_res[kChunks] = {};
-    cudaEvent_t ev_in[kChunks] = {}, ev_done[kChunks] = {}, ev_slot[kRing] = {};
+    cudaEvent_t ev_in[kChunks] = {}, ev_raw[kChunks] = {}, ev_done[kChunks] = {}, ev_slot[kRing] = {};
     kmer_b200_result *res = nullptr;
-    std::vector<uint64_t> part_max(T * 4);
-    std::vector<uint8_t> part_ok(T * 4, 1);
+    // producer -> calling thread
+    std::mutex mu;
+    std::condition_variable cv;
+    int produced = 0;                // chunks [0, produced) are queued on a copy stream
+    bool producer_failed = false;    // unsupported / bad rank / allocation: see the flags
+    std::atomic<bool> stop{false};
     bool unsupported = false, bad_rank = false;
+    uint64_t h2d = 0;
+    std::thread producer;
     auto cleanup = [&](int code) {
-        pool.wait();
+        stop.store(true);
+        if (producer.joinable()) producer.join();
         cudaStreamSynchronize(ix->copy_in);
+        cudaStreamSynchronize(ix->copy_in2);
         cudaStreamSynchronize(ix->copy_out);
         cudaStreamSynchronize(st);
         for (int c = 0; c < kChunks; ++c) {
             if (chunk_res[c]) kmer_b200_result_free(chunk_res[c]);
             if (ev_in[c]) cudaEventDestroy(ev_in[c]);
+            if (ev_raw[c]) cudaEventDestroy(ev_raw[c]);
             if (ev_done[c]) cudaEventDestroy(ev_done[c]);
             dev_free(ix, (uint8_t *)d_in[c]);
             dev_free(ix, d_words[c]);
@@ -2345,23 +2369,55 @@ static int search_batch_host_stream(kmer_b200_index *ix, const uint8_t *q_ranks,
         dev_free(ix, d_scan);
         for (int r = 0; r < kRing; ++r) {
             if (ev_slot[r]) cudaEventDestroy(ev_slot[r]);
-            pinned_put(h_lens[r], cap_lens[r]);
             pinned_put(h_words[r], cap_words[r]);
         }
+        pinned_put(h_lens, cap_lens);
         if (code != 0 && res) kmer_b200_result_free(res);
         return code;
     };
-    for (int r = 0; r < kRing; ++r) {
-        h_lens[r] = (uint16_t *)pinned_get(per * sizeof(uint16_t), &cap_lens[r]);
-        h_words[r] = (uint64_t *)pinned_get(per * 2 * sizeof(uint64_t), &cap_words[r]);  // grown when a chunk needs more
-        if (!h_lens[r] || !h_words[r]) return cleanup(fail(KMER_B200_ERR_OUT_OF_MEMORY, "pinned host allocation failed"));
-        cudaEventCreateWithFlags(&ev_slot[r], cudaEventDisableTiming);
-    }
+    h_lens = (uint16_t *)pinned_get(std::max<uint64_t>(Q, 1) * sizeof(uint16_t), &cap_lens);
+    if (!h_lens) return cleanup(fail(KMER_B200_ERR_OUT_OF_MEMORY, "pinned host allocation failed"));
+    uint64_t ring_words = 1;
     for (int c = 0; c < kChunks; ++c) {
+        n_sym_c[c] = q_offsets[c0[c + 1]] - q_offsets[c0[c]];
+        n_stream_words[c] = kb::pack_stream_words(n_sym_c[c], bits);
+        if (!raw[c]) ring_words = std::max(ring_words, n_stream_words[c] + 1);
         cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming);
     }
+    for (int r = 0; r < kRing; ++r) {
+        h_words[r] = (uint64_t *)pinned_get(ring_words * sizeof(uint64_t), &cap_words[r]);
+        if (!h_words[r]) return cleanup(fail(KMER_B200_ERR_OUT_OF_MEMORY, "pinned host allocation failed"));
+        cudaEventCreateWithFlags(&ev_slot[r], cudaEventDisableTiming);
+    }
+    // every device buffer the copy streams write, allocated now (stream-ordered on `st`) and fenced once
     if (dev_alloc(ix, &d_scan, kb::offsets_scan_blocks(per) + 1, false)) return cleanup(KMER_B200_ERR_OUT_OF_MEMORY);
+    for (int c = 0; c < kChunks; ++c) {
+        const uint64_t Qc = c0[c + 1] - c0[c];
+        if (Qc == 0) continue;
+        uint8_t *bytes = nullptr;
+        if (dev_alloc(ix, &d_lens[c], Qc, false) || dev_alloc(ix, &d_off[c], Qc + 1, false) ||
+            dev_alloc(ix, &bytes, raw[c] ? n_sym_c[c] : (n_stream_words[c] + 1) * sizeof(uint64_t), false))
+            return cleanup(KMER_B200_ERR_OUT_OF_MEMORY);
+        d_in[c] = bytes;
+    }
+    {
+        cudaEvent_t ev0;  // no copy stream runs ahead of the allocations or of work already queued on `st`
+        cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming);
+        cudaEventRecord(ev0, st);
+        cudaStreamWaitEvent(ix->copy_in, ev0, 0);
+        cudaStreamWaitEvent(ix->copy_in2, ev0, 0);
+        cudaStreamWaitEvent(ix->copy_out, ev0, 0);
+        cudaEventDestroy(ev0);
+    }
+    // the ranks of every raw chunk are queued now, on their own stream: the copy engine is busy from the first
+    // microsecond and never waits for the host threads (the chunks' lengths follow on the other stream, in chunk order)
+    for (int c = 0; c < kChunks; ++c) {
+        if (!raw[c] || c0[c + 1] == c0[c]) continue;
+        cudaEventCreateWithFlags(&ev_raw[c], cudaEventDisableTiming);
+        if (n_sym_c[c]) cudaMemcpyAsync(d_in[c], q_ranks + q_offsets[c0[c]], n_sym_c[c], cudaMemcpyHostToDevice, ix->copy_in2);
+        cudaEventRecord(ev_raw[c], ix->copy_in2);
+    }
     res = new (std::nothrow) kmer_b200_result();
     if (!res) return cleanup(fail(KMER_B200_ERR_OUT_OF_MEMORY, "host allocation failed"));
     res->index = ix;
@@ -2371,102 +2427,87 @@ static int search_batch_host_stream(kmer_b200_index *ix, const uint8_t *q_ranks,
     res->status = (uint8_t *)pinned_get(Q, &res->cap_status);
     if (!res->offsets || !res->status) return cleanup(fail(KMER_B200_ERR_OUT_OF_MEMORY, "pinned host allocation failed"));
 
-    // device buffers are allocated in stream order on `st`; the copy-in stream must not touch them earlier
-    auto fence_allocations = [&] {
-        cudaEvent_t ev_alloc;
-        cudaEventCreateWithFlags(&ev_alloc, cudaEventDisableTiming);
-        cudaEventRecord(ev_alloc, st);
-        cudaStreamWaitEvent(ix->copy_in, ev_alloc, 0);
-        cudaEventDestroy(ev_alloc);
-    };
-    // stage 1 of chunk c: lengths + longest query (blocking, short). A raw chunk is then handed to the copy engine at
-    // once; a stream chunk's pack is started on the pool (asynchronous) and uploaded by finish()
-    auto start = [&](int c) -> int {
-        const uint64_t qa = c0[c], qb = c0[c + 1], Qc = qb - qa;
-        if (Qc == 0 || unsupported) return 0;
-        const int slot = c % kRing;
-        if (c >= kRing) cudaEventSynchronize(ev_slot[slot]);  // the slot's previous H2D has left the staging buffers
-        pool.run(T * 4, [&, qa, qb, slot](unsigned t) { part_max[t] = kb::query_lengths_host(q_offsets, qa, qb, h_lens[slot], t, T * 4); });
-        uint64_t mx = 0;
-        for (uint64_t v : part_max) mx = std::max(mx, v);
-        max_len[c] = mx;
-        stride[c] = (uint32_t)std::max<uint64_t>(1, (mx + spw - 1) / spw);
-        if (mx > 65535 || (!raw[c] && stride[c] > max_stride)) {
-            unsupported = true;
-            return 0;
+    const int device = ix->device;
+    producer = std::thread([&] {
+        cudaSetDevice(device);
+        const auto t_begin = now();
+        std::vector<uint64_t> part_max(T * 4);
+        std::vector<uint8_t> part_ok(T * 4, 1);
+        int used = 0;
+        bool failed = false;
+        for (int c = 0; c < kChunks && !failed && !stop.load(); ++c) {
+            const uint64_t qa = c0[c], qb = c0[c + 1], Qc = qb - qa;
+            if (Qc) {
+                const uint8_t *src = q_ranks + q_offsets[qa];
+                const uint64_t n_sym = n_sym_c[c];
+                int slot = 0;
+                auto t0 = now();
+                if (!raw[c]) {
+                    slot = used++ % kRing;
+                    if (used > kRing) cudaEventSynchronize(ev_slot[slot]);  // the slot's previous H2D has left the staging buffer
+                    t_slot += since(t0);
+                    t0 = now();
+                    std::fill(part_ok.begin(), part_ok.end(), 1);
+                }
+                uint64_t *dst = h_words[slot];
+                const bool is_raw = raw[c];
+                pool.run(T * 4, [&, qa, qb, src, n_sym, dst, is_raw](unsigned t) {
+                    part_max[t] = kb::query_lengths_host(q_offsets, qa, qb, h_lens + qa, t, T * 4);
+                    if (!is_raw) part_ok[t] = kb::pack_stream_host(src, n_sym, bits, sigma, dst, t, T * 4) ? 1 : 0;
+                });
+                t_pool += since(t0);
+                t0 = now();
+                uint64_t mx = 0;
+                for (uint64_t v : part_max) mx = std::max(mx, v);
+                max_len[c] = mx;
+                stride[c] = (uint32_t)std::max<uint64_t>(1, (mx + spw - 1) / spw);
+                if (mx > 65535 || (!is_raw && stride[c] > max_stride)) unsupported = failed = true;
+                if (!is_raw)
+                    for (uint8_t ok : part_ok)
+                        if (!ok) bad_rank = failed = true;
+                if (!failed) {
+                    cudaStream_t cs = ix->copy_in;
+                    if (is_raw) {
+                        h2d += n_sym + Qc * sizeof(uint16_t);
+                    } else {
+                        dst[n_stream_words[c]] = 0;  // the padding word align_stream_kernel may read
+                        cudaMemcpyAsync(d_in[c], dst, (n_stream_words[c] + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, cs);
+                        h2d += (n_stream_words[c] + 1) * sizeof(uint64_t) + Qc * sizeof(uint16_t);
+                    }
+                    cudaMemcpyAsync(d_lens[c], h_lens + qa, Qc * sizeof(uint16_t), cudaMemcpyHostToDevice, cs);
+                    cudaEventRecord(ev_in[c], cs);
+                    if (!is_raw) cudaEventRecord(ev_slot[slot], cs);
+                }
+                t_enqueue += since(t0);
+            }
+            {
+                std::lock_guard<std::mutex> lock(mu);
+                if (failed) producer_failed = true;
+                else produced = c + 1;
+            }
+            cv.notify_all();
         }
-        const uint64_t n_sym = q_offsets[qb] - q_offsets[qa];
-        KB_TRY(dev_alloc(ix, &d_lens[c], Qc, false));
-        KB_TRY(dev_alloc(ix, &d_off[c], Qc + 1, false));
-        if (raw[c]) {
-            uint8_t *d_raw = nullptr;
-            KB_TRY(dev_alloc(ix, &d_raw, n_sym, false));
-            d_in[c] = d_raw;
-            fence_allocations();
-            if (n_sym) cudaMemcpyAsync(d_raw, q_ranks + q_offsets[qa], n_sym, cudaMemcpyHostToDevice, ix->copy_in);
-            cudaMemcpyAsync(d_lens[c], h_lens[slot], Qc * sizeof(uint16_t), cudaMemcpyHostToDevice, ix->copy_in);
-            h2d += n_sym + Qc * sizeof(uint16_t);
-            cudaEventRecord(ev_in[c], ix->copy_in);
-            cudaEventRecord(ev_slot[slot], ix->copy_in);
-            return 0;
-        }
-        n_stream_words[c] = kb::pack_stream_words(n_sym, bits);
-        const size_t need = (n_stream_words[c] + 1) * sizeof(uint64_t);
-        if (need > cap_words[slot]) {
-            pinned_put(h_words[slot], cap_words[slot]);
-            h_words[slot] = (uint64_t *)pinned_get(need, &cap_words[slot]);
-            if (!h_words[slot]) return fail(KMER_B200_ERR_OUT_OF_MEMORY, "pinned host allocation failed");
-        }
-        std::fill(part_ok.begin(), part_ok.end(), 1);
-        const uint8_t *src = q_ranks + q_offsets[qa];
-        pool.submit(T * 4, [&, src, n_sym, slot](unsigned t) {
-            part_ok[t] = kb::pack_stream_host(src, n_sym, bits, ix->sigma, h_words[slot], t, T * 4) ? 1 : 0;
-        });
-        return 0;
-    };
-    auto finish = [&](int c) -> int {
-        const uint64_t qa = c0[c], qb = c0[c + 1], Qc = qb - qa;
-        if (Qc == 0 || raw[c]) return 0;
-        pool.wait();
-        if (unsupported) return 0;
-        for (uint8_t ok : part_ok) bad_rank = bad_rank || !ok;
-        const int slot = c % kRing;
-        h_words[slot][n_stream_words[c]] = 0;  // the padding word align_stream_kernel may read
-        uint64_t *d_stream = nullptr;
-        KB_TRY(dev_alloc(ix, &d_stream, n_stream_words[c] + 1, false));
-        d_in[c] = d_stream;
-        KB_TRY(dev_alloc(ix, &d_words[c], Qc * stride[c], false));
-        fence_allocations();
-        cudaMemcpyAsync(d_stream, h_words[slot], (n_stream_words[c] + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ix->copy_in);
-        cudaMemcpyAsync(d_lens[c], h_lens[slot], Qc * sizeof(uint16_t), cudaMemcpyHostToDevice, ix->copy_in);
-        h2d += (n_stream_words[c] + 1) * sizeof(uint64_t) + Qc * sizeof(uint16_t);
-        cudaEventRecord(ev_in[c], ix->copy_in);
-        cudaEventRecord(ev_slot[slot], ix->copy_in);
-        return 0;
-    };
+        t_producer = since(t_begin);
+    });
 
-    {
-        cudaEvent_t ev0;  // the copy-out stream must not run ahead of work already queued on `st`
-        cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming);
-        cudaEventRecord(ev0, st);
-        cudaStreamWaitEvent(ix->copy_out, ev0, 0);
-        cudaEventDestroy(ev0);
-    }
-    if (int s = start(0)) return cleanup(s);
-    if (int s = finish(0)) return cleanup(s);
-    if (kChunks > 1)
-        if (int s = start(1)) return cleanup(s);
     uint64_t base = 0;
-    for (int c = 0; c < kChunks && !unsupported; ++c) {
-        if (c + 1 < kChunks) {
-            if (int s = finish(c + 1)) return cleanup(s);
-            if (c + 2 < kChunks)
-                if (int s = start(c + 2)) return cleanup(s);
+    bool ok_so_far = true;
+    for (int c = 0; c < kChunks; ++c) {
+        {
+            const auto t0 = now();
+            std::unique_lock<std::mutex> lock(mu);
+            cv.wait(lock, [&] { return produced > c || producer_failed; });
+            t_wait_chunk += since(t0);
+            if (produced <= c) {
+                ok_so_far = false;
+                break;
+            }
         }
-        if (unsupported || bad_rank) break;
         const uint64_t qa = c0[c], qb = c0[c + 1], Qc = qb - qa;
         if (Qc == 0) continue;
+        const auto t0 = now();
         cudaStreamWaitEvent(st, ev_in[c], 0);
+        if (raw[c]) cudaStreamWaitEvent(st, ev_raw[c], 0);
         // lengths -> chunk-relative offsets: widen, exclusive scan (the total lands in entry Qc)
         widen_lens_kernel<<<(unsigned)((Qc + 255) / 256), 256, 0, st>>>(d_lens[c], Qc, d_off[c]);
         kb::launch_offsets_scan(d_off[c], Qc, d_scan, st);
@@ -2475,10 +2516,13 @@ static int search_batch_host_stream(kmer_b200_index *ix, const uint8_t *q_ranks,
             s = search_device_impl(ix, (const uint8_t *)d_in[c], d_off[c], Qc, max_len[c], mode, nullptr, 0, kFlavorFull, &chunk_res[c]);
         } else {
             const uint64_t n_out = Qc * stride[c];
-            align_stream_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>((const uint64_t *)d_in[c], d_off[c], d_lens[c], Qc,
-                                                                                stride[c], bits, d_words[c]);
-            PackedQueries pk{d_words[c], d_lens[c], stride[c]};
-            s = search_device_impl(ix, nullptr, nullptr, Qc, max_len[c], mode, nullptr, 0, kFlavorFull, &chunk_res[c], &pk);
+            s = dev_alloc(ix, &d_words[c], n_out, false);
+            if (s == 0) {
+                align_stream_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>((const uint64_t *)d_in[c], d_off[c], d_lens[c], Qc,
+                                                                                    stride[c], bits, d_words[c]);
+                PackedQueries pk{d_words[c], d_lens[c], stride[c]};
+                s = search_device_impl(ix, nullptr, nullptr, Qc, max_len[c], mode, nullptr, 0, kFlavorFull, &chunk_res[c], &pk);
+            }
         }
         if (s != 0) return cleanup(s);
         kmer_b200_result *cr = chunk_res[c];
@@ -2488,9 +2532,11 @@ static int search_batch_host_stream(kmer_b200_index *ix, const uint8_t *q_ranks,
         cudaMemcpyAsync(res->offsets + qa, cr->offsets, Qc * sizeof(uint64_t), cudaMemcpyDeviceToHost, ix->copy_out);
         cudaMemcpyAsync(res->status + qa, cr->status, Qc, cudaMemcpyDeviceToHost, ix->copy_out);
         base += cr->n_positions;
+        t_search += since(t0);
     }
+    producer.join();
     if (bad_rank) return cleanup(fail(KMER_B200_ERR_INVALID_RANK, "a query contains a rank >= sigma"));
-    if (unsupported) return cleanup(KMER_B200_ERR_UNSUPPORTED);  // the caller falls back to the unpacked pipeline
+    if (unsupported || !ok_so_far) return cleanup(KMER_B200_ERR_UNSUPPORTED);  // the caller falls back to the unpacked pipeline
     res->n_positions = base;
     const size_t pos_bytes = base * sizeof(uint32_t);
     if (pos_bytes > (8ull << 30)) {
@@ -2514,7 +2560,13 @@ static int search_batch_host_stream(kmer_b200_index *ix, const uint8_t *q_ranks,
     ix->last_h2d = h2d;
     ix->last_d2h = Q * 9 + base * sizeof(uint32_t);
     *out = res;
-    return cleanup(0);
+    const double t_loop = since(t_call);
+    const int code = cleanup(0);
+    if (trace)
+        std::fprintf(stderr, "[kmer_b200 host trace] raw %u %%: producer %.2f (slot wait %.2f | lengths + pack %.2f | enqueue %.2f) | caller: "
+                     "wait for chunk %.2f | search %.2f | to last D2H %.2f | with cleanup %.2f ms\n", raw_pct, t_producer, t_slot, t_pool,
+                     t_enqueue, t_wait_chunk, t_search, t_loop, since(t_call));
+    return code;
 }
 
 static int search_batch_host(kmer_b200_index *ix, const uint8_t *q_ranks, const uint64_t *q_offsets, uint64_t Q,
@@ -2579,7 +2631,7 @@ static int search_batch_host(kmer_b200_index *ix, const uint8_t *q_ranks, const 
             double rate = 0;
             if (!input_pageable && forced != 2) {
                 rate = stream_pack_rate(q_ranks + q_offsets[0], n_sym, ix->bits, ix->sigma);
-                raw_pct = raw_chunk_percent(rate / std::max(1u, ix->host_sharers), ix->bits);
+                raw_pct = raw_chunk_percent(rate / std::max(1u, ix->host_sharers), ix->bits, n_sym, Q);
                 if (const char *env = std::getenv("KMER_B200_HOST_RAW_PCT")) raw_pct = (uint32_t)std::max(0, std::min(100, std::atoi(env)));
             }
             const int s = search_batch_host_stream(ix, q_ranks, q_offsets, Q, mode, raw_pct, out);

@@ -73,6 +73,48 @@ def _planted(text, Q, m_lo, m_hi, seed):
     return text[idx], off
 
 
+@pytest.mark.parametrize("sigma,k", [(4, 12), (15, 6)])
+def test_pipelined_text_upload_equals_plain(kb, sigma, k):
+    """Host texts of 64 Mi symbols or more (2- and 4-bit alphabets) reach the device through the host threads' streaming
+    pack, pinned ones partly as 1-byte ranks over the copy engine at the same time: the index must be the one the plain
+    upload builds, and a rank >= sigma must be reported from either kind of chunk."""
+    import os
+
+    import torch
+
+    from kmer_index_b200 import synth
+    n = 70_000_037
+    text = synth.random_text(n, sigma, TEXT_SEED + 3)
+    pinned = torch.from_numpy(text).pin_memory()
+    os.environ["KMER_B200_NO_TEXT_PIPELINE"] = "1"
+    try:
+        with kb.KmerIndex(text, sigma, [k]) as ix:
+            want = ix.element_arrays(0)
+    finally:
+        del os.environ["KMER_B200_NO_TEXT_PIPELINE"]
+    builds = [("pageable", text, None), ("pinned, calibrated share", pinned.numpy(), None),
+              ("pinned, 34 % raw", pinned.numpy(), "34"), ("pinned, all raw", pinned.numpy(), "100")]
+    for label, src, pct in builds:
+        if pct is not None:
+            os.environ["KMER_B200_HOST_RAW_PCT"] = pct
+        try:
+            with kb.KmerIndex(src, sigma, [k]) as ix:
+                got = ix.element_arrays(0)
+        finally:
+            os.environ.pop("KMER_B200_HOST_RAW_PCT", None)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), label
+    os.environ["KMER_B200_HOST_RAW_PCT"] = "50"
+    try:
+        for at in (3, 40_000_000, n - 1):                      # first chunk (raw), a packed chunk, the last word
+            bad = pinned.numpy().copy()
+            bad[at] = sigma
+            with pytest.raises(kb.KmerB200Error) as e:
+                kb.KmerIndex(torch.from_numpy(bad).pin_memory().numpy(), sigma, [k])
+            assert e.value.code == -4, at
+    finally:
+        del os.environ["KMER_B200_HOST_RAW_PCT"]
+
+
 def test_pipelined_host_batch_equals_plain(kb):
     """Host batches >= 256 MiB are searched in pipelined chunks (H2D / search / D2H overlapped); the result must be
     the plain path's, offsets included."""
