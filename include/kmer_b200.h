@@ -385,6 +385,9 @@ uint64_t kmer_b200_last_search_gathers(const kmer_b200_index *index);
 /* Bytes the last kmer_b200_search_batch / _ptrs / _text on this handle moved over PCIe: host to device (ranks as they are
    or packed, offsets or 16-bit lengths -- whichever the call chose) and device to host (offsets, status, positions). */
 void kmer_b200_last_search_transfer(const kmer_b200_index *index, uint64_t *h2d_bytes, uint64_t *d2h_bytes);
+/* Bytes the text took over PCIe when the index was built from a host buffer (large 2- / 4-bit texts are partly packed on
+   the host threads first); 0 for an index built from device memory or loaded from a file. */
+uint64_t kmer_b200_build_transfer(const kmer_b200_index *index);
 /* Which host pipeline that call took: 0 = one copy each way (small batches), 1 = chunks of 1-byte ranks, 2 = chunks packed
    query by query on the host threads, 3 = chunks packed as a stream on the host threads (+ raw_pct percent of the chunks
    sent as 1-byte ranks at the same time; pack_gbs = the host's measured streaming pack rate, 0 when not needed). */

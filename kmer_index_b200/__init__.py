@@ -561,6 +561,10 @@ class KmerIndex:
         self._L.kmer_b200_last_search_transfer(self._h, C.byref(a), C.byref(b))
         return int(a.value), int(b.value)
 
+    def build_transfer(self) -> int:
+        """Bytes the text took over PCIe when this index was built from a host buffer (kmer_b200_build_transfer)."""
+        return int(self._L.kmer_b200_build_transfer(self._h))
+
     def last_search_host_path(self) -> dict:
         """Which host pipeline the last host-buffer search took (kmer_b200_last_search_host_path)."""
         a, b, r = C.c_uint32(0), C.c_uint32(0), C.c_double(0)

@@ -140,6 +140,7 @@ SYMBOLS = {
     "kmer_b200_debug_guard_selftest": (C.c_int, []),
     "kmer_b200_last_search_gathers": (C.c_uint64, [C.c_void_p]),
     "kmer_b200_last_search_transfer": (None, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "kmer_b200_build_transfer": (C.c_uint64, [C.c_void_p]),
     "kmer_b200_last_search_host_path": (None, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_double)]),
     "kmer_b200_gather_probe": (C.c_int, [C.c_uint64, C.c_uint64, C.c_void_p, C.POINTER(C.c_double)]),
     "kmer_b200_gather_probe_at": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.POINTER(C.c_double)]),

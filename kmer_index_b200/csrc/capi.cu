@@ -12,6 +12,7 @@
 #include <unordered_map>
 #include <new>
 #include <string>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -213,6 +214,7 @@ struct kmer_b200_index {
     unsigned long long *d_gathers = nullptr;  // profile mode: sectors gathered by the last search
     uint64_t last_gathers = 0;
     uint64_t last_h2d = 0, last_d2h = 0;  // bytes the last host-buffer search moved over PCIe (kmer_b200_last_search_transfer)
+    uint64_t build_h2d = 0;               // bytes the text took on its way to the device (kmer_b200_build_transfer)
     uint32_t last_host_path = 0, last_raw_pct = 0;  // which host pipeline it took (kmer_b200_last_search_host_path)
     double last_pack_gbs = 0;
     uint32_t host_sharers = 1;  // devices of a multi-device handle searching at the same time: they share the host packers
@@ -1049,6 +1051,7 @@ static int upload_text_stream(kmer_b200_index *ix, const uint8_t *ranks, uint64_
     cudaMemsetAsync(ix->d_text + n_words, 0, (ix->text_words - n_words) * sizeof(uint64_t), st);
     cudaEventRecord(ev, st);
     cudaStreamWaitEvent(ix->copy_in, ev, 0);
+    ix->build_h2d = 0;
     // chunks in text order: a raw chunk costs the host nothing (one enqueue), so the copy engine always has some queued
     // while the host threads pack; the ring's slots are handed over in the same queue and come back in time
     uint64_t at = 0, used = 0;
@@ -1059,6 +1062,7 @@ static int upload_text_stream(kmer_b200_index *ix, const uint8_t *ranks, uint64_
         const uint64_t s0 = c * chunk, len = std::min(chunk, n - s0);
         if (raw[c]) {
             cudaMemcpyAsync(d_raw + at, ranks + s0, len, cudaMemcpyHostToDevice, ix->copy_in);
+            ix->build_h2d += len;
             cudaEventRecord(ev, ix->copy_in);
             cudaStreamWaitEvent(st, ev, 0);
             kb::launch_pack_text(d_raw + at, len, bits, ix->sigma, kb::pack_stream_words(len, bits), ix->d_text + s0 / spw, ix->d_flags, st);
@@ -1073,6 +1077,7 @@ static int upload_text_stream(kmer_b200_index *ix, const uint8_t *ranks, uint64_
         if (bad_rank) break;
         cudaMemcpyAsync(ix->d_text + s0 / spw, h_words[slot], kb::pack_stream_words(len, bits) * sizeof(uint64_t), cudaMemcpyHostToDevice,
                         ix->copy_in);
+        ix->build_h2d += kb::pack_stream_words(len, bits) * sizeof(uint64_t);
         cudaEventRecord(ev_slot[slot], ix->copy_in);
     }
     ix->prof.end();
@@ -1103,6 +1108,7 @@ int create_impl(const uint8_t *ranks, bool ranks_on_device, uint64_t n, uint32_t
             if (!ranks_on_device) {
                 KB_TRY(dev_alloc(ix, &d_ranks_owned, n, false));
                 KB_CUDA_RET(cudaMemcpyAsync(d_ranks_owned, ranks, n, cudaMemcpyHostToDevice, ix->stream));
+                ix->build_h2d = n;
                 d_ranks = d_ranks_owned;
                 if (lut256) KB_TRY(translate_on_device(ix, d_ranks_owned, n, lut256));  // invalid characters map to >= sigma
             }
@@ -2338,7 +2344,7 @@ static int search_batch_host_stream(kmer_b200_index *ix, const uint8_t *q_ranks,
     uint32_t stride[kChunks] = {};
     uint64_t max_len[kChunks] = {}, n_sym_c[kChunks] = {}, n_stream_words[kChunks] = {};
     kmer_b200_result *chunk_res[kChunks] = {};
-    cudaEvent_t ev_in[kChunks] = {}, ev_raw[kChunks] = {}, ev_done[kChunks] = {}, ev_slot[kRing] = {};
+    cudaEvent_t ev_in[kChunks] = {}, ev_done[kChunks] = {}, ev_slot[kRing] = {};
     kmer_b200_result *res = nullptr;
     // producer -> calling thread
     std::mutex mu;
@@ -2359,7 +2365,6 @@ static int search_batch_host_stream(kmer_b200_index *ix, const uint8_t *q_ranks,
         for (int c = 0; c < kChunks; ++c) {
             if (chunk_res[c]) kmer_b200_result_free(chunk_res[c]);
             if (ev_in[c]) cudaEventDestroy(ev_in[c]);
-            if (ev_raw[c]) cudaEventDestroy(ev_raw[c]);
             if (ev_done[c]) cudaEventDestroy(ev_done[c]);
             dev_free(ix, (uint8_t *)d_in[c]);
             dev_free(ix, d_words[c]);
@@ -2410,14 +2415,6 @@ static int search_batch_host_stream(kmer_b200_index *ix, const uint8_t *q_ranks,
         cudaStreamWaitEvent(ix->copy_out, ev0, 0);
         cudaEventDestroy(ev0);
     }
-    // the ranks of every raw chunk are queued now, on their own stream: the copy engine is busy from the first
-    // microsecond and never waits for the host threads (the chunks' lengths follow on the other stream, in chunk order)
-    for (int c = 0; c < kChunks; ++c) {
-        if (!raw[c] || c0[c + 1] == c0[c]) continue;
-        cudaEventCreateWithFlags(&ev_raw[c], cudaEventDisableTiming);
-        if (n_sym_c[c]) cudaMemcpyAsync(d_in[c], q_ranks + q_offsets[c0[c]], n_sym_c[c], cudaMemcpyHostToDevice, ix->copy_in2);
-        cudaEventRecord(ev_raw[c], ix->copy_in2);
-    }
     res = new (std::nothrow) kmer_b200_result();
     if (!res) return cleanup(fail(KMER_B200_ERR_OUT_OF_MEMORY, "host allocation failed"));
     res->index = ix;
@@ -2428,7 +2425,7 @@ static int search_batch_host_stream(kmer_b200_index *ix, const uint8_t *q_ranks,
     if (!res->offsets || !res->status) return cleanup(fail(KMER_B200_ERR_OUT_OF_MEMORY, "pinned host allocation failed"));
 
     const int device = ix->device;
-    producer = std::thread([&] {
+    auto produce = [&] {
         cudaSetDevice(device);
         const auto t_begin = now();
         std::vector<uint64_t> part_max(T * 4);
@@ -2466,8 +2463,12 @@ static int search_batch_host_stream(kmer_b200_index *ix, const uint8_t *q_ranks,
                     for (uint8_t ok : part_ok)
                         if (!ok) bad_rank = failed = true;
                 if (!failed) {
-                    cudaStream_t cs = ix->copy_in;
+                    // raw chunks on their own H2D stream: a 175 MB copy does not hold up the packed chunk behind it, whose
+                    // ring slot the packers want back (queueing every raw chunk up front was tried: the raw stream then
+                    // starves the packed one and the ring stalls -- 64 ms against 54)
+                    cudaStream_t cs = is_raw ? ix->copy_in2 : ix->copy_in;
                     if (is_raw) {
+                        if (n_sym) cudaMemcpyAsync(d_in[c], src, n_sym, cudaMemcpyHostToDevice, cs);
                         h2d += n_sym + Qc * sizeof(uint16_t);
                     } else {
                         dst[n_stream_words[c]] = 0;  // the padding word align_stream_kernel may read
@@ -2488,7 +2489,12 @@ static int search_batch_host_stream(kmer_b200_index *ix, const uint8_t *q_ranks,
             cv.notify_all();
         }
         t_producer = since(t_begin);
-    });
+    };
+    try {
+        producer = std::thread(produce);
+    } catch (const std::system_error &) {  // no thread to be had: the caller takes one of the single-threaded pipelines
+        return cleanup(KMER_B200_ERR_UNSUPPORTED);
+    }
 
     uint64_t base = 0;
     bool ok_so_far = true;
@@ -2507,7 +2513,6 @@ static int search_batch_host_stream(kmer_b200_index *ix, const uint8_t *q_ranks,
         if (Qc == 0) continue;
         const auto t0 = now();
         cudaStreamWaitEvent(st, ev_in[c], 0);
-        if (raw[c]) cudaStreamWaitEvent(st, ev_raw[c], 0);
         // lengths -> chunk-relative offsets: widen, exclusive scan (the total lands in entry Qc)
         widen_lens_kernel<<<(unsigned)((Qc + 255) / 256), 256, 0, st>>>(d_lens[c], Qc, d_off[c]);
         kb::launch_offsets_scan(d_off[c], Qc, d_scan, st);
@@ -3996,6 +4001,14 @@ int kmer_b200_debug_guard_selftest(void) {
 }
 
 uint64_t kmer_b200_last_search_gathers(const kmer_b200_index *ix) { return ix ? primary(ix)->last_gathers : 0; }
+
+uint64_t kmer_b200_build_transfer(const kmer_b200_index *ix) {
+    if (!ix) return 0;
+    if (ix->replicas.empty()) return ix->build_h2d;
+    uint64_t sum = 0;
+    for (const kmer_b200_index *r : ix->replicas) sum += r->build_h2d;
+    return sum;
+}
 
 void kmer_b200_last_search_host_path(const kmer_b200_index *ix, uint32_t *pipeline, uint32_t *raw_pct, double *pack_gbs) {
     const kmer_b200_index *p = ix && !ix->replicas.empty() ? ix->replicas[0] : ix;

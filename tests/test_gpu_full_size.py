@@ -100,9 +100,17 @@ def test_pipelined_text_upload_equals_plain(kb, sigma, k):
         try:
             with kb.KmerIndex(src, sigma, [k]) as ix:
                 got = ix.element_arrays(0)
+                moved = ix.build_transfer()
         finally:
             os.environ.pop("KMER_B200_HOST_RAW_PCT", None)
         assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), label
+        bits = 2 if sigma <= 4 else 4
+        if label == "pageable":
+            assert n * bits // 8 <= moved <= n * bits // 8 + 64, (label, moved)   # every chunk crossed the link packed
+        elif pct == "100":
+            assert moved == n, (label, moved)
+        else:
+            assert n * bits // 8 <= moved <= n, (label, moved)
     os.environ["KMER_B200_HOST_RAW_PCT"] = "50"
     try:
         for at in (3, 40_000_000, n - 1):                      # first chunk (raw), a packed chunk, the last word
