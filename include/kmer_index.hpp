@@ -32,9 +32,11 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#include <memory>
 #include <ranges>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <utility>
 #include <vector>
@@ -158,6 +160,51 @@ namespace kmer
             auto end() const noexcept { return _positions.end(); }
         };
 
+        // read-only view of an array that a batch result keeps alive (search_batch() hands the library's pinned result
+        // buffers out as they are: a batch of 10^8 queries is 0.9 GB that nobody should copy on one thread)
+        template<typename T>
+        class array_view
+        {
+            T const* _data = nullptr;
+            std::size_t _size = 0;
+
+        public:
+            using value_type = T;
+            array_view() = default;
+            array_view(T const* data, std::size_t size) : _data(data), _size(size) {}
+            std::size_t size() const noexcept { return _size; }
+            bool empty() const noexcept { return _size == 0; }
+            T const* data() const noexcept { return _data; }
+            T const* begin() const noexcept { return _data; }
+            T const* end() const noexcept { return _data + _size; }
+            T const& operator[](std::size_t i) const { return _data[i]; }
+            T const& front() const { return _data[0]; }
+            T const& back() const { return _data[_size - 1]; }
+            std::vector<T> to_vector() const { return std::vector<T>(begin(), end()); }
+            friend bool operator==(array_view const& a, array_view const& b)
+            {
+                return a._size == b._size && std::equal(a.begin(), a.end(), b.begin());
+            }
+            friend bool operator==(array_view const& a, std::vector<T> const& b)
+            {
+                return a._size == b.size() && std::equal(a.begin(), a.end(), b.begin());
+            }
+        };
+
+        // fn(lo, hi) over [0, n) on the host's cores (large batches only: a thread costs more than 10^4 iterations)
+        template<typename fn_t>
+        void parallel_ranges(std::size_t n, fn_t&& fn)
+        {
+            std::size_t const n_threads = n < (std::size_t(1) << 18) ? 1 : std::min<std::size_t>(std::max(1u, std::thread::hardware_concurrency()), 32);
+            if (n_threads == 1)
+                return fn(std::size_t(0), n);
+            std::vector<std::thread> workers;
+            for (std::size_t t = 0; t < n_threads; ++t)
+                workers.emplace_back([&fn, n, t, n_threads] { fn(n * t / n_threads, n * (t + 1) / n_threads); });
+            for (auto& w : workers)
+                w.join();
+        }
+
         inline void check(int status)
         {
             if (status == KMER_B200_OK)
@@ -186,13 +233,16 @@ namespace kmer
         }
     }
 
-    // result of search_batch(): CSR over the batch
+    // result of search_batch(): CSR over the batch. offsets / status (and positions, for 32-bit position types) are views
+    // of the library's result buffers, which this object keeps alive; copies of the object share them.
     template<typename position_t>
     struct kmer_batch_result
     {
-        std::vector<std::uint64_t> offsets;   // [n_queries + 1]
-        std::vector<position_t> positions;    // ascending per query
-        std::vector<std::uint8_t> status;     // kmer_b200_query_status per query
+        using positions_t = std::conditional_t<std::is_same_v<position_t, std::uint32_t>, detail::array_view<std::uint32_t>,
+                                               std::vector<position_t>>;
+        detail::array_view<std::uint64_t> offsets;   // [n_queries + 1]
+        positions_t positions;                       // ascending per query
+        detail::array_view<std::uint8_t> status;     // kmer_b200_query_status per query
 
         std::size_t size() const noexcept { return status.size(); }
         bool threw(std::size_t i) const { return status[i] == KMER_B200_QUERY_THROW_INVALID_ARGUMENT; }
@@ -201,6 +251,21 @@ namespace kmer
             return detail::kmer_index_result<position_t>(
                 std::vector<position_t>(positions.begin() + offsets[i], positions.begin() + offsets[i + 1]));
         }
+
+        kmer_batch_result() = default;
+        explicit kmer_batch_result(kmer_b200_result* r) : _owner(r, kmer_b200_result_free)
+        {
+            const std::uint64_t n_q = kmer_b200_result_n_queries(r), n_p = kmer_b200_result_n_positions(r);
+            offsets = {kmer_b200_result_offsets(r), std::size_t(n_q + 1)};
+            status = {kmer_b200_result_status(r), std::size_t(n_q)};
+            if constexpr (std::is_same_v<position_t, std::uint32_t>)
+                positions = {kmer_b200_result_positions(r), std::size_t(n_p)};
+            else if (n_p)
+                positions.assign(kmer_b200_result_positions(r), kmer_b200_result_positions(r) + n_p);
+        }
+
+    private:
+        std::shared_ptr<kmer_b200_result> _owner;
     };
 
     // tag for the shared-positions constructor below
@@ -333,14 +398,33 @@ namespace kmer
             if constexpr (detail::ranks_in_place<query_t> && std::is_lvalue_reference_v<std::ranges::range_reference_t<queries_t const>>)
             {
                 // queries in their own contiguous 1-byte storage: hand over pointers, the library gathers them in parallel
-                std::vector<std::uint8_t const*> ptrs;
-                std::vector<std::uint64_t> lens;
-                for (auto const& q : queries)
+                if constexpr (std::ranges::random_access_range<queries_t const> && std::ranges::sized_range<queries_t const>)
                 {
-                    ptrs.push_back(reinterpret_cast<std::uint8_t const*>(std::ranges::data(q)));
-                    lens.push_back(std::ranges::size(q));
+                    // (a batch of 10^8 std::vectors: collecting the pointers is 2.4 GB of reads -- all cores)
+                    const std::size_t n_q = std::ranges::size(queries);
+                    std::unique_ptr<std::uint8_t const*[]> ptrs(new std::uint8_t const*[n_q]);
+                    std::unique_ptr<std::uint64_t[]> lens(new std::uint64_t[n_q]);
+                    detail::parallel_ranges(n_q, [&](std::size_t lo, std::size_t hi) {
+                        auto it = std::ranges::begin(queries) + static_cast<std::ranges::range_difference_t<queries_t const>>(lo);
+                        for (std::size_t i = lo; i < hi; ++i, ++it)
+                        {
+                            ptrs[i] = reinterpret_cast<std::uint8_t const*>(std::ranges::data(*it));
+                            lens[i] = std::ranges::size(*it);
+                        }
+                    });
+                    detail::check(kmer_b200_search_batch_ptrs(_handle, ptrs.get(), lens.get(), n_q, UINT32_MAX, &r));
                 }
-                detail::check(kmer_b200_search_batch_ptrs(_handle, ptrs.data(), lens.data(), ptrs.size(), UINT32_MAX, &r));
+                else
+                {
+                    std::vector<std::uint8_t const*> ptrs;
+                    std::vector<std::uint64_t> lens;
+                    for (auto const& q : queries)
+                    {
+                        ptrs.push_back(reinterpret_cast<std::uint8_t const*>(std::ranges::data(q)));
+                        lens.push_back(std::ranges::size(q));
+                    }
+                    detail::check(kmer_b200_search_batch_ptrs(_handle, ptrs.data(), lens.data(), ptrs.size(), UINT32_MAX, &r));
+                }
             }
             else
             {
@@ -354,14 +438,7 @@ namespace kmer
                 }
                 detail::check(kmer_b200_search_batch(_handle, ranks.data(), offsets.data(), offsets.size() - 1, UINT32_MAX, &r));
             }
-            kmer_batch_result<position_t> out;
-            const std::uint64_t n_q = kmer_b200_result_n_queries(r), n_p = kmer_b200_result_n_positions(r);
-            out.offsets.assign(kmer_b200_result_offsets(r), kmer_b200_result_offsets(r) + n_q + 1);
-            out.status.assign(kmer_b200_result_status(r), kmer_b200_result_status(r) + n_q);
-            if (n_p)
-                out.positions.assign(kmer_b200_result_positions(r), kmer_b200_result_positions(r) + n_p);
-            kmer_b200_result_free(r);
-            return out;
+            return kmer_batch_result<position_t>(r);
         }
 
         // kmer_index_element::search_k (kmer_index.hpp:182-190): the bucket of the k symbols starting at `it`, for one
@@ -387,7 +464,7 @@ namespace kmer
                 throw std::invalid_argument("query size too low for specified k");
             if (batch.status[0] != KMER_B200_QUERY_OK)
                 throw std::invalid_argument("query length 0 or 10000 is undefined in the reference (kmer_index.hpp:195,512)");
-            return result_t(std::move(batch.positions));
+            return result_t(std::vector<position_t>(batch.positions.begin(), batch.positions.end()));
         }
 
         result_t search(std::vector<alphabet_t>&& query) const   // :561-565, with the missing return

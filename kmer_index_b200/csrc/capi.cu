@@ -2739,7 +2739,7 @@ int kmer_b200_search_batch_ptrs(kmer_b200_index *ix, const uint8_t *const *q_ptr
     // gather into one buffer with the host threads (offsets by a two-level prefix sum), then the ordinary host batch
     kb::HostPool &pool = kb::HostPool::instance();
     const unsigned T = std::max(1u, pool.threads());
-    std::vector<uint64_t> offsets(Q + 1), part_sum(T + 1, 0);
+    std::vector<uint64_t> part_sum(T + 1, 0);
     pool.run(T, [&](unsigned t) {
         uint64_t s = 0;
         for (uint64_t i = Q * t / T; i < Q * (t + 1) / T; ++i) s += q_lens[i];
@@ -2747,12 +2747,25 @@ int kmer_b200_search_batch_ptrs(kmer_b200_index *ix, const uint8_t *const *q_ptr
     });
     for (unsigned t = 0; t < T; ++t) part_sum[t + 1] += part_sum[t];
     const uint64_t total = part_sum[T];
+    // both buffers are first touched by the threads that fill them (a zero-initialised vector of 10^8 offsets would be
+    // 0.8 GB of page faults on the calling thread)
+    uint64_t *offsets = (uint64_t *)std::malloc((Q + 1) * sizeof(uint64_t));
     uint8_t *ranks = (uint8_t *)std::malloc(std::max<uint64_t>(total, 1) + 8);
-    if (!ranks) return fail(KMER_B200_ERR_OUT_OF_MEMORY, "host allocation failed");
+    if (!ranks || !offsets) {
+        std::free(offsets);
+        std::free(ranks);
+        return fail(KMER_B200_ERR_OUT_OF_MEMORY, "host allocation failed");
+    }
     bool null_query = false;
     pool.run(T, [&](unsigned t) {
         uint64_t o = part_sum[t];
-        for (uint64_t i = Q * t / T; i < Q * (t + 1) / T; ++i) {
+        const uint64_t i_end = Q * (t + 1) / T;
+        for (uint64_t i = Q * t / T; i < i_end; ++i) {
+            // the queries are heap blocks of their own: a cache miss each unless asked for ahead of time
+            if (i + 16 < i_end && q_ptrs[i + 16]) {
+                __builtin_prefetch(q_ptrs[i + 16]);
+                __builtin_prefetch(q_ptrs[i + 16] + 63);
+            }
             offsets[i] = o;
             if (q_lens[i]) {
                 if (!q_ptrs[i]) {
@@ -2766,8 +2779,9 @@ int kmer_b200_search_batch_ptrs(kmer_b200_index *ix, const uint8_t *const *q_ptr
     });
     offsets[Q] = total;
     int s = null_query ? fail(KMER_B200_ERR_INVALID_ARGUMENT, "a query pointer is null")
-                       : search_batch_host(ix, ranks, offsets.data(), Q, mode, nullptr, out);
+                       : search_batch_host(ix, ranks, offsets, Q, mode, nullptr, out);
     std::free(ranks);
+    std::free(offsets);
     return s;
 }
 
