@@ -161,7 +161,11 @@ int kmer_b200_load(const char *path, const kmer_b200_config *cfg, kmer_b200_inde
    by kmer_index_result::to_vector() (kmer_index_result.hpp:244-260), for a batch of Q queries.
    q_ranks: all queries' ranks back to back; q_offsets[Q+1]: start of each query in q_ranks.
    The result holds, in host memory, offsets[Q+1], the per-query ascending hit positions back to back,
-   and status[Q] (kmer_b200_query_status). mode: a kmer_b200_mode, or UINT32_MAX for the index default. */
+   and status[Q] (kmer_b200_query_status). mode: a kmer_b200_mode, or UINT32_MAX for the index default.
+   Batches of 256 MiB or more are cut into chunks that are uploaded, searched and downloaded concurrently; for 2- and
+   4-bit alphabets the library's host threads pack part of the chunks before they cross PCIe (all of them when the
+   buffers are pageable), the copy engine moves the rest as they are ("Host path"). The buffers may
+   be pinned or pageable; they are only read, and only during the call. */
 int kmer_b200_search_batch(kmer_b200_index *index, const uint8_t *q_ranks, const uint64_t *q_offsets, uint64_t n_queries,
                            uint32_t mode, kmer_b200_result **out);
 
