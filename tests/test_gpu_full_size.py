@@ -185,6 +185,11 @@ def test_pipelined_host_batch_equals_plain(kb):
         finally:
             os.environ.pop("KMER_B200_HOST_PACK", None)
             os.environ.pop("KMER_B200_NO_LENS16", None)
+        # the same long query through the default choice: the streaming pipeline refuses the batch part-way (its lengths
+        # travel as 16 bits), the per-query packer refuses it too (> 16 words), the raw-chunk pipeline answers
+        default_long = ix.search_batch(q_long, off_long, mode=kb.MODE_CORRECT).as_tuple()
+        assert ix.last_search_host_path()["pipeline"] == "raw chunks"
+        pinned_long = ix.search_batch(torch.from_numpy(q_long).pin_memory().numpy(), off_long, mode=kb.MODE_CORRECT).as_tuple()
         os.environ["KMER_B200_NO_PIPELINE"] = "1"
         try:
             plain = ix.search_batch(q, off).as_tuple()
@@ -201,6 +206,8 @@ def test_pipelined_host_batch_equals_plain(kb):
     assert_results_equal(piped_off, plain, label="pipelined (offsets as they are) vs plain")
     assert plain_long[0][-1] - plain_long[0][-2] == 1          # the long query occurs once, at position 1000
     assert_results_equal(piped_long, plain_long, label="pipelined with a 70 000-symbol query vs plain")
+    assert_results_equal(default_long, plain_long, label="default pipeline choice with a 70 000-symbol query vs plain")
+    assert_results_equal(pinned_long, plain_long, label="default pipeline choice, pinned, with a 70 000-symbol query vs plain")
     assert_results_equal(packed, plain, label="stream-packed pipeline (pageable input) vs plain")
     assert_results_equal(packed_per_query, plain, label="per-query host-packed pipeline vs plain")
     assert_results_equal(mixed_auto, plain, label=f"stream-packed + raw chunks ({path_auto}) vs plain")
