@@ -23,6 +23,17 @@ def test_header_compiles_and_links(tmp_path):
     _compile(tmp_path)
 
 
+def test_header_bench_tool_compiles(tmp_path):
+    """profiles/tools/header_bench.cpp (the drop-in header on a batch held as std::vector<std::vector<dna4>>) stays in
+    step with the header: it must compile and link against the library."""
+    from kmer_index_b200 import build
+    build.build()
+    libdir = os.path.join(ROOT, "kmer_index_b200")
+    subprocess.run(["g++", "-std=c++20", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "profiles", "tools", "header_bench.cpp"), "-o", str(tmp_path / "header_bench"),
+                    "-L", libdir, "-lkmer_b200", f"-Wl,-rpath,{libdir}", "-pthread"], check=True)
+
+
 @pytest.mark.gpu
 def test_header_runs(tmp_path):
     exe = _compile(tmp_path)
