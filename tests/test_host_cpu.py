@@ -127,3 +127,32 @@ def test_host_stream_pack_matches_the_bit_layout(kb, sigma, bits):
             with pytest.raises(kb.KmerB200Error) as e:
                 kb.host_pack_stream(bad, sigma)
             assert e.value.code == -4
+
+
+def test_host_pool_serves_several_callers_at_once(kb):
+    """The library's host thread pool is shared by every caller in the process (the devices of a multi-device handle search
+    their slices of a batch at the same time, each with its own producer thread): concurrent kmer_b200_host_pack_stream
+    calls must neither deadlock nor mix their batches up."""
+    import threading
+    rng = np.random.default_rng(11)
+    inputs = [rng.integers(0, 4, 3_000_017 + 1000 * t, dtype=np.uint8) for t in range(6)]
+    want = [_pack_stream_reference(x, 2) for x in inputs]
+    errors = []
+
+    def worker(t):
+        try:
+            for _ in range(8):
+                got = kb.host_pack_stream(inputs[t], 4)
+                if not np.array_equal(got, want[t]):
+                    errors.append(f"caller {t}: wrong words")
+                    return
+        except Exception as e:   # noqa: BLE001
+            errors.append(f"caller {t}: {e!r}")
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(len(inputs))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=120)
+    assert not any(th.is_alive() for th in threads), "a caller is stuck in the pool"
+    assert not errors, errors
