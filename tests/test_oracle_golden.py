@@ -96,3 +96,44 @@ def test_restricted_oracle_equals_full_on_random_text(oracle_mod):
     assert want[1].size > 1000
     assert_results_equal(got, want, label="restricted vs full")
     assert oracle_mod.Oracle.restricted_misses() == 0
+
+
+REFERENCE_SHAPES = [(4, [10]), (4, [12]), (4, [5, 7, 9, 11, 13]), (15, [8]), (27, [5]), (4, [16]), (4, [3]), (4, [5]), (4, [6]),
+                    (4, [14]), (4, [9, 10]), (4, [10, 11, 12]), (15, [5]), (15, [10]), (15, [5, 6, 7]), (15, [10, 11, 12]),
+                    (5, [4]), (27, [3]), (27, [9, 10]), (27, [12]), (5, [18]), (4, [20]), (15, [16])]
+
+
+def _sweep_texts(sigma, seed):
+    from kmer_index_b200 import synth
+    yield "low entropy", synth.low_entropy_text(seed, sigma=sigma)
+    yield "random", synth.random_text(20000, sigma, seed)
+    yield "random over two ranks", synth.random_text(9000, min(sigma, 2), seed + 1)
+    rng = np.random.default_rng(seed)
+    p = int(rng.integers(1, 9))
+    t = np.tile(rng.integers(0, sigma, p, dtype=np.uint8), 5000 // p + 1)[:5000]
+    t[rng.integers(0, 5000, 20)] = rng.integers(0, sigma, 20, dtype=np.uint8)
+    yield f"period {p} with 20 point changes", t
+
+
+@pytest.mark.parametrize("sigma,ks", REFERENCE_SHAPES)
+def test_oracle_matches_live_reference_sweep(oracle_mod, sigma, ks):
+    """Every shape the compiled reference was instantiated for (oracle/ref_driver.cpp), four kinds of text (long buckets,
+    periodic stretches: every multi-part plan returns non-empty results), queries of 1 .. 6 k + 7 symbols. Queries on
+    which the reference dereferences an end iterator (kmer_index.hpp:317, :546; the oracle flags them) are skipped in the
+    exact comparison -- there the reference's answer depends on stale heap bytes -- but must still agree with the
+    oracle's defined value almost always."""
+    if not oracle_mod.have_reference():
+        pytest.skip("oracle/_ref not built on this box (needs /root/reference)")
+    from kmer_index_b200 import synth
+    flagged = agree = 0
+    for kind, text in _sweep_texts(sigma, 100 + ks[0]):
+        q, off = synth.stress_queries(text, 300, 1, min(6 * max(ks) + 7, 130), sigma, 7000 + ks[0], low_sigma=2)
+        with oracle_mod.Oracle(text, sigma, ks) as o, oracle_mod.Reference(text, sigma, ks) as r:
+            got, want = o.search(q, off), r.search(q, off)
+            ub = np.asarray(o.last_ub).astype(bool)
+            assert_results_equal(got, want, skip=o.last_ub, label=f"sigma={sigma} ks={ks} {kind}")
+            for i in np.nonzero(ub)[0]:
+                flagged += 1
+                agree += bool(got[2][i] == want[2][i] and np.array_equal(got[1][int(got[0][i]):int(got[0][i + 1])],
+                                                                         want[1][int(want[0][i]):int(want[0][i + 1])]))
+    assert agree >= 0.95 * flagged, (agree, flagged)
