@@ -21,6 +21,9 @@
 //   * n_threads is accepted and ignored; extend_query_size_range() is rejected above 10000.
 //   * texts and queries held in contiguous storage of 1-byte alphabet objects (std::vector<kmer::dna4>, seqan3
 //     alphabets) are handed to the library as they are -- the object's byte IS its rank -- without a per-symbol copy.
+//   * search_batch() returns views of the library's result buffers (kmer_batch_result keeps them alive; .to_vector() on
+//     a view copies it) and collects the queries' pointers on all host cores: 10^8 queries in a
+//     std::vector<std::vector<dna4>> take 0.47 s, 63 ms of it inside the library (profiles/r02/header_bench.txt).
 //   * an index can span several GPUs: kmer_index(text, devices) builds it from key-range parts on all of them and
 //     search_batch() stripes the batch over them (kmer_b200_config.device_ids).
 //   * the alphabet requirement is `a.to_rank()` plus kmer::alphabet_size<A>; seqan3 alphabets satisfy it when
